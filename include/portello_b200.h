@@ -1,0 +1,275 @@
+/*
+ * portello_b200.h — C-ABI of the B200-native read-mapping transfer ("liftover") path.
+ *
+ * The reference (PacificBiosciences/portello, Rust) has no FFI/plugin seam; the path sits behind ordinary Rust
+ * calls.  This header is the seam a maintainer would bind from Rust (`extern "C"` in a `portello-b200-sys` crate,
+ * see INTEGRATION.md): plain pointers and sizes, no C++/torch types, integer status codes, no unwinding.
+ *
+ * Every entry point cites the reference interface it replaces (paths relative to the reference repo root).
+ *
+ * The same ABI is exported twice:
+ *   - libportello_b200.so : `ptl_*`        — the product, hand-written sm_100a CUDA kernels, NO CPU fallback
+ *   - oracle/_build/libptl_oracle.so : `ptl_oracle_*` — CPU restatement of the reference (TEST INFRASTRUCTURE ONLY)
+ * so one harness drives both through identical structs.
+ *
+ * Conventions
+ *   - CIGAR ops are BAM-encoded u32: (len << 4) | op, op codes M=0 I=1 D=2 N=3 S=4 H=5 P=6 '='=7 X=8
+ *     (= rust_htslib::bam::record::Cigar variants Match/Ins/Del/RefSkip/SoftClip/HardClip/Pad/Equal/Diff).
+ *   - read bases are BAM-native 4-bit packed (high nibble first), decode table "=ACMGRSVTWYHKDBN"
+ *     (what `Record::seq().as_bytes()` yields, src/read_alignment_scanner.rs:127,170,238).
+ *   - reference / rev_contig bases are ASCII bytes exactly as the reference holds them
+ *     (upper-cased FASTA, lib/rust-vc-utils/src/genome_ref.rs:53; rev_contig_seq,
+ *     src/contig_alignment_scanner/mod.rs:113-125).
+ *   - positions are 0-based; CSR arrays have n+1 entries.
+ *   - all input pointers are borrowed for the duration of the call only, unless stated otherwise.
+ */
+#ifndef PORTELLO_B200_H
+#define PORTELLO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---------------------------------------------------------------- status codes */
+enum {
+    PTL_OK = 0,
+    PTL_ERR_INVALID_ARG = 1,
+    PTL_ERR_CUDA = 2,          /* CUDA runtime failure (message in ptl_last_error) */
+    PTL_ERR_NO_DEVICE = 3,     /* no usable sm_100 device: the product path has no CPU fallback */
+    PTL_ERR_STATE = 4,         /* call sequence error (e.g. wait without submit) */
+    PTL_ERR_LIFT_PANIC = 5,    /* >=1 pair hit a condition on which the reference panics (see rec status / n_errors) */
+    PTL_ERR_INPUT = 6          /* malformed input on which the reference panics during table preparation */
+};
+
+/* per-pair / per-record status (ptl_result.rec_status, stage results) */
+enum {
+    PTL_REC_LIFTED = 1,        /* Some(record) from get_liftover_alignment_for_read_and_contig_segment */
+    PTL_REC_UNMAPPED = 0,      /* unmapped fallback copy, finish_remapped_alignment_set :317-335 */
+    PTL_PAIR_NONE = 0,         /* liftover returned None (stage API) */
+    PTL_PAIR_ERR_LENGTH = -1,  /* lifted CIGAR read length != seq_len  (panic, src/read_alignment_scanner.rs:204-229) */
+    PTL_PAIR_ERR_BOUNDS = -2,  /* sequence index out of bounds (Rust slice-index panic in a5/a9 base compares) */
+    PTL_PAIR_ERR_CAPACITY = -3 /* internal op-slot bound exceeded (library bug guard; never expected) */
+};
+
+/* stage mask for ptl_lift_submit_ex (testing individual kernels against the reference's unit vectors) */
+enum {
+    PTL_STAGE_LEFT_SHIFT = 1,  /* a5: left_shift_indels on reverse-strand contig segments */
+    PTL_STAGE_LIFTOVER = 2,    /* a6: liftover_read_alignment */
+    PTL_STAGE_SIMPLIFY = 4,    /* a9: simplify_alignment_indels */
+    PTL_STAGE_ALL = 7
+};
+
+typedef struct ptl_ctx ptl_ctx;
+
+/* ---------------------------------------------------------------- inputs */
+
+/* Contig->reference mapping segments AFTER trim/join, i.e. the value returned by `scan_contig_bam`
+ * (src/contig_alignment_scanner/mod.rs:452-458): per contig an ordered (sequencing-order) list of
+ * `ContigMappingSegmentInfo` (mod.rs:25-32) + optional `rev_contig_seq` (mod.rs:38-47).
+ * Contig ids index the read->assembly BAM header (AllContigMappingInfo, mod.rs:72-76). */
+typedef struct ptl_contig_segments {
+    uint32_t n_contigs;
+    const uint64_t* contig_len;            /* [n_contigs] length from the read->asm header (read_alignment_scanner.rs:164) */
+    const uint32_t* contig_seg_begin;      /* [n_contigs+1] CSR into the segment arrays */
+    const uint8_t* const* rev_contig_seq;  /* [n_contigs] ASCII, contig_len bytes each, NULL where the reference holds None */
+    uint32_t n_segments;
+    const uint32_t* seg_seq_order_start;   /* [n_segments] SeqOrderSplitReadSegment.seq_order_read_start (split_read.rs:15-32) */
+    const uint32_t* seg_seq_order_end;     /* [n_segments] .seq_order_read_end */
+    const int32_t* seg_chrom_index;        /* [n_segments] .chrom_index (reference chromosome) */
+    const int64_t* seg_pos;                /* [n_segments] .pos */
+    const uint8_t* seg_is_fwd;             /* [n_segments] .is_fwd_strand */
+    const uint8_t* seg_mapq;               /* [n_segments] .mapq */
+    const uint64_t* seg_cigar_begin;       /* [n_segments+1] CSR into cigar */
+    const uint32_t* cigar;                 /* contig->ref CIGAR ops */
+} ptl_contig_segments;
+
+/* One batch of primary read->contig records with their split segments already parsed
+ * (get_seq_order_read_split_segments, lib/rust-vc-utils/src/bam_utils/split_read.rs:56-155; the packer
+ * ptl_pack_* below does that parsing).  Mirrors the per-read loop body src/read_alignment_scanner.rs:419-472. */
+typedef struct ptl_batch {
+    uint32_t n_reads;
+    const uint16_t* read_flag;        /* [n_reads] BAM flag of the primary record */
+    const uint8_t* read_mapq;         /* [n_reads] MAPQ of the primary record (-> ZM:C, :251,267-269) */
+    const uint16_t* read_bin;         /* [n_reads] BAM bin of the primary record (kept by the unmapped fallback, :322-334) */
+    const uint32_t* read_seq_len;     /* [n_reads] record.seq_len() */
+    const uint64_t* read_seq_off;     /* [n_reads] byte offset of the read's packed bases in seq4 */
+    const uint32_t* read_seg_begin;   /* [n_reads+1] CSR into the read-segment arrays (sequencing order, split_read.rs:140) */
+    uint32_t n_read_segments;
+    const uint32_t* rseg_contig;      /* [n_read_segments] .chrom_index (assembly contig id; may differ from the primary's) */
+    const int64_t* rseg_pos;          /* [n_read_segments] .pos on the contig */
+    const uint8_t* rseg_is_fwd;       /* [n_read_segments] .is_fwd_strand */
+    const uint64_t* rseg_cigar_begin; /* [n_read_segments] first op of the segment CIGAR in `cigar` */
+    const uint32_t* rseg_cigar_len;   /* [n_read_segments] number of ops */
+    const uint32_t* cigar;            /* CIGAR pool */
+    uint64_t n_cigar;                 /* ops in the pool */
+    const uint8_t* seq4;              /* packed bases pool; for ptl_lift_submit pinned host memory gives async copies */
+    uint64_t seq4_bytes;
+} ptl_batch;
+
+/* ---------------------------------------------------------------- outputs */
+
+/* Result of one batch, in submission order.  Records of a read are contiguous and ordered
+ * (read-segment sequencing order) x (contig-segment index) exactly as src/read_alignment_scanner.rs:430-471 pushes
+ * them; a read with no lifted pair yields one PTL_REC_UNMAPPED record (:317-335).
+ * Buffers are owned by the ctx slot and stay valid until the next submit on that slot. */
+typedef struct ptl_result {
+    uint32_t n_reads;
+    const uint32_t* read_rec_begin;       /* [n_reads+1] CSR into the record arrays */
+    uint32_t n_records;
+    const int8_t* rec_status;             /* PTL_REC_LIFTED / PTL_REC_UNMAPPED */
+    const uint32_t* rec_read_segment;     /* batch-global read-segment index (-> contig name for PS:Z, :255-265) */
+    const uint32_t* rec_contig_segment;   /* contig-segment index within its contig (the PS "split" index, :260) */
+    const int32_t* rec_tid;               /* reference chromosome index, -1 if unmapped */
+    const int64_t* rec_pos;               /* 0-based, -1 if unmapped */
+    const uint8_t* rec_mapq;              /* contig segment MAPQ (:250-252); 255 if unmapped (:326) */
+    const uint16_t* rec_flag;             /* final BAM flag incl. reverse flip, supplementary, unmapped */
+    const uint16_t* rec_bin;              /* bam_reg2bin(pos,end) (:278-279); original bin if unmapped */
+    const uint8_t* rec_need_flip;         /* 1: host must revcomp seq + reverse qual (:274-276, :330-332) */
+    const uint64_t* rec_cigar_begin;      /* [n_records+1] CSR into cigar */
+    const uint32_t* cigar;                /* output CIGAR pool, dense, record order */
+    uint64_t n_cigar;
+    /* counters (work done; used for the roofline arithmetic) */
+    uint64_t n_pairs;                     /* attempted (read segment x contig segment) pairs = a4 calls */
+    uint64_t n_lifted;                    /* pairs that produced a record */
+    uint64_t n_errors;                    /* pairs with a negative status (reference would have panicked) */
+    int64_t first_error_read;             /* batch read index of the first such pair, -1 if none */
+    int32_t first_error_status;
+} ptl_result;
+
+/* ---------------------------------------------------------------- lifecycle */
+
+/* One ctx per GPU (replaces the per-thread reader set of src/worker_thread_data.rs:8-30 as the unit of concurrency).
+ * `n_slots` >= 1 double/triple-buffered batch slots, each with its own CUDA stream. */
+int ptl_create(int device, int n_slots, ptl_ctx** out);
+void ptl_destroy(ptl_ctx* ctx);
+/* Message for the last non-OK status on this ctx (owned by ctx; "" if none). Thread-compatible, not thread-safe. */
+const char* ptl_last_error(const ptl_ctx* ctx);
+/* Library/ABI version string, e.g. "portello_b200 0.1 (sm_100a)". */
+const char* ptl_version(void);
+
+/* Reference genome bytes = `reference: &[Vec<u8>]` built by get_chrom_array (src/main.rs:24-62). Copied to device. */
+int ptl_set_reference(ptl_ctx* ctx, uint32_t n_chrom, const uint64_t* chrom_len, const uint8_t* const* chrom_seq);
+
+/* Install `AllContigMappingInfo` (post trim/join) and build the device segment tables, the flat form of
+ * ReadToRefTreeMap (lib/rust-vc-utils/src/bam_utils/read_to_ref_map.rs:59-137), with a CUDA kernel. */
+int ptl_set_contig_segments(ptl_ctx* ctx, const ptl_contig_segments* segs);
+
+/* Same, but from RAW (pre-trim) segments as assembled by add_primary_read + supplementary fill-in
+ * (mod.rs:91-183,360-439): runs clip_repeated_contig_matches (contig_repeated_match_trimmer.rs:214-303) and
+ * join_colinear_contig_segments (contig_colinear_segment_joiner.rs:124-186) in-library (host C++), then installs.
+ * The processed segments can be read back with ptl_get_contig_segments. */
+int ptl_set_raw_contig_segments(ptl_ctx* ctx, const ptl_contig_segments* raw);
+/* The contig->reference BAM records as scan_contig_bam's record loop sees them (mod.rs:186-240), BAM decode excluded. */
+typedef struct ptl_contig_records {
+    uint32_t n_records;
+    const uint32_t* contig_id;         /* [n_records] assembly contig index of the record's qname (mod.rs:219-220) */
+    const uint16_t* flag;              /* BAM flag (unmapped/secondary skipped :208, supplementary :222, reverse) */
+    const int32_t* tid;                /* reference chromosome index */
+    const int64_t* pos;
+    const uint8_t* mapq;
+    const uint64_t* cigar_begin;       /* [n_records+1] */
+    const uint32_t* cigar;
+    const char* const* sa_tag;         /* [n_records] SA:Z value or NULL */
+    const uint8_t* const* seq;         /* [n_records] ASCII decode of the stored bases (needed on primary records), else NULL */
+    uint32_t n_contigs;
+    const uint64_t* contig_len;        /* [n_contigs] */
+    const char* const* contig_names;   /* [n_contigs] (error messages only) */
+    uint32_t n_ref_chrom;
+    const char* const* ref_chrom_names; /* [n_ref_chrom] resolves SA rname -> chrom index */
+} ptl_contig_records;
+/* = scan_contig_bam minus BAM I/O (src/contig_alignment_scanner/mod.rs:290-459): add_primary_read (:91-133),
+ * supplementary exact-CIGAR fill-in keyed by SplitReadKey (:49-56,135-183,360-439), rev_contig_seq (:113-125),
+ * then trim + join, then install (host C++ for the O(#contig records) part, CUDA for the tables). */
+int ptl_set_contig_records(ptl_ctx* ctx, const ptl_contig_records* recs);
+/* Borrow the installed (post trim/join) segments; pointers owned by ctx, valid until the next set call. */
+int ptl_get_contig_segments(const ptl_ctx* ctx, ptl_contig_segments* out);
+/* Copy the device-built table of one global segment index back to the host (testing a7):
+ * keys[i] = contig read_pos starting a block, vals[i] = ref pos or -1 for None. Returns count via *n; pass cap. */
+int ptl_get_segment_table(ptl_ctx* ctx, uint32_t segment, uint32_t cap, uint32_t* keys, int32_t* vals, uint32_t* n);
+
+/* ---------------------------------------------------------------- the hot path */
+
+/* Lift one batch: = the loop body of scan_chromosome_segment (src/read_alignment_scanner.rs:419-487) for n_reads
+ * records: pair enumeration (:80-103), per-pair get_liftover_alignment_for_read_and_contig_segment (:136-288:
+ * left_shift_indels, liftover_read_alignment, length check, simplify_alignment_indels, field updates) and
+ * finish_remapped_alignment_set (:310-366: primary selection / unmapped fallback; SA text is ptl_format_sa_tags).
+ * Asynchronous on the slot's stream (H2D copies, kernels, D2H); returns after enqueue.
+ * Distinct slots may be driven from distinct host threads. */
+int ptl_lift_submit(ptl_ctx* ctx, int slot, const ptl_batch* batch);
+/* As above with a stage mask (PTL_STAGE_*), used to pin single kernels to the reference's unit vectors.
+ * Without PTL_STAGE_LIFTOVER the pair's (pos,CIGAR) after the enabled stage is returned in contig coordinates
+ * with tid = -2. */
+int ptl_lift_submit_ex(ptl_ctx* ctx, int slot, const ptl_batch* batch, uint32_t stage_mask);
+/* Block until the slot's batch is done and expose its result. Returns PTL_ERR_LIFT_PANIC if n_errors > 0
+ * (the reference aborts the whole run in that case; here the remaining records are still valid). */
+int ptl_lift_wait(ptl_ctx* ctx, int slot, ptl_result* out);
+
+/* Split phases of submit/wait for device-resident measurement (bench.py `value`): */
+int ptl_lift_upload(ptl_ctx* ctx, int slot, const ptl_batch* batch);   /* H2D only (async) */
+int ptl_lift_run(ptl_ctx* ctx, int slot, uint32_t stage_mask);         /* kernels only, on the resident batch (async) */
+int ptl_lift_download(ptl_ctx* ctx, int slot, ptl_result* out);        /* D2H + sync */
+/* cudaStream_t of a slot (as void*), so callers can bracket work with their own CUDA events. */
+void* ptl_slot_stream(ptl_ctx* ctx, int slot);
+/* Per-kernel device time of the LAST ptl_lift_run on the slot, CUDA events on the slot stream.
+ * names[i] are static strings; returns the number of stages filled (<= cap). Syncs the slot. */
+int ptl_slot_kernel_times(ptl_ctx* ctx, int slot, int cap, const char** names, float* ms);
+/* Number of kernel launches issued by this ctx so far (bench.py `gpu_launches`). */
+uint64_t ptl_launch_count(const ptl_ctx* ctx);
+/* 0: copy seq4 to the device (default). 1: seq4 of subsequent batches must be pinned+mapped host memory
+ * (ptl_host_alloc); kernels read the few bases they need over PCIe instead of uploading every base. */
+int ptl_set_seq_zero_copy(ptl_ctx* ctx, int enable);
+
+/* Pinned (page-locked, device-mapped) host memory for batches: replaces nothing in the reference, it is the
+ * "pinned structure-of-arrays batches" of the north star. */
+void* ptl_host_alloc(size_t bytes);
+void ptl_host_free(void* p);
+
+/* ---------------------------------------------------------------- host-side helpers (C++, no GPU needed) */
+
+/* Parse an SA:Z aux value into split segments = parse_sa_aux_val (lib/rust-vc-utils/src/bam_utils/aux/sa_tag_parser.rs:25-59)
+ * + the segment construction / stable ordering of get_seq_order_read_split_segments (split_read.rs:56-155) for one
+ * primary record.  `contig_names` resolves rname -> index (ChromList.label_to_index).
+ * Outputs (caller-allocated, capacity `cap_segments` / `cap_cigar`): segments in sequencing order incl. the primary.
+ * Returns PTL_OK, PTL_ERR_INPUT where the reference panics (message via ptl_pack_last_error), or
+ * PTL_ERR_INVALID_ARG if capacities are too small (*n_segments / *n_cigar then hold the needed sizes). */
+typedef struct ptl_split_segments {
+    uint32_t* seq_order_start;
+    uint32_t* seq_order_end;
+    uint32_t* contig;
+    int64_t* pos;
+    uint8_t* is_fwd;
+    uint8_t* mapq;
+    uint8_t* from_primary;
+    uint32_t* cigar_begin;  /* [cap_segments+1] */
+    uint32_t* cigar;
+} ptl_split_segments;
+int ptl_pack_split_segments(uint32_t n_contig_names, const char* const* contig_names,
+                            int32_t tid, int64_t pos, uint16_t flag, uint8_t mapq,
+                            const uint32_t* cigar, uint32_t n_cigar, const char* sa_tag /* NULL if none */,
+                            uint32_t cap_segments, uint32_t cap_cigar,
+                            ptl_split_segments* out, uint32_t* n_segments, uint32_t* n_cigar_out);
+const char* ptl_pack_last_error(void);
+
+/* SA:Z text for every record of a result = get_sa_tag_segment + the concatenation loop
+ * (src/read_alignment_scanner.rs:292-301,349-363).  Writes one NUL-terminated string per record into `buf`
+ * (record i at sa_begin[i]; empty string where the reference pushes no SA tag). Returns needed bytes in *need. */
+int ptl_format_sa_tags(const ptl_result* res, uint32_t n_chrom, const char* const* chrom_names,
+                       char* buf, uint64_t cap, uint64_t* sa_begin /* [n_records+1] */, uint64_t* need);
+
+/* Work-unit sharding (multi-GPU): the reference's units are (contig x <=20 Mb window), get_region_segments
+ * (lib/rust-vc-utils/src/util.rs:50-67) as used at src/read_alignment_scanner.rs:508,574-576. */
+uint32_t ptl_region_segment_count(uint64_t size, uint64_t segment_size);
+void ptl_region_segments(uint64_t size, uint64_t segment_size, uint64_t* begin, uint64_t* end);
+/* Greedy LPT bin-packing of units (weights = read counts) onto n_ranks; owner[i] = rank of unit i. Deterministic. */
+void ptl_shard_units(uint32_t n_units, const uint64_t* weight, uint32_t n_ranks, uint32_t* owner);
+
+/* BAM bin, = bam_reg2bin (lib/rust-vc-utils/src/bam_utils/util.rs:10-35). */
+uint16_t ptl_reg2bin(int64_t begin, int64_t end);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PORTELLO_B200_H */

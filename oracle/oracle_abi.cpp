@@ -1,0 +1,661 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY.
+//
+// C-ABI around the CPU restatement of the reference (cigar.hpp, liftover.hpp, contig_prep.hpp, read_scan.hpp).
+// Exports the SAME structs as include/portello_b200.h under the `ptl_oracle_` prefix so one harness drives both the
+// CUDA product and this checker, plus function-level entry points (`ptl_oracle_fn_*`) that mirror the reference's
+// pure functions one-to-one so the reference's own unit-test vectors (tests/golden/) can be replayed.
+//
+// Parity status: PINNED by the reference's in-file unit tests, transcribed into tests/golden/*.json.
+// The reference itself (Rust) cannot be built in this image (no cargo/rustc), so there is no oracle/_ref.
+//
+// Only tests/, __graft_entry__.smoke() and bench.py (cpu_baseline leg / --impl reference) may load this library.
+#include <atomic>
+#include <cstring>
+#include <memory>
+#include <thread>
+
+#include "../include/portello_b200.h"
+#include "read_scan.hpp"
+
+using namespace orc;
+
+namespace {
+
+struct Slot {
+    bool submitted = false;
+    std::vector<uint32_t> read_rec_begin;
+    std::vector<int8_t> rec_status;
+    std::vector<uint32_t> rec_read_segment, rec_contig_segment;
+    std::vector<int32_t> rec_tid;
+    std::vector<int64_t> rec_pos;
+    std::vector<uint8_t> rec_mapq, rec_need_flip;
+    std::vector<uint16_t> rec_flag, rec_bin;
+    std::vector<uint64_t> rec_cigar_begin;
+    std::vector<uint32_t> cigar;
+    ptl_result res{};
+    PairStats stats;
+};
+
+// Flat copy of the installed segments, lent out by ptl_oracle_get_contig_segments.
+struct FlatSegments {
+    std::vector<uint64_t> contig_len;
+    std::vector<uint32_t> contig_seg_begin;
+    std::vector<const uint8_t*> rev_ptr;
+    std::vector<uint32_t> so_start, so_end;
+    std::vector<int32_t> chrom;
+    std::vector<int64_t> pos;
+    std::vector<uint8_t> is_fwd, mapq;
+    std::vector<uint64_t> cigar_begin;
+    std::vector<uint32_t> cigar;
+};
+
+}  // namespace
+
+struct ptl_ctx {
+    std::string err;
+    int n_slots = 1;
+    int n_threads = 1;
+    bool faithful_decode = true;
+    std::vector<std::vector<uint8_t>> reference;
+    std::vector<uint64_t> contig_len;
+    AllContigMappingInfo contigs;
+    FlatSegments flat;
+    std::vector<Slot> slots;
+};
+
+namespace {
+
+int fail(ptl_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    return code;
+}
+
+CigarVec decode_cigar(const uint32_t* ops, size_t n) {
+    CigarVec v(n);
+    for (size_t i = 0; i < n; ++i) v[i] = decode(ops[i]);
+    return v;
+}
+
+void flatten(ptl_ctx* ctx) {
+    FlatSegments& f = ctx->flat;
+    f = FlatSegments{};
+    f.contig_len = ctx->contig_len;
+    f.contig_seg_begin.push_back(0);
+    f.cigar_begin.push_back(0);
+    for (const auto& info : ctx->contigs) {
+        f.rev_ptr.push_back(info.has_rev_contig_seq ? info.rev_contig_seq.data() : nullptr);
+        for (const auto& si : info.ordered_contig_segment_info) {
+            const auto& s = si.seq_order_segment;
+            f.so_start.push_back(uint32_t(s.seq_order_read_start));
+            f.so_end.push_back(uint32_t(s.seq_order_read_end));
+            f.chrom.push_back(int32_t(s.chrom_index));
+            f.pos.push_back(s.pos);
+            f.is_fwd.push_back(s.is_fwd_strand);
+            f.mapq.push_back(s.mapq);
+            for (const auto& c : s.cigar) f.cigar.push_back(encode(c));
+            f.cigar_begin.push_back(f.cigar.size());
+        }
+        f.contig_seg_begin.push_back(uint32_t(f.so_start.size()));
+    }
+}
+
+// Build AllContigMappingInfo from the flat struct (tables via get_read_segment_to_ref_pos_tree_map, as the reference
+// does after every trim/join, contig_repeated_match_trimmer.rs:132-133, contig_colinear_segment_joiner.rs:117).
+void load_segments(ptl_ctx* ctx, const ptl_contig_segments* s) {
+    ctx->contigs.clear();
+    ctx->contig_len.assign(s->contig_len, s->contig_len + s->n_contigs);
+    for (uint32_t ci = 0; ci < s->n_contigs; ++ci) {
+        ContigMappingInfo info;
+        info.qname = "contig" + std::to_string(ci);
+        if (s->rev_contig_seq && s->rev_contig_seq[ci]) {
+            info.has_rev_contig_seq = true;
+            info.rev_contig_seq.assign(s->rev_contig_seq[ci], s->rev_contig_seq[ci] + s->contig_len[ci]);
+        }
+        for (uint32_t k = s->contig_seg_begin[ci]; k < s->contig_seg_begin[ci + 1]; ++k) {
+            ContigMappingSegmentInfo si;
+            auto& g = si.seq_order_segment;
+            g.seq_order_read_start = s->seg_seq_order_start[k];
+            g.seq_order_read_end = s->seg_seq_order_end[k];
+            g.chrom_index = size_t(s->seg_chrom_index[k]);
+            g.pos = s->seg_pos[k];
+            g.is_fwd_strand = s->seg_is_fwd[k] != 0;
+            g.mapq = s->seg_mapq[k];
+            g.cigar = decode_cigar(s->cigar + s->seg_cigar_begin[k], s->seg_cigar_begin[k + 1] - s->seg_cigar_begin[k]);
+            si.contig_to_ref_map = get_read_segment_to_ref_pos_tree_map(g.pos, g.cigar, false);
+            info.ordered_contig_segment_info.push_back(std::move(si));
+        }
+        ctx->contigs.push_back(std::move(info));
+    }
+}
+
+struct ChunkOut {
+    std::vector<uint32_t> n_rec_per_read;
+    std::vector<LiftedRecord> recs;
+    std::vector<uint32_t> rec_rseg;  // batch-global read-segment index
+    PairStats stats;
+    int64_t first_error_read = -1;
+    int first_error_status = 0;
+    uint64_t n_errors = 0;
+};
+
+void lift_chunk(const ptl_ctx* ctx, const ptl_batch* b, uint32_t r0, uint32_t r1, uint32_t stage_mask, ChunkOut& out) {
+    ScanOptions opt;
+    opt.faithful_decode = ctx->faithful_decode;
+    opt.stage_mask = stage_mask;
+    std::vector<SeqOrderSplitReadSegment> splits;
+    for (uint32_t r = r0; r < r1; ++r) {
+        ReadRecord rec;
+        rec.flag = b->read_flag[r];
+        rec.mapq = b->read_mapq[r];
+        rec.bin = b->read_bin[r];
+        rec.seq_len = b->read_seq_len[r];
+        rec.seq4 = b->seq4 + b->read_seq_off[r];
+        splits.clear();
+        const uint32_t s0 = b->read_seg_begin[r], s1 = b->read_seg_begin[r + 1];
+        for (uint32_t s = s0; s < s1; ++s) {
+            SeqOrderSplitReadSegment g;
+            g.chrom_index = b->rseg_contig[s];
+            g.pos = b->rseg_pos[s];
+            g.is_fwd_strand = b->rseg_is_fwd[s] != 0;
+            g.cigar = decode_cigar(b->cigar + b->rseg_cigar_begin[s], b->rseg_cigar_len[s]);
+            splits.push_back(std::move(g));
+        }
+        std::vector<LiftedRecord> recs;
+        try {
+            recs = lift_read(ctx->reference, ctx->contig_len, ctx->contigs, rec, splits, opt, out.stats);
+        } catch (const Panic& p) {
+            // The reference aborts the run here. Record the error and emit the unmapped fallback so shapes stay defined.
+            out.n_errors++;
+            if (out.first_error_read < 0) {
+                out.first_error_read = r;
+                out.first_error_status = p.code;
+            }
+            recs = finish_remapped_alignment_set(rec, {});
+        }
+        out.n_rec_per_read.push_back(uint32_t(recs.size()));
+        for (auto& x : recs) {
+            out.rec_rseg.push_back(x.status == 0 ? s0 : s0 + x.read_segment);
+            out.recs.push_back(std::move(x));
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int ptl_oracle_create(int /*device*/, int n_slots, ptl_ctx** out) {
+    if (!out || n_slots < 1) return PTL_ERR_INVALID_ARG;
+    auto* ctx = new ptl_ctx();
+    ctx->n_slots = n_slots;
+    ctx->slots.resize(size_t(n_slots));
+    *out = ctx;
+    return PTL_OK;
+}
+void ptl_oracle_destroy(ptl_ctx* ctx) { delete ctx; }
+const char* ptl_oracle_last_error(const ptl_ctx* ctx) { return ctx ? ctx->err.c_str() : ""; }
+const char* ptl_oracle_version(void) { return "portello_b200 oracle 0.1 (CPU restatement of portello v0.6.1)"; }
+
+// CPU-baseline knobs (no counterpart in the product ABI).
+int ptl_oracle_set_threads(ptl_ctx* ctx, int n) {
+    if (!ctx || n < 1) return PTL_ERR_INVALID_ARG;
+    ctx->n_threads = n;
+    return PTL_OK;
+}
+int ptl_oracle_set_faithful_decode(ptl_ctx* ctx, int on) {
+    if (!ctx) return PTL_ERR_INVALID_ARG;
+    ctx->faithful_decode = on != 0;
+    return PTL_OK;
+}
+
+int ptl_oracle_set_reference(ptl_ctx* ctx, uint32_t n_chrom, const uint64_t* chrom_len, const uint8_t* const* chrom_seq) {
+    if (!ctx) return PTL_ERR_INVALID_ARG;
+    ctx->reference.clear();
+    for (uint32_t i = 0; i < n_chrom; ++i) ctx->reference.emplace_back(chrom_seq[i], chrom_seq[i] + chrom_len[i]);
+    return PTL_OK;
+}
+
+int ptl_oracle_set_contig_segments(ptl_ctx* ctx, const ptl_contig_segments* s) {
+    if (!ctx || !s) return PTL_ERR_INVALID_ARG;
+    load_segments(ctx, s);
+    flatten(ctx);
+    return PTL_OK;
+}
+
+int ptl_oracle_set_raw_contig_segments(ptl_ctx* ctx, const ptl_contig_segments* s) {
+    if (!ctx || !s) return PTL_ERR_INVALID_ARG;
+    try {
+        load_segments(ctx, s);
+        clip_repeated_contig_matches(ctx->contigs);
+        join_colinear_contig_segments(ctx->contigs);
+    } catch (const Panic& p) {
+        return fail(ctx, PTL_ERR_INPUT, p.what());
+    }
+    flatten(ctx);
+    return PTL_OK;
+}
+
+int ptl_oracle_set_contig_records(ptl_ctx* ctx, const ptl_contig_records* r) {
+    if (!ctx || !r) return PTL_ERR_INVALID_ARG;
+    try {
+        NameIndex ref_index;
+        for (uint32_t i = 0; i < r->n_ref_chrom; ++i) ref_index[r->ref_chrom_names[i]] = i;
+        std::vector<std::string> names;
+        for (uint32_t i = 0; i < r->n_contigs; ++i) names.push_back(r->contig_names ? r->contig_names[i] : "contig" + std::to_string(i));
+        std::vector<ContigRecord> recs(r->n_records);
+        for (uint32_t i = 0; i < r->n_records; ++i) {
+            auto& c = recs[i];
+            c.contig_id = r->contig_id[i];
+            c.aln.tid = r->tid[i];
+            c.aln.pos = r->pos[i];
+            c.aln.flag = r->flag[i];
+            c.aln.mapq = r->mapq[i];
+            c.aln.cigar = decode_cigar(r->cigar + r->cigar_begin[i], r->cigar_begin[i + 1] - r->cigar_begin[i]);
+            if (r->sa_tag && r->sa_tag[i]) {
+                c.aln.has_sa = true;
+                c.aln.sa = r->sa_tag[i];
+            }
+            if (r->seq && r->seq[i]) c.seq.assign(r->seq[i], r->seq[i] + r->contig_len[c.contig_id]);
+        }
+        ctx->contig_len.assign(r->contig_len, r->contig_len + r->n_contigs);
+        ctx->contigs = scan_contig_records(recs, r->n_contigs, ref_index, names);
+    } catch (const Panic& p) {
+        return fail(ctx, PTL_ERR_INPUT, p.what());
+    }
+    flatten(ctx);
+    return PTL_OK;
+}
+
+int ptl_oracle_get_contig_segments(const ptl_ctx* ctx, ptl_contig_segments* out) {
+    if (!ctx || !out) return PTL_ERR_INVALID_ARG;
+    const FlatSegments& f = ctx->flat;
+    out->n_contigs = uint32_t(f.contig_len.size());
+    out->contig_len = f.contig_len.data();
+    out->contig_seg_begin = f.contig_seg_begin.data();
+    out->rev_contig_seq = f.rev_ptr.data();
+    out->n_segments = uint32_t(f.so_start.size());
+    out->seg_seq_order_start = f.so_start.data();
+    out->seg_seq_order_end = f.so_end.data();
+    out->seg_chrom_index = f.chrom.data();
+    out->seg_pos = f.pos.data();
+    out->seg_is_fwd = f.is_fwd.data();
+    out->seg_mapq = f.mapq.data();
+    out->seg_cigar_begin = f.cigar_begin.data();
+    out->cigar = f.cigar.data();
+    return PTL_OK;
+}
+
+int ptl_oracle_get_segment_table(ptl_ctx* ctx, uint32_t segment, uint32_t cap, uint32_t* keys, int32_t* vals, uint32_t* n) {
+    if (!ctx || !n) return PTL_ERR_INVALID_ARG;
+    uint32_t k = 0;
+    for (const auto& info : ctx->contigs) {
+        for (const auto& si : info.ordered_contig_segment_info) {
+            if (k++ != segment) continue;
+            uint32_t i = 0;
+            for (const auto& kv : si.contig_to_ref_map.map) {
+                if (i < cap) {
+                    keys[i] = uint32_t(kv.first);
+                    vals[i] = kv.second ? int32_t(*kv.second) : -1;
+                }
+                ++i;
+            }
+            *n = i;
+            return i <= cap ? PTL_OK : PTL_ERR_INVALID_ARG;
+        }
+    }
+    return fail(ctx, PTL_ERR_INVALID_ARG, "segment index out of range");
+}
+
+int ptl_oracle_lift_submit_ex(ptl_ctx* ctx, int slot, const ptl_batch* b, uint32_t stage_mask) {
+    if (!ctx || !b || slot < 0 || slot >= ctx->n_slots) return PTL_ERR_INVALID_ARG;
+    Slot& sl = ctx->slots[size_t(slot)];
+    const uint32_t chunk = 512;
+    const uint32_t n_chunks = (b->n_reads + chunk - 1) / chunk;
+    std::vector<ChunkOut> outs(n_chunks);
+    std::atomic<uint32_t> next{0};
+    auto worker = [&]() {
+        for (;;) {
+            const uint32_t c = next.fetch_add(1);
+            if (c >= n_chunks) break;
+            lift_chunk(ctx, b, c * chunk, std::min(b->n_reads, (c + 1) * chunk), stage_mask, outs[c]);
+        }
+    };
+    const int nt = std::max(1, std::min<int>(ctx->n_threads, int(n_chunks)));
+    if (nt == 1) {
+        worker();
+    } else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; ++t) th.emplace_back(worker);
+        for (auto& t : th) t.join();
+    }
+    // gather in submission order
+    size_t n_rec = 0, n_ops = 0;
+    for (const auto& o : outs) {
+        n_rec += o.recs.size();
+        for (const auto& r : o.recs) n_ops += r.cigar.size();
+    }
+    sl.read_rec_begin.assign(1, 0);
+    sl.read_rec_begin.reserve(b->n_reads + 1);
+    sl.rec_status.resize(n_rec); sl.rec_read_segment.resize(n_rec); sl.rec_contig_segment.resize(n_rec);
+    sl.rec_tid.resize(n_rec); sl.rec_pos.resize(n_rec); sl.rec_mapq.resize(n_rec); sl.rec_need_flip.resize(n_rec);
+    sl.rec_flag.resize(n_rec); sl.rec_bin.resize(n_rec);
+    sl.rec_cigar_begin.assign(1, 0);
+    sl.rec_cigar_begin.reserve(n_rec + 1);
+    sl.cigar.clear();
+    sl.cigar.reserve(n_ops);
+    sl.stats = PairStats{};
+    ptl_result& res = sl.res;
+    res = ptl_result{};
+    res.first_error_read = -1;
+    size_t k = 0;
+    for (const auto& o : outs) {
+        for (uint32_t n : o.n_rec_per_read) sl.read_rec_begin.push_back(sl.read_rec_begin.back() + n);
+        for (size_t i = 0; i < o.recs.size(); ++i, ++k) {
+            const LiftedRecord& r = o.recs[i];
+            sl.rec_status[k] = r.status;
+            sl.rec_read_segment[k] = o.rec_rseg[i];
+            sl.rec_contig_segment[k] = r.status == 0 ? 0xffffffffu : r.contig_segment;
+            sl.rec_tid[k] = r.tid;
+            sl.rec_pos[k] = r.pos;
+            sl.rec_mapq[k] = r.mapq;
+            sl.rec_need_flip[k] = r.need_flip;
+            sl.rec_flag[k] = r.flag;
+            sl.rec_bin[k] = r.bin;
+            for (const auto& c : r.cigar) sl.cigar.push_back(encode(c));
+            sl.rec_cigar_begin.push_back(sl.cigar.size());
+        }
+        sl.stats.n_pairs += o.stats.n_pairs;
+        sl.stats.n_lifted += o.stats.n_lifted;
+        sl.stats.n_in_ops += o.stats.n_in_ops;
+        sl.stats.n_out_ops += o.stats.n_out_ops;
+        sl.stats.cmp.base_bytes += o.stats.cmp.base_bytes;
+        res.n_errors += o.n_errors;
+        if (res.first_error_read < 0 && o.first_error_read >= 0) {
+            res.first_error_read = o.first_error_read;
+            res.first_error_status = o.first_error_status;
+        }
+    }
+    res.n_reads = b->n_reads;
+    res.read_rec_begin = sl.read_rec_begin.data();
+    res.n_records = uint32_t(n_rec);
+    res.rec_status = sl.rec_status.data();
+    res.rec_read_segment = sl.rec_read_segment.data();
+    res.rec_contig_segment = sl.rec_contig_segment.data();
+    res.rec_tid = sl.rec_tid.data();
+    res.rec_pos = sl.rec_pos.data();
+    res.rec_mapq = sl.rec_mapq.data();
+    res.rec_flag = sl.rec_flag.data();
+    res.rec_bin = sl.rec_bin.data();
+    res.rec_need_flip = sl.rec_need_flip.data();
+    res.rec_cigar_begin = sl.rec_cigar_begin.data();
+    res.cigar = sl.cigar.data();
+    res.n_cigar = sl.cigar.size();
+    res.n_pairs = sl.stats.n_pairs;
+    res.n_lifted = sl.stats.n_lifted;
+    sl.submitted = true;
+    return PTL_OK;
+}
+int ptl_oracle_lift_submit(ptl_ctx* ctx, int slot, const ptl_batch* b) {
+    return ptl_oracle_lift_submit_ex(ctx, slot, b, PTL_STAGE_ALL);
+}
+int ptl_oracle_lift_wait(ptl_ctx* ctx, int slot, ptl_result* out) {
+    if (!ctx || !out || slot < 0 || slot >= ctx->n_slots) return PTL_ERR_INVALID_ARG;
+    Slot& sl = ctx->slots[size_t(slot)];
+    if (!sl.submitted) return fail(ctx, PTL_ERR_STATE, "wait without submit");
+    *out = sl.res;
+    if (sl.res.n_errors) return fail(ctx, PTL_ERR_LIFT_PANIC, "reference would panic on read " + std::to_string(sl.res.first_error_read));
+    return PTL_OK;
+}
+// out[0..5) = n_pairs, n_lifted, n_in_ops, n_out_ops, compared base bytes  (roofline arithmetic)
+int ptl_oracle_last_stats(ptl_ctx* ctx, int slot, uint64_t* out) {
+    if (!ctx || !out || slot < 0 || slot >= ctx->n_slots) return PTL_ERR_INVALID_ARG;
+    const PairStats& s = ctx->slots[size_t(slot)].stats;
+    out[0] = s.n_pairs; out[1] = s.n_lifted; out[2] = s.n_in_ops; out[3] = s.n_out_ops; out[4] = s.cmp.base_bytes;
+    return PTL_OK;
+}
+
+// ---------------------------------------------------------------- function-level mirrors (golden vectors)
+// All return the number of output ops (or -1 for None / -100-code on a reference panic); out arrays need `cap` entries.
+
+static int64_t emit(const CigarVec& c, uint32_t* out, uint32_t cap) {
+    for (size_t i = 0; i < c.size() && i < cap; ++i) out[i] = encode(c[i]);
+    return int64_t(c.size());
+}
+
+int64_t ptl_oracle_fn_liftover(int64_t c2r_pos, const uint32_t* c2r_cigar, uint32_t n_c2r, int has_map, int64_t pos,
+                               const uint32_t* cigar, uint32_t n, int64_t* out_pos, uint32_t* out, uint32_t cap) {
+    ReadToRefTreeMap map;
+    if (has_map) map = get_read_segment_to_ref_pos_tree_map(c2r_pos, decode_cigar(c2r_cigar, n_c2r), false);
+    auto r = liftover_read_alignment(map, pos, decode_cigar(cigar, n));
+    if (!r) return -1;
+    *out_pos = r->pos;
+    return emit(r->cigar, out, cap);
+}
+int64_t ptl_oracle_fn_simplify(int64_t pos, const uint32_t* cigar, uint32_t n, const uint8_t* ref, uint64_t ref_len,
+                               const uint8_t* read, uint64_t read_len, int64_t* out_pos, uint32_t* out, uint32_t cap) {
+    try {
+        auto r = simplify_alignment_indels(pos, decode_cigar(cigar, n), ref, ref_len, ReadSeq::from_ascii(read, read_len));
+        *out_pos = r.pos;
+        return emit(r.cigar, out, cap);
+    } catch (const Panic& p) { return -100 + p.code; }
+}
+int64_t ptl_oracle_fn_shift(int right, int64_t pos, const uint32_t* cigar, uint32_t n, const uint8_t* ref, uint64_t ref_len,
+                            const uint8_t* read, uint64_t read_len, int64_t* out_pos, uint32_t* out, uint32_t cap) {
+    try {
+        auto rs = ReadSeq::from_ascii(read, read_len);
+        auto r = right ? right_shift_indels(pos, decode_cigar(cigar, n), ref, ref_len, rs)
+                       : left_shift_indels(pos, decode_cigar(cigar, n), ref, ref_len, rs);
+        *out_pos = r.pos;
+        return emit(r.cigar, out, cap);
+    } catch (const Panic& p) { return -100 + p.code; }
+}
+int64_t ptl_oracle_fn_compress(const uint32_t* cigar, uint32_t n, uint32_t* out, uint32_t cap) {
+    return emit(compress_cigar(decode_cigar(cigar, n)), out, cap);
+}
+// in-place; returns the shift
+int64_t ptl_oracle_fn_cleanup(uint32_t* cigar, uint32_t n) {
+    CigarVec c = decode_cigar(cigar, n);
+    const size_t shift = clean_up_cigar_edge_indels(c);
+    for (uint32_t i = 0; i < n; ++i) cigar[i] = encode(c[i]);
+    return int64_t(shift);
+}
+int64_t ptl_oracle_fn_clip_read_edges(const uint32_t* cigar, uint32_t n, uint64_t left, uint64_t right, int64_t* ref_shift,
+                                      uint32_t* out, uint32_t cap) {
+    auto r = clip_alignment_read_edges(decode_cigar(cigar, n), left, right);
+    *ref_shift = r.second;
+    return emit(r.first, out, cap);
+}
+void ptl_oracle_fn_read_clip_positions(const uint32_t* cigar, uint32_t n, int ignore_hard_clip, uint64_t* out3) {
+    auto c = get_read_clip_positions(decode_cigar(cigar, n), ignore_hard_clip != 0);
+    out3[0] = c.left; out3[1] = c.right; out3[2] = c.size;
+}
+void ptl_oracle_fn_offsets(const uint32_t* cigar, uint32_t n, int ignore_hard_clip, int64_t* ref_pos, uint64_t* read_pos) {
+    // running (ref_pos, read_pos) after each op, update_ref_and_read_pos
+    int64_t rp = ref_pos[0];
+    size_t qp = size_t(read_pos[0]);
+    for (uint32_t i = 0; i < n; ++i) {
+        update_ref_and_read_pos(decode(cigar[i]), rp, qp, ignore_hard_clip != 0);
+        ref_pos[i] = rp;
+        read_pos[i] = qp;
+    }
+}
+void ptl_oracle_fn_homology(const uint8_t* ref, uint64_t ref_len, int64_t ref_s, int64_t ref_e, const uint8_t* read,
+                            uint64_t read_len, int64_t read_s, int64_t read_e, int64_t* out_range2, uint8_t* hom,
+                            uint32_t cap, uint32_t* hom_len) {
+    auto r = get_indel_breakend_homology_info(ref, ref_len, IntRange{ref_s, ref_e}, ReadSeq::from_ascii(read, read_len),
+                                              IntRange{read_s, read_e});
+    out_range2[0] = r.first.start;
+    out_range2[1] = r.first.end;
+    *hom_len = uint32_t(r.second.size());
+    for (size_t i = 0; i < r.second.size() && i < cap; ++i) hom[i] = r.second[i];
+}
+// keys/vals of the tree map; vals -1 = None.  Returns count.
+int64_t ptl_oracle_fn_tree_map(int64_t ref_pos, const uint32_t* cigar, uint32_t n, int ignore_hard_clip, uint64_t* keys,
+                               int64_t* vals, uint32_t cap) {
+    auto m = get_read_segment_to_ref_pos_tree_map(ref_pos, decode_cigar(cigar, n), ignore_hard_clip != 0);
+    uint32_t i = 0;
+    for (const auto& kv : m.map) {
+        if (i < cap) {
+            keys[i] = kv.first;
+            vals[i] = kv.second ? *kv.second : -1;
+        }
+        ++i;
+    }
+    return i;
+}
+// get_ref_pos for read_pos in [0, n_pos); INT64_MIN = None
+void ptl_oracle_fn_tree_map_ref_pos(int64_t ref_pos, const uint32_t* cigar, uint32_t n, int ignore_hard_clip,
+                                    uint32_t n_pos, int64_t* out) {
+    auto m = get_read_segment_to_ref_pos_tree_map(ref_pos, decode_cigar(cigar, n), ignore_hard_clip != 0);
+    for (uint32_t i = 0; i < n_pos; ++i) {
+        auto v = m.get_ref_pos(i);
+        out[i] = v ? *v : INT64_MIN;
+    }
+}
+int64_t ptl_oracle_fn_tree_map_ref_range(int64_t ref_pos, const uint32_t* cigar, uint32_t n, int ignore_hard_clip,
+                                         uint64_t start, uint64_t end, uint64_t* keys, int64_t* vals, uint32_t cap) {
+    auto m = get_read_segment_to_ref_pos_tree_map(ref_pos, decode_cigar(cigar, n), ignore_hard_clip != 0);
+    auto r = m.get_ref_range(start, end);
+    uint32_t i = 0;
+    for (auto it = r.first; it != r.second; ++it, ++i) {
+        if (i < cap) {
+            keys[i] = it->first;
+            vals[i] = it->second ? *it->second : -1;
+        }
+    }
+    return i;
+}
+// clip_seg_isec_range on one segment; io arrays: so[2] (seq-order start,end), pos; returns new cigar len or -1 if eliminated
+int64_t ptl_oracle_fn_clip_seg_isec_range(uint64_t* so, int64_t* pos, int is_fwd, const uint32_t* cigar, uint32_t n,
+                                          int64_t isec_start, int64_t isec_end, uint32_t* out, uint32_t cap) {
+    SeqOrderSplitReadSegment s;
+    s.seq_order_read_start = so[0];
+    s.seq_order_read_end = so[1];
+    s.pos = *pos;
+    s.is_fwd_strand = is_fwd != 0;
+    s.cigar = decode_cigar(cigar, n);
+    const bool eliminated = clip_seg_isec_range(s, IntRange{isec_start, isec_end});
+    so[0] = s.seq_order_read_start;
+    so[1] = s.seq_order_read_end;
+    *pos = s.pos;
+    const int64_t len = emit(s.cigar, out, cap);
+    return eliminated ? -1 : len;
+}
+double ptl_oracle_fn_gci(const uint32_t* cigar, uint32_t n) {
+    try {
+        return get_gap_compressed_identity_no_align_match(decode_cigar(cigar, n));
+    } catch (const Panic&) { return -1.0; }
+}
+uint16_t ptl_oracle_fn_reg2bin(int64_t begin, int64_t end) { return bam_reg2bin(size_t(begin), size_t(end)); }
+uint32_t ptl_oracle_fn_region_segments(uint64_t size, uint64_t segment_size, uint64_t* begin, uint64_t* end, uint32_t cap) {
+    auto v = get_region_segments(size, segment_size);
+    for (size_t i = 0; i < v.size() && i < cap; ++i) {
+        begin[i] = v[i].first;
+        end[i] = v[i].second;
+    }
+    return uint32_t(v.size());
+}
+void ptl_oracle_fn_rev_comp(uint8_t* seq, uint64_t n) {
+    std::vector<uint8_t> v(seq, seq + n);
+    rev_comp_in_place(v);
+    std::memcpy(seq, v.data(), n);
+}
+int64_t ptl_oracle_fn_strip_clip(int trailing, const uint32_t* cigar, uint32_t n, uint32_t* out, uint32_t cap) {
+    CigarVec c = decode_cigar(cigar, n);
+    if (trailing) strip_trailing_clip(c); else strip_leading_clip(c);
+    return emit(c, out, cap);
+}
+
+// parse_sa_aux_val: returns segment count (or -1 on a reference panic); rnames are written '\n'-joined.
+int64_t ptl_oracle_fn_parse_sa(const char* sa, uint32_t cap, int64_t* pos, uint8_t* is_fwd, uint8_t* mapq, int32_t* nm,
+                               uint32_t* n_cigar, char* rnames, uint32_t rnames_cap) {
+    try {
+        auto v = parse_sa_aux_val(sa);
+        std::string names;
+        for (size_t i = 0; i < v.size(); ++i) {
+            if (i < cap) {
+                pos[i] = v[i].pos; is_fwd[i] = v[i].is_fwd_strand; mapq[i] = v[i].mapq; nm[i] = v[i].nm;
+                n_cigar[i] = uint32_t(v[i].cigar.size());
+            }
+            names += v[i].rname;
+            names.push_back('\n');
+        }
+        if (names.size() + 1 <= rnames_cap) std::memcpy(rnames, names.c_str(), names.size() + 1);
+        return int64_t(v.size());
+    } catch (const Panic&) { return -1; }
+}
+
+// get_seq_order_read_split_segments for one record.  Same outputs as ptl_pack_split_segments.
+static thread_local std::string g_split_err;
+const char* ptl_oracle_split_last_error(void) { return g_split_err.c_str(); }
+int ptl_oracle_split_segments(uint32_t n_names, const char* const* names, int32_t tid, int64_t pos, uint16_t flag,
+                              uint8_t mapq, const uint32_t* cigar, uint32_t n_cigar, const char* sa_tag,
+                              uint32_t cap_segments, uint32_t cap_cigar, ptl_split_segments* out, uint32_t* n_segments,
+                              uint32_t* n_cigar_out) {
+    try {
+        NameIndex idx;
+        for (uint32_t i = 0; i < n_names; ++i) idx[names[i]] = i;
+        AlnRecord rec;
+        rec.tid = tid; rec.pos = pos; rec.flag = flag; rec.mapq = mapq;
+        rec.cigar = decode_cigar(cigar, n_cigar);
+        if (sa_tag) { rec.has_sa = true; rec.sa = sa_tag; }
+        auto segs = get_seq_order_read_split_segments(idx, rec);
+        size_t total = 0;
+        for (const auto& s : segs) total += s.cigar.size();
+        *n_segments = uint32_t(segs.size());
+        *n_cigar_out = uint32_t(total);
+        if (segs.size() > cap_segments || total > cap_cigar) return PTL_ERR_INVALID_ARG;
+        uint32_t w = 0;
+        for (size_t i = 0; i < segs.size(); ++i) {
+            const auto& s = segs[i];
+            out->seq_order_start[i] = uint32_t(s.seq_order_read_start);
+            out->seq_order_end[i] = uint32_t(s.seq_order_read_end);
+            out->contig[i] = uint32_t(s.chrom_index);
+            out->pos[i] = s.pos;
+            out->is_fwd[i] = s.is_fwd_strand;
+            out->mapq[i] = s.mapq;
+            out->from_primary[i] = s.from_primary_bam_record;
+            out->cigar_begin[i] = w;
+            for (const auto& c : s.cigar) out->cigar[w++] = encode(c);
+        }
+        out->cigar_begin[segs.size()] = w;
+        return PTL_OK;
+    } catch (const Panic& p) {
+        g_split_err = p.what();
+        return PTL_ERR_INPUT;
+    }
+}
+
+// SA:Z text, same contract as ptl_format_sa_tags.
+int ptl_oracle_format_sa_tags(const ptl_result* res, uint32_t n_chrom, const char* const* chrom_names, char* buf,
+                              uint64_t cap, uint64_t* sa_begin, uint64_t* need) {
+    std::vector<std::string> names(chrom_names, chrom_names + n_chrom);
+    std::string all;
+    std::vector<uint64_t> begin;
+    for (uint32_t r = 0; r < res->n_reads; ++r) {
+        std::vector<LiftedRecord> recs;
+        for (uint32_t k = res->read_rec_begin[r]; k < res->read_rec_begin[r + 1]; ++k) {
+            LiftedRecord x;
+            x.status = res->rec_status[k];
+            x.tid = res->rec_tid[k];
+            x.pos = res->rec_pos[k];
+            x.flag = res->rec_flag[k];
+            x.mapq = res->rec_mapq[k];
+            x.cigar = decode_cigar(res->cigar + res->rec_cigar_begin[k], res->rec_cigar_begin[k + 1] - res->rec_cigar_begin[k]);
+            recs.push_back(std::move(x));
+        }
+        for (const auto& s : format_sa_tags(names, recs)) {
+            begin.push_back(all.size());
+            all += s;
+            all.push_back('\0');
+        }
+    }
+    begin.push_back(all.size());
+    *need = all.size();
+    if (all.size() > cap) return PTL_ERR_INVALID_ARG;
+    std::memcpy(buf, all.data(), all.size());
+    std::memcpy(sa_begin, begin.data(), begin.size() * sizeof(uint64_t));
+    return PTL_OK;
+}
+
+}  // extern "C"
