@@ -184,6 +184,14 @@ typedef struct ptl_contig_records {
  * supplementary exact-CIGAR fill-in keyed by SplitReadKey (:49-56,135-183,360-439), rev_contig_seq (:113-125),
  * then trim + join, then install (host C++ for the O(#contig records) part, CUDA for the tables). */
 int ptl_set_contig_records(ptl_ctx* ctx, const ptl_contig_records* recs);
+/* Host-only form of the two calls above (no device needed): prepare, inspect, free.  Used by hosts that want the
+ * post trim/join segments (e.g. for PS:Z split indices) before a GPU is involved, and by the CPU test-suite. */
+typedef struct ptl_prepared_contigs ptl_prepared_contigs;
+int ptl_prepare_contig_records(const ptl_contig_records* recs, ptl_prepared_contigs** out);
+int ptl_prepare_raw_contig_segments(const ptl_contig_segments* raw, ptl_prepared_contigs** out);
+void ptl_prepared_contigs_view(const ptl_prepared_contigs* p, ptl_contig_segments* out);
+void ptl_prepared_contigs_free(ptl_prepared_contigs* p);
+const char* ptl_prepare_last_error(void);
 /* Borrow the installed (post trim/join) segments; pointers owned by ctx, valid until the next set call. */
 int ptl_get_contig_segments(const ptl_ctx* ctx, ptl_contig_segments* out);
 /* Copy the device-built table of one global segment index back to the host (testing a7):
@@ -218,6 +226,10 @@ void* ptl_slot_stream(ptl_ctx* ctx, int slot);
 int ptl_slot_kernel_times(ptl_ctx* ctx, int slot, int cap, const char** names, float* ms);
 /* Number of kernel launches issued by this ctx so far (bench.py `gpu_launches`). */
 uint64_t ptl_launch_count(const ptl_ctx* ctx);
+/* Work counters of the last finished batch on a slot (syncs the slot): out[0..6) = attempted pairs, lifted pairs,
+ * input CIGAR ops walked, output CIGAR ops, base bytes compared (both operands), scratch op slots used.
+ * These feed the algorithmic-bytes formula of the roofline. */
+int ptl_slot_counters(ptl_ctx* ctx, int slot, uint64_t* out);
 /* 0: copy seq4 to the device (default). 1: seq4 of subsequent batches must be pinned+mapped host memory
  * (ptl_host_alloc); kernels read the few bases they need over PCIe instead of uploading every base. */
 int ptl_set_seq_zero_copy(ptl_ctx* ctx, int enable);
@@ -228,6 +240,36 @@ void* ptl_host_alloc(size_t bytes);
 void ptl_host_free(void* p);
 
 /* ---------------------------------------------------------------- host-side helpers (C++, no GPU needed) */
+
+/* Read->contig primary records as scan_chromosome_segment sees them after BAM decode
+ * (src/read_alignment_scanner.rs:382-406: mapped, non-supplementary), in BAM order. */
+typedef struct ptl_read_records {
+    uint32_t n_reads;
+    const int32_t* tid;            /* contig index */
+    const int64_t* pos;
+    const uint16_t* flag;
+    const uint8_t* mapq;
+    const uint16_t* bin;
+    const uint32_t* seq_len;
+    const uint64_t* seq_off;       /* byte offset of the record's packed bases in seq4 */
+    const uint8_t* seq4;
+    uint64_t seq4_bytes;
+    const uint64_t* cigar_begin;   /* [n_reads+1] */
+    const uint32_t* cigar;
+    const char* const* sa_tag;     /* [n_reads] SA:Z value, NULL if absent */
+} ptl_read_records;
+
+/* The host packer (replaces the record loop head of scan_chromosome_segment, :393-421): turns records
+ * [first, first+count) into one SoA ptl_batch, running get_seq_order_read_split_segments (split_read.rs:56-155) for
+ * every record that carries an SA tag.  Small arrays are (optionally pinned) copies; the packed bases are NOT copied,
+ * the batch borrows recs->seq4.  Returns PTL_ERR_INPUT where the reference panics (ptl_pack_last_error). */
+typedef struct ptl_packed_batch ptl_packed_batch;
+int ptl_pack_batch(const ptl_read_records* recs, uint32_t first, uint32_t count, uint32_t n_contigs,
+                   const char* const* contig_names, int pinned, ptl_packed_batch** out);
+void ptl_packed_batch_view(const ptl_packed_batch* p, ptl_batch* out);
+/* [view.n_reads] index of each batch read in `recs` (supplementary records are dropped by the packer). */
+const uint32_t* ptl_packed_batch_record_index(const ptl_packed_batch* p);
+void ptl_packed_batch_free(ptl_packed_batch* p);
 
 /* Parse an SA:Z aux value into split segments = parse_sa_aux_val (lib/rust-vc-utils/src/bam_utils/aux/sa_tag_parser.rs:25-59)
  * + the segment construction / stable ordering of get_seq_order_read_split_segments (split_read.rs:56-155) for one

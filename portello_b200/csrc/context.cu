@@ -1,0 +1,648 @@
+// Host orchestration + C-ABI of libportello_b200.so (include/portello_b200.h).
+//
+// One ptl_ctx per GPU.  Static state (reference, rev_contig_seq, segment tables) is uploaded once; each of the
+// n_slots batch slots owns a CUDA stream, grow-only device buffers and pinned host result buffers, which replaces
+// the reference's per-thread reader/worker pool (src/worker_thread_data.rs:8-30) with a multi-buffered stream
+// pipeline.  There is NO CPU fallback: without a usable device ptl_create fails with PTL_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/portello_b200.h"
+#include "device/kernels.hpp"
+#include "host/contig_prep.hpp"
+
+using namespace ptl;
+
+namespace {
+
+struct CudaError {
+    std::string msg;
+};
+#define CK(call)                                                                                                  \
+    do {                                                                                                          \
+        cudaError_t e_ = (call);                                                                                  \
+        if (e_ != cudaSuccess)                                                                                    \
+            throw CudaError{std::string(#call) + ": " + cudaGetErrorString(e_) + " (" __FILE__ ":" + std::to_string(__LINE__) + ")"}; \
+    } while (0)
+
+// grow-only device buffer
+struct DBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    void ensure(size_t bytes, cudaStream_t st) {
+        if (bytes <= cap) return;
+        if (p) {
+            CK(cudaStreamSynchronize(st));
+            CK(cudaFree(p));
+            p = nullptr;
+            cap = 0;
+        }
+        const size_t want = std::max<size_t>(bytes + bytes / 8, 256);
+        CK(cudaMalloc(&p, want));
+        cap = want;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T* as() const { return static_cast<T*>(p); }
+};
+// grow-only pinned host buffer
+struct HBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    void ensure(size_t bytes) {
+        if (bytes <= cap) return;
+        if (p) CK(cudaFreeHost(p));
+        p = nullptr;
+        cap = 0;
+        const size_t want = std::max<size_t>(bytes + bytes / 8, 256);
+        CK(cudaHostAlloc(&p, want, cudaHostAllocPortable));
+        cap = want;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    StageEvents ev{};
+    bool have_events = false;
+    // device copies of the batch
+    DBuf d_read_flag, d_read_mapq, d_read_bin, d_read_seq_len, d_read_seq_off, d_read_seg_begin, d_rseg_contig, d_rseg_pos,
+        d_rseg_is_fwd, d_rseg_cigar_begin, d_rseg_cigar_len, d_cigar, d_seq4;
+    // work
+    DBuf w_rseg_read, w_rseg_pair_begin, w_rseg_ref_len, w_pair_rseg, w_pair_seg, w_pair_slot_begin, w_pair_status, w_pair_flip,
+        w_pair_pos, w_pair_n_out, w_pair_out_off, w_scratch, w_read_counts, w_read_primary, w_scan_tmp, w_totals;
+    // results (device)
+    DBuf r_read_rec_begin, r_status, r_rseg, r_cseg, r_tid, r_pos, r_mapq, r_flag, r_bin, r_flip, r_cigar_begin, r_cigar;
+    // results (pinned host)
+    HBuf h_read_rec_begin, h_status, h_rseg, h_cseg, h_tid, h_pos, h_mapq, h_flag, h_bin, h_flip, h_cigar_begin, h_cigar, h_totals;
+    DevBatch B;
+    DevWork W;
+    DevResult R;
+    uint32_t stage_mask = PTL_STAGE_ALL;
+    bool uploaded = false, ran = false;
+    uint64_t n_cigar_in = 0;
+    ptl_result res{};
+    DevTotals totals{};
+};
+
+}  // namespace
+
+struct ptl_ctx {
+    int device = 0;
+    std::string err;
+    std::vector<Slot> slots;
+    cudaStream_t setup_stream = nullptr;
+    uint64_t launches = 0;
+    bool zero_copy_seq = false;
+    // static state
+    DBuf s_ref, s_chrom_off, s_contig_seg_begin, s_contig_len, s_contig_rev_off, s_rev_pool, s_so_start, s_so_end, s_chrom, s_pos,
+        s_is_fwd, s_mapq, s_cigar_begin, s_cigar, s_tab_begin, s_table;
+    DevStatic S;
+    bool have_reference = false, have_segments = false;
+    FlatContigs flat;
+    std::vector<uint32_t> h_tab_begin;
+};
+
+namespace {
+
+int fail(ptl_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    return code;
+}
+
+template <class F>
+int guarded(ptl_ctx* ctx, F f) {
+    try {
+        if (ctx) CK(cudaSetDevice(ctx->device));
+        return f();
+    } catch (const CudaError& e) {
+        return fail(ctx, PTL_ERR_CUDA, e.msg);
+    } catch (const InputError& e) {
+        return fail(ctx, PTL_ERR_INPUT, e.what());
+    } catch (const std::exception& e) {
+        return fail(ctx, PTL_ERR_INVALID_ARG, e.what());
+    }
+}
+
+template <class T>
+const T* upload(DBuf& b, const T* src, size_t n, cudaStream_t st) {
+    b.ensure(std::max<size_t>(n, 1) * sizeof(T), st);
+    if (n) CK(cudaMemcpyAsync(b.p, src, n * sizeof(T), cudaMemcpyHostToDevice, st));
+    return b.as<T>();
+}
+
+void install_segments(ptl_ctx* ctx, std::vector<HostContig>& contigs) {
+    cudaStream_t st = ctx->setup_stream;
+    ctx->flat.build(contigs);
+    const FlatContigs& f = ctx->flat;
+    const uint32_t nc = uint32_t(f.contig_len.size()), ns = uint32_t(f.so_start.size());
+    for (uint32_t g = 0; g < ns; ++g) {
+        if (f.chrom[g] < 0 || (ctx->have_reference && uint32_t(f.chrom[g]) >= ctx->S.n_chrom))
+            throw InputError("contig segment with a chromosome index outside the reference");
+        if (f.pos[g] < 0 || f.pos[g] > 0x7fffffffLL) throw InputError("contig segment position outside the BAM int32 range");
+    }
+    DevStatic& S = ctx->S;
+    S.n_contigs = nc;
+    S.n_segments = ns;
+    S.contig_seg_begin = upload(ctx->s_contig_seg_begin, f.seg_begin.data(), nc + 1, st);
+    S.contig_len = upload(ctx->s_contig_len, f.contig_len.data(), nc, st);
+    // rev_contig_seq pool
+    std::vector<uint64_t> rev_off(nc, ~0ull);
+    uint64_t pool = 0;
+    for (uint32_t c = 0; c < nc; ++c)
+        if (f.has_rev[c]) { rev_off[c] = pool; pool += (f.contig_len[c] + 15) & ~15ull; }
+    ctx->s_rev_pool.ensure(std::max<uint64_t>(pool, 16), st);
+    for (uint32_t c = 0; c < nc; ++c)
+        if (f.has_rev[c] && f.contig_len[c])
+            CK(cudaMemcpyAsync(ctx->s_rev_pool.as<uint8_t>() + rev_off[c], f.rev_seq[c].data(), f.contig_len[c], cudaMemcpyHostToDevice, st));
+    S.rev_pool = ctx->s_rev_pool.as<uint8_t>();
+    S.contig_rev_off = upload(ctx->s_contig_rev_off, rev_off.data(), nc, st);
+    S.seg_so_start = upload(ctx->s_so_start, f.so_start.data(), ns, st);
+    S.seg_so_end = upload(ctx->s_so_end, f.so_end.data(), ns, st);
+    S.seg_chrom = upload(ctx->s_chrom, f.chrom.data(), ns, st);
+    S.seg_pos = upload(ctx->s_pos, f.pos.data(), ns, st);
+    S.seg_is_fwd = upload(ctx->s_is_fwd, f.is_fwd.data(), ns, st);
+    S.seg_mapq = upload(ctx->s_mapq, f.mapq.data(), ns, st);
+    S.seg_cigar_begin = upload(ctx->s_cigar_begin, f.cigar_begin.data(), ns + 1, st);
+    S.seg_cigar = upload(ctx->s_cigar, f.cigar.data(), f.cigar.size(), st);
+    // device tables: count -> scan -> fill
+    ctx->s_tab_begin.ensure((size_t(ns) + 1) * 4, st);
+    CK(cudaMemsetAsync(ctx->s_tab_begin.p, 0, (size_t(ns) + 1) * 4, st));
+    S.seg_tab_begin = ctx->s_tab_begin.as<uint32_t>();
+    S.table = nullptr;
+    ctx->h_tab_begin.assign(size_t(ns) + 1, 0);
+    if (ns) {
+        launch_table_build(S, ctx->s_tab_begin.as<uint32_t>(), nullptr, st);
+        ++ctx->launches;
+        DBuf tmp;
+        tmp.ensure(scan_tmp_bytes(ns + 1), st);
+        exclusive_scan_inplace<uint32_t>(ctx->s_tab_begin.as<uint32_t>(), uint64_t(ns) + 1, tmp.p, tmp.cap, st, &ctx->launches);
+        CK(cudaMemcpyAsync(ctx->h_tab_begin.data(), ctx->s_tab_begin.p, (size_t(ns) + 1) * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        tmp.release();
+        const uint32_t total = ctx->h_tab_begin[ns];
+        ctx->s_table.ensure(std::max<size_t>(total, 1) * sizeof(int2), st);
+        S.table = ctx->s_table.as<int2>();
+        launch_table_build(S, nullptr, ctx->s_table.as<int2>(), st);
+        ++ctx->launches;
+    }
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    ctx->have_segments = true;
+}
+
+void upload_batch(ptl_ctx* ctx, Slot& sl, const ptl_batch* b) {
+    cudaStream_t st = sl.stream;
+    const uint32_t n = b->n_reads, ns = b->n_read_segments;
+    // cheap host-side validation of what would be an index panic in the reference
+    if (n && b->read_seg_begin[n] != ns) throw std::runtime_error("read_seg_begin[n_reads] != n_read_segments");
+    for (uint32_t s = 0; s < ns; ++s) {
+        if (b->rseg_contig[s] >= ctx->S.n_contigs) throw std::runtime_error("read segment refers to a contig index outside the assembly");
+        if (b->rseg_cigar_begin[s] + b->rseg_cigar_len[s] > b->n_cigar) throw std::runtime_error("read segment CIGAR outside the pool");
+    }
+    DevBatch& B = sl.B;
+    B.n_reads = n;
+    B.n_rsegs = ns;
+    B.n_cigar = b->n_cigar;
+    B.read_flag = upload(sl.d_read_flag, b->read_flag, n, st);
+    B.read_mapq = upload(sl.d_read_mapq, b->read_mapq, n, st);
+    B.read_bin = upload(sl.d_read_bin, b->read_bin, n, st);
+    B.read_seq_len = upload(sl.d_read_seq_len, b->read_seq_len, n, st);
+    B.read_seq_off = upload(sl.d_read_seq_off, b->read_seq_off, n, st);
+    B.read_seg_begin = upload(sl.d_read_seg_begin, b->read_seg_begin, size_t(n) + 1, st);
+    B.rseg_contig = upload(sl.d_rseg_contig, b->rseg_contig, ns, st);
+    B.rseg_pos = upload(sl.d_rseg_pos, b->rseg_pos, ns, st);
+    B.rseg_is_fwd = upload(sl.d_rseg_is_fwd, b->rseg_is_fwd, ns, st);
+    B.rseg_cigar_begin = upload(sl.d_rseg_cigar_begin, b->rseg_cigar_begin, ns, st);
+    B.rseg_cigar_len = upload(sl.d_rseg_cigar_len, b->rseg_cigar_len, ns, st);
+    B.cigar = upload(sl.d_cigar, b->cigar, b->n_cigar, st);
+    if (ctx->zero_copy_seq) {
+        void* dptr = nullptr;
+        CK(cudaHostGetDevicePointer(&dptr, const_cast<uint8_t*>(b->seq4), 0));  // must come from ptl_host_alloc
+        B.seq4 = static_cast<const uint8_t*>(dptr);
+    } else {
+        B.seq4 = upload(sl.d_seq4, b->seq4, b->seq4_bytes, st);
+    }
+    sl.n_cigar_in = b->n_cigar;
+    sl.uploaded = true;
+    sl.ran = false;
+}
+
+void size_work(Slot& sl, uint32_t want_pairs, uint64_t want_scratch, uint32_t want_recs, uint64_t want_cigar) {
+    cudaStream_t st = sl.stream;
+    const uint32_t n = sl.B.n_reads, ns = sl.B.n_rsegs;
+    DevWork& W = sl.W;
+    sl.w_rseg_read.ensure(size_t(ns) * 4 + 4, st);
+    sl.w_rseg_pair_begin.ensure((size_t(ns) + 1) * 4, st);
+    sl.w_rseg_ref_len.ensure(size_t(ns) * 8 + 8, st);
+    W.rseg_read = sl.w_rseg_read.as<uint32_t>();
+    W.rseg_pair_begin = sl.w_rseg_pair_begin.as<uint32_t>();
+    W.rseg_ref_len = sl.w_rseg_ref_len.as<int64_t>();
+    const uint32_t pc = std::max(W.pair_cap, want_pairs);
+    sl.w_pair_rseg.ensure(size_t(pc) * 4, st);
+    sl.w_pair_seg.ensure(size_t(pc) * 4, st);
+    sl.w_pair_slot_begin.ensure((size_t(pc) + 1) * 8, st);
+    sl.w_pair_status.ensure(size_t(pc), st);
+    sl.w_pair_flip.ensure(size_t(pc), st);
+    sl.w_pair_pos.ensure(size_t(pc) * 8, st);
+    sl.w_pair_n_out.ensure(size_t(pc) * 4, st);
+    sl.w_pair_out_off.ensure(size_t(pc) * 8, st);
+    W.pair_cap = pc;
+    W.pair_rseg = sl.w_pair_rseg.as<uint32_t>();
+    W.pair_seg = sl.w_pair_seg.as<uint32_t>();
+    W.pair_slot_begin = sl.w_pair_slot_begin.as<uint64_t>();
+    W.pair_status = sl.w_pair_status.as<int8_t>();
+    W.pair_flip = sl.w_pair_flip.as<uint8_t>();
+    W.pair_pos = sl.w_pair_pos.as<int64_t>();
+    W.pair_n_out = sl.w_pair_n_out.as<uint32_t>();
+    W.pair_out_off = sl.w_pair_out_off.as<uint64_t>();
+    const uint64_t sc = std::max(W.scratch_cap, want_scratch);
+    sl.w_scratch.ensure(size_t(sc) * 4, st);
+    W.scratch_cap = sc;
+    W.scratch = sl.w_scratch.as<uint32_t>();
+    sl.w_read_counts.ensure((size_t(n) + 1) * sizeof(uint2), st);
+    sl.w_read_primary.ensure(size_t(n) * 4 + 4, st);
+    W.read_counts = sl.w_read_counts.as<uint2>();
+    W.read_primary = sl.w_read_primary.as<uint32_t>();
+    const uint64_t biggest = std::max<uint64_t>({uint64_t(ns) + 1, uint64_t(pc) + 1, uint64_t(n) + 1});
+    sl.w_scan_tmp.ensure(scan_tmp_bytes(biggest), st);
+    sl.w_totals.ensure(sizeof(DevTotals), st);
+    DevResult& R = sl.R;
+    const uint32_t rc = std::max(R.rec_cap, want_recs);
+    const uint64_t cc = std::max(R.cigar_cap, want_cigar);
+    sl.r_read_rec_begin.ensure((size_t(n) + 1) * 4, st);
+    sl.r_status.ensure(size_t(rc), st);
+    sl.r_rseg.ensure(size_t(rc) * 4, st);
+    sl.r_cseg.ensure(size_t(rc) * 4, st);
+    sl.r_tid.ensure(size_t(rc) * 4, st);
+    sl.r_pos.ensure(size_t(rc) * 8, st);
+    sl.r_mapq.ensure(size_t(rc), st);
+    sl.r_flag.ensure(size_t(rc) * 2, st);
+    sl.r_bin.ensure(size_t(rc) * 2, st);
+    sl.r_flip.ensure(size_t(rc), st);
+    sl.r_cigar_begin.ensure((size_t(rc) + 1) * 8, st);
+    sl.r_cigar.ensure(size_t(cc) * 4 + 4, st);
+    R.rec_cap = rc;
+    R.cigar_cap = cc;
+    R.read_rec_begin = sl.r_read_rec_begin.as<uint32_t>();
+    R.rec_status = sl.r_status.as<int8_t>();
+    R.rec_read_segment = sl.r_rseg.as<uint32_t>();
+    R.rec_contig_segment = sl.r_cseg.as<uint32_t>();
+    R.rec_tid = sl.r_tid.as<int32_t>();
+    R.rec_pos = sl.r_pos.as<int64_t>();
+    R.rec_mapq = sl.r_mapq.as<uint8_t>();
+    R.rec_flag = sl.r_flag.as<uint16_t>();
+    R.rec_bin = sl.r_bin.as<uint16_t>();
+    R.rec_need_flip = sl.r_flip.as<uint8_t>();
+    R.rec_cigar_begin = sl.r_cigar_begin.as<uint64_t>();
+    R.cigar = sl.r_cigar.as<uint32_t>();
+}
+
+void enqueue_run(ptl_ctx* ctx, Slot& sl) {
+    launch_lift(ctx->S, sl.B, sl.W, sl.R, sl.w_totals.as<DevTotals>(), sl.stage_mask, sl.w_scan_tmp.p, sl.w_scan_tmp.cap, sl.stream,
+                &ctx->launches, sl.have_events ? &sl.ev : nullptr);
+    sl.h_totals.ensure(sizeof(DevTotals));
+    CK(cudaMemcpyAsync(sl.h_totals.p, sl.w_totals.p, sizeof(DevTotals), cudaMemcpyDeviceToHost, sl.stream));
+    sl.ran = true;
+}
+
+void run_batch(ptl_ctx* ctx, Slot& sl, uint32_t stage_mask) {
+    if (!ctx->have_segments) throw std::runtime_error("ptl_set_contig_segments / ptl_set_contig_records has not been called");
+    if ((stage_mask & PTL_STAGE_SIMPLIFY) && !ctx->have_reference) throw std::runtime_error("ptl_set_reference has not been called");
+    sl.stage_mask = stage_mask;
+    // optimistic capacities (no host round trip before the kernels); overflow is detected on the device and the
+    // batch is re-run with exact sizes (finish_batch).  Steady-state batches of similar shape never re-run.
+    const uint32_t ns = sl.B.n_rsegs, n = sl.B.n_reads;
+    const uint32_t want_pairs = ns + ns / 8 + 1024;
+    const uint64_t want_scratch = 40ull * sl.n_cigar_in + 96ull * want_pairs;
+    const uint32_t want_recs = want_pairs + n;
+    const uint64_t want_cigar = sl.n_cigar_in + sl.n_cigar_in / 2 + 16ull * n + 1024;
+    size_work(sl, want_pairs, want_scratch, want_recs, want_cigar);
+    enqueue_run(ctx, sl);
+}
+
+// Wait for the kernels, re-run on capacity overflow, leave totals in sl.totals.
+void finish_batch(ptl_ctx* ctx, Slot& sl) {
+    for (int attempt = 0; attempt < 6; ++attempt) {
+        CK(cudaStreamSynchronize(sl.stream));
+        CK(cudaGetLastError());
+        std::memcpy(&sl.totals, sl.h_totals.p, sizeof(DevTotals));
+        const DevTotals& t = sl.totals;
+        if (!t.overflow) return;
+        const uint32_t want_pairs = uint32_t(std::max<uint64_t>(t.n_pairs, sl.W.pair_cap));
+        uint64_t want_scratch = sl.W.scratch_cap, want_cigar = sl.R.cigar_cap;
+        uint32_t want_recs = sl.R.rec_cap;
+        if (!(t.overflow & OVF_PAIRS)) {
+            want_scratch = std::max<uint64_t>(want_scratch, t.scratch_needed);
+            if (!(t.overflow & OVF_SCRATCH)) {
+                want_recs = uint32_t(std::max<uint64_t>(want_recs, t.n_records));
+                want_cigar = std::max<uint64_t>(want_cigar, t.n_cigar_out);
+            }
+        }
+        want_recs = std::max<uint32_t>(want_recs, want_pairs + sl.B.n_reads);
+        size_work(sl, want_pairs, want_scratch, want_recs, want_cigar);
+        enqueue_run(ctx, sl);
+    }
+    throw std::runtime_error("work buffers still overflow after resizing (internal error)");
+}
+
+template <class T>
+const T* fetch(HBuf& h, const DBuf& d, size_t n, cudaStream_t st) {
+    h.ensure(std::max<size_t>(n, 1) * sizeof(T));
+    if (n) CK(cudaMemcpyAsync(h.p, d.p, n * sizeof(T), cudaMemcpyDeviceToHost, st));
+    return h.as<T>();
+}
+
+int download(ptl_ctx* ctx, Slot& sl, ptl_result* out) {
+    finish_batch(ctx, sl);
+    const DevTotals& t = sl.totals;
+    cudaStream_t st = sl.stream;
+    const size_t n = sl.B.n_reads, nr = size_t(t.n_records), nc = size_t(t.n_cigar_out);
+    ptl_result& r = sl.res;
+    r = ptl_result{};
+    r.n_reads = uint32_t(n);
+    r.n_records = uint32_t(nr);
+    r.n_cigar = nc;
+    if (n) {
+        r.read_rec_begin = fetch<uint32_t>(sl.h_read_rec_begin, sl.r_read_rec_begin, n + 1, st);
+        r.rec_status = fetch<int8_t>(sl.h_status, sl.r_status, nr, st);
+        r.rec_read_segment = fetch<uint32_t>(sl.h_rseg, sl.r_rseg, nr, st);
+        r.rec_contig_segment = fetch<uint32_t>(sl.h_cseg, sl.r_cseg, nr, st);
+        r.rec_tid = fetch<int32_t>(sl.h_tid, sl.r_tid, nr, st);
+        r.rec_pos = fetch<int64_t>(sl.h_pos, sl.r_pos, nr, st);
+        r.rec_mapq = fetch<uint8_t>(sl.h_mapq, sl.r_mapq, nr, st);
+        r.rec_flag = fetch<uint16_t>(sl.h_flag, sl.r_flag, nr, st);
+        r.rec_bin = fetch<uint16_t>(sl.h_bin, sl.r_bin, nr, st);
+        r.rec_need_flip = fetch<uint8_t>(sl.h_flip, sl.r_flip, nr, st);
+        r.rec_cigar_begin = fetch<uint64_t>(sl.h_cigar_begin, sl.r_cigar_begin, nr + 1, st);
+        r.cigar = fetch<uint32_t>(sl.h_cigar, sl.r_cigar, nc, st);
+        CK(cudaStreamSynchronize(st));
+    } else {
+        sl.h_read_rec_begin.ensure(4);
+        sl.h_cigar_begin.ensure(8);
+        sl.h_read_rec_begin.as<uint32_t>()[0] = 0;
+        sl.h_cigar_begin.as<uint64_t>()[0] = 0;
+        r.read_rec_begin = sl.h_read_rec_begin.as<uint32_t>();
+        r.rec_cigar_begin = sl.h_cigar_begin.as<uint64_t>();
+    }
+    r.n_pairs = t.n_pairs;
+    r.n_lifted = t.n_lifted;
+    r.n_errors = t.n_errors;
+    if (t.n_errors) {
+        r.first_error_read = t.first_error_read >> 8;
+        r.first_error_status = int32_t(int8_t(t.first_error_read & 0xff));
+    } else {
+        r.first_error_read = -1;
+        r.first_error_status = 0;
+    }
+    *out = r;
+    if (t.n_errors)
+        return fail(ctx, PTL_ERR_LIFT_PANIC,
+                    "the reference would panic on read " + std::to_string(r.first_error_read) + " (status " + std::to_string(r.first_error_status) + ")");
+    return PTL_OK;
+}
+
+Slot* get_slot(ptl_ctx* ctx, int slot) {
+    if (!ctx || slot < 0 || size_t(slot) >= ctx->slots.size()) return nullptr;
+    return &ctx->slots[size_t(slot)];
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ptl_version(void) { return "portello_b200 0.1 (sm_100a CUDA kernels, C-ABI 1)"; }
+
+int ptl_create(int device, int n_slots, ptl_ctx** out) {
+    if (!out || n_slots < 1 || n_slots > 64) return PTL_ERR_INVALID_ARG;
+    *out = nullptr;
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || device < 0 || device >= n_dev) {
+        cudaGetLastError();
+        return PTL_ERR_NO_DEVICE;  // no CPU fallback by design
+    }
+    cudaDeviceProp prop{};
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major < 10) {
+        cudaGetLastError();
+        return PTL_ERR_NO_DEVICE;  // the kernels are compiled for sm_100a only
+    }
+    auto* ctx = new ptl_ctx();
+    ctx->device = device;
+    const int rc = guarded(ctx, [&]() {
+        CK(cudaStreamCreateWithFlags(&ctx->setup_stream, cudaStreamNonBlocking));
+        ctx->slots.resize(size_t(n_slots));
+        for (auto& sl : ctx->slots) {
+            CK(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+            for (auto& e : sl.ev.e) CK(cudaEventCreate(&e));
+            sl.have_events = true;
+        }
+        return PTL_OK;
+    });
+    if (rc != PTL_OK) {
+        std::fprintf(stderr, "ptl_create: %s\n", ctx->err.c_str());
+        delete ctx;
+        return rc;
+    }
+    *out = ctx;
+    return PTL_OK;
+}
+
+void ptl_destroy(ptl_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    for (auto& sl : ctx->slots) {
+        if (sl.stream) cudaStreamSynchronize(sl.stream);
+        for (DBuf* b : {&sl.d_read_flag, &sl.d_read_mapq, &sl.d_read_bin, &sl.d_read_seq_len, &sl.d_read_seq_off, &sl.d_read_seg_begin,
+                        &sl.d_rseg_contig, &sl.d_rseg_pos, &sl.d_rseg_is_fwd, &sl.d_rseg_cigar_begin, &sl.d_rseg_cigar_len, &sl.d_cigar,
+                        &sl.d_seq4, &sl.w_rseg_read, &sl.w_rseg_pair_begin, &sl.w_rseg_ref_len, &sl.w_pair_rseg, &sl.w_pair_seg,
+                        &sl.w_pair_slot_begin, &sl.w_pair_status, &sl.w_pair_flip, &sl.w_pair_pos, &sl.w_pair_n_out, &sl.w_pair_out_off,
+                        &sl.w_scratch, &sl.w_read_counts, &sl.w_read_primary, &sl.w_scan_tmp, &sl.w_totals, &sl.r_read_rec_begin,
+                        &sl.r_status, &sl.r_rseg, &sl.r_cseg, &sl.r_tid, &sl.r_pos, &sl.r_mapq, &sl.r_flag, &sl.r_bin, &sl.r_flip,
+                        &sl.r_cigar_begin, &sl.r_cigar})
+            b->release();
+        for (HBuf* b : {&sl.h_read_rec_begin, &sl.h_status, &sl.h_rseg, &sl.h_cseg, &sl.h_tid, &sl.h_pos, &sl.h_mapq, &sl.h_flag,
+                        &sl.h_bin, &sl.h_flip, &sl.h_cigar_begin, &sl.h_cigar, &sl.h_totals})
+            b->release();
+        if (sl.have_events)
+            for (auto& e : sl.ev.e) cudaEventDestroy(e);
+        if (sl.stream) cudaStreamDestroy(sl.stream);
+    }
+    for (DBuf* b : {&ctx->s_ref, &ctx->s_chrom_off, &ctx->s_contig_seg_begin, &ctx->s_contig_len, &ctx->s_contig_rev_off, &ctx->s_rev_pool,
+                    &ctx->s_so_start, &ctx->s_so_end, &ctx->s_chrom, &ctx->s_pos, &ctx->s_is_fwd, &ctx->s_mapq, &ctx->s_cigar_begin,
+                    &ctx->s_cigar, &ctx->s_tab_begin, &ctx->s_table})
+        b->release();
+    if (ctx->setup_stream) cudaStreamDestroy(ctx->setup_stream);
+    delete ctx;
+}
+
+const char* ptl_last_error(const ptl_ctx* ctx) { return ctx ? ctx->err.c_str() : ""; }
+
+int ptl_set_reference(ptl_ctx* ctx, uint32_t n_chrom, const uint64_t* chrom_len, const uint8_t* const* chrom_seq) {
+    if (!ctx || (n_chrom && (!chrom_len || !chrom_seq))) return PTL_ERR_INVALID_ARG;
+    return guarded(ctx, [&]() {
+        cudaStream_t st = ctx->setup_stream;
+        // chromosomes are packed back to back (byte loads need no alignment); chrom_off[c+1]-chrom_off[c] is the exact length
+        std::vector<uint64_t> off(size_t(n_chrom) + 1, 0);
+        for (uint32_t c = 0; c < n_chrom; ++c) off[c + 1] = off[c] + chrom_len[c];
+        ctx->s_ref.ensure(std::max<uint64_t>(off[n_chrom], 16), st);
+        for (uint32_t c = 0; c < n_chrom; ++c)
+            if (chrom_len[c]) CK(cudaMemcpyAsync(ctx->s_ref.as<uint8_t>() + off[c], chrom_seq[c], chrom_len[c], cudaMemcpyHostToDevice, st));
+        ctx->S.ref = ctx->s_ref.as<uint8_t>();
+        ctx->S.chrom_off = upload(ctx->s_chrom_off, off.data(), size_t(n_chrom) + 1, st);
+        ctx->S.n_chrom = n_chrom;
+        CK(cudaStreamSynchronize(st));
+        ctx->have_reference = true;
+        return PTL_OK;
+    });
+}
+
+int ptl_set_contig_segments(ptl_ctx* ctx, const ptl_contig_segments* segs) {
+    if (!ctx || !segs) return PTL_ERR_INVALID_ARG;
+    return guarded(ctx, [&]() {
+        auto contigs = contigs_from_flat(*segs);
+        install_segments(ctx, contigs);
+        return PTL_OK;
+    });
+}
+int ptl_set_raw_contig_segments(ptl_ctx* ctx, const ptl_contig_segments* raw) {
+    if (!ctx || !raw) return PTL_ERR_INVALID_ARG;
+    return guarded(ctx, [&]() {
+        auto contigs = contigs_from_flat(*raw);
+        trim_repeated_matches(contigs);
+        join_colinear(contigs);
+        install_segments(ctx, contigs);
+        return PTL_OK;
+    });
+}
+int ptl_set_contig_records(ptl_ctx* ctx, const ptl_contig_records* recs) {
+    if (!ctx || !recs) return PTL_ERR_INVALID_ARG;
+    return guarded(ctx, [&]() {
+        auto contigs = assemble_from_records(*recs);
+        trim_repeated_matches(contigs);
+        join_colinear(contigs);
+        install_segments(ctx, contigs);
+        return PTL_OK;
+    });
+}
+int ptl_get_contig_segments(const ptl_ctx* ctx, ptl_contig_segments* out) {
+    if (!ctx || !out || !ctx->have_segments) return PTL_ERR_INVALID_ARG;
+    ctx->flat.view(out);
+    return PTL_OK;
+}
+int ptl_get_segment_table(ptl_ctx* ctx, uint32_t segment, uint32_t cap, uint32_t* keys, int32_t* vals, uint32_t* n) {
+    if (!ctx || !n || !ctx->have_segments || segment >= ctx->S.n_segments) return PTL_ERR_INVALID_ARG;
+    return guarded(ctx, [&]() {
+        const uint32_t t0 = ctx->h_tab_begin[segment], t1 = ctx->h_tab_begin[segment + 1];
+        *n = t1 - t0;
+        if (*n > cap) return int(PTL_ERR_INVALID_ARG);
+        std::vector<int2> tmp(*n);
+        if (*n) CK(cudaMemcpy(tmp.data(), ctx->s_table.as<int2>() + t0, size_t(*n) * sizeof(int2), cudaMemcpyDeviceToHost));
+        for (uint32_t i = 0; i < *n; ++i) {
+            keys[i] = uint32_t(tmp[i].x);
+            vals[i] = tmp[i].y;
+        }
+        return int(PTL_OK);
+    });
+}
+
+int ptl_lift_upload(ptl_ctx* ctx, int slot, const ptl_batch* batch) {
+    Slot* sl = get_slot(ctx, slot);
+    if (!sl || !batch) return PTL_ERR_INVALID_ARG;
+    return guarded(ctx, [&]() {
+        if (!ctx->have_segments) throw std::runtime_error("ptl_set_contig_segments / ptl_set_contig_records has not been called");
+        upload_batch(ctx, *sl, batch);
+        return PTL_OK;
+    });
+}
+int ptl_lift_run(ptl_ctx* ctx, int slot, uint32_t stage_mask) {
+    Slot* sl = get_slot(ctx, slot);
+    if (!sl) return PTL_ERR_INVALID_ARG;
+    if (!sl->uploaded) return fail(ctx, PTL_ERR_STATE, "ptl_lift_run without ptl_lift_upload");
+    return guarded(ctx, [&]() {
+        run_batch(ctx, *sl, stage_mask);
+        return PTL_OK;
+    });
+}
+int ptl_lift_download(ptl_ctx* ctx, int slot, ptl_result* out) {
+    Slot* sl = get_slot(ctx, slot);
+    if (!sl || !out) return PTL_ERR_INVALID_ARG;
+    if (!sl->ran) return fail(ctx, PTL_ERR_STATE, "ptl_lift_download / ptl_lift_wait without a submitted batch");
+    return guarded(ctx, [&]() { return download(ctx, *sl, out); });
+}
+int ptl_lift_submit_ex(ptl_ctx* ctx, int slot, const ptl_batch* batch, uint32_t stage_mask) {
+    Slot* sl = get_slot(ctx, slot);
+    if (!sl || !batch) return PTL_ERR_INVALID_ARG;
+    return guarded(ctx, [&]() {
+        if (!ctx->have_segments) throw std::runtime_error("ptl_set_contig_segments / ptl_set_contig_records has not been called");
+        upload_batch(ctx, *sl, batch);
+        run_batch(ctx, *sl, stage_mask);
+        return PTL_OK;
+    });
+}
+int ptl_lift_submit(ptl_ctx* ctx, int slot, const ptl_batch* batch) { return ptl_lift_submit_ex(ctx, slot, batch, PTL_STAGE_ALL); }
+int ptl_lift_wait(ptl_ctx* ctx, int slot, ptl_result* out) { return ptl_lift_download(ctx, slot, out); }
+
+void* ptl_slot_stream(ptl_ctx* ctx, int slot) {
+    Slot* sl = get_slot(ctx, slot);
+    return sl ? static_cast<void*>(sl->stream) : nullptr;
+}
+int ptl_slot_kernel_times(ptl_ctx* ctx, int slot, int cap, const char** names, float* ms) {
+    Slot* sl = get_slot(ctx, slot);
+    if (!sl || !sl->ran || !sl->have_events) return 0;
+    static const char* kNames[] = {"enumerate_pairs", "lift_pairs", "finalize_emit"};
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(sl->stream);
+    int n = 0;
+    for (int i = 0; i + 1 < StageEvents::N && n < cap; ++i, ++n) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, sl->ev.e[i], sl->ev.e[i + 1]) != cudaSuccess) { cudaGetLastError(); t = -1.f; }
+        names[n] = kNames[i];
+        ms[n] = t;
+    }
+    return n;
+}
+uint64_t ptl_launch_count(const ptl_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int ptl_set_seq_zero_copy(ptl_ctx* ctx, int enable) {
+    if (!ctx) return PTL_ERR_INVALID_ARG;
+    ctx->zero_copy_seq = enable != 0;
+    return PTL_OK;
+}
+// Counters of the last finished batch on a slot: out[0..6) = n_pairs, n_lifted, n_in_ops, n_out_ops, base bytes compared,
+// scratch ops needed (roofline arithmetic).
+int ptl_slot_counters(ptl_ctx* ctx, int slot, uint64_t* out) {
+    Slot* sl = get_slot(ctx, slot);
+    if (!sl || !out || !sl->ran) return PTL_ERR_INVALID_ARG;
+    return guarded(ctx, [&]() {
+        finish_batch(ctx, *sl);
+        const DevTotals& t = sl->totals;
+        out[0] = t.n_pairs; out[1] = t.n_lifted; out[2] = t.n_in_ops; out[3] = t.n_cigar_out; out[4] = t.n_base_bytes; out[5] = t.scratch_needed;
+        return PTL_OK;
+    });
+}
+
+void* ptl_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void ptl_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+}  // extern "C"

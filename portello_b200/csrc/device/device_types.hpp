@@ -1,0 +1,113 @@
+// Device-side data model shared by the kernels (kernels.cu) and the host orchestration (context.cu).
+// Layout rationale is in DESIGN.md §3 ("Data layout in HBM").
+#pragma once
+#include <cstdint>
+
+namespace ptl {
+
+// ---- static, read-only state (replicated per GPU): reference, contigs, segment tables ------------------------
+struct DevStatic {
+    // reference genome, ASCII, chromosomes concatenated (ptl_set_reference)
+    const uint8_t* ref = nullptr;
+    const uint64_t* chrom_off = nullptr;  // [n_chrom+1]
+    uint32_t n_chrom = 0;
+    // contigs
+    uint32_t n_contigs = 0;
+    const uint32_t* contig_seg_begin = nullptr;  // [n_contigs+1]
+    const uint64_t* contig_len = nullptr;        // [n_contigs]
+    const uint64_t* contig_rev_off = nullptr;    // [n_contigs] offset into rev_pool, ~0 = None
+    const uint8_t* rev_pool = nullptr;           // rev_contig_seq bytes, ASCII
+    // contig->ref segments (post trim/join), SoA
+    uint32_t n_segments = 0;
+    const uint32_t* seg_so_start = nullptr;
+    const uint32_t* seg_so_end = nullptr;
+    const int32_t* seg_chrom = nullptr;
+    const int64_t* seg_pos = nullptr;
+    const uint8_t* seg_is_fwd = nullptr;
+    const uint8_t* seg_mapq = nullptr;
+    const uint64_t* seg_cigar_begin = nullptr;   // [n_segments+1]
+    const uint32_t* seg_cigar = nullptr;
+    // flat ReadToRefTreeMap: per segment a sorted run of (key = contig read_pos, val = ref pos or -1 for None)
+    const uint32_t* seg_tab_begin = nullptr;     // [n_segments+1]
+    const int2* table = nullptr;
+};
+
+// ---- one batch on the device ------------------------------------------------------------------------------------
+struct DevBatch {
+    uint32_t n_reads = 0, n_rsegs = 0;
+    uint64_t n_cigar = 0;
+    const uint16_t* read_flag = nullptr;
+    const uint8_t* read_mapq = nullptr;
+    const uint16_t* read_bin = nullptr;
+    const uint32_t* read_seq_len = nullptr;
+    const uint64_t* read_seq_off = nullptr;
+    const uint32_t* read_seg_begin = nullptr;
+    const uint32_t* rseg_contig = nullptr;
+    const int64_t* rseg_pos = nullptr;
+    const uint8_t* rseg_is_fwd = nullptr;
+    const uint64_t* rseg_cigar_begin = nullptr;
+    const uint32_t* rseg_cigar_len = nullptr;
+    const uint32_t* cigar = nullptr;
+    const uint8_t* seq4 = nullptr;  // device copy, or a mapped pinned host pointer in zero-copy mode
+};
+
+// ---- per-batch work arrays ---------------------------------------------------------------------------------------
+struct DevWork {
+    // per read segment
+    uint32_t* rseg_read = nullptr;       // owning read
+    uint32_t* rseg_pair_begin = nullptr; // [n_rsegs+1] (count, then exclusive scan in place)
+    int64_t* rseg_ref_len = nullptr;     // get_cigar_ref_offset of the segment
+    // per pair
+    uint32_t pair_cap = 0;
+    uint32_t* pair_rseg = nullptr;
+    uint32_t* pair_seg = nullptr;        // global contig-segment index
+    uint64_t* pair_slot_begin = nullptr; // [pair_cap+1] (bound, then exclusive scan in place) ops of scratch
+    int8_t* pair_status = nullptr;
+    uint8_t* pair_flip = nullptr;
+    int64_t* pair_pos = nullptr;
+    uint32_t* pair_n_out = nullptr;
+    uint64_t* pair_out_off = nullptr;    // where the final ops of the pair start in scratch
+    // scratch op slots
+    uint64_t scratch_cap = 0;            // in ops
+    uint32_t* scratch = nullptr;
+    // per read
+    uint2* read_counts = nullptr;        // [n_reads+1] (.x records, .y ops) -> exclusive scan
+    uint32_t* read_primary = nullptr;    // pair index chosen as primary, ~0 if none lifted
+};
+
+// ---- result pools on the device (mirrors ptl_result) ------------------------------------------------------------
+struct DevResult {
+    uint32_t rec_cap = 0;
+    uint64_t cigar_cap = 0;
+    uint32_t* read_rec_begin = nullptr;  // [n_reads+1]
+    int8_t* rec_status = nullptr;
+    uint32_t* rec_read_segment = nullptr;
+    uint32_t* rec_contig_segment = nullptr;
+    int32_t* rec_tid = nullptr;
+    int64_t* rec_pos = nullptr;
+    uint8_t* rec_mapq = nullptr;
+    uint16_t* rec_flag = nullptr;
+    uint16_t* rec_bin = nullptr;
+    uint8_t* rec_need_flip = nullptr;
+    uint64_t* rec_cigar_begin = nullptr; // [rec_cap+1]
+    uint32_t* cigar = nullptr;
+};
+
+// ---- totals / flags written by the kernels, read back once per batch ---------------------------------------------
+struct DevTotals {
+    unsigned long long n_pairs;
+    unsigned long long scratch_needed;   // ops
+    unsigned long long n_records;
+    unsigned long long n_cigar_out;
+    unsigned long long n_lifted;
+    unsigned long long n_errors;
+    long long first_error_read;          // min read index with an error, or INT64_MAX
+    int first_error_status;
+    unsigned int overflow;               // bit0 pairs, bit1 scratch, bit2 records, bit3 cigar pool
+    unsigned long long n_in_ops;         // sum of input CIGAR ops over attempted pairs   (roofline arithmetic)
+    unsigned long long n_base_bytes;     // base bytes compared (both operands)            (roofline arithmetic)
+};
+
+enum : unsigned { OVF_PAIRS = 1, OVF_SCRATCH = 2, OVF_RECORDS = 4, OVF_CIGAR = 8 };
+
+}  // namespace ptl

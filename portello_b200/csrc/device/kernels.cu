@@ -1,0 +1,517 @@
+// CUDA kernels of the liftover path (sm_100a).  Launch wrappers at the bottom (kernels.hpp).
+//
+// Per batch:   pair_count -> scan -> pair_fill -> scan -> lift_pairs -> read_finalize -> scan -> emit_records
+// Once:        table_count -> scan -> table_fill   (flat ReadToRefTreeMap per contig segment)
+//
+// This is HBM/latency-bound integer work: no tensor cores.  Grids are sized from the work (>> 148 SMs x resident CTAs
+// for real batches); scratch traffic is thread-private and stays in L1/L2.
+#include <cuda_runtime.h>
+
+#include "kernels.hpp"
+#include "lift_device.cuh"
+
+namespace ptl {
+
+// =================================================================================================== scans
+namespace {
+
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 4;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ uint32_t shfl_up_t(uint32_t v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
+__device__ __forceinline__ uint64_t shfl_up_t(uint64_t v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
+__device__ __forceinline__ uint2 shfl_up_t(uint2 v, int d) {
+    return make_uint2(__shfl_up_sync(0xffffffffu, v.x, d), __shfl_up_sync(0xffffffffu, v.y, d));
+}
+__device__ __forceinline__ uint32_t add_t(uint32_t a, uint32_t b) { return a + b; }
+__device__ __forceinline__ uint64_t add_t(uint64_t a, uint64_t b) { return a + b; }
+__device__ __forceinline__ uint2 add_t(uint2 a, uint2 b) { return make_uint2(a.x + b.x, a.y + b.y); }
+template <class T> __device__ __forceinline__ T zero_t();
+template <> __device__ __forceinline__ uint32_t zero_t<uint32_t>() { return 0u; }
+template <> __device__ __forceinline__ uint64_t zero_t<uint64_t>() { return 0ull; }
+template <> __device__ __forceinline__ uint2 zero_t<uint2>() { return make_uint2(0u, 0u); }
+
+// Exclusive scan of one tile per block, in place; block totals to sums[blockIdx] (if sums != nullptr).
+template <class T>
+__global__ void __launch_bounds__(SCAN_THREADS) scan_tile_kernel(T* a, uint64_t n, T* sums) {
+    __shared__ T warp_tot[SCAN_THREADS / 32];
+    const uint64_t base = uint64_t(blockIdx.x) * SCAN_TILE + uint64_t(threadIdx.x) * SCAN_ITEMS;
+    T v[SCAN_ITEMS];
+    T run = zero_t<T>();
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        v[k] = (base + k < n) ? a[base + k] : zero_t<T>();
+        run = add_t(run, v[k]);
+    }
+    // inclusive warp scan of per-thread totals
+    T inc = run;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        T o = shfl_up_t(inc, d);
+        if (lane >= d) inc = add_t(inc, o);
+    }
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    T warp_off = zero_t<T>();
+    T block_tot = zero_t<T>();
+#pragma unroll
+    for (int w = 0; w < SCAN_THREADS / 32; ++w) {
+        if (w < warp) warp_off = add_t(warp_off, warp_tot[w]);
+        block_tot = add_t(block_tot, warp_tot[w]);
+    }
+    T o = shfl_up_t(inc, 1);
+    T excl = add_t(warp_off, lane ? o : zero_t<T>());
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        if (base + k < n) a[base + k] = excl;
+        excl = add_t(excl, v[k]);
+    }
+    if (sums && threadIdx.x == 0) sums[blockIdx.x] = block_tot;
+}
+
+template <class T>
+__global__ void __launch_bounds__(SCAN_THREADS) scan_add_kernel(T* a, uint64_t n, const T* sums) {
+    const T off = sums[blockIdx.x];
+    const uint64_t base = uint64_t(blockIdx.x) * SCAN_TILE + uint64_t(threadIdx.x) * SCAN_ITEMS;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k)
+        if (base + k < n) a[base + k] = add_t(a[base + k], off);
+}
+
+}  // namespace
+
+template <class T>
+void exclusive_scan_inplace(T* a, uint64_t n, void* tmp, size_t tmp_bytes, cudaStream_t st, uint64_t* launches) {
+    if (n == 0) return;
+    const uint64_t blocks = (n + SCAN_TILE - 1) / SCAN_TILE;
+    if (blocks == 1) {
+        scan_tile_kernel<T><<<1, SCAN_THREADS, 0, st>>>(a, n, nullptr);
+        ++*launches;
+        return;
+    }
+    T* sums = static_cast<T*>(tmp);
+    const size_t used = ((blocks * sizeof(T)) + 255) & ~size_t(255);
+    scan_tile_kernel<T><<<unsigned(blocks), SCAN_THREADS, 0, st>>>(a, n, sums);
+    ++*launches;
+    exclusive_scan_inplace<T>(sums, blocks, static_cast<char*>(tmp) + used, tmp_bytes - used, st, launches);
+    scan_add_kernel<T><<<unsigned(blocks), SCAN_THREADS, 0, st>>>(a, n, sums);
+    ++*launches;
+}
+template void exclusive_scan_inplace<uint32_t>(uint32_t*, uint64_t, void*, size_t, cudaStream_t, uint64_t*);
+template void exclusive_scan_inplace<uint64_t>(uint64_t*, uint64_t, void*, size_t, cudaStream_t, uint64_t*);
+template void exclusive_scan_inplace<uint2>(uint2*, uint64_t, void*, size_t, cudaStream_t, uint64_t*);
+
+size_t scan_tmp_bytes(uint64_t n) {
+    size_t total = 0;
+    while (n > uint64_t(SCAN_TILE)) {
+        n = (n + SCAN_TILE - 1) / SCAN_TILE;
+        total += ((n * 16) + 255) & ~size_t(255);
+    }
+    return total + 256;
+}
+
+// =================================================================================================== segment tables
+// a7: get_read_segment_to_ref_pos_tree_map (lib/rust-vc-utils/src/bam_utils/read_to_ref_map.rs:101-137), flattened.
+// A run of M/=/X ops (any other op ends it) with total length > 0 yields (run_start_read_pos -> run_start_ref_pos) and
+// (run_end_read_pos -> None); the None is overwritten when the next run starts at the same read_pos (:111-119).
+// One thread per segment walks its CIGAR; `out == nullptr` counts.  Built once per run.
+namespace {
+__global__ void table_build_kernel(DevStatic S, uint32_t* counts, int2* out) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= S.n_segments) return;
+    const uint32_t* c = S.seg_cigar + S.seg_cigar_begin[g];
+    const uint32_t n = uint32_t(S.seg_cigar_begin[g + 1] - S.seg_cigar_begin[g]);
+    int64_t ref_pos = S.seg_pos[g];
+    uint64_t read_pos = 0, match_len = 0;
+    uint32_t w = 0;
+    int2* o = out ? out + S.seg_tab_begin[g] : nullptr;
+    // The overwrite decision must not depend on reading `out` (the count pass has none): track the last None key.
+    uint32_t last_key = 0xffffffffu;
+    bool have_last = false;
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t x = c[i];
+        if (op_is_match(x & 0xfu)) {
+            match_len += x >> 4;
+        } else if (match_len > 0) {
+            const uint32_t k0 = uint32_t(read_pos - match_len);
+            if (have_last && last_key == k0) --w;
+            if (o) { o[w] = make_int2(int(k0), int32_t(ref_pos - int64_t(match_len))); }
+            ++w;
+            if (o) { o[w] = make_int2(int(uint32_t(read_pos)), -1); }
+            ++w;
+            last_key = uint32_t(read_pos);
+            have_last = true;
+            match_len = 0;
+        }
+        ref_pos += op_ref_adv(x);
+        read_pos += op_read_adv(x);
+    }
+    if (match_len > 0) {
+        const uint32_t k0 = uint32_t(read_pos - match_len);
+        if (have_last && last_key == k0) --w;
+        if (o) { o[w] = make_int2(int(k0), int32_t(ref_pos - int64_t(match_len))); }
+        ++w;
+        if (o) { o[w] = make_int2(int(uint32_t(read_pos)), -1); }
+        ++w;
+    }
+    if (!out) counts[g] = w;
+}
+}  // namespace
+
+void launch_table_build(const DevStatic& S, uint32_t* counts, int2* out, cudaStream_t st) {
+    if (!S.n_segments) return;
+    table_build_kernel<<<(S.n_segments + 127) / 128, 128, 0, st>>>(S, counts, out);
+}
+
+// =================================================================================================== per-batch kernels
+namespace {
+
+// a3 (count): get_contig_split_segments_from_read_mapping (src/read_alignment_scanner.rs:80-103) + get_cigar_ref_offset.
+// One thread per read walks its 1..k split segments.
+__global__ void __launch_bounds__(128) pair_count_kernel(DevStatic S, DevBatch B, DevWork W) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= B.n_reads) {
+        if (r == B.n_reads) W.rseg_pair_begin[B.n_rsegs] = 0;
+        return;
+    }
+    for (uint32_t s = B.read_seg_begin[r]; s < B.read_seg_begin[r + 1]; ++s) {
+        W.rseg_read[s] = r;
+        const uint32_t* c = B.cigar + B.rseg_cigar_begin[s];
+        const uint32_t n = B.rseg_cigar_len[s];
+        int64_t ref_len = 0;
+        for (uint32_t i = 0; i < n; ++i) ref_len += op_ref_adv(c[i]);
+        W.rseg_ref_len[s] = ref_len;
+        const int64_t start = B.rseg_pos[s], end = start + ref_len;
+        const uint32_t ctg = B.rseg_contig[s];
+        uint32_t cnt = 0;
+        for (uint32_t g = S.contig_seg_begin[ctg]; g < S.contig_seg_begin[ctg + 1]; ++g) {
+            // IntRange::intersect_range with the segment as `self`: other.end >= self.start && other.start < self.end
+            if (end >= int64_t(S.seg_so_start[g]) && start < int64_t(S.seg_so_end[g])) ++cnt;
+        }
+        W.rseg_pair_begin[s] = cnt;
+    }
+}
+
+__device__ __forceinline__ uint32_t lower_bound_key(const int2* tab, uint32_t lo, uint32_t hi, int64_t key) {
+    while (lo < hi) {  // first index with tab.key >= key
+        const uint32_t mid = (lo + hi) >> 1;
+        if (int64_t(uint32_t(tab[mid].x)) < key) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+// a3 (fill): pair list in (read segment, contig segment index) order + the scratch-slot bound of each pair.
+__global__ void __launch_bounds__(128) pair_fill_kernel(DevStatic S, DevBatch B, DevWork W, DevTotals* T) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= B.n_rsegs) {
+        if (s == B.n_rsegs) {
+            const uint32_t np = W.rseg_pair_begin[B.n_rsegs];
+            T->n_pairs = np;
+            if (np > W.pair_cap) atomicOr(&T->overflow, OVF_PAIRS);
+            else W.pair_slot_begin[np] = 0;
+        }
+        return;
+    }
+    uint32_t p = W.rseg_pair_begin[s];
+    const uint32_t p_end = W.rseg_pair_begin[s + 1];
+    if (p == p_end) return;
+    const int64_t start = B.rseg_pos[s], ref_len = W.rseg_ref_len[s], end = start + ref_len;
+    const uint32_t ctg = B.rseg_contig[s];
+    const uint32_t n_in = B.rseg_cigar_len[s];
+    for (uint32_t g = S.contig_seg_begin[ctg]; g < S.contig_seg_begin[ctg + 1]; ++g) {
+        if (!(end >= int64_t(S.seg_so_start[g]) && start < int64_t(S.seg_so_end[g]))) continue;
+        if (p < W.pair_cap) {
+            W.pair_rseg[p] = s;
+            W.pair_seg[p] = g;
+            // contig interval walked by the liftover, in the orientation of the segment's table
+            const bool fwd = S.seg_is_fwd[g] != 0;
+            const int64_t a = fwd ? start : int64_t(S.contig_len[ctg]) - end;
+            const uint32_t t0 = S.seg_tab_begin[g], t1 = S.seg_tab_begin[g + 1];
+            const uint32_t n_keys = lower_bound_key(S.table, t0, t1, a + ref_len) - lower_bound_key(S.table, t0, t1, a);
+            // op-slot bounds: shift <= 2 n_in + 1; lifted <= 3 n_shift + 2 n_keys + 4; simplified <= 2 lifted.
+            const uint64_t n_shift = fwd ? uint64_t(n_in) : 2ull * n_in + 1ull;
+            const uint64_t cap_b = 3ull * n_shift + 2ull * n_keys + 4ull;
+            W.pair_slot_begin[p] = 3ull * cap_b;  // [0,cap_b) = buffer B, [cap_b, 3 cap_b) = buffer A
+        }
+        ++p;
+    }
+}
+
+// a4 + a5 + a6 + a8 + a9: get_liftover_alignment_for_read_and_contig_segment (src/read_alignment_scanner.rs:136-288),
+// one thread per pair.
+__global__ void __launch_bounds__(128) lift_pairs_kernel(DevStatic S, DevBatch B, DevWork W, DevTotals* T, uint32_t stage_mask) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n_pairs = min(uint32_t(T->n_pairs), W.pair_cap);
+    uint32_t n_in_ops = 0;
+    PairCounters cnt;
+    if (p < n_pairs) {
+        const uint32_t s = W.pair_rseg[p], g = W.pair_seg[p], r = W.rseg_read[s];
+        const uint64_t slot0 = W.pair_slot_begin[p], slot1 = W.pair_slot_begin[p + 1];
+        int status = ST_NONE;
+        int64_t out_pos = 0;
+        uint32_t n_out = 0;
+        uint64_t out_off = slot0;
+        const bool contig_fwd = S.seg_is_fwd[g] != 0;
+        const bool rec_rev = (B.read_flag[r] & 0x10) != 0;
+        const bool changes_strand = (rec_rev == (B.rseg_is_fwd[s] != 0));
+        const bool need_flip = (!contig_fwd) != changes_strand;
+        if (slot1 > W.scratch_cap) {
+            atomicOr(&T->overflow, OVF_SCRATCH);
+            status = ST_ERR_CAPACITY;
+        } else {
+            const uint32_t cap_b = uint32_t((slot1 - slot0) / 3);
+            uint32_t* buf_b = W.scratch + slot0;
+            uint32_t* buf_a = buf_b + cap_b;
+            const uint32_t cap_a = 2 * cap_b;
+            const uint32_t ctg = B.rseg_contig[s];
+            const uint32_t seq_len = B.read_seq_len[r];
+            const ReadBases read{B.seq4 + B.read_seq_off[r], seq_len, need_flip};
+            OpSource cur{B.cigar + B.rseg_cigar_begin[s], B.rseg_cigar_len[s], false};
+            n_in_ops = cur.n;
+            int64_t pos = B.rseg_pos[s];
+            int err = 0;
+            bool cur_is_a = false, cur_is_raw = true;
+            status = ST_LIFTED;
+            if (!contig_fwd) {
+                // reverse-strand contig segment: flip onto the contig's reverse strand, then left-shift there (:162-176)
+                pos = int64_t(S.contig_len[ctg]) - (pos + W.rseg_ref_len[s]);
+                cur.reversed = true;
+                if (stage_mask & 1u) {
+                    const uint64_t rev_off = S.contig_rev_off[ctg];
+                    if (rev_off == ~0ull) {
+                        err = ST_ERR_BOUNDS;  // Option::unwrap on None (:174)
+                    } else {
+                        OpSink sink(buf_a, cap_a);
+                        pos = run_left_shift(cur, pos, S.rev_pool + rev_off, S.contig_len[ctg], read, sink, cnt, err);
+                        if (sink.overflow) err = ST_ERR_CAPACITY;
+                        cur = OpSource{buf_a, sink.n, false};
+                        cur_is_a = true;
+                        cur_is_raw = false;
+                    }
+                }
+            }
+            if (!err && (stage_mask & 2u)) {
+                OpSink sink(buf_b, cap_b);
+                int64_t lifted_pos = 0;
+                const bool some = run_liftover(cur, pos, S.table, S.seg_tab_begin[g], S.seg_tab_begin[g + 1], sink, &lifted_pos);
+                if (sink.overflow) err = ST_ERR_CAPACITY;
+                else if (!some) status = ST_NONE;
+                else if (sink.read_len != uint64_t(seq_len)) err = ST_ERR_LENGTH;  // :204-229
+                pos = lifted_pos;
+                cur = OpSource{buf_b, sink.n, false};
+                cur_is_a = false;
+                cur_is_raw = false;
+            }
+            if (!err && status == ST_LIFTED && (stage_mask & 4u)) {
+                const int32_t chrom = S.seg_chrom[g];
+                const uint8_t* ref = S.ref + S.chrom_off[chrom];
+                const uint64_t ref_len = S.chrom_off[chrom + 1] - S.chrom_off[chrom];
+                uint32_t* dst = cur_is_a ? buf_b : buf_a;
+                const uint32_t dcap = cur_is_a ? cap_b : cap_a;
+                // raw input in reversed order is only possible in stage tests (no shift, no liftover); copy semantics hold
+                OpSink sink(dst, dcap);
+                pos = run_simplify(cur, pos, ref, ref_len, read, sink, cnt, err);
+                if (sink.overflow) err = ST_ERR_CAPACITY;
+                cur = OpSource{dst, sink.n, false};
+                cur_is_a = !cur_is_a;
+                cur_is_raw = false;
+            }
+            if (!err && status == ST_LIFTED && cur_is_raw) {
+                // stage tests with every stage disabled for this pair: hand the (possibly reversed) input back verbatim
+                for (uint32_t i = 0; i < cur.n && i < cap_a; ++i) buf_a[i] = cur.get(i);
+                cur = OpSource{buf_a, min(cur.n, cap_a), false};
+            }
+            if (err) status = err;
+            if (status == ST_LIFTED) {
+                n_out = cur.n;
+                out_off = uint64_t(cur.p - W.scratch);
+                out_pos = pos;
+            }
+        }
+        W.pair_status[p] = int8_t(status);
+        W.pair_flip[p] = need_flip;
+        W.pair_pos[p] = out_pos;
+        W.pair_n_out[p] = n_out;
+        W.pair_out_off[p] = out_off;
+    }
+    // roofline arithmetic: input ops walked + base bytes compared (warp-aggregated atomics)
+    uint32_t a = n_in_ops, b = cnt.base_bytes;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        a += __shfl_down_sync(0xffffffffu, a, d);
+        b += __shfl_down_sync(0xffffffffu, b, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (a) atomicAdd(&T->n_in_ops, (unsigned long long)a);
+        if (b) atomicAdd(&T->n_base_bytes, (unsigned long long)b);
+    }
+}
+
+// a10 (field part): finish_remapped_alignment_set (src/read_alignment_scanner.rs:310-366): record counts per read,
+// primary = first max MAPQ (:338-346), unmapped fallback when nothing lifted (:317-335).  One thread per read.
+__global__ void __launch_bounds__(128) read_finalize_kernel(DevStatic S, DevBatch B, DevWork W, DevTotals* T, int do_finish) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= B.n_reads) {
+        if (r == B.n_reads) W.read_counts[B.n_reads] = make_uint2(0u, 0u);
+        return;
+    }
+    const uint32_t s0 = B.read_seg_begin[r], s1 = B.read_seg_begin[r + 1];
+    const uint32_t p0 = W.rseg_pair_begin[s0], p1 = min(W.rseg_pair_begin[s1], W.pair_cap);
+    uint32_t lifted = 0, ops = 0, primary = 0xffffffffu;
+    int best_mapq = -1, first_err = 0;
+    for (uint32_t p = p0; p < p1; ++p) {
+        const int st = W.pair_status[p];
+        if (st < 0) { if (!first_err) first_err = st; continue; }
+        if (st != ST_LIFTED) continue;
+        ++lifted;
+        ops += W.pair_n_out[p];
+        const int mq = S.seg_mapq[W.pair_seg[p]];
+        if (mq > best_mapq) { best_mapq = mq; primary = p; }
+    }
+    if (first_err) {
+        // the reference panics here; report, and emit the unmapped fallback so the batch stays well-formed
+        atomicAdd(&T->n_errors, 1ull);
+        const long long packed = (static_cast<long long>(r) << 8) | (first_err & 0xff);
+        atomicMin(&T->first_error_read, packed);
+        lifted = 0; ops = 0; primary = 0xffffffffu;
+    }
+    atomicAdd(&T->n_lifted, (unsigned long long)lifted);
+    uint32_t n_rec = lifted;
+    if (lifted == 0 && do_finish) n_rec = 1;
+    if (!do_finish) primary = 0xffffffffu - 1u;  // stage tests: no primary is chosen, no fallback
+    W.read_counts[r] = make_uint2(n_rec, ops);
+    W.read_primary[r] = (lifted == 0) ? 0xffffffffu : primary;
+}
+
+// Record assembly: one warp per read. Lane 0 writes the SoA fields, all lanes copy CIGAR ops from the scratch slots
+// into the dense pool (coalesced both ways) and reduce the reference span for end / bin (:278-279).
+__global__ void __launch_bounds__(256) emit_records_kernel(DevStatic S, DevBatch B, DevWork W, DevResult R, DevTotals* T,
+                                                            uint32_t stage_mask) {
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (warp >= B.n_reads) return;
+    const uint32_t r = warp;
+    const uint2 base = W.read_counts[r];
+    const uint2 next = W.read_counts[r + 1];
+    const uint2 total = W.read_counts[B.n_reads];
+    if (r == 0 && lane == 0) {
+        T->n_records = total.x;
+        T->n_cigar_out = total.y;
+        if (total.x > R.rec_cap) atomicOr(&T->overflow, OVF_RECORDS);
+        if (total.y > R.cigar_cap) atomicOr(&T->overflow, OVF_CIGAR);
+    }
+    if (total.x > R.rec_cap || total.y > R.cigar_cap) return;
+    if (lane == 0) {
+        R.read_rec_begin[r] = base.x;
+        if (r == B.n_reads - 1) {
+            R.read_rec_begin[B.n_reads] = total.x;
+            R.rec_cigar_begin[total.x] = total.y;
+        }
+    }
+    const uint32_t n_rec = next.x - base.x;
+    if (n_rec == 0) return;
+    const uint16_t flag0 = B.read_flag[r];
+    const uint32_t primary = W.read_primary[r];
+    const uint32_t s0 = B.read_seg_begin[r], s1 = B.read_seg_begin[r + 1];
+    if (primary == 0xffffffffu) {  // unmapped fallback (:317-335)
+        if (lane == 0) {
+            const uint32_t k = base.x;
+            uint16_t f = uint16_t((flag0 | 0x4) & ~0x800);
+            uint8_t flip = 0;
+            if (f & 0x10) { f ^= 0x10; flip = 1; }
+            R.rec_status[k] = 0;
+            R.rec_read_segment[k] = s0;
+            R.rec_contig_segment[k] = 0xffffffffu;
+            R.rec_tid[k] = -1;
+            R.rec_pos[k] = -1;
+            R.rec_mapq[k] = 255;
+            R.rec_flag[k] = f;
+            R.rec_bin[k] = B.read_bin[r];
+            R.rec_need_flip[k] = flip;
+            R.rec_cigar_begin[k] = base.y;
+        }
+        return;
+    }
+    const uint32_t p0 = W.rseg_pair_begin[s0], p1 = min(W.rseg_pair_begin[s1], W.pair_cap);
+    uint32_t k = base.x;
+    uint64_t op_at = base.y;
+    for (uint32_t p = p0; p < p1; ++p) {
+        if (W.pair_status[p] != ST_LIFTED) continue;
+        const uint32_t n = W.pair_n_out[p];
+        const uint32_t* src = W.scratch + W.pair_out_off[p];
+        uint32_t ref_span = 0;
+        for (uint32_t i = lane; i < n; i += 32) {
+            const uint32_t c = src[i];
+            R.cigar[op_at + i] = c;
+            ref_span += op_ref_adv(c);
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) ref_span += __shfl_down_sync(0xffffffffu, ref_span, d);
+        if (lane == 0) {
+            const uint32_t g = W.pair_seg[p], s = W.pair_rseg[p];
+            const uint32_t ctg = B.rseg_contig[s];
+            const int64_t pos = W.pair_pos[p];
+            const uint8_t flip = W.pair_flip[p];
+            uint16_t f = uint16_t(flag0 ^ (flip ? 0x10 : 0));
+            f |= 0x800;
+            if (p == primary) f &= ~0x800;
+            R.rec_status[k] = 1;
+            R.rec_read_segment[k] = s;
+            R.rec_contig_segment[k] = g - S.contig_seg_begin[ctg];
+            R.rec_tid[k] = (stage_mask & 2u) ? S.seg_chrom[g] : -2;
+            R.rec_pos[k] = pos;
+            R.rec_mapq[k] = S.seg_mapq[g];
+            R.rec_flag[k] = f;
+            R.rec_bin[k] = reg2bin(pos, pos + int64_t(ref_span));
+            R.rec_need_flip[k] = flip;
+            R.rec_cigar_begin[k] = op_at;
+        }
+        ++k;
+        op_at += n;
+    }
+}
+
+__global__ void totals_init_kernel(DevTotals* T) {
+    T->n_pairs = 0; T->scratch_needed = 0; T->n_records = 0; T->n_cigar_out = 0; T->n_lifted = 0; T->n_errors = 0;
+    T->first_error_read = 0x7fffffffffffffffLL; T->first_error_status = 0; T->overflow = 0; T->n_in_ops = 0; T->n_base_bytes = 0;
+}
+__global__ void scratch_needed_kernel(DevWork W, DevTotals* T) {
+    const uint32_t np = min(uint32_t(T->n_pairs), W.pair_cap);
+    T->scratch_needed = W.pair_slot_begin[np];
+}
+
+}  // namespace
+
+void launch_lift(const DevStatic& S, const DevBatch& B, const DevWork& W, const DevResult& R, DevTotals* T, uint32_t stage_mask,
+                 void* scan_tmp, size_t scan_tmp_bytes_, cudaStream_t st, uint64_t* launches, StageEvents* ev) {
+    auto mark = [&](int i) { if (ev) cudaEventRecord(ev->e[i], st); };
+    const int do_finish = (stage_mask == 7u);
+    mark(0);
+    totals_init_kernel<<<1, 1, 0, st>>>(T);
+    ++*launches;
+    if (B.n_reads == 0) { for (int i = 1; i < StageEvents::N; ++i) mark(i); return; }
+    pair_count_kernel<<<(B.n_reads + 1 + 127) / 128, 128, 0, st>>>(S, B, W);
+    ++*launches;
+    exclusive_scan_inplace<uint32_t>(W.rseg_pair_begin, uint64_t(B.n_rsegs) + 1, scan_tmp, scan_tmp_bytes_, st, launches);
+    pair_fill_kernel<<<(B.n_rsegs + 1 + 127) / 128, 128, 0, st>>>(S, B, W, T);
+    ++*launches;
+    // the pair count is only known on the device: scan / launch over the capacity, kernels clamp to n_pairs
+    exclusive_scan_inplace<uint64_t>(W.pair_slot_begin, uint64_t(W.pair_cap) + 1, scan_tmp, scan_tmp_bytes_, st, launches);
+    scratch_needed_kernel<<<1, 1, 0, st>>>(W, T);
+    ++*launches;
+    mark(1);
+    lift_pairs_kernel<<<(W.pair_cap + 127) / 128, 128, 0, st>>>(S, B, W, T, stage_mask);
+    ++*launches;
+    mark(2);
+    read_finalize_kernel<<<(B.n_reads + 1 + 127) / 128, 128, 0, st>>>(S, B, W, T, do_finish);
+    ++*launches;
+    exclusive_scan_inplace<uint2>(W.read_counts, uint64_t(B.n_reads) + 1, scan_tmp, scan_tmp_bytes_, st, launches);
+    emit_records_kernel<<<(uint64_t(B.n_reads) * 32 + 255) / 256, 256, 0, st>>>(S, B, W, R, T, stage_mask);
+    ++*launches;
+    mark(3);
+}
+
+}  // namespace ptl

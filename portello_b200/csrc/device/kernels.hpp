@@ -1,0 +1,28 @@
+// Launch wrappers of the CUDA kernels (kernels.cu) used by the host orchestration (context.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdint>
+
+#include "device_types.hpp"
+
+namespace ptl {
+
+// CUDA events bracketing the stages of one launch_lift: [0] start, [1] pairs enumerated, [2] pairs lifted, [3] records emitted
+struct StageEvents {
+    static constexpr int N = 4;
+    cudaEvent_t e[N];
+};
+
+template <class T>
+void exclusive_scan_inplace(T* a, uint64_t n, void* tmp, size_t tmp_bytes, cudaStream_t st, uint64_t* launches);
+size_t scan_tmp_bytes(uint64_t n);
+
+// counts != nullptr, out == nullptr : count table entries per segment; then (after a scan into S.seg_tab_begin) fill `out`.
+void launch_table_build(const DevStatic& S, uint32_t* counts, int2* out, cudaStream_t st);
+
+void launch_lift(const DevStatic& S, const DevBatch& B, const DevWork& W, const DevResult& R, DevTotals* T, uint32_t stage_mask,
+                 void* scan_tmp, size_t scan_tmp_bytes, cudaStream_t st, uint64_t* launches, StageEvents* ev);
+
+}  // namespace ptl

@@ -1,0 +1,398 @@
+// Host packer + small host helpers of the product library (no CUDA in this file).
+//
+//   ptl_pack_split_segments / ptl_pack_batch : a2 — parse_sa_aux_val (lib/rust-vc-utils/src/bam_utils/aux/sa_tag_parser.rs:25-59)
+//        + get_seq_order_read_split_segments (lib/rust-vc-utils/src/bam_utils/split_read.rs:56-155), and the record
+//        filter of scan_chromosome_segment (src/read_alignment_scanner.rs:396-406).
+//   ptl_format_sa_tags : a10 text part (src/read_alignment_scanner.rs:292-301,349-363)
+//   ptl_region_segments / ptl_shard_units : a13 work units (lib/rust-vc-utils/src/util.rs:50-67) + LPT sharding
+//   ptl_reg2bin : lib/rust-vc-utils/src/bam_utils/util.rs:10-35
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <unordered_map>
+
+#include "../../../include/portello_b200.h"
+#include "host_util.hpp"
+
+using namespace ptl;
+
+namespace {
+
+thread_local std::string g_pack_err;
+
+struct Seg {
+    uint32_t so_start, so_end, contig;
+    int64_t pos;
+    uint8_t is_fwd, mapq, from_primary;
+    uint32_t cig_off, cig_len;  // into a scratch pool
+};
+
+// strict decimal parse of [b,e) as Rust's str::parse would: optional sign, >=1 digit, nothing else
+bool parse_i64(const char* b, const char* e, int64_t& out) {
+    if (b == e) return false;
+    bool neg = false;
+    if (*b == '+' || *b == '-') { neg = (*b == '-'); ++b; }
+    if (b == e) return false;
+    int64_t v = 0;
+    for (; b != e; ++b) {
+        if (*b < '0' || *b > '9') return false;
+        if (v > (INT64_MAX - 9) / 10) return false;
+        v = v * 10 + (*b - '0');
+    }
+    out = neg ? -v : v;
+    return true;
+}
+
+// CIGAR text -> ops appended to pool; false on syntax error (rust_htslib CigarString::try_from fails -> unwrap panic)
+bool parse_cigar_text(const char* b, const char* e, Ops& pool) {
+    static const char ops[] = "MIDNSHP=X";
+    uint64_t n = 0;
+    bool have = false;
+    for (; b != e; ++b) {
+        if (*b >= '0' && *b <= '9') {
+            n = n * 10 + uint64_t(*b - '0');
+            if (n > 0x0fffffffull) return false;
+            have = true;
+        } else {
+            const char* p = static_cast<const char*>(std::memchr(ops, *b, 9));
+            if (!p || !have) return false;
+            pool.push_back(mk(uint32_t(p - ops), n));
+            n = 0;
+            have = false;
+        }
+    }
+    return !have;
+}
+
+// Resolve contig names lazily: the map is built once per pack call.
+struct NameMap {
+    std::unordered_map<std::string, uint32_t> m;
+    NameMap(uint32_t n, const char* const* names) {
+        m.reserve(n * 2);
+        for (uint32_t i = 0; i < n; ++i) m.emplace(names[i], i);
+    }
+};
+
+// The segments of one primary record, sequencing order. `pool` receives SA CIGARs; the primary's CIGAR is referenced
+// as (prim_off, n_cigar) in the caller's own pool and flagged by from_primary.
+void split_segments(const NameMap& names, int32_t tid, int64_t pos, uint16_t flag, uint8_t mapq, const uint32_t* cigar,
+                    uint32_t n_cigar, const char* sa, std::vector<Seg>& segs, Ops& pool) {
+    segs.clear();
+    const bool rev = flag & 0x10;
+    const ClipPos pc = clip_positions(cigar, n_cigar);
+    auto seq_order = [](const ClipPos& c, bool fwd, uint32_t& s, uint32_t& e) {
+        if (fwd) { s = uint32_t(c.left); e = uint32_t(c.right); }
+        else { s = uint32_t(c.size - c.right); e = uint32_t(c.size - c.left); }
+    };
+    Seg p{};
+    seq_order(pc, !rev, p.so_start, p.so_end);
+    p.contig = uint32_t(tid);
+    p.pos = pos;
+    p.is_fwd = !rev;
+    p.mapq = mapq;
+    p.from_primary = 1;
+    p.cig_off = 0;
+    p.cig_len = n_cigar;
+    segs.push_back(p);
+    if (sa) {
+        const char* s = sa;
+        const char* end = sa + std::strlen(sa);
+        while (s < end) {
+            const char* semi = static_cast<const char*>(std::memchr(s, ';', size_t(end - s)));
+            const char* seg_end = semi ? semi : end;
+            // split_terminator(','): a trailing empty field is dropped
+            const char* f[8];
+            const char* fe[8];
+            int nf = 0;
+            const char* q = s;
+            while (true) {
+                const char* comma = static_cast<const char*>(std::memchr(q, ',', size_t(seg_end - q)));
+                if (!comma) {
+                    if (q < seg_end) { if (nf < 8) { f[nf] = q; fe[nf] = seg_end; } ++nf; }
+                    break;
+                }
+                if (nf < 8) { f[nf] = q; fe[nf] = comma; }
+                ++nf;
+                q = comma + 1;
+            }
+            if (nf != 6) throw InputError("Unexpected segment in bam SA tag: " + std::string(s, seg_end));
+            int64_t sa_pos, sa_mapq, sa_nm;
+            if (!parse_i64(f[1], fe[1], sa_pos)) throw InputError("SA tag: bad position");
+            const bool fwd = (fe[2] - f[2] == 1 && *f[2] == '+');
+            const uint32_t off = uint32_t(pool.size());
+            if (!parse_cigar_text(f[3], fe[3], pool)) throw InputError("SA tag: bad CIGAR");
+            if (!parse_i64(f[4], fe[4], sa_mapq) || sa_mapq < 0 || sa_mapq > 255) throw InputError("SA tag: bad MAPQ");
+            if (!parse_i64(f[5], fe[5], sa_nm) || sa_nm < INT32_MIN || sa_nm > INT32_MAX) throw InputError("SA tag: bad NM");
+            const uint32_t len = uint32_t(pool.size()) - off;
+            bool aligned = false;
+            for (uint32_t i = 0; i < len; ++i) aligned |= is_match(pool[off + i]);
+            if (!aligned) throw InputError("Bam record split segment is unaligned");  // split_read.rs:107-110
+            const ClipPos c = clip_positions(pool.data() + off, len);
+            if (c.size != pc.size) throw InputError("SA segment read size differs from the primary record");  // :113
+            auto it = names.m.find(std::string(f[0], fe[0]));
+            if (it == names.m.end()) throw InputError("SA tag describes a split read mapped to an unknown contig: " + std::string(f[0], fe[0]));
+            Seg g{};
+            seq_order(c, fwd, g.so_start, g.so_end);
+            g.contig = it->second;
+            g.pos = sa_pos - 1;
+            g.is_fwd = fwd;
+            g.mapq = uint8_t(sa_mapq);
+            g.from_primary = 0;
+            g.cig_off = off;
+            g.cig_len = len;
+            segs.push_back(g);
+            s = semi ? semi + 1 : end;
+        }
+        std::stable_sort(segs.begin(), segs.end(), [](const Seg& a, const Seg& b) { return a.so_start < b.so_start; });  // :140
+    }
+    for (const Seg& g : segs)
+        if (g.so_start >= g.so_end) throw InputError("Can't parse consistent split read information from SA tag");  // :145-152
+}
+
+size_t align_up(size_t x) { return (x + 255) & ~size_t(255); }
+
+}  // namespace
+
+struct ptl_packed_batch {
+    void* arena = nullptr;
+    bool pinned = false;
+    ptl_batch view{};
+    std::vector<uint32_t> record_index;  // batch read -> index into the source records
+    uint32_t n_skipped_supplementary = 0;
+};
+
+extern "C" {
+
+const char* ptl_pack_last_error(void) { return g_pack_err.c_str(); }
+
+int ptl_pack_split_segments(uint32_t n_names, const char* const* contig_names, int32_t tid, int64_t pos, uint16_t flag,
+                            uint8_t mapq, const uint32_t* cigar, uint32_t n_cigar, const char* sa_tag, uint32_t cap_segments,
+                            uint32_t cap_cigar, ptl_split_segments* out, uint32_t* n_segments, uint32_t* n_cigar_out) {
+    if (!out || !n_segments || !n_cigar_out) return PTL_ERR_INVALID_ARG;
+    try {
+        NameMap names(n_names, contig_names);
+        std::vector<Seg> segs;
+        Ops pool;
+        split_segments(names, tid, pos, flag, mapq, cigar, n_cigar, sa_tag, segs, pool);
+        size_t total = 0;
+        for (const Seg& g : segs) total += g.cig_len;
+        *n_segments = uint32_t(segs.size());
+        *n_cigar_out = uint32_t(total);
+        if (segs.size() > cap_segments || total > cap_cigar) return PTL_ERR_INVALID_ARG;
+        uint32_t w = 0;
+        for (size_t i = 0; i < segs.size(); ++i) {
+            const Seg& g = segs[i];
+            out->seq_order_start[i] = g.so_start;
+            out->seq_order_end[i] = g.so_end;
+            out->contig[i] = g.contig;
+            out->pos[i] = g.pos;
+            out->is_fwd[i] = g.is_fwd;
+            out->mapq[i] = g.mapq;
+            out->from_primary[i] = g.from_primary;
+            out->cigar_begin[i] = w;
+            const uint32_t* src = g.from_primary ? cigar : pool.data() + g.cig_off;
+            std::memcpy(out->cigar + w, src, size_t(g.cig_len) * 4);
+            w += g.cig_len;
+        }
+        out->cigar_begin[segs.size()] = w;
+        return PTL_OK;
+    } catch (const InputError& e) {
+        g_pack_err = e.what();
+        return PTL_ERR_INPUT;
+    }
+}
+
+int ptl_pack_batch(const ptl_read_records* recs, uint32_t first, uint32_t count, uint32_t n_contigs,
+                   const char* const* contig_names, int pinned, ptl_packed_batch** out) {
+    if (!recs || !out || uint64_t(first) + count > recs->n_reads) return PTL_ERR_INVALID_ARG;
+    try {
+        NameMap names(n_contigs, contig_names);
+        // pass 1: parse SA tags (rare), collect segment lists
+        std::vector<Seg> segs, tmp;
+        std::vector<uint32_t> seg_begin{0}, kept;
+        Ops sa_pool;
+        const uint64_t cig0 = recs->cigar_begin[first], cig1 = recs->cigar_begin[first + count];
+        uint32_t skipped = 0;
+        for (uint32_t r = first; r < first + count; ++r) {
+            const uint16_t flag = recs->flag[r];
+            if (flag & 0x4) throw InputError("unmapped record in the mapped read scan (assert, read_alignment_scanner.rs:396)");
+            if (flag & 0x800) { ++skipped; continue; }  // supplementary records are skipped (:404)
+            const uint32_t* cg = recs->cigar + recs->cigar_begin[r];
+            const uint32_t ncg = uint32_t(recs->cigar_begin[r + 1] - recs->cigar_begin[r]);
+            const char* sa = recs->sa_tag ? recs->sa_tag[r] : nullptr;
+            const uint32_t pool_before = uint32_t(sa_pool.size());
+            split_segments(names, recs->tid[r], recs->pos[r], flag, recs->mapq[r], cg, ncg, sa, tmp, sa_pool);
+            for (Seg g : tmp) {
+                // rebase CIGAR offsets into the batch pool: [record cigars of the slice][SA cigars]
+                if (g.from_primary) g.cig_off = uint32_t(recs->cigar_begin[r] - cig0);
+                else g.cig_off = uint32_t(cig1 - cig0) + g.cig_off;
+                segs.push_back(g);
+            }
+            (void)pool_before;
+            seg_begin.push_back(uint32_t(segs.size()));
+            kept.push_back(r);
+        }
+        const uint32_t n = uint32_t(kept.size()), ns = uint32_t(segs.size());
+        const uint64_t n_cig = (cig1 - cig0) + sa_pool.size();
+        // one arena for all small arrays
+        size_t off = 0;
+        auto take = [&](size_t bytes) { const size_t o = off; off = align_up(off + bytes); return o; };
+        const size_t o_flag = take(n * 2), o_mapq = take(n), o_bin = take(n * 2), o_len = take(n * 4), o_soff = take(n * 8),
+                     o_sb = take((n + 1) * 4), o_ctg = take(ns * 4), o_pos = take(ns * 8), o_fwd = take(ns), o_cb = take(ns * 8),
+                     o_cl = take(ns * 4), o_cig = take(n_cig * 4);
+        auto* pb = new ptl_packed_batch();
+        pb->pinned = pinned != 0;
+        pb->arena = pinned ? ptl_host_alloc(std::max<size_t>(off, 256)) : std::malloc(std::max<size_t>(off, 256));
+        if (!pb->arena) {
+            delete pb;
+            g_pack_err = pinned ? "pinned allocation failed (no CUDA device?)" : "out of memory";
+            return PTL_ERR_CUDA;
+        }
+        char* a = static_cast<char*>(pb->arena);
+        auto* flag = reinterpret_cast<uint16_t*>(a + o_flag);
+        auto* mapq = reinterpret_cast<uint8_t*>(a + o_mapq);
+        auto* bin = reinterpret_cast<uint16_t*>(a + o_bin);
+        auto* slen = reinterpret_cast<uint32_t*>(a + o_len);
+        auto* soff = reinterpret_cast<uint64_t*>(a + o_soff);
+        auto* sb = reinterpret_cast<uint32_t*>(a + o_sb);
+        auto* ctg = reinterpret_cast<uint32_t*>(a + o_ctg);
+        auto* pos = reinterpret_cast<int64_t*>(a + o_pos);
+        auto* fwd = reinterpret_cast<uint8_t*>(a + o_fwd);
+        auto* cb = reinterpret_cast<uint64_t*>(a + o_cb);
+        auto* cl = reinterpret_cast<uint32_t*>(a + o_cl);
+        auto* cig = reinterpret_cast<uint32_t*>(a + o_cig);
+        for (uint32_t i = 0; i < n; ++i) {
+            const uint32_t r = kept[i];
+            flag[i] = recs->flag[r];
+            mapq[i] = recs->mapq[r];
+            bin[i] = recs->bin[r];
+            slen[i] = recs->seq_len[r];
+            soff[i] = recs->seq_off[r];
+        }
+        std::memcpy(sb, seg_begin.data(), size_t(n + 1) * 4);
+        for (uint32_t k = 0; k < ns; ++k) {
+            ctg[k] = segs[k].contig;
+            pos[k] = segs[k].pos;
+            fwd[k] = segs[k].is_fwd;
+            cb[k] = segs[k].cig_off;
+            cl[k] = segs[k].cig_len;
+        }
+        if (cig1 > cig0) std::memcpy(cig, recs->cigar + cig0, size_t(cig1 - cig0) * 4);
+        if (!sa_pool.empty()) std::memcpy(cig + (cig1 - cig0), sa_pool.data(), sa_pool.size() * 4);
+        ptl_batch& v = pb->view;
+        v.n_reads = n;
+        v.read_flag = flag; v.read_mapq = mapq; v.read_bin = bin; v.read_seq_len = slen; v.read_seq_off = soff;
+        v.read_seg_begin = sb;
+        v.n_read_segments = ns;
+        v.rseg_contig = ctg; v.rseg_pos = pos; v.rseg_is_fwd = fwd; v.rseg_cigar_begin = cb; v.rseg_cigar_len = cl;
+        v.cigar = cig;
+        v.n_cigar = n_cig;
+        v.seq4 = recs->seq4;  // borrowed
+        v.seq4_bytes = recs->seq4_bytes;
+        pb->record_index = std::move(kept);
+        pb->n_skipped_supplementary = skipped;
+        *out = pb;
+        return PTL_OK;
+    } catch (const InputError& e) {
+        g_pack_err = e.what();
+        return PTL_ERR_INPUT;
+    }
+}
+void ptl_packed_batch_view(const ptl_packed_batch* p, ptl_batch* out) { *out = p->view; }
+const uint32_t* ptl_packed_batch_record_index(const ptl_packed_batch* p) { return p->record_index.data(); }
+void ptl_packed_batch_free(ptl_packed_batch* p) {
+    if (!p) return;
+    if (p->arena) { if (p->pinned) ptl_host_free(p->arena); else std::free(p->arena); }
+    delete p;
+}
+
+int ptl_format_sa_tags(const ptl_result* res, uint32_t n_chrom, const char* const* chrom_names, char* buf, uint64_t cap,
+                       uint64_t* sa_begin, uint64_t* need) {
+    if (!res || !need) return PTL_ERR_INVALID_ARG;
+    static const char opc[] = "MIDNSHP=X";
+    std::string all;
+    std::vector<std::string> seg;
+    std::vector<uint64_t> begin;
+    begin.reserve(size_t(res->n_records) + 1);
+    for (uint32_t r = 0; r < res->n_reads; ++r) {
+        const uint32_t k0 = res->read_rec_begin[r], k1 = res->read_rec_begin[r + 1];
+        seg.clear();
+        const bool lifted = !(k1 - k0 == 1 && res->rec_status[k0] != PTL_REC_LIFTED);
+        if (lifted) {
+            for (uint32_t k = k0; k < k1; ++k) {  // get_sa_tag_segment, :292-301
+                const int32_t tid = res->rec_tid[k];
+                if (tid < 0 || uint32_t(tid) >= n_chrom) return PTL_ERR_INVALID_ARG;
+                std::string s = chrom_names[tid];
+                s += ',';
+                s += std::to_string(res->rec_pos[k] + 1);
+                s += (res->rec_flag[k] & 0x10) ? ",-," : ",+,";
+                for (uint64_t c = res->rec_cigar_begin[k]; c < res->rec_cigar_begin[k + 1]; ++c) {
+                    s += std::to_string(len_of(res->cigar[c]));
+                    s += opc[op_of(res->cigar[c])];
+                }
+                s += ',';
+                s += std::to_string(unsigned(res->rec_mapq[k]));
+                s += ",0;";
+                seg.push_back(std::move(s));
+            }
+        }
+        for (uint32_t k = k0; k < k1; ++k) {  // :349-363
+            begin.push_back(all.size());
+            if (lifted)
+                for (uint32_t j = k0; j < k1; ++j)
+                    if (j != k) all += seg[j - k0];
+            all.push_back('\0');
+        }
+    }
+    begin.push_back(all.size());
+    *need = all.size();
+    if (all.size() > cap || !buf || !sa_begin) return PTL_ERR_INVALID_ARG;
+    std::memcpy(buf, all.data(), all.size());
+    std::memcpy(sa_begin, begin.data(), begin.size() * sizeof(uint64_t));
+    return PTL_OK;
+}
+
+uint32_t ptl_region_segment_count(uint64_t size, uint64_t segment_size) {
+    if (!size || !segment_size) return 0;
+    return uint32_t(1 + (size - 1) / segment_size);
+}
+void ptl_region_segments(uint64_t size, uint64_t segment_size, uint64_t* begin, uint64_t* end) {
+    const uint64_t count = ptl_region_segment_count(size, segment_size);
+    if (!count) return;
+    const uint64_t base = size / count, extra = size % count;
+    uint64_t start = 0;
+    for (uint64_t i = 0; i < count; ++i) {
+        const uint64_t e = std::min(start + base + (i < extra ? 1 : 0), size);
+        begin[i] = start;
+        end[i] = e;
+        start = e;
+    }
+}
+void ptl_shard_units(uint32_t n_units, const uint64_t* weight, uint32_t n_ranks, uint32_t* owner) {
+    if (!n_ranks) return;
+    std::vector<uint32_t> order(n_units);
+    std::iota(order.begin(), order.end(), 0u);
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return weight[a] > weight[b]; });
+    std::vector<uint64_t> load(n_ranks, 0);
+    for (uint32_t u : order) {
+        const uint32_t r = uint32_t(std::min_element(load.begin(), load.end()) - load.begin());  // lowest rank wins ties
+        owner[u] = r;
+        load[r] += weight[u];
+    }
+}
+
+uint16_t ptl_reg2bin(int64_t begin, int64_t end) {
+    const uint64_t b = uint64_t(begin), e = uint64_t(end) - 1;
+    uint32_t shift = 14;
+    uint32_t offset = ((1u << 15) - 1) / 7;
+    for (int level = 5; level > 0; --level) {
+        if ((b >> shift) == (e >> shift)) return uint16_t(offset + (b >> shift));
+        shift += 3;
+        offset -= 1u << ((level - 1) * 3);
+    }
+    return 0;
+}
+
+}  // extern "C"
