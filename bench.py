@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""bench.py — read alignments lifted per second on B200 (BASELINE.json metric), next to the CPU path.
+
+A "step" is one pass of the liftover hot path over one synthetic batch: BASELINE.json configs[1]
+(chr20-scale: 64 Mb reference, ~40 contig->ref alignments carrying SVs, 1,000,000 HiFi reads) per GPU.
+
+  value     device-resident throughput: the batch is already in HBM, K x ptl_lift_run timed with CUDA events on the
+            library's stream (pair enumeration -> lift -> finalize -> record emission), max over ranks.
+  e2e       the same work through the public C-ABI call a host makes (ptl_lift_submit / ptl_lift_wait) from pinned HOST
+            buffers, H2D and D2H inside the timed region, pipelined over 3 slots.
+  roofline  lift_pairs kernel: algorithmic bytes / its CUDA-event duration vs MEASURED_PEAKS.json HBM GB/s.
+  cpu_baseline  the oracle (CPU restatement of the reference) on a bounded sample, all host threads.
+
+`--impl reference` times the oracle instead (the reference is Rust and cannot be built in this image).
+Multi-GPU: one process per GPU (torchrun), weak scaling, reads shard by contig set with no collective on the data path;
+torch.distributed (NCCL) is used only for the barrier and the max-over-ranks reduction of the timings.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "read alignments lifted/sec"
+UNIT = "alignments/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default="chr20")
+    ap.add_argument("--reads", type=int, default=0, help="override reads per GPU (default: the workload's own)")
+    ap.add_argument("--chunk", type=int, default=131072, help="reads per submitted batch in the e2e pipeline")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the cpu_baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--zero-copy", default="auto", choices=["auto", "on", "off"])
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.rows, self.p = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.idx)],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def stop(self):
+        if self.p:
+            self.p.terminate()
+            try:
+                self.p.wait(timeout=2)
+            except Exception:
+                self.p.kill()
+
+    def summary(self, windows):
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for t, r in self.rows:
+            if not any(a <= t <= b for a, b in windows) or len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1]))
+                mx = max(mx, float(r[2]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if r[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def algorithmic_bytes(cnt, n_table_entries, n_segments):
+    """sum_p [32 + 4 n_in + s + 16 + 4 n_out] (+ 8 T + 24 C once per run, reported separately)."""
+    per_pairs = 48 * cnt["n_pairs"] + 4 * cnt["n_in_ops"] + cnt["base_bytes"] + 4 * cnt["n_out_ops"]
+    return per_pairs, 8 * n_table_entries + 24 * n_segments
+
+
+def oracle_ctx_for(s, threads, faithful=True):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers
+
+    return helpers.oracle_context(s, threads=threads, faithful=faithful)
+
+
+def time_oracle(octx, batch_c, reps=1):
+    from portello_b200 import abi
+    import oracle_lib
+
+    O = oracle_lib.load()
+    best, pairs = None, 0
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        rc = O._lift_submit(octx.h, 0, C.byref(batch_c))
+        r = abi.ResultC()
+        rc2 = O._lift_wait(octx.h, 0, C.byref(r))
+        dt = time.perf_counter() - t0
+        assert rc == 0 and rc2 == 0, (rc, rc2)
+        pairs = int(r.n_pairs)
+        best = dt if best is None else min(best, dt)
+    return best, pairs
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the CPU restatement of the reference on all host threads (rank 0 only)."""
+    if rank != 0:
+        return
+    from portello_b200 import lib, synth
+
+    kw = {}
+    n_sample = args.cpu_sample or 100_000
+    kw["n_reads"] = min(args.reads or synth.WORKLOADS[args.workload]["n_reads"], n_sample)
+    s = synth.make(args.workload, **kw)
+    threads = os.cpu_count() or 1
+    octx = oracle_ctx_for(s, threads, faithful=True)
+    pb = lib.PackedBatch(lib.load(), s.read_records, 0, s.read_records.n_reads, s.contig_names)
+    for _ in range(args.warmup):
+        time_oracle(octx, pb.c)
+    times, pairs = [], 0
+    for _ in range(args.steps):
+        dt, pairs = time_oracle(octx, pb.c)
+        times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    value = pairs / (ms / 1e3)
+    sample = f"{pb.c.n_reads} reads ({pairs} pairs) of the {args.workload} workload per step"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+        "config": {"workload": f"{args.workload} (BASELINE.json configs[1] shape), bounded sample", "reads_per_step": int(pb.c.n_reads)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": sample + "; oracle = C++ restatement of portello's path incl. its per-pair read decode (faithful_decode)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from portello_b200 import abi, lib, synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the liftover path has no CPU fallback (use --impl reference for the CPU oracle)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    L = lib.load(build_if_missing=False)
+    # ---- data: every rank owns a different contig set (seed + rank) of the same shape: weak scaling, no exchange
+    kw = {"seed": synth.WORKLOADS[args.workload]["seed"] + rank}
+    if args.reads:
+        kw["n_reads"] = args.reads
+    t0 = time.time()
+    alloc = C.cast(L.dll.ptl_host_alloc, C.c_void_p)
+    free = C.cast(L.dll.ptl_host_free, C.c_void_p)
+    s = synth.make(args.workload, host_alloc=alloc, host_free=free, **kw)  # packed bases generated into pinned, mapped memory
+    t_gen = time.time() - t0
+    n_reads = s.read_records.n_reads
+
+    ctx = lib.GpuContext(local_rank, n_slots=3)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers
+
+    ctx.set_reference(helpers.reference_arrays(s))
+    ctx.set_contig_records(s.contig_records)
+    segs = ctx.get_contig_segments()
+    n_segments = len(segs.seg_pos)
+    n_table = sum(len(ctx.get_segment_table(g)[0]) for g in range(n_segments))
+
+    whole = lib.PackedBatch(L, s.read_records, 0, n_reads, s.contig_names, pinned=True)
+    chunks = [lib.PackedBatch(L, s.read_records, a, min(args.chunk, n_reads - a), s.contig_names, pinned=True)
+              for a in range(0, n_reads, args.chunk)]
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    windows = []
+
+    # ---------------------------------------------------------------- value: device-resident
+    stream = torch.cuda.ExternalStream(ctx.stream(0), device=torch.device("cuda", local_rank))
+    ctx.upload(whole.c, 0)
+    for _ in range(max(args.warmup, 3)):
+        ctx.run(0)
+    cnt = ctx.counters(0)  # syncs; also settles buffer capacities (a capacity re-run can only happen here)
+    ctx.run(0)
+    ctx.counters(0)
+    barrier()
+    launches0 = ctx.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.time()
+    ev0.record(stream)
+    lift_ms = []
+    for _ in range(args.steps):
+        ctx.run(0)
+    ev1.record(stream)
+    ev1.synchronize()
+    barrier()
+    w1 = time.time()
+    windows.append((w0, w1))
+    launches_value = ctx.launch_count() - launches0
+    dev_ms = ev0.elapsed_time(ev1) / args.steps
+    kt = ctx.kernel_times(0)  # CUDA events around the stages of the LAST timed run, on the library's stream
+    cnt = ctx.counters(0)
+    # per-stage times averaged over a few extra (untimed for `value`) runs, each bracketed by its own events
+    stage_acc = {}
+    for _ in range(min(args.steps, 5)):
+        ctx.run(0)
+        for k, v in ctx.kernel_times(0).items():
+            stage_acc.setdefault(k, []).append(v)
+    stage_ms = {k: float(np.mean(v)) for k, v in stage_acc.items()}
+    dev_ms_max = max_over_ranks(dev_ms)
+    pairs_total = sum_over_ranks(float(cnt["n_pairs"]))
+    value = pairs_total / (dev_ms_max / 1e3)
+
+    # ---------------------------------------------------------------- parity spot check (outside every timed region)
+    parity = "skipped"
+    if rank == 0:
+        sub = lib.PackedBatch(L, s.read_records, n_reads // 3, min(4000, n_reads - n_reads // 3), s.contig_names)
+        rg = helpers.lift_c(ctx, sub.c, slot=1)
+        ro = helpers.lift_c(helpers.oracle_context(s, threads=min(8, os.cpu_count() or 1)), sub.c)
+        d = rg.diff(ro)
+        if d is not None:
+            raise SystemExit(f"PARITY FAILURE vs oracle on the bench workload: {d}")
+        parity = f"bit-exact vs oracle on {sub.c.n_reads} reads of this workload"
+
+    # ---------------------------------------------------------------- e2e: host buffers -> records on the host
+    def e2e_step():
+        n_slots = 3
+        inflight = [None] * n_slots
+        recs = 0
+        for i, ch in enumerate(chunks):
+            sl = i % n_slots
+            if inflight[sl] is not None:
+                recs += ctx.wait_c(sl).n_records
+            ctx.submit_c(ch.c, sl)
+            inflight[sl] = ch
+        for k in range(n_slots):
+            sl = (len(chunks) + k) % n_slots
+            if inflight[sl] is not None:
+                recs += ctx.wait_c(sl).n_records
+                inflight[sl] = None
+        return recs
+
+    def measure_e2e(zero_copy):
+        ctx.set_seq_zero_copy(zero_copy)
+        for _ in range(max(args.warmup, 3)):
+            e2e_step()
+        barrier()
+        l0 = ctx.launch_count()
+        t0 = time.time()
+        p0 = time.perf_counter()
+        for _ in range(args.steps):
+            n_rec = e2e_step()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - p0) / args.steps
+        barrier()
+        windows.append((t0, time.time()))
+        return dt, n_rec, ctx.launch_count() - l0
+
+    small_h2d = sum(int(ch.c.n_reads) * (2 + 1 + 2 + 4 + 8 + 4) + int(ch.c.n_read_segments) * (4 + 8 + 1 + 8 + 4) + int(ch.c.n_cigar) * 4 for ch in chunks)
+    seq_h2d = sum(int(ch.c.seq4_bytes) for ch in chunks)
+    e2e_runs = {}
+    modes = {"auto": [False, True], "on": [True], "off": [False]}[args.zero_copy]
+    for zc in modes:
+        dt, n_rec, nl = measure_e2e(zc)
+        e2e_runs[zc] = (max_over_ranks(dt), n_rec, nl)
+    best_zc = min(e2e_runs, key=lambda k: e2e_runs[k][0])
+    e2e_dt, n_rec, launches_e2e = e2e_runs[best_zc]
+    d2h = int(n_rec) * (1 + 4 + 4 + 4 + 8 + 1 + 2 + 2 + 1 + 8) + int(cnt["n_out_ops"]) * 4 + (n_reads + 1) * 4
+    e2e_value = pairs_total / e2e_dt
+    sampler.stop()
+
+    # ---------------------------------------------------------------- roofline of the dominant kernel
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "B200_PROFILING.md fallback 6.65 TB/s"
+    alg_bytes, table_bytes = algorithmic_bytes(cnt, n_table, n_segments)
+    lift_ms_avg = stage_ms.get("lift_pairs", float("nan"))
+    achieved = alg_bytes / (lift_ms_avg / 1e3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "lift_pairs_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg_bytes), "table_bytes_once": int(table_bytes),
+                "kernel_ms": lift_ms_avg, "stage_ms": stage_ms,
+                "whole_step_frac": alg_bytes / (dev_ms / 1e3) / 1e9 / peak}
+
+    # ---------------------------------------------------------------- CPU baseline (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        n_sample = args.cpu_sample or min(n_reads, max(20_000, 2500 * threads))
+        sub = lib.PackedBatch(L, s.read_records, 0, n_sample, s.contig_names)
+        octx = helpers.oracle_context(s, threads=threads, faithful=True)
+        time_oracle(octx, sub.c)
+        dt, pairs = time_oracle(octx, sub.c, reps=3)
+        octx1 = helpers.oracle_context(s, threads=threads, faithful=False)
+        dt_lean, _ = time_oracle(octx1, sub.c, reps=3)
+        cpu = {"value": pairs / dt, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"first {n_sample} reads ({pairs} pairs) of this workload, best of 3; oracle = C++ restatement incl. the reference's "
+                         f"per-pair read decode; without that decode (lazy base access): {pairs / dt_lean:.3e} {UNIT}"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": dev_ms_max, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: BASELINE.json configs[1] (64 Mb reference, {s.contig_records.n_records} contig alignment records -> "
+                                   f"{n_segments} segments after trim/join, {n_reads} HiFi reads per GPU)",
+                       "reads_per_gpu": int(n_reads), "pairs_per_step_per_gpu": int(cnt["n_pairs"]), "lifted_per_step_per_gpu": int(cnt["n_lifted"]),
+                       "l2_policy": "inputs larger than L2 (CIGAR pools + op scratch > 126 MB per step)", "sharding": "by contig set, no collective",
+                       "e2e_pipeline": f"{len(chunks)} batches of {args.chunk} reads over 3 slots", "e2e_seq_zero_copy": bool(best_zc),
+                       "parity": parity, "generate_s": round(t_gen, 1)},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(small_h2d + (0 if best_zc else seq_h2d)), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": e2e_dt * 1e3,
+                    "alternatives": {("seq_zero_copy" if k else "seq_bulk_upload"): {"value": pairs_total / v[0], "ms_per_step": v[0] * 1e3} for k, v in e2e_runs.items()}},
+            "gpu_launches": int(launches_value),
+            "gpu_launches_e2e": int(launches_e2e),
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "clocks": sampler.summary(windows),
+            "counters": cnt,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -263,13 +263,22 @@ int ptl_pack_batch(const ptl_read_records* recs, uint32_t first, uint32_t count,
         auto* cb = reinterpret_cast<uint64_t*>(a + o_cb);
         auto* cl = reinterpret_cast<uint32_t*>(a + o_cl);
         auto* cig = reinterpret_cast<uint32_t*>(a + o_cig);
+        // the batch lends out only the byte range of the packed-bases pool that its reads occupy
+        uint64_t seq_lo = UINT64_MAX, seq_hi = 0;
+        for (uint32_t i = 0; i < n; ++i) {
+            const uint32_t r = kept[i];
+            seq_lo = std::min(seq_lo, recs->seq_off[r]);
+            seq_hi = std::max(seq_hi, recs->seq_off[r] + (uint64_t(recs->seq_len[r]) + 1) / 2);
+        }
+        if (n == 0) seq_lo = seq_hi = 0;
+        if (seq_hi > recs->seq4_bytes) throw InputError("read bases outside the seq4 pool");
         for (uint32_t i = 0; i < n; ++i) {
             const uint32_t r = kept[i];
             flag[i] = recs->flag[r];
             mapq[i] = recs->mapq[r];
             bin[i] = recs->bin[r];
             slen[i] = recs->seq_len[r];
-            soff[i] = recs->seq_off[r];
+            soff[i] = recs->seq_off[r] - seq_lo;
         }
         std::memcpy(sb, seg_begin.data(), size_t(n + 1) * 4);
         for (uint32_t k = 0; k < ns; ++k) {
@@ -289,8 +298,8 @@ int ptl_pack_batch(const ptl_read_records* recs, uint32_t first, uint32_t count,
         v.rseg_contig = ctg; v.rseg_pos = pos; v.rseg_is_fwd = fwd; v.rseg_cigar_begin = cb; v.rseg_cigar_len = cl;
         v.cigar = cig;
         v.n_cigar = n_cig;
-        v.seq4 = recs->seq4;  // borrowed
-        v.seq4_bytes = recs->seq4_bytes;
+        v.seq4 = recs->seq4 + seq_lo;  // borrowed
+        v.seq4_bytes = seq_hi - seq_lo;
         pb->record_index = std::move(kept);
         pb->n_skipped_supplementary = skipped;
         *out = pb;

@@ -165,6 +165,7 @@ class PackedBatch:
             raise PtlError(rc, lib.dll.ptl_pack_last_error().decode())
         self.c = BatchC()
         lib.dll.ptl_packed_batch_view(self.h, C.byref(self.c))
+        self.c._owner = self  # the view must keep the arena alive (`pack(...).c` would otherwise dangle)
         self._recs = recs_c  # the batch borrows seq4
 
     def record_index(self) -> np.ndarray:

@@ -1,0 +1,154 @@
+"""Bit-exact parity of the CUDA path against the CPU oracle on seeded synthetic data, through the C-ABI."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import helpers
+from portello_b200 import abi, lib, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def both(s, stage_mask=abi.STAGE_ALL, first=0, count=None):
+    pb = helpers.pack(s, first, count)
+    octx = helpers.oracle_context(s)
+    gctx = helpers.gpu_context(s)
+    ro = helpers.lift_c(octx, pb.c, stage_mask)
+    rg = helpers.lift_c(gctx, pb.c, stage_mask)
+    return ro, rg, octx, gctx, pb
+
+
+@pytest.mark.parametrize("name,kw", [
+    ("tiny", {}),
+    ("tiny", dict(seed=11, chrom_len=3_000_000, contigs_per_chrom=3, junction_per_mb=8, n_reads=20000)),
+    ("config1", {}),
+    ("stress", dict(n_reads=1500)),
+], ids=["tiny", "tiny-junctions", "config1", "stress"])
+def test_full_path_parity(name, kw):
+    s = synth.make(name, **kw)
+    ro, rg, octx, gctx, pb = both(s)
+    assert ro.n_errors == 0
+    d = rg.diff(ro)
+    assert d is None, d
+    assert rg.n_records >= pb.c.n_reads and rg.n_lifted > 0
+    # SA:Z text built by the product's host helper from the GPU result == oracle's
+    r = abi.ResultC()
+    gctx._check(gctx.lib._lift_wait(gctx.h, 0, C.byref(r)))
+    import oracle_lib
+    O = oracle_lib.load()
+    sa_g = lib.load().format_sa_tags(r, s.chrom_names)
+    sa_o = lib.format_sa_tags_call(O.dll.ptl_oracle_format_sa_tags, r, s.chrom_names)
+    assert sa_g == sa_o
+    assert any(x for x in sa_g)
+
+
+@pytest.mark.parametrize("mask", [abi.STAGE_LEFT_SHIFT, abi.STAGE_LIFTOVER, abi.STAGE_LEFT_SHIFT | abi.STAGE_LIFTOVER,
+                                  abi.STAGE_LIFTOVER | abi.STAGE_SIMPLIFY])
+def test_stage_parity(mask):
+    s = synth.make("tiny", seed=23, n_reads=4000)
+    ro, rg, *_ = both(s, mask)
+    d = rg.diff(ro)
+    assert d is None, d
+
+
+def test_tables_match_oracle():
+    s = synth.make("tiny", seed=5, chrom_len=2_000_000, junction_per_mb=10)
+    octx = helpers.oracle_context(s)
+    gctx = helpers.gpu_context(s)
+    so, sg = octx.get_contig_segments(), gctx.get_contig_segments()
+    assert np.array_equal(so.cigar, sg.cigar) and np.array_equal(so.seg_pos, sg.seg_pos)
+    for g in range(len(so.seg_pos)):
+        ko, vo = octx.get_segment_table(g)
+        kg, vg = gctx.get_segment_table(g)
+        assert np.array_equal(ko, kg) and np.array_equal(vo, vg), g
+
+
+def test_batches_slots_and_order():
+    """Several batches in flight on different slots give the same records as one big batch, in submission order."""
+    s = synth.make("tiny", seed=31, n_reads=6000)
+    gctx = helpers.gpu_context(s, n_slots=3)
+    whole = helpers.lift_c(gctx, helpers.pack(s).c)
+    n = s.read_records.n_reads
+    cuts = [0, n // 3, 2 * n // 3, n]
+    packs = [helpers.pack(s, cuts[i], cuts[i + 1] - cuts[i]) for i in range(3)]
+    for i, p in enumerate(packs):
+        gctx._check(gctx.lib._lift_submit(gctx.h, i, C.byref(p.c)))
+    parts = []
+    for i in range(3):
+        r = abi.ResultC()
+        gctx._check(gctx.lib._lift_wait(gctx.h, i, C.byref(r)))
+        parts.append(abi.Result.from_c(r))
+    assert sum(p.n_records for p in parts) == whole.n_records
+    assert np.array_equal(np.concatenate([p.rec_pos for p in parts]), whole.rec_pos)
+    assert np.array_equal(np.concatenate([p.cigar for p in parts]), whole.cigar)
+    assert np.array_equal(np.concatenate([p.rec_flag for p in parts]), whole.rec_flag)
+
+
+def test_empty_and_degenerate_batches():
+    s = synth.make("tiny", seed=3, n_reads=500)
+    gctx = helpers.gpu_context(s)
+    octx = helpers.oracle_context(s)
+    pb = helpers.pack(s, 0, 0)
+    rg = helpers.lift_c(gctx, pb.c)
+    assert rg.n_records == 0 and rg.n_pairs == 0 and list(rg.read_rec_begin) == [0]
+    one = helpers.pack(s, 17, 1)
+    d = helpers.lift_c(gctx, one.c).diff(helpers.lift_c(octx, one.c))
+    assert d is None, d
+
+
+def test_reference_panics_are_reported_not_hidden():
+    """A read whose seq_len disagrees with its CIGAR makes the reference panic (read_alignment_scanner.rs:204-229):
+    both implementations must flag the same read with PTL_PAIR_ERR_LENGTH and keep the rest of the batch intact."""
+    s = synth.make("tiny", seed=3, n_reads=300, unmapped_contig_frac=0.0)
+    pb = helpers.pack(s)
+    b = pb.c
+    lens = np.ctypeslib.as_array(b.read_seq_len, (b.n_reads,)).copy()
+    lens[100] += 1
+    b2 = abi.BatchC.from_buffer_copy(b)
+    b2.read_seq_len = lens.ctypes.data_as(abi.u32p)
+    octx, gctx = helpers.oracle_context(s), helpers.gpu_context(s)
+    ro = helpers.lift_c(octx, b2, allow_panic=True)
+    rg = helpers.lift_c(gctx, b2, allow_panic=True)
+    assert ro.n_errors == 1 and rg.n_errors == 1
+    assert rg.first_error_read == ro.first_error_read == 100
+    assert rg.first_error_status == ro.first_error_status == -1
+    assert rg.diff(ro) is None
+
+
+def test_determinism_and_rerun_after_capacity_growth():
+    s = synth.make("tiny", seed=41, n_reads=5000)
+    gctx = helpers.gpu_context(s, n_slots=1)
+    small = helpers.lift_c(gctx, helpers.pack(s, 0, 50).c)     # sizes the work buffers for a tiny batch
+    big1 = helpers.lift_c(gctx, helpers.pack(s).c)             # forces growth
+    big2 = helpers.lift_c(gctx, helpers.pack(s).c)
+    assert big1.diff(big2) is None and small.n_records >= 50
+
+
+def test_size_independent_properties_at_scale():
+    """configs[1]-shaped data at 1/5 scale: properties that must hold at any size."""
+    s = synth.make("chr20", n_reads=200_000)
+    gctx = helpers.gpu_context(s)
+    pb = helpers.pack(s)
+    r = helpers.lift_c(gctx, pb.c)
+    b = pb.c
+    assert r.n_errors == 0                                  # lifted read length == seq_len for every pair (kernel check)
+    assert np.all(np.diff(r.read_rec_begin.astype(np.int64)) >= 1)
+    assert np.all(np.diff(r.rec_cigar_begin.astype(np.int64)) >= 0) and int(r.rec_cigar_begin[-1]) == len(r.cigar)
+    lifted = r.rec_status == 1
+    # exactly one non-supplementary record per read
+    prim = ((r.rec_flag & 0x800) == 0)
+    assert np.array_equal(np.add.reduceat(prim.astype(np.int64), r.read_rec_begin[:-1].astype(np.int64)), np.ones(b.n_reads, np.int64))
+    # read length of every lifted CIGAR equals seq_len; no =/X survive; first/last aligned op is M
+    ops, lens = r.cigar & 15, r.cigar >> 4
+    assert not np.any((ops == 7) | (ops == 8))
+    consumes_read = np.isin(ops, [0, 1, 4, 5])
+    csum = np.concatenate([[0], np.cumsum(np.where(consumes_read, lens, 0).astype(np.int64))])
+    rec_read_len = csum[r.rec_cigar_begin[1:].astype(np.int64)] - csum[r.rec_cigar_begin[:-1].astype(np.int64)]
+    seq_len = np.ctypeslib.as_array(b.read_seq_len, (b.n_reads,))
+    rec_read = np.repeat(np.arange(b.n_reads), np.diff(r.read_rec_begin.astype(np.int64)))
+    assert np.array_equal(rec_read_len[lifted], seq_len[rec_read][lifted].astype(np.int64))
+    # oracle agrees on a random window of the batch
+    octx = helpers.oracle_context(s)
+    sub = helpers.pack(s, 77_000, 5_000)
+    assert helpers.lift_c(gctx, sub.c).diff(helpers.lift_c(octx, sub.c)) is None
