@@ -91,6 +91,9 @@ inline bool get_liftover_alignment_for_read_and_contig_segment(
         const int64_t contig_length = int64_t(contig_len[read_segment.chrom_index]);
         const int64_t read_segment_end = read_segment.pos + get_cigar_ref_offset(read_segment.cigar);
         const int64_t rev_pos = contig_length - read_segment_end;
+        // Invalid input (read runs past the contig end): the reference wraps `rev_pos as usize` and then either panics
+        // inside BTreeMap::range (start > end) or looks up garbage.  Both implementations report a bounds panic.
+        if (rev_pos < 0) throw Panic(-2, "read alignment extends past the end of a reverse-strand contig segment");
         CigarVec rev_cigar(read_segment.cigar.rbegin(), read_segment.cigar.rend());
         if (opt.stage_mask & 1) {
             decode_read();

@@ -82,7 +82,7 @@ struct Slot {
     DBuf d_read_flag, d_read_mapq, d_read_bin, d_read_seq_len, d_read_seq_off, d_read_seg_begin, d_rseg_contig, d_rseg_pos,
         d_rseg_is_fwd, d_rseg_cigar_begin, d_rseg_cigar_len, d_cigar, d_seq4;
     // work
-    DBuf w_rseg_read, w_rseg_pair_begin, w_rseg_ref_len, w_pair_rseg, w_pair_seg, w_pair_slot_begin, w_pair_status, w_pair_flip,
+    DBuf w_rseg_read, w_rseg_pair_begin, w_rseg_ref_len, w_rseg_n_id, w_rseg_read_len, w_pair_cap_b, w_pair_rseg, w_pair_seg, w_pair_slot_begin, w_pair_status, w_pair_flip,
         w_pair_pos, w_pair_n_out, w_pair_out_off, w_scratch, w_read_counts, w_read_primary, w_scan_tmp, w_totals;
     // results (device)
     DBuf r_read_rec_begin, r_status, r_rseg, r_cseg, r_tid, r_pos, r_mapq, r_flag, r_bin, r_flip, r_cigar_begin, r_cigar;
@@ -154,6 +154,8 @@ void install_segments(ptl_ctx* ctx, std::vector<HostContig>& contigs) {
             throw InputError("contig segment with a chromosome index outside the reference");
         if (f.pos[g] < 0 || f.pos[g] > 0x7fffffffLL) throw InputError("contig segment position outside the BAM int32 range");
     }
+    for (uint32_t c = 0; c < nc; ++c)
+        if (f.contig_len[c] > 0x7fffffffULL) throw InputError("contig longer than the BAM int32 sequence length limit");
     DevStatic& S = ctx->S;
     S.n_contigs = nc;
     S.n_segments = ns;
@@ -212,6 +214,7 @@ void upload_batch(ptl_ctx* ctx, Slot& sl, const ptl_batch* b) {
     for (uint32_t s = 0; s < ns; ++s) {
         if (b->rseg_contig[s] >= ctx->S.n_contigs) throw std::runtime_error("read segment refers to a contig index outside the assembly");
         if (b->rseg_cigar_begin[s] + b->rseg_cigar_len[s] > b->n_cigar) throw std::runtime_error("read segment CIGAR outside the pool");
+        if (b->rseg_pos[s] < 0 || b->rseg_pos[s] > 0x7fffffffLL) throw std::runtime_error("read segment position outside the BAM int32 range");
     }
     DevBatch& B = sl.B;
     B.n_reads = n;
@@ -248,13 +251,18 @@ void size_work(Slot& sl, uint32_t want_pairs, uint64_t want_scratch, uint32_t wa
     sl.w_rseg_read.ensure(size_t(ns) * 4 + 4, st);
     sl.w_rseg_pair_begin.ensure((size_t(ns) + 1) * 4, st);
     sl.w_rseg_ref_len.ensure(size_t(ns) * 8 + 8, st);
+    sl.w_rseg_n_id.ensure(size_t(ns) * 4 + 4, st);
+    sl.w_rseg_read_len.ensure(size_t(ns) * 4 + 4, st);
     W.rseg_read = sl.w_rseg_read.as<uint32_t>();
     W.rseg_pair_begin = sl.w_rseg_pair_begin.as<uint32_t>();
     W.rseg_ref_len = sl.w_rseg_ref_len.as<int64_t>();
+    W.rseg_n_id = sl.w_rseg_n_id.as<uint32_t>();
+    W.rseg_read_len = sl.w_rseg_read_len.as<uint32_t>();
     const uint32_t pc = std::max(W.pair_cap, want_pairs);
     sl.w_pair_rseg.ensure(size_t(pc) * 4, st);
     sl.w_pair_seg.ensure(size_t(pc) * 4, st);
     sl.w_pair_slot_begin.ensure((size_t(pc) + 1) * 8, st);
+    sl.w_pair_cap_b.ensure(size_t(pc) * 4, st);
     sl.w_pair_status.ensure(size_t(pc), st);
     sl.w_pair_flip.ensure(size_t(pc), st);
     sl.w_pair_pos.ensure(size_t(pc) * 8, st);
@@ -264,6 +272,7 @@ void size_work(Slot& sl, uint32_t want_pairs, uint64_t want_scratch, uint32_t wa
     W.pair_rseg = sl.w_pair_rseg.as<uint32_t>();
     W.pair_seg = sl.w_pair_seg.as<uint32_t>();
     W.pair_slot_begin = sl.w_pair_slot_begin.as<uint64_t>();
+    W.pair_cap_b = sl.w_pair_cap_b.as<uint32_t>();
     W.pair_status = sl.w_pair_status.as<int8_t>();
     W.pair_flip = sl.w_pair_flip.as<uint8_t>();
     W.pair_pos = sl.w_pair_pos.as<int64_t>();
@@ -327,7 +336,7 @@ void run_batch(ptl_ctx* ctx, Slot& sl, uint32_t stage_mask) {
     // batch is re-run with exact sizes (finish_batch).  Steady-state batches of similar shape never re-run.
     const uint32_t ns = sl.B.n_rsegs, n = sl.B.n_reads;
     const uint32_t want_pairs = ns + ns / 8 + 1024;
-    const uint64_t want_scratch = 40ull * sl.n_cigar_in + 96ull * want_pairs;
+    const uint64_t want_scratch = 8ull * sl.n_cigar_in + 64ull * want_pairs;
     const uint32_t want_recs = want_pairs + n;
     const uint64_t want_cigar = sl.n_cigar_in + sl.n_cigar_in / 2 + 16ull * n + 1024;
     size_work(sl, want_pairs, want_scratch, want_recs, want_cigar);
@@ -467,7 +476,7 @@ void ptl_destroy(ptl_ctx* ctx) {
         if (sl.stream) cudaStreamSynchronize(sl.stream);
         for (DBuf* b : {&sl.d_read_flag, &sl.d_read_mapq, &sl.d_read_bin, &sl.d_read_seq_len, &sl.d_read_seq_off, &sl.d_read_seg_begin,
                         &sl.d_rseg_contig, &sl.d_rseg_pos, &sl.d_rseg_is_fwd, &sl.d_rseg_cigar_begin, &sl.d_rseg_cigar_len, &sl.d_cigar,
-                        &sl.d_seq4, &sl.w_rseg_read, &sl.w_rseg_pair_begin, &sl.w_rseg_ref_len, &sl.w_pair_rseg, &sl.w_pair_seg,
+                        &sl.d_seq4, &sl.w_rseg_read, &sl.w_rseg_pair_begin, &sl.w_rseg_ref_len, &sl.w_rseg_n_id, &sl.w_rseg_read_len, &sl.w_pair_cap_b, &sl.w_pair_rseg, &sl.w_pair_seg,
                         &sl.w_pair_slot_begin, &sl.w_pair_status, &sl.w_pair_flip, &sl.w_pair_pos, &sl.w_pair_n_out, &sl.w_pair_out_off,
                         &sl.w_scratch, &sl.w_read_counts, &sl.w_read_primary, &sl.w_scan_tmp, &sl.w_totals, &sl.r_read_rec_begin,
                         &sl.r_status, &sl.r_rseg, &sl.r_cseg, &sl.r_tid, &sl.r_pos, &sl.r_mapq, &sl.r_flag, &sl.r_bin, &sl.r_flip,

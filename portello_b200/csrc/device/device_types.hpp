@@ -57,11 +57,14 @@ struct DevWork {
     uint32_t* rseg_read = nullptr;       // owning read
     uint32_t* rseg_pair_begin = nullptr; // [n_rsegs+1] (count, then exclusive scan in place)
     int64_t* rseg_ref_len = nullptr;     // get_cigar_ref_offset of the segment
+    uint32_t* rseg_n_id = nullptr;       // number of I/D ops of the segment CIGAR (slot bounds)
+    uint32_t* rseg_read_len = nullptr;   // read bases consumed by the segment CIGAR incl. hard clips (length check)
     // per pair
     uint32_t pair_cap = 0;
     uint32_t* pair_rseg = nullptr;
     uint32_t* pair_seg = nullptr;        // global contig-segment index
     uint64_t* pair_slot_begin = nullptr; // [pair_cap+1] (bound, then exclusive scan in place) ops of scratch
+    uint32_t* pair_cap_b = nullptr;      // capacity of the pair's buffer B (the slot is [B | A])
     int8_t* pair_status = nullptr;
     uint8_t* pair_flip = nullptr;
     int64_t* pair_pos = nullptr;

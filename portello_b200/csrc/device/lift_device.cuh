@@ -7,6 +7,15 @@
 // (clean_up_cigar_edge_indels + compress_cigar, lib/rust-vc-utils/src/bam_utils/cigar/mod.rs:204-291) into the
 // write: leading-edge conversion and run merging happen as ops are pushed, the trailing edge is fixed in place at
 // finish().  Integer arithmetic only; bases are compared as the exact bytes the reference compares.
+//
+// Execution shape (ncu r01a-r01c, profiles/): written naively, the base fetches of the homology walk were issued by ONE
+// lane at a time (1.0 threads/inst, 64% of stall samples) because lanes reach their indel clusters at different op
+// indices; a fully flattened state machine fixed that but tripled the instruction count.  The shape kept here:
+//   - op walks are tight nested loops over L1-resident ops (ALU-bound, short divergent arms),
+//   - everything that needs a DRAM/L2 round trip (homology walk, cluster trimming) is hoisted into a warp-converged
+//     middle phase over a per-lane list of recorded clusters, so 32 lanes x 4 loads are in flight per warp,
+//   - the table block under the walk and the next key live in registers; the table is read only when a key is crossed.
+// Contig coordinates are 32-bit (BAM l_seq is int32); reference positions are widened only where they leave the loop.
 #pragma once
 #include <cstdint>
 
@@ -19,6 +28,7 @@ constexpr uint32_t kMatchMask = (1u << OP_M) | (1u << OP_EQ) | (1u << OP_X);
 constexpr uint32_t kRefMask = kMatchMask | (1u << OP_D) | (1u << OP_N);
 constexpr uint32_t kReadMask = kMatchMask | (1u << OP_I) | (1u << OP_S) | (1u << OP_H);
 constexpr uint32_t NO_OP = 0xffffffffu;
+constexpr uint32_t FULL = 0xffffffffu;
 
 constexpr int ST_LIFTED = 1, ST_NONE = 0, ST_ERR_LENGTH = -1, ST_ERR_BOUNDS = -2, ST_ERR_CAPACITY = -3;
 
@@ -38,25 +48,17 @@ struct ReadBases {
         const uint32_t j = flip ? (len - 1u - idx) : idx;
         const uint32_t byte = seq4[j >> 1];
         const uint32_t nib = (j & 1u) ? (byte & 0xfu) : (byte >> 4);
-        uint8_t c = decode_nt16(nib);
-        if (flip) c = comp(c);
-        return c;
+        return decode(nib, flip);
     }
-    static __device__ __forceinline__ uint8_t decode_nt16(uint32_t nib) {
-        // "=ACMGRSVTWYHKDBN" packed little-endian into two 64-bit immediates (no table load)
-        const unsigned long long w0 = 0x565352474D43413DULL;  // V S R G M C A =
-        const unsigned long long w1 = 0x4E42444B48595754ULL;  // N B D K H Y W T
-        const unsigned long long w = (nib & 8u) ? w1 : w0;
+    // nibble -> ASCII, branch-free: two 16-byte tables held as 64-bit immediates.
+    //   forward : "=ACMGRSVTWYHKDBN"   (rust-htslib decode)
+    //   flipped : comp_base of the above = "NTGNCNNNANNNNNNN"  (A<->T, C<->G, everything else incl. '=' and IUPAC -> 'N')
+    static __device__ __forceinline__ uint8_t decode(uint32_t nib, bool flipped) {
+        const unsigned long long f0 = 0x565352474D43413DULL, f1 = 0x4E42444B48595754ULL;  // V S R G M C A = | N B D K H Y W T
+        const unsigned long long r0 = 0x4E4E4E434E47544EULL, r1 = 0x4E4E4E4E4E4E4E41ULL;  // N N N C N G T N | N N N N N N N A
+        const unsigned long long lo = flipped ? r0 : f0, hi = flipped ? r1 : f1;
+        const unsigned long long w = (nib & 8u) ? hi : lo;
         return uint8_t(w >> ((nib & 7u) * 8u));
-    }
-    static __device__ __forceinline__ uint8_t comp(uint8_t c) {
-        switch (c) {
-            case 'A': return 'T';
-            case 'T': return 'A';
-            case 'C': return 'G';
-            case 'G': return 'C';
-            default: return 'N';  // 'N' -> 'N'; every other 4-bit symbol -> 'N' (lower case never occurs in a BAM decode)
-        }
     }
 };
 
@@ -66,37 +68,36 @@ struct OpSink {
     uint32_t* buf;
     uint32_t cap;
     uint32_t n = 0;
-    uint32_t pend = NO_OP;
+    uint32_t pend_op = NO_OP, pend_len = 0;
     int32_t last_match_idx = -1;  // index (in buf) of the last alignment-match op, counting the pending one
     bool seen_match = false;
     bool overflow = false;
-    uint64_t lead_del_shift = 0;  // return value of clean_up_cigar_edge_indels
-    uint64_t read_len = 0;        // get_cigar_read_offset(result, ignore_hard_clip=false)
+    uint32_t lead_del_shift = 0;  // return value of clean_up_cigar_edge_indels
 
     __device__ __forceinline__ OpSink(uint32_t* b, uint32_t c) : buf(b), cap(c) {}
 
     __device__ __forceinline__ void flush() {
-        if (pend != NO_OP) {
-            if (n < cap) buf[n] = pend;
+        if (pend_op != NO_OP) {
+            if (n < cap) buf[n] = (pend_len << 4) | pend_op;
             else overflow = true;
             ++n;
-            pend = NO_OP;
+            pend_op = NO_OP;
         }
     }
     __device__ __forceinline__ void push(uint32_t op, uint32_t len) {
         if (len == 0) return;  // compress_cigar filters empty elements (no stage emits an empty alignment match)
-        if ((kReadMask >> op) & 1u) read_len += len;
         if (!seen_match) {  // leading edge (cigar/mod.rs:278-280)
             if (op_is_match(op)) seen_match = true;
             else if (op == OP_I) op = OP_S;
             else if (op == OP_D) { lead_del_shift += len; return; }  // -> SoftClip(0), later dropped
         }
-        if (pend != NO_OP && (pend & 0xfu) == op) {
-            if (op != OP_P) pend += len << 4;  // a Pad after a Pad is dropped, not merged (cigar/mod.rs:208-215)
+        if (pend_op == op) {
+            if (op != OP_P) pend_len += len;  // a Pad after a Pad is dropped, not merged (cigar/mod.rs:208-215)
             return;
         }
         flush();
-        pend = (len << 4) | op;
+        pend_op = op;
+        pend_len = len;
         if (op_is_match(op)) last_match_idx = int32_t(n);
     }
     // trailing edge (cigar/mod.rs:282-288) + re-merge of what the conversion made adjacent
@@ -135,253 +136,333 @@ struct PairCounters {
 };
 
 // ------------------------------------------------------------------------------------------------------------------
+// One round trip of the left homology walk: W independent (ref, read) byte pairs are loaded, then compared in order.
+// Indices past `limit` are clamped (loaded, never compared).
+template <int W>
+__device__ __forceinline__ void walk_homology(const uint8_t* __restrict__ ref_seq, const ReadBases& read, uint32_t ref_end, uint32_t read_end,
+                                              uint32_t limit, uint32_t& hom, bool& walking, PairCounters& cnt) {
+    uint8_t rb[W], qb[W];
+#pragma unroll
+    for (int q = 0; q < W; ++q) {
+        const uint32_t idx = min(hom + uint32_t(q), limit - 1u);
+        rb[q] = ref_seq[ref_end - 1u - idx];
+        qb[q] = read.at(read_end - 1u - idx);
+    }
+#pragma unroll
+    for (int q = 0; q < W; ++q) {
+        if (walking && hom < limit) {
+            cnt.base_bytes += 2;
+            if (rb[q] != qb[q]) walking = false;
+            else ++hom;
+        }
+    }
+    if (hom >= limit) walking = false;
+}
+
 // a5: left_shift_indels (lib/rust-vc-utils/.../shift_indels/left_shift_indels.rs:17-39) with CigarShiftBuilder in Left
 // mode (cigar_indel_shifter.rs:45-164) and the left walk of get_indel_breakend_homology_info
-// (indel_breakend_homology.rs:35-49).  Only min(match_block, homology) matters (:124), so the walk stops at
-// match_block: same result, bounded work.
-struct LeftShifter {
-    const uint8_t* ref_seq;
-    uint64_t ref_len;
-    ReadBases read;
-    OpSink& sink;
-    PairCounters& cnt;
-    int err = 0;
-    uint32_t match_block = 0;
-    bool in_indel = false;
-    int64_t blk_ref = 0;
-    uint64_t blk_read = 0;
-    uint32_t del = 0, ins = 0;
-
-    __device__ __forceinline__ LeftShifter(const uint8_t* r, uint64_t rl, ReadBases rd, OpSink& s, PairCounters& c)
-        : ref_seq(r), ref_len(rl), read(rd), sink(s), cnt(c) {}
-
-    __device__ __forceinline__ void end_indel() {
-        if (!in_indel) return;
-        in_indel = false;
-        const int64_t ref_end = blk_ref + int64_t(del);
-        const int64_t read_end = int64_t(blk_read) + int64_t(ins);
-        const int64_t max_left = min(blk_ref, int64_t(blk_read));
-        uint32_t hom = 0;
-        if (max_left > 0) {
+// (indel_breakend_homology.rs:35-49).
+//
+// Three phases per lane, the middle one warp-converged (the base compares are the only latency-bound part):
+//   A  walk the ops, record each indel cluster (ref_end, read_end, walk limit) in `clus`      -- ALU + L1 hits
+//   B  for k = 0,1,2..: every lane with a k-th cluster walks its homology                     -- 32 lanes x 4 loads in flight
+//   C  walk the ops again and emit, consuming the recorded homologies                          -- ALU + stores
+// Only min(match_block, homology) matters (:124) and match_block_k <= gap_k + homology_{k-1}, so phase A can bound the
+// walk of cluster k by limit_k = min(max_left_k, gap_k + limit_{k-1}) without knowing the homologies: same result.
+// `clus` needs 3 words per cluster.  Warp-collective.  Returns the shifted position.
+__device__ __forceinline__ uint32_t run_left_shift_warp(bool active, const OpSource& in, uint32_t ref_pos, const uint8_t* __restrict__ ref_seq,
+                                                        uint32_t ref_len, const ReadBases& read, uint32_t* __restrict__ clus, OpSink& sink,
+                                                        PairCounters& cnt, int& err) {
+    // ---- phase A
+    uint32_t n_clus = 0;
+    if (active) {
+        uint32_t ref_head = ref_pos, read_head = 0, gap = 0, prev_limit = 0;
+        uint32_t blk_ref = 0, blk_read = 0, del = 0, ins = 0;
+        bool in_indel = false;
+        auto close = [&]() {
+            const uint32_t ref_end = blk_ref + del, read_end = blk_read + ins;
+            const uint32_t max_left = min(blk_ref, blk_read);
+            uint32_t limit = min(max_left, gap + prev_limit);
             // first access is ref_seq[ref_end-1] / read_seq[read_end-1]; later ones only move down and stay >= 0
-            if (ref_end > int64_t(ref_len) || read_end > int64_t(read.len)) {
-                err = ST_ERR_BOUNDS;
+            if (max_left > 0 && (ref_end > ref_len || read_end > read.len)) { err = ST_ERR_BOUNDS; limit = 0; }
+            clus[3 * n_clus] = ref_end;
+            clus[3 * n_clus + 1] = read_end;
+            clus[3 * n_clus + 2] = limit;
+            ++n_clus;
+            prev_limit = limit;
+            gap = 0;
+            in_indel = false;
+            del = 0;
+            ins = 0;
+        };
+        for (uint32_t i = 0; i < in.n; ++i) {
+            const uint32_t c = in.get(i);
+            const uint32_t op = c & 0xfu, len = c >> 4;
+            if (op == OP_D || op == OP_I) {
+                if (len > 0) {
+                    if (!in_indel) { in_indel = true; blk_ref = ref_head; blk_read = read_head; }
+                    if (op == OP_D) del += len; else ins += len;
+                }
             } else {
-                const uint32_t limit = uint32_t(min(max_left, int64_t(match_block)));
-                while (hom < limit) {
-                    const uint8_t rb = ref_seq[ref_end - 1 - hom];
-                    const uint8_t qb = read.at(uint32_t(read_end - 1 - hom));
-                    cnt.base_bytes += 2;
-                    if (rb != qb) break;
-                    ++hom;
+                if (in_indel) close();
+                if (op_is_match(op)) gap += len;
+                else { gap = 0; prev_limit = 0; }  // add_other flushes the match block: no carry across it
+            }
+            ref_head += op_ref_adv(c);
+            read_head += op_read_adv(c);
+        }
+        if (in_indel) close();
+    }
+    // ---- phase B
+    for (uint32_t k = 0; __any_sync(FULL, k < n_clus); ++k) {
+        uint32_t hom = 0, limit = 0, ref_end = 0, read_end = 0;
+        if (k < n_clus) {
+            ref_end = clus[3 * k];
+            read_end = clus[3 * k + 1];
+            limit = clus[3 * k + 2];
+        }
+        bool walking = limit > 0;
+        // probe 4 bases first (almost every walk ends there), then 8 per round trip: long walks only happen in
+        // repeats or reducible I/D clusters, and they hold the whole warp
+        if (__any_sync(FULL, walking)) {
+            if (walking) walk_homology<4>(ref_seq, read, ref_end, read_end, limit, hom, walking, cnt);
+            while (__any_sync(FULL, walking)) {
+                if (walking) walk_homology<8>(ref_seq, read, ref_end, read_end, limit, hom, walking, cnt);
+            }
+        }
+        if (k < n_clus) clus[3 * k] = hom;
+    }
+    // ---- phase C
+    if (active) {
+        uint32_t match_block = 0, del = 0, ins = 0, k = 0;
+        bool in_indel = false;
+        auto close = [&]() {  // end_indel (:101-148)
+            const uint32_t actual = min(match_block, clus[3 * k]);
+            ++k;
+            sink.push(OP_M, match_block - actual);
+            match_block = actual;
+            sink.push(OP_I, ins);  // nImD order (:141-147)
+            sink.push(OP_D, del);
+            in_indel = false;
+            del = 0;
+            ins = 0;
+        };
+        for (uint32_t i = 0; i < in.n; ++i) {
+            const uint32_t c = in.get(i);
+            const uint32_t op = c & 0xfu, len = c >> 4;
+            if (op == OP_D || op == OP_I) {
+                if (len > 0) {
+                    in_indel = true;
+                    if (op == OP_D) del += len; else ins += len;
+                }
+            } else {
+                if (in_indel) close();
+                if (op_is_match(op)) {
+                    match_block += len;
+                } else {  // add_other (:155-164)
+                    sink.push(OP_M, match_block);
+                    match_block = 0;
+                    sink.push(op, len);
                 }
             }
         }
-        const uint32_t actual = min(match_block, hom);
-        sink.push(OP_M, match_block - actual);
-        match_block = actual;
-        sink.push(OP_I, ins);  // nImD order (:141-147)
-        sink.push(OP_D, del);
-        ins = 0;
-        del = 0;
-    }
-    __device__ __forceinline__ void add(uint32_t c, int64_t ref_head, uint64_t read_head) {
-        const uint32_t op = c & 0xfu, len = c >> 4;
-        if (op == OP_D || op == OP_I) {
-            if (len > 0) {
-                if (!in_indel) { in_indel = true; blk_ref = ref_head; blk_read = read_head; }
-                if (op == OP_D) del += len; else ins += len;
-            }
-        } else if (op_is_match(op)) {
-            end_indel();
-            match_block += len;
-        } else {
-            end_indel();
-            sink.push(OP_M, match_block);
-            match_block = 0;
-            sink.push(op, len);
-        }
-    }
-    __device__ __forceinline__ void end() {
-        end_indel();
+        if (in_indel) close();
         sink.push(OP_M, match_block);
-        match_block = 0;
+        sink.finish();
     }
-};
-
-// returns the shifted position
-__device__ __forceinline__ int64_t run_left_shift(const OpSource& in, int64_t ref_pos, const uint8_t* ref_seq, uint64_t ref_len,
-                                                  const ReadBases& read, OpSink& sink, PairCounters& cnt, int& err) {
-    LeftShifter ls(ref_seq, ref_len, read, sink, cnt);
-    int64_t ref_head = ref_pos;
-    uint64_t read_head = 0;
-    for (uint32_t i = 0; i < in.n; ++i) {
-        const uint32_t c = in.get(i);
-        ls.add(c, ref_head, read_head);
-        ref_head += op_ref_adv(c);
-        read_head += op_read_adv(c);
-    }
-    ls.end();
-    sink.finish();
-    if (ls.err) err = ls.err;
-    return ref_pos + int64_t(sink.lead_del_shift);
+    return ref_pos + sink.lead_del_shift;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
 // a6: liftover_read_alignment (src/liftover_read_alignment.rs:137-223).  The reference re-searches its BTreeMap for
 // every reference-consuming op; read-op boundaries and table keys both advance monotonically, so one binary search
-// per pair plus a forward merge visits exactly the same (piece, block) sequence.
+// per pair plus a forward merge visits exactly the same (piece, block) sequence.  The current block and the next key
+// live in registers; the table is touched only when the walk crosses a key.
 // Returns true if ref2_start_pos was set (Some); *out_pos = start + leading-deletion shift.
-__device__ __forceinline__ bool run_liftover(const OpSource& in, int64_t pos, const int2* __restrict__ tab, uint32_t t0,
-                                             uint32_t t1, OpSink& sink, int64_t* out_pos) {
+__device__ __forceinline__ bool run_liftover(const OpSource& in, uint32_t pos, const int2* __restrict__ tab, uint32_t t0, uint32_t t1,
+                                             OpSink& sink, int64_t* out_pos) {
+    constexpr uint32_t INF = 0xffffffffu;
     bool start_set = false, end2_set = false;
-    int64_t start = 0, end2 = 0;
-    // cursor = index of the greatest key <= pos, or t0-1 (as int64 to allow -1 when t0 == 0)
-    int64_t cur;
+    int32_t start = 0, end2 = 0;  // reference positions fit int32 (BAM)
+    // block cursor: the current block is the greatest key <= the walk position (kind 0 = before the first key);
+    // ti = index of the NEXT table entry (the one whose key is nk)
+    uint32_t ti, nk = INF, blk_k = 0, blk_kind = 0;  // kind: 0 no block, 1 None block, 2 Some block
+    int32_t blk_v = -1;
     {
         uint32_t lo = t0, hi = t1;  // first index with key > pos
         while (lo < hi) {
             const uint32_t mid = (lo + hi) >> 1;
-            if (int64_t(uint32_t(tab[mid].x)) <= pos) lo = mid + 1;
+            if (uint32_t(tab[mid].x) <= pos) lo = mid + 1;
             else hi = mid;
         }
-        cur = int64_t(lo) - 1;
+        ti = lo;
+        if (lo > t0) {
+            const int2 b = tab[lo - 1];
+            blk_k = uint32_t(b.x);
+            blk_v = b.y;
+            blk_kind = (b.y < 0) ? 1u : 2u;
+        }
+        if (lo < t1) nk = uint32_t(tab[lo].x);
     }
-    int64_t p = pos;
+    uint32_t p = pos;
     for (uint32_t i = 0; i < in.n; ++i) {
         const uint32_t c = in.get(i);
         const uint32_t op = c & 0xfu, len = c >> 4;
-        if (op == OP_I || op == OP_S || op == OP_H) {
-            sink.push(op, len);  // read-only ops transfer verbatim (:157-160)
+        if (!((kRefMask >> op) & 1u)) {
+            if (op != OP_P) sink.push(op, len);  // I/S/H transfer verbatim (:157-160); Pad is ignored (:213)
             continue;
         }
-        if (!((kRefMask >> op) & 1u)) continue;  // Pad (:213)
         if (len == 0) continue;
         const bool is_match = op_is_match(op);
-        const int64_t s = p, e = p + int64_t(len);
-        while (cur + 1 < int64_t(t1) && int64_t(uint32_t(tab[cur + 1].x)) <= s) ++cur;
-        int64_t bp = s;
-        int64_t li = (cur >= int64_t(t0)) ? cur : -1;  // "last" block, -1 = None
-        int64_t nx = cur + 1;
+        const uint32_t main_op = is_match ? uint32_t(OP_M) : op;  // D stays D, N stays N, M/=/X become M (:103-107)
+        const uint32_t e = p + len;
+        uint32_t bp = p;
         for (;;) {
-            const int64_t nk = (nx < int64_t(t1)) ? int64_t(uint32_t(tab[nx].x)) : INT64_MAX;
-            const int64_t seg_end = min(nk, e);
-            if (seg_end > bp) {  // update_ref2_cigar_segment (:35-133) for the piece [bp, seg_end)
-                const uint32_t plen = uint32_t(seg_end - bp);
-                if (li < 0) {
-                    if (is_match) sink.push(OP_S, plen);
-                } else {
-                    const int2 blk = tab[li];
-                    const int64_t k = int64_t(uint32_t(blk.x));
-                    if (blk.y < 0) {
-                        if (is_match) sink.push(OP_I, plen);
-                    } else {
-                        const int64_t r = int64_t(blk.y);
-                        if (is_match && !start_set) { start = r + (bp - k); start_set = true; }
-                        if (end2_set) {
-                            const int64_t dlen = r - end2;
-                            if (dlen > 0 && start_set) sink.push(OP_D, uint32_t(dlen));
-                        }
-                        end2 = r + (seg_end - k);
-                        end2_set = true;
-                        if (is_match || start_set) sink.push(op == OP_D ? OP_D : (op == OP_N ? OP_N : OP_M), plen);
+            // piece [bp, seg_end) against the current block (update_ref2_cigar_segment, :35-133)
+            const uint32_t seg_end = min(nk, e);
+            if (seg_end > bp) {
+                const uint32_t plen = seg_end - bp;
+                if (blk_kind == 2) {
+                    if (is_match && !start_set) { start = blk_v + int32_t(bp - blk_k); start_set = true; }
+                    if (end2_set && start_set) {
+                        const int32_t dlen = blk_v - end2;
+                        if (dlen > 0) sink.push(OP_D, uint32_t(dlen));
                     }
+                    end2 = blk_v + int32_t(seg_end - blk_k);
+                    end2_set = true;
+                    if (start_set) sink.push(main_op, plen);
+                } else if (is_match) {
+                    sink.push(blk_kind == 1 ? uint32_t(OP_I) : uint32_t(OP_S), plen);
                 }
                 bp = seg_end;
             }
             if (nk >= e) break;
-            li = nx;
-            ++nx;
+            const int2 b = tab[ti];  // cross the key: it becomes the current block
+            blk_k = uint32_t(b.x);
+            blk_v = b.y;
+            blk_kind = (b.y < 0) ? 1u : 2u;
+            ++ti;
+            nk = (ti < t1) ? uint32_t(tab[ti].x) : INF;
         }
-        cur = nx - 1;
         p = e;
     }
     if (!start_set) return false;
     sink.finish();
-    *out_pos = start + int64_t(sink.lead_del_shift);
+    *out_pos = int64_t(start) + int64_t(sink.lead_del_shift);
     return true;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
 // a9: simplify_alignment_indels (src/simplify_alignment_indels.rs:119-156) with CigarBlockInfo::end_indel (:35-111).
-struct Simplifier {
-    const uint8_t* ref_seq;
-    uint64_t ref_len;
-    ReadBases read;
-    OpSink& sink;
-    PairCounters& cnt;
-    int err = 0;
-    bool in_indel = false;
-    int64_t blk_ref = 0;
-    uint64_t blk_read = 0;
-    uint32_t del = 0, ins = 0;
-
-    __device__ __forceinline__ Simplifier(const uint8_t* r, uint64_t rl, ReadBases rd, OpSink& s, PairCounters& c)
-        : ref_seq(r), ref_len(rl), read(rd), sink(s), cnt(c) {}
-
-    __device__ __forceinline__ bool fetch(int64_t ref_idx, int64_t read_idx, uint8_t& rb, uint8_t& qb) {
-        if (ref_idx < 0 || uint64_t(ref_idx) >= ref_len || read_idx < 0 || uint64_t(read_idx) >= read.len) {
-            err = ST_ERR_BOUNDS;  // Rust slice index panic
-            return false;
+// Same three-phase shape as the left shift: (A) walk and record the MIXED clusters (both I and D, not 1/1) in `rec`
+// (4 words each), (B) warp-converged base trimming of the k-th mixed cluster of every lane, (C) walk again and emit.
+// Warp-collective.  Returns the (possibly shifted) position.
+__device__ __forceinline__ int64_t run_simplify_warp(bool active, const OpSource& in, int64_t ref_pos, const uint8_t* __restrict__ ref_seq,
+                                                     uint64_t ref_len, const ReadBases& read, uint32_t* __restrict__ rec, OpSink& sink,
+                                                     PairCounters& cnt, int& err) {
+    // ---- phase A
+    uint32_t n_mixed = 0;
+    if (active) {
+        uint32_t ref_off = 0, read_head = 0, blk_ref = 0, blk_read = 0, del = 0, ins = 0;
+        bool in_indel = false;
+        for (uint32_t i = 0; i <= in.n; ++i) {
+            const uint32_t c = (i < in.n) ? in.get(i) : 0u;  // a sentinel match op closes a trailing cluster
+            const uint32_t op = c & 0xfu, len = c >> 4;
+            if (i < in.n && (op == OP_D || op == OP_I)) {
+                if (!in_indel) { in_indel = true; blk_ref = ref_off; blk_read = read_head; }
+                if (op == OP_D) del += len; else ins += len;
+            } else if (in_indel) {
+                if (del > 0 && ins > 0 && !(del == 1 && ins == 1)) {
+                    rec[4 * n_mixed] = blk_ref;
+                    rec[4 * n_mixed + 1] = blk_read;
+                    rec[4 * n_mixed + 2] = del;
+                    rec[4 * n_mixed + 3] = ins;
+                    ++n_mixed;
+                }
+                in_indel = false;
+                del = 0;
+                ins = 0;
+            }
+            ref_off += op_ref_adv(c);
+            read_head += op_read_adv(c);
         }
-        rb = ref_seq[ref_idx];
-        qb = read.at(uint32_t(read_idx));
-        cnt.base_bytes += 2;
-        return true;
     }
-    __device__ __forceinline__ void end_indel() {
-        if (!in_indel) return;
-        in_indel = false;
-        uint32_t d = del, n = ins;
-        del = 0;
-        ins = 0;
-        if (d == 0 || n == 0) {  // (0,0) nothing, (0,len) Ins, (len,0) Del
-            sink.push(OP_I, n);
-            sink.push(OP_D, d);
-            return;
+    // ---- phase B: trim equal bases from the right first, then from the left (:55-85)
+    for (uint32_t k = 0; __any_sync(FULL, k < n_mixed); ++k) {
+        const bool mine = k < n_mixed;
+        int64_t blk_ref = 0;
+        uint32_t blk_read = 0, d = 0, n = 0, pre = 0, post = 0;
+        if (mine) {
+            blk_ref = ref_pos + int64_t(rec[4 * k]);
+            blk_read = rec[4 * k + 1];
+            d = rec[4 * k + 2];
+            n = rec[4 * k + 3];
         }
-        if (d == 1 && n == 1) { sink.push(OP_M, 1); return; }
-        uint32_t pre = 0, post = 0;
-        uint8_t rb, qb;
-        while (d > 0 && n > 0) {  // right side first
-            if (!fetch(blk_ref + int64_t(d) - 1, int64_t(blk_read) + int64_t(n) - 1, rb, qb)) return;
-            if (rb != qb) break;
-            --d; --n; ++post;
+        uint32_t side = mine ? 1u : 0u;  // 1 right, 2 left, 0 done
+        while (__any_sync(FULL, side != 0u)) {
+            if (side != 0u) {
+                if (d == 0 || n == 0) {
+                    side = (side == 1u) ? 2u : 0u;
+                } else {
+                    const int64_t f_ref = (side == 1u) ? blk_ref + int64_t(d) - 1 : blk_ref + int64_t(pre);
+                    const uint32_t f_read = (side == 1u) ? blk_read + n - 1u : blk_read + pre;
+                    if (f_ref < 0 || uint64_t(f_ref) >= ref_len || f_read >= read.len) {
+                        err = ST_ERR_BOUNDS;  // Rust slice index panic
+                        side = 0u;
+                    } else {
+                        const uint8_t rb = ref_seq[f_ref];
+                        const uint8_t qb = read.at(f_read);
+                        cnt.base_bytes += 2;
+                        if (rb == qb) {
+                            --d; --n;
+                            if (side == 1u) ++post; else ++pre;
+                        } else {
+                            side = (side == 1u) ? 2u : 0u;
+                        }
+                    }
+                }
+            }
         }
-        while (d > 0 && n > 0) {  // then left side
-            if (!fetch(blk_ref + int64_t(pre), int64_t(blk_read) + int64_t(pre), rb, qb)) return;
-            if (rb != qb) break;
-            --d; --n; ++pre;
+        if (mine) {
+            if (d == 1 && n == 1) { d = 0; n = 0; ++post; }  // down to a SNP: 1 edit instead of 2 (:88-92)
+            rec[4 * k] = pre;
+            rec[4 * k + 1] = post;
+            rec[4 * k + 2] = d;
+            rec[4 * k + 3] = n;
         }
-        if (d == 1 && n == 1) { d = 0; n = 0; ++post; }
-        sink.push(OP_M, pre);
-        sink.push(OP_I, n);
-        sink.push(OP_D, d);
-        sink.push(OP_M, post);
     }
-};
-
-__device__ __forceinline__ int64_t run_simplify(const OpSource& in, int64_t ref_pos, const uint8_t* ref_seq, uint64_t ref_len,
-                                                const ReadBases& read, OpSink& sink, PairCounters& cnt, int& err) {
-    Simplifier sp(ref_seq, ref_len, read, sink, cnt);
-    int64_t ref_head = ref_pos;
-    uint64_t read_head = 0;
-    for (uint32_t i = 0; i < in.n; ++i) {
-        const uint32_t c = in.get(i);
-        const uint32_t op = c & 0xfu, len = c >> 4;
-        if (op == OP_D || op == OP_I) {
-            if (!sp.in_indel) { sp.in_indel = true; sp.blk_ref = ref_head; sp.blk_read = read_head; }
-            if (op == OP_D) sp.del += len; else sp.ins += len;
-        } else {
-            sp.end_indel();
-            sink.push(op, len);
+    // ---- phase C
+    if (active) {
+        uint32_t del = 0, ins = 0, k = 0;
+        bool in_indel = false;
+        for (uint32_t i = 0; i <= in.n; ++i) {
+            const uint32_t c = (i < in.n) ? in.get(i) : 0u;
+            const uint32_t op = c & 0xfu, len = c >> 4;
+            if (i < in.n && (op == OP_D || op == OP_I)) {
+                in_indel = true;
+                if (op == OP_D) del += len; else ins += len;
+                continue;
+            }
+            if (in_indel) {  // end_indel (:35-111)
+                if (del == 0 || ins == 0) {
+                    sink.push(del ? uint32_t(OP_D) : uint32_t(OP_I), del + ins);  // (0,0) nothing, (0,len) Ins, (len,0) Del
+                } else if (del == 1 && ins == 1) {
+                    sink.push(OP_M, 1);  // do not even look at the bases (:45-48)
+                } else {
+                    sink.push(OP_M, rec[4 * k]);
+                    sink.push(OP_I, rec[4 * k + 3]);
+                    sink.push(OP_D, rec[4 * k + 2]);
+                    sink.push(OP_M, rec[4 * k + 1]);
+                    ++k;
+                }
+                in_indel = false;
+                del = 0;
+                ins = 0;
+            }
+            if (i < in.n) sink.push(op, len);
         }
-        ref_head += op_ref_adv(c);
-        read_head += op_read_adv(c);
+        sink.finish();
     }
-    sp.end_indel();
-    sink.finish();
-    if (sp.err) err = sp.err;
     return ref_pos + int64_t(sink.lead_del_shift);
 }
 

@@ -279,22 +279,37 @@ void gen_part(const std::vector<uint8_t>& C, int64_t start, uint32_t L, const pt
         }
         copy_eq(p);
         const bool cluster = rng.chance(P.read_cluster_frac);
+        // An adjacent I/D cluster is only emitted in a form an aligner could report: the first and the last inserted
+        // base differ from the first / last deleted base (otherwise the match would simply extend into the cluster).
+        auto cluster_ins = [&](uint32_t n, int64_t del_at, uint32_t d) {
+            std::vector<uint8_t> v(n);
+            for (auto& x : v) x = rand_base(rng);
+            v.front() = other_base(rng, C[size_t(del_at)]);
+            if (n == 1) { while (v[0] == C[size_t(del_at)] || v[0] == C[size_t(del_at + d - 1)]) v[0] = rand_base(rng); }
+            else v.back() = other_base(rng, C[size_t(del_at + d - 1)]);
+            return v;
+        };
         if (is_ins) {
-            out.bases.insert(out.bases.end(), ins.begin(), ins.end());
-            push_op(out.ops, I, ins.size());
             if (cluster) {
                 const uint32_t d = 1 + uint32_t(rng.below(3));
+                ins = cluster_ins(uint32_t(ins.size()), c, d);
+                out.bases.insert(out.bases.end(), ins.begin(), ins.end());
+                push_op(out.ops, I, ins.size());
                 push_op(out.ops, D, d);
                 c += d;
+            } else {
+                out.bases.insert(out.bases.end(), ins.begin(), ins.end());
+                push_op(out.ops, I, ins.size());
             }
         } else {
             push_op(out.ops, D, len);
-            c += len;
             if (cluster) {
                 const uint32_t n = 1 + uint32_t(rng.below(3));
-                for (uint32_t k = 0; k < n; ++k) out.bases.push_back(rand_base(rng));
+                const std::vector<uint8_t> v = cluster_ins(n, c, len);
+                out.bases.insert(out.bases.end(), v.begin(), v.end());
                 push_op(out.ops, I, n);
             }
+            c += len;
         }
         prev_event_end = c;
         // one matching base after the event keeps separate events separate
