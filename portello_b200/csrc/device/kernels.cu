@@ -313,6 +313,7 @@ __global__ void __launch_bounds__(128) lift_pairs_kernel(DevStatic S, DevBatch B
         }
     }
     bool cur_is_a = false, cur_is_raw = true;
+    bool simplify_is_identity = false;
 
     // ---- a5: left-shift on the contig's reverse strand (:168-175)
     {
@@ -346,6 +347,9 @@ __global__ void __launch_bounds__(128) lift_pairs_kernel(DevStatic S, DevBatch B
         if (sink.overflow) err = ST_ERR_CAPACITY;
         else if (!some) status = ST_NONE;
         else if (W.rseg_read_len[s] != seq_len) err = ST_ERR_LENGTH;
+        // simplify_alignment_indels rewrites only I/D runs that hold both kinds; on a cleaned + compressed CIGAR without
+        // such a run it is the identity (single-kind runs are already one op, edges are already clean), so it is skipped
+        simplify_is_identity = !sink.mixed_cluster;
         rpos = lifted_pos;
         cur = OpSource{buf_b, sink.n, false};
         cur_is_a = false;
@@ -353,7 +357,7 @@ __global__ void __launch_bounds__(128) lift_pairs_kernel(DevStatic S, DevBatch B
     }
     // ---- a9: simplify (:236-243): always B (or the raw input) -> A
     {
-        const bool go = usable && !err && status == ST_LIFTED && (stage_mask & 4u);
+        const bool go = usable && !err && status == ST_LIFTED && (stage_mask & 4u) && !simplify_is_identity;
         if (__any_sync(FULL, go)) {
             const uint8_t* ref = nullptr;
             uint64_t ref_len = 0;
@@ -449,91 +453,120 @@ __global__ void __launch_bounds__(128) read_finalize_kernel(DevStatic S, DevBatc
     if ((threadIdx.x & 31) == 0 && tot) atomicAdd(&T->n_lifted, (unsigned long long)tot);
 }
 
-// Record assembly: one warp per read. Lane 0 writes the SoA fields, all lanes copy CIGAR ops from the scratch slots
-// into the dense pool (coalesced both ways) and reduce the reference span for end / bin (:278-279).
+// Record assembly (:245-282 field updates).  A warp owns 32 consecutive reads: lane l writes the SoA fields of read l's
+// records (adjacent lanes -> adjacent records -> coalesced), then the warp copies the CIGAR ops of each record from
+// its scratch slot into the dense pool cooperatively (coalesced both ways) and reduces the reference span for
+// end / bin (:278-279).
 __global__ void __launch_bounds__(256) emit_records_kernel(DevStatic S, DevBatch B, DevWork W, DevResult R, DevTotals* T,
                                                             uint32_t stage_mask) {
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;
-    if (warp >= B.n_reads) return;
-    const uint32_t r = warp;
-    const uint2 base = W.read_counts[r];
-    const uint2 next = W.read_counts[r + 1];
+    const uint32_t r = warp * 32u + lane;
+    if (warp * 32u >= B.n_reads) return;
     const uint2 total = W.read_counts[B.n_reads];
-    if (r == 0 && lane == 0) {
+    if (r == 0) {
         T->n_records = total.x;
         T->n_cigar_out = total.y;
         if (total.x > R.rec_cap) atomicOr(&T->overflow, OVF_RECORDS);
         if (total.y > R.cigar_cap) atomicOr(&T->overflow, OVF_CIGAR);
     }
     if (total.x > R.rec_cap || total.y > R.cigar_cap) return;
-    if (lane == 0) {
+    const bool live = r < B.n_reads;
+    uint32_t k = 0, p = 0, p1 = 0, primary = 0xffffffffu;
+    uint64_t op_at = 0;
+    uint16_t flag0 = 0;
+    bool has_recs = false;
+    if (live) {
+        const uint2 base = W.read_counts[r];
+        const uint2 next = W.read_counts[r + 1];
         R.read_rec_begin[r] = base.x;
         if (r == B.n_reads - 1) {
             R.read_rec_begin[B.n_reads] = total.x;
             R.rec_cigar_begin[total.x] = total.y;
         }
-    }
-    const uint32_t n_rec = next.x - base.x;
-    if (n_rec == 0) return;
-    const uint16_t flag0 = B.read_flag[r];
-    const uint32_t primary = W.read_primary[r];
-    const uint32_t s0 = B.read_seg_begin[r], s1 = B.read_seg_begin[r + 1];
-    if (primary == 0xffffffffu) {  // unmapped fallback (:317-335)
-        if (lane == 0) {
-            const uint32_t k = base.x;
-            uint16_t f = uint16_t((flag0 | 0x4) & ~0x800);
-            uint8_t flip = 0;
-            if (f & 0x10) { f ^= 0x10; flip = 1; }
-            R.rec_status[k] = 0;
-            R.rec_read_segment[k] = s0;
-            R.rec_contig_segment[k] = 0xffffffffu;
-            R.rec_tid[k] = -1;
-            R.rec_pos[k] = -1;
-            R.rec_mapq[k] = 255;
-            R.rec_flag[k] = f;
-            R.rec_bin[k] = B.read_bin[r];
-            R.rec_need_flip[k] = flip;
-            R.rec_cigar_begin[k] = base.y;
+        k = base.x;
+        op_at = base.y;
+        flag0 = B.read_flag[r];
+        primary = W.read_primary[r];
+        const uint32_t s0 = B.read_seg_begin[r], s1 = B.read_seg_begin[r + 1];
+        if (next.x > base.x) {
+            if (primary == 0xffffffffu) {  // unmapped fallback (:317-335)
+                uint16_t f = uint16_t((flag0 | 0x4) & ~0x800);
+                uint8_t flip = 0;
+                if (f & 0x10) { f ^= 0x10; flip = 1; }
+                R.rec_status[k] = 0;
+                R.rec_read_segment[k] = s0;
+                R.rec_contig_segment[k] = 0xffffffffu;
+                R.rec_tid[k] = -1;
+                R.rec_pos[k] = -1;
+                R.rec_mapq[k] = 255;
+                R.rec_flag[k] = f;
+                R.rec_bin[k] = B.read_bin[r];
+                R.rec_need_flip[k] = flip;
+                R.rec_cigar_begin[k] = op_at;
+            } else {
+                has_recs = true;
+                p = W.rseg_pair_begin[s0];
+                p1 = min(W.rseg_pair_begin[s1], W.pair_cap);
+            }
         }
-        return;
     }
-    const uint32_t p0 = W.rseg_pair_begin[s0], p1 = min(W.rseg_pair_begin[s1], W.pair_cap);
-    uint32_t k = base.x;
-    uint64_t op_at = base.y;
-    for (uint32_t p = p0; p < p1; ++p) {
-        if (W.pair_status[p] != ST_LIFTED) continue;
-        const uint32_t n = W.pair_n_out[p];
-        const uint32_t* src = W.scratch + W.pair_out_off[p];
-        uint32_t ref_span = 0;
-        for (uint32_t i = lane; i < n; i += 32) {
-            const uint32_t c = src[i];
-            R.cigar[op_at + i] = c;
-            ref_span += op_ref_adv(c);
+    // round j: every lane contributes its j-th lifted pair (most reads have exactly one)
+    for (;;) {
+        uint32_t n = 0, my_k = 0;
+        uint64_t src_off = 0, dst_off = 0;
+        int64_t pos = 0;
+        bool mine = false;
+        if (has_recs) {
+            while (p < p1 && W.pair_status[p] != ST_LIFTED) ++p;
+            if (p < p1) {
+                mine = true;
+                n = W.pair_n_out[p];
+                src_off = W.pair_out_off[p];
+                dst_off = op_at;
+                my_k = k;
+                pos = W.pair_pos[p];
+                const uint32_t g = W.pair_seg[p], s = W.pair_rseg[p];
+                const uint8_t flip = W.pair_flip[p];
+                uint16_t f = uint16_t(flag0 ^ (flip ? 0x10 : 0));
+                f |= 0x800;
+                if (p == primary) f &= ~0x800;
+                R.rec_status[k] = 1;
+                R.rec_read_segment[k] = s;
+                R.rec_contig_segment[k] = g - S.contig_seg_begin[B.rseg_contig[s]];
+                R.rec_tid[k] = (stage_mask & 2u) ? S.seg_chrom[g] : -2;
+                R.rec_pos[k] = pos;
+                R.rec_mapq[k] = S.seg_mapq[g];
+                R.rec_flag[k] = f;
+                R.rec_need_flip[k] = flip;
+                R.rec_cigar_begin[k] = op_at;
+                ++k;
+                op_at += n;
+                ++p;
+            } else {
+                has_recs = false;
+            }
         }
+        const uint32_t who = __ballot_sync(0xffffffffu, mine);
+        if (!who) break;
+        uint32_t my_span = 0;
+        for (uint32_t m = who; m; m &= m - 1) {
+            const int l2 = __ffs(m) - 1;
+            const uint32_t n2 = __shfl_sync(0xffffffffu, n, l2);
+            const uint64_t src2 = __shfl_sync(0xffffffffu, src_off, l2);
+            const uint64_t dst2 = __shfl_sync(0xffffffffu, dst_off, l2);
+            const uint32_t* src = W.scratch + src2;
+            uint32_t span = 0;
+            for (uint32_t i = lane; i < n2; i += 32) {
+                const uint32_t c = src[i];
+                R.cigar[dst2 + i] = c;
+                span += op_ref_adv(c);
+            }
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) ref_span += __shfl_down_sync(0xffffffffu, ref_span, d);
-        if (lane == 0) {
-            const uint32_t g = W.pair_seg[p], s = W.pair_rseg[p];
-            const uint32_t ctg = B.rseg_contig[s];
-            const int64_t pos = W.pair_pos[p];
-            const uint8_t flip = W.pair_flip[p];
-            uint16_t f = uint16_t(flag0 ^ (flip ? 0x10 : 0));
-            f |= 0x800;
-            if (p == primary) f &= ~0x800;
-            R.rec_status[k] = 1;
-            R.rec_read_segment[k] = s;
-            R.rec_contig_segment[k] = g - S.contig_seg_begin[ctg];
-            R.rec_tid[k] = (stage_mask & 2u) ? S.seg_chrom[g] : -2;
-            R.rec_pos[k] = pos;
-            R.rec_mapq[k] = S.seg_mapq[g];
-            R.rec_flag[k] = f;
-            R.rec_bin[k] = reg2bin(pos, pos + int64_t(ref_span));
-            R.rec_need_flip[k] = flip;
-            R.rec_cigar_begin[k] = op_at;
+            for (int d = 16; d > 0; d >>= 1) span += __shfl_xor_sync(0xffffffffu, span, d);
+            if (int(lane) == l2) my_span = span;
         }
-        ++k;
-        op_at += n;
+        if (mine) R.rec_bin[my_k] = reg2bin(pos, pos + int64_t(my_span));
     }
 }
 
@@ -572,7 +605,7 @@ void launch_lift(const DevStatic& S, const DevBatch& B, const DevWork& W, const 
     read_finalize_kernel<<<(B.n_reads + 1 + 127) / 128, 128, 0, st>>>(S, B, W, T, do_finish);
     ++*launches;
     exclusive_scan_inplace<uint2>(W.read_counts, uint64_t(B.n_reads) + 1, scan_tmp, scan_tmp_bytes_, st, launches);
-    emit_records_kernel<<<(uint64_t(B.n_reads) * 32 + 255) / 256, 256, 0, st>>>(S, B, W, R, T, stage_mask);
+    emit_records_kernel<<<(B.n_reads + 255) / 256, 256, 0, st>>>(S, B, W, R, T, stage_mask);
     ++*launches;
     mark(3);
 }

@@ -72,6 +72,8 @@ struct OpSink {
     int32_t last_match_idx = -1;  // index (in buf) of the last alignment-match op, counting the pending one
     bool seen_match = false;
     bool overflow = false;
+    bool mixed_cluster = false;   // some run of I/D ops closed so far holds both an I and a D (simplify would rewrite it)
+    uint32_t run_kinds = 0;       // bit0: I seen in the open I/D run, bit1: D seen
     uint32_t lead_del_shift = 0;  // return value of clean_up_cigar_edge_indels
 
     __device__ __forceinline__ OpSink(uint32_t* b, uint32_t c) : buf(b), cap(c) {}
@@ -98,7 +100,18 @@ struct OpSink {
         flush();
         pend_op = op;
         pend_len = len;
-        if (op_is_match(op)) last_match_idx = int32_t(n);
+        if (op == OP_I || op == OP_D) {
+            run_kinds |= op;  // OP_I = 1, OP_D = 2
+        } else {
+            mixed_cluster |= (run_kinds == 3u);
+            run_kinds = 0;
+            if (op_is_match(op)) last_match_idx = int32_t(n);
+        }
+    }
+    // hot path of the liftover: extend a pending alignment match without the general machinery
+    __device__ __forceinline__ void push_match(uint32_t len) {
+        if (pend_op == OP_M) pend_len += len;
+        else push(OP_M, len);
     }
     // trailing edge (cigar/mod.rs:282-288) + re-merge of what the conversion made adjacent
     __device__ __forceinline__ void finish() {
@@ -232,42 +245,46 @@ __device__ __forceinline__ uint32_t run_left_shift_warp(bool active, const OpSou
         }
         if (k < n_clus) clus[3 * k] = hom;
     }
-    // ---- phase C
+    // ---- phase C: every iteration ends in the same push sequence M I D M op (empty pushes cost a compare)
     if (active) {
         uint32_t match_block = 0, del = 0, ins = 0, k = 0;
         bool in_indel = false;
-        auto close = [&]() {  // end_indel (:101-148)
-            const uint32_t actual = min(match_block, clus[3 * k]);
-            ++k;
-            sink.push(OP_M, match_block - actual);
-            match_block = actual;
-            sink.push(OP_I, ins);  // nImD order (:141-147)
-            sink.push(OP_D, del);
-            in_indel = false;
-            del = 0;
-            ins = 0;
-        };
-        for (uint32_t i = 0; i < in.n; ++i) {
-            const uint32_t c = in.get(i);
+        for (uint32_t i = 0; i <= in.n; ++i) {
+            // the sentinel behaves like get_cigar's add_other(None): closes a trailing cluster, flushes the match block
+            const uint32_t c = (i < in.n) ? in.get(i) : uint32_t(OP_S);
             const uint32_t op = c & 0xfu, len = c >> 4;
+            uint32_t m1 = 0, e_ins = 0, e_del = 0, m2 = 0, o_len = 0;
             if (op == OP_D || op == OP_I) {
                 if (len > 0) {
                     in_indel = true;
                     if (op == OP_D) del += len; else ins += len;
                 }
             } else {
-                if (in_indel) close();
+                if (in_indel) {  // end_indel (:101-148)
+                    const uint32_t actual = min(match_block, clus[3 * k]);
+                    ++k;
+                    m1 = match_block - actual;
+                    match_block = actual;
+                    e_ins = ins;  // nImD order (:141-147)
+                    e_del = del;
+                    in_indel = false;
+                    del = 0;
+                    ins = 0;
+                }
                 if (op_is_match(op)) {
                     match_block += len;
                 } else {  // add_other (:155-164)
-                    sink.push(OP_M, match_block);
+                    m2 = match_block;
                     match_block = 0;
-                    sink.push(op, len);
+                    o_len = len;
                 }
             }
+            sink.push(OP_M, m1);
+            sink.push(OP_I, e_ins);
+            sink.push(OP_D, e_del);
+            sink.push(OP_M, m2);
+            sink.push(op, o_len);
         }
-        if (in_indel) close();
-        sink.push(OP_M, match_block);
         sink.finish();
     }
     return ref_pos + sink.lead_del_shift;
@@ -308,42 +325,51 @@ __device__ __forceinline__ bool run_liftover(const OpSource& in, uint32_t pos, c
     for (uint32_t i = 0; i < in.n; ++i) {
         const uint32_t c = in.get(i);
         const uint32_t op = c & 0xfu, len = c >> 4;
-        if (!((kRefMask >> op) & 1u)) {
-            if (op != OP_P) sink.push(op, len);  // I/S/H transfer verbatim (:157-160); Pad is ignored (:213)
-            continue;
-        }
-        if (len == 0) continue;
+        const bool is_ref = (kRefMask >> op) & 1u;
+        if (op == OP_P || (is_ref && len == 0)) continue;  // Pad is ignored (:213); empty ops produce no piece
         const bool is_match = op_is_match(op);
         const uint32_t main_op = is_match ? uint32_t(OP_M) : op;  // D stays D, N stays N, M/=/X become M (:103-107)
-        const uint32_t e = p + len;
+        const uint32_t e = is_ref ? p + len : p;
         uint32_t bp = p;
-        for (;;) {
-            // piece [bp, seg_end) against the current block (update_ref2_cigar_segment, :35-133)
-            const uint32_t seg_end = min(nk, e);
-            if (seg_end > bp) {
-                const uint32_t plen = seg_end - bp;
-                if (blk_kind == 2) {
-                    if (is_match && !start_set) { start = blk_v + int32_t(bp - blk_k); start_set = true; }
-                    if (end2_set && start_set) {
-                        const int32_t dlen = blk_v - end2;
-                        if (dlen > 0) sink.push(OP_D, uint32_t(dlen));
+        bool more;
+        // Every iteration ends in the SAME two pushes (gap deletion, then the piece / verbatim op): lanes sit in
+        // different arms above, but the expensive sink code is shared, not replicated per arm.
+        do {
+            uint32_t gap = 0, m_op = op, m_len = is_ref ? 0u : len;  // I/S/H transfer verbatim (:157-160)
+            more = false;
+            if (is_ref) {
+                // piece [bp, seg_end) against the current block (update_ref2_cigar_segment, :35-133)
+                const uint32_t seg_end = min(nk, e);
+                if (seg_end > bp) {
+                    const uint32_t plen = seg_end - bp;
+                    if (blk_kind == 2) {
+                        if (is_match && !start_set) { start = blk_v + int32_t(bp - blk_k); start_set = true; }
+                        if (end2_set && start_set) {
+                            const int32_t dlen = blk_v - end2;
+                            if (dlen > 0) gap = uint32_t(dlen);
+                        }
+                        end2 = blk_v + int32_t(seg_end - blk_k);
+                        end2_set = true;
+                        if (start_set) { m_op = main_op; m_len = plen; }
+                    } else if (is_match) {
+                        m_op = (blk_kind == 1) ? uint32_t(OP_I) : uint32_t(OP_S);
+                        m_len = plen;
                     }
-                    end2 = blk_v + int32_t(seg_end - blk_k);
-                    end2_set = true;
-                    if (start_set) sink.push(main_op, plen);
-                } else if (is_match) {
-                    sink.push(blk_kind == 1 ? uint32_t(OP_I) : uint32_t(OP_S), plen);
+                    bp = seg_end;
                 }
-                bp = seg_end;
+                if (nk < e) {  // cross the key: it becomes the current block
+                    const int2 b = tab[ti];
+                    blk_k = uint32_t(b.x);
+                    blk_v = b.y;
+                    blk_kind = (b.y < 0) ? 1u : 2u;
+                    ++ti;
+                    nk = (ti < t1) ? uint32_t(tab[ti].x) : INF;
+                    more = true;
+                }
             }
-            if (nk >= e) break;
-            const int2 b = tab[ti];  // cross the key: it becomes the current block
-            blk_k = uint32_t(b.x);
-            blk_v = b.y;
-            blk_kind = (b.y < 0) ? 1u : 2u;
-            ++ti;
-            nk = (ti < t1) ? uint32_t(tab[ti].x) : INF;
-        }
+            sink.push(OP_D, gap);
+            sink.push(m_op, m_len);
+        } while (more);
         p = e;
     }
     if (!start_set) return false;
@@ -431,35 +457,42 @@ __device__ __forceinline__ int64_t run_simplify_warp(bool active, const OpSource
             rec[4 * k + 3] = n;
         }
     }
-    // ---- phase C
+    // ---- phase C: every iteration ends in the same push sequence M I D M op
     if (active) {
         uint32_t del = 0, ins = 0, k = 0;
         bool in_indel = false;
         for (uint32_t i = 0; i <= in.n; ++i) {
             const uint32_t c = (i < in.n) ? in.get(i) : 0u;
             const uint32_t op = c & 0xfu, len = c >> 4;
+            uint32_t m1 = 0, e_ins = 0, e_del = 0, m2 = 0, o_len = 0;
             if (i < in.n && (op == OP_D || op == OP_I)) {
                 in_indel = true;
                 if (op == OP_D) del += len; else ins += len;
-                continue;
-            }
-            if (in_indel) {  // end_indel (:35-111)
-                if (del == 0 || ins == 0) {
-                    sink.push(del ? uint32_t(OP_D) : uint32_t(OP_I), del + ins);  // (0,0) nothing, (0,len) Ins, (len,0) Del
-                } else if (del == 1 && ins == 1) {
-                    sink.push(OP_M, 1);  // do not even look at the bases (:45-48)
-                } else {
-                    sink.push(OP_M, rec[4 * k]);
-                    sink.push(OP_I, rec[4 * k + 3]);
-                    sink.push(OP_D, rec[4 * k + 2]);
-                    sink.push(OP_M, rec[4 * k + 1]);
-                    ++k;
+            } else {
+                if (in_indel) {  // end_indel (:35-111)
+                    if (del == 0 || ins == 0) {
+                        e_ins = ins;  // (0,0) nothing, (0,len) Ins, (len,0) Del
+                        e_del = del;
+                    } else if (del == 1 && ins == 1) {
+                        m1 = 1;  // do not even look at the bases (:45-48)
+                    } else {
+                        m1 = rec[4 * k];
+                        e_ins = rec[4 * k + 3];
+                        e_del = rec[4 * k + 2];
+                        m2 = rec[4 * k + 1];
+                        ++k;
+                    }
+                    in_indel = false;
+                    del = 0;
+                    ins = 0;
                 }
-                in_indel = false;
-                del = 0;
-                ins = 0;
+                if (i < in.n) o_len = len;
             }
-            if (i < in.n) sink.push(op, len);
+            sink.push(OP_M, m1);
+            sink.push(OP_I, e_ins);
+            sink.push(OP_D, e_del);
+            sink.push(OP_M, m2);
+            sink.push(op, o_len);
         }
         sink.finish();
     }

@@ -57,10 +57,11 @@ def _load():
 # Named workloads = BASELINE.json configs, scaled where noted.
 WORKLOADS = {
     # configs[0]: 1 Mb reference, 2 contigs (one reverse-strand), 20k 15 kb reads
-    "config1": dict(seed=1001, n_chrom=1, chrom_len=1_000_000, haplotypes=2, contigs_per_chrom=1, n_reads=20_000),
+    # (adjacent I/D clusters are rare in HiFi-vs-own-assembly alignments: 0.5 % of read indels; configs[4] makes them dense)
+    "config1": dict(seed=1001, n_chrom=1, chrom_len=1_000_000, haplotypes=2, contigs_per_chrom=1, n_reads=20_000, read_cluster_frac=0.005),
     # configs[1]: chr20-scale: 64 Mb reference, ~40 contig alignments carrying SVs, 1M reads
     "chr20": dict(seed=2002, n_chrom=1, chrom_len=64_000_000, haplotypes=2, contigs_per_chrom=5, junction_per_mb=0.25,
-                  sv_per_mb=3.0, n_reads=1_000_000),
+                  sv_per_mb=3.0, n_reads=1_000_000, read_cluster_frac=0.005),
     # tiny cases for the CPU test-suite
     "tiny": dict(seed=7, n_chrom=2, chrom_len=400_000, haplotypes=2, contigs_per_chrom=2, junction_per_mb=12.0,
                  sv_per_mb=8.0, n_reads=3000, read_len_mean=6000, read_len_sd=1500, read_len_min=1000, read_len_max=12000,
