@@ -70,6 +70,7 @@ struct DevWork {
     int64_t* pair_pos = nullptr;
     uint32_t* pair_n_out = nullptr;
     uint64_t* pair_out_off = nullptr;    // where the final ops of the pair start in scratch
+    uint32_t* simplify_list = nullptr;   // [pair_cap] pairs whose lifted CIGAR needs simplify_alignment_indels
     // scratch op slots
     uint64_t scratch_cap = 0;            // in ops
     uint32_t* scratch = nullptr;
@@ -109,6 +110,7 @@ struct DevTotals {
     unsigned int overflow;               // bit0 pairs, bit1 scratch, bit2 records, bit3 cigar pool
     unsigned long long n_in_ops;         // sum of input CIGAR ops over attempted pairs   (roofline arithmetic)
     unsigned long long n_base_bytes;     // base bytes compared (both operands)            (roofline arithmetic)
+    unsigned int n_simplify;             // length of DevWork::simplify_list
 };
 
 enum : unsigned { OVF_PAIRS = 1, OVF_SCRATCH = 2, OVF_RECORDS = 4, OVF_CIGAR = 8 };

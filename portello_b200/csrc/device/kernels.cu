@@ -7,6 +7,8 @@
 // for real batches); scratch traffic is thread-private and stays in L1/L2.
 #include <cuda_runtime.h>
 
+#include <algorithm>
+
 #include "kernels.hpp"
 #include "lift_device.cuh"
 
@@ -355,9 +357,18 @@ __global__ void __launch_bounds__(128) lift_pairs_kernel(DevStatic S, DevBatch B
         cur_is_a = false;
         cur_is_raw = false;
     }
-    // ---- a9: simplify (:236-243): always B (or the raw input) -> A
-    {
-        const bool go = usable && !err && status == ST_LIFTED && (stage_mask & 4u) && !simplify_is_identity;
+    // ---- a9: simplify (:236-243).  Only the few pairs whose lifted CIGAR holds a mixed I/D run need it: they are
+    //      appended to a worklist and finished by simplify_pairs_kernel with all lanes busy (inline, the stage ran at
+    //      1.9 active threads per instruction and cost 22 % of this kernel, ncu r01g).
+    bool deferred = false;
+    if (usable && !err && status == ST_LIFTED && (stage_mask & 4u) && !simplify_is_identity) {
+        if (stage_mask & 2u) {
+            deferred = true;
+            W.simplify_list[atomicAdd(&T->n_simplify, 1u)] = p;
+        }
+    }
+    {   // stage tests without the liftover stage: simplify inline, (raw input or A) -> A
+        const bool go = usable && !err && status == ST_LIFTED && (stage_mask & 4u) && !(stage_mask & 2u);
         if (__any_sync(FULL, go)) {
             const uint8_t* ref = nullptr;
             uint64_t ref_len = 0;
@@ -366,7 +377,7 @@ __global__ void __launch_bounds__(128) lift_pairs_kernel(DevStatic S, DevBatch B
                 const int32_t chrom = S.seg_chrom[g];
                 ref = S.ref + S.chrom_off[chrom];
                 ref_len = S.chrom_off[chrom + 1] - S.chrom_off[chrom];
-                if (cur_is_a) {  // stage tests only (shift without liftover): move the input out of the way
+                if (cur_is_a) {  // shift without liftover: move the input out of the way
                     const uint32_t n = min(cur.n, cap_b);
                     for (uint32_t i = 0; i < n; ++i) buf_b[i] = buf_a[i];
                     cur = OpSource{buf_b, n, false};
@@ -394,6 +405,7 @@ __global__ void __launch_bounds__(128) lift_pairs_kernel(DevStatic S, DevBatch B
     if (valid) {
         if (err) status = err;
         const bool ok = (status == ST_LIFTED);
+        if (ok && deferred) status = ST_PENDING_SIMPLIFY;
         W.pair_status[p] = int8_t(status);
         W.pair_flip[p] = need_flip;
         W.pair_pos[p] = ok ? rpos : 0;
@@ -411,6 +423,61 @@ __global__ void __launch_bounds__(128) lift_pairs_kernel(DevStatic S, DevBatch B
         if (a) atomicAdd(&T->n_in_ops, (unsigned long long)a);
         if (b) atomicAdd(&T->n_base_bytes, (unsigned long long)b);
     }
+}
+
+// a9 for the worklist of pairs whose lifted CIGAR holds a mixed I/D run: dense, warp-collective, B -> A.
+__global__ void __launch_bounds__(128) simplify_pairs_kernel(DevStatic S, DevBatch B, DevWork W, DevTotals* T) {
+    const uint32_t n = min(T->n_simplify, W.pair_cap);
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+    PairCounters cnt;
+    for (uint32_t base = warp * 32u; base < n; base += n_warps * 32u) {
+        const uint32_t t = base + lane;
+        const bool active = t < n;
+        uint32_t p = 0, cap_b = 0, n_in = 0;
+        uint32_t* buf_a = nullptr;
+        uint32_t* rec = nullptr;
+        const uint8_t* ref = nullptr;
+        uint64_t ref_len = 0;
+        int64_t rpos = 0;
+        OpSource cur{nullptr, 0, false};
+        ReadBases read{nullptr, 0, false};
+        uint32_t sink_cap = 0;
+        if (active) {
+            p = W.simplify_list[t];
+            const uint32_t s = W.pair_rseg[p], g = W.pair_seg[p], r = W.rseg_read[s];
+            const uint64_t slot0 = W.pair_slot_begin[p], slot1 = W.pair_slot_begin[p + 1];
+            cap_b = W.pair_cap_b[p];
+            const uint32_t cap_a = uint32_t(slot1 - slot0) - cap_b;
+            uint32_t* buf_b = W.scratch + slot0;
+            buf_a = buf_b + cap_b;
+            n_in = W.pair_n_out[p];
+            cur = OpSource{buf_b, n_in, false};
+            rpos = W.pair_pos[p];
+            read = ReadBases{B.seq4 + B.read_seq_off[r], B.read_seq_len[r], W.pair_flip[p] != 0};
+            const int32_t chrom = S.seg_chrom[g];
+            ref = S.ref + S.chrom_off[chrom];
+            ref_len = S.chrom_off[chrom + 1] - S.chrom_off[chrom];
+            const uint32_t n_rec = 4u * ((cap_a - cap_b - 8u) / 6u);
+            rec = buf_a + (cap_a - n_rec);
+            sink_cap = uint32_t(rec - buf_a);
+        }
+        int err = 0;
+        OpSink sink(buf_a, sink_cap);
+        const int64_t simp = run_simplify_warp(active, cur, rpos, ref, ref_len, read, rec, sink, cnt, err);
+        if (active) {
+            if (sink.overflow) err = ST_ERR_CAPACITY;
+            W.pair_status[p] = int8_t(err ? err : ST_LIFTED);
+            W.pair_pos[p] = err ? 0 : simp;
+            W.pair_n_out[p] = err ? 0u : sink.n;
+            W.pair_out_off[p] = uint64_t(buf_a - W.scratch);
+        }
+    }
+    uint32_t b = cnt.base_bytes;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) b += __shfl_down_sync(FULL, b, d);
+    if (lane == 0 && b) atomicAdd(&T->n_base_bytes, (unsigned long long)b);
 }
 
 // a10 (field part): finish_remapped_alignment_set (src/read_alignment_scanner.rs:310-366): record counts per read,
@@ -572,7 +639,7 @@ __global__ void __launch_bounds__(256) emit_records_kernel(DevStatic S, DevBatch
 
 __global__ void totals_init_kernel(DevTotals* T) {
     T->n_pairs = 0; T->scratch_needed = 0; T->n_records = 0; T->n_cigar_out = 0; T->n_lifted = 0; T->n_errors = 0;
-    T->first_error_read = 0x7fffffffffffffffLL; T->first_error_status = 0; T->overflow = 0; T->n_in_ops = 0; T->n_base_bytes = 0;
+    T->first_error_read = 0x7fffffffffffffffLL; T->first_error_status = 0; T->overflow = 0; T->n_in_ops = 0; T->n_base_bytes = 0; T->n_simplify = 0;
 }
 __global__ void scratch_needed_kernel(DevWork W, DevTotals* T) {
     const uint32_t np = min(uint32_t(T->n_pairs), W.pair_cap);
@@ -601,6 +668,12 @@ void launch_lift(const DevStatic& S, const DevBatch& B, const DevWork& W, const 
     mark(1);
     lift_pairs_kernel<<<(W.pair_cap + 127) / 128, 128, 0, st>>>(S, B, W, T, stage_mask);
     ++*launches;
+    if ((stage_mask & 6u) == 6u) {
+        // worklist length is only known on the device: a fixed grid strides over it (a few % of the pairs)
+        const unsigned blocks = unsigned(std::min<uint64_t>((uint64_t(W.pair_cap) + 127) / 128, 148ull * 16));
+        simplify_pairs_kernel<<<blocks, 128, 0, st>>>(S, B, W, T);
+        ++*launches;
+    }
     mark(2);
     read_finalize_kernel<<<(B.n_reads + 1 + 127) / 128, 128, 0, st>>>(S, B, W, T, do_finish);
     ++*launches;

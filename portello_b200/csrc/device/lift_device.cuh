@@ -30,7 +30,7 @@ constexpr uint32_t kReadMask = kMatchMask | (1u << OP_I) | (1u << OP_S) | (1u <<
 constexpr uint32_t NO_OP = 0xffffffffu;
 constexpr uint32_t FULL = 0xffffffffu;
 
-constexpr int ST_LIFTED = 1, ST_NONE = 0, ST_ERR_LENGTH = -1, ST_ERR_BOUNDS = -2, ST_ERR_CAPACITY = -3;
+constexpr int ST_LIFTED = 1, ST_NONE = 0, ST_PENDING_SIMPLIFY = 2, ST_ERR_LENGTH = -1, ST_ERR_BOUNDS = -2, ST_ERR_CAPACITY = -3;
 
 __device__ __forceinline__ bool op_is_match(uint32_t op) { return (kMatchMask >> op) & 1u; }
 __device__ __forceinline__ uint32_t op_ref_adv(uint32_t c) { return ((kRefMask >> (c & 0xf)) & 1u) ? (c >> 4) : 0u; }
