@@ -161,10 +161,18 @@ void lift_chunk(const ptl_ctx* ctx, const ptl_batch* b, uint32_t r0, uint32_t r1
             splits.push_back(std::move(g));
         }
         std::vector<LiftedRecord> recs;
+        const PairStats before = out.stats;
         try {
             recs = lift_read(ctx->reference, ctx->contig_len, ctx->contigs, rec, splits, opt, out.stats);
         } catch (const Panic& p) {
             // The reference aborts the run here. Record the error and emit the unmapped fallback so shapes stay defined.
+            // Counters follow the ABI's definition: n_pairs = all enumerated pairs, n_lifted = lifted pairs of reads
+            // that produced records.
+            out.stats.n_lifted = before.n_lifted;
+            out.stats.n_out_ops = before.n_out_ops;
+            out.stats.n_pairs = before.n_pairs;
+            for (const auto& g : splits)
+                out.stats.n_pairs += get_contig_split_segments_from_read_mapping(g, ctx->contigs.at(g.chrom_index).ordered_contig_segment_info).size();
             out.n_errors++;
             if (out.first_error_read < 0) {
                 out.first_error_read = r;

@@ -507,7 +507,7 @@ __global__ void __launch_bounds__(128) read_finalize_kernel(DevStatic S, DevBatc
         lifted = 0; ops = 0; primary = 0xffffffffu;
     }
     uint32_t n_rec = lifted;
-    if (lifted == 0 && do_finish) n_rec = 1;
+    if (lifted == 0 && (do_finish || first_err)) n_rec = 1;  // a panicking read always yields the fallback record
     if (!do_finish) primary = 0xffffffffu - 1u;  // stage tests: no primary is chosen, no fallback
     if (live) {
         W.read_counts[r] = make_uint2(n_rec, ops);
