@@ -83,7 +83,7 @@ struct Slot {
         d_rseg_is_fwd, d_rseg_cigar_begin, d_rseg_cigar_len, d_cigar, d_seq4;
     // work
     DBuf w_rseg_read, w_rseg_pair_begin, w_rseg_ref_len, w_rseg_n_id, w_rseg_read_len, w_pair_cap_b, w_pair_rseg, w_pair_seg, w_pair_slot_begin, w_pair_status, w_pair_flip,
-        w_pair_pos, w_pair_n_out, w_pair_out_off, w_simplify_list, w_scratch, w_read_counts, w_read_primary, w_scan_tmp, w_totals;
+        w_pair_pos, w_pair_n_out, w_pair_bin, w_pair_out_off, w_simplify_list, w_scratch, w_read_counts, w_read_primary, w_scan_tmp, w_totals;
     // results (device)
     DBuf r_read_rec_begin, r_status, r_rseg, r_cseg, r_tid, r_pos, r_mapq, r_flag, r_bin, r_flip, r_cigar_begin, r_cigar;
     // results (pinned host)
@@ -267,6 +267,7 @@ void size_work(Slot& sl, uint32_t want_pairs, uint64_t want_scratch, uint32_t wa
     sl.w_pair_flip.ensure(size_t(pc), st);
     sl.w_pair_pos.ensure(size_t(pc) * 8, st);
     sl.w_pair_n_out.ensure(size_t(pc) * 4, st);
+    sl.w_pair_bin.ensure(size_t(pc) * 2, st);
     sl.w_pair_out_off.ensure(size_t(pc) * 8, st);
     sl.w_simplify_list.ensure(size_t(pc) * 4, st);
     W.pair_cap = pc;
@@ -278,6 +279,7 @@ void size_work(Slot& sl, uint32_t want_pairs, uint64_t want_scratch, uint32_t wa
     W.pair_flip = sl.w_pair_flip.as<uint8_t>();
     W.pair_pos = sl.w_pair_pos.as<int64_t>();
     W.pair_n_out = sl.w_pair_n_out.as<uint32_t>();
+    W.pair_bin = sl.w_pair_bin.as<uint16_t>();
     W.pair_out_off = sl.w_pair_out_off.as<uint64_t>();
     W.simplify_list = sl.w_simplify_list.as<uint32_t>();
     const uint64_t sc = std::max(W.scratch_cap, want_scratch);
@@ -479,7 +481,7 @@ void ptl_destroy(ptl_ctx* ctx) {
         for (DBuf* b : {&sl.d_read_flag, &sl.d_read_mapq, &sl.d_read_bin, &sl.d_read_seq_len, &sl.d_read_seq_off, &sl.d_read_seg_begin,
                         &sl.d_rseg_contig, &sl.d_rseg_pos, &sl.d_rseg_is_fwd, &sl.d_rseg_cigar_begin, &sl.d_rseg_cigar_len, &sl.d_cigar,
                         &sl.d_seq4, &sl.w_rseg_read, &sl.w_rseg_pair_begin, &sl.w_rseg_ref_len, &sl.w_rseg_n_id, &sl.w_rseg_read_len, &sl.w_pair_cap_b, &sl.w_pair_rseg, &sl.w_pair_seg,
-                        &sl.w_pair_slot_begin, &sl.w_pair_status, &sl.w_pair_flip, &sl.w_pair_pos, &sl.w_pair_n_out, &sl.w_pair_out_off, &sl.w_simplify_list,
+                        &sl.w_pair_slot_begin, &sl.w_pair_status, &sl.w_pair_flip, &sl.w_pair_pos, &sl.w_pair_n_out, &sl.w_pair_bin, &sl.w_pair_out_off, &sl.w_simplify_list,
                         &sl.w_scratch, &sl.w_read_counts, &sl.w_read_primary, &sl.w_scan_tmp, &sl.w_totals, &sl.r_read_rec_begin,
                         &sl.r_status, &sl.r_rseg, &sl.r_cseg, &sl.r_tid, &sl.r_pos, &sl.r_mapq, &sl.r_flag, &sl.r_bin, &sl.r_flip,
                         &sl.r_cigar_begin, &sl.r_cigar})

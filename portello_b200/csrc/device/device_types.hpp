@@ -69,6 +69,7 @@ struct DevWork {
     uint8_t* pair_flip = nullptr;
     int64_t* pair_pos = nullptr;
     uint32_t* pair_n_out = nullptr;
+    uint16_t* pair_bin = nullptr;        // bam_reg2bin(pos, end) of the final record
     uint64_t* pair_out_off = nullptr;    // where the final ops of the pair start in scratch
     uint32_t* simplify_list = nullptr;   // [pair_cap] pairs whose lifted CIGAR needs simplify_alignment_indels
     // scratch op slots

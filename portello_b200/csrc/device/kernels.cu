@@ -316,6 +316,7 @@ __global__ void __launch_bounds__(128) lift_pairs_kernel(DevStatic S, DevBatch B
     }
     bool cur_is_a = false, cur_is_raw = true;
     bool simplify_is_identity = false;
+    uint32_t span = 0;  // reference span of the final CIGAR (end = pos + span, :278)
 
     // ---- a5: left-shift on the contig's reverse strand (:168-175)
     {
@@ -331,6 +332,7 @@ __global__ void __launch_bounds__(128) lift_pairs_kernel(DevStatic S, DevBatch B
                                                          go ? uint32_t(S.contig_len[ctg]) : 0u, read, buf_b, sink, cnt, err);
             if (go) {
                 cpos = shifted;
+                span = sink.ref_span;
                 if (sink.overflow) err = ST_ERR_CAPACITY;
                 cur = OpSource{buf_a, sink.n, false};
                 cur_is_a = true;
@@ -352,6 +354,7 @@ __global__ void __launch_bounds__(128) lift_pairs_kernel(DevStatic S, DevBatch B
         // simplify_alignment_indels rewrites only I/D runs that hold both kinds; on a cleaned + compressed CIGAR without
         // such a run it is the identity (single-kind runs are already one op, edges are already clean), so it is skipped
         simplify_is_identity = !sink.mixed_cluster;
+        span = sink.ref_span;
         rpos = lifted_pos;
         cur = OpSource{buf_b, sink.n, false};
         cur_is_a = false;
@@ -389,6 +392,7 @@ __global__ void __launch_bounds__(128) lift_pairs_kernel(DevStatic S, DevBatch B
             const int64_t simp = run_simplify_warp(go, cur, rpos, ref, ref_len, read, rec, sink, cnt, err);
             if (go) {
                 rpos = simp;
+                span = sink.ref_span;
                 if (sink.overflow) err = ST_ERR_CAPACITY;
                 cur = OpSource{buf_a, sink.n, false};
                 cur_is_a = true;
@@ -399,7 +403,7 @@ __global__ void __launch_bounds__(128) lift_pairs_kernel(DevStatic S, DevBatch B
     if (usable && !err && status == ST_LIFTED && cur_is_raw) {
         // stage tests with every stage disabled for this pair: hand the (possibly reversed) input back verbatim
         const uint32_t n = min(cur.n, cap_a);
-        for (uint32_t i = 0; i < n; ++i) buf_a[i] = cur.get(i);
+        for (uint32_t i = 0; i < n; ++i) { const uint32_t c = cur.get(i); buf_a[i] = c; span += op_ref_adv(c); }
         cur = OpSource{buf_a, n, false};
     }
     if (valid) {
@@ -411,6 +415,7 @@ __global__ void __launch_bounds__(128) lift_pairs_kernel(DevStatic S, DevBatch B
         W.pair_pos[p] = ok ? rpos : 0;
         W.pair_n_out[p] = ok ? cur.n : 0u;
         W.pair_out_off[p] = ok ? uint64_t(cur.p - W.scratch) : slot0;
+        W.pair_bin[p] = ok ? reg2bin(rpos, rpos + int64_t(span)) : uint16_t(0);  // bam_reg2bin(pos, end) (:278-279)
     }
     // roofline arithmetic: input ops walked + base bytes compared (warp-aggregated atomics)
     uint32_t a = n_in_ops, b = cnt.base_bytes;
@@ -472,6 +477,7 @@ __global__ void __launch_bounds__(128) simplify_pairs_kernel(DevStatic S, DevBat
             W.pair_pos[p] = err ? 0 : simp;
             W.pair_n_out[p] = err ? 0u : sink.n;
             W.pair_out_off[p] = uint64_t(buf_a - W.scratch);
+            W.pair_bin[p] = err ? uint16_t(0) : reg2bin(simp, simp + int64_t(sink.ref_span));
         }
     }
     uint32_t b = cnt.base_bytes;
@@ -578,11 +584,12 @@ __global__ void __launch_bounds__(256) emit_records_kernel(DevStatic S, DevBatch
             }
         }
     }
-    // round j: every lane contributes its j-th lifted pair (most reads have exactly one)
+    // round j: every lane contributes its j-th lifted pair (most reads have exactly one); the ops of the <= 32 records
+    // of a round are copied as ONE flat index space so that every lane moves an op per iteration (independent loads,
+    // coalesced stores) instead of one record at a time
     for (;;) {
-        uint32_t n = 0, my_k = 0;
+        uint32_t n = 0;
         uint64_t src_off = 0, dst_off = 0;
-        int64_t pos = 0;
         bool mine = false;
         if (has_recs) {
             while (p < p1 && W.pair_status[p] != ST_LIFTED) ++p;
@@ -591,8 +598,6 @@ __global__ void __launch_bounds__(256) emit_records_kernel(DevStatic S, DevBatch
                 n = W.pair_n_out[p];
                 src_off = W.pair_out_off[p];
                 dst_off = op_at;
-                my_k = k;
-                pos = W.pair_pos[p];
                 const uint32_t g = W.pair_seg[p], s = W.pair_rseg[p];
                 const uint8_t flip = W.pair_flip[p];
                 uint16_t f = uint16_t(flag0 ^ (flip ? 0x10 : 0));
@@ -602,9 +607,10 @@ __global__ void __launch_bounds__(256) emit_records_kernel(DevStatic S, DevBatch
                 R.rec_read_segment[k] = s;
                 R.rec_contig_segment[k] = g - S.contig_seg_begin[B.rseg_contig[s]];
                 R.rec_tid[k] = (stage_mask & 2u) ? S.seg_chrom[g] : -2;
-                R.rec_pos[k] = pos;
+                R.rec_pos[k] = W.pair_pos[p];
                 R.rec_mapq[k] = S.seg_mapq[g];
                 R.rec_flag[k] = f;
+                R.rec_bin[k] = W.pair_bin[p];
                 R.rec_need_flip[k] = flip;
                 R.rec_cigar_begin[k] = op_at;
                 ++k;
@@ -614,26 +620,33 @@ __global__ void __launch_bounds__(256) emit_records_kernel(DevStatic S, DevBatch
                 has_recs = false;
             }
         }
-        const uint32_t who = __ballot_sync(0xffffffffu, mine);
-        if (!who) break;
-        uint32_t my_span = 0;
-        for (uint32_t m = who; m; m &= m - 1) {
-            const int l2 = __ffs(m) - 1;
-            const uint32_t n2 = __shfl_sync(0xffffffffu, n, l2);
-            const uint64_t src2 = __shfl_sync(0xffffffffu, src_off, l2);
-            const uint64_t dst2 = __shfl_sync(0xffffffffu, dst_off, l2);
-            const uint32_t* src = W.scratch + src2;
-            uint32_t span = 0;
-            for (uint32_t i = lane; i < n2; i += 32) {
-                const uint32_t c = src[i];
-                R.cigar[dst2 + i] = c;
-                span += op_ref_adv(c);
-            }
+        if (!__any_sync(0xffffffffu, mine)) break;
+        // inclusive prefix of op counts over the lanes
+        uint32_t incl = n;
 #pragma unroll
-            for (int d = 16; d > 0; d >>= 1) span += __shfl_xor_sync(0xffffffffu, span, d);
-            if (int(lane) == l2) my_span = span;
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (int(lane) >= d) incl += o;
         }
-        if (mine) R.rec_bin[my_k] = reg2bin(pos, pos + int64_t(my_span));
+        const uint32_t total_ops = __shfl_sync(0xffffffffu, incl, 31);
+        const uint32_t excl = incl - n;
+        // the destination is contiguous across the lanes of a round only if every read has a single record; use each
+        // record's own (src, dst) pair to stay general
+        for (uint32_t base = 0; base < total_ops; base += 32) {
+            const uint32_t i = base + lane;
+            // owner = last lane whose exclusive prefix <= i (binary search over the warp's registers)
+            uint32_t lo = 0, hi = 31;
+#pragma unroll
+            for (int it = 0; it < 5; ++it) {
+                const uint32_t mid = (lo + hi + 1) >> 1;
+                const uint32_t ex_mid = __shfl_sync(0xffffffffu, excl, mid);
+                if (ex_mid <= i) lo = mid; else hi = mid - 1;
+            }
+            const uint64_t s2 = __shfl_sync(0xffffffffu, src_off, lo);
+            const uint64_t d2 = __shfl_sync(0xffffffffu, dst_off, lo);
+            const uint32_t e2 = __shfl_sync(0xffffffffu, excl, lo);
+            if (i < total_ops) R.cigar[d2 + (i - e2)] = W.scratch[s2 + (i - e2)];
+        }
     }
 }
 

@@ -75,6 +75,7 @@ struct OpSink {
     bool mixed_cluster = false;   // some run of I/D ops closed so far holds both an I and a D (simplify would rewrite it)
     uint32_t run_kinds = 0;       // bit0: I seen in the open I/D run, bit1: D seen
     uint32_t lead_del_shift = 0;  // return value of clean_up_cigar_edge_indels
+    uint32_t ref_span = 0;        // reference bases consumed by the stored ops = get_alignment_end - pos (after finish())
 
     __device__ __forceinline__ OpSink(uint32_t* b, uint32_t c) : buf(b), cap(c) {}
 
@@ -83,6 +84,7 @@ struct OpSink {
             if (n < cap) buf[n] = (pend_len << 4) | pend_op;
             else overflow = true;
             ++n;
+            if ((kRefMask >> pend_op) & 1u) ref_span += pend_len;
             pend_op = NO_OP;
         }
     }
@@ -122,7 +124,7 @@ struct OpSink {
         for (uint32_t i = start; i < n; ++i) {
             uint32_t c = buf[i];
             uint32_t op = c & 0xfu;
-            if (op == OP_D) continue;
+            if (op == OP_D) { ref_span -= c >> 4; continue; }
             if (op == OP_I) { op = OP_S; c = (c & ~0xfu) | OP_S; }
             if (prev != NO_OP && (prev & 0xfu) == op) {
                 if (op != OP_P) prev += c & ~0xfu;
