@@ -29,6 +29,12 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
+WORKLOAD_DOC = {
+    "config1": "BASELINE.json configs[0], 1 Mb reference, 2 contigs, 20k 15 kb HiFi reads",
+    "chr20": "BASELINE.json configs[1], chr20-scale synthetic, ~40 contig alignments carrying SVs, 15 kb HiFi reads",
+    "wg": "BASELINE.json configs[2], whole-genome synthetic diploid assembly, ~500 contigs per haplotype, 15 kb HiFi reads",
+    "stress": "BASELINE.json configs[4], fragmented assembly, 100 kb reads with dense clustered indels and SA segments",
+}
 METRIC = "read alignments lifted/sec"
 UNIT = "alignments/s"
 
@@ -333,8 +339,15 @@ def main():
     alg_bytes, table_bytes = algorithmic_bytes(cnt, n_table, n_segments)
     lift_ms_avg = stage_ms.get("lift_pairs", float("nan"))
     achieved = alg_bytes / (lift_ms_avg / 1e3) / 1e9
+    traffic = None
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum of the same kernel on the same workload, from the committed ncu capture
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["lift_pairs_kernel"]
+        if tj["workload"] == args.workload and tj["reads_per_gpu"] == n_reads:
+            traffic = tj["dram_bytes_per_launch"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": "lift_pairs_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg_bytes), "table_bytes_once": int(table_bytes),
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg_bytes), "table_bytes_once": int(table_bytes),
                 "kernel_ms": lift_ms_avg, "stage_ms": stage_ms,
                 "whole_step_frac": alg_bytes / (dev_ms / 1e3) / 1e9 / peak}
 
@@ -357,8 +370,9 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": dev_ms_max, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: BASELINE.json configs[1] (64 Mb reference, {s.contig_records.n_records} contig alignment records -> "
-                                   f"{n_segments} segments after trim/join, {n_reads} HiFi reads per GPU)",
+            "config": {"workload": f"{args.workload}: {WORKLOAD_DOC.get(args.workload, 'custom')} ({s.n_chrom} x {int(s.chrom_len[0])} bp reference, "
+                                   f"{s.contig_records.n_records} contig alignment records -> {n_segments} segments after trim/join, "
+                                   f"{n_reads} reads per GPU)",
                        "reads_per_gpu": int(n_reads), "pairs_per_step_per_gpu": int(cnt["n_pairs"]), "lifted_per_step_per_gpu": int(cnt["n_lifted"]),
                        "l2_policy": "inputs larger than L2 (CIGAR pools + op scratch > 126 MB per step)", "sharding": "by contig set, no collective",
                        "e2e_pipeline": f"{len(chunks)} batches of {args.chunk} reads over 3 slots", "e2e_seq_zero_copy": bool(best_zc),

@@ -62,6 +62,9 @@ WORKLOADS = {
     # configs[1]: chr20-scale: 64 Mb reference, ~40 contig alignments carrying SVs, 1M reads
     "chr20": dict(seed=2002, n_chrom=1, chrom_len=64_000_000, haplotypes=2, contigs_per_chrom=5, junction_per_mb=0.25,
                   sv_per_mb=3.0, n_reads=1_000_000, read_cluster_frac=0.005),
+    # configs[2]: whole-genome synthetic diploid assembly (~3.1 Gb reference, ~500 contigs per haplotype), 30x HiFi = ~6M reads
+    "wg": dict(seed=3003, n_chrom=24, chrom_len=130_000_000, haplotypes=2, contigs_per_chrom=21, rev_contig_frac=0.45, junction_per_mb=0.25,
+               sv_per_mb=3.0, n_reads=6_000_000, read_cluster_frac=0.005),
     # tiny cases for the CPU test-suite
     "tiny": dict(seed=7, n_chrom=2, chrom_len=400_000, haplotypes=2, contigs_per_chrom=2, junction_per_mb=12.0,
                  sv_per_mb=8.0, n_reads=3000, read_len_mean=6000, read_len_sd=1500, read_len_min=1000, read_len_max=12000,
