@@ -151,23 +151,41 @@ struct PairCounters {
 };
 
 // ------------------------------------------------------------------------------------------------------------------
-// One round trip of the left homology walk: W independent (ref, read) byte pairs are loaded, then compared in order.
-// Indices past `limit` are clamped (loaded, never compared).
-template <int W>
-__device__ __forceinline__ void walk_homology(const uint8_t* __restrict__ ref_seq, const ReadBases& read, uint32_t ref_end, uint32_t read_end,
-                                              uint32_t limit, uint32_t& hom, bool& walking, PairCounters& cnt) {
-    uint8_t rb[W], qb[W];
+// n_bytes (<= 8) bytes at an arbitrary address, little-endian in the result, with one aligned 64-bit load, or two when
+// the range straddles an 8-byte boundary.  An aligned word that holds at least one requested byte never leaves the
+// allocation granule (256 B device, 4 KB pinned host), so no byte outside the buffer's allocation is touched.
+__device__ __forceinline__ uint64_t load_bytes_le(const uint8_t* a, uint32_t n_bytes) {
+    const unsigned long long addr = reinterpret_cast<unsigned long long>(a);
+    const uint64_t* base = reinterpret_cast<const uint64_t*>(addr & ~7ull);
+    const uint32_t off = uint32_t(addr & 7ull);
+    uint64_t w = base[0] >> (off * 8u);
+    if (off + n_bytes > 8u) w |= base[1] << (64u - off * 8u);  // off > 0 here
+    return w;
+}
+
+// One round trip of the left homology walk: up to 8 (ref, read) base pairs are fetched with ONE word load per side (two
+// if the window straddles an 8-byte boundary) and compared in order.  In zero-copy mode this is one PCIe read per
+// probe instead of one per base.
+__device__ __forceinline__ void walk_homology8(const uint8_t* __restrict__ ref_seq, const ReadBases& read, uint32_t ref_end, uint32_t read_end,
+                                               uint32_t limit, uint32_t& hom, bool& walking, PairCounters& cnt) {
+    const uint32_t nv = min(8u, limit - hom);  // >= 1 while walking
+    // reference side: ASCII bytes ref_seq[rhi - q], q = 0..nv-1
+    const uint32_t rhi = ref_end - 1u - hom, rlo = rhi - (nv - 1u);
+    const uint64_t rw = load_bytes_le(ref_seq + rlo, nv);
+    // read side: 4-bit bases at stored positions jhi - q (forward view) or jlo + q (reverse-complement view)
+    uint32_t jlo, jhi;
+    if (!read.flip) { jhi = read_end - 1u - hom; jlo = jhi - (nv - 1u); }
+    else { jlo = read.len - read_end + hom; jhi = jlo + (nv - 1u); }
+    const uint32_t b0 = jlo >> 1;
+    const uint64_t qw = load_bytes_le(read.seq4 + b0, (jhi >> 1) - b0 + 1u);
 #pragma unroll
-    for (int q = 0; q < W; ++q) {
-        const uint32_t idx = min(hom + uint32_t(q), limit - 1u);
-        rb[q] = ref_seq[ref_end - 1u - idx];
-        qb[q] = read.at(read_end - 1u - idx);
-    }
-#pragma unroll
-    for (int q = 0; q < W; ++q) {
-        if (walking && hom < limit) {
+    for (uint32_t q = 0; q < 8; ++q) {
+        if (walking && q < nv) {
+            const uint32_t rb = uint32_t(rw >> (8u * (nv - 1u - q))) & 0xffu;
+            const uint32_t j = read.flip ? jlo + q : jhi - q;
+            const uint32_t nib = uint32_t(qw >> (8u * ((j >> 1) - b0) + ((j & 1u) ? 0u : 4u))) & 0xfu;
             cnt.base_bytes += 2;
-            if (rb[q] != qb[q]) walking = false;
+            if (rb != uint32_t(ReadBases::decode(nib, read.flip))) walking = false;
             else ++hom;
         }
     }
@@ -237,13 +255,10 @@ __device__ __forceinline__ uint32_t run_left_shift_warp(bool active, const OpSou
             limit = clus[3 * k + 2];
         }
         bool walking = limit > 0;
-        // probe 4 bases first (almost every walk ends there), then 8 per round trip: long walks only happen in
-        // repeats or reducible I/D clusters, and they hold the whole warp
-        if (__any_sync(FULL, walking)) {
-            if (walking) walk_homology<4>(ref_seq, read, ref_end, read_end, limit, hom, walking, cnt);
-            while (__any_sync(FULL, walking)) {
-                if (walking) walk_homology<8>(ref_seq, read, ref_end, read_end, limit, hom, walking, cnt);
-            }
+        // 8 bases per round trip (almost every walk ends in the first): long walks only happen in repeats or reducible
+        // I/D clusters, and they hold the whole warp
+        while (__any_sync(FULL, walking)) {
+            if (walking) walk_homology8(ref_seq, read, ref_end, read_end, limit, hom, walking, cnt);
         }
         if (k < n_clus) clus[3 * k] = hom;
     }
