@@ -169,3 +169,34 @@ def test_region_segments_shard_units_reg2bin(oracle):
         loads = np.bincount(owner, weights=w, minlength=n)
         assert owner.max() < n and loads.max() <= loads.mean() + w.max()  # LPT bound
         assert np.array_equal(owner, L.shard_units(w, n))                 # deterministic: every rank computes the same map
+
+
+def test_format_sa_tags_matches_oracle_text(oracle):
+    """a10 text part: SA:Z strings built by the product's host helper from a result == the oracle's
+    (get_sa_tag_segment + concatenation, src/read_alignment_scanner.rs:292-301,349-363)."""
+    import ctypes as C
+
+    s = synth.make("tiny", seed=29, n_reads=1200, read_sa_frac=0.3, junction_per_mb=10.0)
+    octx = helpers.oracle_context(s)
+    pb = helpers.pack(s)
+    O = oracle
+    assert O._lift_submit(octx.h, 0, C.byref(pb.c)) == 0
+    r = abi.ResultC()
+    assert O._lift_wait(octx.h, 0, C.byref(r)) == 0
+    got = lib.load().format_sa_tags(r, s.chrom_names)
+    want = lib.format_sa_tags_call(O.dll.ptl_oracle_format_sa_tags, r, s.chrom_names)
+    assert got == want
+    res = abi.Result.from_c(r)
+    multi = [k for rd in range(len(res.read_rec_begin) - 1) for k in range(res.read_rec_begin[rd], res.read_rec_begin[rd + 1])
+             if res.read_rec_begin[rd + 1] - res.read_rec_begin[rd] > 1]
+    assert len(multi) > 20 and all(got[k].endswith(",0;") for k in multi)
+    single_unmapped = [k for k in range(res.n_records) if res.rec_status[k] == 0]
+    assert all(got[k] == "" for k in single_unmapped)
+    # spot-check the format of one entry: chrom,pos+1,strand,CIGAR,mapq,0;
+    k = multi[0]
+    rd = int(np.searchsorted(res.read_rec_begin, k, side="right") - 1)
+    others = [j for j in range(res.read_rec_begin[rd], res.read_rec_begin[rd + 1]) if j != k]
+    j = others[0]
+    first = got[k].split(";")[0].split(",")
+    assert first[0] == s.chrom_names[res.rec_tid[j]] and int(first[1]) == int(res.rec_pos[j]) + 1
+    assert first[2] == ("-" if res.rec_flag[j] & 0x10 else "+") and first[3] == res.record_cigar(j) and int(first[4]) == int(res.rec_mapq[j])
