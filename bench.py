@@ -317,8 +317,24 @@ def main():
 
     small_h2d = sum(int(ch.c.n_reads) * (2 + 1 + 2 + 4 + 8 + 4) + int(ch.c.n_read_segments) * (4 + 8 + 1 + 8 + 4) + int(ch.c.n_cigar) * 4 for ch in chunks)
     seq_h2d = sum(int(ch.c.seq4_bytes) for ch in chunks)
+    def result_digest(zero_copy):
+        """Order-sensitive checksum of every result array of the whole batch (outside the timed region)."""
+        ctx.set_seq_zero_copy(zero_copy)
+        ctx.submit_c(whole.c, 0)
+        r = abi.Result.from_c(ctx.wait_c(0), copy=False)
+        acc = np.uint64(1469598103934665603)
+        for f in abi.Result.FIELDS:
+            a = np.ascontiguousarray(getattr(r, f)).view(np.uint8)
+            pad = (-len(a)) % 8
+            w = np.concatenate([a, np.zeros(pad, np.uint8)]).view(np.uint64) if pad else a.view(np.uint64)
+            acc = np.uint64((int(acc) * 1099511628211 + int(np.bitwise_xor.reduce(w * (np.arange(len(w), dtype=np.uint64) | np.uint64(1))))) & 0xFFFFFFFFFFFFFFFF)
+        return int(acc)
+
     e2e_runs = {}
     modes = {"auto": [False, True], "on": [True], "off": [False]}[args.zero_copy]
+    digests = {zc: result_digest(zc) for zc in modes}
+    if len(set(digests.values())) != 1:
+        raise SystemExit(f"PARITY FAILURE: zero-copy and bulk-upload runs of the full batch differ: {digests}")
     for zc in modes:
         dt, n_rec, nl = measure_e2e(zc)
         e2e_runs[zc] = (max_over_ranks(dt), n_rec, nl)
@@ -376,7 +392,8 @@ def main():
                        "reads_per_gpu": int(n_reads), "pairs_per_step_per_gpu": int(cnt["n_pairs"]), "lifted_per_step_per_gpu": int(cnt["n_lifted"]),
                        "l2_policy": "inputs larger than L2 (CIGAR pools + op scratch > 126 MB per step)", "sharding": "by contig set, no collective",
                        "e2e_pipeline": f"{len(chunks)} batches of {args.chunk} reads over 3 slots", "e2e_seq_zero_copy": bool(best_zc),
-                       "parity": parity, "generate_s": round(t_gen, 1)},
+                       "parity": parity, "full_batch_digest": f"{list(digests.values())[0]:016x} (identical across {len(digests)} base-transfer modes)",
+                       "generate_s": round(t_gen, 1)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(small_h2d + (0 if best_zc else seq_h2d)), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_dt * 1e3,
                     "alternatives": {("seq_zero_copy" if k else "seq_bulk_upload"): {"value": pairs_total / v[0], "ms_per_step": v[0] * 1e3} for k, v in e2e_runs.items()}},

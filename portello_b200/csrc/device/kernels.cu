@@ -26,6 +26,11 @@ __device__ __forceinline__ uint64_t shfl_up_t(uint64_t v, int d) { return __shfl
 __device__ __forceinline__ uint2 shfl_up_t(uint2 v, int d) {
     return make_uint2(__shfl_up_sync(0xffffffffu, v.x, d), __shfl_up_sync(0xffffffffu, v.y, d));
 }
+__device__ __forceinline__ uint32_t shfl_down_t(uint32_t v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
+__device__ __forceinline__ uint64_t shfl_down_t(uint64_t v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
+__device__ __forceinline__ uint2 shfl_down_t(uint2 v, int d) {
+    return make_uint2(__shfl_down_sync(0xffffffffu, v.x, d), __shfl_down_sync(0xffffffffu, v.y, d));
+}
 __device__ __forceinline__ uint32_t add_t(uint32_t a, uint32_t b) { return a + b; }
 __device__ __forceinline__ uint64_t add_t(uint64_t a, uint64_t b) { return a + b; }
 __device__ __forceinline__ uint2 add_t(uint2 a, uint2 b) { return make_uint2(a.x + b.x, a.y + b.y); }
@@ -82,6 +87,30 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_add_kernel(T* a, uint64_t n
         if (base + k < n) a[base + k] = add_t(a[base + k], off);
 }
 
+// Second (and last) pass for a moderate number of tiles: every block reduces the totals of the tiles before it
+// (L2-resident, <= a few thousand values) instead of waiting for a separate scan-of-sums kernel.
+template <class T>
+__global__ void __launch_bounds__(SCAN_THREADS) scan_add_reduce_kernel(T* a, uint64_t n, const T* sums) {
+    __shared__ T warp_tot[SCAN_THREADS / 32];
+    T acc = zero_t<T>();
+    for (uint32_t i = threadIdx.x; i < blockIdx.x; i += SCAN_THREADS) acc = add_t(acc, sums[i]);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        T o = shfl_down_t(acc, d);
+        acc = add_t(acc, o);
+    }
+    if (lane == 0) warp_tot[warp] = acc;
+    __syncthreads();
+    T off = zero_t<T>();
+#pragma unroll
+    for (int w = 0; w < SCAN_THREADS / 32; ++w) off = add_t(off, warp_tot[w]);
+    const uint64_t base = uint64_t(blockIdx.x) * SCAN_TILE + uint64_t(threadIdx.x) * SCAN_ITEMS;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k)
+        if (base + k < n) a[base + k] = add_t(a[base + k], off);
+}
+
 }  // namespace
 
 template <class T>
@@ -97,6 +126,11 @@ void exclusive_scan_inplace(T* a, uint64_t n, void* tmp, size_t tmp_bytes, cudaS
     const size_t used = ((blocks * sizeof(T)) + 255) & ~size_t(255);
     scan_tile_kernel<T><<<unsigned(blocks), SCAN_THREADS, 0, st>>>(a, n, sums);
     ++*launches;
+    if (blocks <= 8192) {
+        scan_add_reduce_kernel<T><<<unsigned(blocks), SCAN_THREADS, 0, st>>>(a, n, sums);
+        ++*launches;
+        return;
+    }
     exclusive_scan_inplace<T>(sums, blocks, static_cast<char*>(tmp) + used, tmp_bytes - used, st, launches);
     scan_add_kernel<T><<<unsigned(blocks), SCAN_THREADS, 0, st>>>(a, n, sums);
     ++*launches;
@@ -170,12 +204,21 @@ void launch_table_build(const DevStatic& S, uint32_t* counts, int2* out, cudaStr
 // =================================================================================================== per-batch kernels
 namespace {
 
+__device__ __forceinline__ void totals_reset(DevTotals* T) {
+    T->n_pairs = 0; T->scratch_needed = 0; T->n_records = 0; T->n_cigar_out = 0; T->n_lifted = 0; T->n_errors = 0;
+    T->first_error_read = 0x7fffffffffffffffLL; T->first_error_status = 0; T->overflow = 0; T->n_in_ops = 0; T->n_base_bytes = 0;
+    T->n_simplify = 0;
+}
+
 // a3 (count): get_contig_split_segments_from_read_mapping (src/read_alignment_scanner.rs:80-103) + get_cigar_ref_offset.
 // One thread per read walks its 1..k split segments.
-__global__ void __launch_bounds__(128) pair_count_kernel(DevStatic S, DevBatch B, DevWork W) {
+__global__ void __launch_bounds__(128) pair_count_kernel(DevStatic S, DevBatch B, DevWork W, DevTotals* T) {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= B.n_reads) {
-        if (r == B.n_reads) W.rseg_pair_begin[B.n_rsegs] = 0;
+        if (r == B.n_reads) {
+            W.rseg_pair_begin[B.n_rsegs] = 0;
+            totals_reset(T);  // first kernel of the batch: nothing has touched the totals yet
+        }
         return;
     }
     for (uint32_t s = B.read_seg_begin[r]; s < B.read_seg_begin[r + 1]; ++s) {
@@ -265,6 +308,7 @@ __global__ void __launch_bounds__(128) lift_pairs_kernel(DevStatic S, DevBatch B
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t n_pairs = min(uint32_t(T->n_pairs), W.pair_cap);
     const bool valid = p < n_pairs;
+    if (p == 0) T->scratch_needed = W.pair_slot_begin[n_pairs];  // total op slots of the batch (capacity feedback)
     PairCounters cnt;
     uint32_t n_in_ops = 0;
     int status = ST_NONE, err = 0;
@@ -650,14 +694,7 @@ __global__ void __launch_bounds__(256) emit_records_kernel(DevStatic S, DevBatch
     }
 }
 
-__global__ void totals_init_kernel(DevTotals* T) {
-    T->n_pairs = 0; T->scratch_needed = 0; T->n_records = 0; T->n_cigar_out = 0; T->n_lifted = 0; T->n_errors = 0;
-    T->first_error_read = 0x7fffffffffffffffLL; T->first_error_status = 0; T->overflow = 0; T->n_in_ops = 0; T->n_base_bytes = 0; T->n_simplify = 0;
-}
-__global__ void scratch_needed_kernel(DevWork W, DevTotals* T) {
-    const uint32_t np = min(uint32_t(T->n_pairs), W.pair_cap);
-    T->scratch_needed = W.pair_slot_begin[np];
-}
+__global__ void totals_init_kernel(DevTotals* T) { totals_reset(T); }
 
 }  // namespace
 
@@ -666,18 +703,19 @@ void launch_lift(const DevStatic& S, const DevBatch& B, const DevWork& W, const 
     auto mark = [&](int i) { if (ev) cudaEventRecord(ev->e[i], st); };
     const int do_finish = (stage_mask == 7u);
     mark(0);
-    totals_init_kernel<<<1, 1, 0, st>>>(T);
-    ++*launches;
-    if (B.n_reads == 0) { for (int i = 1; i < StageEvents::N; ++i) mark(i); return; }
-    pair_count_kernel<<<(B.n_reads + 1 + 127) / 128, 128, 0, st>>>(S, B, W);
+    if (B.n_reads == 0) {
+        totals_init_kernel<<<1, 1, 0, st>>>(T);
+        ++*launches;
+        for (int i = 1; i < StageEvents::N; ++i) mark(i);
+        return;
+    }
+    pair_count_kernel<<<(B.n_reads + 1 + 127) / 128, 128, 0, st>>>(S, B, W, T);
     ++*launches;
     exclusive_scan_inplace<uint32_t>(W.rseg_pair_begin, uint64_t(B.n_rsegs) + 1, scan_tmp, scan_tmp_bytes_, st, launches);
     pair_fill_kernel<<<(B.n_rsegs + 1 + 127) / 128, 128, 0, st>>>(S, B, W, T);
     ++*launches;
     // the pair count is only known on the device: scan / launch over the capacity, kernels clamp to n_pairs
     exclusive_scan_inplace<uint64_t>(W.pair_slot_begin, uint64_t(W.pair_cap) + 1, scan_tmp, scan_tmp_bytes_, st, launches);
-    scratch_needed_kernel<<<1, 1, 0, st>>>(W, T);
-    ++*launches;
     mark(1);
     lift_pairs_kernel<<<(W.pair_cap + 127) / 128, 128, 0, st>>>(S, B, W, T, stage_mask);
     ++*launches;

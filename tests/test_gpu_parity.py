@@ -152,3 +152,37 @@ def test_size_independent_properties_at_scale():
     octx = helpers.oracle_context(s)
     sub = helpers.pack(s, 77_000, 5_000)
     assert helpers.lift_c(gctx, sub.c).diff(helpers.lift_c(octx, sub.c)) is None
+
+
+def test_zero_copy_bases_give_identical_results():
+    """Zero-copy mode (packed bases stay in pinned, mapped host memory; kernels fetch the few bytes they need over PCIe)
+    must equal the bulk-upload mode and the oracle bit for bit."""
+    L = lib.load()
+    alloc = C.cast(L.dll.ptl_host_alloc, C.c_void_p)
+    free = C.cast(L.dll.ptl_host_free, C.c_void_p)
+    s = synth.make("tiny", host_alloc=alloc, host_free=free, seed=53, n_reads=6000, rev_contig_frac=0.7, read_cluster_frac=0.2)
+    pb = helpers.pack(s, pinned=True)
+    gctx = helpers.gpu_context(s)
+    bulk = helpers.lift_c(gctx, pb.c)
+    gctx.set_seq_zero_copy(True)
+    zc = helpers.lift_c(gctx, pb.c)
+    gctx.set_seq_zero_copy(False)
+    assert zc.diff(bulk) is None
+    ro = helpers.lift_c(helpers.oracle_context(s), pb.c)
+    assert zc.diff(ro) is None
+    # chunked zero-copy submissions over several slots (the e2e pipeline of bench.py)
+    gctx.set_seq_zero_copy(True)
+    n = s.read_records.n_reads
+    packs = [helpers.pack(s, a, min(2048, n - a), pinned=True) for a in range(0, n, 2048)]
+    recs = []
+    for i, p in enumerate(packs):
+        sl = i % 2
+        if i >= 2:
+            recs.append(abi.Result.from_c(gctx.wait_c(sl)))
+        gctx.submit_c(p.c, sl)
+    for i in range(len(packs), len(packs) + 2):
+        if i - 2 >= 0 and i - 2 < len(packs):
+            recs.append(abi.Result.from_c(gctx.wait_c(i % 2)))
+    assert np.array_equal(np.concatenate([r.cigar for r in recs]), bulk.cigar)
+    assert np.array_equal(np.concatenate([r.rec_pos for r in recs]), bulk.rec_pos)
+    assert np.array_equal(np.concatenate([r.rec_bin for r in recs]), bulk.rec_bin)
