@@ -329,7 +329,10 @@ void size_work(Slot& sl, uint32_t want_pairs, uint64_t want_scratch, uint32_t wa
     W.read_primary = sl.w_read_primary.as<uint32_t>();
     const uint64_t biggest = std::max<uint64_t>({uint64_t(ns) + 1, uint64_t(pc) + 1, uint64_t(n) + 1});
     sl.w_scan_tmp.ensure(scan_tmp_bytes(biggest), st);
-    sl.w_totals.ensure(sizeof(DevTotals), st);
+    if (!sl.w_totals.p) {
+        sl.w_totals.ensure(sizeof(DevTotals), st);
+        CK(cudaMemsetAsync(sl.w_totals.p, 0, sl.w_totals.cap, st));  // padding bytes too (they travel in the D2H of the totals)
+    }
     DevResult& R = sl.R;
     const uint32_t rc = std::max(R.rec_cap, want_recs);
     const uint64_t cc = std::max(R.cigar_cap, want_cigar);

@@ -40,9 +40,13 @@ template <> __device__ __forceinline__ uint64_t zero_t<uint64_t>() { return 0ull
 template <> __device__ __forceinline__ uint2 zero_t<uint2>() { return make_uint2(0u, 0u); }
 
 // Exclusive scan of one tile per block, in place; block totals to sums[blockIdx] (if sums != nullptr).
+// `n_dev` (optional): the live length is min(n, *n_dev + 1); tiles past it are skipped (the pair arrays are sized by
+// capacity, the pair count only exists on the device).
 template <class T>
-__global__ void __launch_bounds__(SCAN_THREADS) scan_tile_kernel(T* a, uint64_t n, T* sums) {
+__global__ void __launch_bounds__(SCAN_THREADS) scan_tile_kernel(T* a, uint64_t n, T* sums, const unsigned long long* n_dev) {
     __shared__ T warp_tot[SCAN_THREADS / 32];
+    if (n_dev) { const uint64_t live = uint64_t(*n_dev) + 1ull; if (live < n) n = live; }
+    if (uint64_t(blockIdx.x) * SCAN_TILE >= n) return;
     const uint64_t base = uint64_t(blockIdx.x) * SCAN_TILE + uint64_t(threadIdx.x) * SCAN_ITEMS;
     T v[SCAN_ITEMS];
     T run = zero_t<T>();
@@ -90,8 +94,10 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_add_kernel(T* a, uint64_t n
 // Second (and last) pass for a moderate number of tiles: every block reduces the totals of the tiles before it
 // (L2-resident, <= a few thousand values) instead of waiting for a separate scan-of-sums kernel.
 template <class T>
-__global__ void __launch_bounds__(SCAN_THREADS) scan_add_reduce_kernel(T* a, uint64_t n, const T* sums) {
+__global__ void __launch_bounds__(SCAN_THREADS) scan_add_reduce_kernel(T* a, uint64_t n, const T* sums, const unsigned long long* n_dev) {
     __shared__ T warp_tot[SCAN_THREADS / 32];
+    if (n_dev) { const uint64_t live = uint64_t(*n_dev) + 1ull; if (live < n) n = live; }
+    if (uint64_t(blockIdx.x) * SCAN_TILE >= n) return;
     T acc = zero_t<T>();
     for (uint32_t i = threadIdx.x; i < blockIdx.x; i += SCAN_THREADS) acc = add_t(acc, sums[i]);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -114,30 +120,32 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_add_reduce_kernel(T* a, uin
 }  // namespace
 
 template <class T>
-void exclusive_scan_inplace(T* a, uint64_t n, void* tmp, size_t tmp_bytes, cudaStream_t st, uint64_t* launches) {
+void exclusive_scan_inplace(T* a, uint64_t n, void* tmp, size_t tmp_bytes, cudaStream_t st, uint64_t* launches,
+                            const unsigned long long* n_dev) {
     if (n == 0) return;
     const uint64_t blocks = (n + SCAN_TILE - 1) / SCAN_TILE;
     if (blocks == 1) {
-        scan_tile_kernel<T><<<1, SCAN_THREADS, 0, st>>>(a, n, nullptr);
+        scan_tile_kernel<T><<<1, SCAN_THREADS, 0, st>>>(a, n, nullptr, n_dev);
         ++*launches;
         return;
     }
     T* sums = static_cast<T*>(tmp);
     const size_t used = ((blocks * sizeof(T)) + 255) & ~size_t(255);
-    scan_tile_kernel<T><<<unsigned(blocks), SCAN_THREADS, 0, st>>>(a, n, sums);
+    scan_tile_kernel<T><<<unsigned(blocks), SCAN_THREADS, 0, st>>>(a, n, sums, n_dev);
     ++*launches;
     if (blocks <= 8192) {
-        scan_add_reduce_kernel<T><<<unsigned(blocks), SCAN_THREADS, 0, st>>>(a, n, sums);
+        scan_add_reduce_kernel<T><<<unsigned(blocks), SCAN_THREADS, 0, st>>>(a, n, sums, n_dev);
         ++*launches;
         return;
     }
-    exclusive_scan_inplace<T>(sums, blocks, static_cast<char*>(tmp) + used, tmp_bytes - used, st, launches);
+    // (very large inputs: classic three-pass scan over the full capacity; n_dev is not needed for correctness)
+    exclusive_scan_inplace<T>(sums, blocks, static_cast<char*>(tmp) + used, tmp_bytes - used, st, launches, nullptr);
     scan_add_kernel<T><<<unsigned(blocks), SCAN_THREADS, 0, st>>>(a, n, sums);
     ++*launches;
 }
-template void exclusive_scan_inplace<uint32_t>(uint32_t*, uint64_t, void*, size_t, cudaStream_t, uint64_t*);
-template void exclusive_scan_inplace<uint64_t>(uint64_t*, uint64_t, void*, size_t, cudaStream_t, uint64_t*);
-template void exclusive_scan_inplace<uint2>(uint2*, uint64_t, void*, size_t, cudaStream_t, uint64_t*);
+template void exclusive_scan_inplace<uint32_t>(uint32_t*, uint64_t, void*, size_t, cudaStream_t, uint64_t*, const unsigned long long*);
+template void exclusive_scan_inplace<uint64_t>(uint64_t*, uint64_t, void*, size_t, cudaStream_t, uint64_t*, const unsigned long long*);
+template void exclusive_scan_inplace<uint2>(uint2*, uint64_t, void*, size_t, cudaStream_t, uint64_t*, const unsigned long long*);
 
 size_t scan_tmp_bytes(uint64_t n) {
     size_t total = 0;
@@ -304,7 +312,10 @@ __global__ void __launch_bounds__(128) pair_fill_kernel(DevStatic S, DevBatch B,
 // a4 + a5 + a6 + a8 + a9: get_liftover_alignment_for_read_and_contig_segment (src/read_alignment_scanner.rs:136-288),
 // one thread per pair; the stages are warp-collective (all 32 lanes enter, idle lanes carry active = false) so that
 // the latency-bound base fetches of a warp are issued together (see LeftShifter).
-__global__ void __launch_bounds__(128) lift_pairs_kernel(DevStatic S, DevBatch B, DevWork W, DevTotals* T, uint32_t stage_mask) {
+#ifndef LIFT_MIN_BLOCKS
+#define LIFT_MIN_BLOCKS 1
+#endif
+__global__ void __launch_bounds__(128, LIFT_MIN_BLOCKS) lift_pairs_kernel(DevStatic S, DevBatch B, DevWork W, DevTotals* T, uint32_t stage_mask) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t n_pairs = min(uint32_t(T->n_pairs), W.pair_cap);
     const bool valid = p < n_pairs;
@@ -711,11 +722,11 @@ void launch_lift(const DevStatic& S, const DevBatch& B, const DevWork& W, const 
     }
     pair_count_kernel<<<(B.n_reads + 1 + 127) / 128, 128, 0, st>>>(S, B, W, T);
     ++*launches;
-    exclusive_scan_inplace<uint32_t>(W.rseg_pair_begin, uint64_t(B.n_rsegs) + 1, scan_tmp, scan_tmp_bytes_, st, launches);
+    exclusive_scan_inplace<uint32_t>(W.rseg_pair_begin, uint64_t(B.n_rsegs) + 1, scan_tmp, scan_tmp_bytes_, st, launches, nullptr);
     pair_fill_kernel<<<(B.n_rsegs + 1 + 127) / 128, 128, 0, st>>>(S, B, W, T);
     ++*launches;
     // the pair count is only known on the device: scan / launch over the capacity, kernels clamp to n_pairs
-    exclusive_scan_inplace<uint64_t>(W.pair_slot_begin, uint64_t(W.pair_cap) + 1, scan_tmp, scan_tmp_bytes_, st, launches);
+    exclusive_scan_inplace<uint64_t>(W.pair_slot_begin, uint64_t(W.pair_cap) + 1, scan_tmp, scan_tmp_bytes_, st, launches, &T->n_pairs);
     mark(1);
     lift_pairs_kernel<<<(W.pair_cap + 127) / 128, 128, 0, st>>>(S, B, W, T, stage_mask);
     ++*launches;
@@ -728,7 +739,7 @@ void launch_lift(const DevStatic& S, const DevBatch& B, const DevWork& W, const 
     mark(2);
     read_finalize_kernel<<<(B.n_reads + 1 + 127) / 128, 128, 0, st>>>(S, B, W, T, do_finish);
     ++*launches;
-    exclusive_scan_inplace<uint2>(W.read_counts, uint64_t(B.n_reads) + 1, scan_tmp, scan_tmp_bytes_, st, launches);
+    exclusive_scan_inplace<uint2>(W.read_counts, uint64_t(B.n_reads) + 1, scan_tmp, scan_tmp_bytes_, st, launches, nullptr);
     emit_records_kernel<<<(B.n_reads + 255) / 256, 256, 0, st>>>(S, B, W, R, T, stage_mask);
     ++*launches;
     mark(3);

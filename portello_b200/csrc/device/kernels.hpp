@@ -16,7 +16,8 @@ struct StageEvents {
 };
 
 template <class T>
-void exclusive_scan_inplace(T* a, uint64_t n, void* tmp, size_t tmp_bytes, cudaStream_t st, uint64_t* launches);
+void exclusive_scan_inplace(T* a, uint64_t n, void* tmp, size_t tmp_bytes, cudaStream_t st, uint64_t* launches,
+                            const unsigned long long* n_dev = nullptr);
 size_t scan_tmp_bytes(uint64_t n);
 
 // counts != nullptr, out == nullptr : count table entries per segment; then (after a scan into S.seg_tab_begin) fill `out`.
