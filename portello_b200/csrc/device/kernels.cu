@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(128) pair_fill_kernel(DevStatic S, DevBatch B,
 // one thread per pair; the stages are warp-collective (all 32 lanes enter, idle lanes carry active = false) so that
 // the latency-bound base fetches of a warp are issued together (see LeftShifter).
 #ifndef LIFT_MIN_BLOCKS
-#define LIFT_MIN_BLOCKS 1
+#define LIFT_MIN_BLOCKS 8  // 64 registers, 32 warps per SM (sweep in profiles/: 8 -> 0.558 ms, 1 -> 0.579 ms, 12 spills)
 #endif
 __global__ void __launch_bounds__(128, LIFT_MIN_BLOCKS) lift_pairs_kernel(DevStatic S, DevBatch B, DevWork W, DevTotals* T, uint32_t stage_mask) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
