@@ -339,8 +339,10 @@ __device__ __forceinline__ bool run_liftover(const OpSource& in, uint32_t pos, c
         if (lo < t1) nk = uint32_t(tab[lo].x);
     }
     uint32_t p = pos;
+    uint32_t c_next = in.n ? in.get(0) : 0u;  // software prefetch: the load of op i+1 overlaps the work on op i
     for (uint32_t i = 0; i < in.n; ++i) {
-        const uint32_t c = in.get(i);
+        const uint32_t c = c_next;
+        if (i + 1 < in.n) c_next = in.get(i + 1);
         const uint32_t op = c & 0xfu, len = c >> 4;
         const bool is_ref = (kRefMask >> op) & 1u;
         if (op == OP_P || (is_ref && len == 0)) continue;  // Pad is ignored (:213); empty ops produce no piece

@@ -109,6 +109,12 @@ class Synth:
         self.read_records = ReadRecordsC()
         d.ptl_synth_read_records(self.h, C.byref(self.read_records))
 
+    def reference_arrays(self):
+        """The chromosomes as borrowed numpy uint8 views (valid while this object lives)."""
+        import numpy as np
+
+        return [np.ctypeslib.as_array(self.chrom_seq[i], (int(self.chrom_len[i]),)) for i in range(self.n_chrom)]
+
     def close(self):
         if self.h:
             _load().ptl_synth_destroy(self.h)
