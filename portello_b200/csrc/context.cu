@@ -197,9 +197,9 @@ void install_segments(ptl_ctx* ctx, std::vector<HostContig>& contigs) {
         CK(cudaStreamSynchronize(st));
         tmp.release();
         const uint32_t total = ctx->h_tab_begin[ns];
-        ctx->s_table.ensure(std::max<size_t>(total, 1) * sizeof(int2), st);
-        S.table = ctx->s_table.as<int2>();
-        launch_table_build(S, nullptr, ctx->s_table.as<int2>(), st);
+        ctx->s_table.ensure(std::max<size_t>(total, 1) * sizeof(TabEntry), st);
+        S.table = ctx->s_table.as<TabEntry>();
+        launch_table_build(S, nullptr, ctx->s_table.as<TabEntry>(), st);
         ++ctx->launches;
     }
     CK(cudaStreamSynchronize(st));
@@ -601,11 +601,11 @@ int ptl_get_segment_table(ptl_ctx* ctx, uint32_t segment, uint32_t cap, uint32_t
         const uint32_t t0 = ctx->h_tab_begin[segment], t1 = ctx->h_tab_begin[segment + 1];
         *n = t1 - t0;
         if (*n > cap) return int(PTL_ERR_INVALID_ARG);
-        std::vector<int2> tmp(*n);
-        if (*n) CK(cudaMemcpy(tmp.data(), ctx->s_table.as<int2>() + t0, size_t(*n) * sizeof(int2), cudaMemcpyDeviceToHost));
+        std::vector<TabEntry> tmp(*n);
+        if (*n) CK(cudaMemcpy(tmp.data(), ctx->s_table.as<TabEntry>() + t0, size_t(*n) * sizeof(TabEntry), cudaMemcpyDeviceToHost));
         for (uint32_t i = 0; i < *n; ++i) {
-            keys[i] = uint32_t(tmp[i].x);
-            vals[i] = tmp[i].y;
+            keys[i] = tmp[i].key;
+            vals[i] = tmp[i].val;
         }
         return int(PTL_OK);
     });

@@ -5,6 +5,22 @@
 
 namespace ptl {
 
+// One entry of a flat ReadToRefTreeMap (lib/rust-vc-utils/src/bam_utils/read_to_ref_map.rs:59-137), 16 bytes so that a
+// key crossing of the liftover walk is ONE 128-bit load.
+//   key : contig read_pos where the block starts
+//   val : reference position of the block start, or -1 for a None block (run end)
+//   gap : for a Some block, max(0, val - reference end of the previous aligned run of the same segment) = the length
+//         of the deletion update_ref2_cigar_segment (src/liftover_read_alignment.rs:91-96) pushes when the walk enters
+//         this block from the previous one; 0 for the first run and for None blocks.  Precomputed because the walk
+//         covers the contig interval contiguously: when it enters a block, `ref2_end_pos` is always the end of the
+//         previous aligned run (if the walk touched it at all).
+struct alignas(16) TabEntry {
+    uint32_t key;
+    int32_t val;
+    uint32_t gap;
+    uint32_t pad;
+};
+
 // ---- static, read-only state (replicated per GPU): reference, contigs, segment tables ------------------------
 struct DevStatic {
     // reference genome, ASCII, chromosomes concatenated (ptl_set_reference)
@@ -27,9 +43,9 @@ struct DevStatic {
     const uint8_t* seg_mapq = nullptr;
     const uint64_t* seg_cigar_begin = nullptr;   // [n_segments+1]
     const uint32_t* seg_cigar = nullptr;
-    // flat ReadToRefTreeMap: per segment a sorted run of (key = contig read_pos, val = ref pos or -1 for None)
+    // flat ReadToRefTreeMap: per segment a sorted run of TabEntry
     const uint32_t* seg_tab_begin = nullptr;     // [n_segments+1]
-    const int2* table = nullptr;
+    const TabEntry* table = nullptr;
 };
 
 // ---- one batch on the device ------------------------------------------------------------------------------------

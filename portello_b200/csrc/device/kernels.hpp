@@ -21,7 +21,7 @@ void exclusive_scan_inplace(T* a, uint64_t n, void* tmp, size_t tmp_bytes, cudaS
 size_t scan_tmp_bytes(uint64_t n);
 
 // counts != nullptr, out == nullptr : count table entries per segment; then (after a scan into S.seg_tab_begin) fill `out`.
-void launch_table_build(const DevStatic& S, uint32_t* counts, int2* out, cudaStream_t st);
+void launch_table_build(const DevStatic& S, uint32_t* counts, TabEntry* out, cudaStream_t st);
 
 void launch_lift(const DevStatic& S, const DevBatch& B, const DevWork& W, const DevResult& R, DevTotals* T, uint32_t stage_mask,
                  void* scan_tmp, size_t scan_tmp_bytes, cudaStream_t st, uint64_t* launches, StageEvents* ev);

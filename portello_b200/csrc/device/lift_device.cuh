@@ -14,7 +14,8 @@
 //   - op walks are tight nested loops over L1-resident ops (ALU-bound, short divergent arms),
 //   - everything that needs a DRAM/L2 round trip (homology walk, cluster trimming) is hoisted into a warp-converged
 //     middle phase over a per-lane list of recorded clusters, so 32 lanes x 4 loads are in flight per warp,
-//   - the table block under the walk and the next key live in registers; the table is read only when a key is crossed.
+//   - the liftover merge of op boundaries and table keys is one flat event loop (see run_liftover); the table block
+//     under the walk lives in registers and the next entry is prefetched.
 // Contig coordinates are 32-bit (BAM l_seq is int32); reference positions are widened only where they leave the loop.
 #pragma once
 #include <cstdint>
@@ -64,29 +65,42 @@ struct ReadBases {
 
 // ------------------------------------------------------------------------------------------------------------------
 // Streaming clean_up_cigar_edge_indels + compress_cigar.
+// The pending (not yet stored) op is kept as ONE packed BAM word; an empty sink holds the word 0 = "M of length 0", so
+// the first alignment match merges into it and anything else replaces it (a zero-length word is never stored).
 struct OpSink {
     uint32_t* buf;
     uint32_t cap;
     uint32_t n = 0;
-    uint32_t pend_op = NO_OP, pend_len = 0;
+    uint32_t pend = 0;            // (len << 4) | op of the open run
     int32_t last_match_idx = -1;  // index (in buf) of the last alignment-match op, counting the pending one
     bool seen_match = false;
     bool overflow = false;
-    bool mixed_cluster = false;   // some run of I/D ops closed so far holds both an I and a D (simplify would rewrite it)
-    uint32_t run_kinds = 0;       // bit0: I seen in the open I/D run, bit1: D seen
+    bool mixed_cluster = false;   // two adjacent stored ops are an I and a D: simplify_alignment_indels would rewrite them
     uint32_t lead_del_shift = 0;  // return value of clean_up_cigar_edge_indels
     uint32_t ref_span = 0;        // reference bases consumed by the stored ops = get_alignment_end - pos (after finish())
 
     __device__ __forceinline__ OpSink(uint32_t* b, uint32_t c) : buf(b), cap(c) {}
 
     __device__ __forceinline__ void flush() {
-        if (pend_op != NO_OP) {
-            if (n < cap) buf[n] = (pend_len << 4) | pend_op;
+        if (pend >> 4) {
+            if (n < cap) buf[n] = pend;
             else overflow = true;
             ++n;
-            if ((kRefMask >> pend_op) & 1u) ref_span += pend_len;
-            pend_op = NO_OP;
+            if ((kRefMask >> (pend & 0xfu)) & 1u) ref_span += pend >> 4;
         }
+    }
+    // after the leading edge: merge into the open run or start a new one
+    __device__ __forceinline__ void push_body(uint32_t op, uint32_t len) {
+        const uint32_t pop = pend & 0xfu;
+        if (pop == op) {
+            if (op != OP_P) pend += len << 4;  // a Pad after a Pad is dropped, not merged (cigar/mod.rs:208-215)
+        } else {
+            flush();
+            // an I/D run of the compressed CIGAR holds both kinds iff two adjacent stored ops are {I, D}
+            mixed_cluster |= (((1u << pop) | (1u << op)) == ((1u << OP_I) | (1u << OP_D)));
+            pend = (len << 4) | op;
+        }
+        if (op_is_match(op)) last_match_idx = int32_t(n);
     }
     __device__ __forceinline__ void push(uint32_t op, uint32_t len) {
         if (len == 0) return;  // compress_cigar filters empty elements (no stage emits an empty alignment match)
@@ -95,29 +109,12 @@ struct OpSink {
             else if (op == OP_I) op = OP_S;
             else if (op == OP_D) { lead_del_shift += len; return; }  // -> SoftClip(0), later dropped
         }
-        if (pend_op == op) {
-            if (op != OP_P) pend_len += len;  // a Pad after a Pad is dropped, not merged (cigar/mod.rs:208-215)
-            return;
-        }
-        flush();
-        pend_op = op;
-        pend_len = len;
-        if (op == OP_I || op == OP_D) {
-            run_kinds |= op;  // OP_I = 1, OP_D = 2
-        } else {
-            mixed_cluster |= (run_kinds == 3u);
-            run_kinds = 0;
-            if (op_is_match(op)) last_match_idx = int32_t(n);
-        }
-    }
-    // hot path of the liftover: extend a pending alignment match without the general machinery
-    __device__ __forceinline__ void push_match(uint32_t len) {
-        if (pend_op == OP_M) pend_len += len;
-        else push(OP_M, len);
+        push_body(op, len);
     }
     // trailing edge (cigar/mod.rs:282-288) + re-merge of what the conversion made adjacent
     __device__ __forceinline__ void finish() {
         flush();
+        pend = 0;
         if (overflow || last_match_idx < 0) return;  // no match at all: the leading pass already converted everything
         const uint32_t start = uint32_t(last_match_idx) + 1u;
         uint32_t w = start, prev = NO_OP;
@@ -308,88 +305,103 @@ __device__ __forceinline__ uint32_t run_left_shift_warp(bool active, const OpSou
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// a6: liftover_read_alignment (src/liftover_read_alignment.rs:137-223).  The reference re-searches its BTreeMap for
-// every reference-consuming op; read-op boundaries and table keys both advance monotonically, so one binary search
-// per pair plus a forward merge visits exactly the same (piece, block) sequence.  The current block and the next key
-// live in registers; the table is touched only when the walk crosses a key.
+// a6: liftover_read_alignment (src/liftover_read_alignment.rs:137-223) + update_ref2_cigar_segment (:35-133).
+//
+// The reference re-searches its BTreeMap for every reference-consuming op.  Read-op boundaries and table keys both
+// advance monotonically, so one binary search per pair plus a forward merge visits exactly the same (piece, block)
+// sequence.  The merge is ONE flat loop (ncu r01q: the nested op/piece loops ran at 10 active lanes per instruction;
+// a warp paid max-ops x max-pieces-per-op iterations): every iteration handles one event of one lane,
+//     [fetch the next op]  ->  [cross a table key]  ->  [one piece, or the verbatim I/S/H op]  ->  ONE sink push
+// so a warp runs max(n_ops + keys inside ops) iterations and all lanes share the sink code.  The current block lives in
+// registers and the NEXT table entry is prefetched (one 128-bit load, a crossing only moves registers).
+//
+// `ref2_end_pos` (:91-100) is not tracked: pieces tile the walked contig interval contiguously, so when the walk enters a
+// Some block the previous Some piece ended exactly at the end of the previous aligned run, and the pushed deletion is
+// the entry's precomputed `gap` (TabEntry) - valid iff some Some piece was seen before (the walk touched that run).
 // Returns true if ref2_start_pos was set (Some); *out_pos = start + leading-deletion shift.
-__device__ __forceinline__ bool run_liftover(const OpSource& in, uint32_t pos, const int2* __restrict__ tab, uint32_t t0, uint32_t t1,
+__device__ __forceinline__ bool run_liftover(const OpSource& in, uint32_t pos, const TabEntry* __restrict__ tab, uint32_t t0, uint32_t t1,
                                              OpSink& sink, int64_t* out_pos) {
     constexpr uint32_t INF = 0xffffffffu;
-    bool start_set = false, end2_set = false;
-    int32_t start = 0, end2 = 0;  // reference positions fit int32 (BAM)
-    // block cursor: the current block is the greatest key <= the walk position (kind 0 = before the first key);
-    // ti = index of the NEXT table entry (the one whose key is nk)
-    uint32_t ti, nk = INF, blk_k = 0, blk_kind = 0;  // kind: 0 no block, 1 None block, 2 Some block
-    int32_t blk_v = -1;
+    // block cursor: the current block is the greatest key <= the walk position (blk_v: >= 0 Some, -1 None, -2 before
+    // the first key); (nk, nv, ngap) = the prefetched NEXT entry, ti = its index
+    uint32_t ti, nk = INF, ngap = 0, blk_k = 0, pgap = 0;
+    int32_t blk_v = -2, nv = -1;
     {
         uint32_t lo = t0, hi = t1;  // first index with key > pos
         while (lo < hi) {
             const uint32_t mid = (lo + hi) >> 1;
-            if (uint32_t(tab[mid].x) <= pos) lo = mid + 1;
+            if (tab[mid].key <= pos) lo = mid + 1;
             else hi = mid;
         }
         ti = lo;
         if (lo > t0) {
-            const int2 b = tab[lo - 1];
-            blk_k = uint32_t(b.x);
-            blk_v = b.y;
-            blk_kind = (b.y < 0) ? 1u : 2u;
+            const TabEntry b = tab[lo - 1];
+            blk_k = b.key;
+            blk_v = b.val;
         }
-        if (lo < t1) nk = uint32_t(tab[lo].x);
+        if (lo < t1) {
+            const TabEntry b = tab[lo];
+            nk = b.key;
+            nv = b.val;
+            ngap = b.gap;
+        }
     }
-    uint32_t p = pos;
+    bool start_set = false, some_seen = false, is_match = false;
+    int32_t start = 0;  // reference positions fit int32 (BAM)
+    uint32_t p = pos, e = pos;  // [p, e) = what is left of the open reference-consuming op; e == p: none open
+    uint32_t i = 0, main_op = 0;
     uint32_t c_next = in.n ? in.get(0) : 0u;  // software prefetch: the load of op i+1 overlaps the work on op i
-    for (uint32_t i = 0; i < in.n; ++i) {
-        const uint32_t c = c_next;
-        if (i + 1 < in.n) c_next = in.get(i + 1);
-        const uint32_t op = c & 0xfu, len = c >> 4;
-        const bool is_ref = (kRefMask >> op) & 1u;
-        if (op == OP_P || (is_ref && len == 0)) continue;  // Pad is ignored (:213); empty ops produce no piece
-        const bool is_match = op_is_match(op);
-        const uint32_t main_op = is_match ? uint32_t(OP_M) : op;  // D stays D, N stays N, M/=/X become M (:103-107)
-        const uint32_t e = is_ref ? p + len : p;
-        uint32_t bp = p;
-        bool more;
-        // Every iteration ends in the SAME two pushes (gap deletion, then the piece / verbatim op): lanes sit in
-        // different arms above, but the expensive sink code is shared, not replicated per arm.
-        do {
-            uint32_t gap = 0, m_op = op, m_len = is_ref ? 0u : len;  // I/S/H transfer verbatim (:157-160)
-            more = false;
-            if (is_ref) {
-                // piece [bp, seg_end) against the current block (update_ref2_cigar_segment, :35-133)
-                const uint32_t seg_end = min(nk, e);
-                if (seg_end > bp) {
-                    const uint32_t plen = seg_end - bp;
-                    if (blk_kind == 2) {
-                        if (is_match && !start_set) { start = blk_v + int32_t(bp - blk_k); start_set = true; }
-                        if (end2_set && start_set) {
-                            const int32_t dlen = blk_v - end2;
-                            if (dlen > 0) gap = uint32_t(dlen);
-                        }
-                        end2 = blk_v + int32_t(seg_end - blk_k);
-                        end2_set = true;
-                        if (start_set) { m_op = main_op; m_len = plen; }
-                    } else if (is_match) {
-                        m_op = (blk_kind == 1) ? uint32_t(OP_I) : uint32_t(OP_S);
-                        m_len = plen;
-                    }
-                    bp = seg_end;
-                }
-                if (nk < e) {  // cross the key: it becomes the current block
-                    const int2 b = tab[ti];
-                    blk_k = uint32_t(b.x);
-                    blk_v = b.y;
-                    blk_kind = (b.y < 0) ? 1u : 2u;
-                    ++ti;
-                    nk = (ti < t1) ? uint32_t(tab[ti].x) : INF;
-                    more = true;
+    for (;;) {
+        uint32_t gap = 0, m_op = 0, m_len = 0;
+        if (e == p) {  // fetch the next op
+            if (i == in.n) break;
+            const uint32_t c = c_next;
+            ++i;
+            if (i < in.n) c_next = in.get(i);
+            const uint32_t op = c & 0xfu, len = c >> 4;
+            if ((kRefMask >> op) & 1u) {
+                e = p + len;  // an empty op opens nothing: no piece (get_ref_range of an empty interval)
+                is_match = op_is_match(op);
+                main_op = is_match ? uint32_t(OP_M) : op;  // D stays D, N stays N, M/=/X become M (:103-107)
+            } else if (op != OP_P) {  // I/S/H transfer verbatim (:157-160); Pad is ignored (:213)
+                m_op = op;
+                m_len = len;
+            }
+        }
+        if (e != p) {  // one piece of the open op against the block under p (update_ref2_cigar_segment)
+            if (nk == p) {  // the walk reached the next key: it becomes the current block
+                blk_k = nk;
+                blk_v = nv;
+                pgap = ngap;
+                ++ti;
+                if (ti < t1) {
+                    const TabEntry b = tab[ti];
+                    nk = b.key;
+                    nv = b.val;
+                    ngap = b.gap;
+                } else {
+                    nk = INF;
                 }
             }
-            sink.push(OP_D, gap);
-            sink.push(m_op, m_len);
-        } while (more);
-        p = e;
+            const uint32_t seg_end = min(nk, e);  // > p: keys are strictly increasing
+            const uint32_t plen = seg_end - p;
+            if (blk_v >= 0) {
+                if (is_match && !start_set) { start = blk_v + int32_t(p - blk_k); start_set = true; }  // :84-88
+                if (start_set) {
+                    if (some_seen) gap = pgap;  // :91-96, only the first piece of a block can see a positive distance
+                    m_op = main_op;             // :102-109
+                    m_len = plen;
+                }
+                pgap = 0;
+                some_seen = true;  // ref2_end_pos is set by every Some piece (:98-100)
+            } else if (is_match) {
+                m_op = (blk_v == -1) ? uint32_t(OP_I) : uint32_t(OP_S);  // None block: insertion (:111-115); no block: clip (:117-123)
+                m_len = plen;
+            }
+            p = seg_end;
+        }
+        if (gap) sink.push(OP_D, gap);
+        sink.push(m_op, m_len);
     }
     if (!start_set) return false;
     sink.finish();

@@ -27,7 +27,7 @@ def ref_len(c):
     return int(sum(int(v) >> 4 for v in c if (int(v) & 15) in (0, 2, 3, 7, 8)))
 
 
-def make_case(seed, n_contigs=6, n_reads=400):
+def make_case(seed, n_contigs=6, n_reads=400, zero_prob=0.05):
     rng = np.random.default_rng(seed)
     n_chrom = 2
     chrom_len = 60_000
@@ -74,7 +74,7 @@ def make_case(seed, n_contigs=6, n_reads=400):
     off = 0
     for _ in range(n_reads):
         nseg = int(rng.choice([1, 1, 1, 2, 3]))
-        body = rand_cigar(rng, int(rng.integers(1, 30)), w_read)
+        body = rand_cigar(rng, int(rng.integers(1, 30)), w_read, zero_prob=zero_prob)
         L = read_len(body)
         if L == 0:
             body = np.concatenate([body, np.array([(5 << 4) | 0], np.uint32)])
@@ -89,7 +89,7 @@ def make_case(seed, n_contigs=6, n_reads=400):
             if k == 0:
                 cg = body
             else:  # another segment CIGAR with the same read length
-                cg = rand_cigar(rng, int(rng.integers(1, 20)), w_read)
+                cg = rand_cigar(rng, int(rng.integers(1, 20)), w_read, zero_prob=zero_prob)
                 d = L - read_len(cg)
                 if d > 0:
                     cg = np.concatenate([cg, np.array([(d << 4) | 4], np.uint32)])
