@@ -224,8 +224,15 @@ def main():
     n_table = sum(len(ctx.get_segment_table(g)[0]) for g in range(n_segments))
 
     whole = lib.PackedBatch(L, s.read_records, 0, n_reads, s.contig_names, pinned=True)
-    chunks = [lib.PackedBatch(L, s.read_records, a, min(args.chunk, n_reads - a), s.contig_names, pinned=True)
-              for a in range(0, n_reads, args.chunk)]
+    rev_mask = ctx.reverse_mask()
+    chunk_sets = {
+        False: [lib.PackedBatch(L, s.read_records, a, min(args.chunk, n_reads - a), s.contig_names, pinned=True)
+                for a in range(0, n_reads, args.chunk)],
+        # indel windows (ptl_pack_batch_ex) for the read segments on contigs that own a reverse-strand segment
+        True: [lib.PackedBatch(L, s.read_records, a, min(args.chunk, n_reads - a), s.contig_names, pinned=True, windows=rev_mask)
+               for a in range(0, n_reads, args.chunk)],
+    }
+    whole_win = lib.PackedBatch(L, s.read_records, 0, n_reads, s.contig_names, pinned=True, windows=rev_mask)
 
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -283,7 +290,7 @@ def main():
         parity = f"bit-exact vs oracle on {sub.c.n_reads} reads of this workload"
 
     # ---------------------------------------------------------------- e2e: host buffers -> records on the host
-    def e2e_step():
+    def e2e_step(chunks):
         n_slots = 3
         inflight = [None] * n_slots
         recs = 0
@@ -300,28 +307,40 @@ def main():
                 inflight[sl] = None
         return recs
 
-    def measure_e2e(zero_copy):
+    def measure_e2e(mode):
+        zero_copy, windows = MODES[mode]
+        chunks = chunk_sets[windows]
         ctx.set_seq_zero_copy(zero_copy)
         for _ in range(max(args.warmup, 3)):
-            e2e_step()
+            e2e_step(chunks)
         barrier()
         l0 = ctx.launch_count()
         t0 = time.time()
         p0 = time.perf_counter()
         for _ in range(args.steps):
-            n_rec = e2e_step()
+            n_rec = e2e_step(chunks)
         torch.cuda.synchronize()
         dt = (time.perf_counter() - p0) / args.steps
         barrier()
         windows.append((t0, time.time()))
         return dt, n_rec, ctx.launch_count() - l0
 
-    small_h2d = sum(int(ch.c.n_reads) * (2 + 1 + 2 + 4 + 8 + 4) + int(ch.c.n_read_segments) * (4 + 8 + 1 + 8 + 4) + int(ch.c.n_cigar) * 4 for ch in chunks)
-    seq_h2d = sum(int(ch.c.seq4_bytes) for ch in chunks)
-    def result_digest(zero_copy):
+    # base-transfer modes of the e2e call: (zero-copy packed bases, indel windows travelling with the batch)
+    MODES = {"seq_bulk_upload": (False, False), "seq_zero_copy": (True, False), "seq_zero_copy_indel_windows": (True, True)}
+
+    def h2d_bytes(mode):
+        zero_copy, windows = MODES[mode]
+        chunks = chunk_sets[windows]
+        small = sum(int(ch.c.n_reads) * (2 + 1 + 2 + 4 + 8 + 4) + int(ch.c.n_read_segments) * (4 + 8 + 1 + 8 + 4) + int(ch.c.n_cigar) * 4 for ch in chunks)
+        win = sum((int(ch.c.n_read_segments) + 1) * 4 + int(ch.c.n_indel_win) * 8 for ch in chunks) if windows else 0
+        seq = 0 if zero_copy else sum(int(ch.c.seq4_bytes) for ch in chunks)
+        return small + win + seq
+
+    def result_digest(mode):
         """Order-sensitive checksum of every result array of the whole batch (outside the timed region)."""
+        zero_copy, windows = MODES[mode]
         ctx.set_seq_zero_copy(zero_copy)
-        ctx.submit_c(whole.c, 0)
+        ctx.submit_c((whole_win if windows else whole).c, 0)
         r = abi.Result.from_c(ctx.wait_c(0), copy=False)
         acc = np.uint64(1469598103934665603)
         for f in abi.Result.FIELDS:
@@ -332,15 +351,16 @@ def main():
         return int(acc)
 
     e2e_runs = {}
-    modes = {"auto": [False, True], "on": [True], "off": [False]}[args.zero_copy]
-    digests = {zc: result_digest(zc) for zc in modes}
+    modes = {"auto": list(MODES), "on": ["seq_zero_copy", "seq_zero_copy_indel_windows"], "off": ["seq_bulk_upload"]}[args.zero_copy]
+    digests = {m: result_digest(m) for m in modes}
     if len(set(digests.values())) != 1:
-        raise SystemExit(f"PARITY FAILURE: zero-copy and bulk-upload runs of the full batch differ: {digests}")
-    for zc in modes:
-        dt, n_rec, nl = measure_e2e(zc)
-        e2e_runs[zc] = (max_over_ranks(dt), n_rec, nl)
-    best_zc = min(e2e_runs, key=lambda k: e2e_runs[k][0])
-    e2e_dt, n_rec, launches_e2e = e2e_runs[best_zc]
+        raise SystemExit(f"PARITY FAILURE: the base-transfer modes of the full batch differ: {digests}")
+    for m in modes:
+        dt, n_rec, nl = measure_e2e(m)
+        e2e_runs[m] = (max_over_ranks(dt), n_rec, nl)
+    best_mode = min(e2e_runs, key=lambda k: e2e_runs[k][0])
+    e2e_dt, n_rec, launches_e2e = e2e_runs[best_mode]
+    chunks = chunk_sets[False]
     d2h = int(n_rec) * (1 + 4 + 4 + 4 + 8 + 1 + 2 + 2 + 1 + 8) + int(cnt["n_out_ops"]) * 4 + (n_reads + 1) * 4
     e2e_value = pairs_total / e2e_dt
     sampler.stop()
@@ -392,12 +412,12 @@ def main():
                                    f"{n_reads} reads per GPU)",
                        "reads_per_gpu": int(n_reads), "pairs_per_step_per_gpu": int(cnt["n_pairs"]), "lifted_per_step_per_gpu": int(cnt["n_lifted"]),
                        "l2_policy": "inputs larger than L2 (CIGAR pools + op scratch > 126 MB per step)", "sharding": "by contig set, no collective",
-                       "e2e_pipeline": f"{len(chunks)} batches of {args.chunk} reads over 3 slots", "e2e_seq_zero_copy": bool(best_zc),
+                       "e2e_pipeline": f"{len(chunks)} batches of {args.chunk} reads over 3 slots", "e2e_base_transfer": best_mode,
                        "parity": parity, "full_batch_digest": f"{list(digests.values())[0]:016x} (identical across {len(digests)} base-transfer modes)",
                        "generate_s": round(t_gen, 1)},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(small_h2d + (0 if best_zc else seq_h2d)), "d2h_bytes_per_step": int(d2h),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes(best_mode)), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_dt * 1e3,
-                    "alternatives": {("seq_zero_copy" if k else "seq_bulk_upload"): {"value": pairs_total / v[0], "ms_per_step": v[0] * 1e3} for k, v in e2e_runs.items()}},
+                    "alternatives": {k: {"value": pairs_total / v[0], "ms_per_step": v[0] * 1e3, "h2d_bytes_per_step": int(h2d_bytes(k))} for k, v in e2e_runs.items()}},
             "gpu_launches": int(launches_value),
             "gpu_launches_e2e": int(launches_e2e),
             "roofline": roofline,

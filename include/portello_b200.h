@@ -107,6 +107,17 @@ typedef struct ptl_batch {
     uint64_t n_cigar;                 /* ops in the pool */
     const uint8_t* seq4;              /* packed bases pool; for ptl_lift_submit pinned host memory gives async copies */
     uint64_t seq4_bytes;
+    /* Optional "indel windows" (NULL / 0 = absent).  left_shift_indels (a5) compares, for every I/D cluster of a read
+     * segment that sits on a reverse-strand contig segment, a few read bases next to the cluster
+     * (lib/rust-vc-utils/src/indel_breakend_homology.rs:35-49); which ones is data dependent, but they always START at
+     * the cluster.  A window holds the first 16 bases the walk of one cluster can touch, 4 bits each (bits [4q,4q+4) =
+     * the stored BAM nibble compared at walk step q), so the kernels need the packed bases themselves (seq4, over PCIe
+     * in zero-copy mode) only for walks longer than 16 bases and for simplify_alignment_indels.  Windows of read
+     * segment s are indel_win[rseg_win_begin[s] .. rseg_win_begin[s+1]) in the cluster order of the REVERSED segment
+     * CIGAR (:165-167); a segment may have none (the kernels then read seq4).  Built by ptl_pack_batch_ex. */
+    const uint64_t* indel_win;
+    const uint32_t* rseg_win_begin;   /* [n_read_segments+1] */
+    uint64_t n_indel_win;
 } ptl_batch;
 
 /* ---------------------------------------------------------------- outputs */
@@ -233,6 +244,8 @@ int ptl_slot_counters(ptl_ctx* ctx, int slot, uint64_t* out);
 /* 0: copy seq4 to the device (default). 1: seq4 of subsequent batches must be pinned+mapped host memory
  * (ptl_host_alloc); kernels read the few bases they need over PCIe instead of uploading every base. */
 int ptl_set_seq_zero_copy(ptl_ctx* ctx, int enable);
+/* out[c] = 1 if contig c owns a reverse-strand contig->ref segment (after trim/join), else 0.  cap >= n_contigs. */
+int ptl_contig_reverse_mask(const ptl_ctx* ctx, uint32_t cap, uint8_t* out);
 
 /* Pinned (page-locked, device-mapped) host memory for batches: replaces nothing in the reference, it is the
  * "pinned structure-of-arrays batches" of the north star. */
@@ -266,6 +279,12 @@ typedef struct ptl_read_records {
 typedef struct ptl_packed_batch ptl_packed_batch;
 int ptl_pack_batch(const ptl_read_records* recs, uint32_t first, uint32_t count, uint32_t n_contigs,
                    const char* const* contig_names, int pinned, ptl_packed_batch** out);
+/* As ptl_pack_batch, plus indel windows (ptl_batch.indel_win) for every read segment on a contig c with
+ * contig_wants_windows[c] != 0 (NULL = no windows at all = ptl_pack_batch).  ptl_contig_reverse_mask gives the contigs
+ * that own a reverse-strand segment, the only ones whose read segments go through left_shift_indels. */
+int ptl_pack_batch_ex(const ptl_read_records* recs, uint32_t first, uint32_t count, uint32_t n_contigs,
+                      const char* const* contig_names, int pinned, const uint8_t* contig_wants_windows,
+                      ptl_packed_batch** out);
 void ptl_packed_batch_view(const ptl_packed_batch* p, ptl_batch* out);
 /* [view.n_reads] index of each batch read in `recs` (supplementary records are dropped by the packer). */
 const uint32_t* ptl_packed_batch_record_index(const ptl_packed_batch* p);

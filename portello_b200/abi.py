@@ -93,6 +93,9 @@ class BatchC(C.Structure):
         ("n_cigar", C.c_uint64),
         ("seq4", u8p),
         ("seq4_bytes", C.c_uint64),
+        ("indel_win", u64p),
+        ("rseg_win_begin", u32p),
+        ("n_indel_win", C.c_uint64),
     ]
 
 

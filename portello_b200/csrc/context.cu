@@ -81,7 +81,7 @@ struct Slot {
     bool have_events = false;
     // device copies of the batch
     DBuf d_read_flag, d_read_mapq, d_read_bin, d_read_seq_len, d_read_seq_off, d_read_seg_begin, d_rseg_contig, d_rseg_pos,
-        d_rseg_is_fwd, d_rseg_cigar_begin, d_rseg_cigar_len, d_cigar, d_seq4, d_arena;
+        d_rseg_is_fwd, d_rseg_cigar_begin, d_rseg_cigar_len, d_cigar, d_seq4, d_arena, d_win_begin, d_win;
     // work
     DBuf w_rseg_read, w_rseg_pair_begin, w_rseg_ref_len, w_rseg_n_id, w_rseg_read_len, w_pair_cap_b, w_pair_rseg, w_pair_seg, w_pair_slot_begin, w_pair_status, w_pair_flip,
         w_pair_pos, w_pair_n_out, w_pair_bin, w_pair_out_off, w_simplify_list, w_scratch, w_read_counts, w_read_primary, w_scan_tmp, w_totals;
@@ -224,8 +224,10 @@ void upload_batch(ptl_ctx* ctx, Slot& sl, const ptl_batch* b) {
     // The packer (ptl_pack_batch) lays every small array out in ONE contiguous arena: move it with a single DMA instead
     // of twelve (31 -> ~50 GB/s effective on the 136 MB of a 1 M-read batch).  Arbitrary caller layouts take the
     // per-array path.
+    const bool have_win = b->indel_win != nullptr && b->rseg_win_begin != nullptr;
+    if (have_win && ns && b->rseg_win_begin[ns] > b->n_indel_win) throw std::runtime_error("rseg_win_begin outside the indel window pool");
     struct Arr { const void* p; size_t bytes; };
-    const Arr arrs[12] = {{b->read_flag, size_t(n) * 2}, {b->read_mapq, size_t(n)}, {b->read_bin, size_t(n) * 2}, {b->read_seq_len, size_t(n) * 4},
+    const Arr arrs[14] = {{b->rseg_win_begin, have_win ? (size_t(ns) + 1) * 4 : 0}, {b->indel_win, have_win ? size_t(b->n_indel_win) * 8 : 0},{b->read_flag, size_t(n) * 2}, {b->read_mapq, size_t(n)}, {b->read_bin, size_t(n) * 2}, {b->read_seq_len, size_t(n) * 4},
                           {b->read_seq_off, size_t(n) * 8}, {b->read_seg_begin, (size_t(n) + 1) * 4}, {b->rseg_contig, size_t(ns) * 4},
                           {b->rseg_pos, size_t(ns) * 8}, {b->rseg_is_fwd, size_t(ns)}, {b->rseg_cigar_begin, size_t(ns) * 8},
                           {b->rseg_cigar_len, size_t(ns) * 4}, {b->cigar, size_t(b->n_cigar) * 4}};
@@ -255,6 +257,8 @@ void upload_batch(ptl_ctx* ctx, Slot& sl, const ptl_batch* b) {
         B.rseg_cigar_begin = reinterpret_cast<const uint64_t*>(at(b->rseg_cigar_begin));
         B.rseg_cigar_len = reinterpret_cast<const uint32_t*>(at(b->rseg_cigar_len));
         B.cigar = reinterpret_cast<const uint32_t*>(at(b->cigar));
+        B.rseg_win_begin = have_win ? reinterpret_cast<const uint32_t*>(at(b->rseg_win_begin)) : nullptr;
+        B.indel_win = have_win ? reinterpret_cast<const uint64_t*>(at(b->indel_win)) : nullptr;
     } else {
         B.read_flag = upload(sl.d_read_flag, b->read_flag, n, st);
         B.read_mapq = upload(sl.d_read_mapq, b->read_mapq, n, st);
@@ -268,6 +272,8 @@ void upload_batch(ptl_ctx* ctx, Slot& sl, const ptl_batch* b) {
         B.rseg_cigar_begin = upload(sl.d_rseg_cigar_begin, b->rseg_cigar_begin, ns, st);
         B.rseg_cigar_len = upload(sl.d_rseg_cigar_len, b->rseg_cigar_len, ns, st);
         B.cigar = upload(sl.d_cigar, b->cigar, b->n_cigar, st);
+        B.rseg_win_begin = have_win ? upload(sl.d_win_begin, b->rseg_win_begin, size_t(ns) + 1, st) : nullptr;
+        B.indel_win = have_win ? upload(sl.d_win, b->indel_win, size_t(b->n_indel_win), st) : nullptr;
     }
     if (ctx->zero_copy_seq) {
         void* dptr = nullptr;
@@ -520,7 +526,7 @@ void ptl_destroy(ptl_ctx* ctx) {
         if (sl.stream) cudaStreamSynchronize(sl.stream);
         for (DBuf* b : {&sl.d_read_flag, &sl.d_read_mapq, &sl.d_read_bin, &sl.d_read_seq_len, &sl.d_read_seq_off, &sl.d_read_seg_begin,
                         &sl.d_rseg_contig, &sl.d_rseg_pos, &sl.d_rseg_is_fwd, &sl.d_rseg_cigar_begin, &sl.d_rseg_cigar_len, &sl.d_cigar,
-                        &sl.d_seq4, &sl.d_arena, &sl.w_rseg_read, &sl.w_rseg_pair_begin, &sl.w_rseg_ref_len, &sl.w_rseg_n_id, &sl.w_rseg_read_len, &sl.w_pair_cap_b, &sl.w_pair_rseg, &sl.w_pair_seg,
+                        &sl.d_seq4, &sl.d_arena, &sl.d_win_begin, &sl.d_win, &sl.w_rseg_read, &sl.w_rseg_pair_begin, &sl.w_rseg_ref_len, &sl.w_rseg_n_id, &sl.w_rseg_read_len, &sl.w_pair_cap_b, &sl.w_pair_rseg, &sl.w_pair_seg,
                         &sl.w_pair_slot_begin, &sl.w_pair_status, &sl.w_pair_flip, &sl.w_pair_pos, &sl.w_pair_n_out, &sl.w_pair_bin, &sl.w_pair_out_off, &sl.w_simplify_list,
                         &sl.w_scratch, &sl.w_read_counts, &sl.w_read_primary, &sl.w_scan_tmp, &sl.w_totals, &sl.r_read_rec_begin,
                         &sl.r_status, &sl.r_rseg, &sl.r_cseg, &sl.r_tid, &sl.r_pos, &sl.r_mapq, &sl.r_flag, &sl.r_bin, &sl.r_flip,
@@ -671,6 +677,16 @@ uint64_t ptl_launch_count(const ptl_ctx* ctx) { return ctx ? ctx->launches : 0; 
 int ptl_set_seq_zero_copy(ptl_ctx* ctx, int enable) {
     if (!ctx) return PTL_ERR_INVALID_ARG;
     ctx->zero_copy_seq = enable != 0;
+    return PTL_OK;
+}
+int ptl_contig_reverse_mask(const ptl_ctx* ctx, uint32_t cap, uint8_t* out) {
+    if (!ctx || !out || !ctx->have_segments || cap < ctx->S.n_contigs) return PTL_ERR_INVALID_ARG;
+    const FlatContigs& f = ctx->flat;
+    for (uint32_t c = 0; c < ctx->S.n_contigs; ++c) {
+        uint8_t any = 0;
+        for (uint32_t g = f.seg_begin[c]; g < f.seg_begin[c + 1]; ++g) any |= (f.is_fwd[g] == 0);
+        out[c] = any;
+    }
     return PTL_OK;
 }
 // Counters of the last finished batch on a slot: out[0..6) = n_pairs, n_lifted, n_in_ops, n_out_ops, base bytes compared,

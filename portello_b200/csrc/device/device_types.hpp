@@ -65,6 +65,9 @@ struct DevBatch {
     const uint32_t* rseg_cigar_len = nullptr;
     const uint32_t* cigar = nullptr;
     const uint8_t* seq4 = nullptr;  // device copy, or a mapped pinned host pointer in zero-copy mode
+    // optional indel windows (ptl_batch.indel_win): the first 16 read nibbles the homology walk of each I/D cluster touches
+    const uint64_t* indel_win = nullptr;
+    const uint32_t* rseg_win_begin = nullptr;  // [n_rsegs+1], nullptr = no windows
 };
 
 // ---- per-batch work arrays ---------------------------------------------------------------------------------------

@@ -161,26 +161,38 @@ __device__ __forceinline__ uint64_t load_bytes_le(const uint8_t* a, uint32_t n_b
 }
 
 // One round trip of the left homology walk: up to 8 (ref, read) base pairs are fetched with ONE word load per side (two
-// if the window straddles an 8-byte boundary) and compared in order.  In zero-copy mode this is one PCIe read per
-// probe instead of one per base.
+// if the window straddles an 8-byte boundary) and compared in order.  The first 16 read bases of a walk come from the
+// cluster's indel window when the batch carries one (`have_win`; no read-side memory access at all); otherwise, and
+// beyond 16 bases, they are read from the packed bases (in zero-copy mode one PCIe read per probe).
 __device__ __forceinline__ void walk_homology8(const uint8_t* __restrict__ ref_seq, const ReadBases& read, uint32_t ref_end, uint32_t read_end,
-                                               uint32_t limit, uint32_t& hom, bool& walking, PairCounters& cnt) {
+                                               uint32_t limit, uint64_t win, bool have_win, uint32_t& hom, bool& walking, PairCounters& cnt) {
     const uint32_t nv = min(8u, limit - hom);  // >= 1 while walking
     // reference side: ASCII bytes ref_seq[rhi - q], q = 0..nv-1
     const uint32_t rhi = ref_end - 1u - hom, rlo = rhi - (nv - 1u);
     const uint64_t rw = load_bytes_le(ref_seq + rlo, nv);
-    // read side: 4-bit bases at stored positions jhi - q (forward view) or jlo + q (reverse-complement view)
-    uint32_t jlo, jhi;
-    if (!read.flip) { jhi = read_end - 1u - hom; jlo = jhi - (nv - 1u); }
-    else { jlo = read.len - read_end + hom; jhi = jlo + (nv - 1u); }
-    const uint32_t b0 = jlo >> 1;
-    const uint64_t qw = load_bytes_le(read.seq4 + b0, (jhi >> 1) - b0 + 1u);
+    // read side, as the nibble of walk step hom + q in bits [4q, 4q+4) of `nibs`
+    uint32_t nibs;
+    if (have_win && hom < 16u) {  // hom is 0 or 8 here
+        nibs = uint32_t(win >> (4u * hom));
+    } else {
+        // 4-bit bases at stored positions jhi - q (forward view) or jlo + q (reverse-complement view)
+        uint32_t jlo, jhi;
+        if (!read.flip) { jhi = read_end - 1u - hom; jlo = jhi - (nv - 1u); }
+        else { jlo = read.len - read_end + hom; jhi = jlo + (nv - 1u); }
+        const uint32_t b0 = jlo >> 1;
+        const uint64_t qw = load_bytes_le(read.seq4 + b0, (jhi >> 1) - b0 + 1u);
+        nibs = 0;
+#pragma unroll
+        for (uint32_t q = 0; q < 8; ++q) {
+            const uint32_t j = read.flip ? jlo + q : jhi - q;  // (steps >= nv are never compared)
+            nibs |= (uint32_t(qw >> ((8u * ((j >> 1) - b0) + ((j & 1u) ? 0u : 4u)) & 63u)) & 0xfu) << (4u * q);
+        }
+    }
 #pragma unroll
     for (uint32_t q = 0; q < 8; ++q) {
         if (walking && q < nv) {
             const uint32_t rb = uint32_t(rw >> (8u * (nv - 1u - q))) & 0xffu;
-            const uint32_t j = read.flip ? jlo + q : jhi - q;
-            const uint32_t nib = uint32_t(qw >> (8u * ((j >> 1) - b0) + ((j & 1u) ? 0u : 4u))) & 0xfu;
+            const uint32_t nib = (nibs >> (4u * q)) & 0xfu;
             cnt.base_bytes += 2;
             if (rb != uint32_t(ReadBases::decode(nib, read.flip))) walking = false;
             else ++hom;
@@ -200,9 +212,10 @@ __device__ __forceinline__ void walk_homology8(const uint8_t* __restrict__ ref_s
 // Only min(match_block, homology) matters (:124) and match_block_k <= gap_k + homology_{k-1}, so phase A can bound the
 // walk of cluster k by limit_k = min(max_left_k, gap_k + limit_{k-1}) without knowing the homologies: same result.
 // `clus` needs 3 words per cluster.  Warp-collective.  Returns the shifted position.
+// `win` / `n_win`: the indel windows of the read segment (cluster order of this walk), used iff n_win == the cluster count.
 __device__ __forceinline__ uint32_t run_left_shift_warp(bool active, const OpSource& in, uint32_t ref_pos, const uint8_t* __restrict__ ref_seq,
-                                                        uint32_t ref_len, const ReadBases& read, uint32_t* __restrict__ clus, OpSink& sink,
-                                                        PairCounters& cnt, int& err) {
+                                                        uint32_t ref_len, const ReadBases& read, const uint64_t* __restrict__ win, uint32_t n_win,
+                                                        uint32_t* __restrict__ clus, OpSink& sink, PairCounters& cnt, int& err) {
     // ---- phase A
     uint32_t n_clus = 0;
     if (active) {
@@ -244,18 +257,21 @@ __device__ __forceinline__ uint32_t run_left_shift_warp(bool active, const OpSou
         if (in_indel) close();
     }
     // ---- phase B
+    const bool have_win = (n_win == n_clus) && n_clus > 0;
     for (uint32_t k = 0; __any_sync(FULL, k < n_clus); ++k) {
         uint32_t hom = 0, limit = 0, ref_end = 0, read_end = 0;
+        uint64_t w = 0;
         if (k < n_clus) {
             ref_end = clus[3 * k];
             read_end = clus[3 * k + 1];
             limit = clus[3 * k + 2];
+            if (have_win && limit > 0) w = win[k];
         }
         bool walking = limit > 0;
         // 8 bases per round trip (almost every walk ends in the first): long walks only happen in repeats or reducible
         // I/D clusters, and they hold the whole warp
         while (__any_sync(FULL, walking)) {
-            if (walking) walk_homology8(ref_seq, read, ref_end, read_end, limit, hom, walking, cnt);
+            if (walking) walk_homology8(ref_seq, read, ref_end, read_end, limit, w, have_win, hom, walking, cnt);
         }
         if (k < n_clus) clus[3 * k] = hom;
     }

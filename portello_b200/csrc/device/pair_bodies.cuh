@@ -202,8 +202,15 @@ __device__ __forceinline__ void lift_pair_body(const DevStatic& S, const DevBatc
         }
         if (__any_sync(FULL, go)) {
             OpSink sink(buf_a, go ? cap_a : 0u);
+            const uint64_t* win = nullptr;
+            uint32_t n_win = 0;
+            if (go && B.rseg_win_begin) {
+                const uint32_t w0 = B.rseg_win_begin[s];
+                win = B.indel_win + w0;
+                n_win = B.rseg_win_begin[s + 1] - w0;
+            }
             const uint32_t shifted = run_left_shift_warp(go, cur, cpos, go ? S.rev_pool + rev_off : nullptr,
-                                                         go ? uint32_t(S.contig_len[ctg]) : 0u, read, buf_b, sink, cnt, err);
+                                                         go ? uint32_t(S.contig_len[ctg]) : 0u, read, win, n_win, buf_b, sink, cnt, err);
             if (go) {
                 cpos = shifted;
                 span = sink.ref_span;

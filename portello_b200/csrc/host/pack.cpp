@@ -206,6 +206,11 @@ int ptl_pack_split_segments(uint32_t n_names, const char* const* contig_names, i
 
 int ptl_pack_batch(const ptl_read_records* recs, uint32_t first, uint32_t count, uint32_t n_contigs,
                    const char* const* contig_names, int pinned, ptl_packed_batch** out) {
+    return ptl_pack_batch_ex(recs, first, count, n_contigs, contig_names, pinned, nullptr, out);
+}
+
+int ptl_pack_batch_ex(const ptl_read_records* recs, uint32_t first, uint32_t count, uint32_t n_contigs,
+                      const char* const* contig_names, int pinned, const uint8_t* contig_wants_windows, ptl_packed_batch** out) {
     if (!recs || !out || uint64_t(first) + count > recs->n_reads) return PTL_ERR_INVALID_ARG;
     try {
         NameMap names(n_contigs, contig_names);
@@ -236,12 +241,38 @@ int ptl_pack_batch(const ptl_read_records* recs, uint32_t first, uint32_t count,
         }
         const uint32_t n = uint32_t(kept.size()), ns = uint32_t(segs.size());
         const uint64_t n_cig = (cig1 - cig0) + sa_pool.size();
+        auto seg_cigar = [&](const Seg& g) {
+            return g.cig_off < uint32_t(cig1 - cig0) ? recs->cigar + cig0 + g.cig_off : sa_pool.data() + (g.cig_off - uint32_t(cig1 - cig0));
+        };
+        // indel windows: count the I/D clusters (maximal runs of non-empty I/D ops, as CigarShiftBuilder forms them,
+        // cigar_indel_shifter.rs:63-85) of every segment that wants them
+        std::vector<uint32_t> win_begin;
+        uint64_t n_win = 0;
+        if (contig_wants_windows) {
+            win_begin.assign(size_t(ns) + 1, 0);
+            for (uint32_t k = 0; k < ns; ++k) {
+                win_begin[k] = uint32_t(n_win);
+                const Seg& g = segs[k];
+                if (g.contig >= n_contigs || !contig_wants_windows[g.contig]) continue;
+                const uint32_t* c = seg_cigar(g);
+                bool in_indel = false;
+                for (uint32_t i = 0; i < g.cig_len; ++i) {
+                    const uint32_t op = op_of(c[i]);
+                    if (op == OP_I || op == OP_D) { if (len_of(c[i]) > 0) in_indel = true; }
+                    else if (in_indel) { ++n_win; in_indel = false; }
+                }
+                if (in_indel) ++n_win;
+                if (n_win > 0xffffffffull) throw InputError("too many indel clusters in one batch");
+            }
+            win_begin[ns] = uint32_t(n_win);
+        }
         // one arena for all small arrays
         size_t off = 0;
         auto take = [&](size_t bytes) { const size_t o = off; off = align_up(off + bytes); return o; };
         const size_t o_flag = take(n * 2), o_mapq = take(n), o_bin = take(n * 2), o_len = take(n * 4), o_soff = take(n * 8),
                      o_sb = take((n + 1) * 4), o_ctg = take(ns * 4), o_pos = take(ns * 8), o_fwd = take(ns), o_cb = take(ns * 8),
                      o_cl = take(ns * 4), o_cig = take(n_cig * 4);
+        const size_t o_wb = contig_wants_windows ? take((size_t(ns) + 1) * 4) : 0, o_win = contig_wants_windows ? take(n_win * 8) : 0;
         auto* pb = new ptl_packed_batch();
         pb->pinned = pinned != 0;
         pb->arena = pinned ? ptl_host_alloc(std::max<size_t>(off, 256)) : std::malloc(std::max<size_t>(off, 256));
@@ -291,6 +322,60 @@ int ptl_pack_batch(const ptl_read_records* recs, uint32_t first, uint32_t count,
         if (cig1 > cig0) std::memcpy(cig, recs->cigar + cig0, size_t(cig1 - cig0) * 4);
         if (!sa_pool.empty()) std::memcpy(cig + (cig1 - cig0), sa_pool.data(), sa_pool.size() * 4);
         ptl_batch& v = pb->view;
+        if (contig_wants_windows) {
+            // The walk of cluster k (in the order of the REVERSED CIGAR, read_alignment_scanner.rs:165-167) compares
+            // read_view[read_end - 1 - q], q = 0,1,..; read_view is the record's bases, reverse-complemented when
+            // need_flipped_read_alignment (:153-157), which for a reverse-strand contig segment is
+            // !(record.is_reverse() == segment.is_fwd_strand).  The window stores the BAM nibble of each step.
+            auto* wb = reinterpret_cast<uint32_t*>(a + o_wb);
+            auto* win = reinterpret_cast<uint64_t*>(a + o_win);
+            std::memcpy(wb, win_begin.data(), (size_t(ns) + 1) * 4);
+            for (uint32_t i = 0; i < n; ++i) {
+                const uint32_t r = kept[i];
+                const uint8_t* sq = recs->seq4 + recs->seq_off[r];
+                const uint32_t len = recs->seq_len[r];
+                const bool rec_rev = (recs->flag[r] & 0x10) != 0;
+                for (uint32_t k = seg_begin[i]; k < seg_begin[i + 1]; ++k) {
+                    if (win_begin[k] == win_begin[k + 1]) continue;
+                    const Seg& g = segs[k];
+                    const bool flip = !(rec_rev == (g.is_fwd != 0));
+                    const uint32_t* c = seg_cigar(g);
+                    uint64_t* w = win + win_begin[k];
+                    uint32_t read_head = 0, blk_read = 0, ins = 0;
+                    bool in_indel = false;
+                    auto close = [&]() {
+                        const uint32_t read_end = blk_read + ins;
+                        uint64_t bits = 0;
+                        for (uint32_t q = 0; q < 16 && q < read_end; ++q) {
+                            const uint32_t idx = read_end - 1u - q;
+                            if (idx >= len) continue;  // out of bounds: the kernel reports the reference's panic before reading
+                            const uint32_t j = flip ? len - 1u - idx : idx;
+                            const uint32_t nib = (j & 1u) ? (sq[j >> 1] & 0xfu) : (sq[j >> 1] >> 4);
+                            bits |= uint64_t(nib) << (4u * q);
+                        }
+                        *w++ = bits;
+                        in_indel = false;
+                        ins = 0;
+                    };
+                    for (uint32_t t = g.cig_len; t-- > 0;) {
+                        const uint32_t x = c[t], op = op_of(x), l = len_of(x);
+                        if (op == OP_I || op == OP_D) {
+                            if (l > 0) {
+                                if (!in_indel) { in_indel = true; blk_read = read_head; }
+                                if (op == OP_I) ins += l;
+                            }
+                        } else if (in_indel) {
+                            close();
+                        }
+                        read_head += uint32_t(read_adv(x));
+                    }
+                    if (in_indel) close();
+                }
+            }
+            v.indel_win = win;
+            v.rseg_win_begin = wb;
+            v.n_indel_win = n_win;
+        }
         v.n_reads = n;
         v.read_flag = flag; v.read_mapq = mapq; v.read_bin = bin; v.read_seq_len = slen; v.read_seq_off = soff;
         v.read_seg_begin = sb;

@@ -29,7 +29,8 @@ struct EmulSlot {
     std::vector<uint16_t> read_flag, read_bin;
     std::vector<uint8_t> read_mapq, rseg_is_fwd, seq4;
     std::vector<uint32_t> read_seq_len, read_seg_begin, rseg_contig, rseg_cigar_len, cigar;
-    std::vector<uint64_t> read_seq_off, rseg_cigar_begin;
+    std::vector<uint64_t> read_seq_off, rseg_cigar_begin, indel_win;
+    std::vector<uint32_t> rseg_win_begin;
     std::vector<int64_t> rseg_pos;
     // results
     std::vector<uint32_t> read_rec_begin, rec_rseg, rec_cseg, out_cigar;
@@ -155,6 +156,12 @@ int run_batch(ptl_ctx* ctx, EmulSlot& sl, const ptl_batch* b, uint32_t stage_mas
     B.rseg_contig = sl.rseg_contig.data(); B.rseg_pos = sl.rseg_pos.data(); B.rseg_is_fwd = sl.rseg_is_fwd.data();
     B.rseg_cigar_begin = sl.rseg_cigar_begin.data(); B.rseg_cigar_len = sl.rseg_cigar_len.data(); B.cigar = sl.cigar.data();
     B.seq4 = sl.seq4.data();
+    if (b->indel_win && b->rseg_win_begin) {
+        sl.rseg_win_begin = padded_copy(b->rseg_win_begin, size_t(ns) + 1);
+        sl.indel_win = padded_copy(b->indel_win, b->n_indel_win);
+        B.rseg_win_begin = sl.rseg_win_begin.data();
+        B.indel_win = sl.indel_win.data();
+    }
     const DevStatic& S = ctx->S;
     DevTotals& T = sl.totals;
     totals_reset(&T);

@@ -29,10 +29,10 @@ def gpu_context(s, n_slots=2):
     return ctx
 
 
-def pack(s, first=0, count=None, pinned=False):
+def pack(s, first=0, count=None, pinned=False, windows=None):
     n = s.read_records.n_reads
     count = n - first if count is None else count
-    return lib.PackedBatch(lib.load(), s.read_records, first, count, s.contig_names, pinned)
+    return lib.PackedBatch(lib.load(), s.read_records, first, count, s.contig_names, pinned, windows=windows)
 
 
 def lift_c(ctx, batch_c, stage_mask=abi.STAGE_ALL, slot=0, allow_panic=False):

@@ -186,3 +186,29 @@ def test_zero_copy_bases_give_identical_results():
     assert np.array_equal(np.concatenate([r.cigar for r in recs]), bulk.cigar)
     assert np.array_equal(np.concatenate([r.rec_pos for r in recs]), bulk.rec_pos)
     assert np.array_equal(np.concatenate([r.rec_bin for r in recs]), bulk.rec_bin)
+
+
+def test_indel_windows_give_identical_results():
+    """Batches packed with indel windows (ptl_pack_batch_ex; the first 16 read bases of every homology walk travel with
+    the batch, so zero-copy runs stop fetching them over PCIe) must equal the plain batches and the oracle bit for bit."""
+    L = lib.load()
+    alloc = C.cast(L.dll.ptl_host_alloc, C.c_void_p)
+    free = C.cast(L.dll.ptl_host_free, C.c_void_p)
+    s = synth.make("tiny", host_alloc=alloc, host_free=free, seed=59, n_reads=6000, rev_contig_frac=0.7, read_cluster_frac=0.2)
+    gctx = helpers.gpu_context(s)
+    mask = gctx.reverse_mask()
+    assert mask.any() and len(mask) == len(s.contig_names)
+    plain = helpers.pack(s, pinned=True)
+    win = helpers.pack(s, pinned=True, windows=mask)
+    assert 0 < win.c.n_indel_win
+    ro = helpers.lift_c(helpers.oracle_context(s), plain.c)
+    for zero_copy in (False, True):
+        gctx.set_seq_zero_copy(zero_copy)
+        assert helpers.lift_c(gctx, win.c).diff(ro) is None
+        assert helpers.lift_c(gctx, plain.c).diff(ro) is None
+    # windows for every contig (mask = all ones) and a stress-shaped workload with long walks (> 16 bases fall back to seq4)
+    s2 = synth.make("stress", host_alloc=alloc, host_free=free, n_reads=800)
+    g2 = helpers.gpu_context(s2)
+    w2 = helpers.pack(s2, pinned=True, windows=True)
+    g2.set_seq_zero_copy(True)
+    assert helpers.lift_c(g2, w2.c).diff(helpers.lift_c(helpers.oracle_context(s2), w2.c)) is None

@@ -9,9 +9,11 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
 s = synth.make("chr20", host_alloc=alloc, host_free=free, n_reads=n)
 ctx = lib.GpuContext(0, 3)
 ctx.set_reference(helpers.reference_arrays(s)); ctx.set_contig_records(s.contig_records)
-pb = lib.PackedBatch(L, s.read_records, 0, n, s.contig_names, pinned=True)
+pb0 = lib.PackedBatch(L, s.read_records, 0, n, s.contig_names, pinned=True)
+pbw = lib.PackedBatch(L, s.read_records, 0, n, s.contig_names, pinned=True, windows=ctx.reverse_mask())
+print(f"reads {n}  rsegs {pb0.c.n_read_segments}  cigar ops {pb0.c.n_cigar}  indel windows {pbw.c.n_indel_win}")
 def sync(): torch.cuda.synchronize()
-for zc in (False, True):
+for zc, pb in ((False, pb0), (True, pb0), (True, pbw)):
     ctx.set_seq_zero_copy(zc)
     for rep in range(3):
         sync(); t0 = time.perf_counter()
@@ -19,7 +21,7 @@ for zc in (False, True):
         ctx.run(0); sync(); t2 = time.perf_counter()
         r = ctx.download(0, copy=False); t3 = time.perf_counter()
     kt = ctx.kernel_times(0)
-    print(f"zero_copy={zc}: upload {1e3*(t1-t0):.2f} ms  run {1e3*(t2-t1):.2f} ms  download {1e3*(t3-t2):.2f} ms   stages {kt}")
+    print(f"zero_copy={zc} windows={pb is pbw}: upload {1e3*(t1-t0):.2f} ms  run {1e3*(t2-t1):.2f} ms  download {1e3*(t3-t2):.2f} ms   stages {kt}")
     sync(); t0 = time.perf_counter()
     for rep in range(5):
         ctx.submit_c(pb.c, 0); ctx.wait_c(0)
