@@ -224,15 +224,15 @@ def main():
     n_table = sum(len(ctx.get_segment_table(g)[0]) for g in range(n_segments))
 
     whole = lib.PackedBatch(L, s.read_records, 0, n_reads, s.contig_names, pinned=True)
-    rev_mask = ctx.reverse_mask()
+    win_segs = ctx.get_contig_segments()
     chunk_sets = {
         False: [lib.PackedBatch(L, s.read_records, a, min(args.chunk, n_reads - a), s.contig_names, pinned=True)
                 for a in range(0, n_reads, args.chunk)],
-        # indel windows (ptl_pack_batch_ex) for the read segments on contigs that own a reverse-strand segment
-        True: [lib.PackedBatch(L, s.read_records, a, min(args.chunk, n_reads - a), s.contig_names, pinned=True, windows=rev_mask)
+        # indel windows (ptl_pack_batch_ex) for the read segments that pair with a reverse-strand contig segment
+        True: [lib.PackedBatch(L, s.read_records, a, min(args.chunk, n_reads - a), s.contig_names, pinned=True, windows=win_segs)
                for a in range(0, n_reads, args.chunk)],
     }
-    whole_win = lib.PackedBatch(L, s.read_records, 0, n_reads, s.contig_names, pinned=True, windows=rev_mask)
+    whole_win = lib.PackedBatch(L, s.read_records, 0, n_reads, s.contig_names, pinned=True, windows=win_segs)
 
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -308,8 +308,8 @@ def main():
         return recs
 
     def measure_e2e(mode):
-        zero_copy, windows = MODES[mode]
-        chunks = chunk_sets[windows]
+        zero_copy, use_win = MODES[mode]
+        chunks = chunk_sets[use_win]
         ctx.set_seq_zero_copy(zero_copy)
         for _ in range(max(args.warmup, 3)):
             e2e_step(chunks)
@@ -329,18 +329,18 @@ def main():
     MODES = {"seq_bulk_upload": (False, False), "seq_zero_copy": (True, False), "seq_zero_copy_indel_windows": (True, True)}
 
     def h2d_bytes(mode):
-        zero_copy, windows = MODES[mode]
-        chunks = chunk_sets[windows]
+        zero_copy, use_win = MODES[mode]
+        chunks = chunk_sets[use_win]
         small = sum(int(ch.c.n_reads) * (2 + 1 + 2 + 4 + 8 + 4) + int(ch.c.n_read_segments) * (4 + 8 + 1 + 8 + 4) + int(ch.c.n_cigar) * 4 for ch in chunks)
-        win = sum((int(ch.c.n_read_segments) + 1) * 4 + int(ch.c.n_indel_win) * 8 for ch in chunks) if windows else 0
+        win = sum((int(ch.c.n_read_segments) + 1) * 4 + int(ch.c.n_indel_win) * 8 for ch in chunks) if use_win else 0
         seq = 0 if zero_copy else sum(int(ch.c.seq4_bytes) for ch in chunks)
         return small + win + seq
 
     def result_digest(mode):
         """Order-sensitive checksum of every result array of the whole batch (outside the timed region)."""
-        zero_copy, windows = MODES[mode]
+        zero_copy, use_win = MODES[mode]
         ctx.set_seq_zero_copy(zero_copy)
-        ctx.submit_c((whole_win if windows else whole).c, 0)
+        ctx.submit_c((whole_win if use_win else whole).c, 0)
         r = abi.Result.from_c(ctx.wait_c(0), copy=False)
         acc = np.uint64(1469598103934665603)
         for f in abi.Result.FIELDS:

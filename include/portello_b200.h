@@ -244,8 +244,7 @@ int ptl_slot_counters(ptl_ctx* ctx, int slot, uint64_t* out);
 /* 0: copy seq4 to the device (default). 1: seq4 of subsequent batches must be pinned+mapped host memory
  * (ptl_host_alloc); kernels read the few bases they need over PCIe instead of uploading every base. */
 int ptl_set_seq_zero_copy(ptl_ctx* ctx, int enable);
-/* out[c] = 1 if contig c owns a reverse-strand contig->ref segment (after trim/join), else 0.  cap >= n_contigs. */
-int ptl_contig_reverse_mask(const ptl_ctx* ctx, uint32_t cap, uint8_t* out);
+
 
 /* Pinned (page-locked, device-mapped) host memory for batches: replaces nothing in the reference, it is the
  * "pinned structure-of-arrays batches" of the north star. */
@@ -279,11 +278,15 @@ typedef struct ptl_read_records {
 typedef struct ptl_packed_batch ptl_packed_batch;
 int ptl_pack_batch(const ptl_read_records* recs, uint32_t first, uint32_t count, uint32_t n_contigs,
                    const char* const* contig_names, int pinned, ptl_packed_batch** out);
-/* As ptl_pack_batch, plus indel windows (ptl_batch.indel_win) for every read segment on a contig c with
- * contig_wants_windows[c] != 0 (NULL = no windows at all = ptl_pack_batch).  ptl_contig_reverse_mask gives the contigs
- * that own a reverse-strand segment, the only ones whose read segments go through left_shift_indels. */
+/* As ptl_pack_batch, plus indel windows (ptl_batch.indel_win):
+ *   PTL_WIN_NONE           no windows (= ptl_pack_batch)
+ *   PTL_WIN_ALL            for every read segment
+ *   PTL_WIN_REVERSE_PAIRS  only for read segments that pair (get_contig_split_segments_from_read_mapping,
+ *                          src/read_alignment_scanner.rs:80-103) with a reverse-strand contig segment of `segs`
+ *                          (ptl_get_contig_segments) - the only ones that go through left_shift_indels. */
+enum { PTL_WIN_NONE = 0, PTL_WIN_ALL = 1, PTL_WIN_REVERSE_PAIRS = 2 };
 int ptl_pack_batch_ex(const ptl_read_records* recs, uint32_t first, uint32_t count, uint32_t n_contigs,
-                      const char* const* contig_names, int pinned, const uint8_t* contig_wants_windows,
+                      const char* const* contig_names, int pinned, int window_mode, const ptl_contig_segments* segs,
                       ptl_packed_batch** out);
 void ptl_packed_batch_view(const ptl_packed_batch* p, ptl_batch* out);
 /* [view.n_reads] index of each batch read in `recs` (supplementary records are dropped by the packer). */

@@ -679,16 +679,6 @@ int ptl_set_seq_zero_copy(ptl_ctx* ctx, int enable) {
     ctx->zero_copy_seq = enable != 0;
     return PTL_OK;
 }
-int ptl_contig_reverse_mask(const ptl_ctx* ctx, uint32_t cap, uint8_t* out) {
-    if (!ctx || !out || !ctx->have_segments || cap < ctx->S.n_contigs) return PTL_ERR_INVALID_ARG;
-    const FlatContigs& f = ctx->flat;
-    for (uint32_t c = 0; c < ctx->S.n_contigs; ++c) {
-        uint8_t any = 0;
-        for (uint32_t g = f.seg_begin[c]; g < f.seg_begin[c + 1]; ++g) any |= (f.is_fwd[g] == 0);
-        out[c] = any;
-    }
-    return PTL_OK;
-}
 // Counters of the last finished batch on a slot: out[0..6) = n_pairs, n_lifted, n_in_ops, n_out_ops, base bytes compared,
 // scratch ops needed (roofline arithmetic).
 int ptl_slot_counters(ptl_ctx* ctx, int slot, uint64_t* out) {

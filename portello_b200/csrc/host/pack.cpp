@@ -206,12 +206,14 @@ int ptl_pack_split_segments(uint32_t n_names, const char* const* contig_names, i
 
 int ptl_pack_batch(const ptl_read_records* recs, uint32_t first, uint32_t count, uint32_t n_contigs,
                    const char* const* contig_names, int pinned, ptl_packed_batch** out) {
-    return ptl_pack_batch_ex(recs, first, count, n_contigs, contig_names, pinned, nullptr, out);
+    return ptl_pack_batch_ex(recs, first, count, n_contigs, contig_names, pinned, PTL_WIN_NONE, nullptr, out);
 }
 
 int ptl_pack_batch_ex(const ptl_read_records* recs, uint32_t first, uint32_t count, uint32_t n_contigs,
-                      const char* const* contig_names, int pinned, const uint8_t* contig_wants_windows, ptl_packed_batch** out) {
+                      const char* const* contig_names, int pinned, int window_mode, const ptl_contig_segments* wsegs, ptl_packed_batch** out) {
     if (!recs || !out || uint64_t(first) + count > recs->n_reads) return PTL_ERR_INVALID_ARG;
+    if (window_mode < PTL_WIN_NONE || window_mode > PTL_WIN_REVERSE_PAIRS || (window_mode == PTL_WIN_REVERSE_PAIRS && !wsegs)) return PTL_ERR_INVALID_ARG;
+    const bool contig_wants_windows = window_mode != PTL_WIN_NONE;
     try {
         NameMap names(n_contigs, contig_names);
         // pass 1: parse SA tags (rare), collect segment lists
@@ -253,8 +255,16 @@ int ptl_pack_batch_ex(const ptl_read_records* recs, uint32_t first, uint32_t cou
             for (uint32_t k = 0; k < ns; ++k) {
                 win_begin[k] = uint32_t(n_win);
                 const Seg& g = segs[k];
-                if (g.contig >= n_contigs || !contig_wants_windows[g.contig]) continue;
                 const uint32_t* c = seg_cigar(g);
+                if (window_mode == PTL_WIN_REVERSE_PAIRS) {
+                    // the pair test of :80-103 against the reverse-strand segments of the read segment's contig
+                    if (g.contig >= wsegs->n_contigs) continue;
+                    const int64_t start = g.pos, end = g.pos + ref_span(c, g.cig_len);
+                    bool hit = false;
+                    for (uint32_t q = wsegs->contig_seg_begin[g.contig]; q < wsegs->contig_seg_begin[g.contig + 1] && !hit; ++q)
+                        hit = !wsegs->seg_is_fwd[q] && end >= int64_t(wsegs->seg_seq_order_start[q]) && start < int64_t(wsegs->seg_seq_order_end[q]);
+                    if (!hit) continue;
+                }
                 bool in_indel = false;
                 for (uint32_t i = 0; i < g.cig_len; ++i) {
                     const uint32_t op = op_of(c[i]);

@@ -76,10 +76,8 @@ class ProductLib(LiftLib):
         d.ptl_pack_batch.restype = C.c_int
         d.ptl_pack_batch.argtypes = [C.POINTER(ReadRecordsC), C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_char_p), C.c_int, C.POINTER(C.c_void_p)]
         d.ptl_pack_batch_ex.restype = C.c_int
-        d.ptl_pack_batch_ex.argtypes = [C.POINTER(ReadRecordsC), C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_char_p), C.c_int, u8p,
-                                        C.POINTER(C.c_void_p)]
-        d.ptl_contig_reverse_mask.restype = C.c_int
-        d.ptl_contig_reverse_mask.argtypes = [C.c_void_p, C.c_uint32, u8p]
+        d.ptl_pack_batch_ex.argtypes = [C.POINTER(ReadRecordsC), C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_char_p), C.c_int, C.c_int,
+                                        C.POINTER(ContigSegmentsC), C.POINTER(C.c_void_p)]
         d.ptl_packed_batch_view.argtypes = [C.c_void_p, C.POINTER(BatchC)]
         d.ptl_packed_batch_record_index.restype = u32p
         d.ptl_packed_batch_record_index.argtypes = [C.c_void_p]
@@ -162,16 +160,18 @@ class PackedBatch:
     """Owner of a ptl_packed_batch (the host packer's output)."""
 
     def __init__(self, lib: ProductLib, recs_c: ReadRecordsC, first: int, count: int, contig_names, pinned: bool = False, windows=None):
-        """`windows`: None = no indel windows; True = for every contig; or a uint8 mask per contig (GpuContext.reverse_mask())."""
+        """`windows`: None = no indel windows; True = for every read segment; or a ContigSegments (Context.get_contig_segments()):
+        only for read segments that pair with a reverse-strand contig segment (the ones that go through left_shift_indels)."""
         self.lib = lib
         self.h = C.c_void_p()
         names = (C.c_char_p * len(contig_names))(*[n.encode() for n in contig_names])
         if windows is None:
             rc = lib.dll.ptl_pack_batch(C.byref(recs_c), first, count, len(contig_names), names, int(pinned), C.byref(self.h))
+        elif windows is True:
+            rc = lib.dll.ptl_pack_batch_ex(C.byref(recs_c), first, count, len(contig_names), names, int(pinned), 1, None, C.byref(self.h))
         else:
-            mask = np.ones(len(contig_names), np.uint8) if windows is True else np.ascontiguousarray(windows, dtype=np.uint8)
-            assert len(mask) == len(contig_names)
-            rc = lib.dll.ptl_pack_batch_ex(C.byref(recs_c), first, count, len(contig_names), names, int(pinned), mask.ctypes.data_as(u8p), C.byref(self.h))
+            segs_c = windows.to_c()
+            rc = lib.dll.ptl_pack_batch_ex(C.byref(recs_c), first, count, len(contig_names), names, int(pinned), 2, C.byref(segs_c), C.byref(self.h))
         if rc != 0:
             raise PtlError(rc, lib.dll.ptl_pack_last_error().decode())
         self.c = BatchC()
@@ -255,13 +255,6 @@ class GpuContext(Context):
 
     def launch_count(self) -> int:
         return int(self.lib.dll.ptl_launch_count(self.h))
-
-    def reverse_mask(self) -> np.ndarray:
-        """uint8 per contig: 1 if the contig owns a reverse-strand contig->ref segment (its reads go through left_shift_indels)."""
-        n = len(self.get_contig_segments().contig_len)
-        m = np.zeros(max(n, 1), np.uint8)
-        self._check(self.lib.dll.ptl_contig_reverse_mask(self.h, n, m.ctypes.data_as(u8p)))
-        return m[:n]
 
     def set_seq_zero_copy(self, on: bool):
         self._check(self.lib.dll.ptl_set_seq_zero_copy(self.h, int(on)))

@@ -177,6 +177,10 @@ def test_emulated_indel_windows_change_nothing(emul, name, kw):
     c0 = np.zeros(6, np.uint64)
     assert emul.dll.ptl_emul_slot_counters(ectx.h, 0, c0.ctypes.data_as(abi.u64p)) == 0
     assert np.array_equal(cw, c0) and int(cw[4]) > 0
+    # PTL_WIN_REVERSE_PAIRS: only the read segments that pair with a reverse-strand contig segment carry windows
+    px = helpers.pack(s, windows=ectx.get_contig_segments())
+    assert 0 < px.c.n_indel_win <= pw.c.n_indel_win
+    assert helpers.lift_c(ectx, px.c).diff(ro) is None
 
 
 def test_emulated_windows_are_used_not_the_bases(emul):

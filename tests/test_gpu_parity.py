@@ -196,17 +196,15 @@ def test_indel_windows_give_identical_results():
     free = C.cast(L.dll.ptl_host_free, C.c_void_p)
     s = synth.make("tiny", host_alloc=alloc, host_free=free, seed=59, n_reads=6000, rev_contig_frac=0.7, read_cluster_frac=0.2)
     gctx = helpers.gpu_context(s)
-    mask = gctx.reverse_mask()
-    assert mask.any() and len(mask) == len(s.contig_names)
     plain = helpers.pack(s, pinned=True)
-    win = helpers.pack(s, pinned=True, windows=mask)
-    assert 0 < win.c.n_indel_win
+    win = helpers.pack(s, pinned=True, windows=gctx.get_contig_segments())
+    assert 0 < win.c.n_indel_win < helpers.pack(s, windows=True).c.n_indel_win
     ro = helpers.lift_c(helpers.oracle_context(s), plain.c)
     for zero_copy in (False, True):
         gctx.set_seq_zero_copy(zero_copy)
         assert helpers.lift_c(gctx, win.c).diff(ro) is None
         assert helpers.lift_c(gctx, plain.c).diff(ro) is None
-    # windows for every contig (mask = all ones) and a stress-shaped workload with long walks (> 16 bases fall back to seq4)
+    # windows for every read segment and a stress-shaped workload with long walks (> 16 bases fall back to seq4)
     s2 = synth.make("stress", host_alloc=alloc, host_free=free, n_reads=800)
     g2 = helpers.gpu_context(s2)
     w2 = helpers.pack(s2, pinned=True, windows=True)

@@ -10,7 +10,7 @@ s = synth.make("chr20", host_alloc=alloc, host_free=free, n_reads=n)
 ctx = lib.GpuContext(0, 3)
 ctx.set_reference(helpers.reference_arrays(s)); ctx.set_contig_records(s.contig_records)
 pb0 = lib.PackedBatch(L, s.read_records, 0, n, s.contig_names, pinned=True)
-pbw = lib.PackedBatch(L, s.read_records, 0, n, s.contig_names, pinned=True, windows=ctx.reverse_mask())
+pbw = lib.PackedBatch(L, s.read_records, 0, n, s.contig_names, pinned=True, windows=ctx.get_contig_segments())
 print(f"reads {n}  rsegs {pb0.c.n_read_segments}  cigar ops {pb0.c.n_cigar}  indel windows {pbw.c.n_indel_win}")
 def sync(): torch.cuda.synchronize()
 for zc, pb in ((False, pb0), (True, pb0), (True, pbw)):
