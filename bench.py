@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--workload", default="chr20")
     ap.add_argument("--reads", type=int, default=0, help="override reads per GPU (default: the workload's own)")
     ap.add_argument("--chunk", type=int, default=131072, help="reads per submitted batch in the e2e pipeline")
+    ap.add_argument("--slots", type=int, default=3, help="batch slots (CUDA streams) of the e2e pipeline")
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--zero-copy", default="auto", choices=["auto", "on", "off"])
@@ -216,7 +217,7 @@ def main():
     t_gen = time.time() - t0
     n_reads = s.read_records.n_reads
 
-    ctx = lib.GpuContext(local_rank, n_slots=3)
+    ctx = lib.GpuContext(local_rank, n_slots=max(args.slots, 2))
     ctx.set_reference(s.reference_arrays())
     ctx.set_contig_records(s.contig_records)
     segs = ctx.get_contig_segments()
@@ -291,7 +292,7 @@ def main():
 
     # ---------------------------------------------------------------- e2e: host buffers -> records on the host
     def e2e_step(chunks):
-        n_slots = 3
+        n_slots = max(args.slots, 2)
         inflight = [None] * n_slots
         recs = 0
         for i, ch in enumerate(chunks):
@@ -412,7 +413,7 @@ def main():
                                    f"{n_reads} reads per GPU)",
                        "reads_per_gpu": int(n_reads), "pairs_per_step_per_gpu": int(cnt["n_pairs"]), "lifted_per_step_per_gpu": int(cnt["n_lifted"]),
                        "l2_policy": "inputs larger than L2 (CIGAR pools + op scratch > 126 MB per step)", "sharding": "by contig set, no collective",
-                       "e2e_pipeline": f"{len(chunks)} batches of {args.chunk} reads over 3 slots", "e2e_base_transfer": best_mode,
+                       "e2e_pipeline": f"{len(chunks)} batches of {args.chunk} reads over {max(args.slots, 2)} slots", "e2e_base_transfer": best_mode,
                        "parity": parity, "full_batch_digest": f"{list(digests.values())[0]:016x} (identical across {len(digests)} base-transfer modes)",
                        "generate_s": round(t_gen, 1)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes(best_mode)), "d2h_bytes_per_step": int(d2h),

@@ -85,15 +85,16 @@ struct Slot {
     // work
     DBuf w_rseg_read, w_rseg_pair_begin, w_rseg_ref_len, w_rseg_n_id, w_rseg_read_len, w_pair_cap_b, w_pair_rseg, w_pair_seg, w_pair_slot_begin, w_pair_status, w_pair_flip,
         w_pair_pos, w_pair_n_out, w_pair_bin, w_pair_out_off, w_simplify_list, w_scratch, w_read_counts, w_read_primary, w_scan_tmp, w_totals;
-    // results (device)
-    DBuf r_read_rec_begin, r_status, r_rseg, r_cseg, r_tid, r_pos, r_mapq, r_flag, r_bin, r_flip, r_cigar_begin, r_cigar;
-    // results (pinned host)
-    HBuf h_read_rec_begin, h_status, h_rseg, h_cseg, h_tid, h_pos, h_mapq, h_flag, h_bin, h_flip, h_cigar_begin, h_cigar, h_totals;
+    // results: one compact arena on the device (device_types.hpp: result_layout) and its pinned host twin
+    DBuf r_arena;
+    HBuf h_arena;
+    uint64_t arena_cap = 0;     // bytes usable by the kernels (<= both buffers)
+    uint64_t copied_bytes = 0;  // prefix of the arena already enqueued for D2H behind the kernels
+    double est_rec_per_read = 0, est_out_per_in = 0;  // shape of the previous batch on this slot (sizes the speculative copy)
     DevBatch B;
     DevWork W;
-    DevResult R;
     uint32_t stage_mask = PTL_STAGE_ALL;
-    bool uploaded = false, ran = false;
+    bool uploaded = false, ran = false, with_results = true;
     uint64_t n_cigar_in = 0;
     ptl_result res{};
     DevTotals totals{};
@@ -287,7 +288,7 @@ void upload_batch(ptl_ctx* ctx, Slot& sl, const ptl_batch* b) {
     sl.ran = false;
 }
 
-void size_work(Slot& sl, uint32_t want_pairs, uint64_t want_scratch, uint32_t want_recs, uint64_t want_cigar) {
+void size_work(Slot& sl, uint32_t want_pairs, uint64_t want_scratch, uint64_t want_arena) {
     cudaStream_t st = sl.stream;
     const uint32_t n = sl.B.n_reads, ns = sl.B.n_rsegs;
     DevWork& W = sl.W;
@@ -339,46 +340,34 @@ void size_work(Slot& sl, uint32_t want_pairs, uint64_t want_scratch, uint32_t wa
         sl.w_totals.ensure(sizeof(DevTotals), st);
         CK(cudaMemsetAsync(sl.w_totals.p, 0, sl.w_totals.cap, st));  // padding bytes too (they travel in the D2H of the totals)
     }
-    DevResult& R = sl.R;
-    const uint32_t rc = std::max(R.rec_cap, want_recs);
-    const uint64_t cc = std::max(R.cigar_cap, want_cigar);
-    sl.r_read_rec_begin.ensure((size_t(n) + 1) * 4, st);
-    sl.r_status.ensure(size_t(rc), st);
-    sl.r_rseg.ensure(size_t(rc) * 4, st);
-    sl.r_cseg.ensure(size_t(rc) * 4, st);
-    sl.r_tid.ensure(size_t(rc) * 4, st);
-    sl.r_pos.ensure(size_t(rc) * 8, st);
-    sl.r_mapq.ensure(size_t(rc), st);
-    sl.r_flag.ensure(size_t(rc) * 2, st);
-    sl.r_bin.ensure(size_t(rc) * 2, st);
-    sl.r_flip.ensure(size_t(rc), st);
-    sl.r_cigar_begin.ensure((size_t(rc) + 1) * 8, st);
-    sl.r_cigar.ensure(size_t(cc) * 4 + 4, st);
-    R.rec_cap = rc;
-    R.cigar_cap = cc;
-    R.read_rec_begin = sl.r_read_rec_begin.as<uint32_t>();
-    R.rec_status = sl.r_status.as<int8_t>();
-    R.rec_read_segment = sl.r_rseg.as<uint32_t>();
-    R.rec_contig_segment = sl.r_cseg.as<uint32_t>();
-    R.rec_tid = sl.r_tid.as<int32_t>();
-    R.rec_pos = sl.r_pos.as<int64_t>();
-    R.rec_mapq = sl.r_mapq.as<uint8_t>();
-    R.rec_flag = sl.r_flag.as<uint16_t>();
-    R.rec_bin = sl.r_bin.as<uint16_t>();
-    R.rec_need_flip = sl.r_flip.as<uint8_t>();
-    R.rec_cigar_begin = sl.r_cigar_begin.as<uint64_t>();
-    R.cigar = sl.r_cigar.as<uint32_t>();
+    const uint64_t ac = std::max<uint64_t>({sl.arena_cap, want_arena, kResultHeaderBytes});
+    sl.r_arena.ensure(ac, st);
+    sl.h_arena.ensure(ac);
+    sl.arena_cap = ac;
 }
 
-void enqueue_run(ptl_ctx* ctx, Slot& sl) {
-    launch_lift(ctx->S, sl.B, sl.W, sl.R, sl.w_totals.as<DevTotals>(), sl.stage_mask, sl.w_scan_tmp.p, sl.w_scan_tmp.cap, sl.stream,
-                &ctx->launches, sl.have_events ? &sl.ev : nullptr);
-    sl.h_totals.ensure(sizeof(DevTotals));
-    CK(cudaMemcpyAsync(sl.h_totals.p, sl.w_totals.p, sizeof(DevTotals), cudaMemcpyDeviceToHost, sl.stream));
+// Bytes of the arena a batch of this shape is expected to fill (from the previous batch on the slot), or the whole
+// capacity when nothing is known yet.
+uint64_t predicted_result_bytes(const Slot& sl) {
+    if (sl.est_rec_per_read <= 0) return sl.arena_cap;
+    const uint64_t n = sl.B.n_reads;
+    const uint64_t nr = uint64_t(double(n) * sl.est_rec_per_read * 1.02) + 256, nc = uint64_t(double(sl.n_cigar_in) * sl.est_out_per_in * 1.02) + 4096;
+    return std::min<uint64_t>(sl.arena_cap, result_layout(n, nr, nc).total);
+}
+
+// Kernels + the D2H copy of the results behind them on the slot's stream.  `with_results`: copy the predicted extent of
+// the arena right away (ptl_lift_submit: one DMA, no host round trip in between); otherwise only the 128-byte header
+// (ptl_lift_run: the device-resident path).
+void enqueue_run(ptl_ctx* ctx, Slot& sl, bool with_results) {
+    launch_lift(ctx->S, sl.B, sl.W, sl.r_arena.as<char>(), sl.arena_cap, sl.w_totals.as<DevTotals>(), sl.stage_mask, sl.w_scan_tmp.p,
+                sl.w_scan_tmp.cap, sl.stream, &ctx->launches, sl.have_events ? &sl.ev : nullptr);
+    sl.copied_bytes = with_results ? predicted_result_bytes(sl) : kResultHeaderBytes;
+    CK(cudaMemcpyAsync(sl.h_arena.p, sl.r_arena.p, sl.copied_bytes, cudaMemcpyDeviceToHost, sl.stream));
+    sl.with_results = with_results;
     sl.ran = true;
 }
 
-void run_batch(ptl_ctx* ctx, Slot& sl, uint32_t stage_mask) {
+void run_batch(ptl_ctx* ctx, Slot& sl, uint32_t stage_mask, bool with_results) {
     if (!ctx->have_segments) throw std::runtime_error("ptl_set_contig_segments / ptl_set_contig_records has not been called");
     if ((stage_mask & PTL_STAGE_SIMPLIFY) && !ctx->have_reference) throw std::runtime_error("ptl_set_reference has not been called");
     sl.stage_mask = stage_mask;
@@ -387,10 +376,10 @@ void run_batch(ptl_ctx* ctx, Slot& sl, uint32_t stage_mask) {
     const uint32_t ns = sl.B.n_rsegs, n = sl.B.n_reads;
     const uint32_t want_pairs = ns + ns / 8 + 1024;
     const uint64_t want_scratch = 8ull * sl.n_cigar_in + 64ull * want_pairs;
-    const uint32_t want_recs = want_pairs + n;
+    const uint64_t want_recs = uint64_t(want_pairs) + n;
     const uint64_t want_cigar = sl.n_cigar_in + sl.n_cigar_in / 2 + 16ull * n + 1024;
-    size_work(sl, want_pairs, want_scratch, want_recs, want_cigar);
-    enqueue_run(ctx, sl);
+    size_work(sl, want_pairs, want_scratch, result_layout(n, want_recs, want_cigar).total);
+    enqueue_run(ctx, sl, with_results);
 }
 
 // Wait for the kernels, re-run on capacity overflow, leave totals in sl.totals.
@@ -398,64 +387,67 @@ void finish_batch(ptl_ctx* ctx, Slot& sl) {
     for (int attempt = 0; attempt < 6; ++attempt) {
         CK(cudaStreamSynchronize(sl.stream));
         CK(cudaGetLastError());
-        std::memcpy(&sl.totals, sl.h_totals.p, sizeof(DevTotals));
+        std::memcpy(&sl.totals, sl.h_arena.p, sizeof(DevTotals));
         const DevTotals& t = sl.totals;
-        if (!t.overflow) return;
+        if (!t.overflow) {
+            if (sl.B.n_reads) {
+                sl.est_rec_per_read = double(t.n_records) / double(sl.B.n_reads);
+                sl.est_out_per_in = double(t.n_cigar_out) / double(std::max<uint64_t>(sl.n_cigar_in, 1));
+            }
+            return;
+        }
         const uint32_t want_pairs = uint32_t(std::max<uint64_t>(t.n_pairs, sl.W.pair_cap));
-        uint64_t want_scratch = sl.W.scratch_cap, want_cigar = sl.R.cigar_cap;
-        uint32_t want_recs = sl.R.rec_cap;
+        uint64_t want_scratch = sl.W.scratch_cap, want_arena = sl.arena_cap;
         if (!(t.overflow & OVF_PAIRS)) {
             want_scratch = std::max<uint64_t>(want_scratch, t.scratch_needed);
-            if (!(t.overflow & OVF_SCRATCH)) {
-                want_recs = uint32_t(std::max<uint64_t>(want_recs, t.n_records));
-                want_cigar = std::max<uint64_t>(want_cigar, t.n_cigar_out);
-            }
+            if (!(t.overflow & OVF_SCRATCH)) want_arena = std::max<uint64_t>(want_arena, result_layout(sl.B.n_reads, t.n_records, t.n_cigar_out).total);
         }
-        want_recs = std::max<uint32_t>(want_recs, want_pairs + sl.B.n_reads);
-        size_work(sl, want_pairs, want_scratch, want_recs, want_cigar);
-        enqueue_run(ctx, sl);
+        want_arena = std::max<uint64_t>(want_arena, result_layout(sl.B.n_reads, uint64_t(want_pairs) + sl.B.n_reads, 0).total);
+        size_work(sl, want_pairs, want_scratch, want_arena);
+        enqueue_run(ctx, sl, sl.with_results);
     }
     throw std::runtime_error("work buffers still overflow after resizing (internal error)");
-}
-
-template <class T>
-const T* fetch(HBuf& h, const DBuf& d, size_t n, cudaStream_t st) {
-    h.ensure(std::max<size_t>(n, 1) * sizeof(T));
-    if (n) CK(cudaMemcpyAsync(h.p, d.p, n * sizeof(T), cudaMemcpyDeviceToHost, st));
-    return h.as<T>();
 }
 
 int download(ptl_ctx* ctx, Slot& sl, ptl_result* out) {
     finish_batch(ctx, sl);
     const DevTotals& t = sl.totals;
-    cudaStream_t st = sl.stream;
-    const size_t n = sl.B.n_reads, nr = size_t(t.n_records), nc = size_t(t.n_cigar_out);
+    const size_t n = sl.B.n_reads;
+    const ResultLayout L = result_layout(n, t.n_records, t.n_cigar_out);
+    if (n && L.total > sl.copied_bytes) {  // the speculative copy was short (first batch of a new shape, or ptl_lift_run): fetch the rest
+        CK(cudaMemcpyAsync(sl.h_arena.as<char>() + sl.copied_bytes, sl.r_arena.as<char>() + sl.copied_bytes, L.total - sl.copied_bytes,
+                           cudaMemcpyDeviceToHost, sl.stream));
+        CK(cudaStreamSynchronize(sl.stream));
+        sl.copied_bytes = L.total;
+    }
     ptl_result& r = sl.res;
     r = ptl_result{};
     r.n_reads = uint32_t(n);
-    r.n_records = uint32_t(nr);
-    r.n_cigar = nc;
+    r.n_records = uint32_t(t.n_records);
+    r.n_cigar = t.n_cigar_out;
     if (n) {
-        r.read_rec_begin = fetch<uint32_t>(sl.h_read_rec_begin, sl.r_read_rec_begin, n + 1, st);
-        r.rec_status = fetch<int8_t>(sl.h_status, sl.r_status, nr, st);
-        r.rec_read_segment = fetch<uint32_t>(sl.h_rseg, sl.r_rseg, nr, st);
-        r.rec_contig_segment = fetch<uint32_t>(sl.h_cseg, sl.r_cseg, nr, st);
-        r.rec_tid = fetch<int32_t>(sl.h_tid, sl.r_tid, nr, st);
-        r.rec_pos = fetch<int64_t>(sl.h_pos, sl.r_pos, nr, st);
-        r.rec_mapq = fetch<uint8_t>(sl.h_mapq, sl.r_mapq, nr, st);
-        r.rec_flag = fetch<uint16_t>(sl.h_flag, sl.r_flag, nr, st);
-        r.rec_bin = fetch<uint16_t>(sl.h_bin, sl.r_bin, nr, st);
-        r.rec_need_flip = fetch<uint8_t>(sl.h_flip, sl.r_flip, nr, st);
-        r.rec_cigar_begin = fetch<uint64_t>(sl.h_cigar_begin, sl.r_cigar_begin, nr + 1, st);
-        r.cigar = fetch<uint32_t>(sl.h_cigar, sl.r_cigar, nc, st);
-        CK(cudaStreamSynchronize(st));
+        const DevResult R = DevResult::view(sl.h_arena.as<char>(), L);
+        r.read_rec_begin = R.read_rec_begin;
+        r.rec_status = R.rec_status;
+        r.rec_read_segment = R.rec_read_segment;
+        r.rec_contig_segment = R.rec_contig_segment;
+        r.rec_tid = R.rec_tid;
+        r.rec_pos = R.rec_pos;
+        r.rec_mapq = R.rec_mapq;
+        r.rec_flag = R.rec_flag;
+        r.rec_bin = R.rec_bin;
+        r.rec_need_flip = R.rec_need_flip;
+        r.rec_cigar_begin = R.rec_cigar_begin;
+        r.cigar = R.cigar;
     } else {
-        sl.h_read_rec_begin.ensure(4);
-        sl.h_cigar_begin.ensure(8);
-        sl.h_read_rec_begin.as<uint32_t>()[0] = 0;
-        sl.h_cigar_begin.as<uint64_t>()[0] = 0;
-        r.read_rec_begin = sl.h_read_rec_begin.as<uint32_t>();
-        r.rec_cigar_begin = sl.h_cigar_begin.as<uint64_t>();
+        // an empty batch: the kernels only wrote the header; lend out the two one-element CSR arrays from behind it
+        const ResultLayout L0 = result_layout(0, 0, 0);
+        sl.h_arena.ensure(L0.total);
+        const DevResult R = DevResult::view(sl.h_arena.as<char>(), L0);
+        R.read_rec_begin[0] = 0;
+        R.rec_cigar_begin[0] = 0;
+        r.read_rec_begin = R.read_rec_begin;
+        r.rec_cigar_begin = R.rec_cigar_begin;
     }
     r.n_pairs = t.n_pairs;
     r.n_lifted = t.n_lifted;
@@ -528,13 +520,9 @@ void ptl_destroy(ptl_ctx* ctx) {
                         &sl.d_rseg_contig, &sl.d_rseg_pos, &sl.d_rseg_is_fwd, &sl.d_rseg_cigar_begin, &sl.d_rseg_cigar_len, &sl.d_cigar,
                         &sl.d_seq4, &sl.d_arena, &sl.d_win_begin, &sl.d_win, &sl.w_rseg_read, &sl.w_rseg_pair_begin, &sl.w_rseg_ref_len, &sl.w_rseg_n_id, &sl.w_rseg_read_len, &sl.w_pair_cap_b, &sl.w_pair_rseg, &sl.w_pair_seg,
                         &sl.w_pair_slot_begin, &sl.w_pair_status, &sl.w_pair_flip, &sl.w_pair_pos, &sl.w_pair_n_out, &sl.w_pair_bin, &sl.w_pair_out_off, &sl.w_simplify_list,
-                        &sl.w_scratch, &sl.w_read_counts, &sl.w_read_primary, &sl.w_scan_tmp, &sl.w_totals, &sl.r_read_rec_begin,
-                        &sl.r_status, &sl.r_rseg, &sl.r_cseg, &sl.r_tid, &sl.r_pos, &sl.r_mapq, &sl.r_flag, &sl.r_bin, &sl.r_flip,
-                        &sl.r_cigar_begin, &sl.r_cigar})
+                        &sl.w_scratch, &sl.w_read_counts, &sl.w_read_primary, &sl.w_scan_tmp, &sl.w_totals, &sl.r_arena})
             b->release();
-        for (HBuf* b : {&sl.h_read_rec_begin, &sl.h_status, &sl.h_rseg, &sl.h_cseg, &sl.h_tid, &sl.h_pos, &sl.h_mapq, &sl.h_flag,
-                        &sl.h_bin, &sl.h_flip, &sl.h_cigar_begin, &sl.h_cigar, &sl.h_totals})
-            b->release();
+        sl.h_arena.release();
         if (sl.have_events)
             for (auto& e : sl.ev.e) cudaEventDestroy(e);
         if (sl.stream) cudaStreamDestroy(sl.stream);
@@ -631,7 +619,7 @@ int ptl_lift_run(ptl_ctx* ctx, int slot, uint32_t stage_mask) {
     if (!sl) return PTL_ERR_INVALID_ARG;
     if (!sl->uploaded) return fail(ctx, PTL_ERR_STATE, "ptl_lift_run without ptl_lift_upload");
     return guarded(ctx, [&]() {
-        run_batch(ctx, *sl, stage_mask);
+        run_batch(ctx, *sl, stage_mask, /*with_results=*/false);
         return PTL_OK;
     });
 }
@@ -647,7 +635,7 @@ int ptl_lift_submit_ex(ptl_ctx* ctx, int slot, const ptl_batch* batch, uint32_t 
     return guarded(ctx, [&]() {
         if (!ctx->have_segments) throw std::runtime_error("ptl_set_contig_segments / ptl_set_contig_records has not been called");
         upload_batch(ctx, *sl, batch);
-        run_batch(ctx, *sl, stage_mask);
+        run_batch(ctx, *sl, stage_mask, /*with_results=*/true);
         return PTL_OK;
     });
 }

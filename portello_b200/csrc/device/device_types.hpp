@@ -3,6 +3,12 @@
 #pragma once
 #include <cstdint>
 
+#ifdef __CUDACC__
+#define PTL_HD __host__ __device__
+#else
+#define PTL_HD
+#endif
+
 namespace ptl {
 
 // One entry of a flat ReadToRefTreeMap (lib/rust-vc-utils/src/bam_utils/read_to_ref_map.rs:59-137), 16 bytes so that a
@@ -99,10 +105,37 @@ struct DevWork {
     uint32_t* read_primary = nullptr;    // pair index chosen as primary, ~0 if none lifted
 };
 
-// ---- result pools on the device (mirrors ptl_result) ------------------------------------------------------------
+// ---- results of one batch: ONE compact arena (device), copied to the host with a single DMA ------------------------
+// [header: DevTotals, 128 B][read_rec_begin][rec_cigar_begin][rec_pos][rec_read_segment][rec_contig_segment][rec_tid]
+// [rec_flag][rec_bin][rec_status][rec_mapq][rec_need_flip][cigar], every array sized EXACTLY by the batch's own record and
+// op counts (known on the device after the scan of the per-read counts) and 16-byte aligned.  The host derives the same
+// layout from the header, so no per-array copies and no size round trip before the copy are needed.
+struct ResultLayout {
+    uint64_t read_rec_begin, rec_cigar_begin, rec_pos, rec_rseg, rec_cseg, rec_tid, rec_flag, rec_bin, rec_status, rec_mapq, rec_flip, cigar, total;
+};
+constexpr uint64_t kResultHeaderBytes = 128;
+PTL_HD inline ResultLayout result_layout(uint64_t n_reads, uint64_t n_rec, uint64_t n_cigar) {
+    ResultLayout L;
+    uint64_t off = kResultHeaderBytes;
+    auto take = [&](uint64_t bytes) { const uint64_t o = off; off = (off + bytes + 15ull) & ~15ull; return o; };
+    L.read_rec_begin = take((n_reads + 1) * 4);
+    L.rec_cigar_begin = take((n_rec + 1) * 8);
+    L.rec_pos = take(n_rec * 8);
+    L.rec_rseg = take(n_rec * 4);
+    L.rec_cseg = take(n_rec * 4);
+    L.rec_tid = take(n_rec * 4);
+    L.rec_flag = take(n_rec * 2);
+    L.rec_bin = take(n_rec * 2);
+    L.rec_status = take(n_rec);
+    L.rec_mapq = take(n_rec);
+    L.rec_flip = take(n_rec);
+    L.cigar = take(n_cigar * 4);
+    L.total = off;
+    return L;
+}
+
+// typed view of an arena (mirrors ptl_result)
 struct DevResult {
-    uint32_t rec_cap = 0;
-    uint64_t cigar_cap = 0;
     uint32_t* read_rec_begin = nullptr;  // [n_reads+1]
     int8_t* rec_status = nullptr;
     uint32_t* rec_read_segment = nullptr;
@@ -113,8 +146,24 @@ struct DevResult {
     uint16_t* rec_flag = nullptr;
     uint16_t* rec_bin = nullptr;
     uint8_t* rec_need_flip = nullptr;
-    uint64_t* rec_cigar_begin = nullptr; // [rec_cap+1]
+    uint64_t* rec_cigar_begin = nullptr; // [n_rec+1]
     uint32_t* cigar = nullptr;
+    PTL_HD static DevResult view(char* base, const ResultLayout& L) {
+        DevResult R;
+        R.read_rec_begin = reinterpret_cast<uint32_t*>(base + L.read_rec_begin);
+        R.rec_cigar_begin = reinterpret_cast<uint64_t*>(base + L.rec_cigar_begin);
+        R.rec_pos = reinterpret_cast<int64_t*>(base + L.rec_pos);
+        R.rec_read_segment = reinterpret_cast<uint32_t*>(base + L.rec_rseg);
+        R.rec_contig_segment = reinterpret_cast<uint32_t*>(base + L.rec_cseg);
+        R.rec_tid = reinterpret_cast<int32_t*>(base + L.rec_tid);
+        R.rec_flag = reinterpret_cast<uint16_t*>(base + L.rec_flag);
+        R.rec_bin = reinterpret_cast<uint16_t*>(base + L.rec_bin);
+        R.rec_status = reinterpret_cast<int8_t*>(base + L.rec_status);
+        R.rec_mapq = reinterpret_cast<uint8_t*>(base + L.rec_mapq);
+        R.rec_need_flip = reinterpret_cast<uint8_t*>(base + L.rec_flip);
+        R.cigar = reinterpret_cast<uint32_t*>(base + L.cigar);
+        return R;
+    }
 };
 
 // ---- totals / flags written by the kernels, read back once per batch ---------------------------------------------
@@ -127,12 +176,13 @@ struct DevTotals {
     unsigned long long n_errors;
     long long first_error_read;          // min read index with an error, or INT64_MAX
     int first_error_status;
-    unsigned int overflow;               // bit0 pairs, bit1 scratch, bit2 records, bit3 cigar pool
+    unsigned int overflow;               // bit0 pairs, bit1 scratch, bit2 result arena
     unsigned long long n_in_ops;         // sum of input CIGAR ops over attempted pairs   (roofline arithmetic)
     unsigned long long n_base_bytes;     // base bytes compared (both operands)            (roofline arithmetic)
     unsigned int n_simplify;             // length of DevWork::simplify_list
 };
 
-enum : unsigned { OVF_PAIRS = 1, OVF_SCRATCH = 2, OVF_RECORDS = 4, OVF_CIGAR = 8 };
+enum : unsigned { OVF_PAIRS = 1, OVF_SCRATCH = 2, OVF_RESULT = 4 };
+static_assert(sizeof(DevTotals) <= kResultHeaderBytes, "the totals are the header of the result arena");
 
 }  // namespace ptl

@@ -254,20 +254,25 @@ __global__ void __launch_bounds__(128) read_finalize_kernel(DevStatic S, DevBatc
 // records (adjacent lanes -> adjacent records -> coalesced), then the warp copies the CIGAR ops of each record from
 // its scratch slot into the dense pool cooperatively (coalesced both ways) and reduces the reference span for
 // end / bin (:278-279).
-__global__ void __launch_bounds__(256) emit_records_kernel(DevStatic S, DevBatch B, DevWork W, DevResult R, DevTotals* T,
+// The arrays live in ONE compact arena laid out from the batch's own totals (device_types.hpp: result_layout); thread 0
+// also publishes the totals as the arena header, so one D2H copy brings everything the host needs.
+__global__ void __launch_bounds__(256) emit_records_kernel(DevStatic S, DevBatch B, DevWork W, char* arena, uint64_t arena_cap, DevTotals* T,
                                                             uint32_t stage_mask) {
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t r = warp * 32u + lane;
     if (warp * 32u >= B.n_reads) return;
     const uint2 total = W.read_counts[B.n_reads];
+    const ResultLayout L = result_layout(B.n_reads, total.x, total.y);
+    const bool fits = L.total <= arena_cap;
     if (r == 0) {
         T->n_records = total.x;
         T->n_cigar_out = total.y;
-        if (total.x > R.rec_cap) atomicOr(&T->overflow, OVF_RECORDS);
-        if (total.y > R.cigar_cap) atomicOr(&T->overflow, OVF_CIGAR);
+        if (!fits) T->overflow |= OVF_RESULT;  // every other writer of the totals finished in earlier kernels
+        *reinterpret_cast<DevTotals*>(arena) = *T;
     }
-    if (total.x > R.rec_cap || total.y > R.cigar_cap) return;
+    if (!fits) return;
+    const DevResult R = DevResult::view(arena, L);
     const bool live = r < B.n_reads;
     uint32_t k = 0, p = 0, p1 = 0, primary = 0xffffffffu;
     uint64_t op_at = 0;
@@ -348,17 +353,17 @@ __global__ void __launch_bounds__(256) emit_records_kernel(DevStatic S, DevBatch
     }
 }
 
-__global__ void totals_init_kernel(DevTotals* T) { totals_reset(T); }
+__global__ void totals_init_kernel(DevTotals* T, DevTotals* header) { totals_reset(T); *header = *T; }
 
 }  // namespace
 
-void launch_lift(const DevStatic& S, const DevBatch& B, const DevWork& W, const DevResult& R, DevTotals* T, uint32_t stage_mask,
+void launch_lift(const DevStatic& S, const DevBatch& B, const DevWork& W, char* arena, uint64_t arena_cap, DevTotals* T, uint32_t stage_mask,
                  void* scan_tmp, size_t scan_tmp_bytes_, cudaStream_t st, uint64_t* launches, StageEvents* ev) {
     auto mark = [&](int i) { if (ev) cudaEventRecord(ev->e[i], st); };
     const int do_finish = (stage_mask == 7u);
     mark(0);
     if (B.n_reads == 0) {
-        totals_init_kernel<<<1, 1, 0, st>>>(T);
+        totals_init_kernel<<<1, 1, 0, st>>>(T, reinterpret_cast<DevTotals*>(arena));
         ++*launches;
         for (int i = 1; i < StageEvents::N; ++i) mark(i);
         return;
@@ -383,7 +388,7 @@ void launch_lift(const DevStatic& S, const DevBatch& B, const DevWork& W, const 
     read_finalize_kernel<<<(B.n_reads + 1 + 127) / 128, 128, 0, st>>>(S, B, W, T, do_finish);
     ++*launches;
     exclusive_scan_inplace<uint2>(W.read_counts, uint64_t(B.n_reads) + 1, scan_tmp, scan_tmp_bytes_, st, launches, nullptr);
-    emit_records_kernel<<<(B.n_reads + 255) / 256, 256, 0, st>>>(S, B, W, R, T, stage_mask);
+    emit_records_kernel<<<(B.n_reads + 255) / 256, 256, 0, st>>>(S, B, W, arena, arena_cap, T, stage_mask);
     ++*launches;
     mark(3);
 }

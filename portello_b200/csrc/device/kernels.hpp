@@ -23,7 +23,8 @@ size_t scan_tmp_bytes(uint64_t n);
 // counts != nullptr, out == nullptr : count table entries per segment; then (after a scan into S.seg_tab_begin) fill `out`.
 void launch_table_build(const DevStatic& S, uint32_t* counts, TabEntry* out, cudaStream_t st);
 
-void launch_lift(const DevStatic& S, const DevBatch& B, const DevWork& W, const DevResult& R, DevTotals* T, uint32_t stage_mask,
+// `arena`: the compact result arena (device_types.hpp: result_layout) of `arena_cap` bytes, header = the batch totals.
+void launch_lift(const DevStatic& S, const DevBatch& B, const DevWork& W, char* arena, uint64_t arena_cap, DevTotals* T, uint32_t stage_mask,
                  void* scan_tmp, size_t scan_tmp_bytes, cudaStream_t st, uint64_t* launches, StageEvents* ev);
 
 }  // namespace ptl

@@ -32,14 +32,8 @@ struct EmulSlot {
     std::vector<uint64_t> read_seq_off, rseg_cigar_begin, indel_win;
     std::vector<uint32_t> rseg_win_begin;
     std::vector<int64_t> rseg_pos;
-    // results
-    std::vector<uint32_t> read_rec_begin, rec_rseg, rec_cseg, out_cigar;
-    std::vector<int8_t> rec_status;
-    std::vector<int32_t> rec_tid;
-    std::vector<int64_t> rec_pos;
-    std::vector<uint8_t> rec_mapq, rec_flip;
-    std::vector<uint16_t> rec_flag, rec_bin;
-    std::vector<uint64_t> rec_cigar_begin;
+    // results: the compact arena of the product (device_types.hpp: result_layout)
+    std::vector<char> arena;
     ptl_result res{};
     DevTotals totals{};
     bool ran = false;
@@ -216,16 +210,9 @@ int run_batch(ptl_ctx* ctx, EmulSlot& sl, const ptl_batch* b, uint32_t stage_mas
     const uint64_t nc = read_counts[n].y;
     T.n_records = nr;
     T.n_cigar_out = nc;
-    sl.read_rec_begin.assign(size_t(n) + 1, 0);
-    sl.rec_status.assign(nr + 1, 0); sl.rec_rseg.assign(nr + 1, 0); sl.rec_cseg.assign(nr + 1, 0); sl.rec_tid.assign(nr + 1, 0);
-    sl.rec_pos.assign(nr + 1, 0); sl.rec_mapq.assign(nr + 1, 0); sl.rec_flag.assign(nr + 1, 0); sl.rec_bin.assign(nr + 1, 0);
-    sl.rec_flip.assign(nr + 1, 0); sl.rec_cigar_begin.assign(size_t(nr) + 1, 0); sl.out_cigar.assign(nc + 1, 0);
-    DevResult R;
-    R.rec_cap = nr; R.cigar_cap = nc;
-    R.read_rec_begin = sl.read_rec_begin.data(); R.rec_status = sl.rec_status.data(); R.rec_read_segment = sl.rec_rseg.data();
-    R.rec_contig_segment = sl.rec_cseg.data(); R.rec_tid = sl.rec_tid.data(); R.rec_pos = sl.rec_pos.data(); R.rec_mapq = sl.rec_mapq.data();
-    R.rec_flag = sl.rec_flag.data(); R.rec_bin = sl.rec_bin.data(); R.rec_need_flip = sl.rec_flip.data();
-    R.rec_cigar_begin = sl.rec_cigar_begin.data(); R.cigar = sl.out_cigar.data();
+    const ResultLayout L = result_layout(n, nr, nc);
+    sl.arena.assign(L.total + 64, char(0x5a));
+    const DevResult R = DevResult::view(sl.arena.data(), L);
     for (uint32_t r = 0; r < n; ++r) {  // what emit_records_kernel does for read r (lane per read on the device)
         const uint2 base = read_counts[r], next = read_counts[r + 1];
         R.read_rec_begin[r] = base.x;
@@ -252,12 +239,12 @@ int run_batch(ptl_ctx* ctx, EmulSlot& sl, const ptl_batch* b, uint32_t stage_mas
     ptl_result& res = sl.res;
     res = ptl_result{};
     res.n_reads = n;
-    res.read_rec_begin = sl.read_rec_begin.data();
+    res.read_rec_begin = R.read_rec_begin;
     res.n_records = nr;
-    res.rec_status = sl.rec_status.data(); res.rec_read_segment = sl.rec_rseg.data(); res.rec_contig_segment = sl.rec_cseg.data();
-    res.rec_tid = sl.rec_tid.data(); res.rec_pos = sl.rec_pos.data(); res.rec_mapq = sl.rec_mapq.data(); res.rec_flag = sl.rec_flag.data();
-    res.rec_bin = sl.rec_bin.data(); res.rec_need_flip = sl.rec_flip.data(); res.rec_cigar_begin = sl.rec_cigar_begin.data();
-    res.cigar = sl.out_cigar.data();
+    res.rec_status = R.rec_status; res.rec_read_segment = R.rec_read_segment; res.rec_contig_segment = R.rec_contig_segment;
+    res.rec_tid = R.rec_tid; res.rec_pos = R.rec_pos; res.rec_mapq = R.rec_mapq; res.rec_flag = R.rec_flag;
+    res.rec_bin = R.rec_bin; res.rec_need_flip = R.rec_need_flip; res.rec_cigar_begin = R.rec_cigar_begin;
+    res.cigar = R.cigar;
     res.n_cigar = nc;
     res.n_pairs = T.n_pairs;
     res.n_lifted = T.n_lifted;
