@@ -211,13 +211,9 @@ void install_segments(ptl_ctx* ctx, std::vector<HostContig>& contigs) {
 void upload_batch(ptl_ctx* ctx, Slot& sl, const ptl_batch* b) {
     cudaStream_t st = sl.stream;
     const uint32_t n = b->n_reads, ns = b->n_read_segments;
-    // cheap host-side validation of what would be an index panic in the reference
-    if (n && b->read_seg_begin[n] != ns) throw std::runtime_error("read_seg_begin[n_reads] != n_read_segments");
-    for (uint32_t s = 0; s < ns; ++s) {
-        if (b->rseg_contig[s] >= ctx->S.n_contigs) throw std::runtime_error("read segment refers to a contig index outside the assembly");
-        if (b->rseg_cigar_begin[s] + b->rseg_cigar_len[s] > b->n_cigar) throw std::runtime_error("read segment CIGAR outside the pool");
-        if (b->rseg_pos[s] < 0 || b->rseg_pos[s] > 0x7fffffffLL) throw std::runtime_error("read segment position outside the BAM int32 range");
-    }
+    // O(1) checks here; per-segment index validation happens on the device (pair_count_body -> OVF_INVALID), so that
+    // submit costs the host no pass over the batch
+    if (n && (b->read_seg_begin[0] != 0 || b->read_seg_begin[n] != ns)) throw std::runtime_error("read_seg_begin must run from 0 to n_read_segments");
     DevBatch& B = sl.B;
     B.n_reads = n;
     B.n_rsegs = ns;
@@ -283,6 +279,7 @@ void upload_batch(ptl_ctx* ctx, Slot& sl, const ptl_batch* b) {
     } else {
         B.seq4 = upload(sl.d_seq4, b->seq4, b->seq4_bytes, st);
     }
+    B.seq4_bytes = b->seq4_bytes;
     sl.n_cigar_in = b->n_cigar;
     sl.uploaded = true;
     sl.ran = false;
@@ -389,6 +386,8 @@ void finish_batch(ptl_ctx* ctx, Slot& sl) {
         CK(cudaGetLastError());
         std::memcpy(&sl.totals, sl.h_arena.p, sizeof(DevTotals));
         const DevTotals& t = sl.totals;
+        if (t.overflow & OVF_INVALID)
+            throw std::runtime_error("malformed batch: a read segment's contig index, CIGAR range, position (BAM int32) or base range lies outside its pool");
         if (!t.overflow) {
             if (sl.B.n_reads) {
                 sl.est_rec_per_read = double(t.n_records) / double(sl.B.n_reads);

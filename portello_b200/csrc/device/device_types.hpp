@@ -71,6 +71,7 @@ struct DevBatch {
     const uint32_t* rseg_cigar_len = nullptr;
     const uint32_t* cigar = nullptr;
     const uint8_t* seq4 = nullptr;  // device copy, or a mapped pinned host pointer in zero-copy mode
+    uint64_t seq4_bytes = 0;
     // optional indel windows (ptl_batch.indel_win): the first 16 read nibbles the homology walk of each I/D cluster touches
     const uint64_t* indel_win = nullptr;
     const uint32_t* rseg_win_begin = nullptr;  // [n_rsegs+1], nullptr = no windows
@@ -176,13 +177,14 @@ struct DevTotals {
     unsigned long long n_errors;
     long long first_error_read;          // min read index with an error, or INT64_MAX
     int first_error_status;
-    unsigned int overflow;               // bit0 pairs, bit1 scratch, bit2 result arena
+    unsigned int overflow;               // bit0 pairs, bit1 scratch, bit2 result arena, bit4 malformed batch
     unsigned long long n_in_ops;         // sum of input CIGAR ops over attempted pairs   (roofline arithmetic)
     unsigned long long n_base_bytes;     // base bytes compared (both operands)            (roofline arithmetic)
     unsigned int n_simplify;             // length of DevWork::simplify_list
 };
 
-enum : unsigned { OVF_PAIRS = 1, OVF_SCRATCH = 2, OVF_RESULT = 4 };
+// OVF_INVALID: the batch itself is malformed (an index outside its pool); reported by ptl_lift_wait as PTL_ERR_INVALID_ARG
+enum : unsigned { OVF_PAIRS = 1, OVF_SCRATCH = 2, OVF_RESULT = 4, OVF_INVALID = 16 };
 static_assert(sizeof(DevTotals) <= kResultHeaderBytes, "the totals are the header of the result arena");
 
 }  // namespace ptl

@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(128) pair_count_kernel(DevStatic S, DevBatch B
         }
         return;
     }
-    pair_count_body(S, B, W, r);
+    pair_count_body(S, B, W, T, r);
 }
 
 // a3 (fill).  One thread per read segment.

@@ -62,11 +62,25 @@ __device__ __forceinline__ void table_build_body(const DevStatic& S, uint32_t g,
 // =================================================================================================== pair enumeration
 // a3 (count): get_contig_split_segments_from_read_mapping (src/read_alignment_scanner.rs:80-103) + get_cigar_ref_offset,
 // for the 1..k split segments of read r.
-__device__ __forceinline__ void pair_count_body(const DevStatic& S, const DevBatch& B, const DevWork& W, uint32_t r) {
-    for (uint32_t s = B.read_seg_begin[r]; s < B.read_seg_begin[r + 1]; ++s) {
+// Also validates what the reference's slice indexing would panic on (a malformed batch, not a malformed alignment): a
+// segment whose contig, CIGAR range, position or base range lies outside its pool gets no pairs and raises OVF_INVALID.
+__device__ __forceinline__ void pair_count_body(const DevStatic& S, const DevBatch& B, const DevWork& W, DevTotals* T, uint32_t r) {
+    const uint32_t s0 = B.read_seg_begin[r], s1 = B.read_seg_begin[r + 1];
+    bool bad = s0 > s1 || s1 > B.n_rsegs || B.read_seq_off[r] + (uint64_t(B.read_seq_len[r]) + 1u) / 2u > B.seq4_bytes;
+    for (uint32_t s = s0; s < s1 && s < B.n_rsegs; ++s) {
         W.rseg_read[s] = r;
-        const uint32_t* c = B.cigar + B.rseg_cigar_begin[s];
+        const uint64_t c0 = B.rseg_cigar_begin[s];
         const uint32_t n = B.rseg_cigar_len[s];
+        const int64_t pos = B.rseg_pos[s];
+        if (bad || B.rseg_contig[s] >= S.n_contigs || c0 + n > B.n_cigar || pos < 0 || pos > 0x7fffffffLL) {
+            bad = true;
+            W.rseg_ref_len[s] = 0;
+            W.rseg_n_id[s] = 0;
+            W.rseg_read_len[s] = 0;
+            W.rseg_pair_begin[s] = 0;
+            continue;
+        }
+        const uint32_t* c = B.cigar + c0;
         int64_t ref_len = 0;
         uint32_t n_id = 0, read_len = 0;
         for (uint32_t i = 0; i < n; ++i) {
@@ -87,6 +101,7 @@ __device__ __forceinline__ void pair_count_body(const DevStatic& S, const DevBat
         }
         W.rseg_pair_begin[s] = cnt;
     }
+    if (bad) atomicOr(&T->overflow, OVF_INVALID);
 }
 
 __device__ __forceinline__ uint32_t lower_bound_key(const TabEntry* tab, uint32_t lo, uint32_t hi, int64_t key) {

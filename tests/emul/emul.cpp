@@ -124,12 +124,7 @@ int run_batch(ptl_ctx* ctx, EmulSlot& sl, const ptl_batch* b, uint32_t stage_mas
     if (!ctx->have_segments) return fail(ctx, PTL_ERR_INVALID_ARG, "ptl_set_contig_segments / ptl_set_contig_records has not been called");
     if ((stage_mask & PTL_STAGE_SIMPLIFY) && !ctx->have_reference) return fail(ctx, PTL_ERR_INVALID_ARG, "ptl_set_reference has not been called");
     const uint32_t n = b->n_reads, ns = b->n_read_segments;
-    if (n && b->read_seg_begin[n] != ns) return fail(ctx, PTL_ERR_INVALID_ARG, "read_seg_begin[n_reads] != n_read_segments");
-    for (uint32_t s = 0; s < ns; ++s) {
-        if (b->rseg_contig[s] >= ctx->S.n_contigs) return fail(ctx, PTL_ERR_INVALID_ARG, "read segment refers to a contig index outside the assembly");
-        if (b->rseg_cigar_begin[s] + b->rseg_cigar_len[s] > b->n_cigar) return fail(ctx, PTL_ERR_INVALID_ARG, "read segment CIGAR outside the pool");
-        if (b->rseg_pos[s] < 0 || b->rseg_pos[s] > 0x7fffffffLL) return fail(ctx, PTL_ERR_INVALID_ARG, "read segment position outside the BAM int32 range");
-    }
+    if (n && (b->read_seg_begin[0] != 0 || b->read_seg_begin[n] != ns)) return fail(ctx, PTL_ERR_INVALID_ARG, "read_seg_begin must run from 0 to n_read_segments");
     sl.read_flag = padded_copy(b->read_flag, n);
     sl.read_mapq = padded_copy(b->read_mapq, n);
     sl.read_bin = padded_copy(b->read_bin, n);
@@ -150,6 +145,7 @@ int run_batch(ptl_ctx* ctx, EmulSlot& sl, const ptl_batch* b, uint32_t stage_mas
     B.rseg_contig = sl.rseg_contig.data(); B.rseg_pos = sl.rseg_pos.data(); B.rseg_is_fwd = sl.rseg_is_fwd.data();
     B.rseg_cigar_begin = sl.rseg_cigar_begin.data(); B.rseg_cigar_len = sl.rseg_cigar_len.data(); B.cigar = sl.cigar.data();
     B.seq4 = sl.seq4.data();
+    B.seq4_bytes = b->seq4_bytes;
     if (b->indel_win && b->rseg_win_begin) {
         sl.rseg_win_begin = padded_copy(b->rseg_win_begin, size_t(ns) + 1);
         sl.indel_win = padded_copy(b->indel_win, b->n_indel_win);
@@ -167,7 +163,7 @@ int run_batch(ptl_ctx* ctx, EmulSlot& sl, const ptl_batch* b, uint32_t stage_mas
     DevWork W;
     W.rseg_read = rseg_read.data(); W.rseg_pair_begin = rseg_pair_begin.data(); W.rseg_ref_len = rseg_ref_len.data();
     W.rseg_n_id = rseg_n_id.data(); W.rseg_read_len = rseg_read_len.data();
-    for (uint32_t r = 0; r < n; ++r) pair_count_body(S, B, W, r);
+    for (uint32_t r = 0; r < n; ++r) pair_count_body(S, B, W, &T, r);
     rseg_pair_begin[ns] = 0;
     exclusive_scan(rseg_pair_begin.data(), size_t(ns) + 1);
     const uint32_t np = rseg_pair_begin[ns];
@@ -331,6 +327,7 @@ int ptl_emul_lift_wait(ptl_ctx* ctx, int slot, ptl_result* out) {
     EmulSlot* sl = get_slot(ctx, slot);
     if (!sl || !out) return PTL_ERR_INVALID_ARG;
     if (!sl->ran) return fail(ctx, PTL_ERR_STATE, "ptl_lift_wait without a submitted batch");
+    if (sl->totals.overflow & OVF_INVALID) return fail(ctx, PTL_ERR_INVALID_ARG, "malformed batch");
     *out = sl->res;
     if (sl->res.n_errors)
         return fail(ctx, PTL_ERR_LIFT_PANIC, "the reference would panic on read " + std::to_string(sl->res.first_error_read) + " (status " +

@@ -47,6 +47,28 @@ def lift_c(ctx, batch_c, stage_mask=abi.STAGE_ALL, slot=0, allow_panic=False):
     return abi.Result.from_c(r)
 
 
+def malformed_batches(s):
+    """Batches whose indices leave their pools (the reference would panic on the slice index): one per field."""
+    pb = pack(s)
+    b = pb.c
+    out = []
+    def clone(field, dtype, n, mutate):
+        arr = np.ctypeslib.as_array(getattr(b, field), (n,)).copy()
+        mutate(arr)
+        b2 = abi.BatchC.from_buffer_copy(b)
+        setattr(b2, field, arr.ctypes.data_as(dict(abi.BatchC._fields_)[field]))
+        b2._keep = (arr, pb)
+        return b2
+    ns, n = b.n_read_segments, b.n_reads
+    out.append(("contig", clone("rseg_contig", np.uint32, ns, lambda a: a.__setitem__(7, 10**6))))
+    out.append(("cigar range", clone("rseg_cigar_len", np.uint32, ns, lambda a: a.__setitem__(ns - 1, 10**8))))
+    out.append(("position", clone("rseg_pos", np.int64, ns, lambda a: a.__setitem__(3, -5))))
+    out.append(("position int32", clone("rseg_pos", np.int64, ns, lambda a: a.__setitem__(3, 2**31))))
+    out.append(("bases", clone("read_seq_off", np.uint64, n, lambda a: a.__setitem__(n - 1, int(b.seq4_bytes)))))
+    out.append(("segment csr", clone("read_seg_begin", np.uint32, n + 1, lambda a: a.__setitem__(5, ns + 9))))
+    return out
+
+
 def single_pair_case(c2r_cigar, c2r_pos, c2r_fwd, contig_len, rev_seq, pos, cigar, read_seq4, seq_len, read_flag=0, rseg_fwd=1,
                      mapq=60):
     """One contig with one segment + one read with one segment (golden-vector replay through the full ABI)."""
@@ -63,7 +85,7 @@ def single_pair_case(c2r_cigar, c2r_pos, c2r_fwd, contig_len, rev_seq, pos, ciga
         read_seq_len=np.array([seq_len], np.uint32), read_seq_off=np.array([0], np.uint64), read_seg_begin=np.array([0, 1], np.uint32),
         rseg_contig=np.array([0], np.uint32), rseg_pos=np.array([pos], np.int64), rseg_is_fwd=np.array([rseg_fwd], np.uint8),
         rseg_cigar_begin=np.array([0], np.uint64), rseg_cigar_len=np.array([len(cg)], np.uint32), cigar=cg,
-        seq4=np.asarray(read_seq4, np.uint8) if len(read_seq4) else np.zeros(8, np.uint8))
+        seq4=np.asarray(read_seq4, np.uint8) if len(read_seq4) else np.zeros(max(8, (seq_len + 1) // 2), np.uint8))
     return segs, batch
 
 

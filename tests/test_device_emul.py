@@ -201,3 +201,14 @@ def test_emulated_windows_are_used_not_the_bases(emul):
         same = np.sum(blind.rec_pos == ref.rec_pos) if len(blind.rec_pos) == len(ref.rec_pos) else 0
         assert same >= 0.98 * len(ref.rec_pos), diff
     assert good.n_lifted > 0
+
+
+def test_emulated_malformed_batches_are_rejected(emul):
+    """Index validation runs inside pair_count_body (no host pass over the batch): the wait reports PTL_ERR_INVALID_ARG."""
+    s = synth.make("tiny", seed=3, n_reads=200)
+    ectx = emul_context(emul, s)
+    for what, b2 in helpers.malformed_batches(s):
+        with pytest.raises(abi.PtlError) as e:
+            helpers.lift_c(ectx, b2)
+        assert e.value.code == abi.PTL_ERR_INVALID_ARG, what
+    assert helpers.lift_c(ectx, helpers.pack(s).c).n_lifted > 0  # the context stays usable

@@ -210,3 +210,16 @@ def test_indel_windows_give_identical_results():
     w2 = helpers.pack(s2, pinned=True, windows=True)
     g2.set_seq_zero_copy(True)
     assert helpers.lift_c(g2, w2.c).diff(helpers.lift_c(helpers.oracle_context(s2), w2.c)) is None
+
+
+def test_malformed_batches_are_rejected_not_dereferenced():
+    """A batch whose indices leave their pools must come back as PTL_ERR_INVALID_ARG from the wait (validation runs on
+    the device, inside the pair enumeration) and leave the context usable."""
+    s = synth.make("tiny", seed=3, n_reads=200)
+    gctx = helpers.gpu_context(s)
+    for what, b2 in helpers.malformed_batches(s):
+        with pytest.raises(abi.PtlError) as e:
+            helpers.lift_c(gctx, b2)
+        assert e.value.code == abi.PTL_ERR_INVALID_ARG, what
+    ok = helpers.lift_c(gctx, helpers.pack(s).c)
+    assert ok.diff(helpers.lift_c(helpers.oracle_context(s), helpers.pack(s).c)) is None
