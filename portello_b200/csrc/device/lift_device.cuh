@@ -89,27 +89,33 @@ struct OpSink {
             if ((kRefMask >> (pend & 0xfu)) & 1u) ref_span += pend >> 4;
         }
     }
-    // after the leading edge: merge into the open run or start a new one
-    __device__ __forceinline__ void push_body(uint32_t op, uint32_t len) {
-        const uint32_t pop = pend & 0xfu;
-        if (pop == op) {
-            if (op != OP_P) pend += len << 4;  // a Pad after a Pad is dropped, not merged (cigar/mod.rs:208-215)
-        } else {
-            flush();
-            // an I/D run of the compressed CIGAR holds both kinds iff two adjacent stored ops are {I, D}
-            mixed_cluster |= (((1u << pop) | (1u << op)) == ((1u << OP_I) | (1u << OP_D)));
-            pend = (len << 4) | op;
-        }
-        if (op_is_match(op)) last_match_idx = int32_t(n);
-    }
+    // Branch-free: lanes of a warp push different ops at the same time, so every arm of a branchy push ran with a
+    // handful of active lanes (ncu r02a: 7-10 threads per instruction on these lines).  An empty push (len == 0) falls
+    // out as "merge nothing into the open run".
     __device__ __forceinline__ void push(uint32_t op, uint32_t len) {
-        if (len == 0) return;  // compress_cigar filters empty elements (no stage emits an empty alignment match)
-        if (!seen_match) {  // leading edge (cigar/mod.rs:278-280)
-            if (op_is_match(op)) seen_match = true;
-            else if (op == OP_I) op = OP_S;
-            else if (op == OP_D) { lead_del_shift += len; return; }  // -> SoftClip(0), later dropped
+        // leading edge (cigar/mod.rs:278-280): before the first alignment match I -> S, D -> SoftClip(0) (+ shift)
+        const bool lead = !seen_match;
+        const bool drop = lead && op == OP_D;
+        lead_del_shift += drop ? len : 0u;
+        len = drop ? 0u : len;
+        op = (lead && op == OP_I) ? uint32_t(OP_S) : op;
+        const bool match = op_is_match(op) && len != 0u;
+        seen_match |= match;
+        // compress_cigar (cigar/mod.rs:204-228): merge into the open run or start a new one
+        const uint32_t pop = pend & 0xfu;
+        const bool same = (pop == op) || len == 0u;
+        const bool store = !same && (pend >> 4) != 0u;
+        if (store) {
+            if (n < cap) buf[n] = pend;
+            else overflow = true;
         }
-        push_body(op, len);
+        n += store ? 1u : 0u;
+        ref_span += (store && ((kRefMask >> pop) & 1u)) ? (pend >> 4) : 0u;
+        // an I/D run of the compressed CIGAR holds both kinds iff two adjacent stored ops are {I, D}
+        mixed_cluster |= !same && (((1u << pop) | (1u << op)) == ((1u << OP_I) | (1u << OP_D)));
+        // a Pad after a Pad is dropped, not merged (cigar/mod.rs:208-215)
+        pend = same ? pend + ((op != OP_P && len != 0u) ? (len << 4) : 0u) : ((len << 4) | op);
+        last_match_idx = match ? int32_t(n) : last_match_idx;
     }
     // trailing edge (cigar/mod.rs:282-288) + re-merge of what the conversion made adjacent
     __device__ __forceinline__ void finish() {

@@ -114,7 +114,8 @@ __device__ __forceinline__ uint32_t lower_bound_key(const TabEntry* tab, uint32_
 }
 
 // a3 (fill): pair list of read segment s in (read segment, contig segment index) order + the scratch-slot bound of each pair.
-__device__ __forceinline__ void pair_fill_body(const DevStatic& S, const DevBatch& B, const DevWork& W, uint32_t s) {
+// `hist` (kOrderBins counters, block-shared on the device) receives the work bin of every pair.
+__device__ __forceinline__ void pair_fill_body(const DevStatic& S, const DevBatch& B, const DevWork& W, uint32_t s, uint32_t* hist) {
     uint32_t p = W.rseg_pair_begin[s];
     const uint32_t p_end = W.rseg_pair_begin[s + 1];
     if (p == p_end) return;
@@ -143,6 +144,12 @@ __device__ __forceinline__ void pair_fill_body(const DevStatic& S, const DevBatc
             const uint32_t cap_a = cap_b + 6u * (n_id + n_keys) + 8u;
             W.pair_cap_b[p] = cap_b;
             W.pair_slot_begin[p] = uint64_t(cap_a) + cap_b;  // [0,cap_b) = buffer B, [cap_b, cap_b+cap_a) = buffer A
+            // work bin: loop iterations the pair will cost (forward: one liftover event per op and per key; reverse: two
+            // more walks of the ops for the left shift), clamped; reverse-strand pairs sort behind all forward ones
+            const uint32_t work = (fwd ? n_in : 3u * n_in) + n_keys;
+            const uint32_t key = min(work, kOrderBins / 2u - 1u) + (fwd ? 0u : kOrderBins / 2u);
+            W.pair_key[p] = uint16_t(key);
+            atomicAdd(&hist[key], 1u);
         }
         ++p;
     }
@@ -153,8 +160,12 @@ __device__ __forceinline__ void pair_fill_body(const DevStatic& S, const DevBatc
 // (src/read_alignment_scanner.rs:136-288) for pair p.  Warp-collective: all 32 lanes enter (idle lanes carry
 // valid = false) so that the latency-bound base fetches of a warp are issued together (see run_left_shift_warp).
 // Adds the pair's roofline counters (input ops walked, base bytes compared) to n_in_ops / n_base_bytes.
+// kAllStages: the production instantiation (stage_mask == PTL_STAGE_ALL); the stage-test paths (a stage switched off,
+// simplify inline, verbatim hand-back) compile away, which is worth registers in the hot kernel.
+template <bool kAllStages>
 __device__ __forceinline__ void lift_pair_body(const DevStatic& S, const DevBatch& B, const DevWork& W, DevTotals* T, uint32_t p, bool valid,
-                                               uint32_t stage_mask, uint32_t& n_in_ops, uint32_t& n_base_bytes) {
+                                               uint32_t stage_mask_in, uint32_t& n_in_ops, uint32_t& n_base_bytes) {
+    const uint32_t stage_mask = kAllStages ? 7u : stage_mask_in;
     PairCounters cnt;
     int status = ST_NONE, err = 0;
     uint32_t cpos = 0;   // position on the contig strand the segment's table is written in
@@ -266,7 +277,7 @@ __device__ __forceinline__ void lift_pair_body(const DevStatic& S, const DevBatc
             W.simplify_list[atomicAdd(&T->n_simplify, 1u)] = p;
         }
     }
-    {   // stage tests without the liftover stage: simplify inline, (raw input or A) -> A
+    if (!kAllStages) {   // stage tests without the liftover stage: simplify inline, (raw input or A) -> A
         const bool go = usable && !err && status == ST_LIFTED && (stage_mask & 4u) && !(stage_mask & 2u);
         if (__any_sync(FULL, go)) {
             const uint8_t* ref = nullptr;
@@ -296,7 +307,7 @@ __device__ __forceinline__ void lift_pair_body(const DevStatic& S, const DevBatc
             }
         }
     }
-    if (usable && !err && status == ST_LIFTED && cur_is_raw) {
+    if (!kAllStages && usable && !err && status == ST_LIFTED && cur_is_raw) {
         // stage tests with every stage disabled for this pair: hand the (possibly reversed) input back verbatim
         const uint32_t n = min(cur.n, cap_a);
         for (uint32_t i = 0; i < n; ++i) { const uint32_t c = cur.get(i); buf_a[i] = c; span += op_ref_adv(c); }
@@ -369,7 +380,8 @@ __device__ __forceinline__ uint32_t read_finalize_body(const DevStatic& S, const
                                                        int do_finish) {
     uint32_t lifted = 0, ops = 0, primary = 0xffffffffu;
     int best_mapq = -1, first_err = 0;
-    const uint32_t s0 = B.read_seg_begin[r], s1 = B.read_seg_begin[r + 1];
+    // (clamped: a malformed batch is rejected by the host afterwards, but must not be dereferenced out of bounds here)
+    const uint32_t s0 = min(B.read_seg_begin[r], B.n_rsegs), s1 = min(max(B.read_seg_begin[r + 1], s0), B.n_rsegs);
     const uint32_t p0 = W.rseg_pair_begin[s0], p1 = min(W.rseg_pair_begin[s1], W.pair_cap);
     for (uint32_t p = p0; p < p1; ++p) {
         const int st = W.pair_status[p];

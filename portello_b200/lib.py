@@ -15,7 +15,8 @@ from .abi import (BatchC, ContigRecordsC, ContigSegments, ContigSegmentsC, Conte
                   SplitSegmentsC, u8p, u16p, u32p, u64p, i32p, i64p)
 
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
-SO = os.path.join(CSRC, "libportello_b200.so")
+# PORTELLO_B200_LIB: load another build of the same library (kernel tuning A/B runs under gpurun)
+SO = os.environ.get("PORTELLO_B200_LIB") or os.path.join(CSRC, "libportello_b200.so")
 
 
 class ReadRecordsC(C.Structure):
