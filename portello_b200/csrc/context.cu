@@ -84,7 +84,7 @@ struct Slot {
         d_rseg_is_fwd, d_rseg_cigar_begin, d_rseg_cigar_len, d_cigar, d_seq4, d_arena, d_win_begin, d_win;
     // work
     DBuf w_rseg_read, w_rseg_pair_begin, w_rseg_ref_len, w_rseg_n_id, w_rseg_read_len, w_pair_cap_b, w_pair_rseg, w_pair_seg, w_pair_slot_begin, w_pair_status, w_pair_flip,
-        w_pair_pos, w_pair_n_out, w_pair_bin, w_pair_out_off, w_simplify_list, w_pair_key, w_pair_order, w_order_hist, w_scratch, w_read_counts, w_read_primary, w_scan_tmp, w_totals;
+        w_pair_pos, w_pair_n_out, w_pair_bin, w_pair_out_off, w_simplify_list, w_scratch, w_read_counts, w_read_primary, w_scan_tmp, w_totals;
     // results: one compact arena on the device (device_types.hpp: result_layout) and its pinned host twin
     DBuf r_arena;
     HBuf h_arena;
@@ -311,12 +311,6 @@ void size_work(Slot& sl, uint32_t want_pairs, uint64_t want_scratch, uint64_t wa
     sl.w_pair_bin.ensure(size_t(pc) * 2, st);
     sl.w_pair_out_off.ensure(size_t(pc) * 8, st);
     sl.w_simplify_list.ensure(size_t(pc) * 4, st);
-    sl.w_pair_key.ensure(size_t(pc) * 2, st);
-    sl.w_pair_order.ensure(size_t(pc) * 4, st);
-    sl.w_order_hist.ensure(2 * kOrderBins * 4, st);
-    W.pair_key = sl.w_pair_key.as<uint16_t>();
-    W.pair_order = sl.w_pair_order.as<uint32_t>();
-    W.order_hist = sl.w_order_hist.as<uint32_t>();
     W.pair_cap = pc;
     W.pair_rseg = sl.w_pair_rseg.as<uint32_t>();
     W.pair_seg = sl.w_pair_seg.as<uint32_t>();
@@ -524,7 +518,7 @@ void ptl_destroy(ptl_ctx* ctx) {
         for (DBuf* b : {&sl.d_read_flag, &sl.d_read_mapq, &sl.d_read_bin, &sl.d_read_seq_len, &sl.d_read_seq_off, &sl.d_read_seg_begin,
                         &sl.d_rseg_contig, &sl.d_rseg_pos, &sl.d_rseg_is_fwd, &sl.d_rseg_cigar_begin, &sl.d_rseg_cigar_len, &sl.d_cigar,
                         &sl.d_seq4, &sl.d_arena, &sl.d_win_begin, &sl.d_win, &sl.w_rseg_read, &sl.w_rseg_pair_begin, &sl.w_rseg_ref_len, &sl.w_rseg_n_id, &sl.w_rseg_read_len, &sl.w_pair_cap_b, &sl.w_pair_rseg, &sl.w_pair_seg,
-                        &sl.w_pair_slot_begin, &sl.w_pair_status, &sl.w_pair_flip, &sl.w_pair_pos, &sl.w_pair_n_out, &sl.w_pair_bin, &sl.w_pair_out_off, &sl.w_simplify_list, &sl.w_pair_key, &sl.w_pair_order, &sl.w_order_hist,
+                        &sl.w_pair_slot_begin, &sl.w_pair_status, &sl.w_pair_flip, &sl.w_pair_pos, &sl.w_pair_n_out, &sl.w_pair_bin, &sl.w_pair_out_off, &sl.w_simplify_list,
                         &sl.w_scratch, &sl.w_read_counts, &sl.w_read_primary, &sl.w_scan_tmp, &sl.w_totals, &sl.r_arena})
             b->release();
         sl.h_arena.release();

@@ -77,7 +77,6 @@ struct DevBatch {
     const uint32_t* rseg_win_begin = nullptr;  // [n_rsegs+1], nullptr = no windows
 };
 
-constexpr uint32_t kOrderBins = 512;
 
 // ---- per-batch work arrays ---------------------------------------------------------------------------------------
 struct DevWork {
@@ -102,9 +101,6 @@ struct DevWork {
     uint32_t* simplify_list = nullptr;   // [pair_cap] pairs whose lifted CIGAR needs simplify_alignment_indels
     // work-sorted processing order of the pairs (lanes of a warp then walk CIGARs of similar length; ncu r02a: in batch
     // order a warp ran max(n_ops) = 38 iterations for a mean of 21.7)
-    uint16_t* pair_key = nullptr;        // [pair_cap] work bin of the pair (kOrderBins bins, reverse-strand pairs in the upper half)
-    uint32_t* pair_order = nullptr;      // [pair_cap] permutation: the i-th thread of lift_pairs handles pair pair_order[i]
-    uint32_t* order_hist = nullptr;      // [2 * kOrderBins] per batch: bin sizes, then the per-bin fill cursors
     // scratch op slots
     uint64_t scratch_cap = 0;            // in ops
     uint32_t* scratch = nullptr;

@@ -114,8 +114,7 @@ __device__ __forceinline__ uint32_t lower_bound_key(const TabEntry* tab, uint32_
 }
 
 // a3 (fill): pair list of read segment s in (read segment, contig segment index) order + the scratch-slot bound of each pair.
-// `hist` (kOrderBins counters, block-shared on the device) receives the work bin of every pair.
-__device__ __forceinline__ void pair_fill_body(const DevStatic& S, const DevBatch& B, const DevWork& W, uint32_t s, uint32_t* hist) {
+__device__ __forceinline__ void pair_fill_body(const DevStatic& S, const DevBatch& B, const DevWork& W, uint32_t s) {
     uint32_t p = W.rseg_pair_begin[s];
     const uint32_t p_end = W.rseg_pair_begin[s + 1];
     if (p == p_end) return;
@@ -144,12 +143,6 @@ __device__ __forceinline__ void pair_fill_body(const DevStatic& S, const DevBatc
             const uint32_t cap_a = cap_b + 6u * (n_id + n_keys) + 8u;
             W.pair_cap_b[p] = cap_b;
             W.pair_slot_begin[p] = uint64_t(cap_a) + cap_b;  // [0,cap_b) = buffer B, [cap_b, cap_b+cap_a) = buffer A
-            // work bin: loop iterations the pair will cost (forward: one liftover event per op and per key; reverse: two
-            // more walks of the ops for the left shift), clamped; reverse-strand pairs sort behind all forward ones
-            const uint32_t work = (fwd ? n_in : 3u * n_in) + n_keys;
-            const uint32_t key = min(work, kOrderBins / 2u - 1u) + (fwd ? 0u : kOrderBins / 2u);
-            W.pair_key[p] = uint16_t(key);
-            atomicAdd(&hist[key], 1u);
         }
         ++p;
     }

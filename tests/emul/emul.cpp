@@ -178,15 +178,7 @@ int run_batch(ptl_ctx* ctx, EmulSlot& sl, const ptl_batch* b, uint32_t stage_mas
     W.pair_rseg = pair_rseg.data(); W.pair_seg = pair_seg.data(); W.pair_slot_begin = pair_slot_begin.data(); W.pair_cap_b = pair_cap_b.data();
     W.pair_status = pair_status.data(); W.pair_flip = pair_flip.data(); W.pair_pos = pair_pos.data(); W.pair_n_out = pair_n_out.data();
     W.pair_bin = pair_bin.data(); W.pair_out_off = pair_out_off.data(); W.simplify_list = simplify_list.data();
-    std::vector<uint16_t> pair_key(np + 1);
-    std::vector<uint32_t> order_hist(2 * kOrderBins, 0), pair_order(np + 1);
-    W.pair_key = pair_key.data(); W.pair_order = pair_order.data(); W.order_hist = order_hist.data();
-    for (uint32_t s = 0; s < ns; ++s) pair_fill_body(S, B, W, s, order_hist.data());
-    {   // pair_order_kernel: counting sort of the pairs by work bin (the lift loop below runs in that order)
-        std::vector<uint32_t> start(kOrderBins + 1, 0);
-        for (uint32_t k = 0; k < kOrderBins; ++k) start[k + 1] = start[k] + order_hist[k];
-        for (uint32_t p = 0; p < np; ++p) pair_order[start[pair_key[p]]++] = p;
-    }
+    for (uint32_t s = 0; s < ns; ++s) pair_fill_body(S, B, W, s);
     pair_slot_begin[np] = 0;
     exclusive_scan(pair_slot_begin.data(), size_t(np) + 1);
     std::vector<uint32_t> scratch(pair_slot_begin[np] + 16, 0xdeadbeefu);
@@ -196,8 +188,7 @@ int run_batch(ptl_ctx* ctx, EmulSlot& sl, const ptl_batch* b, uint32_t stage_mas
 
     // ---- lift_pairs (+ simplify worklist)
     uint32_t in_ops = 0, base_bytes = 0;
-    for (uint32_t i = 0; i < np; ++i) {  // the kernel launches the production instantiation for the full stage mask
-        const uint32_t p = pair_order[i];
+    for (uint32_t p = 0; p < np; ++p) {  // the kernel launches the production instantiation for the full stage mask
         if (stage_mask == 7u) lift_pair_body<true>(S, B, W, &T, p, true, stage_mask, in_ops, base_bytes);
         else lift_pair_body<false>(S, B, W, &T, p, true, stage_mask, in_ops, base_bytes);
     }
