@@ -213,9 +213,11 @@ __global__ void __launch_bounds__(LIFT_BLOCK, LIFT_MIN_BLOCKS) lift_pairs_kernel
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t n_pairs = min(uint32_t(T->n_pairs), W.pair_cap);
     if (i == 0) T->scratch_needed = W.pair_slot_begin[n_pairs];  // total op slots of the batch (capacity feedback)
+    if (blockIdx.x * blockDim.x >= n_pairs) return;  // (block-uniform; the grid covers the pair capacity)
     const bool valid = i < n_pairs;
     // natural pair order: the lanes of a warp own consecutive read segments, whose CIGARs are adjacent in the pool and
-    // whose table ranges overlap (a work-sorted order ran 33 % slower: L1 hit rate 77 % -> 54 %, profiles/r03a)
+    // whose table ranges overlap (a work-sorted order ran 33 % slower: L1 hit rate 77 % -> 54 %, profiles/r03a; ranking only
+    // the pairs of a block by work changed nothing at 128 threads and lost 5-12 % at 256-512)
     const uint32_t p = valid ? i : 0u;
     uint32_t a = 0, b = 0;
     lift_pair_body<kAllStages>(S, B, W, T, p, valid, stage_mask, a, b);
