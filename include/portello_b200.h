@@ -244,6 +244,9 @@ int ptl_slot_counters(ptl_ctx* ctx, int slot, uint64_t* out);
 /* 0: copy seq4 to the device (default). 1: seq4 of subsequent batches must be pinned+mapped host memory
  * (ptl_host_alloc); kernels read the few bases they need over PCIe instead of uploading every base. */
 int ptl_set_seq_zero_copy(ptl_ctx* ctx, int enable);
+/* Tuning: a pair whose read->contig CIGAR has more than `n_ops` ops is lifted by a whole warp (lanes over ops) instead
+ * of one thread; 0 sends every pair down the warp-cooperative path.  Same results either way (default 64). */
+int ptl_set_long_pair_ops(ptl_ctx* ctx, uint32_t n_ops);
 
 
 /* Pinned (page-locked, device-mapped) host memory for batches: replaces nothing in the reference, it is the

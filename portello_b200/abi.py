@@ -433,6 +433,14 @@ class Context:
     def __exit__(self, *a):
         self.close()
 
+    def set_long_pair_ops(self, n_ops: int):
+        """Pairs with more CIGAR ops than this are lifted warp-cooperatively (0 = every pair); results do not change.
+        A library without the knob (the oracle) ignores the call."""
+        fn = getattr(self.lib.dll, self.lib.prefix + "set_long_pair_ops", None)
+        if fn is not None:
+            fn.restype, fn.argtypes = C.c_int, [C.c_void_p, C.c_uint32]
+            self._check(fn(self.h, int(n_ops)))
+
     def _check(self, rc: int, allow=()):
         if rc != PTL_OK and rc not in allow:
             raise PtlError(rc, self.lib._last_error(self.h).decode())

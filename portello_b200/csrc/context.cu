@@ -6,6 +6,8 @@
 // pipeline.  There is NO CPU fallback: without a usable device ptl_create fails with PTL_ERR_NO_DEVICE.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include <algorithm>
 #include <cstdio>
 #include <cstdint>
@@ -84,7 +86,7 @@ struct Slot {
         d_rseg_is_fwd, d_rseg_cigar_begin, d_rseg_cigar_len, d_cigar, d_seq4, d_arena, d_win_begin, d_win;
     // work
     DBuf w_rseg_read, w_rseg_pair_begin, w_rseg_ref_len, w_rseg_n_id, w_rseg_read_len, w_pair_cap_b, w_pair_rseg, w_pair_seg, w_pair_slot_begin, w_pair_status, w_pair_flip,
-        w_pair_pos, w_pair_n_out, w_pair_bin, w_pair_out_off, w_simplify_list, w_scratch, w_read_counts, w_read_primary, w_scan_tmp, w_totals;
+        w_pair_pos, w_pair_n_out, w_pair_bin, w_pair_out_off, w_simplify_list, w_long_list, w_scratch, w_read_counts, w_read_primary, w_scan_tmp, w_totals;
     // results: one compact arena on the device (device_types.hpp: result_layout) and its pinned host twin
     DBuf r_arena;
     HBuf h_arena;
@@ -109,6 +111,7 @@ struct ptl_ctx {
     cudaStream_t setup_stream = nullptr;
     uint64_t launches = 0;
     bool zero_copy_seq = false;
+    uint32_t long_pair_ops = 64;  // ptl_set_long_pair_ops
     // static state
     DBuf s_ref, s_chrom_off, s_contig_seg_begin, s_contig_len, s_contig_rev_off, s_rev_pool, s_so_start, s_so_end, s_chrom, s_pos,
         s_is_fwd, s_mapq, s_cigar_begin, s_cigar, s_tab_begin, s_table;
@@ -311,6 +314,7 @@ void size_work(Slot& sl, uint32_t want_pairs, uint64_t want_scratch, uint64_t wa
     sl.w_pair_bin.ensure(size_t(pc) * 2, st);
     sl.w_pair_out_off.ensure(size_t(pc) * 8, st);
     sl.w_simplify_list.ensure(size_t(pc) * 4, st);
+    sl.w_long_list.ensure(size_t(pc) * 4, st);
     W.pair_cap = pc;
     W.pair_rseg = sl.w_pair_rseg.as<uint32_t>();
     W.pair_seg = sl.w_pair_seg.as<uint32_t>();
@@ -323,6 +327,7 @@ void size_work(Slot& sl, uint32_t want_pairs, uint64_t want_scratch, uint64_t wa
     W.pair_bin = sl.w_pair_bin.as<uint16_t>();
     W.pair_out_off = sl.w_pair_out_off.as<uint64_t>();
     W.simplify_list = sl.w_simplify_list.as<uint32_t>();
+    W.long_list = sl.w_long_list.as<uint32_t>();
     const uint64_t sc = std::max(W.scratch_cap, want_scratch);
     sl.w_scratch.ensure(size_t(sc) * 4, st);
     W.scratch_cap = sc;
@@ -375,6 +380,7 @@ void run_batch(ptl_ctx* ctx, Slot& sl, uint32_t stage_mask, bool with_results) {
     const uint64_t want_scratch = 8ull * sl.n_cigar_in + 64ull * want_pairs;
     const uint64_t want_recs = uint64_t(want_pairs) + n;
     const uint64_t want_cigar = sl.n_cigar_in + sl.n_cigar_in / 2 + 16ull * n + 1024;
+    sl.W.long_ops = ctx->long_pair_ops;
     size_work(sl, want_pairs, want_scratch, result_layout(n, want_recs, want_cigar).total);
     enqueue_run(ctx, sl, with_results);
 }
@@ -518,7 +524,7 @@ void ptl_destroy(ptl_ctx* ctx) {
         for (DBuf* b : {&sl.d_read_flag, &sl.d_read_mapq, &sl.d_read_bin, &sl.d_read_seq_len, &sl.d_read_seq_off, &sl.d_read_seg_begin,
                         &sl.d_rseg_contig, &sl.d_rseg_pos, &sl.d_rseg_is_fwd, &sl.d_rseg_cigar_begin, &sl.d_rseg_cigar_len, &sl.d_cigar,
                         &sl.d_seq4, &sl.d_arena, &sl.d_win_begin, &sl.d_win, &sl.w_rseg_read, &sl.w_rseg_pair_begin, &sl.w_rseg_ref_len, &sl.w_rseg_n_id, &sl.w_rseg_read_len, &sl.w_pair_cap_b, &sl.w_pair_rseg, &sl.w_pair_seg,
-                        &sl.w_pair_slot_begin, &sl.w_pair_status, &sl.w_pair_flip, &sl.w_pair_pos, &sl.w_pair_n_out, &sl.w_pair_bin, &sl.w_pair_out_off, &sl.w_simplify_list,
+                        &sl.w_pair_slot_begin, &sl.w_pair_status, &sl.w_pair_flip, &sl.w_pair_pos, &sl.w_pair_n_out, &sl.w_pair_bin, &sl.w_pair_out_off, &sl.w_simplify_list, &sl.w_long_list,
                         &sl.w_scratch, &sl.w_read_counts, &sl.w_read_primary, &sl.w_scan_tmp, &sl.w_totals, &sl.r_arena})
             b->release();
         sl.h_arena.release();
@@ -661,6 +667,11 @@ int ptl_slot_kernel_times(ptl_ctx* ctx, int slot, int cap, const char** names, f
     return n;
 }
 uint64_t ptl_launch_count(const ptl_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int ptl_set_long_pair_ops(ptl_ctx* ctx, uint32_t n_ops) {
+    if (!ctx) return PTL_ERR_INVALID_ARG;
+    ctx->long_pair_ops = n_ops;
+    return PTL_OK;
+}
 int ptl_set_seq_zero_copy(ptl_ctx* ctx, int enable) {
     if (!ctx) return PTL_ERR_INVALID_ARG;
     ctx->zero_copy_seq = enable != 0;

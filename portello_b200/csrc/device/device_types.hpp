@@ -99,8 +99,8 @@ struct DevWork {
     uint16_t* pair_bin = nullptr;        // bam_reg2bin(pos, end) of the final record
     uint64_t* pair_out_off = nullptr;    // where the final ops of the pair start in scratch
     uint32_t* simplify_list = nullptr;   // [pair_cap] pairs whose lifted CIGAR needs simplify_alignment_indels
-    // work-sorted processing order of the pairs (lanes of a warp then walk CIGARs of similar length; ncu r02a: in batch
-    // order a warp ran max(n_ops) = 38 iterations for a mean of 21.7)
+    uint32_t* long_list = nullptr;       // [pair_cap] pairs whose liftover runs warp-cooperatively (status ST_PENDING_LIFT)
+    uint32_t long_ops = 64;              // a pair with more CIGAR ops than this goes to long_list
     // scratch op slots
     uint64_t scratch_cap = 0;            // in ops
     uint32_t* scratch = nullptr;
@@ -184,6 +184,7 @@ struct DevTotals {
     unsigned long long n_in_ops;         // sum of input CIGAR ops over attempted pairs   (roofline arithmetic)
     unsigned long long n_base_bytes;     // base bytes compared (both operands)            (roofline arithmetic)
     unsigned int n_simplify;             // length of DevWork::simplify_list
+    unsigned int n_long;                 // length of DevWork::long_list
 };
 
 // OVF_INVALID: the batch itself is malformed (an index outside its pool); reported by ptl_lift_wait as PTL_ERR_INVALID_ARG

@@ -1,0 +1,395 @@
+// Warp-cooperative liftover (sm_100a): ONE WARP per (read segment x contig segment) pair, lanes over CIGAR ops.
+//
+//   a6  liftover_read_alignment + update_ref2_cigar_segment   (src/liftover_read_alignment.rs:35-223)
+//   a8  clean_up_cigar_edge_indels + compress_cigar            (lib/rust-vc-utils/src/bam_utils/cigar/mod.rs:204-291)
+//
+// The per-thread walk of lift_device.cuh::run_liftover pays one dependent load per op and leaves a 100 kb read (hundreds
+// of ops) to a single lane; here the same result is computed as data-parallel steps over chunks of 32 ops:
+//
+//   1. coalesced load of 32 ops; warp scan of their reference advance -> contig interval [p_i, e_i) of every op
+//   2. the table entries inside the chunk's interval are loaded ONCE, one per lane (the "window"); every lane counts the
+//      keys <= p_i and < e_i by register shuffles -> block under p_i and number of pieces of its op
+//   3. warp scan of the piece counts; lanes are re-assigned to PIECES (load-balancing search over the scan), so an op
+//      that crosses many table keys costs rounds, not a serial inner loop
+//   4. every piece yields at most two ops (the deletion pushed when the walk enters an aligned run, then the piece
+//      itself); the sequential state of the reference (ref2_start_pos set / ref2_end_pos set) is a prefix-OR = a ballot
+//   5. WarpSink: edge clean-up + run compression of the 64 candidate ops of a round with ballots and one scan, carrying the
+//      open run between rounds; complete runs go to memory with one coalesced store
+//
+// Only min() / compares / adds on integers; identical results to run_liftover by construction of the same piece
+// sequence (tests: every golden liftover vector + randomised parity against the oracle through both paths).
+#pragma once
+#include <cstdint>
+
+#include "cigar_ops.cuh"
+#include "device_types.hpp"
+
+namespace ptl {
+
+__device__ __forceinline__ uint32_t lanes_lt(uint32_t lane) { return (1u << lane) - 1u; }
+__device__ __forceinline__ uint32_t lanes_le(uint32_t lane) { return (2u << lane) - 1u; }  // lane 31: 0 - 1 = all
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, uint32_t lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(FULL, v, d);
+        if (int(lane) >= d) v += o;
+    }
+    return v;
+}
+__device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Streaming clean_up_cigar_edge_indels + compress_cigar for a warp.  Every round each lane offers up to two ops in
+// order: A = Del(a_len) then B = (b_op, b_len); empty ops (len 0) vanish.  Uniform state is identical in all lanes.
+struct WarpSink {
+    uint32_t* buf;
+    uint32_t cap;
+    uint32_t n = 0;               // stored ops (uniform)
+    uint32_t pend = 0;            // open run (len << 4 | op), len 0 = none (uniform)
+    int32_t last_match_idx = -1;  // index of the last alignment-match run, counting the open one (uniform)
+    bool seen_match = false;      // (uniform)
+    // per-lane partial sums, reduced once in finish()
+    uint32_t acc_span = 0, acc_shift = 0;
+    bool lane_mixed = false;
+    // results of finish() (uniform)
+    bool overflow = false, mixed_cluster = false;
+    uint32_t ref_span = 0, lead_del_shift = 0;
+
+    __device__ __forceinline__ WarpSink(uint32_t* b, uint32_t c) : buf(b), cap(c) {}
+
+    __device__ __forceinline__ void store(uint32_t idx, uint32_t word) {
+        if (idx < cap) buf[idx] = word;
+    }
+
+    __device__ __forceinline__ void push2(uint32_t lane, uint32_t a_len, uint32_t b_op, uint32_t b_len) {
+        // leading edge (cigar/mod.rs:278-280): before the first alignment match I -> S, D -> dropped (+ position shift)
+        const bool b_match = b_len != 0u && op_is_match(b_op);
+        const uint32_t mmask = __ballot_sync(FULL, b_match);
+        if (!seen_match && (mmask & lanes_lt(lane)) == 0u) {
+            acc_shift += a_len;
+            a_len = 0;
+            if (!b_match) {
+                if (b_op == OP_D) { acc_shift += b_len; b_len = 0; }
+                else if (b_op == OP_I) b_op = OP_S;
+            }
+        }
+        seen_match = seen_match || mmask != 0u;
+        acc_span += a_len + (((kRefMask >> b_op) & 1u) ? b_len : 0u);
+        // compress_cigar (cigar/mod.rs:204-228) over the 64 candidates + the open run
+        const bool nzA = a_len != 0u, nzB = b_len != 0u;
+        const uint32_t any_mask = __ballot_sync(FULL, nzA || nzB);
+        if (any_mask == 0u) return;
+        const uint32_t before = any_mask & lanes_lt(lane);
+        const uint32_t last_op = nzB ? b_op : uint32_t(OP_D);
+        uint32_t prev_op = __shfl_sync(FULL, last_op, before ? (31 - __clz(before)) : 0);
+        if (!before) prev_op = (pend >> 4) ? (pend & 0xfu) : 0xffu;
+        const bool headA = nzA && prev_op != OP_D;
+        const uint32_t prev_b = nzA ? uint32_t(OP_D) : prev_op;
+        const bool headB = nzB && b_op != prev_b;
+        // a Pad after a Pad is dropped, not merged (cigar/mod.rs:208-215)
+        const uint32_t cb = (b_op == OP_P && !headB) ? 0u : b_len;
+        // an I/D run of the compressed CIGAR holds both kinds iff two adjacent runs are {I, D}
+        lane_mixed = lane_mixed || (headA && prev_op == OP_I) || (headB && ((b_op == OP_I && prev_b == OP_D) || (b_op == OP_D && prev_b == OP_I)));
+        const uint32_t t = a_len + cb;
+        const uint32_t incl = warp_incl_scan(t, lane);
+        const uint32_t total = __shfl_sync(FULL, incl, 31);
+        const uint32_t posA = incl - t, posB = posA + a_len;  // flat length prefix in front of A / B
+        const uint32_t hA = __ballot_sync(FULL, headA), hB = __ballot_sync(FULL, headB), hAny = hA | hB;
+        if (hAny == 0u) {  // everything merges into the open run
+            pend += total << 4;
+            return;
+        }
+        const uint32_t fh = headA ? posA : posB;  // prefix in front of this lane's first head
+        const uint32_t after = hAny & ~lanes_le(lane);
+        uint32_t nextpos = __shfl_sync(FULL, fh, after ? (__ffs(after) - 1) : 0);
+        if (!after) nextpos = total;
+        const uint32_t segA = headA ? ((headB ? posB : nextpos) - posA) : 0u;
+        const uint32_t segB = headB ? (nextpos - posB) : 0u;
+        const uint32_t n_heads = __popc(hA) + __popc(hB);
+        const uint32_t idxA = __popc(hA & lanes_lt(lane)) + __popc(hB & lanes_lt(lane));
+        const uint32_t idxB = idxA + (headA ? 1u : 0u);
+        // the open run absorbs what precedes the first head, then is stored
+        const uint32_t fpos = __shfl_sync(FULL, fh, __ffs(hAny) - 1);
+        const uint32_t closed = pend + (fpos << 4);
+        uint32_t base = n;
+        if (closed >> 4) {
+            if (lane == 0u) store(base, closed);
+            ++base;
+        }
+        // every head but the last is a complete run; the last one stays open
+        if (headA && idxA != n_heads - 1u) store(base + idxA, (segA << 4) | OP_D);
+        if (headB && idxB != n_heads - 1u) store(base + idxB, (segB << 4) | b_op);
+        const uint32_t my_last = headB ? ((segB << 4) | b_op) : ((segA << 4) | OP_D);
+        pend = __shfl_sync(FULL, my_last, 31 - __clz(hAny));
+        n = base + n_heads - 1u;
+        const uint32_t mh = __ballot_sync(FULL, headB && op_is_match(b_op));
+        if (mh) last_match_idx = int32_t(__shfl_sync(FULL, base + idxB, 31 - __clz(mh)));
+    }
+
+    // flush + trailing edge (cigar/mod.rs:282-288) + re-merge of what the conversion made adjacent
+    __device__ __forceinline__ void finish(uint32_t lane) {
+        if (pend >> 4) {
+            if (lane == 0u) store(n, pend);
+            ++n;
+        }
+        pend = 0;
+        overflow = n > cap;
+        ref_span = warp_sum(acc_span);
+        lead_del_shift = warp_sum(acc_shift);
+        mixed_cluster = __any_sync(FULL, lane_mixed);
+        __syncwarp();
+        if (overflow || last_match_idx < 0) return;
+        // the tail behind the last match is a handful of ops: every lane walks it, lane 0 writes
+        const uint32_t start = uint32_t(last_match_idx) + 1u;
+        uint32_t w = start, prev = NO_OP;
+        for (uint32_t i = start; i < n; ++i) {
+            uint32_t c = buf[i];
+            uint32_t op = c & 0xfu;
+            if (op == OP_D) { ref_span -= c >> 4; continue; }
+            if (op == OP_I) { op = OP_S; c = (c & ~0xfu) | OP_S; }
+            if (prev != NO_OP && (prev & 0xfu) == op) {
+                if (op != OP_P) prev += c & ~0xfu;
+            } else {
+                if (prev != NO_OP) { if (lane == 0u) buf[w] = prev; ++w; }
+                prev = c;
+            }
+        }
+        if (prev != NO_OP) { if (lane == 0u) buf[w] = prev; ++w; }
+        n = w;
+        __syncwarp();
+    }
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+// First index in [lo, hi) whose key is > pos (kUpper) or >= pos (!kUpper): 32-ary search, the lanes probe 32 evenly
+// spaced entries per round (a 2^17-entry segment table takes 4 rounds instead of 17 dependent loads).  Uniform result.
+template <bool kUpper>
+__device__ __forceinline__ uint32_t warp_table_bound(const TabEntry* __restrict__ tab, uint32_t lo, uint32_t hi, uint32_t pos, uint32_t lane) {
+    while (lo < hi) {
+        const uint32_t step = (hi - lo + 31u) >> 5;
+        const uint32_t idx = lo + (lane + 1u) * step - 1u;
+        bool below = false;
+        if (idx < hi) {
+            const uint32_t k = tab[idx].key;
+            below = kUpper ? (k <= pos) : (k < pos);
+        }
+        const uint32_t c = __popc(__ballot_sync(FULL, below));  // monotone: a prefix of the probes
+        const uint32_t lo_old = lo;
+        lo = lo_old + c * step;
+        hi = min(hi, lo_old + (c + 1u) * step - 1u);
+    }
+    return lo;
+}
+
+__device__ __forceinline__ uint32_t lane_table_bound_upper(const TabEntry* __restrict__ tab, uint32_t lo, uint32_t hi, uint32_t pos) {
+    while (lo < hi) {  // first index with key > pos
+        const uint32_t mid = (lo + hi) >> 1;
+        if (tab[mid].key <= pos) lo = mid + 1u; else hi = mid;
+    }
+    return lo;
+}
+__device__ __forceinline__ uint32_t lane_table_bound_lower(const TabEntry* __restrict__ tab, uint32_t lo, uint32_t hi, uint32_t pos) {
+    while (lo < hi) {  // first index with key >= pos
+        const uint32_t mid = (lo + hi) >> 1;
+        if (tab[mid].key < pos) lo = mid + 1u; else hi = mid;
+    }
+    return lo;
+}
+
+// a6 for one pair, all 32 lanes.  `in`/`n`/`reversed`: the read->contig CIGAR (op i = in[reversed ? n-1-i : i]); `pos`: its
+// start on the strand the segment's table [t0, t1) is written in.  Ops go through `sink`; the caller runs sink.finish().
+// Returns true if ref2_start_pos was set (uniform); *start = that position (before the leading-deletion shift).
+__device__ __forceinline__ bool warp_liftover(const uint32_t* __restrict__ in, uint32_t n, bool reversed, uint32_t pos,
+                                              const TabEntry* __restrict__ tab, uint32_t t0, uint32_t t1, WarpSink& sink, uint32_t lane,
+                                              int32_t* start_out) {
+    constexpr uint32_t INF = 0xffffffffu;
+    // cursor: tcur = first entry with key > p_base; (b0_*) = the entry in front of it = the block under p_base
+    uint32_t tcur = warp_table_bound<true>(tab, t0, t1, pos, lane);
+    uint32_t b0_key = 0, b0_gap = 0;
+    int32_t b0_val = -2;  // -2: in front of the first key
+    if (tcur > t0) {
+        const TabEntry b = tab[tcur - 1u];
+        b0_key = b.key; b0_val = b.val; b0_gap = b.gap;
+    }
+    uint32_t p_base = pos;
+    bool start_set = false, some_seen = false;
+    int32_t start = 0;
+    for (uint32_t base = 0; base < n; base += 32u) {
+        // ---- 1. ops of the chunk and their contig intervals
+        const uint32_t i = base + lane;
+        const uint32_t c = (i < n) ? in[reversed ? (n - 1u - i) : i] : 0u;
+        const uint32_t op = c & 0xfu, len = c >> 4;
+        const uint32_t radv = ((kRefMask >> op) & 1u) ? len : 0u;
+        const uint32_t incl = warp_incl_scan(radv, lane);
+        const uint32_t e_i = p_base + incl, p_i = e_i - radv;
+        const uint32_t chunk_end = __shfl_sync(FULL, e_i, 31);
+        // ---- 2. table window: entries with p_base < key < chunk_end, one per lane
+        uint32_t wkey = INF, wgap = 0;
+        int32_t wval = -1;
+        if (tcur + lane < t1) {
+            const TabEntry w = tab[tcur + lane];
+            wkey = w.key; wval = w.val; wgap = w.gap;
+        }
+        const uint32_t nwin = __popc(__ballot_sync(FULL, wkey < chunk_end));  // keys increase: a prefix of the lanes
+        const bool big = nwin == 32u;  // more keys may follow: per-lane look-ups in memory for this chunk
+        uint32_t cnt_p = 0, cnt_e = 0;  // window keys <= p_i, < e_i
+        if (!big) {
+            for (uint32_t j = 0; j < nwin; ++j) {
+                const uint32_t kj = __shfl_sync(FULL, wkey, j);
+                cnt_p += (kj <= p_i) ? 1u : 0u;
+                cnt_e += (kj < e_i) ? 1u : 0u;
+            }
+        } else if (radv) {
+            cnt_p = lane_table_bound_upper(tab, tcur, t1, p_i) - tcur;
+            cnt_e = lane_table_bound_lower(tab, tcur, t1, e_i) - tcur;
+        }
+        // ---- 3. pieces: a reference-consuming op is cut at every key inside it; I/S/H pass verbatim; Pad and empty ops vanish
+        const bool verbatim = op == OP_I || op == OP_S || op == OP_H;
+        const uint32_t pieces = radv ? (cnt_e - cnt_p + 1u) : (verbatim ? 1u : 0u);
+        const uint32_t pincl = warp_incl_scan(pieces, lane);
+        const uint32_t pex = pincl - pieces;
+        const uint32_t n_pieces = __shfl_sync(FULL, pincl, 31);
+        for (uint32_t q0 = 0; q0 < n_pieces; q0 += 32u) {
+            const uint32_t q = q0 + lane;
+            const bool act = q < n_pieces;
+            // owner op of piece q = last lane whose exclusive piece prefix is <= q
+            uint32_t lo = 0, hi = 31;
+#pragma unroll
+            for (int it = 0; it < 5; ++it) {
+                const uint32_t mid = (lo + hi + 1u) >> 1;
+                const uint32_t v = __shfl_sync(FULL, pex, mid);
+                if (v <= q) lo = mid; else hi = mid - 1u;
+            }
+            const uint32_t oc = __shfl_sync(FULL, c, lo);
+            const uint32_t o_p = __shfl_sync(FULL, p_i, lo), o_e = __shfl_sync(FULL, e_i, lo);
+            const uint32_t o_cnt = __shfl_sync(FULL, cnt_p | (cnt_e << 16), lo);  // (window counts <= 32; in `big` chunks see below)
+            const uint32_t o_pex = __shfl_sync(FULL, pex, lo);
+            uint32_t o_cp = o_cnt & 0xffffu, o_ce = o_cnt >> 16;
+            if (big) {  // counts may exceed 16 bits
+                o_cp = __shfl_sync(FULL, cnt_p, lo);
+                o_ce = __shfl_sync(FULL, cnt_e, lo);
+            }
+            const uint32_t o_op = oc & 0xfu, o_len = oc >> 4;
+            const bool o_ref = ((kRefMask >> o_op) & 1u) && o_len != 0u;
+            const uint32_t j = q - o_pex;
+            // block of the piece: window index rel (-1 = the block under p_base), and the key that ends it
+            const int32_t rel = (act && o_ref) ? int32_t(o_cp + j) - 1 : 0;
+            uint32_t bkey, bgap, nkey;
+            int32_t bval;
+            if (!big) {
+                bkey = __shfl_sync(FULL, wkey, rel & 31);
+                bval = __shfl_sync(FULL, wval, rel & 31);
+                bgap = __shfl_sync(FULL, wgap, rel & 31);
+                nkey = __shfl_sync(FULL, wkey, (rel + 1) & 31);
+            } else {
+                bkey = 0; bval = -1; bgap = 0; nkey = INF;
+                if (act && o_ref) {
+                    if (rel >= 0) { const TabEntry b = tab[tcur + uint32_t(rel)]; bkey = b.key; bval = b.val; bgap = b.gap; }
+                    if (tcur + uint32_t(rel + 1) < t1) nkey = tab[tcur + uint32_t(rel + 1)].key;
+                }
+            }
+            if (rel < 0) { bkey = b0_key; bval = b0_val; bgap = b0_gap; }
+            const bool is_m = op_is_match(o_op);
+            const bool last = j == o_ce - o_cp;
+            const uint32_t pstart = j ? bkey : o_p;
+            const uint32_t plen = (last ? o_e : nkey) - pstart;
+            const bool ref_piece = act && o_ref;
+            const bool some = ref_piece && bval >= 0;
+            // ---- 4. sequential state as prefix-ORs over the pieces (src/liftover_read_alignment.rs:84-100)
+            const uint32_t cand_mask = __ballot_sync(FULL, some && is_m);  // pieces that can set ref2_start_pos
+            const uint32_t some_mask = __ballot_sync(FULL, some);           // pieces that set ref2_end_pos
+            const bool start_incl = start_set || (cand_mask & lanes_le(lane)) != 0u;
+            const bool seen_excl = some_seen || (some_mask & lanes_lt(lane)) != 0u;
+            if (!start_set && cand_mask) {
+                start = __shfl_sync(FULL, bval + int32_t(pstart - bkey), __ffs(cand_mask) - 1);
+                start_set = true;
+            }
+            some_seen = some_seen || some_mask != 0u;
+            uint32_t a_len = 0, b_op = 0, b_len = 0;
+            if (ref_piece) {
+                if (some) {
+                    if (start_incl) {
+                        b_op = is_m ? uint32_t(OP_M) : o_op;  // D stays D, N stays N, M/=/X become M (:103-107)
+                        b_len = plen;
+                        // the deletion between the previous aligned run and this one (:91-96): only the first piece
+                        // inside a block can see a positive distance
+                        if (seen_excl && (j != 0u || o_p == bkey)) a_len = bgap;
+                    }
+                } else if (is_m) {
+                    b_op = (bval == -1) ? uint32_t(OP_I) : uint32_t(OP_S);  // None block: insertion (:111-115); no block: clip (:117-123)
+                    b_len = plen;
+                }
+            } else if (act) {  // I/S/H transfer verbatim (:157-160)
+                b_op = o_op;
+                b_len = o_len;
+            }
+            sink.push2(lane, a_len, b_op, b_len);
+        }
+        // ---- move the cursor behind the chunk: entries with key <= chunk_end are passed
+        uint32_t n_le;
+        if (!big) {
+            const uint32_t k_next = __shfl_sync(FULL, wkey, nwin & 31u);  // (nwin < 32 here)
+            n_le = nwin + ((k_next == chunk_end) ? 1u : 0u);
+            if (n_le) {
+                b0_key = __shfl_sync(FULL, wkey, n_le - 1u);
+                b0_val = __shfl_sync(FULL, wval, n_le - 1u);
+                b0_gap = __shfl_sync(FULL, wgap, n_le - 1u);
+            }
+        } else {
+            n_le = warp_table_bound<true>(tab, tcur, t1, chunk_end, lane) - tcur;
+            const TabEntry b = tab[tcur + n_le - 1u];
+            b0_key = b.key; b0_val = b.val; b0_gap = b.gap;
+        }
+        tcur += n_le;
+        p_base = chunk_end;
+    }
+    *start_out = start;
+    return start_set;
+}
+
+// a4 + a6 + a8 for entry t of DevWork::long_list: the pair was prepared by lift_pair_body (strand logic, position on the
+// table's strand, left shift for reverse-strand contig segments) and parked with ST_PENDING_LIFT:
+//   pair_pos = contig position, pair_n_out = ops, pair_out_off = where they start in scratch, or ~0 = the segment's own
+//   CIGAR in the batch pool (read backwards for a reverse-strand contig segment whose left shift is switched off).
+__device__ __forceinline__ void lift_long_pair_body(const DevStatic& S, const DevBatch& B, const DevWork& W, DevTotals* T, uint32_t p, uint32_t lane,
+                                                    uint32_t stage_mask) {
+    const uint32_t s = W.pair_rseg[p], g = W.pair_seg[p];
+    const uint32_t r = W.rseg_read[s];
+    const bool contig_fwd = S.seg_is_fwd[g] != 0;
+    const uint64_t slot0 = W.pair_slot_begin[p];
+    const uint32_t cap_b = W.pair_cap_b[p];
+    uint32_t* buf_b = W.scratch + slot0;
+    const uint32_t n = W.pair_n_out[p];
+    const uint64_t in_off = W.pair_out_off[p];
+    const bool raw = in_off == ~0ull;
+    const uint32_t* in = raw ? B.cigar + B.rseg_cigar_begin[s] : W.scratch + in_off;
+    const uint32_t cpos = uint32_t(W.pair_pos[p]);
+    WarpSink sink(buf_b, cap_b);
+    int32_t start = 0;
+    const bool some = warp_liftover(in, n, raw && !contig_fwd, cpos, S.table, S.seg_tab_begin[g], S.seg_tab_begin[g + 1], sink, lane, &start);
+    sink.finish(lane);
+    int status = ST_LIFTED;
+    if (sink.overflow) status = ST_ERR_CAPACITY;
+    else if (!some) status = ST_NONE;
+    else if (W.rseg_read_len[s] != B.read_seq_len[r]) status = ST_ERR_LENGTH;  // (:204-229, see lift_pair_body)
+    const bool ok = status == ST_LIFTED;
+    const int64_t rpos = int64_t(start) + int64_t(sink.lead_del_shift);
+    if (lane == 0u) {
+        if (ok && sink.mixed_cluster && (stage_mask & 4u)) {  // a9 is not the identity: worklist of simplify_pairs_kernel
+            status = ST_PENDING_SIMPLIFY;
+            W.simplify_list[atomicAdd(&T->n_simplify, 1u)] = p;
+        }
+        W.pair_status[p] = int8_t(status);
+        W.pair_pos[p] = ok ? rpos : 0;
+        W.pair_n_out[p] = ok ? sink.n : 0u;
+        W.pair_out_off[p] = slot0;
+        W.pair_bin[p] = ok ? reg2bin(rpos, rpos + int64_t(sink.ref_span)) : uint16_t(0);
+    }
+}
+
+}  // namespace ptl

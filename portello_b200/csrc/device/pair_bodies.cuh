@@ -13,7 +13,7 @@ namespace ptl {
 __device__ __forceinline__ void totals_reset(DevTotals* T) {
     T->n_pairs = 0; T->scratch_needed = 0; T->n_records = 0; T->n_cigar_out = 0; T->n_lifted = 0; T->n_errors = 0;
     T->first_error_read = 0x7fffffffffffffffLL; T->first_error_status = 0; T->overflow = 0; T->n_in_ops = 0; T->n_base_bytes = 0;
-    T->n_simplify = 0;
+    T->n_simplify = 0; T->n_long = 0;
 }
 
 // =================================================================================================== segment tables
@@ -241,6 +241,17 @@ __device__ __forceinline__ void lift_pair_body(const DevStatic& S, const DevBatc
         }
     }
     rpos = cpos;
+    // ---- long CIGARs: the liftover is finished by the warp-cooperative kernel (lift_warp.cuh), lanes over ops
+    if ((stage_mask & 2u) && usable && !err && cur.n > W.long_ops) {
+        W.pair_status[p] = int8_t(ST_PENDING_LIFT);
+        W.pair_flip[p] = need_flip;
+        W.pair_pos[p] = cpos;
+        W.pair_n_out[p] = cur.n;
+        W.pair_out_off[p] = cur_is_a ? uint64_t(buf_a - W.scratch) : ~0ull;  // ~0: the segment's own CIGAR in the batch pool
+        W.long_list[atomicAdd(&T->n_long, 1u)] = p;
+        n_base_bytes += cnt.base_bytes;
+        return;
+    }
     // ---- a6: liftover (:179-183) + length check (:204-229).  The lifted CIGAR consumes exactly the read bases of the
     //      segment CIGAR (every read-consuming op is re-emitted as M/I/S; the left shift preserves them too), so the
     //      reference's check `seq_len == read length of the lifted CIGAR` is decided by the input CIGAR's read length.

@@ -15,6 +15,9 @@
 
 using namespace ptl;
 
+// emul_warp.cpp: lift_long_pairs_kernel under the 32-lane lock-step shim
+void emul_lift_long_pairs(const ptl::DevStatic& S, const ptl::DevBatch& B, const ptl::DevWork& W, ptl::DevTotals* T, uint32_t stage_mask);
+
 namespace {
 
 template <class T>
@@ -44,6 +47,7 @@ struct EmulSlot {
 struct ptl_ctx {
     std::string err;
     std::vector<EmulSlot> slots;
+    uint32_t long_pair_ops = 64;
     // static state
     std::vector<uint8_t> ref;
     std::vector<uint64_t> chrom_off;
@@ -178,6 +182,9 @@ int run_batch(ptl_ctx* ctx, EmulSlot& sl, const ptl_batch* b, uint32_t stage_mas
     W.pair_rseg = pair_rseg.data(); W.pair_seg = pair_seg.data(); W.pair_slot_begin = pair_slot_begin.data(); W.pair_cap_b = pair_cap_b.data();
     W.pair_status = pair_status.data(); W.pair_flip = pair_flip.data(); W.pair_pos = pair_pos.data(); W.pair_n_out = pair_n_out.data();
     W.pair_bin = pair_bin.data(); W.pair_out_off = pair_out_off.data(); W.simplify_list = simplify_list.data();
+    std::vector<uint32_t> long_list(np + 1);
+    W.long_list = long_list.data();
+    W.long_ops = ctx->long_pair_ops;
     for (uint32_t s = 0; s < ns; ++s) pair_fill_body(S, B, W, s);
     pair_slot_begin[np] = 0;
     exclusive_scan(pair_slot_begin.data(), size_t(np) + 1);
@@ -192,6 +199,7 @@ int run_batch(ptl_ctx* ctx, EmulSlot& sl, const ptl_batch* b, uint32_t stage_mas
         if (stage_mask == 7u) lift_pair_body<true>(S, B, W, &T, p, true, stage_mask, in_ops, base_bytes);
         else lift_pair_body<false>(S, B, W, &T, p, true, stage_mask, in_ops, base_bytes);
     }
+    if (stage_mask & 2u) emul_lift_long_pairs(S, B, W, &T, stage_mask);
     if ((stage_mask & 6u) == 6u)
         for (uint32_t t = 0; t < T.n_simplify; ++t) simplify_pair_body(S, B, W, t, true, base_bytes);
     T.n_in_ops = in_ops;
@@ -335,6 +343,18 @@ int ptl_emul_lift_wait(ptl_ctx* ctx, int slot, ptl_result* out) {
     if (sl->res.n_errors)
         return fail(ctx, PTL_ERR_LIFT_PANIC, "the reference would panic on read " + std::to_string(sl->res.first_error_read) + " (status " +
                                                  std::to_string(sl->res.first_error_status) + ")");
+    return PTL_OK;
+}
+int ptl_emul_set_long_pair_ops(ptl_ctx* ctx, uint32_t n_ops) {
+    if (!ctx) return PTL_ERR_INVALID_ARG;
+    ctx->long_pair_ops = n_ops;
+    return PTL_OK;
+}
+// pairs of the last batch that went through the warp-cooperative liftover
+int ptl_emul_slot_long_pairs(ptl_ctx* ctx, int slot, uint64_t* out) {
+    EmulSlot* sl = get_slot(ctx, slot);
+    if (!sl || !out || !sl->ran) return PTL_ERR_INVALID_ARG;
+    *out = sl->totals.n_long;
     return PTL_OK;
 }
 // counters of the last batch: n_pairs, n_lifted, n_in_ops, n_out_ops, base bytes compared, scratch ops

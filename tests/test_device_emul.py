@@ -1,6 +1,7 @@
 """CPU parity of the KERNEL LOGIC: the product's per-index device bodies (pair_bodies.cuh, lift_device.cuh), compiled for
 the host under a one-lane SIMT shim (tests/emul), against the oracle — same C-ABI, same seeded inputs, bit-exact.
 The GPU itself (32 lanes in lock step, scans, record emission, streams) is covered by the -m gpu tests."""
+import ctypes as C
 import json
 import os
 
@@ -212,3 +213,101 @@ def test_emulated_malformed_batches_are_rejected(emul):
             helpers.lift_c(ectx, b2)
         assert e.value.code == abi.PTL_ERR_INVALID_ARG, what
     assert helpers.lift_c(ectx, helpers.pack(s).c).n_lifted > 0  # the context stays usable
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Warp-cooperative liftover (lift_warp.cuh): 32 host threads in lock step (tests/emul/cuda_shim_warp.hpp).  Slow
+# (~13 us per warp collective), so the cases are small; ptl_set_long_pair_ops(0) sends EVERY pair down that path.
+def long_pairs(emul, ctx):
+    out = C.c_uint64(0)
+    assert emul.dll.ptl_emul_slot_long_pairs(ctx.h, 0, C.byref(out)) == 0
+    return int(out.value)
+
+
+@pytest.mark.parametrize("v", G["liftover"], ids=[f"warp-liftover{i}" for i in range(len(G["liftover"]))])
+def test_emulated_warp_liftover_vectors(emul, v):
+    ctx = abi.Context(emul, 0, 1)
+    ctx.set_long_pair_ops(0)
+    c2r = v["c2r"] if v["c2r"] is not None else "100S"
+    contig_len = helpers.cigar_read_len(c2r)
+    segs, batch = helpers.single_pair_case(c2r, v["c2r_pos"], True, contig_len, None, v["pos"], v["cigar"], [], helpers.cigar_read_len(v["cigar"]))
+    ctx.set_contig_segments(segs)
+    res = ctx.lift(batch, stage_mask=abi.STAGE_LIFTOVER)
+    assert long_pairs(emul, ctx) == 1
+    if v["expect"] is None:
+        assert res.n_records == 0 and res.n_pairs == 1 and res.n_lifted == 0, v["src"]
+    else:
+        assert res.n_records == 1, v["src"]
+        assert (int(res.rec_pos[0]), res.record_cigar(0)) == (v["expect"]["pos"], v["expect"]["cigar"]), v["src"]
+
+
+@pytest.mark.parametrize("name,kw,long_ops", [
+    ("tiny", dict(n_reads=500), 0),
+    ("tiny", dict(seed=53, n_reads=400, rev_contig_frac=0.7, read_cluster_frac=0.2), 0),
+    ("tiny", dict(seed=11, chrom_len=3_000_000, contigs_per_chrom=3, junction_per_mb=8, n_reads=400), 0),
+    ("stress", dict(n_reads=40), 0),
+    ("stress", dict(n_reads=60, seed=77), 64),
+], ids=["tiny", "tiny-reverse-clusters", "tiny-junctions", "stress-all", "stress-long-only"])
+def test_emulated_warp_liftover_matches_oracle(emul, name, kw, long_ops):
+    s = synth.make(name, **kw)
+    pb = helpers.pack(s)
+    ro = helpers.lift_c(helpers.oracle_context(s), pb.c)
+    ectx = emul_context(emul, s)
+    ectx.set_long_pair_ops(long_ops)
+    re = helpers.lift_c(ectx, pb.c)
+    d = re.diff(ro)
+    assert d is None, d
+    n_long = long_pairs(emul, ectx)
+    assert n_long > 0 and (long_ops > 0 or n_long >= re.n_lifted)
+
+
+@pytest.mark.parametrize("mask", [2, 3, 6])
+def test_emulated_warp_liftover_stage_masks(emul, mask):
+    s = synth.make("tiny", seed=23, n_reads=300)
+    pb = helpers.pack(s)
+    ro = helpers.lift_c(helpers.oracle_context(s), pb.c, mask)
+    ectx = emul_context(emul, s)
+    ectx.set_long_pair_ops(0)
+    re = helpers.lift_c(ectx, pb.c, mask)
+    d = re.diff(ro)
+    assert d is None, d
+    assert long_pairs(emul, ectx) > 0
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_emulated_warp_liftover_fuzz(emul, oracle, seed):
+    """Adversarial CIGARs (every op kind, zero lengths, edge indels, Pads) through the warp path."""
+    chroms, segs, batch = make_case(7000 + seed, n_reads=120)
+    octx, ectx = abi.Context(oracle, 0, 1), abi.Context(emul, 0, 1)
+    ectx.set_long_pair_ops(0)
+    for ctx in (octx, ectx):
+        ctx.set_reference(chroms)
+        ctx.set_contig_segments(segs)
+    ro = octx.lift(batch, allow_panic=True)
+    re = ectx.lift(batch, allow_panic=True)
+    d = re.diff(ro)
+    assert d is None, d
+    assert re.first_error_read == ro.first_error_read and re.first_error_status == ro.first_error_status
+
+
+@pytest.mark.parametrize("n_indels,read_cigar", [
+    (40, "3S5000=2I1000=3D2500="),       # one op crossing > 64 table keys: several piece rounds, a `big` window
+    (120, "10=1X4000=5D30=7I4000=20S"),
+    (33, "2000=1I2000="),
+], ids=["40", "120", "33"])
+def test_emulated_warp_liftover_many_keys_per_op(emul, oracle, n_indels, read_cigar):
+    c2r = "".join(f"{40 + (k % 7)}={1 + k % 3}{'ID'[k % 2]}" for k in range(n_indels)) + "9000="
+    contig_len = helpers.cigar_read_len(c2r)
+    rlen = helpers.cigar_read_len(read_cigar)
+    ref = np.frombuffer(b"ACGT" * ((helpers.cigar_ref_len(c2r) + 200) // 4 + 1), dtype=np.uint8).copy()
+    out = []
+    for L, long_ops in ((oracle, 64), (emul, 0), (emul, 1 << 30)):
+        segs, batch = helpers.single_pair_case(c2r, 100, True, contig_len, None, 17, read_cigar, [], rlen)
+        ctx = abi.Context(L, 0, 1)
+        ctx.set_long_pair_ops(long_ops)
+        ctx.set_reference([ref])
+        ctx.set_contig_segments(segs)
+        r = ctx.lift(batch, stage_mask=abi.STAGE_LIFTOVER)
+        assert r.n_records == 1
+        out.append((int(r.rec_pos[0]), r.record_cigar(0)))
+    assert out[0] == out[1] == out[2], out

@@ -108,11 +108,13 @@ def make_case(seed, n_contigs=6, n_reads=400, zero_prob=0.05):
     return chroms, segs, batch
 
 
+@pytest.mark.parametrize("long_ops", [64, 0], ids=["default", "warp-all"])
 @pytest.mark.parametrize("seed", range(12))
-def test_fuzz_full_path(seed, oracle):
+def test_fuzz_full_path(seed, oracle, long_ops):
     chroms, segs, batch = make_case(1000 + seed)
     octx = abi.Context(oracle, 0, 1)
     gctx = lib.GpuContext(0, 1)
+    gctx.set_long_pair_ops(long_ops)
     for ctx in (octx, gctx):
         ctx.set_reference(chroms)
         ctx.set_contig_segments(segs)
@@ -125,11 +127,13 @@ def test_fuzz_full_path(seed, oracle):
     gctx.close()
 
 
+@pytest.mark.parametrize("long_ops", [64, 0], ids=["default", "warp-all"])
 @pytest.mark.parametrize("mask", [1, 2, 3, 6])
-def test_fuzz_stage_masks(mask, oracle):
+def test_fuzz_stage_masks(mask, oracle, long_ops):
     chroms, segs, batch = make_case(77 + mask, n_reads=250)
     octx = abi.Context(oracle, 0, 1)
     gctx = lib.GpuContext(0, 1)
+    gctx.set_long_pair_ops(long_ops)
     for ctx in (octx, gctx):
         ctx.set_reference(chroms)
         ctx.set_contig_segments(segs)

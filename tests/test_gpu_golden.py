@@ -20,8 +20,10 @@ def gpu():
     ctx.close()
 
 
+@pytest.mark.parametrize("long_ops", [64, 0], ids=["thread", "warp"])
 @pytest.mark.parametrize("v", G["liftover"], ids=[f"liftover{i}" for i in range(len(G["liftover"]))])
-def test_liftover_vectors(gpu, v):
+def test_liftover_vectors(gpu, v, long_ops):
+    gpu.set_long_pair_ops(long_ops)  # 0: the warp-cooperative liftover (lift_warp.cuh) instead of the per-thread walk
     c2r = v["c2r"] if v["c2r"] is not None else "100S"  # an empty map: a segment whose CIGAR has no aligned run
     contig_len = helpers.cigar_read_len(c2r)
     segs, batch = helpers.single_pair_case(c2r, v["c2r_pos"], True, contig_len, None, v["pos"], v["cigar"], [], helpers.cigar_read_len(v["cigar"]))
@@ -80,3 +82,27 @@ def test_tree_map_vectors(gpu, oracle):
     keys, vals = gpu.get_segment_table(0)
     assert [list(map(int, keys)), list(map(int, vals))] == [[2, 4, 5, 6], [9, -1, 11, -1]]
     assert oracle.tree_map(9, "2H2M1I1M", False) == [[2, 9], [4, None], [5, 11], [6, None]]
+
+
+@pytest.mark.parametrize("n_indels,read_cigar", [
+    (40, "3S5000=2I1000=3D2500="),       # one op crossing > 64 table keys: several piece rounds, a `big` window
+    (120, "10=1X4000=5D30=7I4000=20S"),
+    (33, "2000=1I2000="),
+], ids=["40", "120", "33"])
+def test_warp_liftover_many_keys_per_op(oracle, n_indels, read_cigar):
+    c2r = "".join(f"{40 + (k % 7)}={1 + k % 3}{'ID'[k % 2]}" for k in range(n_indels)) + "9000="
+    contig_len = helpers.cigar_read_len(c2r)
+    rlen = helpers.cigar_read_len(read_cigar)
+    ref = np.frombuffer(b"ACGT" * ((helpers.cigar_ref_len(c2r) + 200) // 4 + 1), dtype=np.uint8).copy()
+    out = []
+    for L, long_ops in ((oracle, 64), (lib.load(), 0), (lib.load(), 1 << 30)):
+        segs, batch = helpers.single_pair_case(c2r, 100, True, contig_len, None, 17, read_cigar, [], rlen)
+        ctx = abi.Context(L, 0, 1)
+        ctx.set_long_pair_ops(long_ops)
+        ctx.set_reference([ref])
+        ctx.set_contig_segments(segs)
+        r = ctx.lift(batch, stage_mask=abi.STAGE_LIFTOVER)
+        assert r.n_records == 1
+        out.append((int(r.rec_pos[0]), r.record_cigar(0)))
+        ctx.close()
+    assert out[0] == out[1] == out[2], out

@@ -10,10 +10,12 @@ from portello_b200 import abi, lib, synth
 pytestmark = pytest.mark.gpu
 
 
-def both(s, stage_mask=abi.STAGE_ALL, first=0, count=None):
+def both(s, stage_mask=abi.STAGE_ALL, first=0, count=None, long_ops=None):
     pb = helpers.pack(s, first, count)
     octx = helpers.oracle_context(s)
     gctx = helpers.gpu_context(s)
+    if long_ops is not None:
+        gctx.set_long_pair_ops(long_ops)
     ro = helpers.lift_c(octx, pb.c, stage_mask)
     rg = helpers.lift_c(gctx, pb.c, stage_mask)
     return ro, rg, octx, gctx, pb
@@ -25,9 +27,11 @@ def both(s, stage_mask=abi.STAGE_ALL, first=0, count=None):
     ("config1", {}),
     ("stress", dict(n_reads=1500)),
 ], ids=["tiny", "tiny-junctions", "config1", "stress"])
-def test_full_path_parity(name, kw):
+@pytest.mark.parametrize("long_ops", [None, 0, 1 << 30], ids=["default", "warp-all", "thread-all"])
+def test_full_path_parity(name, kw, long_ops):
+    """long_ops: which pairs take the warp-cooperative liftover (default: CIGARs over 64 ops; 0: all; 2^30: none)."""
     s = synth.make(name, **kw)
-    ro, rg, octx, gctx, pb = both(s)
+    ro, rg, octx, gctx, pb = both(s, long_ops=long_ops)
     assert ro.n_errors == 0
     d = rg.diff(ro)
     assert d is None, d
@@ -45,9 +49,10 @@ def test_full_path_parity(name, kw):
 
 @pytest.mark.parametrize("mask", [abi.STAGE_LEFT_SHIFT, abi.STAGE_LIFTOVER, abi.STAGE_LEFT_SHIFT | abi.STAGE_LIFTOVER,
                                   abi.STAGE_LIFTOVER | abi.STAGE_SIMPLIFY])
-def test_stage_parity(mask):
+@pytest.mark.parametrize("long_ops", [None, 0], ids=["default", "warp-all"])
+def test_stage_parity(mask, long_ops):
     s = synth.make("tiny", seed=23, n_reads=4000)
-    ro, rg, *_ = both(s, mask)
+    ro, rg, *_ = both(s, mask, long_ops=long_ops)
     d = rg.diff(ro)
     assert d is None, d
 
