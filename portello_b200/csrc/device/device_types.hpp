@@ -84,7 +84,7 @@ struct DevWork {
     uint32_t* rseg_read = nullptr;       // owning read
     uint32_t* rseg_pair_begin = nullptr; // [n_rsegs+1] (count, then exclusive scan in place)
     int64_t* rseg_ref_len = nullptr;     // get_cigar_ref_offset of the segment
-    uint32_t* rseg_n_id = nullptr;       // number of I/D ops of the segment CIGAR (slot bounds)
+    uint32_t* rseg_n_id = nullptr;       // number of non-match ops (I, D, N, S, H, P) of the segment CIGAR (slot bounds)
     uint32_t* rseg_read_len = nullptr;   // read bases consumed by the segment CIGAR incl. hard clips (length check)
     // per pair
     uint32_t pair_cap = 0;

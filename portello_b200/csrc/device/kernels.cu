@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(LIFT_BLOCK, LIFT_MIN_BLOCKS) lift_pairs_kernel
 }
 
 // a6 + a8 for the worklist of long pairs: one warp per pair, lanes over CIGAR ops (lift_warp.cuh).
-__global__ void __launch_bounds__(128) lift_long_pairs_kernel(DevStatic S, DevBatch B, DevWork W, DevTotals* T, uint32_t stage_mask) {
+__global__ void __launch_bounds__(128, 4) lift_long_pairs_kernel(DevStatic S, DevBatch B, DevWork W, DevTotals* T, uint32_t stage_mask) {
     const uint32_t n = min(T->n_long, W.pair_cap);
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -396,7 +396,7 @@ void launch_lift(const DevStatic& S, const DevBatch& B, const DevWork& W, char* 
     if (stage_mask == 7u) lift_pairs_kernel<true><<<(W.pair_cap + LIFT_BLOCK - 1) / LIFT_BLOCK, LIFT_BLOCK, 0, st>>>(S, B, W, T, stage_mask);
     else lift_pairs_kernel<false><<<(W.pair_cap + LIFT_BLOCK - 1) / LIFT_BLOCK, LIFT_BLOCK, 0, st>>>(S, B, W, T, stage_mask);
     ++*launches;
-    if (stage_mask & 2u) {
+    if ((stage_mask & 2u) || stage_mask == 1u) {
         // worklist length is only known on the device: a fixed grid of warps strides over it
         const unsigned blocks = unsigned(std::min<uint64_t>((uint64_t(W.pair_cap) + 3) / 4, 148ull * 16));
         lift_long_pairs_kernel<<<blocks, 128, 0, st>>>(S, B, W, T, stage_mask);

@@ -23,6 +23,7 @@
 
 #include "cigar_ops.cuh"
 #include "device_types.hpp"
+#include "lift_device.cuh"  // ReadBases, walk_homology8, PairCounters
 
 namespace ptl {
 
@@ -352,10 +353,171 @@ __device__ __forceinline__ bool warp_liftover(const uint32_t* __restrict__ in, u
     return start_set;
 }
 
-// a4 + a6 + a8 for entry t of DevWork::long_list: the pair was prepared by lift_pair_body (strand logic, position on the
-// table's strand, left shift for reverse-strand contig segments) and parked with ST_PENDING_LIFT:
-//   pair_pos = contig position, pair_n_out = ops, pair_out_off = where they start in scratch, or ~0 = the segment's own
-//   CIGAR in the batch pool (read backwards for a reverse-strand contig segment whose left shift is switched off).
+// ------------------------------------------------------------------------------------------------------------------
+// a5 for one pair, all 32 lanes: left_shift_indels (lib/rust-vc-utils/.../shift_indels/left_shift_indels.rs:17-39) with
+// CigarShiftBuilder in Left mode (cigar_indel_shifter.rs:45-164), op-parallel.
+//
+// The sequential builder is a chain of EVENTS: "close" (an I/D cluster ends: emit M(match_block - shift), I, D and carry
+// `shift` matched bases over it) and "other" (a non-match, non-indel op or the end: flush the match block, emit the op).
+//   pass A  lanes over ops: scans give the (ref, read) heads; ballots find cluster starts / ends; every event is written
+//           to `ev` as 6 words {CLOSE | op word, matches since the previous event, ins, del, ref_end, read_end}
+//   pass B  lanes over events: the walk bound limit_k = min(max_left_k, gap_k + limit_{k-1}) and the carried match block
+//           carry_k = min(carry_{k-1} + gap_k, homology_k) are both scans of the functions x -> min(x + a, b), which
+//           compose associatively; the homology walks of 32 clusters run together (walk_homology8); each event's
+//           output ops replace its record in place
+//   pass C  the <= 3 ops per event stream through the WarpSink (edge clean-up + compression)
+// Returns the number of base bytes compared by this lane; *err is uniform.
+struct MinPlus {
+    uint32_t a, b;  // x -> min(x + a, b); identity = (0, kMpInf)
+};
+constexpr uint32_t kMpInf = 0x7fffffffu;
+__device__ __forceinline__ MinPlus mp_then(MinPlus f, MinPlus g) { return MinPlus{f.a + g.a, min(f.b + g.a, g.b)}; }  // f first, then g
+__device__ __forceinline__ MinPlus warp_incl_scan_mp(MinPlus v, uint32_t lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        MinPlus o;
+        o.a = __shfl_up_sync(FULL, v.a, d);
+        o.b = __shfl_up_sync(FULL, v.b, d);
+        if (int(lane) >= d) v = mp_then(o, v);
+    }
+    return v;
+}
+__device__ __forceinline__ int msb(uint32_t m) { return 31 - __clz(m); }
+
+constexpr uint32_t kEvClose = 0xffffffffu;
+constexpr uint32_t kEvWords = 6;
+
+__device__ __forceinline__ void warp_left_shift(const uint32_t* __restrict__ in, uint32_t n, bool reversed, uint32_t ref_pos,
+                                                const uint8_t* __restrict__ ref_seq, uint32_t ref_len, const ReadBases& read,
+                                                const uint64_t* __restrict__ win, uint32_t n_win, uint32_t* __restrict__ ev, uint32_t ev_cap,
+                                                WarpSink& sink, uint32_t lane, PairCounters& cnt, int* err) {
+    const uint32_t lt = lanes_lt(lane);
+    // ---- pass A
+    uint32_t n_ev = 0, n_clus = 0;
+    uint32_t ref_base = ref_pos, read_base = 0;
+    bool c_open = false;
+    uint32_t c_blk_ref = 0, c_blk_read = 0, c_del = 0, c_ins = 0, c_gap = 0;
+    for (uint32_t base = 0; base <= n; base += 32u) {  // index n = the sentinel that closes a trailing cluster and flushes
+        const uint32_t i = base + lane;
+        const uint32_t c = (i < n) ? in[reversed ? (n - 1u - i) : i] : uint32_t(OP_S);
+        const uint32_t op = c & 0xfu, len = c >> 4;
+        const bool is_id = op == OP_I || op == OP_D;
+        // 0 transparent (empty I/D, lanes past the sentinel), 1 indel, 2 match op, 3 other op
+        const uint32_t kind = (i > n) ? 0u : is_id ? (len ? 1u : 0u) : (op_is_match(op) ? 2u : 3u);
+        const uint32_t radv = (i < n) ? op_ref_adv(c) : 0u, qadv = (i < n) ? op_read_adv(c) : 0u;
+        const uint32_t dlen = (kind == 1u && op == OP_D) ? len : 0u, ilen = (kind == 1u && op == OP_I) ? len : 0u;
+        const uint32_t mlen = (kind == 2u) ? len : 0u;
+        const uint32_t r_in = warp_incl_scan(radv, lane), q_in = warp_incl_scan(qadv, lane);
+        const uint32_t d_in = warp_incl_scan(dlen, lane), i_in = warp_incl_scan(ilen, lane), m_in = warp_incl_scan(mlen, lane);
+        const uint32_t ref_ex = ref_base + r_in - radv, read_ex = read_base + q_in - qadv;
+        const uint32_t d_ex = d_in - dlen, i_ex = i_in - ilen, m_ex = m_in - mlen;
+        const uint32_t nt_mask = __ballot_sync(FULL, kind != 0u), idl_mask = __ballot_sync(FULL, kind == 1u);
+        const uint32_t closer_mask = nt_mask & ~idl_mask;
+        const uint32_t pm = nt_mask & lt;
+        const bool in_prev = pm ? ((idl_mask >> msb(pm)) & 1u) != 0u : c_open;  // is a cluster open in front of this op?
+        const uint32_t start_mask = __ballot_sync(FULL, kind == 1u && !in_prev);
+        const bool is_close = kind >= 2u && in_prev, is_other = kind == 3u;
+        const uint32_t close_mask = __ballot_sync(FULL, is_close), other_mask = __ballot_sync(FULL, is_other);
+        const uint32_t ev_mask = close_mask | other_mask;
+        // the cluster a close lane ends: started in this chunk behind the last closer, or carried in
+        const uint32_t sm = start_mask & lt, cm = closer_mask & lt;
+        const bool started_here = sm != 0u && (cm == 0u || msb(sm) > msb(cm));
+        const int s_lane = started_here ? msb(sm) : 0;
+        const uint32_t s_ref = __shfl_sync(FULL, ref_ex, s_lane), s_read = __shfl_sync(FULL, read_ex, s_lane);
+        const uint32_t s_dex = __shfl_sync(FULL, d_ex, s_lane), s_iex = __shfl_sync(FULL, i_ex, s_lane);
+        const uint32_t blk_ref = started_here ? s_ref : c_blk_ref, blk_read = started_here ? s_read : c_blk_read;
+        const uint32_t del = started_here ? d_ex - s_dex : c_del + d_ex, ins = started_here ? i_ex - s_iex : c_ins + i_ex;
+        // matches since the previous event (a match op that closed a cluster counts itself towards the next one)
+        const uint32_t em = ev_mask & lt;
+        const uint32_t e_mex = __shfl_sync(FULL, m_ex, em ? msb(em) : 0);
+        const uint32_t gap = em ? m_ex - e_mex : c_gap + m_ex;
+        const uint32_t n_mine = (is_close ? 1u : 0u) + (is_other ? 1u : 0u);
+        const uint32_t e_in = warp_incl_scan(n_mine, lane);
+        uint32_t at = n_ev + e_in - n_mine;
+        if (is_close) {
+            if (at < ev_cap) {
+                uint32_t* r = ev + size_t(at) * kEvWords;
+                r[0] = kEvClose; r[1] = gap; r[2] = ins; r[3] = del; r[4] = blk_ref + del; r[5] = blk_read + ins;
+            }
+            ++at;
+        }
+        if (is_other && at < ev_cap) {
+            uint32_t* r = ev + size_t(at) * kEvWords;
+            r[0] = c; r[1] = is_close ? 0u : gap; r[2] = 0; r[3] = 0; r[4] = 0; r[5] = 0;
+        }
+        n_ev += __shfl_sync(FULL, e_in, 31);
+        n_clus += __popc(close_mask);
+        // carries into the next chunk
+        const bool open_end = nt_mask ? ((idl_mask >> msb(nt_mask)) & 1u) != 0u : c_open;
+        const uint32_t d_tot = __shfl_sync(FULL, d_in, 31), i_tot = __shfl_sync(FULL, i_in, 31), m_tot = __shfl_sync(FULL, m_in, 31);
+        if (open_end) {
+            const bool started = start_mask != 0u && (closer_mask == 0u || msb(start_mask) > msb(closer_mask));
+            const int sl = started ? msb(start_mask) : 0;
+            const uint32_t o_ref = __shfl_sync(FULL, ref_ex, sl), o_read = __shfl_sync(FULL, read_ex, sl);
+            const uint32_t o_dex = __shfl_sync(FULL, d_ex, sl), o_iex = __shfl_sync(FULL, i_ex, sl);
+            if (started) { c_blk_ref = o_ref; c_blk_read = o_read; c_del = d_tot - o_dex; c_ins = i_tot - o_iex; }
+            else { c_del += d_tot; c_ins += i_tot; }
+        }
+        c_open = open_end;
+        const uint32_t l_mex = __shfl_sync(FULL, m_ex, ev_mask ? msb(ev_mask) : 0);
+        c_gap = ev_mask ? m_tot - l_mex : c_gap + m_tot;
+        ref_base += __shfl_sync(FULL, r_in, 31);
+        read_base += __shfl_sync(FULL, q_in, 31);
+    }
+    if (n_ev > ev_cap) { *err = ST_ERR_CAPACITY; return; }
+    __syncwarp();
+    // ---- pass B: walk bounds, homologies, carried match block; the output ops of an event replace its record
+    const bool have_win = (n_win == n_clus) && n_clus > 0u;
+    uint32_t lim_carry = 0, mb_carry = 0, k_base = 0;
+    bool lane_err = false;
+    for (uint32_t eb = 0; eb < n_ev; eb += 32u) {
+        const uint32_t e = eb + lane;
+        const bool act = e < n_ev;
+        uint32_t w0 = 0, gap = 0, ins = 0, del = 0, ref_end = 0, read_end = 0;
+        uint32_t* r = ev + size_t(act ? e : 0u) * kEvWords;
+        if (act) { w0 = r[0]; gap = r[1]; ins = r[2]; del = r[3]; ref_end = r[4]; read_end = r[5]; }
+        const bool is_close = act && w0 == kEvClose;
+        uint32_t max_left = is_close ? min(ref_end - del, read_end - ins) : 0u;
+        // first access is ref_seq[ref_end-1] / read[read_end-1]; later ones only move down and stay >= 0
+        if (is_close && max_left > 0u && (ref_end > ref_len || read_end > read.len)) { lane_err = true; max_left = 0; }
+        const MinPlus lf = warp_incl_scan_mp(act ? (is_close ? MinPlus{gap, max_left} : MinPlus{0u, 0u}) : MinPlus{0u, kMpInf}, lane);
+        const uint32_t limit = min(lim_carry + lf.a, lf.b);  // (an "other" event flushes the match block: no carry across it)
+        lim_carry = __shfl_sync(FULL, limit, 31);
+        const uint32_t close_mask = __ballot_sync(FULL, is_close);
+        uint32_t hom = 0;
+        bool walking = is_close && limit > 0u;
+        uint64_t w = 0;
+        if (have_win && walking) w = win[k_base + __popc(close_mask & lt)];
+        k_base += __popc(close_mask);
+        while (__any_sync(FULL, walking)) {
+            if (walking) walk_homology8(ref_seq, read, ref_end, read_end, limit, w, have_win, hom, walking, cnt);
+        }
+        const MinPlus cf = warp_incl_scan_mp(act ? (is_close ? MinPlus{gap, hom} : MinPlus{0u, 0u}) : MinPlus{0u, kMpInf}, lane);
+        const uint32_t after = min(mb_carry + cf.a, cf.b);  // match block carried behind this event (:124-131)
+        uint32_t before = __shfl_up_sync(FULL, after, 1);
+        if (lane == 0u) before = mb_carry;
+        mb_carry = __shfl_sync(FULL, after, 31);
+        if (act) {
+            if (is_close) {  // end_indel (:101-148): M(match_block - shift) then nImD
+                r[0] = ((before + gap - after) << 4) | OP_M; r[1] = (ins << 4) | OP_I; r[2] = (del << 4) | OP_D;
+            } else {         // add_other (:155-164): the match block, then the op itself
+                r[0] = ((before + gap) << 4) | OP_M; r[1] = w0; r[2] = 0;
+            }
+        }
+    }
+    if (__any_sync(FULL, lane_err)) { *err = ST_ERR_BOUNDS; return; }
+    __syncwarp();
+    // ---- pass C
+    const uint32_t n_words = 3u * n_ev;
+    for (uint32_t q0 = 0; q0 < n_words; q0 += 32u) {
+        const uint32_t q = q0 + lane;
+        const uint32_t word = (q < n_words) ? ev[size_t(q / 3u) * kEvWords + q % 3u] : 0u;
+        sink.push2(lane, 0u, word & 0xfu, word >> 4);
+    }
+}
+
+// a4 + a5 + a6 + a8 for entry t of DevWork::long_list: lift_pair_body did the strand logic and parked the pair with
+// ST_PENDING_LIFT (pair_pos = start on the table's strand, pair_n_out = ops of the segment CIGAR, pair_flip).
 __device__ __forceinline__ void lift_long_pair_body(const DevStatic& S, const DevBatch& B, const DevWork& W, DevTotals* T, uint32_t p, uint32_t lane,
                                                     uint32_t stage_mask) {
     const uint32_t s = W.pair_rseg[p], g = W.pair_seg[p];
@@ -363,22 +525,80 @@ __device__ __forceinline__ void lift_long_pair_body(const DevStatic& S, const De
     const bool contig_fwd = S.seg_is_fwd[g] != 0;
     const uint64_t slot0 = W.pair_slot_begin[p];
     const uint32_t cap_b = W.pair_cap_b[p];
+    const uint32_t cap_a = uint32_t(W.pair_slot_begin[p + 1] - slot0) - cap_b;
     uint32_t* buf_b = W.scratch + slot0;
-    const uint32_t n = W.pair_n_out[p];
-    const uint64_t in_off = W.pair_out_off[p];
-    const bool raw = in_off == ~0ull;
-    const uint32_t* in = raw ? B.cigar + B.rseg_cigar_begin[s] : W.scratch + in_off;
-    const uint32_t cpos = uint32_t(W.pair_pos[p]);
+    uint32_t* buf_a = buf_b + cap_b;
+    uint32_t n = W.pair_n_out[p];
+    const uint32_t* in = B.cigar + B.rseg_cigar_begin[s];
+    bool reversed = !contig_fwd;  // the CIGAR reversal of :167 is just the read order
+    uint32_t cpos = uint32_t(W.pair_pos[p]);
+    int status = ST_LIFTED;
+    uint32_t span = 0;
+    PairCounters cnt;
+    // ---- a5 on the contig's reverse strand (:168-175)
+    if (!contig_fwd && (stage_mask & 1u)) {
+        const uint32_t ctg = B.rseg_contig[s];
+        const uint64_t rev_off = S.contig_rev_off[ctg];
+        if (rev_off == ~0ull) {
+            status = ST_ERR_BOUNDS;  // Option::unwrap on None (:174)
+        } else {
+            const ReadBases read{B.seq4 + B.read_seq_off[r], B.read_seq_len[r], W.pair_flip[p] != 0};
+            const uint64_t* win = nullptr;
+            uint32_t n_win = 0;
+            if (B.rseg_win_begin) {
+                const uint32_t w0 = B.rseg_win_begin[s];
+                win = B.indel_win + w0;
+                n_win = B.rseg_win_begin[s + 1] - w0;
+            }
+            WarpSink shifted(buf_a, cap_a);
+            int err = 0;
+            warp_left_shift(in, n, true, cpos, S.rev_pool + rev_off, uint32_t(S.contig_len[ctg]), read, win, n_win, buf_b, cap_b / kEvWords, shifted,
+                            lane, cnt, &err);
+            shifted.finish(lane);
+            if (err) status = err;
+            else if (shifted.overflow) status = ST_ERR_CAPACITY;
+            in = buf_a;
+            n = shifted.n;
+            span = shifted.ref_span;
+            reversed = false;
+            cpos += shifted.lead_del_shift;
+        }
+    }
+    if (!(stage_mask & 2u)) {  // stage test: left shift only, hand the shifted CIGAR back
+        if (in != buf_a) {     // nothing to shift: the (possibly reversed) input, verbatim
+            n = min(n, cap_a);
+            for (uint32_t i = lane; i < n; i += 32u) {
+                const uint32_t c = in[reversed ? (W.pair_n_out[p] - 1u - i) : i];
+                buf_a[i] = c;
+                span += op_ref_adv(c);
+            }
+            span = warp_sum(span);
+            in = buf_a;
+            __syncwarp();
+        }
+        if (lane == 0u) {
+            const bool ok = status == ST_LIFTED;
+            W.pair_status[p] = int8_t(status);
+            W.pair_pos[p] = ok ? int64_t(cpos) : 0;
+            W.pair_n_out[p] = ok ? n : 0u;
+            W.pair_out_off[p] = uint64_t(in - W.scratch);
+            W.pair_bin[p] = ok ? reg2bin(cpos, int64_t(cpos) + int64_t(span)) : uint16_t(0);
+        }
+        return;
+    }
+    // ---- a6 + a8
     WarpSink sink(buf_b, cap_b);
     int32_t start = 0;
-    const bool some = warp_liftover(in, n, raw && !contig_fwd, cpos, S.table, S.seg_tab_begin[g], S.seg_tab_begin[g + 1], sink, lane, &start);
-    sink.finish(lane);
-    int status = ST_LIFTED;
-    if (sink.overflow) status = ST_ERR_CAPACITY;
-    else if (!some) status = ST_NONE;
-    else if (W.rseg_read_len[s] != B.read_seq_len[r]) status = ST_ERR_LENGTH;  // (:204-229, see lift_pair_body)
+    if (status == ST_LIFTED) {
+        const bool some = warp_liftover(in, n, reversed, cpos, S.table, S.seg_tab_begin[g], S.seg_tab_begin[g + 1], sink, lane, &start);
+        sink.finish(lane);
+        if (sink.overflow) status = ST_ERR_CAPACITY;
+        else if (!some) status = ST_NONE;
+        else if (W.rseg_read_len[s] != B.read_seq_len[r]) status = ST_ERR_LENGTH;  // (:204-229, see lift_pair_body)
+    }
     const bool ok = status == ST_LIFTED;
     const int64_t rpos = int64_t(start) + int64_t(sink.lead_del_shift);
+    const uint32_t bytes = warp_sum(cnt.base_bytes);
     if (lane == 0u) {
         if (ok && sink.mixed_cluster && (stage_mask & 4u)) {  // a9 is not the identity: worklist of simplify_pairs_kernel
             status = ST_PENDING_SIMPLIFY;
@@ -389,6 +609,7 @@ __device__ __forceinline__ void lift_long_pair_body(const DevStatic& S, const De
         W.pair_n_out[p] = ok ? sink.n : 0u;
         W.pair_out_off[p] = slot0;
         W.pair_bin[p] = ok ? reg2bin(rpos, rpos + int64_t(sink.ref_span)) : uint16_t(0);
+        if (bytes) atomicAdd(&T->n_base_bytes, (unsigned long long)bytes);
     }
 }
 

@@ -87,7 +87,7 @@ __device__ __forceinline__ void pair_count_body(const DevStatic& S, const DevBat
             const uint32_t x = c[i];
             ref_len += op_ref_adv(x);
             read_len += op_read_adv(x);
-            n_id += ((x & 0xfu) == OP_I || (x & 0xfu) == OP_D) ? 1u : 0u;
+            n_id += op_is_match(x & 0xfu) ? 0u : 1u;  // I/D ops, and every other non-match op (each can end a match block)
         }
         W.rseg_ref_len[s] = ref_len;
         W.rseg_n_id[s] = n_id;
@@ -139,7 +139,10 @@ __device__ __forceinline__ void pair_fill_body(const DevStatic& S, const DevBatc
             const uint32_t n_shift = fwd ? n_in : n_in + n_id + 1u;
             //   buffer B doubles as the cluster list of the left shift (3 words per cluster), buffer A keeps 4 words per
             //   mixed cluster of the simplify stage at its top end
-            const uint32_t cap_b = max(n_shift + 2u * n_keys + 4u, fwd ? 0u : 3u * n_id + 4u);
+            //   (a long pair on a reverse-strand segment keeps the 6-word event records of the warp left shift there:
+            //   one per I/D cluster and per other non-match op, plus the end)
+            uint32_t cap_b = max(n_shift + 2u * n_keys + 4u, fwd ? 0u : 3u * n_id + 4u);
+            if (!fwd && n_in > W.long_ops) cap_b = max(cap_b, 6u * (n_id + 1u) + 8u);
             const uint32_t cap_a = cap_b + 6u * (n_id + n_keys) + 8u;
             W.pair_cap_b[p] = cap_b;
             W.pair_slot_begin[p] = uint64_t(cap_a) + cap_b;  // [0,cap_b) = buffer B, [cap_b, cap_b+cap_a) = buffer A
@@ -208,6 +211,13 @@ __device__ __forceinline__ void lift_pair_body(const DevStatic& S, const DevBatc
         }
     }
     bool cur_is_a = false, cur_is_raw = true;
+    // ---- long CIGARs: left shift and liftover run in the warp-cooperative kernel (lift_warp.cuh), lanes over ops
+    //      (the lane stays in this function: the stages below are warp-collective)
+    const bool parked = ((stage_mask & 2u) || stage_mask == 1u) && usable && !err && cur.n > W.long_ops;
+    if (parked) {
+        W.long_list[atomicAdd(&T->n_long, 1u)] = p;
+        usable = false;
+    }
     bool simplify_is_identity = false;
     uint32_t span = 0;  // reference span of the final CIGAR (end = pos + span, :278)
 
@@ -241,17 +251,6 @@ __device__ __forceinline__ void lift_pair_body(const DevStatic& S, const DevBatc
         }
     }
     rpos = cpos;
-    // ---- long CIGARs: the liftover is finished by the warp-cooperative kernel (lift_warp.cuh), lanes over ops
-    if ((stage_mask & 2u) && usable && !err && cur.n > W.long_ops) {
-        W.pair_status[p] = int8_t(ST_PENDING_LIFT);
-        W.pair_flip[p] = need_flip;
-        W.pair_pos[p] = cpos;
-        W.pair_n_out[p] = cur.n;
-        W.pair_out_off[p] = cur_is_a ? uint64_t(buf_a - W.scratch) : ~0ull;  // ~0: the segment's own CIGAR in the batch pool
-        W.long_list[atomicAdd(&T->n_long, 1u)] = p;
-        n_base_bytes += cnt.base_bytes;
-        return;
-    }
     // ---- a6: liftover (:179-183) + length check (:204-229).  The lifted CIGAR consumes exactly the read bases of the
     //      segment CIGAR (every read-consuming op is re-emitted as M/I/S; the left shift preserves them too), so the
     //      reference's check `seq_len == read length of the lifted CIGAR` is decided by the input CIGAR's read length.
@@ -317,7 +316,12 @@ __device__ __forceinline__ void lift_pair_body(const DevStatic& S, const DevBatc
         for (uint32_t i = 0; i < n; ++i) { const uint32_t c = cur.get(i); buf_a[i] = c; span += op_ref_adv(c); }
         cur = OpSource{buf_a, n, false};
     }
-    if (valid) {
+    if (parked) {
+        W.pair_status[p] = int8_t(ST_PENDING_LIFT);
+        W.pair_flip[p] = need_flip;
+        W.pair_pos[p] = cpos;
+        W.pair_n_out[p] = cur.n;
+    } else if (valid) {
         if (err) status = err;
         const bool ok = (status == ST_LIFTED);
         if (ok && deferred) status = ST_PENDING_SIMPLIFY;

@@ -70,3 +70,4 @@ inline int __ffs(unsigned v) { return __builtin_ffs(int(v)); }
 
 // only lane 0 of a warp calls these, and the emulation runs one warp at a time
 inline unsigned int atomicAdd(unsigned int* p, unsigned int v) { const unsigned int o = *p; *p += v; return o; }
+inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { const unsigned long long o = *p; *p += v; return o; }

@@ -261,7 +261,7 @@ def test_emulated_warp_liftover_matches_oracle(emul, name, kw, long_ops):
     assert n_long > 0 and (long_ops > 0 or n_long >= re.n_lifted)
 
 
-@pytest.mark.parametrize("mask", [2, 3, 6])
+@pytest.mark.parametrize("mask", [1, 2, 3, 6])
 def test_emulated_warp_liftover_stage_masks(emul, mask):
     s = synth.make("tiny", seed=23, n_reads=300)
     pb = helpers.pack(s)
@@ -311,3 +311,21 @@ def test_emulated_warp_liftover_many_keys_per_op(emul, oracle, n_indels, read_ci
         assert r.n_records == 1
         out.append((int(r.rec_pos[0]), r.record_cigar(0)))
     assert out[0] == out[1] == out[2], out
+
+
+@pytest.mark.parametrize("v", [x for x in G["shift"] if x["dir"] == "left"], ids=lambda v: "warp-" + v["cigar"])
+def test_emulated_warp_left_shift_vectors(emul, v):
+    """The reference's left_shift_indels vectors through warp_left_shift (lift_warp.cuh)."""
+    ctx = abi.Context(emul, 0, 1)
+    ctx.set_long_pair_ops(0)
+    ref, read = helpers.relabel(v["ref"]), helpers.relabel(v["read"])
+    cig = abi.cigar_from_string(v["cigar"])
+    contig_len = len(ref)
+    pos_fwd = contig_len - (v["pos"] + helpers.cigar_ref_len(v["cigar"]))
+    segs, batch = helpers.single_pair_case(f"{contig_len}=", 0, False, contig_len, ref, pos_fwd, cig[::-1].copy(), abi.pack_seq4(read), len(read),
+                                           read_flag=0, rseg_fwd=0)
+    ctx.set_contig_segments(segs)
+    res = ctx.lift(batch, stage_mask=abi.STAGE_LEFT_SHIFT)
+    assert long_pairs(emul, ctx) == 1
+    assert res.n_records == 1 and int(res.rec_need_flip[0]) == 0
+    assert (int(res.rec_pos[0]), res.record_cigar(0)) == (v["expect"]["pos"], v["expect"]["cigar"]), v["src"]

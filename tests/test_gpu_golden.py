@@ -48,8 +48,10 @@ def test_simplify_vectors(gpu, v):
     assert (int(res.rec_pos[0]), res.record_cigar(0)) == (v["expect"]["pos"], v["expect"]["cigar"]), v["src"]
 
 
+@pytest.mark.parametrize("long_ops", [64, 0], ids=["thread", "warp"])
 @pytest.mark.parametrize("v", [x for x in G["shift"] if x["dir"] == "left"], ids=lambda v: v["cigar"])
-def test_left_shift_vectors(gpu, v):
+def test_left_shift_vectors(gpu, v, long_ops):
+    gpu.set_long_pair_ops(long_ops)  # 0: warp_left_shift (lift_warp.cuh) instead of the per-thread builder
     # The kernel applies the shift on the contig's reverse strand: feed the mirrored alignment so that the kernel's own
     # reversal (rev_pos, reversed CIGAR; src/read_alignment_scanner.rs:163-167) reconstructs the vector's input.
     ref = helpers.relabel(v["ref"])

@@ -50,7 +50,7 @@ def test_full_path_parity(name, kw, long_ops):
 @pytest.mark.parametrize("mask", [abi.STAGE_LEFT_SHIFT, abi.STAGE_LIFTOVER, abi.STAGE_LEFT_SHIFT | abi.STAGE_LIFTOVER,
                                   abi.STAGE_LIFTOVER | abi.STAGE_SIMPLIFY])
 @pytest.mark.parametrize("long_ops", [None, 0], ids=["default", "warp-all"])
-def test_stage_parity(mask, long_ops):
+def test_stage_parity(mask, long_ops):  # (mask 1 = left shift only also runs on the warp path when long_ops = 0)
     s = synth.make("tiny", seed=23, n_reads=4000)
     ro, rg, *_ = both(s, mask, long_ops=long_ops)
     d = rg.diff(ro)
