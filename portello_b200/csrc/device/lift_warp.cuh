@@ -25,6 +25,10 @@
 #include "device_types.hpp"
 #include "lift_device.cuh"  // ReadBases, walk_homology8, PairCounters
 
+#ifndef PTL_ASSERT_UNIFORM
+#define PTL_ASSERT_UNIFORM(v)  // (the lock-step CPU emulation of tests/emul checks warp-uniform state here)
+#endif
+
 namespace ptl {
 
 __device__ __forceinline__ uint32_t lanes_lt(uint32_t lane) { return (1u << lane) - 1u; }
@@ -130,6 +134,7 @@ struct WarpSink {
         n = base + n_heads - 1u;
         const uint32_t mh = __ballot_sync(FULL, headB && op_is_match(b_op));
         if (mh) last_match_idx = int32_t(__shfl_sync(FULL, base + idxB, 31 - __clz(mh)));
+        PTL_ASSERT_UNIFORM(n); PTL_ASSERT_UNIFORM(pend); PTL_ASSERT_UNIFORM(last_match_idx);
     }
 
     // flush + trailing edge (cigar/mod.rs:282-288) + re-merge of what the conversion made adjacent
@@ -145,23 +150,29 @@ struct WarpSink {
         mixed_cluster = __any_sync(FULL, lane_mixed);
         __syncwarp();
         if (overflow || last_match_idx < 0) return;
-        // the tail behind the last match is a handful of ops: every lane walks it, lane 0 writes
-        const uint32_t start = uint32_t(last_match_idx) + 1u;
-        uint32_t w = start, prev = NO_OP;
-        for (uint32_t i = start; i < n; ++i) {
-            uint32_t c = buf[i];
-            uint32_t op = c & 0xfu;
-            if (op == OP_D) { ref_span -= c >> 4; continue; }
-            if (op == OP_I) { op = OP_S; c = (c & ~0xfu) | OP_S; }
-            if (prev != NO_OP && (prev & 0xfu) == op) {
-                if (op != OP_P) prev += c & ~0xfu;
-            } else {
-                if (prev != NO_OP) { if (lane == 0u) buf[w] = prev; ++w; }
-                prev = c;
+        // the tail behind the last match is a handful of ops: lane 0 rewrites it, the others take its counts
+        uint32_t w = n, dropped = 0;
+        if (lane == 0u) {
+            const uint32_t start = uint32_t(last_match_idx) + 1u;
+            uint32_t prev = NO_OP;
+            w = start;
+            for (uint32_t i = start; i < n; ++i) {
+                uint32_t c = buf[i];
+                uint32_t op = c & 0xfu;
+                if (op == OP_D) { dropped += c >> 4; continue; }
+                if (op == OP_I) { op = OP_S; c = (c & ~0xfu) | OP_S; }
+                if (prev != NO_OP && (prev & 0xfu) == op) {
+                    if (op != OP_P) prev += c & ~0xfu;
+                } else {
+                    if (prev != NO_OP) buf[w++] = prev;
+                    prev = c;
+                }
             }
+            if (prev != NO_OP) buf[w++] = prev;
         }
-        if (prev != NO_OP) { if (lane == 0u) buf[w] = prev; ++w; }
-        n = w;
+        n = __shfl_sync(FULL, w, 0);
+        ref_span -= __shfl_sync(FULL, dropped, 0);
+        PTL_ASSERT_UNIFORM(n); PTL_ASSERT_UNIFORM(ref_span);
         __syncwarp();
     }
 };
@@ -348,6 +359,7 @@ __device__ __forceinline__ bool warp_liftover(const uint32_t* __restrict__ in, u
         }
         tcur += n_le;
         p_base = chunk_end;
+        PTL_ASSERT_UNIFORM(tcur); PTL_ASSERT_UNIFORM(p_base); PTL_ASSERT_UNIFORM(b0_key); PTL_ASSERT_UNIFORM(start_set); PTL_ASSERT_UNIFORM(some_seen);
     }
     *start_out = start;
     return start_set;
@@ -464,6 +476,7 @@ __device__ __forceinline__ void warp_left_shift(const uint32_t* __restrict__ in,
         ref_base += __shfl_sync(FULL, r_in, 31);
         read_base += __shfl_sync(FULL, q_in, 31);
     }
+    PTL_ASSERT_UNIFORM(n_ev); PTL_ASSERT_UNIFORM(n_clus); PTL_ASSERT_UNIFORM(c_gap);
     if (n_ev > ev_cap) { *err = ST_ERR_CAPACITY; return; }
     __syncwarp();
     // ---- pass B: walk bounds, homologies, carried match block; the output ops of an event replace its record
@@ -497,6 +510,7 @@ __device__ __forceinline__ void warp_left_shift(const uint32_t* __restrict__ in,
         uint32_t before = __shfl_up_sync(FULL, after, 1);
         if (lane == 0u) before = mb_carry;
         mb_carry = __shfl_sync(FULL, after, 31);
+        PTL_ASSERT_UNIFORM(lim_carry); PTL_ASSERT_UNIFORM(mb_carry); PTL_ASSERT_UNIFORM(k_base);
         if (act) {
             if (is_close) {  // end_indel (:101-148): M(match_block - shift) then nImD
                 r[0] = ((before + gap - after) << 4) | OP_M; r[1] = (ins << 4) | OP_I; r[2] = (del << 4) | OP_D;
@@ -514,6 +528,142 @@ __device__ __forceinline__ void warp_left_shift(const uint32_t* __restrict__ in,
         const uint32_t word = (q < n_words) ? ev[size_t(q / 3u) * kEvWords + q % 3u] : 0u;
         sink.push2(lane, 0u, word & 0xfu, word >> 4);
     }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// a9 for one pair, all 32 lanes: simplify_alignment_indels (src/simplify_alignment_indels.rs:119-156) with
+// CigarBlockInfo::end_indel (:35-111), op-parallel.  `in`/`n`: a cleaned + compressed CIGAR starting at ref_pos.
+//   pass A  lanes over ops: every I/D run (cluster) is summed by scans; the op that ends it emits the rewritten run in
+//           front of itself: nothing, I, D, M1, or for a MIXED cluster (both kinds, not 1/1) the five slots
+//           M(pre) I D M(post) op, whose numbers need bases.  All ops go to `x` (uncompressed, in order); mixed clusters
+//           are listed in `rec` as {blk_ref, blk_read, slot}
+//   pass B  lanes over mixed clusters: trim equal bases from the right first, then from the left (:55-85)
+//   pass C  `x` streams through the sink, which compresses IN PLACE (a run is stored only after the ops it merges were
+//           read, and stored runs never outnumber consumed ops): sink.buf == x
+__device__ __forceinline__ int warp_simplify(const uint32_t* __restrict__ in, uint32_t n, int64_t ref_pos, const uint8_t* __restrict__ ref_seq,
+                                             uint64_t ref_len, const ReadBases& read, uint32_t* __restrict__ x, uint32_t x_cap,
+                                             uint32_t* __restrict__ rec, uint32_t rec_cap, WarpSink& sink, uint32_t lane, PairCounters& cnt) {
+    const uint32_t lt = lanes_lt(lane);
+    // ---- pass A
+    uint32_t n_x = 0, n_mixed = 0;
+    uint32_t ref_base = 0, read_base = 0;  // reference offset from ref_pos, read head
+    bool c_open = false;
+    uint32_t c_blk_ref = 0, c_blk_read = 0, c_del = 0, c_ins = 0;
+    for (uint32_t base = 0; base <= n; base += 32u) {  // index n = a sentinel match op of length 0: closes a trailing cluster
+        const uint32_t i = base + lane;
+        const uint32_t c = (i < n) ? in[i] : 0u;
+        const uint32_t op = c & 0xfu, len = c >> 4;
+        const bool is_id = i < n && (op == OP_I || op == OP_D);
+        const uint32_t kind = (i > n) ? 0u : (is_id ? 1u : 2u);  // 0 past the end, 1 indel, 2 any other op
+        const uint32_t radv = (i < n) ? op_ref_adv(c) : 0u, qadv = (i < n) ? op_read_adv(c) : 0u;
+        const uint32_t dlen = (is_id && op == OP_D) ? len : 0u, ilen = (is_id && op == OP_I) ? len : 0u;
+        const uint32_t r_in = warp_incl_scan(radv, lane), q_in = warp_incl_scan(qadv, lane);
+        const uint32_t d_in = warp_incl_scan(dlen, lane), i_in = warp_incl_scan(ilen, lane);
+        const uint32_t ref_ex = ref_base + r_in - radv, read_ex = read_base + q_in - qadv;
+        const uint32_t d_ex = d_in - dlen, i_ex = i_in - ilen;
+        const uint32_t nt_mask = __ballot_sync(FULL, kind != 0u), idl_mask = __ballot_sync(FULL, kind == 1u);
+        const uint32_t closer_mask = nt_mask & ~idl_mask;
+        const uint32_t pm = nt_mask & lt;
+        const bool in_prev = pm ? ((idl_mask >> msb(pm)) & 1u) != 0u : c_open;
+        const uint32_t start_mask = __ballot_sync(FULL, kind == 1u && !in_prev);
+        const bool is_close = kind == 2u && in_prev;
+        const uint32_t sm = start_mask & lt, cm = closer_mask & lt;
+        const bool started_here = sm != 0u && (cm == 0u || msb(sm) > msb(cm));
+        const int s_lane = started_here ? msb(sm) : 0;
+        const uint32_t s_ref = __shfl_sync(FULL, ref_ex, s_lane), s_read = __shfl_sync(FULL, read_ex, s_lane);
+        const uint32_t s_dex = __shfl_sync(FULL, d_ex, s_lane), s_iex = __shfl_sync(FULL, i_ex, s_lane);
+        const uint32_t blk_ref = started_here ? s_ref : c_blk_ref, blk_read = started_here ? s_read : c_blk_read;
+        const uint32_t del = started_here ? d_ex - s_dex : c_del + d_ex, ins = started_here ? i_ex - s_iex : c_ins + i_ex;
+        const bool mixed = is_close && del > 0u && ins > 0u && !(del == 1u && ins == 1u);
+        const uint32_t mixed_mask = __ballot_sync(FULL, mixed);
+        const uint32_t n_mine = (kind == 2u ? 1u : 0u) + (is_close ? (mixed ? 4u : 1u) : 0u);
+        const uint32_t e_in = warp_incl_scan(n_mine, lane);
+        uint32_t at = n_x + e_in - n_mine;
+        if (kind == 2u && at + n_mine <= x_cap) {
+            if (mixed) {
+                const uint32_t m = n_mixed + __popc(mixed_mask & lt);
+                if (m < rec_cap) { rec[3u * m] = blk_ref; rec[3u * m + 1u] = blk_read; rec[3u * m + 2u] = at; }
+                x[at] = 0; x[at + 1u] = ins; x[at + 2u] = del; x[at + 3u] = 0;
+                at += 4u;
+            } else if (is_close) {
+                // (0, i) -> Ins, (d, 0) -> Del, (1, 1) -> Match(1) without looking at the bases (:38-48)
+                x[at] = (del == 0u) ? ((ins << 4) | OP_I) : (ins == 0u) ? ((del << 4) | OP_D) : ((1u << 4) | OP_M);
+                ++at;
+            }
+            x[at] = c;
+        }
+        n_x += __shfl_sync(FULL, e_in, 31);
+        n_mixed += __popc(mixed_mask);
+        const bool open_end = nt_mask ? ((idl_mask >> msb(nt_mask)) & 1u) != 0u : c_open;
+        const uint32_t d_tot = __shfl_sync(FULL, d_in, 31), i_tot = __shfl_sync(FULL, i_in, 31);
+        if (open_end) {
+            const bool started = start_mask != 0u && (closer_mask == 0u || msb(start_mask) > msb(closer_mask));
+            const int sl = started ? msb(start_mask) : 0;
+            const uint32_t o_ref = __shfl_sync(FULL, ref_ex, sl), o_read = __shfl_sync(FULL, read_ex, sl);
+            const uint32_t o_dex = __shfl_sync(FULL, d_ex, sl), o_iex = __shfl_sync(FULL, i_ex, sl);
+            if (started) { c_blk_ref = o_ref; c_blk_read = o_read; c_del = d_tot - o_dex; c_ins = i_tot - o_iex; }
+            else { c_del += d_tot; c_ins += i_tot; }
+        }
+        c_open = open_end;
+        ref_base += __shfl_sync(FULL, r_in, 31);
+        read_base += __shfl_sync(FULL, q_in, 31);
+    }
+    PTL_ASSERT_UNIFORM(n_x); PTL_ASSERT_UNIFORM(n_mixed);
+    if (n_x > x_cap || n_mixed > rec_cap) return ST_ERR_CAPACITY;
+    __syncwarp();
+    // ---- pass B
+    bool lane_err = false;
+    for (uint32_t kb = 0; kb < n_mixed; kb += 32u) {
+        const uint32_t k = kb + lane;
+        const bool mine = k < n_mixed;
+        int64_t blk_ref = 0;
+        uint32_t blk_read = 0, at = 0, d = 0, q = 0, pre = 0, post = 0;
+        if (mine) {
+            blk_ref = ref_pos + int64_t(rec[3u * k]);
+            blk_read = rec[3u * k + 1u];
+            at = rec[3u * k + 2u];
+            q = x[at + 1u];
+            d = x[at + 2u];
+        }
+        uint32_t side = mine ? 1u : 0u;  // 1 right, 2 left, 0 done
+        while (__any_sync(FULL, side != 0u)) {
+            if (side != 0u) {
+                if (d == 0u || q == 0u) {
+                    side = (side == 1u) ? 2u : 0u;
+                } else {
+                    const int64_t f_ref = (side == 1u) ? blk_ref + int64_t(d) - 1 : blk_ref + int64_t(pre);
+                    const uint32_t f_read = (side == 1u) ? blk_read + q - 1u : blk_read + pre;
+                    if (f_ref < 0 || uint64_t(f_ref) >= ref_len || f_read >= read.len) {
+                        lane_err = true;  // Rust slice index panic
+                        side = 0u;
+                    } else {
+                        const uint8_t rb = ref_seq[f_ref];
+                        const uint8_t qb = read.at(f_read);
+                        cnt.base_bytes += 2;
+                        if (rb == qb) {
+                            --d; --q;
+                            if (side == 1u) ++post; else ++pre;
+                        } else {
+                            side = (side == 1u) ? 2u : 0u;
+                        }
+                    }
+                }
+            }
+        }
+        if (mine) {
+            if (d == 1u && q == 1u) { d = 0; q = 0; ++post; }  // down to a SNP: 1 edit instead of 2 (:88-92)
+            x[at] = (pre << 4) | OP_M; x[at + 1u] = (q << 4) | OP_I; x[at + 2u] = (d << 4) | OP_D; x[at + 3u] = (post << 4) | OP_M;
+        }
+    }
+    if (__any_sync(FULL, lane_err)) return ST_ERR_BOUNDS;
+    __syncwarp();
+    // ---- pass C (in place: sink.buf == x)
+    for (uint32_t q0 = 0; q0 < n_x; q0 += 32u) {
+        const uint32_t q = q0 + lane;
+        const uint32_t word = (q < n_x) ? x[q] : 0u;
+        sink.push2(lane, 0u, word & 0xfu, word >> 4);
+    }
+    return 0;
 }
 
 // a4 + a5 + a6 + a8 for entry t of DevWork::long_list: lift_pair_body did the strand logic and parked the pair with
@@ -596,19 +746,36 @@ __device__ __forceinline__ void lift_long_pair_body(const DevStatic& S, const De
         else if (!some) status = ST_NONE;
         else if (W.rseg_read_len[s] != B.read_seq_len[r]) status = ST_ERR_LENGTH;  // (:204-229, see lift_pair_body)
     }
+    int64_t rpos = int64_t(start) + int64_t(sink.lead_del_shift);
+    uint32_t n_out = sink.n;
+    uint64_t out_off = slot0;
+    span = sink.ref_span;
+    // ---- a9 (:236-243): only when the lifted CIGAR holds a mixed I/D run (otherwise the identity, see lift_pair_body): B -> A
+    if (status == ST_LIFTED && sink.mixed_cluster && (stage_mask & 4u)) {
+        const ReadBases read{B.seq4 + B.read_seq_off[r], B.read_seq_len[r], W.pair_flip[p] != 0};
+        const int32_t chrom = S.seg_chrom[g];
+        // buffer A of a long pair: [ops, uncompressed then compressed in place | 3 words per mixed cluster]  (pair_fill_body)
+        const uint32_t n_clus_cap = (cap_a - cap_b - 16u) / 9u;
+        uint32_t* rec = buf_a + (cap_a - 3u * n_clus_cap);
+        WarpSink simp(buf_a, cap_a - 3u * n_clus_cap);
+        const int err = warp_simplify(buf_b, n_out, rpos, S.ref + S.chrom_off[chrom], S.chrom_off[chrom + 1] - S.chrom_off[chrom], read, buf_a,
+                                      simp.cap, rec, n_clus_cap, simp, lane, cnt);
+        simp.finish(lane);
+        if (err) status = err;
+        else if (simp.overflow) status = ST_ERR_CAPACITY;
+        rpos += int64_t(simp.lead_del_shift);
+        n_out = simp.n;
+        out_off = slot0 + cap_b;
+        span = simp.ref_span;
+    }
     const bool ok = status == ST_LIFTED;
-    const int64_t rpos = int64_t(start) + int64_t(sink.lead_del_shift);
     const uint32_t bytes = warp_sum(cnt.base_bytes);
     if (lane == 0u) {
-        if (ok && sink.mixed_cluster && (stage_mask & 4u)) {  // a9 is not the identity: worklist of simplify_pairs_kernel
-            status = ST_PENDING_SIMPLIFY;
-            W.simplify_list[atomicAdd(&T->n_simplify, 1u)] = p;
-        }
         W.pair_status[p] = int8_t(status);
         W.pair_pos[p] = ok ? rpos : 0;
-        W.pair_n_out[p] = ok ? sink.n : 0u;
-        W.pair_out_off[p] = slot0;
-        W.pair_bin[p] = ok ? reg2bin(rpos, rpos + int64_t(sink.ref_span)) : uint16_t(0);
+        W.pair_n_out[p] = ok ? n_out : 0u;
+        W.pair_out_off[p] = out_off;
+        W.pair_bin[p] = ok ? reg2bin(rpos, rpos + int64_t(span)) : uint16_t(0);
         if (bytes) atomicAdd(&T->n_base_bytes, (unsigned long long)bytes);
     }
 }

@@ -143,7 +143,8 @@ __device__ __forceinline__ void pair_fill_body(const DevStatic& S, const DevBatc
             //   one per I/D cluster and per other non-match op, plus the end)
             uint32_t cap_b = max(n_shift + 2u * n_keys + 4u, fwd ? 0u : 3u * n_id + 4u);
             if (!fwd && n_in > W.long_ops) cap_b = max(cap_b, 6u * (n_id + 1u) + 8u);
-            const uint32_t cap_a = cap_b + 6u * (n_id + n_keys) + 8u;
+            //   (a long pair simplifies on the warp path: A = [lifted ops + 3 per I/D cluster | 3 words per mixed cluster])
+            const uint32_t cap_a = cap_b + (n_in > W.long_ops ? 9u * (n_id + n_keys) + 16u : 6u * (n_id + n_keys) + 8u);
             W.pair_cap_b[p] = cap_b;
             W.pair_slot_begin[p] = uint64_t(cap_a) + cap_b;  // [0,cap_b) = buffer B, [cap_b, cap_b+cap_a) = buffer A
         }

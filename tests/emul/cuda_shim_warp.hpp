@@ -68,6 +68,16 @@ inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __clz(unsigned v) { return v ? __builtin_clz(v) : 32; }
 inline int __ffs(unsigned v) { return __builtin_ffs(int(v)); }
 
+// debug hook of lift_warp.cuh: values the kernels treat as warp-uniform really are identical in all 32 lanes
+#include <cstdio>
+#include <cstdlib>
+template <class T> inline void ptl_assert_uniform(T v, const char* what, int line) {
+    const uint64_t* s = warp_emul::exchange(warp_emul::to_bits(v));
+    for (int i = 1; i < 32; ++i)
+        if (s[i] != s[0]) { std::fprintf(stderr, "lift_warp.cuh:%d: %s differs between lanes (lane 0: %llu, lane %d: %llu)\n", line, what, (unsigned long long)s[0], i, (unsigned long long)s[i]); std::abort(); }
+}
+#define PTL_ASSERT_UNIFORM(v) ptl_assert_uniform((v), #v, __LINE__)
+
 // only lane 0 of a warp calls these, and the emulation runs one warp at a time
 inline unsigned int atomicAdd(unsigned int* p, unsigned int v) { const unsigned int o = *p; *p += v; return o; }
 inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { const unsigned long long o = *p; *p += v; return o; }
