@@ -234,26 +234,23 @@ __global__ void __launch_bounds__(LIFT_BLOCK, LIFT_MIN_BLOCKS) lift_pairs_kernel
     }
 }
 
-// a6 + a8 for the worklist of long pairs: one warp per pair, lanes over CIGAR ops (lift_warp.cuh).
-__global__ void __launch_bounds__(128, 4) lift_long_pairs_kernel(DevStatic S, DevBatch B, DevWork W, DevTotals* T, uint32_t stage_mask) {
-    const uint32_t n = min(T->n_long, W.pair_cap);
+// The two warp-per-pair worklists of a batch in ONE launch (their lengths are only known on the device: a fixed grid of
+// warps strides over the joint index space):
+//   long_list      pairs with more than long_ops CIGAR ops: a5 + a6 + a8 + a9 with lanes over ops (lift_long_pair_body)
+//   simplify_list  pairs lifted by lift_pairs_kernel whose CIGAR holds a mixed I/D run: a9 (simplify_warp_pair_body)
+#ifndef LIFT_LONG_MIN_BLOCKS
+#define LIFT_LONG_MIN_BLOCKS 6  // 80 registers, no spills (sweep on the stress workload: 4 -> 1.50 ms, 6 -> 1.43 ms, 8 spills -> 1.37 ms)
+#endif
+__global__ void __launch_bounds__(128, LIFT_LONG_MIN_BLOCKS) warp_pairs_kernel(DevStatic S, DevBatch B, DevWork W, DevTotals* T, uint32_t stage_mask) {
+    const uint32_t n_long = min(T->n_long, W.pair_cap);
+    const uint32_t n_simp = ((stage_mask & 6u) == 6u) ? min(T->n_simplify, W.pair_cap) : 0u;  // (long pairs simplify inline)
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t t = warp; t < n; t += n_warps) lift_long_pair_body(S, B, W, T, W.long_list[t], lane, stage_mask);
-}
-
-// a9 for the worklist of pairs whose lifted CIGAR holds a mixed I/D run: dense, warp-collective, B -> A.
-__global__ void __launch_bounds__(128) simplify_pairs_kernel(DevStatic S, DevBatch B, DevWork W, DevTotals* T) {
-    const uint32_t n = min(T->n_simplify, W.pair_cap);
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
-    uint32_t b = 0;
-    for (uint32_t base = warp * 32u; base < n; base += n_warps * 32u) simplify_pair_body(S, B, W, base + lane, base + lane < n, b);
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) b += __shfl_down_sync(FULL, b, d);
-    if (lane == 0 && b) atomicAdd(&T->n_base_bytes, (unsigned long long)b);
+    for (uint32_t t = warp; t < n_long + n_simp; t += n_warps) {
+        if (t < n_long) lift_long_pair_body(S, B, W, T, W.long_list[t], lane, stage_mask);
+        else simplify_warp_pair_body(S, B, W, T, W.simplify_list[t - n_long], lane);
+    }
 }
 
 // a10 (field part).  One thread per read.
@@ -397,15 +394,8 @@ void launch_lift(const DevStatic& S, const DevBatch& B, const DevWork& W, char* 
     else lift_pairs_kernel<false><<<(W.pair_cap + LIFT_BLOCK - 1) / LIFT_BLOCK, LIFT_BLOCK, 0, st>>>(S, B, W, T, stage_mask);
     ++*launches;
     if ((stage_mask & 2u) || stage_mask == 1u) {
-        // worklist length is only known on the device: a fixed grid of warps strides over it
         const unsigned blocks = unsigned(std::min<uint64_t>((uint64_t(W.pair_cap) + 3) / 4, 148ull * 16));
-        lift_long_pairs_kernel<<<blocks, 128, 0, st>>>(S, B, W, T, stage_mask);
-        ++*launches;
-    }
-    if ((stage_mask & 6u) == 6u) {
-        // worklist length is only known on the device: a fixed grid strides over it (a few % of the pairs)
-        const unsigned blocks = unsigned(std::min<uint64_t>((uint64_t(W.pair_cap) + 127) / 128, 148ull * 16));
-        simplify_pairs_kernel<<<blocks, 128, 0, st>>>(S, B, W, T);
+        warp_pairs_kernel<<<blocks, 128, 0, st>>>(S, B, W, T, stage_mask);
         ++*launches;
     }
     mark(2);

@@ -625,6 +625,16 @@ __device__ __forceinline__ int warp_simplify(const uint32_t* __restrict__ in, ui
             q = x[at + 1u];
             d = x[at + 2u];
         }
+        // The first probe of BOTH sides is issued up front (4 independent loads: almost every cluster ends each side at
+        // its first or second base, and the dependent DRAM round trips of a few lanes were the whole cost of this pass);
+        // the left probe is still valid after the right trimming because it reads blk_ref + 0 / blk_read + 0.
+        const uint32_t d0 = d, q0 = q;
+        uint32_t pr_r = 0x100u, pr_q = 0x200u, pl_r = 0x100u, pl_q = 0x200u;  // (unequal sentinels: an invalid probe is re-done below)
+        if (mine && d0 > 0u && q0 > 0u) {
+            const int64_t rr = blk_ref + int64_t(d0) - 1, rl = blk_ref;
+            if (rr >= 0 && uint64_t(rr) < ref_len && blk_read + q0 - 1u < read.len) { pr_r = ref_seq[rr]; pr_q = read.at(blk_read + q0 - 1u); }
+            if (rl >= 0 && uint64_t(rl) < ref_len && blk_read < read.len) { pl_r = ref_seq[rl]; pl_q = read.at(blk_read); }
+        }
         uint32_t side = mine ? 1u : 0u;  // 1 right, 2 left, 0 done
         while (__any_sync(FULL, side != 0u)) {
             if (side != 0u) {
@@ -637,8 +647,10 @@ __device__ __forceinline__ int warp_simplify(const uint32_t* __restrict__ in, ui
                         lane_err = true;  // Rust slice index panic
                         side = 0u;
                     } else {
-                        const uint8_t rb = ref_seq[f_ref];
-                        const uint8_t qb = read.at(f_read);
+                        uint32_t rb, qb;
+                        if (side == 1u && d == d0 && pr_r < 0x100u) { rb = pr_r; qb = pr_q; }
+                        else if (side == 2u && pre == 0u && pl_r < 0x100u) { rb = pl_r; qb = pl_q; }
+                        else { rb = ref_seq[f_ref]; qb = read.at(f_read); }
                         cnt.base_bytes += 2;
                         if (rb == qb) {
                             --d; --q;
@@ -776,6 +788,41 @@ __device__ __forceinline__ void lift_long_pair_body(const DevStatic& S, const De
         W.pair_n_out[p] = ok ? n_out : 0u;
         W.pair_out_off[p] = out_off;
         W.pair_bin[p] = ok ? reg2bin(rpos, rpos + int64_t(span)) : uint16_t(0);
+        if (bytes) atomicAdd(&T->n_base_bytes, (unsigned long long)bytes);
+    }
+}
+
+// a9 for a pair lifted by lift_pairs_kernel whose CIGAR holds a mixed I/D run (DevWork::simplify_list): B -> A.
+__device__ __forceinline__ void simplify_warp_pair_body(const DevStatic& S, const DevBatch& B, const DevWork& W, DevTotals* T, uint32_t p, uint32_t lane) {
+    const uint32_t s = W.pair_rseg[p], g = W.pair_seg[p];
+    const uint32_t r = W.rseg_read[s];
+    const uint64_t slot0 = W.pair_slot_begin[p];
+    const uint32_t cap_b = W.pair_cap_b[p];
+    const uint32_t cap_a = uint32_t(W.pair_slot_begin[p + 1] - slot0) - cap_b;
+    uint32_t* buf_b = W.scratch + slot0;
+    uint32_t* buf_a = buf_b + cap_b;
+    // buffer A: [ops, uncompressed then compressed in place | 3 words per mixed cluster]; its size was chosen by
+    // pair_fill_body from (n_id + n_keys) = the possible I/D clusters of the lifted CIGAR
+    const bool long_layout = B.rseg_cigar_len[s] > W.long_ops;
+    const uint32_t n_clus_cap = long_layout ? (cap_a - cap_b - 16u) / 9u : (cap_a - cap_b - 8u) / 6u;
+    uint32_t* rec = buf_a + (cap_a - 3u * n_clus_cap);
+    const ReadBases read{B.seq4 + B.read_seq_off[r], B.read_seq_len[r], W.pair_flip[p] != 0};
+    const int32_t chrom = S.seg_chrom[g];
+    const int64_t rpos = W.pair_pos[p];
+    PairCounters cnt;
+    WarpSink simp(buf_a, cap_a - 3u * n_clus_cap);
+    int status = warp_simplify(buf_b, W.pair_n_out[p], rpos, S.ref + S.chrom_off[chrom], S.chrom_off[chrom + 1] - S.chrom_off[chrom], read, buf_a,
+                               simp.cap, rec, n_clus_cap, simp, lane, cnt);
+    simp.finish(lane);
+    if (!status && simp.overflow) status = ST_ERR_CAPACITY;
+    const int64_t out_pos = rpos + int64_t(simp.lead_del_shift);
+    const uint32_t bytes = warp_sum(cnt.base_bytes);
+    if (lane == 0u) {
+        W.pair_status[p] = int8_t(status ? status : ST_LIFTED);
+        W.pair_pos[p] = status ? 0 : out_pos;
+        W.pair_n_out[p] = status ? 0u : simp.n;
+        W.pair_out_off[p] = slot0 + cap_b;
+        W.pair_bin[p] = status ? uint16_t(0) : reg2bin(out_pos, out_pos + int64_t(simp.ref_span));
         if (bytes) atomicAdd(&T->n_base_bytes, (unsigned long long)bytes);
     }
 }

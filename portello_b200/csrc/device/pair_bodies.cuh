@@ -272,7 +272,7 @@ __device__ __forceinline__ void lift_pair_body(const DevStatic& S, const DevBatc
         cur_is_raw = false;
     }
     // ---- a9: simplify (:236-243).  Only the few pairs whose lifted CIGAR holds a mixed I/D run need it: they are
-    //      appended to a worklist and finished by simplify_pairs_kernel with all lanes busy (inline, the stage ran at
+    //      appended to a worklist and finished warp-per-pair by warp_pairs_kernel (lift_warp.cuh) (inline, the stage ran at
     //      1.9 active threads per instruction and cost 22 % of this kernel, ncu r01g).
     bool deferred = false;
     if (usable && !err && status == ST_LIFTED && (stage_mask & 4u) && !simplify_is_identity) {
@@ -332,52 +332,6 @@ __device__ __forceinline__ void lift_pair_body(const DevStatic& S, const DevBatc
         W.pair_n_out[p] = ok ? cur.n : 0u;
         W.pair_out_off[p] = ok ? uint64_t(cur.p - W.scratch) : slot0;
         W.pair_bin[p] = ok ? reg2bin(rpos, rpos + int64_t(span)) : uint16_t(0);  // bam_reg2bin(pos, end) (:278-279)
-    }
-    n_base_bytes += cnt.base_bytes;
-}
-
-// a9 for entry t of the worklist of pairs whose lifted CIGAR holds a mixed I/D run: B -> A.  Warp-collective.
-__device__ __forceinline__ void simplify_pair_body(const DevStatic& S, const DevBatch& B, const DevWork& W, uint32_t t, bool active,
-                                                   uint32_t& n_base_bytes) {
-    PairCounters cnt;
-    uint32_t p = 0, cap_b = 0, n_in = 0;
-    uint32_t* buf_a = nullptr;
-    uint32_t* rec = nullptr;
-    const uint8_t* ref = nullptr;
-    uint64_t ref_len = 0;
-    int64_t rpos = 0;
-    OpSource cur{nullptr, 0, false};
-    ReadBases read{nullptr, 0, false};
-    uint32_t sink_cap = 0;
-    if (active) {
-        p = W.simplify_list[t];
-        const uint32_t s = W.pair_rseg[p], g = W.pair_seg[p], r = W.rseg_read[s];
-        const uint64_t slot0 = W.pair_slot_begin[p], slot1 = W.pair_slot_begin[p + 1];
-        cap_b = W.pair_cap_b[p];
-        const uint32_t cap_a = uint32_t(slot1 - slot0) - cap_b;
-        uint32_t* buf_b = W.scratch + slot0;
-        buf_a = buf_b + cap_b;
-        n_in = W.pair_n_out[p];
-        cur = OpSource{buf_b, n_in, false};
-        rpos = W.pair_pos[p];
-        read = ReadBases{B.seq4 + B.read_seq_off[r], B.read_seq_len[r], W.pair_flip[p] != 0};
-        const int32_t chrom = S.seg_chrom[g];
-        ref = S.ref + S.chrom_off[chrom];
-        ref_len = S.chrom_off[chrom + 1] - S.chrom_off[chrom];
-        const uint32_t n_rec = 4u * ((cap_a - cap_b - 8u) / 6u);
-        rec = buf_a + (cap_a - n_rec);
-        sink_cap = uint32_t(rec - buf_a);
-    }
-    int err = 0;
-    OpSink sink(buf_a, sink_cap);
-    const int64_t simp = run_simplify_warp(active, cur, rpos, ref, ref_len, read, rec, sink, cnt, err);
-    if (active) {
-        if (sink.overflow) err = ST_ERR_CAPACITY;
-        W.pair_status[p] = int8_t(err ? err : ST_LIFTED);
-        W.pair_pos[p] = err ? 0 : simp;
-        W.pair_n_out[p] = err ? 0u : sink.n;
-        W.pair_out_off[p] = uint64_t(buf_a - W.scratch);
-        W.pair_bin[p] = err ? uint16_t(0) : reg2bin(simp, simp + int64_t(sink.ref_span));
     }
     n_base_bytes += cnt.base_bytes;
 }

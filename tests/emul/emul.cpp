@@ -199,11 +199,9 @@ int run_batch(ptl_ctx* ctx, EmulSlot& sl, const ptl_batch* b, uint32_t stage_mas
         if (stage_mask == 7u) lift_pair_body<true>(S, B, W, &T, p, true, stage_mask, in_ops, base_bytes);
         else lift_pair_body<false>(S, B, W, &T, p, true, stage_mask, in_ops, base_bytes);
     }
-    if ((stage_mask & 2u) || stage_mask == 1u) emul_lift_long_pairs(S, B, W, &T, stage_mask);
-    if ((stage_mask & 6u) == 6u)
-        for (uint32_t t = 0; t < T.n_simplify; ++t) simplify_pair_body(S, B, W, t, true, base_bytes);
     T.n_in_ops = in_ops;
     T.n_base_bytes = base_bytes;
+    if ((stage_mask & 2u) || stage_mask == 1u) emul_lift_long_pairs(S, B, W, &T, stage_mask);  // warp_pairs_kernel
 
     // ---- read_finalize -> scan -> emit_records
     std::vector<uint2> read_counts(size_t(n) + 1, make_uint2(0, 0));

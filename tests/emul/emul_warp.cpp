@@ -1,4 +1,4 @@
-// TEST INFRASTRUCTURE ONLY.  Host emulation of lift_long_pairs_kernel (portello_b200/csrc/device/kernels.cu): the
+// TEST INFRASTRUCTURE ONLY.  Host emulation of warp_pairs_kernel (portello_b200/csrc/device/kernels.cu): the
 // warp-cooperative liftover of lift_warp.cuh run by 32 host threads in lock step (cuda_shim_warp.hpp), one warp at a
 // time over DevWork::long_list.  Compiled as its own translation unit because the rest of the emulation uses the
 // one-lane shim.
@@ -10,8 +10,9 @@
 #include "../../portello_b200/csrc/device/lift_warp.cuh"
 
 void emul_lift_long_pairs(const ptl::DevStatic& S, const ptl::DevBatch& B, const ptl::DevWork& W, ptl::DevTotals* T, uint32_t stage_mask) {
-    const uint32_t n = std::min<uint32_t>(T->n_long, W.pair_cap);
-    if (!n) return;
+    const uint32_t n_long = std::min<uint32_t>(T->n_long, W.pair_cap);
+    const uint32_t n_simp = ((stage_mask & 6u) == 6u) ? std::min<uint32_t>(T->n_simplify, W.pair_cap) : 0u;
+    if (!(n_long + n_simp)) return;
     warp_emul::Warp warp;
     std::vector<std::thread> lanes;
     for (uint32_t lane = 0; lane < 32; ++lane)
@@ -19,7 +20,10 @@ void emul_lift_long_pairs(const ptl::DevStatic& S, const ptl::DevBatch& B, const
             warp_emul::tl_warp = &warp;
             warp_emul::tl_lane = lane;
             warp_emul::tl_parity = 0;
-            for (uint32_t t = 0; t < n; ++t) ptl::lift_long_pair_body(S, B, W, T, W.long_list[t], lane, stage_mask);
+            for (uint32_t t = 0; t < n_long + n_simp; ++t) {
+                if (t < n_long) ptl::lift_long_pair_body(S, B, W, T, W.long_list[t], lane, stage_mask);
+                else ptl::simplify_warp_pair_body(S, B, W, T, W.simplify_list[t - n_long], lane);
+            }
         });
     for (auto& th : lanes) th.join();
 }
