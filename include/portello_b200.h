@@ -230,6 +230,36 @@ int ptl_lift_wait(ptl_ctx* ctx, int slot, ptl_result* out);
 int ptl_lift_upload(ptl_ctx* ctx, int slot, const ptl_batch* batch);   /* H2D only (async) */
 int ptl_lift_run(ptl_ctx* ctx, int slot, uint32_t stage_mask);         /* kernels only, on the resident batch (async) */
 int ptl_lift_download(ptl_ctx* ctx, int slot, ptl_result* out);        /* D2H + sync */
+/* ---------------------------------------------------------------- record assembly, bases
+ *
+ * The read bases and base qualities of every OUTPUT record of the slot's last batch, oriented the way the reference
+ * leaves them: a record with rec_need_flip = 1 went through reverse_alignment_seq_and_qual
+ * (src/read_alignment_scanner.rs:125-133, called at :274-276 and :330-332): bases decoded, reverse-complemented with
+ * rev_comp_in_place (lib/rust-vc-utils/src/seq_util.rs:29-40: A<->T, C<->G, N->N, anything else incl. '=' and IUPAC
+ * codes -> N) and re-encoded by Record::set; qualities reversed.  Other records carry the read's bytes unchanged (every
+ * record of a read is a clone_record of the same input, :105-117).  BAM layout: 4-bit bases, high nibble first, the unused
+ * low nibble of an odd-length sequence zero.
+ * Must follow ptl_lift_wait / ptl_lift_download on the same slot (the batch's packed bases are still resident). */
+typedef struct {
+    const uint8_t* qual;            /* pooled qualities: read r owns qual[read_qual_off[r] .. + read_seq_len[r]) */
+    const uint64_t* read_qual_off;  /* [n_reads] */
+    uint64_t qual_bytes;
+} ptl_read_quals;
+typedef struct {
+    uint32_t n_records;
+    const uint64_t* rec_seq_begin;   /* [n_records+1] byte offsets into seq4; every record starts 4-byte aligned */
+    const uint8_t* seq4;
+    const uint64_t* rec_qual_begin;  /* [n_records+1] byte offsets into qual; every record starts 4-byte aligned */
+    const uint8_t* qual;
+    float kernel_ms;                 /* device time of the assembly kernel (CUDA events on the slot stream) */
+    uint64_t bytes_read, bytes_written;  /* algorithmic bytes of that kernel: bases + qualities in, bases + qualities out */
+} ptl_record_bases;
+/* flags: PTL_ASM_RESIDENT_QUAL = the qualities uploaded by the previous call on this slot are reused (no H2D);
+ *        PTL_ASM_NO_DOWNLOAD   = results stay on the device (out->seq4 / out->qual are NULL): kernel timing only. */
+#define PTL_ASM_RESIDENT_QUAL 1u
+#define PTL_ASM_NO_DOWNLOAD 2u
+int ptl_assemble_bases(ptl_ctx* ctx, int slot, const ptl_read_quals* quals, uint32_t flags, ptl_record_bases* out);
+
 /* cudaStream_t of a slot (as void*), so callers can bracket work with their own CUDA events. */
 void* ptl_slot_stream(ptl_ctx* ctx, int slot);
 /* Per-kernel device time of the LAST ptl_lift_run on the slot, CUDA events on the slot stream.

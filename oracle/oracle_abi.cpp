@@ -34,6 +34,10 @@ struct Slot {
     std::vector<uint32_t> cigar;
     ptl_result res{};
     PairStats stats;
+    // record assembly (ptl_oracle_assemble_bases): the submitted batch (borrowed: the caller keeps it alive) and outputs
+    ptl_batch batch{};
+    std::vector<uint64_t> asm_seq_begin, asm_qual_begin;
+    std::vector<uint8_t> asm_seq4, asm_qual;
 };
 
 // Flat copy of the installed segments, lent out by ptl_oracle_get_contig_segments.
@@ -401,10 +405,69 @@ int ptl_oracle_lift_submit_ex(ptl_ctx* ctx, int slot, const ptl_batch* b, uint32
     res.n_pairs = sl.stats.n_pairs;
     res.n_lifted = sl.stats.n_lifted;
     sl.submitted = true;
+    sl.batch = *b;  // (pointers borrowed: ptl_oracle_assemble_bases reads the batch's bases again)
     return PTL_OK;
 }
 int ptl_oracle_lift_submit(ptl_ctx* ctx, int slot, const ptl_batch* b) {
     return ptl_oracle_lift_submit_ex(ctx, slot, b, PTL_STAGE_ALL);
+}
+
+// Record assembly, bases: what reverse_alignment_seq_and_qual (src/read_alignment_scanner.rs:125-133) does to a flipped
+// record, byte for byte: seq().as_bytes() (4-bit decode) -> rev_comp_in_place (seq_util.rs:29-40) -> Record::set, which
+// re-encodes the ASCII bases with htslib's seq_nt16_table (only A, C, G, T, N can come out of rev_comp); qualities reversed.
+// Records that were not flipped keep the read's bytes (clone_record, :105-117).
+int ptl_oracle_assemble_bases(ptl_ctx* ctx, int slot, const ptl_read_quals* quals, uint32_t /*flags*/, ptl_record_bases* out) {
+    if (!ctx || !out || !quals || slot < 0 || slot >= ctx->n_slots) return PTL_ERR_INVALID_ARG;
+    Slot& sl = ctx->slots[size_t(slot)];
+    if (!sl.submitted) return fail(ctx, PTL_ERR_STATE, "assemble without a lifted batch");
+    const ptl_batch& b = sl.batch;
+    const uint32_t n_rec = sl.res.n_records;
+    // read of every read segment (CSR inverse)
+    std::vector<uint32_t> rseg_read(b.n_read_segments);
+    for (uint32_t r = 0; r < b.n_reads; ++r)
+        for (uint32_t s = b.read_seg_begin[r]; s < b.read_seg_begin[r + 1]; ++s) rseg_read[s] = r;
+    auto encode = [](uint8_t c) -> uint8_t {  // htslib seq_nt16_table
+        switch (c) {
+            case '=': return 0; case 'A': case 'a': return 1; case 'C': case 'c': return 2; case 'M': case 'm': return 3;
+            case 'G': case 'g': return 4; case 'R': case 'r': return 5; case 'S': case 's': return 6; case 'V': case 'v': return 7;
+            case 'T': case 't': return 8; case 'W': case 'w': return 9; case 'Y': case 'y': return 10; case 'H': case 'h': return 11;
+            case 'K': case 'k': return 12; case 'D': case 'd': return 13; case 'B': case 'b': return 14; default: return 15;
+        }
+    };
+    sl.asm_seq_begin.assign(size_t(n_rec) + 1, 0);
+    sl.asm_qual_begin.assign(size_t(n_rec) + 1, 0);
+    for (uint32_t k = 0; k < n_rec; ++k) {
+        const uint64_t len = b.read_seq_len[rseg_read[sl.rec_read_segment[k]]];
+        sl.asm_seq_begin[k + 1] = sl.asm_seq_begin[k] + ((((len + 1) >> 1) + 3) & ~3ull);
+        sl.asm_qual_begin[k + 1] = sl.asm_qual_begin[k] + ((len + 3) & ~3ull);
+    }
+    sl.asm_seq4.assign(sl.asm_seq_begin[n_rec], 0);
+    sl.asm_qual.assign(sl.asm_qual_begin[n_rec], 0);
+    for (uint32_t k = 0; k < n_rec; ++k) {
+        const uint32_t r = rseg_read[sl.rec_read_segment[k]];
+        const uint64_t len = b.read_seq_len[r];
+        const uint8_t* seq4 = b.seq4 + b.read_seq_off[r];
+        const uint8_t* q = quals->qual + quals->read_qual_off[r];
+        uint8_t* o_seq = sl.asm_seq4.data() + sl.asm_seq_begin[k];
+        uint8_t* o_q = sl.asm_qual.data() + sl.asm_qual_begin[k];
+        if (!sl.rec_need_flip[k]) {
+            std::memcpy(o_seq, seq4, (len + 1) >> 1);
+            std::memcpy(o_q, q, len);
+            continue;
+        }
+        std::vector<uint8_t> ascii = decode_seq4(seq4, len);  // record.seq().as_bytes()
+        rev_comp_in_place(ascii);
+        for (uint64_t i = 0; i < len; ++i) o_seq[i >> 1] |= uint8_t(encode(ascii[i]) << ((i & 1) ? 0 : 4));  // Record::set
+        for (uint64_t i = 0; i < len; ++i) o_q[i] = q[len - 1 - i];                                          // qual().iter().rev()
+    }
+    *out = ptl_record_bases{};
+    out->n_records = n_rec;
+    out->rec_seq_begin = sl.asm_seq_begin.data();
+    out->seq4 = sl.asm_seq4.data();
+    out->rec_qual_begin = sl.asm_qual_begin.data();
+    out->qual = sl.asm_qual.data();
+    out->bytes_read = out->bytes_written = sl.asm_seq_begin[n_rec] + sl.asm_qual_begin[n_rec];
+    return PTL_OK;
 }
 int ptl_oracle_lift_wait(ptl_ctx* ctx, int slot, ptl_result* out) {
     if (!ctx || !out || slot < 0 || slot >= ctx->n_slots) return PTL_ERR_INVALID_ARG;

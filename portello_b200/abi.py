@@ -124,6 +124,18 @@ class ResultC(C.Structure):
     ]
 
 
+class ReadQualsC(C.Structure):
+    _fields_ = [("qual", u8p), ("read_qual_off", u64p), ("qual_bytes", C.c_uint64)]
+
+
+class RecordBasesC(C.Structure):
+    _fields_ = [("n_records", C.c_uint32), ("rec_seq_begin", u64p), ("seq4", u8p), ("rec_qual_begin", u64p), ("qual", u8p),
+                ("kernel_ms", C.c_float), ("bytes_read", C.c_uint64), ("bytes_written", C.c_uint64)]
+
+
+ASM_RESIDENT_QUAL, ASM_NO_DOWNLOAD = 1, 2
+
+
 class SplitSegmentsC(C.Structure):
     _fields_ = [
         ("seq_order_start", u32p),
@@ -491,3 +503,24 @@ class Context:
     def lift(self, batch: Batch, slot: int = 0, stage_mask: int = STAGE_ALL, allow_panic: bool = False) -> Result:
         self.submit(batch, slot, stage_mask)
         return self.wait(slot, allow_panic)
+
+    def assemble_bases(self, qual: Optional[np.ndarray], read_qual_off: Optional[np.ndarray], slot: int = 0, flags: int = 0):
+        """ptl_assemble_bases on the slot's last lifted batch.  Returns (RecordBasesC, per-record list of (seq4 bytes, qual bytes))
+        -- the list is None with ASM_NO_DOWNLOAD."""
+        fn = getattr(self.lib.dll, self.lib.prefix + "assemble_bases")
+        fn.restype, fn.argtypes = C.c_int, [C.c_void_p, C.c_int, C.POINTER(ReadQualsC), C.c_uint32, C.POINTER(RecordBasesC)]
+        q = ReadQualsC()
+        if qual is not None:
+            qa, qo = _arr(qual, np.uint8), _arr(read_qual_off, np.uint64)
+            self._keep[("qual", slot)] = (qa, qo)
+            q.qual, q.read_qual_off, q.qual_bytes = _ptr(qa, u8p), _ptr(qo, u64p), qa.size
+        out = RecordBasesC()
+        self._check(fn(self.h, slot, C.byref(q) if qual is not None else None, flags, C.byref(out)))
+        if flags & ASM_NO_DOWNLOAD:
+            return out, None
+        n = out.n_records
+        sb = np.ctypeslib.as_array(out.rec_seq_begin, (n + 1,)).copy()
+        qb = np.ctypeslib.as_array(out.rec_qual_begin, (n + 1,)).copy()
+        seq = np.ctypeslib.as_array(out.seq4, (max(int(sb[n]), 1),)).copy() if n else np.zeros(0, np.uint8)
+        ql = np.ctypeslib.as_array(out.qual, (max(int(qb[n]), 1),)).copy() if n else np.zeros(0, np.uint8)
+        return out, (sb, seq, qb, ql)

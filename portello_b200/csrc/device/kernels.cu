@@ -9,6 +9,7 @@
 
 #include <algorithm>
 
+#include "assemble.cuh"
 #include "kernels.hpp"
 #include "lift_device.cuh"
 #include "lift_warp.cuh"
@@ -405,6 +406,37 @@ void launch_lift(const DevStatic& S, const DevBatch& B, const DevWork& W, char* 
     emit_records_kernel<<<(B.n_reads + 255) / 256, 256, 0, st>>>(S, B, W, arena, arena_cap, T, stage_mask);
     ++*launches;
     mark(3);
+}
+
+// =================================================================================================== record assembly
+namespace {
+__global__ void __launch_bounds__(256) assemble_sizes_kernel(uint32_t n_records, const uint32_t* rec_read_segment, const uint32_t* rseg_read,
+                                                             const uint32_t* read_seq_len, uint32_t* rec_read, uint64_t* seq_begin, uint64_t* qual_begin) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > n_records) return;
+    if (k == n_records) { seq_begin[k] = 0; qual_begin[k] = 0; return; }
+    const uint32_t r = rseg_read[rec_read_segment[k]];
+    const uint64_t len = read_seq_len[r];
+    rec_read[k] = r;
+    seq_begin[k] = (((len + 1) >> 1) + 3) & ~3ull;
+    qual_begin[k] = (len + 3) & ~3ull;
+}
+// One block per output record (22.5 KB in, 22.5 KB out for a 15 kb read): HBM-bound streaming.
+__global__ void __launch_bounds__(256) assemble_records_kernel(AsmArgs A) { assemble_record_body(A, blockIdx.x, threadIdx.x, blockDim.x); }
+}  // namespace
+
+void launch_assemble_sizes(uint32_t n_records, const uint32_t* rec_read_segment, const uint32_t* rseg_read, const uint32_t* read_seq_len,
+                           uint32_t* rec_read, uint64_t* seq_begin, uint64_t* qual_begin, void* scan_tmp, size_t scan_tmp_bytes_, cudaStream_t st,
+                           uint64_t* launches) {
+    assemble_sizes_kernel<<<(n_records + 1 + 255) / 256, 256, 0, st>>>(n_records, rec_read_segment, rseg_read, read_seq_len, rec_read, seq_begin, qual_begin);
+    ++*launches;
+    exclusive_scan_inplace<uint64_t>(seq_begin, uint64_t(n_records) + 1, scan_tmp, scan_tmp_bytes_, st, launches, nullptr);
+    exclusive_scan_inplace<uint64_t>(qual_begin, uint64_t(n_records) + 1, scan_tmp, scan_tmp_bytes_, st, launches, nullptr);
+}
+void launch_assemble_records(const AsmArgs& A, cudaStream_t st, uint64_t* launches) {
+    if (!A.n_records) return;
+    assemble_records_kernel<<<A.n_records, 256, 0, st>>>(A);
+    ++*launches;
 }
 
 }  // namespace ptl

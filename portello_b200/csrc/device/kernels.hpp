@@ -27,4 +27,12 @@ void launch_table_build(const DevStatic& S, uint32_t* counts, TabEntry* out, cud
 void launch_lift(const DevStatic& S, const DevBatch& B, const DevWork& W, char* arena, uint64_t arena_cap, DevTotals* T, uint32_t stage_mask,
                  void* scan_tmp, size_t scan_tmp_bytes, cudaStream_t st, uint64_t* launches, StageEvents* ev);
 
+// Record assembly, bases (assemble.cuh).  Sizes: per record the 4-byte-rounded byte counts of its bases and qualities into
+// seq_begin / qual_begin ([n_records+1], then exclusive scans), and the record's read index into rec_read.
+struct AsmArgs;
+void launch_assemble_sizes(uint32_t n_records, const uint32_t* rec_read_segment, const uint32_t* rseg_read, const uint32_t* read_seq_len,
+                           uint32_t* rec_read, uint64_t* seq_begin, uint64_t* qual_begin, void* scan_tmp, size_t scan_tmp_bytes, cudaStream_t st,
+                           uint64_t* launches);
+void launch_assemble_records(const AsmArgs& A, cudaStream_t st, uint64_t* launches);
+
 }  // namespace ptl
