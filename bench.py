@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--slots", type=int, default=3, help="batch slots (CUDA streams) of the e2e pipeline")
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-assemble", action="store_true", help="skip the record-assembly (bases) measurement")
     ap.add_argument("--zero-copy", default="auto", choices=["auto", "on", "off"])
     return ap.parse_args()
 
@@ -389,6 +390,49 @@ def main():
                 "kernel_ms": lift_ms_avg, "stage_ms": stage_ms,
                 "whole_step_frac": alg_bytes / (dev_ms / 1e3) / 1e9 / peak}
 
+    # ---------------------------------------------------------------- next row: record assembly, bases
+    # Outside every timed region of the headline metric.  One chunk of the workload, bases + qualities resident in HBM,
+    # ptl_assemble_bases in its timing-only mode (no H2D, no D2H): seq revcomp + qual reverse of every output record.
+    assemble = None
+    if rank == 0 and world == 1 and not args.no_assemble:
+        ch = chunk_sets[False][0]
+        ctx.set_seq_zero_copy(False)  # the chunk's packed bases are uploaded: the kernel streams them from HBM
+        ctx.submit_c(ch.c, 0)
+        res = abi.Result.from_c(ctx.wait_c(0), copy=False)
+        seq_len = np.ctypeslib.as_array(ch.c.read_seq_len, (ch.c.n_reads,)).astype(np.int64)
+        qoff = np.zeros(ch.c.n_reads, np.uint64)
+        qoff[1:] = np.cumsum(seq_len[:-1])
+        tile = np.random.default_rng(1).integers(0, 94, 1 << 26, dtype=np.uint8)
+        qual = np.resize(tile, int(seq_len.sum()))
+        o0, _ = ctx.assemble_bases(qual, qoff, 0, flags=abi.ASM_NO_DOWNLOAD)  # uploads the qualities once
+        ms = []
+        for _ in range(max(args.warmup, 3) + args.steps):
+            o, _ = ctx.assemble_bases(None, None, 0, flags=abi.ASM_RESIDENT_QUAL | abi.ASM_NO_DOWNLOAD)
+            ms.append(float(o.kernel_ms))
+        ms = ms[max(args.warmup, 3):]
+        a_ms = float(np.mean(ms))
+        a_bytes = int(o.bytes_read + o.bytes_written)
+        # parity of this very call path on a slice of the chunk, against the oracle (checker only)
+        sub = lib.PackedBatch(L, s.read_records, 0, min(2000, n_reads), s.contig_names)
+        sl_len = np.ctypeslib.as_array(sub.c.read_seq_len, (sub.c.n_reads,)).astype(np.int64)
+        so = np.zeros(sub.c.n_reads, np.uint64)
+        so[1:] = np.cumsum(sl_len[:-1])
+        sq = np.resize(tile, int(sl_len.sum()))
+        octx_a = helpers.oracle_context(s, threads=min(8, os.cpu_count() or 1))
+        helpers.lift_c(octx_a, sub.c)
+        helpers.lift_c(ctx, sub.c, slot=1)
+        _, po = octx_a.assemble_bases(sq, so)
+        _, pg = ctx.assemble_bases(sq, so, 1)
+        if not all(np.array_equal(a, b) for a, b in zip(po, pg)):
+            raise SystemExit("PARITY FAILURE vs oracle in ptl_assemble_bases on the bench workload")
+        assemble = {"kernel": "assemble_records_kernel", "what": "seq revcomp (4-bit, no decode) + qual reverse / copy of every output record "
+                    "(reverse_alignment_seq_and_qual, src/read_alignment_scanner.rs:125-133); bases + qualities resident in HBM",
+                    "records": int(o.n_records), "reads": int(ch.c.n_reads), "flipped_records": int(np.count_nonzero(res.rec_need_flip)),
+                    "kernel_ms": a_ms, "records_per_s": o.n_records / (a_ms / 1e3),
+                    "roofline": {"bound": "hbm", "achieved": a_bytes / (a_ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                                 "frac": a_bytes / (a_ms / 1e3) / 1e9 / peak, "algorithmic_bytes_per_launch": a_bytes, "traffic": None},
+                    "parity": f"byte-exact vs oracle on {sub.c.n_reads} reads of this workload"}
+
     # ---------------------------------------------------------------- CPU baseline (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -425,6 +469,7 @@ def main():
             "cpu_baseline": cpu,
             "clocks": sampler.summary(windows),
             "counters": cnt,
+            "assemble_bases": assemble,
         }
         print(json.dumps(line))
     if world > 1:

@@ -247,9 +247,9 @@ typedef struct {
 } ptl_read_quals;
 typedef struct {
     uint32_t n_records;
-    const uint64_t* rec_seq_begin;   /* [n_records+1] byte offsets into seq4; every record starts 4-byte aligned */
+    const uint64_t* rec_seq_begin;   /* [n_records+1] byte offsets into seq4; every record starts 16-byte aligned, zero padded */
     const uint8_t* seq4;
-    const uint64_t* rec_qual_begin;  /* [n_records+1] byte offsets into qual; every record starts 4-byte aligned */
+    const uint64_t* rec_qual_begin;  /* [n_records+1] byte offsets into qual; every record starts 16-byte aligned, zero padded */
     const uint8_t* qual;
     float kernel_ms;                 /* device time of the assembly kernel (CUDA events on the slot stream) */
     uint64_t bytes_read, bytes_written;  /* algorithmic bytes of that kernel: bases + qualities in, bases + qualities out */

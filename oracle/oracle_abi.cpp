@@ -438,8 +438,8 @@ int ptl_oracle_assemble_bases(ptl_ctx* ctx, int slot, const ptl_read_quals* qual
     sl.asm_qual_begin.assign(size_t(n_rec) + 1, 0);
     for (uint32_t k = 0; k < n_rec; ++k) {
         const uint64_t len = b.read_seq_len[rseg_read[sl.rec_read_segment[k]]];
-        sl.asm_seq_begin[k + 1] = sl.asm_seq_begin[k] + ((((len + 1) >> 1) + 3) & ~3ull);
-        sl.asm_qual_begin[k + 1] = sl.asm_qual_begin[k] + ((len + 3) & ~3ull);
+        sl.asm_seq_begin[k + 1] = sl.asm_seq_begin[k] + ((((len + 1) >> 1) + 15) & ~15ull);
+        sl.asm_qual_begin[k + 1] = sl.asm_qual_begin[k] + ((len + 15) & ~15ull);
     }
     sl.asm_seq4.assign(sl.asm_seq_begin[n_rec], 0);
     sl.asm_qual.assign(sl.asm_qual_begin[n_rec], 0);

@@ -418,8 +418,8 @@ __global__ void __launch_bounds__(256) assemble_sizes_kernel(uint32_t n_records,
     const uint32_t r = rseg_read[rec_read_segment[k]];
     const uint64_t len = read_seq_len[r];
     rec_read[k] = r;
-    seq_begin[k] = (((len + 1) >> 1) + 3) & ~3ull;
-    qual_begin[k] = (len + 3) & ~3ull;
+    seq_begin[k] = (((len + 1) >> 1) + 15) & ~15ull;
+    qual_begin[k] = (len + 15) & ~15ull;
 }
 // One block per output record (22.5 KB in, 22.5 KB out for a 15 kb read): HBM-bound streaming.
 __global__ void __launch_bounds__(256) assemble_records_kernel(AsmArgs A) { assemble_record_body(A, blockIdx.x, threadIdx.x, blockDim.x); }
