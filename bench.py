@@ -425,12 +425,19 @@ def main():
         _, pg = ctx.assemble_bases(sq, so, 1)
         if not all(np.array_equal(a, b) for a, b in zip(po, pg)):
             raise SystemExit("PARITY FAILURE vs oracle in ptl_assemble_bases on the bench workload")
+        a_traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["assemble_records_kernel"]
+            if tj["workload"] == args.workload and tj["reads"] == int(ch.c.n_reads):
+                a_traffic = tj["dram_bytes_per_launch"]
+        except Exception:
+            pass
         assemble = {"kernel": "assemble_records_kernel", "what": "seq revcomp (4-bit, no decode) + qual reverse / copy of every output record "
                     "(reverse_alignment_seq_and_qual, src/read_alignment_scanner.rs:125-133); bases + qualities resident in HBM",
                     "records": int(o.n_records), "reads": int(ch.c.n_reads), "flipped_records": int(np.count_nonzero(res.rec_need_flip)),
                     "kernel_ms": a_ms, "records_per_s": o.n_records / (a_ms / 1e3),
                     "roofline": {"bound": "hbm", "achieved": a_bytes / (a_ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
-                                 "frac": a_bytes / (a_ms / 1e3) / 1e9 / peak, "algorithmic_bytes_per_launch": a_bytes, "traffic": None},
+                                 "frac": a_bytes / (a_ms / 1e3) / 1e9 / peak, "algorithmic_bytes_per_launch": a_bytes, "traffic": a_traffic},
                     "parity": f"byte-exact vs oracle on {sub.c.n_reads} reads of this workload"}
 
     # ---------------------------------------------------------------- CPU baseline (rank 0, N=1 only)
