@@ -421,7 +421,9 @@ def main():
         octx_a = helpers.oracle_context(s, threads=min(8, os.cpu_count() or 1))
         helpers.lift_c(octx_a, sub.c)
         helpers.lift_c(ctx, sub.c, slot=1)
+        t0 = time.perf_counter()
         _, po = octx_a.assemble_bases(sq, so)
+        t_cpu = time.perf_counter() - t0
         _, pg = ctx.assemble_bases(sq, so, 1)
         if not all(np.array_equal(a, b) for a, b in zip(po, pg)):
             raise SystemExit("PARITY FAILURE vs oracle in ptl_assemble_bases on the bench workload")
@@ -438,6 +440,9 @@ def main():
                     "kernel_ms": a_ms, "records_per_s": o.n_records / (a_ms / 1e3),
                     "roofline": {"bound": "hbm", "achieved": a_bytes / (a_ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
                                  "frac": a_bytes / (a_ms / 1e3) / 1e9 / peak, "algorithmic_bytes_per_launch": a_bytes, "traffic": a_traffic},
+                    "cpu_baseline": {"value": len(po[0]) / t_cpu, "unit": "records/s", "cores": 1, "kind": "port",
+                                     "sample": f"{sub.c.n_reads} reads of this workload: decode -> rev_comp_in_place -> re-encode as the reference does, "
+                                               "incl. the python-side copy of the result"},
                     "parity": f"byte-exact vs oracle on {sub.c.n_reads} reads of this workload"}
 
     # ---------------------------------------------------------------- CPU baseline (rank 0, N=1 only)
