@@ -53,16 +53,16 @@ struct ReadBases {
 
 // ------------------------------------------------------------------------------------------------------------------
 // Streaming clean_up_cigar_edge_indels + compress_cigar.
-// The pending (not yet stored) op is kept as ONE packed BAM word; an empty sink holds the word 0 = "M of length 0", so
-// the first alignment match merges into it and anything else replaces it (a zero-length word is never stored).
+// The open (not yet stored) run is kept as (pop, plen) in two registers; an empty sink holds "M of length 0", so the
+// first alignment match merges into it and anything else replaces it (a zero-length run is never stored).
 struct OpSink {
     uint32_t* buf;
     uint32_t cap;
-    uint32_t n = 0;
-    uint32_t pend = 0;            // (len << 4) | op of the open run
-    int32_t last_match_idx = -1;  // index (in buf) of the last alignment-match op, counting the pending one
+    uint32_t n = 0;               // ops stored so far, counting the ones that did not fit (overflow <=> n > cap)
+    uint32_t pop = 0, plen = 0;   // op code and length of the open run
+    int32_t last_match_idx = -1;  // index (in buf) of the last alignment-match op, counting the open run
     bool seen_match = false;
-    bool overflow = false;
+    bool overflow = false;        // valid after finish() / close_unfinished()
     bool mixed_cluster = false;   // two adjacent stored ops are an I and a D: simplify_alignment_indels would rewrite them
     uint32_t lead_del_shift = 0;  // return value of clean_up_cigar_edge_indels
     uint32_t ref_span = 0;        // reference bases consumed by the stored ops = get_alignment_end - pos (after finish())
@@ -70,11 +70,10 @@ struct OpSink {
     __device__ __forceinline__ OpSink(uint32_t* b, uint32_t c) : buf(b), cap(c) {}
 
     __device__ __forceinline__ void flush() {
-        if (pend >> 4) {
-            if (n < cap) buf[n] = pend;
-            else overflow = true;
+        if (plen) {
+            if (n < cap) buf[n] = (plen << 4) | pop;
             ++n;
-            if ((kRefMask >> (pend & 0xfu)) & 1u) ref_span += pend >> 4;
+            if ((kRefMask >> pop) & 1u) ref_span += plen;
         }
     }
     // Branch-free: lanes of a warp push different ops at the same time, so every arm of a branchy push ran with a
@@ -89,26 +88,31 @@ struct OpSink {
         op = (lead && op == OP_I) ? uint32_t(OP_S) : op;
         const bool match = op_is_match(op) && len != 0u;
         seen_match |= match;
+        push_steady(op, len);
+    }
+    // The same without the leading-edge rules: valid once an alignment match has been pushed (seen_match).
+    __device__ __forceinline__ void push_steady(uint32_t op, uint32_t len) {
         // compress_cigar (cigar/mod.rs:204-228): merge into the open run or start a new one
-        const uint32_t pop = pend & 0xfu;
         const bool same = (pop == op) || len == 0u;
-        const bool store = !same && (pend >> 4) != 0u;
-        if (store) {
-            if (n < cap) buf[n] = pend;
-            else overflow = true;
-        }
+        const bool store = !same && plen != 0u;
+        if (store && n < cap) buf[n] = (plen << 4) | pop;
         n += store ? 1u : 0u;
-        ref_span += (store && ((kRefMask >> pop) & 1u)) ? (pend >> 4) : 0u;
+        ref_span += (store && ((kRefMask >> pop) & 1u)) ? plen : 0u;
         // an I/D run of the compressed CIGAR holds both kinds iff two adjacent stored ops are {I, D}
         mixed_cluster |= !same && (((1u << pop) | (1u << op)) == ((1u << OP_I) | (1u << OP_D)));
         // a Pad after a Pad is dropped, not merged (cigar/mod.rs:208-215)
-        pend = same ? pend + ((op != OP_P && len != 0u) ? (len << 4) : 0u) : ((len << 4) | op);
-        last_match_idx = match ? int32_t(n) : last_match_idx;
+        plen = same ? plen + ((op != OP_P) ? len : 0u) : len;
+        pop = same ? pop : op;
+        last_match_idx = (op_is_match(op) && len != 0u) ? int32_t(n) : last_match_idx;
     }
+    // a stage that ends without finish() (liftover to None): only the capacity verdict is needed
+    __device__ __forceinline__ void close_unfinished() { overflow = n > cap; }
     // trailing edge (cigar/mod.rs:282-288) + re-merge of what the conversion made adjacent
     __device__ __forceinline__ void finish() {
         flush();
-        pend = 0;
+        plen = 0;
+        pop = 0;
+        overflow = n > cap;
         if (overflow || last_match_idx < 0) return;  // no match at all: the leading pass already converted everything
         const uint32_t start = uint32_t(last_match_idx) + 1u;
         uint32_t w = start, prev = NO_OP;
@@ -360,14 +364,18 @@ __device__ __forceinline__ bool run_liftover(const OpSource& in, uint32_t pos, c
     int32_t start = 0;  // reference positions fit int32 (BAM)
     uint32_t p = pos, e = pos;  // [p, e) = what is left of the open reference-consuming op; e == p: none open
     uint32_t i = 0, main_op = 0;
-    uint32_t c_next = in.n ? in.get(0) : 0u;  // software prefetch: the load of op i+1 overlaps the work on op i
-    for (;;) {
-        uint32_t gap = 0, m_op = 0, m_len = 0;
+    // op i sits at q[i * step] (the CIGAR reversal of a stage test without the left shift is just a stride)
+    const uint32_t* q = in.reversed ? in.p + (in.n ? in.n - 1u : 0u) : in.p;
+    const int step = in.reversed ? -1 : 1;
+    uint32_t c_next = in.n ? q[0] : 0u;  // software prefetch: the load of op i+1 overlaps the work on op i
+    // One event of the walk up to its push: [fetch the next op] -> [cross a table key] -> [the bounds of one piece].
+    // Returns false when the ops are exhausted.
+    auto step_event = [&](uint32_t& m_op, uint32_t& m_len, uint32_t& plen, bool& piece) -> bool {
         if (e == p) {  // fetch the next op
-            if (i == in.n) break;
+            if (i == in.n) return false;
             const uint32_t c = c_next;
             ++i;
-            if (i < in.n) c_next = in.get(i);
+            if (i < in.n) c_next = q[int64_t(i) * step];
             const uint32_t op = c & 0xfu, len = c >> 4;
             if ((kRefMask >> op) & 1u) {
                 e = p + len;  // an empty op opens nothing: no piece (get_ref_range of an empty interval)
@@ -378,7 +386,8 @@ __device__ __forceinline__ bool run_liftover(const OpSource& in, uint32_t pos, c
                 m_len = len;
             }
         }
-        if (e != p) {  // one piece of the open op against the block under p (update_ref2_cigar_segment)
+        piece = e != p;
+        if (piece) {  // one piece of the open op against the block under p (update_ref2_cigar_segment)
             if (nk == p) {  // the walk reached the next key: it becomes the current block
                 blk_k = nk;
                 blk_v = nv;
@@ -394,12 +403,23 @@ __device__ __forceinline__ bool run_liftover(const OpSource& in, uint32_t pos, c
                 }
             }
             const uint32_t seg_end = min(nk, e);  // > p: keys are strictly increasing
-            const uint32_t plen = seg_end - p;
+            plen = seg_end - p;
+            p = seg_end;
+        }
+        return true;
+    };
+    // ---- until the start position is known (leading clips, pieces outside aligned blocks: a few events)
+    while (!start_set) {
+        uint32_t m_op = 0, m_len = 0, plen = 0, gap = 0;
+        bool piece = false;
+        if (!step_event(m_op, m_len, plen, piece)) break;
+        if (piece) {
             if (blk_v >= 0) {
-                if (is_match && !start_set) { start = blk_v + int32_t(p - blk_k); start_set = true; }  // :84-88
-                if (start_set) {
-                    if (some_seen) gap = pgap;  // :91-96, only the first piece of a block can see a positive distance
-                    m_op = main_op;             // :102-109
+                if (is_match) {  // :84-88
+                    start = blk_v + int32_t(p - plen - blk_k);
+                    start_set = true;
+                    if (some_seen) gap = pgap;  // :91-96 (a leading deletion: the sink turns it into a position shift)
+                    m_op = OP_M;
                     m_len = plen;
                 }
                 pgap = 0;
@@ -408,12 +428,35 @@ __device__ __forceinline__ bool run_liftover(const OpSource& in, uint32_t pos, c
                 m_op = (blk_v == -1) ? uint32_t(OP_I) : uint32_t(OP_S);  // None block: insertion (:111-115); no block: clip (:117-123)
                 m_len = plen;
             }
-            p = seg_end;
         }
         if (gap) sink.push(OP_D, gap);
         sink.push(m_op, m_len);
     }
-    if (!start_set) return false;
+    if (!start_set) {
+        sink.close_unfinished();
+        return false;
+    }
+    // ---- steady state (ncu s5b: the one-loop-for-everything version spent 150 instructions per event): the start is
+    //      set, a Some piece and an alignment match have been seen, so the leading-edge rules of both the liftover and
+    //      the sink are out of the way
+    for (;;) {
+        uint32_t m_op = 0, m_len = 0, plen = 0, gap = 0;
+        bool piece = false;
+        if (!step_event(m_op, m_len, plen, piece)) break;
+        if (piece) {
+            if (blk_v >= 0) {
+                gap = pgap;  // :91-96, only the first piece of a block can see a positive distance
+                pgap = 0;
+                m_op = main_op;  // :102-109
+                m_len = plen;
+            } else if (is_match) {
+                m_op = (blk_v == -1) ? uint32_t(OP_I) : uint32_t(OP_S);
+                m_len = plen;
+            }
+        }
+        if (gap) sink.push_steady(OP_D, gap);
+        sink.push_steady(m_op, m_len);
+    }
     sink.finish();
     *out_pos = int64_t(start) + int64_t(sink.lead_del_shift);
     return true;
