@@ -367,15 +367,21 @@ __device__ __forceinline__ bool run_liftover(const OpSource& in, uint32_t pos, c
     // op i sits at q[i * step] (the CIGAR reversal of a stage test without the left shift is just a stride)
     const uint32_t* q = in.reversed ? in.p + (in.n ? in.n - 1u : 0u) : in.p;
     const int step = in.reversed ? -1 : 1;
-    uint32_t c_next = in.n ? q[0] : 0u;  // software prefetch: the load of op i+1 overlaps the work on op i
+    uint32_t c_next = in.n ? q[0] : 0u;  // software prefetch: the op the NEXT fetch will consume
     // One event of the walk up to its push: [fetch the next op] -> [cross a table key] -> [the bounds of one piece].
     // Returns false when the ops are exhausted.
     auto step_event = [&](uint32_t& m_op, uint32_t& m_len, uint32_t& plen, bool& piece) -> bool {
-        if (e == p) {  // fetch the next op
-            if (i == in.n) return false;
-            const uint32_t c = c_next;
-            ++i;
-            if (i < in.n) c_next = q[int64_t(i) * step];
+        const bool fetch = e == p;
+        if (fetch && i == in.n) return false;
+        // The prefetch is issued unconditionally at the top of the event and handed over at its END: written inside
+        // the fetch arm, the compiler merged the loaded value into c_next right there and every event waited for
+        // its own load (ncu s5b: 11 % of the kernel's stall samples on that one move).
+        const uint32_t i_after = i + (fetch ? 1u : 0u);
+        const uint32_t c_pf = q[int64_t(min(i_after, in.n - 1u)) * step];
+        const uint32_t c = c_next;
+        c_next = c_pf;
+        if (fetch) {  // fetch the next op
+            i = i_after;
             const uint32_t op = c & 0xfu, len = c >> 4;
             if ((kRefMask >> op) & 1u) {
                 e = p + len;  // an empty op opens nothing: no piece (get_ref_range of an empty interval)
