@@ -236,8 +236,13 @@ __device__ __forceinline__ uint32_t run_left_shift_warp(bool active, const OpSou
             del = 0;
             ins = 0;
         };
+        // op i sits at q[i * step]; the load of op i+1 is issued before op i is looked at
+        const uint32_t* q = in.reversed ? in.p + (in.n ? in.n - 1u : 0u) : in.p;
+        const int step = in.reversed ? -1 : 1;
+        uint32_t c_next = in.n ? q[0] : 0u;
         for (uint32_t i = 0; i < in.n; ++i) {
-            const uint32_t c = in.get(i);
+            const uint32_t c = c_next;
+            c_next = q[int64_t(min(i + 1u, in.n - 1u)) * step];
             const uint32_t op = c & 0xfu, len = c >> 4;
             if (op == OP_D || op == OP_I) {
                 if (len > 0) {
@@ -277,9 +282,13 @@ __device__ __forceinline__ uint32_t run_left_shift_warp(bool active, const OpSou
     if (active) {
         uint32_t match_block = 0, del = 0, ins = 0, k = 0;
         bool in_indel = false;
+        const uint32_t* q = in.reversed ? in.p + (in.n ? in.n - 1u : 0u) : in.p;
+        const int step = in.reversed ? -1 : 1;
+        uint32_t c_next = in.n ? q[0] : uint32_t(OP_S);
         for (uint32_t i = 0; i <= in.n; ++i) {
             // the sentinel behaves like get_cigar's add_other(None): closes a trailing cluster, flushes the match block
-            const uint32_t c = (i < in.n) ? in.get(i) : uint32_t(OP_S);
+            const uint32_t c = c_next;
+            c_next = (i + 1u < in.n) ? q[int64_t(i + 1u) * step] : uint32_t(OP_S);
             const uint32_t op = c & 0xfu, len = c >> 4;
             uint32_t m1 = 0, e_ins = 0, e_del = 0, m2 = 0, o_len = 0;
             if (op == OP_D || op == OP_I) {
