@@ -86,7 +86,7 @@ struct Slot {
     DBuf d_read_flag, d_read_mapq, d_read_bin, d_read_seq_len, d_read_seq_off, d_read_seg_begin, d_rseg_contig, d_rseg_pos,
         d_rseg_is_fwd, d_rseg_cigar_begin, d_rseg_cigar_len, d_cigar, d_seq4, d_arena, d_win_begin, d_win;
     // work
-    DBuf w_rseg_read, w_rseg_pair_begin, w_rseg_ref_len, w_rseg_n_id, w_rseg_read_len, w_pair_cap_b, w_pair_rseg, w_pair_seg, w_pair_slot_begin, w_pair_status, w_pair_flip,
+    DBuf w_rseg_read, w_rseg_pair_begin, w_rseg_ref_len, w_rseg_n_id, w_rseg_read_len, w_pair_cap_b, w_pair_tab_lo, w_pair_rseg, w_pair_seg, w_pair_slot_begin, w_pair_status, w_pair_flip,
         w_pair_pos, w_pair_n_out, w_pair_bin, w_pair_out_off, w_simplify_list, w_long_list, w_scratch, w_read_counts, w_read_primary, w_scan_tmp, w_totals;
     // record assembly (ptl_assemble_bases): uploaded qualities, per-record offsets, output pools and their pinned twins
     DBuf a_qual, a_qual_off, a_rec_read, a_seq_begin, a_qual_begin, a_out_seq, a_out_qual;
@@ -313,6 +313,7 @@ void size_work(Slot& sl, uint32_t want_pairs, uint64_t want_scratch, uint64_t wa
     sl.w_pair_seg.ensure(size_t(pc) * 4, st);
     sl.w_pair_slot_begin.ensure((size_t(pc) + 1) * 8, st);
     sl.w_pair_cap_b.ensure(size_t(pc) * 4, st);
+    sl.w_pair_tab_lo.ensure(size_t(pc) * 4, st);
     sl.w_pair_status.ensure(size_t(pc), st);
     sl.w_pair_flip.ensure(size_t(pc), st);
     sl.w_pair_pos.ensure(size_t(pc) * 8, st);
@@ -326,6 +327,7 @@ void size_work(Slot& sl, uint32_t want_pairs, uint64_t want_scratch, uint64_t wa
     W.pair_seg = sl.w_pair_seg.as<uint32_t>();
     W.pair_slot_begin = sl.w_pair_slot_begin.as<uint64_t>();
     W.pair_cap_b = sl.w_pair_cap_b.as<uint32_t>();
+    W.pair_tab_lo = sl.w_pair_tab_lo.as<uint32_t>();
     W.pair_status = sl.w_pair_status.as<int8_t>();
     W.pair_flip = sl.w_pair_flip.as<uint8_t>();
     W.pair_pos = sl.w_pair_pos.as<int64_t>();
@@ -529,7 +531,7 @@ void ptl_destroy(ptl_ctx* ctx) {
         if (sl.stream) cudaStreamSynchronize(sl.stream);
         for (DBuf* b : {&sl.d_read_flag, &sl.d_read_mapq, &sl.d_read_bin, &sl.d_read_seq_len, &sl.d_read_seq_off, &sl.d_read_seg_begin,
                         &sl.d_rseg_contig, &sl.d_rseg_pos, &sl.d_rseg_is_fwd, &sl.d_rseg_cigar_begin, &sl.d_rseg_cigar_len, &sl.d_cigar,
-                        &sl.d_seq4, &sl.d_arena, &sl.d_win_begin, &sl.d_win, &sl.w_rseg_read, &sl.w_rseg_pair_begin, &sl.w_rseg_ref_len, &sl.w_rseg_n_id, &sl.w_rseg_read_len, &sl.w_pair_cap_b, &sl.w_pair_rseg, &sl.w_pair_seg,
+                        &sl.d_seq4, &sl.d_arena, &sl.d_win_begin, &sl.d_win, &sl.w_rseg_read, &sl.w_rseg_pair_begin, &sl.w_rseg_ref_len, &sl.w_rseg_n_id, &sl.w_rseg_read_len, &sl.w_pair_cap_b, &sl.w_pair_tab_lo, &sl.w_pair_rseg, &sl.w_pair_seg,
                         &sl.w_pair_slot_begin, &sl.w_pair_status, &sl.w_pair_flip, &sl.w_pair_pos, &sl.w_pair_n_out, &sl.w_pair_bin, &sl.w_pair_out_off, &sl.w_simplify_list, &sl.w_long_list,
                         &sl.w_scratch, &sl.w_read_counts, &sl.w_read_primary, &sl.w_scan_tmp, &sl.w_totals, &sl.r_arena, &sl.a_qual, &sl.a_qual_off,
                         &sl.a_rec_read, &sl.a_seq_begin, &sl.a_qual_begin, &sl.a_out_seq, &sl.a_out_qual})

@@ -92,6 +92,7 @@ struct DevWork {
     uint32_t* pair_seg = nullptr;        // global contig-segment index
     uint64_t* pair_slot_begin = nullptr; // [pair_cap+1] (bound, then exclusive scan in place) ops of scratch
     uint32_t* pair_cap_b = nullptr;      // capacity of the pair's buffer B (the slot is [B | A])
+    uint32_t* pair_tab_lo = nullptr;     // first table entry with key >= the start of the walked contig interval (cursor hint)
     int8_t* pair_status = nullptr;
     uint8_t* pair_flip = nullptr;
     int64_t* pair_pos = nullptr;

@@ -343,30 +343,45 @@ __device__ __forceinline__ uint32_t run_left_shift_warp(bool active, const OpSou
 // the entry's precomputed `gap` (TabEntry) - valid iff some Some piece was seen before (the walk touched that run).
 // Returns true if ref2_start_pos was set (Some); *out_pos = start + leading-deletion shift.
 __device__ __forceinline__ bool run_liftover(const OpSource& in, uint32_t pos, const TabEntry* __restrict__ tab, uint32_t t0, uint32_t t1,
-                                             OpSink& sink, int64_t* out_pos) {
+                                             uint32_t hint, OpSink& sink, int64_t* out_pos) {
     constexpr uint32_t INF = 0xffffffffu;
     // block cursor: the current block is the greatest key <= the walk position (blk_v: >= 0 Some, -1 None, -2 before
     // the first key); (nk, nv, ngap) = the prefetched NEXT entry, ti = its index
     uint32_t ti, nk = INF, ngap = 0, blk_k = 0, pgap = 0;
     int32_t blk_v = -2, nv = -1;
     {
-        uint32_t lo = t0, hi = t1;  // first index with key > pos
-        while (lo < hi) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (tab[mid].key <= pos) lo = mid + 1;
-            else hi = mid;
+        // first index with key > pos.  `hint` = first index with key >= the start of the pair's contig interval (from the
+        // pair enumeration, which searched the table for the slot bounds anyway); pos is that start, or a little
+        // beyond it when the left shift dropped a leading deletion, so the cursor is 0-1 steps away - the 13 dependent
+        // loads of a binary search per pair were 5 % of the kernel's stall samples (ncu s5b).
+        uint32_t lo = min(max(hint, t0), t1);
+        bool have_prev = lo > t0, have_next = lo < t1;
+        TabEntry prev{0, 0, 0, 0}, next{0, 0, 0, 0};
+        if (have_prev) prev = tab[lo - 1];  // (both loads are in flight together)
+        if (have_next) next = tab[lo];
+        while (have_next && next.key <= pos) {
+            prev = next;
+            have_prev = true;
+            ++lo;
+            have_next = lo < t1;
+            if (have_next) next = tab[lo];
+        }
+        while (have_prev && prev.key > pos) {  // (never taken for a valid hint)
+            next = prev;
+            have_next = true;
+            --lo;
+            have_prev = lo > t0;
+            if (have_prev) prev = tab[lo - 1];
         }
         ti = lo;
-        if (lo > t0) {
-            const TabEntry b = tab[lo - 1];
-            blk_k = b.key;
-            blk_v = b.val;
+        if (have_prev) {
+            blk_k = prev.key;
+            blk_v = prev.val;
         }
-        if (lo < t1) {
-            const TabEntry b = tab[lo];
-            nk = b.key;
-            nv = b.val;
-            ngap = b.gap;
+        if (have_next) {
+            nk = next.key;
+            nv = next.val;
+            ngap = next.gap;
         }
     }
     bool start_set = false, some_seen = false, is_match = false;

@@ -130,7 +130,9 @@ __device__ __forceinline__ void pair_fill_body(const DevStatic& S, const DevBatc
             const bool fwd = S.seg_is_fwd[g] != 0;
             const int64_t a = fwd ? start : int64_t(S.contig_len[ctg]) - end;
             const uint32_t t0 = S.seg_tab_begin[g], t1 = S.seg_tab_begin[g + 1];
-            const uint32_t n_keys = lower_bound_key(S.table, t0, t1, a + ref_len) - lower_bound_key(S.table, t0, t1, a);
+            const uint32_t tab_lo = lower_bound_key(S.table, t0, t1, a);
+            const uint32_t n_keys = lower_bound_key(S.table, t0, t1, a + ref_len) - tab_lo;
+            W.pair_tab_lo[p] = tab_lo;  // the liftover starts its table cursor here instead of searching again
             // op-slot bounds, in stored (compressed) ops:
             //   shifted    <= n_in + n_id + 1            (each I/D op can split one match block in two)
             //   lifted     <= shifted + 2 n_keys          (one extra piece and one gap-D per table key in range)
@@ -258,7 +260,7 @@ __device__ __forceinline__ void lift_pair_body(const DevStatic& S, const DevBatc
     if (usable && !err && (stage_mask & 2u)) {
         OpSink sink(buf_b, cap_b);
         int64_t lifted_pos = 0;
-        const bool some = run_liftover(cur, cpos, S.table, S.seg_tab_begin[g], S.seg_tab_begin[g + 1], sink, &lifted_pos);
+        const bool some = run_liftover(cur, cpos, S.table, S.seg_tab_begin[g], S.seg_tab_begin[g + 1], W.pair_tab_lo[p], sink, &lifted_pos);
         if (sink.overflow) err = ST_ERR_CAPACITY;
         else if (!some) status = ST_NONE;
         else if (W.rseg_read_len[s] != seq_len) err = ST_ERR_LENGTH;

@@ -172,14 +172,14 @@ int run_batch(ptl_ctx* ctx, EmulSlot& sl, const ptl_batch* b, uint32_t stage_mas
     exclusive_scan(rseg_pair_begin.data(), size_t(ns) + 1);
     const uint32_t np = rseg_pair_begin[ns];
     T.n_pairs = np;
-    std::vector<uint32_t> pair_rseg(np + 1), pair_seg(np + 1), pair_cap_b(np + 1), pair_n_out(np + 1), simplify_list(np + 1);
+    std::vector<uint32_t> pair_rseg(np + 1), pair_seg(np + 1), pair_cap_b(np + 1), pair_tab_lo(np + 1), pair_n_out(np + 1), simplify_list(np + 1);
     std::vector<uint64_t> pair_slot_begin(size_t(np) + 1, 0), pair_out_off(np + 1);
     std::vector<int8_t> pair_status(np + 1);
     std::vector<uint8_t> pair_flip(np + 1);
     std::vector<int64_t> pair_pos(np + 1);
     std::vector<uint16_t> pair_bin(np + 1);
     W.pair_cap = np;
-    W.pair_rseg = pair_rseg.data(); W.pair_seg = pair_seg.data(); W.pair_slot_begin = pair_slot_begin.data(); W.pair_cap_b = pair_cap_b.data();
+    W.pair_rseg = pair_rseg.data(); W.pair_seg = pair_seg.data(); W.pair_slot_begin = pair_slot_begin.data(); W.pair_cap_b = pair_cap_b.data(); W.pair_tab_lo = pair_tab_lo.data();
     W.pair_status = pair_status.data(); W.pair_flip = pair_flip.data(); W.pair_pos = pair_pos.data(); W.pair_n_out = pair_n_out.data();
     W.pair_bin = pair_bin.data(); W.pair_out_off = pair_out_off.data(); W.simplify_list = simplify_list.data();
     std::vector<uint32_t> long_list(np + 1);
