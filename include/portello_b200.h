@@ -260,6 +260,42 @@ typedef struct {
 #define PTL_ASM_NO_DOWNLOAD 2u
 int ptl_assemble_bases(ptl_ctx* ctx, int slot, const ptl_read_quals* quals, uint32_t flags, ptl_record_bases* out);
 
+/* ---------------------------------------------------------------- record assembly, whole BAM records
+ *
+ * Every OUTPUT record of the slot's last batch as the bytes bam_write1 would emit for it (SAM spec 4.2: block_size,
+ * refID, pos, l_read_name, mapq, bin, n_cigar_op, flag, l_seq, next_refID, next_pos, tlen, read_name, cigar, seq, qual,
+ * aux), i.e. the record get_liftover_alignment_for_read_and_contig_segment + finish_remapped_alignment_set leave behind:
+ *   clone_record (src/read_alignment_scanner.rs:105-117): the input record minus the FIRST NM, SA, PS and ZM tag;
+ *   set_tid / set_mapq / set_pos / set_cigar / set_bin / flags (:245-282); mate fields and every other tag untouched;
+ *   push_aux PS:Z:{contig}_split{index}{+|-} and ZM:C:{MAPQ of the input record} (:255-269);
+ *   reverse_alignment_seq_and_qual when the record was flipped (:125-133, as ptl_assemble_bases);
+ *   push_aux SA:Z = "{chrom},{pos+1},{+|-},{CIGAR},{mapq},0;" of every OTHER record of the read, in order (:292-301,349-363);
+ *   the unmapped fallback (:317-335): no CIGAR, tid/pos -1, MAPQ 255, original bin, no tag appended.
+ * Aux order: surviving input tags, PS, ZM, SA.  A lifted CIGAR with more than 65535 ops is an error (htslib would move
+ * it into a CG tag at write time; BAM encoding is out of scope).
+ * Needs ptl_set_names once (contig names of the read->assembly header for PS, reference names for SA). */
+int ptl_set_names(ptl_ctx* ctx, uint32_t n_contigs, const char* const* contig_names, uint32_t n_chrom, const char* const* chrom_names);
+typedef struct {
+    const uint64_t* name_off;       /* [n_reads+1] into names: qname bytes of read r WITHOUT the trailing NUL */
+    const uint8_t* names;
+    const uint64_t* aux_off;        /* [n_reads+1] into aux: the raw BAM aux block of read r */
+    const uint8_t* aux;
+    const int32_t* mate_tid;        /* [n_reads] next_refID */
+    const int32_t* mate_pos;        /* [n_reads] next_pos */
+    const int32_t* tlen;            /* [n_reads] */
+    ptl_read_quals quals;           /* as ptl_assemble_bases */
+} ptl_read_extras;
+typedef struct {
+    uint32_t n_records;
+    const uint64_t* rec_begin;       /* [n_records+1] byte offsets into bytes; record k = block_size (u32) + block_size bytes */
+    const uint8_t* bytes;
+    float kernel_ms;                 /* device time of the record-writing kernel (CUDA events on the slot stream) */
+    uint64_t bytes_read, bytes_written;  /* algorithmic bytes of that kernel: every input byte of a record once, every output byte once */
+} ptl_bam_records;
+/* flags: PTL_ASM_RESIDENT_QUAL = everything uploaded by the previous call on this slot is reused (no H2D; extras may be NULL);
+ *        PTL_ASM_NO_DOWNLOAD   = results stay on the device (out->bytes is NULL): kernel timing only. */
+int ptl_assemble_records(ptl_ctx* ctx, int slot, const ptl_read_extras* extras, uint32_t flags, ptl_bam_records* out);
+
 /* cudaStream_t of a slot (as void*), so callers can bracket work with their own CUDA events. */
 void* ptl_slot_stream(ptl_ctx* ctx, int slot);
 /* Per-kernel device time of the LAST ptl_lift_run on the slot, CUDA events on the slot stream.

@@ -38,6 +38,9 @@ struct Slot {
     ptl_batch batch{};
     std::vector<uint64_t> asm_seq_begin, asm_qual_begin;
     std::vector<uint8_t> asm_seq4, asm_qual;
+    // ptl_oracle_assemble_records
+    std::vector<uint64_t> bam_begin;
+    std::vector<uint8_t> bam_bytes;
 };
 
 // Flat copy of the installed segments, lent out by ptl_oracle_get_contig_segments.
@@ -65,6 +68,7 @@ struct ptl_ctx {
     AllContigMappingInfo contigs;
     FlatSegments flat;
     std::vector<Slot> slots;
+    std::vector<std::string> contig_names, chrom_names;  // ptl_oracle_set_names
 };
 
 namespace {
@@ -467,6 +471,172 @@ int ptl_oracle_assemble_bases(ptl_ctx* ctx, int slot, const ptl_read_quals* qual
     out->rec_qual_begin = sl.asm_qual_begin.data();
     out->qual = sl.asm_qual.data();
     out->bytes_read = out->bytes_written = sl.asm_seq_begin[n_rec] + sl.asm_qual_begin[n_rec];
+    return PTL_OK;
+}
+int ptl_oracle_set_names(ptl_ctx* ctx, uint32_t n_contigs, const char* const* contig_names, uint32_t n_chrom, const char* const* chrom_names) {
+    if (!ctx || (n_contigs && !contig_names) || (n_chrom && !chrom_names)) return PTL_ERR_INVALID_ARG;
+    ctx->contig_names.assign(contig_names, contig_names + n_contigs);
+    ctx->chrom_names.assign(chrom_names, chrom_names + n_chrom);
+    return PTL_OK;
+}
+
+namespace {
+// [begin, end) of the FIRST aux field named `tag` (htslib bam_aux_get + bam_aux_del as used by remove_aux), or false.
+// Field sizes per SAM spec 4.2.4; a malformed tail ends the search (nothing behind it can be found).
+bool find_aux(const uint8_t* aux, size_t n, const char* tag, size_t* begin, size_t* end) {
+    size_t i = 0;
+    while (i + 3 <= n) {
+        const size_t start = i;
+        const uint8_t type = aux[i + 2];
+        i += 3;
+        size_t sz = 0;
+        switch (type) {
+            case 'A': case 'c': case 'C': sz = 1; break;
+            case 's': case 'S': sz = 2; break;
+            case 'i': case 'I': case 'f': sz = 4; break;
+            case 'd': sz = 8; break;
+            case 'Z': case 'H': {
+                size_t j = i;
+                while (j < n && aux[j] != 0) ++j;
+                if (j >= n) return false;
+                sz = j - i + 1;
+                break;
+            }
+            case 'B': {
+                if (i + 5 > n) return false;
+                const uint8_t sub = aux[i];
+                uint32_t cnt;
+                std::memcpy(&cnt, aux + i + 1, 4);
+                size_t es = 0;
+                switch (sub) {
+                    case 'c': case 'C': es = 1; break;
+                    case 's': case 'S': es = 2; break;
+                    case 'i': case 'I': case 'f': es = 4; break;
+                    default: return false;
+                }
+                sz = 5 + size_t(cnt) * es;
+                break;
+            }
+            default: return false;
+        }
+        if (i + sz > n) return false;
+        i += sz;
+        if (aux[start] == uint8_t(tag[0]) && aux[start + 1] == uint8_t(tag[1])) { *begin = start; *end = i; return true; }
+    }
+    return false;
+}
+void put_u32(std::vector<uint8_t>& v, uint32_t x) { for (int b = 0; b < 4; ++b) v.push_back(uint8_t(x >> (8 * b))); }
+void put_u16(std::vector<uint8_t>& v, uint16_t x) { v.push_back(uint8_t(x)); v.push_back(uint8_t(x >> 8)); }
+}  // namespace
+
+// Record assembly, whole records: clone_record (src/read_alignment_scanner.rs:105-117) + the field updates and tag
+// pushes of :245-282 + finish_remapped_alignment_set (:310-366), serialised the way bam_write1 lays a record out
+// (SAM spec 4.2).  Tag payloads follow rust-htslib push_aux: Aux::String -> 'Z' + bytes + NUL, Aux::U8 -> 'C' + byte.
+int ptl_oracle_assemble_records(ptl_ctx* ctx, int slot, const ptl_read_extras* x, uint32_t /*flags*/, ptl_bam_records* out) {
+    if (!ctx || !out || !x || slot < 0 || slot >= ctx->n_slots) return PTL_ERR_INVALID_ARG;
+    Slot& sl = ctx->slots[size_t(slot)];
+    if (!sl.submitted) return fail(ctx, PTL_ERR_STATE, "assemble without a lifted batch");
+    const ptl_batch& b = sl.batch;
+    const uint32_t n_rec = sl.res.n_records;
+    static const char kOps[] = "MIDNSHP=X";
+    auto encode = [](uint8_t c) -> uint8_t {  // htslib seq_nt16_table restricted to what rev_comp can produce
+        switch (c) { case 'A': return 1; case 'C': return 2; case 'G': return 4; case 'T': return 8; default: return 15; }
+    };
+    sl.bam_begin.assign(1, 0);
+    sl.bam_bytes.clear();
+    for (uint32_t r = 0; r < b.n_reads; ++r) {
+        const uint32_t k0 = sl.read_rec_begin[r], k1 = sl.read_rec_begin[r + 1];
+        if (k0 == k1) continue;
+        const uint8_t* aux = x->aux + x->aux_off[r];
+        const size_t aux_n = size_t(x->aux_off[r + 1] - x->aux_off[r]);
+        // clone_record: remove NM, then SA, PS, ZM (each: first occurrence, on the already shortened block)
+        std::vector<uint8_t> kept(aux, aux + aux_n);
+        for (const char* tag : {"NM", "SA", "PS", "ZM"}) {
+            size_t a = 0, e = 0;
+            if (find_aux(kept.data(), kept.size(), tag, &a, &e)) kept.erase(kept.begin() + long(a), kept.begin() + long(e));
+        }
+        // get_sa_tag_segment of every record of the read (:292-301)
+        std::vector<std::string> sa(k1 - k0);
+        for (uint32_t k = k0; k < k1; ++k) {
+            if (sl.rec_status[k] != 1) continue;
+            const int32_t tid = sl.rec_tid[k];
+            if (tid < 0 || size_t(tid) >= ctx->chrom_names.size()) return fail(ctx, PTL_ERR_STATE, "ptl_set_names: no name for a reference chromosome");
+            std::string t = ctx->chrom_names[size_t(tid)] + "," + std::to_string(sl.rec_pos[k] + 1) + "," + ((sl.rec_flag[k] & 0x10) ? "-" : "+") + ",";
+            for (uint64_t i = sl.rec_cigar_begin[k]; i < sl.rec_cigar_begin[k + 1]; ++i) {
+                t += std::to_string(sl.cigar[i] >> 4);
+                t += kOps[std::min<uint32_t>(sl.cigar[i] & 0xfu, 8)];
+            }
+            t += "," + std::to_string(unsigned(sl.rec_mapq[k])) + ",0;";
+            sa[k - k0] = t;
+        }
+        const uint64_t len = b.read_seq_len[r];
+        const uint8_t* seq4 = b.seq4 + b.read_seq_off[r];
+        const uint8_t* q = x->quals.qual + x->quals.read_qual_off[r];
+        const uint8_t* name = x->names + x->name_off[r];
+        const size_t name_n = size_t(x->name_off[r + 1] - x->name_off[r]);
+        for (uint32_t k = k0; k < k1; ++k) {
+            const bool lifted = sl.rec_status[k] == 1;
+            std::vector<uint8_t> a = kept;
+            const uint64_t c0 = sl.rec_cigar_begin[k], c1 = sl.rec_cigar_begin[k + 1];
+            if (lifted) {
+                const uint32_t s = sl.rec_read_segment[k];
+                const uint32_t ctg = b.rseg_contig[s];
+                if (ctg >= ctx->contig_names.size()) return fail(ctx, PTL_ERR_STATE, "ptl_set_names: no name for a contig");
+                const uint32_t g = ctx->flat.contig_seg_begin[ctg] + sl.rec_contig_segment[k];
+                const std::string ps = ctx->contig_names[ctg] + "_split" + std::to_string(sl.rec_contig_segment[k]) + (ctx->flat.is_fwd[g] ? "+" : "-");
+                a.insert(a.end(), {'P', 'S', 'Z'});
+                a.insert(a.end(), ps.begin(), ps.end());
+                a.push_back(0);
+                a.insert(a.end(), {'Z', 'M', 'C', b.read_mapq[r]});
+                std::string text;
+                for (uint32_t j = k0; j < k1; ++j)
+                    if (j != k) text += sa[j - k0];
+                if (!text.empty()) {
+                    a.insert(a.end(), {'S', 'A', 'Z'});
+                    a.insert(a.end(), text.begin(), text.end());
+                    a.push_back(0);
+                }
+                if (c1 - c0 > 65535) return fail(ctx, PTL_ERR_STATE, "a lifted CIGAR has more than 65535 ops");
+            }
+            std::vector<uint8_t> rec;
+            put_u32(rec, uint32_t(sl.rec_tid[k]));
+            put_u32(rec, uint32_t(int32_t(sl.rec_pos[k])));
+            rec.push_back(uint8_t(name_n + 1));
+            rec.push_back(sl.rec_mapq[k]);
+            put_u16(rec, sl.rec_bin[k]);
+            put_u16(rec, uint16_t(lifted ? c1 - c0 : 0));
+            put_u16(rec, sl.rec_flag[k]);
+            put_u32(rec, uint32_t(len));
+            put_u32(rec, uint32_t(x->mate_tid[r]));
+            put_u32(rec, uint32_t(x->mate_pos[r]));
+            put_u32(rec, uint32_t(x->tlen[r]));
+            rec.insert(rec.end(), name, name + name_n);
+            rec.push_back(0);
+            if (lifted)
+                for (uint64_t i = c0; i < c1; ++i) put_u32(rec, sl.cigar[i]);
+            if (!sl.rec_need_flip[k]) {
+                rec.insert(rec.end(), seq4, seq4 + ((len + 1) >> 1));
+                rec.insert(rec.end(), q, q + len);
+            } else {  // reverse_alignment_seq_and_qual (:125-133)
+                std::vector<uint8_t> ascii = decode_seq4(seq4, len);
+                rev_comp_in_place(ascii);
+                std::vector<uint8_t> packed((len + 1) >> 1, 0);
+                for (uint64_t i = 0; i < len; ++i) packed[i >> 1] |= uint8_t(encode(ascii[i]) << ((i & 1) ? 0 : 4));
+                rec.insert(rec.end(), packed.begin(), packed.end());
+                for (uint64_t i = 0; i < len; ++i) rec.push_back(q[len - 1 - i]);
+            }
+            rec.insert(rec.end(), a.begin(), a.end());
+            put_u32(sl.bam_bytes, uint32_t(rec.size()));
+            sl.bam_bytes.insert(sl.bam_bytes.end(), rec.begin(), rec.end());
+            sl.bam_begin.push_back(sl.bam_bytes.size());
+        }
+    }
+    if (sl.bam_begin.size() != size_t(n_rec) + 1) return fail(ctx, PTL_ERR_STATE, "record count mismatch (internal)");
+    *out = ptl_bam_records{};
+    out->n_records = n_rec;
+    out->rec_begin = sl.bam_begin.data();
+    sl.bam_bytes.resize(sl.bam_bytes.size() + 16, 0);
+    out->bytes = sl.bam_bytes.data();
     return PTL_OK;
 }
 int ptl_oracle_lift_wait(ptl_ctx* ctx, int slot, ptl_result* out) {

@@ -136,6 +136,16 @@ class RecordBasesC(C.Structure):
 ASM_RESIDENT_QUAL, ASM_NO_DOWNLOAD = 1, 2
 
 
+class ReadExtrasC(C.Structure):
+    _fields_ = [("name_off", u64p), ("names", u8p), ("aux_off", u64p), ("aux", u8p), ("mate_tid", i32p), ("mate_pos", i32p),
+                ("tlen", i32p), ("quals", ReadQualsC)]
+
+
+class BamRecordsC(C.Structure):
+    _fields_ = [("n_records", C.c_uint32), ("rec_begin", u64p), ("bytes", u8p), ("kernel_ms", C.c_float),
+                ("bytes_read", C.c_uint64), ("bytes_written", C.c_uint64)]
+
+
 class SplitSegmentsC(C.Structure):
     _fields_ = [
         ("seq_order_start", u32p),
@@ -524,3 +534,38 @@ class Context:
         seq = np.ctypeslib.as_array(out.seq4, (max(int(sb[n]), 1),)).copy() if n else np.zeros(0, np.uint8)
         ql = np.ctypeslib.as_array(out.qual, (max(int(qb[n]), 1),)).copy() if n else np.zeros(0, np.uint8)
         return out, (sb, seq, qb, ql)
+
+    def set_names(self, contig_names, chrom_names):
+        """ptl_set_names: contig names (PS:Z) and reference names (SA:Z) for ptl_assemble_records."""
+        fn = getattr(self.lib.dll, self.lib.prefix + "set_names")
+        fn.restype, fn.argtypes = C.c_int, [C.c_void_p, C.c_uint32, C.POINTER(C.c_char_p), C.c_uint32, C.POINTER(C.c_char_p)]
+        a = (C.c_char_p * max(len(contig_names), 1))(*[n.encode() for n in contig_names])
+        b = (C.c_char_p * max(len(chrom_names), 1))(*[n.encode() for n in chrom_names])
+        self._check(fn(self.h, len(contig_names), a, len(chrom_names), b))
+
+    def assemble_records(self, extras: Optional[dict], slot: int = 0, flags: int = 0):
+        """ptl_assemble_records on the slot's last lifted batch.  `extras`: dict with name_off, names, aux_off, aux, mate_tid,
+        mate_pos, tlen, qual, qual_off (numpy).  Returns (BamRecordsC, (rec_begin, bytes)) -- the pair is None with ASM_NO_DOWNLOAD."""
+        fn = getattr(self.lib.dll, self.lib.prefix + "assemble_records")
+        fn.restype, fn.argtypes = C.c_int, [C.c_void_p, C.c_int, C.POINTER(ReadExtrasC), C.c_uint32, C.POINTER(BamRecordsC)]
+        x = ReadExtrasC()
+        if extras is not None:
+            k = {
+                "name_off": _arr(extras["name_off"], np.uint64), "names": _arr(extras["names"], np.uint8),
+                "aux_off": _arr(extras["aux_off"], np.uint64), "aux": _arr(extras["aux"], np.uint8),
+                "mate_tid": _arr(extras["mate_tid"], np.int32), "mate_pos": _arr(extras["mate_pos"], np.int32),
+                "tlen": _arr(extras["tlen"], np.int32), "qual": _arr(extras["qual"], np.uint8), "qual_off": _arr(extras["qual_off"], np.uint64),
+            }
+            self._keep[("extras", slot)] = k
+            x.name_off, x.names, x.aux_off, x.aux = _ptr(k["name_off"], u64p), _ptr(k["names"], u8p), _ptr(k["aux_off"], u64p), _ptr(k["aux"], u8p)
+            x.mate_tid, x.mate_pos, x.tlen = _ptr(k["mate_tid"], i32p), _ptr(k["mate_pos"], i32p), _ptr(k["tlen"], i32p)
+            x.quals.qual, x.quals.read_qual_off, x.quals.qual_bytes = _ptr(k["qual"], u8p), _ptr(k["qual_off"], u64p), k["qual"].size
+        out = BamRecordsC()
+        self._check(fn(self.h, slot, C.byref(x) if extras is not None else None, flags, C.byref(out)))
+        if flags & ASM_NO_DOWNLOAD:
+            return out, None
+        n = out.n_records
+        rb = np.ctypeslib.as_array(out.rec_begin, (n + 1,)).copy()
+        by = np.ctypeslib.as_array(out.bytes, (max(int(rb[n]), 1),))[: int(rb[n])].copy() if n else np.zeros(0, np.uint8)
+        return out, (rb, by)
+

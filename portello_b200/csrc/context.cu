@@ -17,6 +17,7 @@
 
 #include "../../include/portello_b200.h"
 #include "device/assemble.cuh"
+#include "device/assemble_bam.cuh"
 #include "device/kernels.hpp"
 #include "host/contig_prep.hpp"
 
@@ -93,6 +94,11 @@ struct Slot {
     HBuf ha_seq_begin, ha_qual_begin, ha_out_seq, ha_out_qual;
     cudaEvent_t a_ev[2] = {nullptr, nullptr};
     uint64_t a_qual_bytes = 0;
+    // record assembly, whole BAM records (ptl_assemble_records): uploaded names / aux / mate fields, work arrays, output
+    DBuf b_name_off, b_names, b_aux_off, b_aux, b_mate_tid, b_mate_pos, b_tlen, b_keep, b_sa_len, b_rec_begin, b_out, b_err;
+    HBuf hb_rec_begin, hb_out, hb_err;
+    bool b_resident = false;
+    uint64_t b_in_bytes = 0;
     // results: one compact arena on the device (device_types.hpp: result_layout) and its pinned host twin
     DBuf r_arena;
     HBuf h_arena;
@@ -120,7 +126,9 @@ struct ptl_ctx {
     uint32_t long_pair_ops = 64;  // ptl_set_long_pair_ops
     // static state
     DBuf s_ref, s_chrom_off, s_contig_seg_begin, s_contig_len, s_contig_rev_off, s_rev_pool, s_so_start, s_so_end, s_chrom, s_pos,
-        s_is_fwd, s_mapq, s_cigar_begin, s_cigar, s_tab_begin, s_table;
+        s_is_fwd, s_mapq, s_cigar_begin, s_cigar, s_tab_begin, s_table, s_contig_name_off, s_contig_names, s_chrom_name_off, s_chrom_names;
+    uint32_t n_contig_names = 0, n_chrom_names = 0;  // ptl_set_names
+    bool have_names = false;
     DevStatic S;
     bool have_reference = false, have_segments = false;
     FlatContigs flat;
@@ -534,10 +542,11 @@ void ptl_destroy(ptl_ctx* ctx) {
                         &sl.d_seq4, &sl.d_arena, &sl.d_win_begin, &sl.d_win, &sl.w_rseg_read, &sl.w_rseg_pair_begin, &sl.w_rseg_ref_len, &sl.w_rseg_n_id, &sl.w_rseg_read_len, &sl.w_pair_cap_b, &sl.w_pair_tab_lo, &sl.w_pair_rseg, &sl.w_pair_seg,
                         &sl.w_pair_slot_begin, &sl.w_pair_status, &sl.w_pair_flip, &sl.w_pair_pos, &sl.w_pair_n_out, &sl.w_pair_bin, &sl.w_pair_out_off, &sl.w_simplify_list, &sl.w_long_list,
                         &sl.w_scratch, &sl.w_read_counts, &sl.w_read_primary, &sl.w_scan_tmp, &sl.w_totals, &sl.r_arena, &sl.a_qual, &sl.a_qual_off,
-                        &sl.a_rec_read, &sl.a_seq_begin, &sl.a_qual_begin, &sl.a_out_seq, &sl.a_out_qual})
+                        &sl.a_rec_read, &sl.a_seq_begin, &sl.a_qual_begin, &sl.a_out_seq, &sl.a_out_qual, &sl.b_name_off, &sl.b_names, &sl.b_aux_off,
+                        &sl.b_aux, &sl.b_mate_tid, &sl.b_mate_pos, &sl.b_tlen, &sl.b_keep, &sl.b_sa_len, &sl.b_rec_begin, &sl.b_out, &sl.b_err})
             b->release();
         sl.h_arena.release();
-        for (HBuf* b : {&sl.ha_seq_begin, &sl.ha_qual_begin, &sl.ha_out_seq, &sl.ha_out_qual}) b->release();
+        for (HBuf* b : {&sl.ha_seq_begin, &sl.ha_qual_begin, &sl.ha_out_seq, &sl.ha_out_qual, &sl.hb_rec_begin, &sl.hb_out, &sl.hb_err}) b->release();
         for (auto& e : sl.a_ev) if (e) cudaEventDestroy(e);
         if (sl.have_events)
             for (auto& e : sl.ev.e) cudaEventDestroy(e);
@@ -545,7 +554,8 @@ void ptl_destroy(ptl_ctx* ctx) {
     }
     for (DBuf* b : {&ctx->s_ref, &ctx->s_chrom_off, &ctx->s_contig_seg_begin, &ctx->s_contig_len, &ctx->s_contig_rev_off, &ctx->s_rev_pool,
                     &ctx->s_so_start, &ctx->s_so_end, &ctx->s_chrom, &ctx->s_pos, &ctx->s_is_fwd, &ctx->s_mapq, &ctx->s_cigar_begin,
-                    &ctx->s_cigar, &ctx->s_tab_begin, &ctx->s_table})
+                    &ctx->s_cigar, &ctx->s_tab_begin, &ctx->s_table, &ctx->s_contig_name_off, &ctx->s_contig_names, &ctx->s_chrom_name_off,
+                    &ctx->s_chrom_names})
         b->release();
     if (ctx->setup_stream) cudaStreamDestroy(ctx->setup_stream);
     delete ctx;
@@ -753,6 +763,146 @@ int ptl_assemble_bases(ptl_ctx* ctx, int slot, const ptl_read_quals* quals, uint
         }
         out->bytes_read = bytes;
         out->bytes_written = bytes;
+        return PTL_OK;
+    });
+}
+// Record assembly, whole BAM records: see include/portello_b200.h.
+int ptl_set_names(ptl_ctx* ctx, uint32_t n_contigs, const char* const* contig_names, uint32_t n_chrom, const char* const* chrom_names) {
+    if (!ctx || (n_contigs && !contig_names) || (n_chrom && !chrom_names)) return PTL_ERR_INVALID_ARG;
+    return guarded(ctx, [&]() {
+        cudaStream_t st = ctx->setup_stream;
+        auto pool = [&](uint32_t n, const char* const* names, DBuf& d_off, DBuf& d_bytes) {
+            std::vector<uint64_t> off(size_t(n) + 1, 0);
+            std::string bytes;
+            for (uint32_t i = 0; i < n; ++i) {
+                if (!names[i]) throw std::runtime_error("ptl_set_names: NULL name");
+                bytes += names[i];
+                off[i + 1] = bytes.size();
+            }
+            bytes.resize(bytes.size() + 16, '\0');
+            upload(d_off, off.data(), off.size(), st);
+            upload(d_bytes, reinterpret_cast<const uint8_t*>(bytes.data()), bytes.size(), st);
+            CK(cudaStreamSynchronize(st));  // (the host vectors die here)
+        };
+        pool(n_contigs, contig_names, ctx->s_contig_name_off, ctx->s_contig_names);
+        pool(n_chrom, chrom_names, ctx->s_chrom_name_off, ctx->s_chrom_names);
+        ctx->n_contig_names = n_contigs;
+        ctx->n_chrom_names = n_chrom;
+        ctx->have_names = true;
+        return PTL_OK;
+    });
+}
+int ptl_assemble_records(ptl_ctx* ctx, int slot, const ptl_read_extras* x, uint32_t flags, ptl_bam_records* out) {
+    Slot* sl = get_slot(ctx, slot);
+    if (!sl || !out || (!x && !(flags & PTL_ASM_RESIDENT_QUAL))) return PTL_ERR_INVALID_ARG;
+    if (!sl->ran) return fail(ctx, PTL_ERR_STATE, "ptl_assemble_records without a lifted batch on the slot");
+    if (!ctx->have_names) return fail(ctx, PTL_ERR_STATE, "ptl_set_names has not been called");
+    return guarded(ctx, [&]() {
+        finish_batch(ctx, *sl);
+        cudaStream_t st = sl->stream;
+        const DevTotals& t = sl->totals;
+        const uint32_t n = sl->B.n_reads, n_rec = uint32_t(t.n_records);
+        *out = ptl_bam_records{};
+        out->n_records = n_rec;
+        if (!(flags & PTL_ASM_RESIDENT_QUAL)) {
+            const uint64_t name_bytes = n ? x->name_off[n] : 0, aux_bytes = n ? x->aux_off[n] : 0;
+            upload(sl->b_name_off, x->name_off, size_t(n) + 1, st);
+            upload(sl->b_aux_off, x->aux_off, size_t(n) + 1, st);
+            sl->b_names.ensure(name_bytes + 32, st);
+            sl->b_aux.ensure(aux_bytes + 32, st);
+            if (name_bytes) CK(cudaMemcpyAsync(sl->b_names.p, x->names, name_bytes, cudaMemcpyHostToDevice, st));
+            if (aux_bytes) CK(cudaMemcpyAsync(sl->b_aux.p, x->aux, aux_bytes, cudaMemcpyHostToDevice, st));
+            upload(sl->b_mate_tid, x->mate_tid, n, st);
+            upload(sl->b_mate_pos, x->mate_pos, n, st);
+            upload(sl->b_tlen, x->tlen, n, st);
+            sl->a_qual.ensure(std::max<uint64_t>(x->quals.qual_bytes, 4) + 32, st);
+            if (x->quals.qual_bytes) CK(cudaMemcpyAsync(sl->a_qual.p, x->quals.qual, x->quals.qual_bytes, cudaMemcpyHostToDevice, st));
+            upload(sl->a_qual_off, x->quals.read_qual_off, n, st);
+            sl->a_qual_bytes = x->quals.qual_bytes;
+            sl->b_resident = true;
+            sl->b_in_bytes = name_bytes + aux_bytes;
+        } else if (!sl->b_resident) {
+            throw std::runtime_error("PTL_ASM_RESIDENT_QUAL without a previous ptl_assemble_records upload on this slot");
+        }
+        const ResultLayout L = result_layout(n, t.n_records, t.n_cigar_out);
+        const DevResult R = DevResult::view(sl->r_arena.as<char>(), L);
+        sl->b_keep.ensure(size_t(n) * 40 + 40, st);
+        sl->b_sa_len.ensure(size_t(n_rec) * 4 + 4, st);
+        sl->b_rec_begin.ensure((size_t(n_rec) + 1) * 8, st);
+        sl->b_err.ensure(4, st);
+        CK(cudaMemsetAsync(sl->b_err.p, 0, 4, st));
+        sl->w_scan_tmp.ensure(scan_tmp_bytes(uint64_t(n_rec) + 1), st);
+        BamAsmArgs A{};
+        A.n_reads = n;
+        A.n_records = n_rec;
+        A.seg_is_fwd = ctx->S.seg_is_fwd;
+        A.contig_seg_begin = ctx->S.contig_seg_begin;
+        A.contig_name_off = ctx->s_contig_name_off.as<uint64_t>();
+        A.contig_names = ctx->s_contig_names.as<uint8_t>();
+        A.n_contig_names = ctx->n_contig_names;
+        A.chrom_name_off = ctx->s_chrom_name_off.as<uint64_t>();
+        A.chrom_names = ctx->s_chrom_names.as<uint8_t>();
+        A.n_chrom_names = ctx->n_chrom_names;
+        A.read_mapq = sl->B.read_mapq;
+        A.read_seq_len = sl->B.read_seq_len;
+        A.read_seq_off = sl->B.read_seq_off;
+        A.seq4 = sl->B.seq4;
+        A.rseg_contig = sl->B.rseg_contig;
+        A.rseg_read = sl->W.rseg_read;
+        A.name_off = sl->b_name_off.as<uint64_t>();
+        A.names = sl->b_names.as<uint8_t>();
+        A.aux_off = sl->b_aux_off.as<uint64_t>();
+        A.aux = sl->b_aux.as<uint8_t>();
+        A.mate_tid = sl->b_mate_tid.as<int32_t>();
+        A.mate_pos = sl->b_mate_pos.as<int32_t>();
+        A.tlen = sl->b_tlen.as<int32_t>();
+        A.qual_off = sl->a_qual_off.as<uint64_t>();
+        A.qual = sl->a_qual.as<uint8_t>();
+        A.read_rec_begin = R.read_rec_begin;
+        A.rec_status = R.rec_status;
+        A.rec_read_segment = R.rec_read_segment;
+        A.rec_contig_segment = R.rec_contig_segment;
+        A.rec_tid = R.rec_tid;
+        A.rec_pos = R.rec_pos;
+        A.rec_mapq = R.rec_mapq;
+        A.rec_flag = R.rec_flag;
+        A.rec_bin = R.rec_bin;
+        A.rec_need_flip = R.rec_need_flip;
+        A.rec_cigar_begin = R.rec_cigar_begin;
+        A.cigar = R.cigar;
+        A.read_keep = sl->b_keep.as<uint32_t>();
+        A.rec_sa_len = sl->b_sa_len.as<uint32_t>();
+        A.rec_begin = sl->b_rec_begin.as<uint64_t>();
+        A.error = sl->b_err.as<unsigned int>();
+        launch_bam_sizes(A, sl->w_scan_tmp.p, sl->w_scan_tmp.cap, st, &ctx->launches);
+        sl->hb_rec_begin.ensure((size_t(n_rec) + 1) * 8);
+        sl->hb_err.ensure(4);
+        CK(cudaMemcpyAsync(sl->hb_rec_begin.p, sl->b_rec_begin.p, (size_t(n_rec) + 1) * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(sl->hb_err.p, sl->b_err.p, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));  // the output size is only known now
+        const unsigned err = *sl->hb_err.as<unsigned int>();
+        if (err & 1u) throw std::runtime_error("ptl_set_names: a contig or reference chromosome of this batch has no name");
+        if (err & 2u) throw std::runtime_error("a lifted CIGAR has more than 65535 ops (BAM needs a CG tag for it: out of scope)");
+        const uint64_t total = sl->hb_rec_begin.as<uint64_t>()[n_rec];
+        sl->b_out.ensure(total + 32, st);
+        A.out = sl->b_out.as<uint8_t>();
+        if (!sl->a_ev[0]) { CK(cudaEventCreate(&sl->a_ev[0])); CK(cudaEventCreate(&sl->a_ev[1])); }
+        CK(cudaEventRecord(sl->a_ev[0], st));
+        launch_bam_write(A, st, &ctx->launches);
+        CK(cudaEventRecord(sl->a_ev[1], st));
+        if (!(flags & PTL_ASM_NO_DOWNLOAD)) {
+            sl->hb_out.ensure(total + 32);
+            if (total) CK(cudaMemcpyAsync(sl->hb_out.p, sl->b_out.p, total, cudaMemcpyDeviceToHost, st));
+            out->bytes = sl->hb_out.as<uint8_t>();
+        }
+        CK(cudaStreamSynchronize(st));
+        CK(cudaGetLastError());
+        CK(cudaEventElapsedTime(&out->kernel_ms, sl->a_ev[0], sl->a_ev[1]));
+        out->rec_begin = sl->hb_rec_begin.as<uint64_t>();
+        // algorithmic bytes: the output once; the input of a record = its output minus what the kernel generates itself
+        // (block_size + core 36 B, PS / ZM / SA text), i.e. name, CIGAR, bases, qualities and surviving aux, read once
+        out->bytes_written = total;
+        out->bytes_read = total - std::min<uint64_t>(total, 36ull * n_rec);
         return PTL_OK;
     });
 }

@@ -10,6 +10,7 @@
 #include <algorithm>
 
 #include "assemble.cuh"
+#include "assemble_bam.cuh"
 #include "kernels.hpp"
 #include "lift_device.cuh"
 #include "lift_warp.cuh"
@@ -436,6 +437,39 @@ void launch_assemble_sizes(uint32_t n_records, const uint32_t* rec_read_segment,
 void launch_assemble_records(const AsmArgs& A, cudaStream_t st, uint64_t* launches) {
     if (!A.n_records) return;
     assemble_records_kernel<<<A.n_records, 256, 0, st>>>(A);
+    ++*launches;
+}
+
+
+// =================================================================================================== record assembly, whole BAM records
+namespace {
+__global__ void __launch_bounds__(128) bam_read_prep_kernel(BamAsmArgs A) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < A.n_reads) bam_read_prep_body(A, r);
+}
+__global__ void __launch_bounds__(128) bam_rec_prep_kernel(BamAsmArgs A) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < A.n_records) bam_rec_prep_body(A, k);
+}
+__global__ void __launch_bounds__(128) bam_rec_size_kernel(BamAsmArgs A) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > A.n_records) return;
+    A.rec_begin[k] = (k < A.n_records) ? bam_rec_layout(A, k).total : 0ull;
+}
+// One block per output record: HBM-bound streaming (assemble_bam.cuh).
+__global__ void __launch_bounds__(256) bam_write_kernel(BamAsmArgs A) { bam_write_body(A, blockIdx.x, threadIdx.x, blockDim.x); }
+}  // namespace
+
+void launch_bam_sizes(const BamAsmArgs& A, void* scan_tmp, size_t scan_tmp_bytes_, cudaStream_t st, uint64_t* launches) {
+    if (A.n_reads) { bam_read_prep_kernel<<<(A.n_reads + 127) / 128, 128, 0, st>>>(A); ++*launches; }
+    if (A.n_records) { bam_rec_prep_kernel<<<(A.n_records + 127) / 128, 128, 0, st>>>(A); ++*launches; }
+    bam_rec_size_kernel<<<(A.n_records + 1 + 127) / 128, 128, 0, st>>>(A);
+    ++*launches;
+    exclusive_scan_inplace<uint64_t>(A.rec_begin, uint64_t(A.n_records) + 1, scan_tmp, scan_tmp_bytes_, st, launches, nullptr);
+}
+void launch_bam_write(const BamAsmArgs& A, cudaStream_t st, uint64_t* launches) {
+    if (!A.n_records) return;
+    bam_write_kernel<<<A.n_records, 256, 0, st>>>(A);
     ++*launches;
 }
 

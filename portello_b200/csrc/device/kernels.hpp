@@ -35,4 +35,10 @@ void launch_assemble_sizes(uint32_t n_records, const uint32_t* rec_read_segment,
                            uint64_t* launches);
 void launch_assemble_records(const AsmArgs& A, cudaStream_t st, uint64_t* launches);
 
+// Record assembly, whole BAM records (assemble_bam.cuh): sizes (aux walk per read, SA entry length per record, record
+// size -> exclusive scan into A.rec_begin), then the writer (one block per record).
+struct BamAsmArgs;
+void launch_bam_sizes(const BamAsmArgs& A, void* scan_tmp, size_t scan_tmp_bytes, cudaStream_t st, uint64_t* launches);
+void launch_bam_write(const BamAsmArgs& A, cudaStream_t st, uint64_t* launches);
+
 }  // namespace ptl

@@ -1,0 +1,235 @@
+"""Record assembly, whole BAM records (ptl_assemble_records): every output record as the bytes
+bam_write1 would emit after clone_record + the field updates / push_aux calls of
+get_liftover_alignment_for_read_and_contig_segment (src/read_alignment_scanner.rs:105-117,245-282) and
+finish_remapped_alignment_set (:310-366).
+
+The reference has no test for record mutation ("parity unpinned"), so the oracle (C++ restatement) is
+pinned here by an independent pure-Python model that builds every record from the SAM-spec layout, and the CUDA kernels
+must equal the oracle byte for byte."""
+import struct
+
+import numpy as np
+import pytest
+
+import helpers
+from portello_b200 import abi, synth
+from test_assemble import COMP, iupac_case, make_quals
+
+OPS = "MIDNSHP=X"
+
+
+def aux_fields(aux: bytes):
+    """[(tag, start, end)] of a well-formed prefix of a BAM aux block (SAM spec 4.2.4)."""
+    out, i, n = [], 0, len(aux)
+    size = {b"A": 1, b"c": 1, b"C": 1, b"s": 2, b"S": 2, b"i": 4, b"I": 4, b"f": 4, b"d": 8}
+    while i + 3 <= n:
+        t = aux[i + 2: i + 3]
+        if t in size:
+            e = i + 3 + size[t]
+        elif t in (b"Z", b"H"):
+            j = aux.find(b"\0", i + 3)
+            if j < 0:
+                break
+            e = j + 1
+        elif t == b"B":
+            if i + 8 > n or aux[i + 3: i + 4] not in (b"c", b"C", b"s", b"S", b"i", b"I", b"f"):
+                break
+            es = {b"c": 1, b"C": 1, b"s": 2, b"S": 2, b"i": 4, b"I": 4, b"f": 4}[aux[i + 3: i + 4]]
+            e = i + 8 + es * struct.unpack_from("<I", aux, i + 4)[0]
+        else:
+            break
+        if e > n:
+            break
+        out.append((aux[i: i + 2], i, e))
+        i = e
+    return out
+
+
+def strip_tags(aux: bytes) -> bytes:
+    """clone_record: drop the first NM, SA, PS and ZM field."""
+    cuts = []
+    for tag in (b"NM", b"SA", b"PS", b"ZM"):
+        for t, a, e in aux_fields(aux):
+            if t == tag:
+                cuts.append((a, e))
+                break
+    keep, at = b"", 0
+    for a, e in sorted(cuts):
+        keep += aux[at:a]
+        at = e
+    return keep + aux[at:]
+
+
+def make_extras(s, pb, seed):
+    """Synthetic qnames, aux blocks (every field type, some NM/SA/PS/ZM tags at random places, a few malformed tails),
+    mate fields and qualities for the reads of a packed batch."""
+    rng = np.random.default_rng(seed)
+    n = pb.c.n_reads
+    names, auxs = [], []
+    for r in range(n):
+        names.append(("m64011_%d/%d/ccs" % (int(rng.integers(1, 10**6)), r)).encode()[: int(rng.integers(1, 40))])
+        fields = []
+        for _ in range(int(rng.integers(0, 9))):
+            kind = int(rng.integers(0, 12))
+            tag = bytes(rng.choice(list(b"abcdefghijXYZ"), 2).astype(np.uint8))
+            if kind == 0: fields.append(tag + b"A" + b"Q")
+            elif kind == 1: fields.append(tag + b"c" + struct.pack("<b", -5))
+            elif kind == 2: fields.append(tag + b"S" + struct.pack("<H", 4711))
+            elif kind == 3: fields.append(tag + b"i" + struct.pack("<i", -123456))
+            elif kind == 4: fields.append(tag + b"f" + struct.pack("<f", 0.25))
+            elif kind == 5: fields.append(tag + b"Z" + bytes(rng.integers(33, 126, int(rng.integers(0, 60)), dtype=np.uint8)) + b"\0")
+            elif kind == 6: fields.append(tag + b"H" + b"1AE301" + b"\0")
+            elif kind == 7: fields.append(tag + b"B" + b"C" + struct.pack("<I", 37) + bytes(rng.integers(0, 256, 37, dtype=np.uint8)))
+            elif kind == 8: fields.append(tag + b"B" + b"f" + struct.pack("<I", 4) + struct.pack("<4f", 1, 2, 3, 4))
+            elif kind == 9: fields.append(b"NM" + b"i" + struct.pack("<i", int(rng.integers(0, 500))))
+            elif kind == 10: fields.append(rng.choice([b"SA", b"PS"]).tobytes() + b"Z" + b"ctg1,100,+,50M,60,0;" + b"\0")
+            else: fields.append(b"ZM" + b"C" + bytes([int(rng.integers(0, 61))]))
+        a = b"".join(fields)
+        if rng.random() < 0.03:
+            a += b"zz" + b"Z" + b"no terminator"  # malformed tail: nothing behind it is found, everything is kept
+        auxs.append(a)
+    name_off = np.zeros(n + 1, np.uint64)
+    name_off[1:] = np.cumsum([len(x) for x in names])
+    aux_off = np.zeros(n + 1, np.uint64)
+    aux_off[1:] = np.cumsum([len(x) for x in auxs])
+    qual, qual_off = make_quals(pb.c, seed)
+    return dict(name_off=name_off, names=np.frombuffer(b"".join(names) + b"\0" * 8, np.uint8).copy(), aux_off=aux_off,
+                aux=np.frombuffer(b"".join(auxs) + b"\0" * 8, np.uint8).copy(),
+                mate_tid=rng.integers(-1, 3, n).astype(np.int32), mate_pos=rng.integers(-1, 10**6, n).astype(np.int32),
+                tlen=rng.integers(-5000, 5000, n).astype(np.int32), qual=qual, qual_off=qual_off), names, auxs
+
+
+def model(s, pb, res, x, names, auxs, contig_seg_is_fwd):
+    """Pure-Python restatement: list of record byte strings (block_size included)."""
+    b = pb.c
+    seg_begin = np.ctypeslib.as_array(b.read_seg_begin, (b.n_reads + 1,))
+    rseg_read = np.repeat(np.arange(b.n_reads), np.diff(seg_begin.astype(np.int64)))
+    rseg_contig = np.ctypeslib.as_array(b.rseg_contig, (b.n_read_segments,))
+    seq_len = np.ctypeslib.as_array(b.read_seq_len, (b.n_reads,))
+    seq_off = np.ctypeslib.as_array(b.read_seq_off, (b.n_reads,))
+    read_mapq = np.ctypeslib.as_array(b.read_mapq, (b.n_reads,))
+    pool = np.ctypeslib.as_array(b.seq4, (int(b.seq4_bytes),))
+    out = []
+    for r in range(b.n_reads):
+        k0, k1 = int(res.read_rec_begin[r]), int(res.read_rec_begin[r + 1])
+        kept = strip_tags(auxs[r])
+        sa = {}
+        for k in range(k0, k1):
+            if res.rec_status[k] == 1:
+                cg = res.cigar[int(res.rec_cigar_begin[k]): int(res.rec_cigar_begin[k + 1])]
+                sa[k] = "%s,%d,%s,%s,%d,0;" % (s.chrom_names[int(res.rec_tid[k])], int(res.rec_pos[k]) + 1, "-" if int(res.rec_flag[k]) & 16 else "+",
+                                              "".join("%d%s" % (int(c) >> 4, OPS[int(c) & 15]) for c in cg), int(res.rec_mapq[k]))
+        n = int(seq_len[r])
+        raw = pool[int(seq_off[r]): int(seq_off[r]) + (n + 1) // 2]
+        q = x["qual"][int(x["qual_off"][r]): int(x["qual_off"][r]) + n]
+        for k in range(k0, k1):
+            lifted = res.rec_status[k] == 1
+            aux = kept
+            cg = res.cigar[int(res.rec_cigar_begin[k]): int(res.rec_cigar_begin[k + 1])] if lifted else res.cigar[:0]
+            if lifted:
+                ctg = int(rseg_contig[int(res.rec_read_segment[k])])
+                idx = int(res.rec_contig_segment[k])
+                aux += b"PSZ" + ("%s_split%d%s" % (s.contig_names[ctg], idx, "+" if contig_seg_is_fwd(ctg, idx) else "-")).encode() + b"\0"
+                aux += b"ZMC" + bytes([int(read_mapq[r])])
+                text = "".join(sa[j] for j in range(k0, k1) if j != k)
+                if text:
+                    aux += b"SAZ" + text.encode() + b"\0"
+            if res.rec_need_flip[k]:
+                nib = np.empty(2 * len(raw), np.uint8)
+                nib[0::2], nib[1::2] = raw >> 4, raw & 15
+                rc = COMP[nib[:n][::-1]]
+                if n & 1:
+                    rc = np.append(rc, np.uint8(0))
+                seq, qq = (rc[0::2] << 4 | rc[1::2]).astype(np.uint8).tobytes(), q[::-1].tobytes()
+            else:
+                seq, qq = raw.tobytes(), q.tobytes()
+            core = struct.pack("<iiBBHHHIiii", int(res.rec_tid[k]), int(res.rec_pos[k]), len(names[r]) + 1, int(res.rec_mapq[k]), int(res.rec_bin[k]),
+                               len(cg), int(res.rec_flag[k]), n, int(x["mate_tid"][r]), int(x["mate_pos"][r]), int(x["tlen"][r]))
+            rec = core + names[r] + b"\0" + np.asarray(cg, "<u4").tobytes() + seq + qq + aux
+            out.append(struct.pack("<I", len(rec)) + rec)
+    return out
+
+
+def seg_is_fwd_fn(ctx):
+    segs = ctx.get_contig_segments()
+    return lambda ctg, idx: bool(segs.seg_is_fwd[int(segs.contig_seg_begin[ctg]) + idx])
+
+
+def check_against_model(ctx, s, pb, res, seed):
+    x, names, auxs = make_extras(s, pb, seed)
+    ctx.set_names(s.contig_names, s.chrom_names)
+    _, (rb, by) = ctx.assemble_records(x)
+    want = model(s, pb, res, x, names, auxs, seg_is_fwd_fn(ctx))
+    assert len(want) == res.n_records == len(rb) - 1
+    for k, w in enumerate(want):
+        got = by[int(rb[k]): int(rb[k + 1])].tobytes()
+        assert got == w, f"record {k}: {len(got)} vs {len(w)} bytes, first difference at {next((i for i, (a, c) in enumerate(zip(got, w)) if a != c), None)}"
+    return x, (rb, by)
+
+
+def test_strip_tags_model():
+    aux = b"NMi\x05\0\0\0" + b"rqf\0\0\x80?" + b"SAZx,1,+,5M,1,0;\0" + b"NMi\x07\0\0\0" + b"ZMC\x09"
+    assert strip_tags(aux) == b"rqf\0\0\x80?" + b"NMi\x07\0\0\0"  # only the FIRST NM goes (bam_aux_get + bam_aux_del)
+    assert strip_tags(b"") == b""
+    assert strip_tags(b"abZno terminator") == b"abZno terminator"
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_oracle_records_match_python_model(seed):
+    seen = np.zeros(3, bool)  # flipped records, unmapped fallbacks, reads with several records (SA tags)
+    for s, pb in (iupac_case(seed, n_reads=300), (lambda s: (s, helpers.pack(s)))(synth.make("tiny", seed=seed, n_reads=1200))):
+        octx = helpers.oracle_context(s)
+        res = helpers.lift_c(octx, pb.c, allow_panic=True)
+        seen |= [bool(res.rec_need_flip.any()), bool((res.rec_status == 0).any()), bool((np.diff(res.read_rec_begin.astype(np.int64)) > 1).any())]
+        check_against_model(octx, s, pb, res, seed)
+    assert seen.all(), seen
+
+
+def test_oracle_records_need_names():
+    s = synth.make("tiny", seed=3, n_reads=50)
+    pb = helpers.pack(s)
+    octx = helpers.oracle_context(s)
+    helpers.lift_c(octx, pb.c)
+    x, _, _ = make_extras(s, pb, 1)
+    with pytest.raises(abi.PtlError):
+        octx.assemble_records(x)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["iupac-odd", "tiny", "config1", "stress"])
+def test_gpu_records_match_oracle(case):
+    if case == "iupac-odd":
+        s, pb = iupac_case(11, n_reads=2000)
+    else:
+        s = synth.make(case, **({"n_reads": 3000} if case == "config1" else {"n_reads": 300} if case == "stress" else {}))
+        pb = helpers.pack(s)
+    octx, gctx = helpers.oracle_context(s), helpers.gpu_context(s)
+    ro = helpers.lift_c(octx, pb.c, allow_panic=True)
+    rg = helpers.lift_c(gctx, pb.c, allow_panic=True)
+    assert rg.diff(ro) is None
+    x, _, _ = make_extras(s, pb, 9)
+    for c in (octx, gctx):
+        c.set_names(s.contig_names, s.chrom_names)
+    _, (rbo, byo) = octx.assemble_records(x)
+    og, (rbg, byg) = gctx.assemble_records(x)
+    assert np.array_equal(rbo, rbg), "record offsets"
+    if not np.array_equal(byo, byg):
+        i = int(np.flatnonzero(byo != byg)[0])
+        k = int(np.searchsorted(rbo, i, side="right") - 1)
+        raise AssertionError(f"record {k} differs at byte {i - int(rbo[k])} of {int(rbo[k + 1] - rbo[k])}")
+    assert og.kernel_ms > 0 and og.bytes_written == int(rbg[-1]) and 0 < og.bytes_read <= og.bytes_written
+    o2, none = gctx.assemble_records(None, flags=abi.ASM_RESIDENT_QUAL | abi.ASM_NO_DOWNLOAD)
+    assert none is None and o2.n_records == og.n_records and o2.kernel_ms > 0
+    if case == "iupac-odd":
+        check_against_model(gctx, s, pb, rg, 9)
+
+
+@pytest.mark.gpu
+def test_gpu_records_need_names():
+    s = synth.make("tiny", seed=3, n_reads=50)
+    pb = helpers.pack(s)
+    gctx = helpers.gpu_context(s)
+    helpers.lift_c(gctx, pb.c)
+    x, _, _ = make_extras(s, pb, 1)
+    with pytest.raises(abi.PtlError):
+        gctx.assemble_records(x)
