@@ -95,7 +95,7 @@ struct Slot {
     cudaEvent_t a_ev[2] = {nullptr, nullptr};
     uint64_t a_qual_bytes = 0;
     // record assembly, whole BAM records (ptl_assemble_records): uploaded names / aux / mate fields, work arrays, output
-    DBuf b_name_off, b_names, b_aux_off, b_aux, b_mate_tid, b_mate_pos, b_tlen, b_keep, b_sa_len, b_rec_begin, b_out, b_err;
+    DBuf b_name_off, b_names, b_aux_off, b_aux, b_mate_tid, b_mate_pos, b_tlen, b_keep, b_sa_len, b_rec_begin, b_rec_desc, b_out, b_err;
     HBuf hb_rec_begin, hb_out, hb_err;
     bool b_resident = false;
     uint64_t b_in_bytes = 0;
@@ -543,7 +543,7 @@ void ptl_destroy(ptl_ctx* ctx) {
                         &sl.w_pair_slot_begin, &sl.w_pair_status, &sl.w_pair_flip, &sl.w_pair_pos, &sl.w_pair_n_out, &sl.w_pair_bin, &sl.w_pair_out_off, &sl.w_simplify_list, &sl.w_long_list,
                         &sl.w_scratch, &sl.w_read_counts, &sl.w_read_primary, &sl.w_scan_tmp, &sl.w_totals, &sl.r_arena, &sl.a_qual, &sl.a_qual_off,
                         &sl.a_rec_read, &sl.a_seq_begin, &sl.a_qual_begin, &sl.a_out_seq, &sl.a_out_qual, &sl.b_name_off, &sl.b_names, &sl.b_aux_off,
-                        &sl.b_aux, &sl.b_mate_tid, &sl.b_mate_pos, &sl.b_tlen, &sl.b_keep, &sl.b_sa_len, &sl.b_rec_begin, &sl.b_out, &sl.b_err})
+                        &sl.b_aux, &sl.b_mate_tid, &sl.b_mate_pos, &sl.b_tlen, &sl.b_keep, &sl.b_sa_len, &sl.b_rec_begin, &sl.b_rec_desc, &sl.b_out, &sl.b_err})
             b->release();
         sl.h_arena.release();
         for (HBuf* b : {&sl.ha_seq_begin, &sl.ha_qual_begin, &sl.ha_out_seq, &sl.ha_out_qual, &sl.hb_rec_begin, &sl.hb_out, &sl.hb_err}) b->release();
@@ -829,6 +829,7 @@ int ptl_assemble_records(ptl_ctx* ctx, int slot, const ptl_read_extras* x, uint3
         sl->b_keep.ensure(size_t(n) * 40 + 40, st);
         sl->b_sa_len.ensure(size_t(n_rec) * 4 + 4, st);
         sl->b_rec_begin.ensure((size_t(n_rec) + 1) * 8, st);
+        sl->b_rec_desc.ensure(size_t(n_rec) * 32 + 32, st);
         sl->b_err.ensure(4, st);
         CK(cudaMemsetAsync(sl->b_err.p, 0, 4, st));
         sl->w_scan_tmp.ensure(scan_tmp_bytes(uint64_t(n_rec) + 1), st);
@@ -873,6 +874,7 @@ int ptl_assemble_records(ptl_ctx* ctx, int slot, const ptl_read_extras* x, uint3
         A.read_keep = sl->b_keep.as<uint32_t>();
         A.rec_sa_len = sl->b_sa_len.as<uint32_t>();
         A.rec_begin = sl->b_rec_begin.as<uint64_t>();
+        A.rec_desc = sl->b_rec_desc.as<uint4>();
         A.error = sl->b_err.as<unsigned int>();
         launch_bam_sizes(A, sl->w_scan_tmp.p, sl->w_scan_tmp.cap, st, &ctx->launches);
         sl->hb_rec_begin.ensure((size_t(n_rec) + 1) * 8);
@@ -883,6 +885,7 @@ int ptl_assemble_records(ptl_ctx* ctx, int slot, const ptl_read_extras* x, uint3
         const unsigned err = *sl->hb_err.as<unsigned int>();
         if (err & 1u) throw std::runtime_error("ptl_set_names: a contig or reference chromosome of this batch has no name");
         if (err & 2u) throw std::runtime_error("a lifted CIGAR has more than 65535 ops (BAM needs a CG tag for it: out of scope)");
+        if (err & 4u) throw std::runtime_error("a contig name longer than 248 bytes or more than 16 MB of SA text in one record");
         const uint64_t total = sl->hb_rec_begin.as<uint64_t>()[n_rec];
         sl->b_out.ensure(total + 32, st);
         A.out = sl->b_out.as<uint8_t>();

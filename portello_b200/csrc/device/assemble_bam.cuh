@@ -66,6 +66,8 @@ struct BamAsmArgs {
     uint32_t* read_keep;     // [n_reads][10]: 5 x (offset, length) pieces of the aux block that survive clone_record
     uint32_t* rec_sa_len;    // [n_records] bytes of the record's own SA entry (0 for the unmapped fallback)
     uint64_t* rec_begin;     // [n_records+1] record sizes, then their exclusive scan
+    uint4* rec_desc;         // [n_records][2] BamRecLayout of the record, computed once by bam_rec_size (the writer's prologue
+                             //                is then two dependent loads deep instead of five)
     uint8_t* out;
     unsigned int* error;     // bit 0: a name is missing, bit 1: a CIGAR has more than 65535 ops
 };
@@ -200,6 +202,22 @@ struct BamRecLayout {
     uint32_t name_n, n_cigar, l_seq, seq_bytes, keep_n, ps_n, sa_n;  // ps_n / sa_n: payload bytes without tag, type and NUL
     bool lifted;
     uint64_t total;  // block_size + 4
+    __device__ __forceinline__ void pack(uint4* d) const {
+        d[0] = make_uint4(r, k0, k1 - k0, name_n | (lifted ? 0x80000000u : 0u));
+        d[1] = make_uint4(n_cigar, l_seq, keep_n, ps_n | (sa_n << 8));
+    }
+    static __device__ __forceinline__ BamRecLayout unpack(const uint4* d) {
+        const uint4 a = d[0], b = d[1];
+        BamRecLayout L;
+        L.r = a.x; L.k0 = a.y; L.k1 = a.y + a.z;
+        L.name_n = a.w & 0x7fffffffu; L.lifted = (a.w >> 31) != 0;
+        L.n_cigar = b.x; L.l_seq = b.y; L.seq_bytes = (b.y + 1u) >> 1; L.keep_n = b.z;
+        L.ps_n = b.w & 0xffu; L.sa_n = b.w >> 8;
+        uint64_t t = 4 + 32 + uint64_t(L.name_n) + 1 + 4ull * L.n_cigar + L.seq_bytes + L.l_seq + L.keep_n;
+        if (L.lifted) t += 3ull + L.ps_n + 1 + 4 + (L.sa_n ? 3ull + L.sa_n + 1 : 0ull);
+        L.total = t;
+        return L;
+    }
 };
 
 __device__ __forceinline__ BamRecLayout bam_rec_layout(const BamAsmArgs& A, uint32_t k) {
@@ -231,15 +249,41 @@ __device__ __forceinline__ BamRecLayout bam_rec_layout(const BamAsmArgs& A, uint
 
 // ------------------------------------------------------------------------------------------------------- the writer
 // 16 bytes `v` of a field at field offset o (dst + o is 16-byte aligned); bytes outside [0, flen) are not stored.
-__device__ __forceinline__ void put16(uint8_t* dst, int64_t o, int64_t flen, const uint4& v) {
-    if (o >= 0 && o + 16 <= flen) {
-        *reinterpret_cast<uint4*>(dst + o) = v;
-    } else {
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+// (the rare paths are kept out of line: inlined, they cost the streaming loop 120 registers and its occupancy)
+static __device__ __noinline__ void put16_partial(uint8_t* dst, int64_t o, int64_t flen, uint4 v) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int b = 0; b < 16; ++b)
-            if (o + b >= 0 && o + b < flen) dst[o + b] = uint8_t(w[b >> 2] >> (8 * (b & 3)));
+    for (int b = 0; b < 16; ++b)
+        if (o + b >= 0 && o + b < flen) dst[o + b] = uint8_t(w[b >> 2] >> (8 * (b & 3)));
+}
+__device__ __forceinline__ void put16(uint8_t* dst, int64_t o, int64_t flen, const uint4& v) {
+    if (o >= 0 && o + 16 <= flen) *reinterpret_cast<uint4*>(dst + o) = v;
+    else put16_partial(dst, o, flen, v);
+}
+static __device__ __noinline__ uint4 window128_guarded(const uint8_t* base, int64_t off, int64_t len) {
+    uint4 v;
+    v.x = window32(base, off, len);
+    v.y = window32(base, off + 4, len);
+    v.z = window32(base, off + 8, len);
+    v.w = window32(base, off + 12, len);
+    return v;
+}
+// window128 (assemble.cuh) with the guarded path out of line
+__device__ __forceinline__ uint4 window128_lean(const uint8_t* __restrict__ base, int64_t off, int64_t len) {
+    const uint64_t addr = reinterpret_cast<uint64_t>(base) + uint64_t(off);
+    const int64_t a0 = off - int64_t(addr & 3ull);
+    if (a0 >= 0 && a0 + 20 <= len) {
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(addr & ~3ull);
+        const uint32_t sh = uint32_t(addr & 3ull) * 8u;
+        const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
+        uint4 v;
+        v.x = __funnelshift_r(w0, w1, sh);
+        v.y = __funnelshift_r(w1, w2, sh);
+        v.z = __funnelshift_r(w2, w3, sh);
+        v.w = __funnelshift_r(w3, w4, sh);
+        return v;
     }
+    return window128_guarded(base, off, len);
 }
 template <class F>
 __device__ __forceinline__ void emit_field(uint8_t* dst, int64_t flen, uint32_t tid, uint32_t n_threads, F produce) {
@@ -252,11 +296,11 @@ __device__ __forceinline__ void emit_field(uint8_t* dst, int64_t flen, uint32_t 
     }
 }
 __device__ __forceinline__ void copy_field(uint8_t* dst, const uint8_t* src, int64_t flen, uint32_t tid, uint32_t n_threads) {
-    emit_field(dst, flen, tid, n_threads, [&](int64_t o) { return window128(src, o, flen); });
+    emit_field(dst, flen, tid, n_threads, [&](int64_t o) { return window128_lean(src, o, flen); });
 }
 
 // 16 output bytes at byte offset o of the reverse-complemented packed bases of a read of `len` bases (assemble.cuh)
-__device__ __forceinline__ uint4 revcomp_chunk(const uint8_t* __restrict__ src_s, int64_t len, int64_t o) {
+static __device__ __noinline__ uint4 revcomp_chunk(const uint8_t* src_s, int64_t len, int64_t o) {
     const int64_t seq_bytes = (len + 1) >> 1;
     const int64_t a = len - 2 * o - 32;  // source nibbles [a, a + 32) in nibble-monotonic form
     const int64_t byte0 = a >> 1;        // floor: a may be negative
@@ -283,7 +327,7 @@ __device__ __forceinline__ uint4 revcomp_chunk(const uint8_t* __restrict__ src_s
 }
 
 __device__ __forceinline__ void bam_write_body(const BamAsmArgs& A, uint32_t k, uint32_t tid, uint32_t n_threads) {
-    const BamRecLayout L = bam_rec_layout(A, k);
+    const BamRecLayout L = BamRecLayout::unpack(A.rec_desc + 2 * size_t(k));
     uint8_t* out = A.out + A.rec_begin[k];
     const uint32_t r = L.r;
     const bool flip = A.rec_need_flip[k] != 0;
@@ -358,7 +402,7 @@ __device__ __forceinline__ void bam_write_body(const BamAsmArgs& A, uint32_t k, 
     } else {
         emit_field(out + o_seq, L.seq_bytes, tid, n_threads, [&](int64_t o) { return revcomp_chunk(src_s, len, o); });
         emit_field(out + o_qual, len, tid, n_threads, [&](int64_t o) {
-            const uint4 s = window128(src_q, len - 16 - o, len);  // the 16 bytes in front of the mirrored position
+            const uint4 s = window128_lean(src_q, len - 16 - o, len);  // the 16 bytes in front of the mirrored position
             uint4 v;
             v.x = __byte_perm(s.w, 0u, 0x0123u);
             v.y = __byte_perm(s.z, 0u, 0x0123u);

@@ -454,10 +454,14 @@ __global__ void __launch_bounds__(128) bam_rec_prep_kernel(BamAsmArgs A) {
 __global__ void __launch_bounds__(128) bam_rec_size_kernel(BamAsmArgs A) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k > A.n_records) return;
-    A.rec_begin[k] = (k < A.n_records) ? bam_rec_layout(A, k).total : 0ull;
+    if (k == A.n_records) { A.rec_begin[k] = 0ull; return; }
+    const BamRecLayout L = bam_rec_layout(A, k);
+    if (L.ps_n > 0xffu || L.sa_n > 0xffffffu) atomicOr(A.error, 4u);  // (descriptor field widths: a 255-byte contig name, 16 MB of SA text)
+    L.pack(A.rec_desc + 2 * size_t(k));
+    A.rec_begin[k] = L.total;
 }
 // One block per output record: HBM-bound streaming (assemble_bam.cuh).
-__global__ void __launch_bounds__(256) bam_write_kernel(BamAsmArgs A) { bam_write_body(A, blockIdx.x, threadIdx.x, blockDim.x); }
+__global__ void __launch_bounds__(256, 6) bam_write_kernel(BamAsmArgs A) { bam_write_body(A, blockIdx.x, threadIdx.x, blockDim.x); }
 }  // namespace
 
 void launch_bam_sizes(const BamAsmArgs& A, void* scan_tmp, size_t scan_tmp_bytes_, cudaStream_t st, uint64_t* launches) {
