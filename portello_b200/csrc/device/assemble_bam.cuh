@@ -3,16 +3,17 @@
 // get_liftover_alignment_for_read_and_contig_segment (src/read_alignment_scanner.rs:105-117,245-282) and
 // finish_remapped_alignment_set (:310-366) leave behind.
 //
-// Four kernels:
+// Five kernels:
 //   bam_read_prep   1 thread / read    walk the aux block once, find the FIRST NM, SA, PS, ZM field (remove_aux_if_found):
 //                                      the surviving aux is <= 5 pieces of the input block
 //   bam_rec_prep    1 thread / record  byte length of the record's own SA entry "{chrom},{pos+1},{+|-},{CIGAR},{mapq},0;"
 //   bam_rec_size    1 thread / record  record size (needs the SA entries of the read's other records) -> exclusive scan
-//   bam_write       1 block  / record  HBM-bound streaming: ~22.6 KB in, ~22.7 KB out for a 15 kb read.  A BAM record is a
-//                                      byte stream without alignment, so every field is produced in 16-byte chunks aligned
-//                                      to the DESTINATION; the source window (arbitrary alignment, mirrored for a flipped
-//                                      record) comes from five aligned 32-bit loads + funnel shifts as in assemble.cuh;
-//                                      only the first and last chunk of a field fall back to byte stores.
+//   bam_write_meta  1 warp   / record  block_size + core, name, CIGAR, surviving aux, PS / ZM / SA: a few hundred bytes, byte-parallel
+//   bam_write_bases 1 block  / record  HBM-bound streaming: ~22.5 KB in, ~22.5 KB out for a 15 kb read.  A BAM record is a
+//                                      byte stream without alignment, so bases and qualities are produced in 16-byte chunks
+//                                      aligned to the DESTINATION; the source window (arbitrary alignment, mirrored for a
+//                                      flipped record) comes from five aligned 32-bit loads + funnel shifts as in
+//                                      assemble.cuh; only the < 16 + 36 bytes at the two ends of a field go byte by byte.
 #pragma once
 #include <cstdint>
 
@@ -295,8 +296,45 @@ __device__ __forceinline__ void emit_field(uint8_t* dst, int64_t flen, uint32_t 
         put16(dst, o, flen, produce(o));
     }
 }
-__device__ __forceinline__ void copy_field(uint8_t* dst, const uint8_t* src, int64_t flen, uint32_t tid, uint32_t n_threads) {
-    emit_field(dst, flen, tid, n_threads, [&](int64_t o) { return window128_lean(src, o, flen); });
+// Plain copy of a field.  [head: bytes up to the first 16-byte boundary of the destination | body: aligned 16-byte stores,
+// each fed by five aligned 32-bit loads + funnel shifts, two chunks in flight per thread | tail: < 36 bytes].  Head and tail go
+// byte by byte (a byte per thread): the guarded partial-chunk paths cost ~190 instructions per chunk at 1-2 active lanes and
+// kept warp 0 of every block busy three times longer than the streaming itself (ncu s5g).
+// The body may read up to 3 bytes in front of `src` (inside the same pool) but never past src + flen.
+__device__ __forceinline__ uint4 window128_body(const uint8_t* __restrict__ p) {
+    const uint64_t addr = reinterpret_cast<uint64_t>(p);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(addr & ~3ull);
+    const uint32_t sh = uint32_t(addr & 3ull) * 8u;
+    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
+    uint4 v;
+    v.x = __funnelshift_r(w0, w1, sh);
+    v.y = __funnelshift_r(w1, w2, sh);
+    v.z = __funnelshift_r(w2, w3, sh);
+    v.w = __funnelshift_r(w3, w4, sh);
+    return v;
+}
+// (one out-of-line copy of the loop for all nine call sites: inlined, the kernel was 5.7 k instructions and stalled on
+// instruction fetch; 32-bit index arithmetic: a BAM record is < 2 GB)
+static __device__ __noinline__ void copy_field(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, uint32_t flen, uint32_t tid, uint32_t n_threads) {
+    if (flen == 0) return;
+    const uint32_t head = min((16u - uint32_t(reinterpret_cast<uint64_t>(dst) & 15ull)) & 15u, flen);
+    const uint32_t n_body = (flen - head >= 20u) ? (flen - head - 20u) / 16u + 1u : 0u;  // chunk c reads src[head + 16 c - 3, head + 16 c + 20)
+    const uint32_t tail = head + 16u * n_body;
+    if (tid < head) dst[tid] = src[tid];                                         // (head < 16 <= n_threads)
+    for (uint32_t i = tail + tid; i < flen; i += n_threads) dst[i] = src[i];     // (< 36 bytes)
+    uint4* d = reinterpret_cast<uint4*>(dst + head);
+    const uint8_t* sb = src + head;
+    for (uint32_t c = tid; c < n_body; c += 2u * n_threads) {
+        const uint32_t c2 = c + n_threads;
+        const uint4 a = window128_body(sb + 16u * c);
+        if (c2 < n_body) {
+            const uint4 b = window128_body(sb + 16u * c2);
+            d[c] = a;
+            d[c2] = b;
+        } else {
+            d[c] = a;
+        }
+    }
 }
 
 // 16 output bytes at byte offset o of the reverse-complemented packed bases of a read of `len` bases (assemble.cuh)
@@ -326,11 +364,12 @@ static __device__ __noinline__ uint4 revcomp_chunk(const uint8_t* src_s, int64_t
     return v;
 }
 
-__device__ __forceinline__ void bam_write_body(const BamAsmArgs& A, uint32_t k, uint32_t tid, uint32_t n_threads) {
+// Everything of record k except bases and qualities (a few hundred bytes): block_size + core, name, CIGAR, surviving aux
+// pieces, PS / ZM / SA tags.  `n_threads` threads (one warp on the device) copy byte-parallel; text goes through single lanes.
+__device__ __forceinline__ void bam_write_meta_body(const BamAsmArgs& A, uint32_t k, uint32_t tid, uint32_t n_threads) {
     const BamRecLayout L = BamRecLayout::unpack(A.rec_desc + 2 * size_t(k));
     uint8_t* out = A.out + A.rec_begin[k];
     const uint32_t r = L.r;
-    const bool flip = A.rec_need_flip[k] != 0;
     // ---- field offsets
     const uint64_t o_name = 36, o_cigar = o_name + L.name_n + 1, o_seq = o_cigar + 4ull * L.n_cigar, o_qual = o_seq + L.seq_bytes,
                    o_aux = o_qual + L.l_seq, o_ps = o_aux + L.keep_n;
@@ -349,7 +388,7 @@ __device__ __forceinline__ void bam_write_body(const BamAsmArgs& A, uint32_t k, 
         out[o_name + L.name_n] = 0;
     }
     // ---- PS:Z, ZM:C (:255-269) and SA:Z (:349-363): short text, one thread each
-    if (L.lifted && tid == 32 % n_threads) {
+    if (L.lifted && tid == 1 % n_threads) {
         uint8_t* p = out + o_ps;
         const uint32_t ctg = A.rseg_contig[A.rec_read_segment[k]];
         *p++ = 'P'; *p++ = 'S'; *p++ = 'Z';
@@ -370,7 +409,7 @@ __device__ __forceinline__ void bam_write_body(const BamAsmArgs& A, uint32_t k, 
         // entry of the j-th other record: one thread each (reads with several records are few and have few records)
         const uint64_t o_sa = o_ps + 3ull + L.ps_n + 1 + 4 + 3;
         const uint32_t n_other = L.k1 - L.k0;
-        for (uint32_t j = tid; j < n_other; j += n_threads) {
+        for (uint32_t j = (tid + n_threads - 2 % n_threads) % n_threads; j < n_other; j += n_threads) {
             const uint32_t kj = L.k0 + j;
             if (kj == k) continue;
             uint64_t at = o_sa;
@@ -379,27 +418,39 @@ __device__ __forceinline__ void bam_write_body(const BamAsmArgs& A, uint32_t k, 
             sa_entry(A, kj, out + at);
         }
     }
-    // ---- name, CIGAR, surviving aux pieces: plain copies
-    copy_field(out + o_name, A.names + A.name_off[r], L.name_n, tid, n_threads);
-    if (L.n_cigar) copy_field(out + o_cigar, reinterpret_cast<const uint8_t*>(A.cigar + A.rec_cigar_begin[k]), 4ll * L.n_cigar, tid, n_threads);
+    // ---- name, CIGAR, surviving aux pieces: byte-parallel copies
+    auto copy_small = [&](uint8_t* d, const uint8_t* src, uint32_t n) {
+        for (uint32_t i = tid; i < n; i += n_threads) d[i] = src[i];
+    };
+    copy_small(out + o_name, A.names + A.name_off[r], L.name_n);
+    copy_small(out + o_cigar, reinterpret_cast<const uint8_t*>(A.cigar + A.rec_cigar_begin[k]), 4u * L.n_cigar);
     {
         const uint32_t* keep = A.read_keep + size_t(r) * 10;
         const uint8_t* aux = A.aux + A.aux_off[r];
         uint64_t at = o_aux;
         for (int j = 0; j < 5; ++j) {
             const uint32_t len = keep[2 * j + 1];
-            if (len) copy_field(out + at, aux + keep[2 * j], len, tid, n_threads);
+            copy_small(out + at, aux + keep[2 * j], len);
             at += len;
         }
     }
-    // ---- bases and qualities (reverse_alignment_seq_and_qual when flipped, :125-133)
+}
+
+// Bases and qualities of record k (99 % of its bytes): the streaming part, one block per record
+// (reverse_alignment_seq_and_qual when flipped, :125-133).
+__device__ __forceinline__ void bam_write_bases_body(const BamAsmArgs& A, uint32_t k, uint32_t tid, uint32_t n_threads) {
+    const BamRecLayout L = BamRecLayout::unpack(A.rec_desc + 2 * size_t(k));
+    uint8_t* out = A.out + A.rec_begin[k];
+    const uint32_t r = L.r;
+    const bool flip = A.rec_need_flip[k] != 0;
+    const uint64_t o_seq = 36ull + L.name_n + 1 + 4ull * L.n_cigar, o_qual = o_seq + L.seq_bytes;
     const uint8_t* src_s = A.seq4 + A.read_seq_off[r];
     const uint8_t* src_q = A.qual + A.qual_off[r];
-    const int64_t len = L.l_seq;
     if (!flip) {
         copy_field(out + o_seq, src_s, L.seq_bytes, tid, n_threads);
-        copy_field(out + o_qual, src_q, len, tid, n_threads);
+        copy_field(out + o_qual, src_q, L.l_seq, tid, n_threads);
     } else {
+        const int64_t len = L.l_seq;
         emit_field(out + o_seq, L.seq_bytes, tid, n_threads, [&](int64_t o) { return revcomp_chunk(src_s, len, o); });
         emit_field(out + o_qual, len, tid, n_threads, [&](int64_t o) {
             const uint4 s = window128_lean(src_q, len - 16 - o, len);  // the 16 bytes in front of the mirrored position

@@ -460,8 +460,13 @@ __global__ void __launch_bounds__(128) bam_rec_size_kernel(BamAsmArgs A) {
     L.pack(A.rec_desc + 2 * size_t(k));
     A.rec_begin[k] = L.total;
 }
-// One block per output record: HBM-bound streaming (assemble_bam.cuh).
-__global__ void __launch_bounds__(256, 6) bam_write_kernel(BamAsmArgs A) { bam_write_body(A, blockIdx.x, threadIdx.x, blockDim.x); }
+// One warp per output record: everything but bases and qualities.
+__global__ void __launch_bounds__(128) bam_write_meta_kernel(BamAsmArgs A) {
+    const uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (k < A.n_records) bam_write_meta_body(A, k, threadIdx.x & 31u, 32u);
+}
+// One block per output record: HBM-bound streaming of bases and qualities (assemble_bam.cuh).
+__global__ void __launch_bounds__(256, 6) bam_write_kernel(BamAsmArgs A) { bam_write_bases_body(A, blockIdx.x, threadIdx.x, blockDim.x); }
 }  // namespace
 
 void launch_bam_sizes(const BamAsmArgs& A, void* scan_tmp, size_t scan_tmp_bytes_, cudaStream_t st, uint64_t* launches) {
@@ -473,8 +478,9 @@ void launch_bam_sizes(const BamAsmArgs& A, void* scan_tmp, size_t scan_tmp_bytes
 }
 void launch_bam_write(const BamAsmArgs& A, cudaStream_t st, uint64_t* launches) {
     if (!A.n_records) return;
+    bam_write_meta_kernel<<<(A.n_records + 3) / 4, 128, 0, st>>>(A);
     bam_write_kernel<<<A.n_records, 256, 0, st>>>(A);
-    ++*launches;
+    *launches += 2;
 }
 
 }  // namespace ptl
