@@ -99,6 +99,8 @@ struct Slot {
     HBuf hb_rec_begin, hb_out, hb_err;
     bool b_resident = false;
     uint64_t b_in_bytes = 0;
+    cudaStream_t b_stream = nullptr;  // the meta kernel of the record assembly runs beside the streaming kernel
+    cudaEvent_t b_fork = nullptr, b_join = nullptr;
     // results: one compact arena on the device (device_types.hpp: result_layout) and its pinned host twin
     DBuf r_arena;
     HBuf h_arena;
@@ -548,6 +550,9 @@ void ptl_destroy(ptl_ctx* ctx) {
         sl.h_arena.release();
         for (HBuf* b : {&sl.ha_seq_begin, &sl.ha_qual_begin, &sl.ha_out_seq, &sl.ha_out_qual, &sl.hb_rec_begin, &sl.hb_out, &sl.hb_err}) b->release();
         for (auto& e : sl.a_ev) if (e) cudaEventDestroy(e);
+        if (sl.b_fork) cudaEventDestroy(sl.b_fork);
+        if (sl.b_join) cudaEventDestroy(sl.b_join);
+        if (sl.b_stream) cudaStreamDestroy(sl.b_stream);
         if (sl.have_events)
             for (auto& e : sl.ev.e) cudaEventDestroy(e);
         if (sl.stream) cudaStreamDestroy(sl.stream);
@@ -890,8 +895,17 @@ int ptl_assemble_records(ptl_ctx* ctx, int slot, const ptl_read_extras* x, uint3
         sl->b_out.ensure(total + 32, st);
         A.out = sl->b_out.as<uint8_t>();
         if (!sl->a_ev[0]) { CK(cudaEventCreate(&sl->a_ev[0])); CK(cudaEventCreate(&sl->a_ev[1])); }
+        if (!sl->b_stream) {
+            CK(cudaStreamCreateWithFlags(&sl->b_stream, cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&sl->b_fork, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&sl->b_join, cudaEventDisableTiming));
+        }
         CK(cudaEventRecord(sl->a_ev[0], st));
-        launch_bam_write(A, st, &ctx->launches);
+        CK(cudaEventRecord(sl->b_fork, st));
+        CK(cudaStreamWaitEvent(sl->b_stream, sl->b_fork, 0));
+        launch_bam_write(A, st, sl->b_stream, &ctx->launches);
+        CK(cudaEventRecord(sl->b_join, sl->b_stream));
+        CK(cudaStreamWaitEvent(st, sl->b_join, 0));
         CK(cudaEventRecord(sl->a_ev[1], st));
         if (!(flags & PTL_ASM_NO_DOWNLOAD)) {
             sl->hb_out.ensure(total + 32);

@@ -476,9 +476,10 @@ void launch_bam_sizes(const BamAsmArgs& A, void* scan_tmp, size_t scan_tmp_bytes
     ++*launches;
     exclusive_scan_inplace<uint64_t>(A.rec_begin, uint64_t(A.n_records) + 1, scan_tmp, scan_tmp_bytes_, st, launches, nullptr);
 }
-void launch_bam_write(const BamAsmArgs& A, cudaStream_t st, uint64_t* launches) {
+void launch_bam_write(const BamAsmArgs& A, cudaStream_t st, cudaStream_t st_meta, uint64_t* launches) {
     if (!A.n_records) return;
-    bam_write_meta_kernel<<<(A.n_records + 3) / 4, 128, 0, st>>>(A);
+    // the two kernels write disjoint bytes of the same records: the small latency-bound one runs beside the streaming one
+    bam_write_meta_kernel<<<(A.n_records + 3) / 4, 128, 0, st_meta>>>(A);
     bam_write_kernel<<<A.n_records, 256, 0, st>>>(A);
     *launches += 2;
 }

@@ -39,6 +39,6 @@ void launch_assemble_records(const AsmArgs& A, cudaStream_t st, uint64_t* launch
 // size -> exclusive scan into A.rec_begin), then the writer (one block per record).
 struct BamAsmArgs;
 void launch_bam_sizes(const BamAsmArgs& A, void* scan_tmp, size_t scan_tmp_bytes, cudaStream_t st, uint64_t* launches);
-void launch_bam_write(const BamAsmArgs& A, cudaStream_t st, uint64_t* launches);
+void launch_bam_write(const BamAsmArgs& A, cudaStream_t st, cudaStream_t st_meta, uint64_t* launches);
 
 }  // namespace ptl

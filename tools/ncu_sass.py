@@ -14,7 +14,8 @@ a = ap.parse_args()
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 so = a.so or os.path.join(root, "portello_b200", "csrc", "libportello_b200.so")
 
-raw = subprocess.run(["ncu", "-i", a.rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+ksel = ["-k", "regex:" + a.kernel.split("ILb")[0] + "$" if "ILb" not in a.kernel and not a.kernel.endswith("kernel") else "regex:" + a.kernel.split("ILb")[0]]  # (the report may hold several kernels)
+raw = subprocess.run(["ncu", "-i", a.rep] + ksel + ["--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units, vals = rows[0], rows[1], rows[2]
 want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
@@ -26,11 +27,11 @@ for i, h in enumerate(hdr):
     if h in want:
         print(f"{h:72s} {vals[i]:>16s} {units[i]}")
 
-src = subprocess.run(["ncu", "-i", a.rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+src = subprocess.run(["ncu", "-i", a.rep] + ksel + ["--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 shdr = rows[1]
 ix = {h: i for i, h in enumerate(shdr)}
-data = rows[2:]
+data = [r for r in rows[2:] if len(r) >= len(shdr) and re.match(r"^(0x)?[0-9a-fA-F]+$", r[ix["Address"]])]
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", so], cwd=tmp, capture_output=True)
 cub = [f for f in os.listdir(tmp) if "kernels" in f][0]
@@ -59,6 +60,12 @@ def addr(r):
     return int(x, 16) if x.startswith("0x") else int(x)
 
 
+seen_addr, uniq = set(), []
+for r in data:  # (a filtered multi-kernel report lists the kernel's instructions once per matching result)
+    if r[ix["Address"]] not in seen_addr:
+        seen_addr.add(r[ix["Address"]])
+        uniq.append(r)
+data = uniq
 base = addr(data[0])
 tot_s = sum(int(r[ix["# Samples"]]) for r in data)
 tot_i = sum(int(r[ix["Instructions Executed"]]) for r in data)
