@@ -223,7 +223,15 @@ struct BamRecLayout {
 
 __device__ __forceinline__ BamRecLayout bam_rec_layout(const BamAsmArgs& A, uint32_t k) {
     BamRecLayout L;
-    L.r = A.rseg_read[A.rec_read_segment[k]];
+    {   // the read that owns record k: last r with read_rec_begin[r] <= k (a fallback record of a read without segments has
+        // no valid rec_read_segment to go through)
+        uint32_t lo = 0, hi = A.n_reads;
+        while (hi - lo > 1u) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (A.read_rec_begin[mid] <= k) lo = mid; else hi = mid;
+        }
+        L.r = lo;
+    }
     L.k0 = A.read_rec_begin[L.r];
     L.k1 = A.read_rec_begin[L.r + 1];
     L.lifted = A.rec_status[k] == 1;
