@@ -192,6 +192,70 @@ __global__ void __launch_bounds__(128) pair_count_kernel(DevStatic S, DevBatch B
     pair_count_body(S, B, W, T, r);
 }
 
+// a3 (count), one WARP per read: lanes over the CIGAR ops and over the contig's segments (same results as
+// pair_count_body).  For 100 kb reads a thread per read walks ~700 ops alone and the batch has too few reads to fill the
+// GPU (configs[4]: 0.33 ms for 29 k read segments); launch_lift picks this kernel from the batch's mean CIGAR length.
+__global__ void __launch_bounds__(128) pair_count_warp_kernel(DevStatic S, DevBatch B, DevWork W, DevTotals* T) {
+    const uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31u;
+    if (r >= B.n_reads) {
+        if (r == B.n_reads && lane == 0) {
+            W.rseg_pair_begin[B.n_rsegs] = 0;
+            totals_reset(T);
+        }
+        return;
+    }
+    const uint32_t s0 = B.read_seg_begin[r], s1 = B.read_seg_begin[r + 1];
+    bool bad = s0 > s1 || s1 > B.n_rsegs || B.read_seq_off[r] + (uint64_t(B.read_seq_len[r]) + 1u) / 2u > B.seq4_bytes;
+    for (uint32_t s = s0; s < s1 && s < B.n_rsegs; ++s) {
+        if (lane == 0) W.rseg_read[s] = r;
+        const uint64_t c0 = B.rseg_cigar_begin[s];
+        const uint32_t n = B.rseg_cigar_len[s];
+        const int64_t pos = B.rseg_pos[s];
+        if (bad || B.rseg_contig[s] >= S.n_contigs || c0 + n > B.n_cigar || pos < 0 || pos > 0x7fffffffLL) {
+            bad = true;
+            if (lane == 0) {
+                W.rseg_ref_len[s] = 0;
+                W.rseg_n_id[s] = 0;
+                W.rseg_read_len[s] = 0;
+                W.rseg_pair_begin[s] = 0;
+            }
+            continue;
+        }
+        const uint32_t* c = B.cigar + c0;
+        unsigned long long ref_len = 0;
+        uint32_t n_id = 0, read_len = 0;
+        for (uint32_t i = lane; i < n; i += 32u) {
+            const uint32_t x = c[i];
+            ref_len += op_ref_adv(x);
+            read_len += op_read_adv(x);
+            n_id += op_is_match(x & 0xfu) ? 0u : 1u;
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            ref_len += __shfl_xor_sync(FULL, ref_len, d);
+            read_len += __shfl_xor_sync(FULL, read_len, d);
+            n_id += __shfl_xor_sync(FULL, n_id, d);
+        }
+        const int64_t start = pos, end = start + int64_t(ref_len);
+        const uint32_t ctg = B.rseg_contig[s];
+        uint32_t cnt = 0;
+        const uint32_t g1 = S.contig_seg_begin[ctg + 1];
+        for (uint32_t g0 = S.contig_seg_begin[ctg]; g0 < g1; g0 += 32u) {
+            const uint32_t g = g0 + lane;
+            const bool hit = g < g1 && end >= int64_t(S.seg_so_start[g]) && start < int64_t(S.seg_so_end[g]);
+            cnt += __popc(__ballot_sync(FULL, hit));
+        }
+        if (lane == 0) {
+            W.rseg_ref_len[s] = int64_t(ref_len);
+            W.rseg_n_id[s] = n_id;
+            W.rseg_read_len[s] = read_len;
+            W.rseg_pair_begin[s] = cnt;
+        }
+    }
+    if (bad && lane == 0) atomicOr(&T->overflow, OVF_INVALID);
+}
+
 // a3 (fill).  One thread per read segment.
 __global__ void __launch_bounds__(128) pair_fill_kernel(DevStatic S, DevBatch B, DevWork W, DevTotals* T) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -272,12 +336,15 @@ __global__ void __launch_bounds__(128) read_finalize_kernel(DevStatic S, DevBatc
 // end / bin (:278-279).
 // The arrays live in ONE compact arena laid out from the batch's own totals (device_types.hpp: result_layout); thread 0
 // also publishes the totals as the arena header, so one D2H copy brings everything the host needs.
+// `rpw` reads per warp (a power of two <= 32; lanes >= rpw own no read and only help with the copies): 32 for HiFi-sized
+// CIGARs; for 100 kb reads with hundreds of ops per record a warp per 32 reads left 0.2 waves of warps on the GPU, each
+// copying 22 k ops through 700 dependent iterations (configs[4]: finalize_emit 0.49 ms for 29 k records).
 __global__ void __launch_bounds__(256) emit_records_kernel(DevStatic S, DevBatch B, DevWork W, char* arena, uint64_t arena_cap, DevTotals* T,
-                                                            uint32_t stage_mask) {
+                                                            uint32_t stage_mask, uint32_t rpw) {
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;
-    const uint32_t r = warp * 32u + lane;
-    if (warp * 32u >= B.n_reads) return;
+    const uint32_t r = (lane < rpw) ? warp * rpw + lane : 0xffffffffu;
+    if (uint64_t(warp) * rpw >= B.n_reads) return;
     const uint2 total = W.read_counts[B.n_reads];
     const ResultLayout L = result_layout(B.n_reads, total.x, total.y);
     const bool fits = L.total <= arena_cap;
@@ -384,7 +451,9 @@ void launch_lift(const DevStatic& S, const DevBatch& B, const DevWork& W, char* 
         for (int i = 1; i < StageEvents::N; ++i) mark(i);
         return;
     }
-    pair_count_kernel<<<(B.n_reads + 1 + 127) / 128, 128, 0, st>>>(S, B, W, T);
+    const uint64_t ops_per_read = B.n_cigar / std::max<uint64_t>(B.n_reads, 1);  // picks kernel shapes only, never results
+    if (ops_per_read > 96) pair_count_warp_kernel<<<unsigned((uint64_t(B.n_reads) + 1 + 3) / 4), 128, 0, st>>>(S, B, W, T);
+    else pair_count_kernel<<<(B.n_reads + 1 + 127) / 128, 128, 0, st>>>(S, B, W, T);
     ++*launches;
     exclusive_scan_inplace<uint32_t>(W.rseg_pair_begin, uint64_t(B.n_rsegs) + 1, scan_tmp, scan_tmp_bytes_, st, launches, nullptr);
     pair_fill_kernel<<<(B.n_rsegs + 1 + 127) / 128, 128, 0, st>>>(S, B, W, T);
@@ -404,7 +473,10 @@ void launch_lift(const DevStatic& S, const DevBatch& B, const DevWork& W, char* 
     read_finalize_kernel<<<(B.n_reads + 1 + 127) / 128, 128, 0, st>>>(S, B, W, T, do_finish);
     ++*launches;
     exclusive_scan_inplace<uint2>(W.read_counts, uint64_t(B.n_reads) + 1, scan_tmp, scan_tmp_bytes_, st, launches, nullptr);
-    emit_records_kernel<<<(B.n_reads + 255) / 256, 256, 0, st>>>(S, B, W, arena, arena_cap, T, stage_mask);
+    // reads per warp of the record emission from the mean CIGAR length of the batch (any value gives the same result)
+    const uint32_t rpw = ops_per_read > 256 ? 1u : ops_per_read > 96 ? 4u : 32u;
+    const uint64_t emit_warps = (uint64_t(B.n_reads) + rpw - 1) / rpw;
+    emit_records_kernel<<<unsigned((emit_warps + 7) / 8), 256, 0, st>>>(S, B, W, arena, arena_cap, T, stage_mask, rpw);
     ++*launches;
     mark(3);
 }
