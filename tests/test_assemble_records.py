@@ -233,3 +233,68 @@ def test_gpu_records_need_names():
     x, _, _ = make_extras(s, pb, 1)
     with pytest.raises(abi.PtlError):
         gctx.assemble_records(x)
+
+
+@pytest.mark.gpu
+def test_gpu_records_properties_at_scale():
+    """Size-independent properties on 60 k reads of configs[1] (no oracle involved): the record stream parses back as BAM
+    records whose core fields are the liftover result, every CIGAR consumes exactly l_seq read bases, a flipped record's
+    qualities are the input's reversed and flipping its bases twice gives the input back, unflipped records carry the
+    input bytes, and the aux block is the surviving input tags followed by PS, ZM and (iff the read has several records) SA."""
+    s = synth.make("chr20", n_reads=60_000)
+    pb = helpers.pack(s)
+    gctx = helpers.gpu_context(s)
+    res = helpers.lift_c(gctx, pb.c)
+    x, names, auxs = make_extras(s, pb, 5)
+    gctx.set_names(s.contig_names, s.chrom_names)
+    out, (rb, by) = gctx.assemble_records(x)
+    assert out.n_records == res.n_records and int(rb[-1]) == by.size == out.bytes_written
+    b = pb.c
+    seg_begin = np.ctypeslib.as_array(b.read_seg_begin, (b.n_reads + 1,))
+    seq_len = np.ctypeslib.as_array(b.read_seq_len, (b.n_reads,))
+    seq_off = np.ctypeslib.as_array(b.read_seq_off, (b.n_reads,))
+    pool = np.ctypeslib.as_array(b.seq4, (int(b.seq4_bytes),))
+    rec_read = np.repeat(np.arange(b.n_reads), np.diff(res.read_rec_begin.astype(np.int64)))
+    raw = by.tobytes()
+    n_flip = n_sa = 0
+    for k in range(0, res.n_records, 7):  # every 7th record (python-side parsing is the slow part)
+        r = int(rec_read[k])
+        o = int(rb[k])
+        (block_size,) = struct.unpack_from("<I", raw, o)
+        assert o + 4 + block_size == int(rb[k + 1])
+        tid, pos, l_name, mapq, bin_, n_cig, flag, l_seq, mtid, mpos, tlen = struct.unpack_from("<iiBBHHHIiii", raw, o + 4)
+        assert (tid, pos, mapq, bin_, flag) == (int(res.rec_tid[k]), int(res.rec_pos[k]), int(res.rec_mapq[k]), int(res.rec_bin[k]), int(res.rec_flag[k]))
+        assert (mtid, mpos, tlen, l_seq) == (int(x["mate_tid"][r]), int(x["mate_pos"][r]), int(x["tlen"][r]), int(seq_len[r]))
+        p = o + 36
+        assert raw[p: p + l_name] == names[r] + b"\0"
+        p += l_name
+        cig = np.frombuffer(raw, "<u4", n_cig, p)
+        assert np.array_equal(cig, res.cigar[int(res.rec_cigar_begin[k]): int(res.rec_cigar_begin[k + 1])])
+        if res.rec_status[k] == 1:
+            assert int(sum(int(c) >> 4 for c in cig if (int(c) & 15) in (0, 1, 4, 7, 8))) == l_seq  # M I S = X consume the read
+        p += 4 * n_cig
+        seq = np.frombuffer(raw, np.uint8, (l_seq + 1) // 2, p)
+        p += (l_seq + 1) // 2
+        qual = np.frombuffer(raw, np.uint8, l_seq, p)
+        p += l_seq
+        src_seq = pool[int(seq_off[r]): int(seq_off[r]) + (l_seq + 1) // 2]
+        src_q = x["qual"][int(x["qual_off"][r]): int(x["qual_off"][r]) + l_seq]
+        if res.rec_need_flip[k]:
+            n_flip += 1
+            assert np.array_equal(qual, src_q[::-1])
+            nib = np.empty(2 * len(seq), np.uint8)
+            nib[0::2], nib[1::2] = seq >> 4, seq & 15
+            back = COMP[nib[:l_seq][::-1]]  # revcomp of the revcomp = the input (the synthetic reads are A/C/G/T)
+            src_nib = np.empty(2 * len(src_seq), np.uint8)
+            src_nib[0::2], src_nib[1::2] = src_seq >> 4, src_seq & 15
+            assert np.array_equal(back, src_nib[:l_seq])
+        else:
+            assert np.array_equal(seq, src_seq) and np.array_equal(qual, src_q)
+        aux = raw[p: int(rb[k + 1])]
+        kept = strip_tags(auxs[r])
+        assert aux.startswith(kept)
+        tail = [t for t, _, _ in aux_fields(aux[len(kept):])]
+        many = int(res.read_rec_begin[r + 1]) - int(res.read_rec_begin[r]) > 1
+        assert tail == ([b"PS", b"ZM"] + ([b"SA"] if many else []) if res.rec_status[k] == 1 else [])
+        n_sa += many
+    assert n_flip > 0 and n_sa > 0
