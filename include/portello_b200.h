@@ -296,6 +296,17 @@ typedef struct {
  *        PTL_ASM_NO_DOWNLOAD   = results stay on the device (out->bytes is NULL): kernel timing only. */
 int ptl_assemble_records(ptl_ctx* ctx, int slot, const ptl_read_extras* extras, uint32_t flags, ptl_bam_records* out);
 
+/* ---------------------------------------------------------------- BAM container (output half; host C++ + zlib)
+ *
+ * What bam::Writer does around the records (src/read_alignment_scanner.rs:537-559), written from the SAM specification
+ * without htslib: the header block (4.2: magic, l_text, text, n_ref, {l_name, name, l_ref}) and BGZF framing (4.1:
+ * independent gzip members of <= 0xff00 payload bytes with the BC size subfield, CRC32, ISIZE; the 28-byte EOF marker).
+ * Feed it the header bytes and then the bytes of ptl_assemble_records; blocks are compressed on n_threads host threads
+ * (the reference's --threads).  Both return the number of bytes written, or a negative PTL_ERR_* code. */
+int64_t ptl_bam_header(const char* sam_text, uint32_t n_ref, const char* const* ref_names, const uint64_t* ref_len, uint8_t* out, uint64_t cap);
+uint64_t ptl_bgzf_bound(uint64_t n);   /* output capacity that always suffices for n input bytes (+ EOF marker) */
+int64_t ptl_bgzf_compress(const uint8_t* in, uint64_t n, int level, int n_threads, int append_eof, uint8_t* out, uint64_t cap);
+
 /* cudaStream_t of a slot (as void*), so callers can bracket work with their own CUDA events. */
 void* ptl_slot_stream(ptl_ctx* ctx, int slot);
 /* Per-kernel device time of the LAST ptl_lift_run on the slot, CUDA events on the slot stream.

@@ -298,3 +298,37 @@ def test_gpu_records_properties_at_scale():
         assert tail == ([b"PS", b"ZM"] + ([b"SA"] if many else []) if res.rec_status[k] == 1 else [])
         n_sa += many
     assert n_flip > 0 and n_sa > 0
+
+
+def _long_cigar_case():
+    """One read whose lifted CIGAR has 70 000 ops (1M1I repeated): more than the u16 n_cigar_op of a BAM record."""
+    n_pairs = 35_000
+    cig = np.tile(np.array([(1 << 4) | 7, (1 << 4) | 1], np.uint32), n_pairs)  # 1= 1I ...
+    seq_len = 2 * n_pairs
+    segs, batch = helpers.single_pair_case(f"{n_pairs + 10}=", 100, True, n_pairs + 10, None, 5, cig, np.full(seq_len // 2, 0x12, np.uint8), seq_len)
+    x = dict(name_off=np.array([0, 2], np.uint64), names=np.frombuffer(b"r1" + b"\0" * 8, np.uint8).copy(), aux_off=np.array([0, 0], np.uint64),
+             aux=np.zeros(8, np.uint8), mate_tid=np.array([-1], np.int32), mate_pos=np.array([-1], np.int32), tlen=np.array([0], np.int32),
+             qual=np.full(seq_len + 8, 30, np.uint8), qual_off=np.array([0], np.uint64))
+    return segs, batch, x
+
+
+def _check_long_cigar_rejected(ctx):
+    segs, batch, x = _long_cigar_case()
+    ctx.set_reference([np.frombuffer(b"A" * 40_000, np.uint8).copy()])
+    ctx.set_contig_segments(segs)
+    res = ctx.lift(batch)
+    assert res.n_records == 1 and res.rec_status[0] == 1 and int(res.rec_cigar_begin[1]) == 70_000
+    ctx.set_names(["ctg"], ["chr1"])
+    with pytest.raises(abi.PtlError, match="65535"):
+        ctx.assemble_records(x)
+
+
+def test_oracle_rejects_cigars_beyond_u16():
+    import oracle_lib
+    _check_long_cigar_rejected(abi.Context(oracle_lib.load(), 0, 1))
+
+
+@pytest.mark.gpu
+def test_gpu_rejects_cigars_beyond_u16():
+    from portello_b200 import lib
+    _check_long_cigar_rejected(lib.GpuContext(0, 1))

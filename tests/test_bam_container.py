@@ -1,0 +1,130 @@
+"""BAM container around the assembled records (output half): ptl_bam_header + ptl_bgzf_compress are
+host code written from the SAM specification (no htslib).  Checked against Python's own zlib/gzip (independent
+implementation of the same RFC 1952 framing) and by parsing the result back."""
+import ctypes as C
+import gzip
+import struct
+import zlib
+
+import numpy as np
+import pytest
+
+import helpers
+from portello_b200 import abi, lib, synth
+
+EOF_BLOCK = bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
+
+
+def _fns():
+    d = lib.load().dll
+    d.ptl_bgzf_bound.restype, d.ptl_bgzf_bound.argtypes = C.c_uint64, [C.c_uint64]
+    d.ptl_bgzf_compress.restype = C.c_int64
+    d.ptl_bgzf_compress.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_uint64]
+    d.ptl_bam_header.restype = C.c_int64
+    d.ptl_bam_header.argtypes = [C.c_char_p, C.c_uint32, C.POINTER(C.c_char_p), C.POINTER(C.c_uint64), C.c_void_p, C.c_uint64]
+    return d
+
+
+def bgzf(data: bytes, level=6, threads=4, eof=True) -> bytes:
+    d = _fns()
+    src = np.frombuffer(data, np.uint8) if data else np.zeros(1, np.uint8)
+    out = np.zeros(int(d.ptl_bgzf_bound(len(data))), np.uint8)
+    n = d.ptl_bgzf_compress(src.ctypes.data, len(data), level, threads, int(eof), out.ctypes.data, out.size)
+    assert n >= 0, n
+    return out[:n].tobytes()
+
+
+def bam_header(text: str, names, lens) -> bytes:
+    d = _fns()
+    arr = (C.c_char_p * max(len(names), 1))(*[n.encode() for n in names])
+    ln = (C.c_uint64 * max(len(lens), 1))(*lens)
+    out = np.zeros(len(text) + 64 + sum(len(n) + 16 for n in names), np.uint8)
+    n = d.ptl_bam_header(text.encode(), len(names), arr, ln, out.ctypes.data, out.size)
+    assert n >= 0, n
+    return out[:n].tobytes()
+
+
+def blocks(stream: bytes):
+    """[(offset, bsize, payload)] of a BGZF stream, checking the fixed header fields of every block (SAM spec 4.1)."""
+    out, at = [], 0
+    while at < len(stream):
+        assert stream[at: at + 4] == b"\x1f\x8b\x08\x04" and stream[at + 10: at + 16] == b"\x06\x00BC\x02\x00"
+        bsize = struct.unpack_from("<H", stream, at + 16)[0] + 1
+        crc, isize = struct.unpack_from("<II", stream, at + bsize - 8)
+        payload = zlib.decompress(stream[at + 18: at + bsize - 8], -15)
+        assert len(payload) == isize and zlib.crc32(payload) == crc and isize <= 0xff00
+        out.append((at, bsize, payload))
+        at += bsize
+    assert at == len(stream)
+    return out
+
+
+@pytest.mark.parametrize("n", [0, 1, 0xff00 - 1, 0xff00, 0xff00 + 1, 1_000_003])
+@pytest.mark.parametrize("kind", ["text", "random"])
+def test_bgzf_round_trip(n, kind):
+    rng = np.random.default_rng(n + 7)
+    data = (rng.integers(65, 70, n, dtype=np.uint8) if kind == "text" else rng.integers(0, 256, n, dtype=np.uint8)).tobytes()  # random = incompressible
+    z = bgzf(data, threads=3)
+    assert gzip.decompress(z) == data                     # python's gzip reads concatenated members
+    bl = blocks(z)
+    assert z.endswith(EOF_BLOCK) and bl[-1][2] == b""     # the EOF marker block
+    assert len(bl) == (n + 0xff00 - 1) // 0xff00 + 1
+    assert b"".join(p for _, _, p in bl) == data
+    assert bgzf(data, threads=1) == z                     # thread count does not change the bytes
+
+
+def test_bgzf_levels_and_no_eof():
+    data = bytes(range(256)) * 999
+    assert gzip.decompress(bgzf(data, level=1)) == data and gzip.decompress(bgzf(data, level=9)) == data
+    z = bgzf(data, eof=False)
+    assert not z.endswith(EOF_BLOCK) and gzip.decompress(z) == data
+
+
+def test_bam_header_layout():
+    text = "@HD\tVN:1.6\tSO:unsorted\n@SQ\tSN:chr1\tLN:1000\n@SQ\tSN:chrUn_x\tLN:77\n"
+    h = bam_header(text, ["chr1", "chrUn_x"], [1000, 77])
+    assert h[:4] == b"BAM\x01"
+    (l_text,) = struct.unpack_from("<i", h, 4)
+    assert h[8: 8 + l_text].decode() == text
+    at = 8 + l_text
+    (n_ref,) = struct.unpack_from("<i", h, at)
+    at += 4
+    got = []
+    for _ in range(n_ref):
+        (l_name,) = struct.unpack_from("<i", h, at)
+        name = h[at + 4: at + 4 + l_name]
+        (l_ref,) = struct.unpack_from("<i", h, at + 4 + l_name)
+        got.append((name, l_ref))
+        at += 8 + l_name
+    assert got == [(b"chr1\0", 1000), (b"chrUn_x\0", 77)] and at == len(h)
+
+
+def test_oracle_records_to_bam_file(tmp_path):
+    """Whole output path on the CPU checker: lift -> records -> header + BGZF -> a .bam file that parses back record by record."""
+    from test_assemble_records import make_extras
+    s = synth.make("tiny", seed=5, n_reads=400)
+    pb = helpers.pack(s)
+    octx = helpers.oracle_context(s)
+    res = helpers.lift_c(octx, pb.c)
+    x, names, _ = make_extras(s, pb, 3)
+    octx.set_names(s.contig_names, s.chrom_names)
+    _, (rb, by) = octx.assemble_records(x)
+    lens = [int(s.chrom_len[i]) for i in range(s.n_chrom)]
+    text = "@HD\tVN:1.6\tSO:unsorted\n" + "".join(f"@SQ\tSN:{n}\tLN:{l}\n" for n, l in zip(s.chrom_names, lens))
+    path = tmp_path / "out.bam"
+    path.write_bytes(bgzf(bam_header(text, s.chrom_names, lens) + by.tobytes()))
+    raw = gzip.open(path, "rb").read()
+    assert raw[:4] == b"BAM\x01"
+    at = 8 + struct.unpack_from("<i", raw, 4)[0]
+    n_ref = struct.unpack_from("<i", raw, at)[0]
+    at += 4
+    for _ in range(n_ref):
+        at += 8 + struct.unpack_from("<i", raw, at)[0]
+    k = 0
+    while at < len(raw):
+        (block_size,) = struct.unpack_from("<I", raw, at)
+        tid, pos = struct.unpack_from("<ii", raw, at + 4)
+        assert (tid, pos) == (int(res.rec_tid[k]), int(res.rec_pos[k]))
+        at += 4 + block_size
+        k += 1
+    assert k == res.n_records and at == len(raw)
