@@ -307,6 +307,25 @@ int64_t ptl_bam_header(const char* sam_text, uint32_t n_ref, const char* const* 
 uint64_t ptl_bgzf_bound(uint64_t n);   /* output capacity that always suffices for n input bytes (+ EOF marker) */
 int64_t ptl_bgzf_compress(const uint8_t* in, uint64_t n, int level, int n_threads, int append_eof, uint8_t* out, uint64_t cap);
 
+/* ---------------------------------------------------------------- BGZF framing on the device, compression level 0
+ *
+ * The reference's documented pipe mode (`--remapped-read-output -`, "to optimize piping into samtools sort") writes
+ * UNCOMPRESSED BAM: bam::Writer::from_stdout + CompressionLevel::Uncompressed (src/read_alignment_scanner.rs:66-71), i.e.
+ * BGZF blocks holding one stored deflate block each.  ptl_bgzf_store_records frames [prefix | the records of the slot's last
+ * ptl_assemble_records] that way on the device (SAM spec 4.1: 18-byte header with the BC subfield, 01 LEN NLEN, <= 0xff00
+ * bytes, CRC32, ISIZE; the CRC is computed in the kernel), so the host only moves bytes to its pipe.  `prefix` (may be NULL)
+ * is typically ptl_bam_header's output on the first batch; at most 32 KB.
+ * flags: PTL_ASM_NO_DOWNLOAD (timing only), PTL_BGZF_EOF (append the 28-byte EOF marker). */
+#define PTL_BGZF_EOF 4u
+typedef struct {
+    uint64_t n_bytes;               /* BGZF bytes */
+    const uint8_t* bytes;           /* NULL with PTL_ASM_NO_DOWNLOAD */
+    uint64_t n_blocks;
+    float kernel_ms;                /* device time of the framing kernel (CUDA events on the slot stream) */
+    uint64_t bytes_read, bytes_written;  /* algorithmic bytes: the stream once in, the framed stream once out */
+} ptl_bgzf_stream;
+int ptl_bgzf_store_records(ptl_ctx* ctx, int slot, const uint8_t* prefix, uint64_t prefix_bytes, uint32_t flags, ptl_bgzf_stream* out);
+
 /* cudaStream_t of a slot (as void*), so callers can bracket work with their own CUDA events. */
 void* ptl_slot_stream(ptl_ctx* ctx, int slot);
 /* Per-kernel device time of the LAST ptl_lift_run on the slot, CUDA events on the slot stream.

@@ -141,6 +141,14 @@ class ReadExtrasC(C.Structure):
                 ("tlen", i32p), ("quals", ReadQualsC)]
 
 
+class BgzfStreamC(C.Structure):
+    _fields_ = [("n_bytes", C.c_uint64), ("bytes", u8p), ("n_blocks", C.c_uint64), ("kernel_ms", C.c_float),
+                ("bytes_read", C.c_uint64), ("bytes_written", C.c_uint64)]
+
+
+BGZF_EOF = 4
+
+
 class BamRecordsC(C.Structure):
     _fields_ = [("n_records", C.c_uint32), ("rec_begin", u64p), ("bytes", u8p), ("kernel_ms", C.c_float),
                 ("bytes_read", C.c_uint64), ("bytes_written", C.c_uint64)]
@@ -568,4 +576,15 @@ class Context:
         rb = np.ctypeslib.as_array(out.rec_begin, (n + 1,)).copy()
         by = np.ctypeslib.as_array(out.bytes, (max(int(rb[n]), 1),))[: int(rb[n])].copy() if n else np.zeros(0, np.uint8)
         return out, (rb, by)
+
+    def bgzf_store_records(self, prefix: bytes = b"", slot: int = 0, flags: int = 0):
+        """ptl_bgzf_store_records: [prefix | records of the slot's last assemble_records] as level-0 BGZF.  Returns
+        (BgzfStreamC, bytes) -- bytes is None with ASM_NO_DOWNLOAD."""
+        fn = getattr(self.lib.dll, self.lib.prefix + "bgzf_store_records")
+        fn.restype, fn.argtypes = C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_uint64, C.c_uint32, C.POINTER(BgzfStreamC)]
+        out = BgzfStreamC()
+        self._check(fn(self.h, slot, prefix if prefix else None, len(prefix), flags, C.byref(out)))
+        if flags & ASM_NO_DOWNLOAD:
+            return out, None
+        return out, bytes(np.ctypeslib.as_array(out.bytes, (max(int(out.n_bytes), 1),))[: int(out.n_bytes)])
 

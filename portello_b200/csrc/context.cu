@@ -18,6 +18,7 @@
 #include "../../include/portello_b200.h"
 #include "device/assemble.cuh"
 #include "device/assemble_bam.cuh"
+#include "device/bgzf_store.cuh"
 #include "device/kernels.hpp"
 #include "host/contig_prep.hpp"
 
@@ -99,6 +100,9 @@ struct Slot {
     HBuf hb_rec_begin, hb_out, hb_err;
     bool b_resident = false;
     uint64_t b_in_bytes = 0;
+    uint64_t b_total = 0;             // bytes of the records assembled last (they start kBamFront bytes into b_out)
+    DBuf z_out;                       // ptl_bgzf_store_records
+    HBuf hz_out;
     cudaStream_t b_stream = nullptr;  // the meta kernel of the record assembly runs beside the streaming kernel
     cudaEvent_t b_fork = nullptr, b_join = nullptr;
     // results: one compact arena on the device (device_types.hpp: result_layout) and its pinned host twin
@@ -128,7 +132,8 @@ struct ptl_ctx {
     uint32_t long_pair_ops = 64;  // ptl_set_long_pair_ops
     // static state
     DBuf s_ref, s_chrom_off, s_contig_seg_begin, s_contig_len, s_contig_rev_off, s_rev_pool, s_so_start, s_so_end, s_chrom, s_pos,
-        s_is_fwd, s_mapq, s_cigar_begin, s_cigar, s_tab_begin, s_table, s_contig_name_off, s_contig_names, s_chrom_name_off, s_chrom_names;
+        s_is_fwd, s_mapq, s_cigar_begin, s_cigar, s_tab_begin, s_table, s_contig_name_off, s_contig_names, s_chrom_name_off, s_chrom_names,
+        s_bgzf_tables;
     uint32_t n_contig_names = 0, n_chrom_names = 0;  // ptl_set_names
     bool have_names = false;
     DevStatic S;
@@ -545,10 +550,10 @@ void ptl_destroy(ptl_ctx* ctx) {
                         &sl.w_pair_slot_begin, &sl.w_pair_status, &sl.w_pair_flip, &sl.w_pair_pos, &sl.w_pair_n_out, &sl.w_pair_bin, &sl.w_pair_out_off, &sl.w_simplify_list, &sl.w_long_list,
                         &sl.w_scratch, &sl.w_read_counts, &sl.w_read_primary, &sl.w_scan_tmp, &sl.w_totals, &sl.r_arena, &sl.a_qual, &sl.a_qual_off,
                         &sl.a_rec_read, &sl.a_seq_begin, &sl.a_qual_begin, &sl.a_out_seq, &sl.a_out_qual, &sl.b_name_off, &sl.b_names, &sl.b_aux_off,
-                        &sl.b_aux, &sl.b_mate_tid, &sl.b_mate_pos, &sl.b_tlen, &sl.b_keep, &sl.b_sa_len, &sl.b_rec_begin, &sl.b_rec_desc, &sl.b_out, &sl.b_err})
+                        &sl.b_aux, &sl.b_mate_tid, &sl.b_mate_pos, &sl.b_tlen, &sl.b_keep, &sl.b_sa_len, &sl.b_rec_begin, &sl.b_rec_desc, &sl.b_out, &sl.b_err, &sl.z_out})
             b->release();
         sl.h_arena.release();
-        for (HBuf* b : {&sl.ha_seq_begin, &sl.ha_qual_begin, &sl.ha_out_seq, &sl.ha_out_qual, &sl.hb_rec_begin, &sl.hb_out, &sl.hb_err}) b->release();
+        for (HBuf* b : {&sl.ha_seq_begin, &sl.ha_qual_begin, &sl.ha_out_seq, &sl.ha_out_qual, &sl.hb_rec_begin, &sl.hb_out, &sl.hb_err, &sl.hz_out}) b->release();
         for (auto& e : sl.a_ev) if (e) cudaEventDestroy(e);
         if (sl.b_fork) cudaEventDestroy(sl.b_fork);
         if (sl.b_join) cudaEventDestroy(sl.b_join);
@@ -560,7 +565,7 @@ void ptl_destroy(ptl_ctx* ctx) {
     for (DBuf* b : {&ctx->s_ref, &ctx->s_chrom_off, &ctx->s_contig_seg_begin, &ctx->s_contig_len, &ctx->s_contig_rev_off, &ctx->s_rev_pool,
                     &ctx->s_so_start, &ctx->s_so_end, &ctx->s_chrom, &ctx->s_pos, &ctx->s_is_fwd, &ctx->s_mapq, &ctx->s_cigar_begin,
                     &ctx->s_cigar, &ctx->s_tab_begin, &ctx->s_table, &ctx->s_contig_name_off, &ctx->s_contig_names, &ctx->s_chrom_name_off,
-                    &ctx->s_chrom_names})
+                    &ctx->s_chrom_names, &ctx->s_bgzf_tables})
         b->release();
     if (ctx->setup_stream) cudaStreamDestroy(ctx->setup_stream);
     delete ctx;
@@ -771,6 +776,73 @@ int ptl_assemble_bases(ptl_ctx* ctx, int slot, const ptl_read_quals* quals, uint
         return PTL_OK;
     });
 }
+// Records are assembled kBamFront bytes into their buffer, so that a stream prefix (the BAM header) can sit right in front.
+constexpr uint64_t kBamFront = 1ull << 16;
+
+// CRC-32 (IEEE 802.3, reflected) table and the GF(2) matrices of "advance the state through 255 * 2^k zero bytes"
+static uint32_t crc_zero_bytes(const uint32_t* t, uint32_t v, uint64_t n) {
+    for (uint64_t i = 0; i < n; ++i) v = t[v & 0xffu] ^ (v >> 8);
+    return v;
+}
+static std::vector<uint32_t> bgzf_tables() {
+    std::vector<uint32_t> t(kBgzfTableWords);
+    for (uint32_t i = 0; i < 256; ++i) {
+        uint32_t c = i;
+        for (int k = 0; k < 8; ++k) c = (c & 1u) ? (c >> 1) ^ 0xEDB88320u : c >> 1;
+        t[i] = c;
+    }
+    for (int k = 0; k < 8; ++k)
+        for (int b = 0; b < 32; ++b) t[256 + 32 * k + b] = crc_zero_bytes(t.data(), 1u << b, 255ull << k);
+    return t;
+}
+
+// BGZF framing on the device, level 0: see include/portello_b200.h.
+int ptl_bgzf_store_records(ptl_ctx* ctx, int slot, const uint8_t* prefix, uint64_t prefix_bytes, uint32_t flags, ptl_bgzf_stream* out) {
+    Slot* sl = get_slot(ctx, slot);
+    if (!sl || !out || (prefix_bytes && !prefix) || prefix_bytes > kBamFront / 2) return PTL_ERR_INVALID_ARG;
+    if (!sl->b_resident || !sl->b_out.p) return fail(ctx, PTL_ERR_STATE, "ptl_bgzf_store_records without ptl_assemble_records on the slot");
+    return guarded(ctx, [&]() {
+        cudaStream_t st = sl->stream;
+        static const std::vector<uint32_t> tables = bgzf_tables();
+        if (!ctx->s_bgzf_tables.p) upload(ctx->s_bgzf_tables, tables.data(), tables.size(), st);
+        uint8_t* stream = sl->b_out.as<uint8_t>() + kBamFront - prefix_bytes;
+        if (prefix_bytes) CK(cudaMemcpyAsync(stream, prefix, prefix_bytes, cudaMemcpyHostToDevice, st));
+        const uint64_t n = prefix_bytes + sl->b_total;
+        const uint64_t n_blocks = (n + kBgzfIn - 1) / kBgzfIn;
+        const uint64_t framed = n + uint64_t(kBgzfOverhead) * n_blocks;
+        static const uint8_t kEof[28] = {0x1f, 0x8b, 0x08, 0x04, 0, 0, 0, 0, 0, 0xff, 0x06, 0, 0x42, 0x43, 0x02, 0, 0x1b, 0, 0x03, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        const uint64_t total = framed + ((flags & PTL_BGZF_EOF) ? sizeof(kEof) : 0);
+        sl->z_out.ensure(total + 64, st);
+        BgzfArgs A{};
+        A.in = stream;
+        A.n = n;
+        A.out = sl->z_out.as<uint8_t>();
+        A.tables = ctx->s_bgzf_tables.as<uint32_t>();
+        A.n_blocks = n_blocks;
+        A.init_full = crc_zero_bytes(tables.data(), 0xffffffffu, kBgzfIn);
+        A.init_last = crc_zero_bytes(tables.data(), 0xffffffffu, n_blocks ? n - (n_blocks - 1) * kBgzfIn : 0);
+        if (!sl->a_ev[0]) { CK(cudaEventCreate(&sl->a_ev[0])); CK(cudaEventCreate(&sl->a_ev[1])); }
+        CK(cudaEventRecord(sl->a_ev[0], st));
+        launch_bgzf_store(A, st, &ctx->launches);
+        CK(cudaEventRecord(sl->a_ev[1], st));
+        if (flags & PTL_BGZF_EOF) CK(cudaMemcpyAsync(sl->z_out.as<uint8_t>() + framed, kEof, sizeof(kEof), cudaMemcpyHostToDevice, st));
+        *out = ptl_bgzf_stream{};
+        if (!(flags & PTL_ASM_NO_DOWNLOAD)) {
+            sl->hz_out.ensure(total + 64);
+            if (total) CK(cudaMemcpyAsync(sl->hz_out.p, sl->z_out.p, total, cudaMemcpyDeviceToHost, st));
+            out->bytes = sl->hz_out.as<uint8_t>();
+        }
+        CK(cudaStreamSynchronize(st));
+        CK(cudaGetLastError());
+        CK(cudaEventElapsedTime(&out->kernel_ms, sl->a_ev[0], sl->a_ev[1]));
+        out->n_bytes = total;
+        out->n_blocks = n_blocks;
+        out->bytes_read = n;
+        out->bytes_written = framed;
+        return PTL_OK;
+    });
+}
+
 // Record assembly, whole BAM records: see include/portello_b200.h.
 int ptl_set_names(ptl_ctx* ctx, uint32_t n_contigs, const char* const* contig_names, uint32_t n_chrom, const char* const* chrom_names) {
     if (!ctx || (n_contigs && !contig_names) || (n_chrom && !chrom_names)) return PTL_ERR_INVALID_ARG;
@@ -892,8 +964,9 @@ int ptl_assemble_records(ptl_ctx* ctx, int slot, const ptl_read_extras* x, uint3
         if (err & 2u) throw std::runtime_error("a lifted CIGAR has more than 65535 ops (BAM needs a CG tag for it: out of scope)");
         if (err & 4u) throw std::runtime_error("a contig name longer than 248 bytes or more than 16 MB of SA text in one record");
         const uint64_t total = sl->hb_rec_begin.as<uint64_t>()[n_rec];
-        sl->b_out.ensure(total + 32, st);
-        A.out = sl->b_out.as<uint8_t>();
+        sl->b_out.ensure(kBamFront + total + 64, st);  // (headroom in front: ptl_bgzf_store_records puts its prefix there)
+        A.out = sl->b_out.as<uint8_t>() + kBamFront;
+        sl->b_total = total;
         if (!sl->a_ev[0]) { CK(cudaEventCreate(&sl->a_ev[0])); CK(cudaEventCreate(&sl->a_ev[1])); }
         if (!sl->b_stream) {
             CK(cudaStreamCreateWithFlags(&sl->b_stream, cudaStreamNonBlocking));
@@ -909,7 +982,7 @@ int ptl_assemble_records(ptl_ctx* ctx, int slot, const ptl_read_extras* x, uint3
         CK(cudaEventRecord(sl->a_ev[1], st));
         if (!(flags & PTL_ASM_NO_DOWNLOAD)) {
             sl->hb_out.ensure(total + 32);
-            if (total) CK(cudaMemcpyAsync(sl->hb_out.p, sl->b_out.p, total, cudaMemcpyDeviceToHost, st));
+            if (total) CK(cudaMemcpyAsync(sl->hb_out.p, sl->b_out.as<uint8_t>() + kBamFront, total, cudaMemcpyDeviceToHost, st));
             out->bytes = sl->hb_out.as<uint8_t>();
         }
         CK(cudaStreamSynchronize(st));

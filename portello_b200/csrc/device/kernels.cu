@@ -11,6 +11,7 @@
 
 #include "assemble.cuh"
 #include "assemble_bam.cuh"
+#include "bgzf_store.cuh"
 #include "kernels.hpp"
 #include "lift_device.cuh"
 #include "lift_warp.cuh"
@@ -649,6 +650,26 @@ void launch_bam_write(const BamAsmArgs& A, cudaStream_t st, cudaStream_t st_meta
     bam_write_meta_kernel<<<(A.n_records + 3) / 4, 128, 0, st_meta>>>(A);
     bam_write_kernel<<<A.n_records, 256, 0, st>>>(A);
     *launches += 2;
+}
+
+// =================================================================================================== BGZF framing, level 0
+namespace {
+__global__ void __launch_bounds__(256) bgzf_store_kernel(BgzfArgs A) {
+    extern __shared__ __align__(16) uint8_t bgzf_smem[];
+    bgzf_store_block_body(A, blockIdx.x, threadIdx.x, bgzf_smem);
+}
+}  // namespace
+
+void launch_bgzf_store(const BgzfArgs& A, cudaStream_t st, uint64_t* launches) {
+    if (!A.n_blocks) return;
+    const int smem = int(kBgzfIn + 48u + (kBgzfTableWords + 8u) * 4u);
+    static bool configured = false;  // (one device per process)
+    if (!configured) {
+        cudaFuncSetAttribute(bgzf_store_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        configured = true;
+    }
+    bgzf_store_kernel<<<unsigned(A.n_blocks), 256, smem, st>>>(A);
+    ++*launches;
 }
 
 }  // namespace ptl

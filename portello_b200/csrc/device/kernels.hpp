@@ -41,4 +41,8 @@ struct BamAsmArgs;
 void launch_bam_sizes(const BamAsmArgs& A, void* scan_tmp, size_t scan_tmp_bytes, cudaStream_t st, uint64_t* launches);
 void launch_bam_write(const BamAsmArgs& A, cudaStream_t st, cudaStream_t st_meta, uint64_t* launches);
 
+// BGZF framing at compression level 0 (bgzf_store.cuh): one thread block per BGZF block.
+struct BgzfArgs;
+void launch_bgzf_store(const BgzfArgs& A, cudaStream_t st, uint64_t* launches);
+
 }  // namespace ptl

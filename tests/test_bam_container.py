@@ -128,3 +128,44 @@ def test_oracle_records_to_bam_file(tmp_path):
         at += 4 + block_size
         k += 1
     assert k == res.n_records and at == len(raw)
+
+
+def bgzf_level0_model(data: bytes, eof: bool) -> bytes:
+    """Level-0 BGZF as htslib writes it: per <= 0xff00 bytes one gzip member holding ONE stored deflate block."""
+    out = []
+    for at in range(0, len(data), 0xff00):
+        d = data[at: at + 0xff00]
+        bsize = len(d) + 31
+        out.append(b"\x1f\x8b\x08\x04\0\0\0\0\0\xff\x06\0BC\x02\0" + struct.pack("<H", bsize - 1) + b"\x01" + struct.pack("<HH", len(d), ~len(d) & 0xffff)
+                   + d + struct.pack("<II", zlib.crc32(d), len(d)))
+    return b"".join(out) + (EOF_BLOCK if eof else b"")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["tiny", "config1", "one-read"])
+def test_gpu_bgzf_store_matches_model(case):
+    """ptl_bgzf_store_records (CRC32 + framing on the device) against the Python model and python's own gzip reader."""
+    from test_assemble_records import make_extras
+    s = synth.make("tiny" if case != "config1" else "config1", seed=6, **({"n_reads": 600} if case == "config1" else {"n_reads": 1 if case == "one-read" else 700}))
+    pb = helpers.pack(s)
+    gctx = helpers.gpu_context(s)
+    helpers.lift_c(gctx, pb.c, allow_panic=True)
+    x, _, _ = make_extras(s, pb, 4)
+    gctx.set_names(s.contig_names, s.chrom_names)
+    _, (rb, by) = gctx.assemble_records(x)
+    lens = [int(s.chrom_len[i]) for i in range(s.n_chrom)]
+    for prefix, eofs in ((b"", (False,)), (bam_header("@HD\tVN:1.6\tSO:unsorted\n", s.chrom_names, lens), (True,)), (b"x" * 12345, (False, True))):
+        for eof in eofs:
+            o, z = gctx.bgzf_store_records(prefix, flags=abi.BGZF_EOF if eof else 0)
+            want = prefix + by.tobytes()
+            assert gzip.decompress(z) == want if want else z == (EOF_BLOCK if eof else b"")
+            assert z == bgzf_level0_model(want, eof)
+            assert o.n_blocks == (len(want) + 0xff00 - 1) // 0xff00 and o.bytes_read == len(want)
+    o2, none = gctx.bgzf_store_records(b"", flags=abi.ASM_NO_DOWNLOAD)
+    assert none is None and o2.kernel_ms >= 0
+
+
+def test_bgzf_level0_model_is_valid_gzip():
+    data = bytes(np.random.default_rng(3).integers(0, 256, 200_001, dtype=np.uint8))
+    assert gzip.decompress(bgzf_level0_model(data, True)) == data
+    assert [len(p) for _, _, p in blocks(bgzf_level0_model(data, True))] == [0xff00, 0xff00, 0xff00, 200_001 - 3 * 0xff00, 0]
