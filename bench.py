@@ -472,6 +472,13 @@ def main():
             ms.append(float(o.kernel_ms))
         r_ms = float(np.mean(ms[max(args.warmup, 3):]))
         r_bytes = int(o.bytes_read + o.bytes_written)
+        # the same records framed as level-0 BGZF on the device (the reference's stdout mode), CRC32 in the kernel
+        zs = []
+        for _ in range(max(args.warmup, 3) + args.steps):
+            zo, _ = ctx.bgzf_store_records(b"", 0, flags=abi.ASM_NO_DOWNLOAD)
+            zs.append(float(zo.kernel_ms))
+        z_ms = float(np.mean(zs[max(args.warmup, 3):]))
+        z_bytes = int(zo.bytes_read + zo.bytes_written)
         xs = extras_for(int(sub.c.n_reads), sl_len, sq, so)
         octx_a.set_names(s.contig_names, s.chrom_names)
         t0 = time.perf_counter()
@@ -481,6 +488,10 @@ def main():
         _, (rbg, byg) = ctx.assemble_records(xs, 1)
         if not (np.array_equal(rbo, rbg) and np.array_equal(byo, byg)):
             raise SystemExit("PARITY FAILURE vs oracle in ptl_assemble_records on the bench workload")
+        import gzip
+        _, zb = ctx.bgzf_store_records(b"", 1, flags=abi.BGZF_EOF)
+        if gzip.decompress(zb) != byg.tobytes():
+            raise SystemExit("ptl_bgzf_store_records: the framed stream does not decompress to the records")
         r_traffic = None
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["bam_write_kernel"]
@@ -496,7 +507,12 @@ def main():
                                      "frac": r_bytes / (r_ms / 1e3) / 1e9 / peak, "algorithmic_bytes_per_launch": r_bytes, "traffic": r_traffic},
                         "cpu_baseline": {"value": (len(rbo) - 1) / t_cpu_r, "unit": "records/s", "cores": 1, "kind": "port",
                                          "sample": f"{sub.c.n_reads} reads of this workload, oracle restatement incl. the python-side copy of the result"},
-                        "parity": f"byte-exact vs oracle on {sub.c.n_reads} reads of this workload"}
+                        "parity": f"byte-exact vs oracle on {sub.c.n_reads} reads of this workload",
+                        "bgzf_store": {"kernel": "bgzf_store_kernel", "what": "the records framed as level-0 BGZF blocks, CRC32 computed on the device "
+                                       "(the reference's stdout mode, src/read_alignment_scanner.rs:66-71)", "blocks": int(zo.n_blocks), "kernel_ms": z_ms,
+                                       "roofline": {"bound": "hbm", "achieved": z_bytes / (z_ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                                                    "frac": z_bytes / (z_ms / 1e3) / 1e9 / peak, "algorithmic_bytes_per_launch": z_bytes, "traffic": None},
+                                       "check": f"python gzip reads the framed stream of {sub.c.n_reads} reads back to the record bytes"}}
 
     # ---------------------------------------------------------------- CPU baseline (rank 0, N=1 only)
     cpu = None

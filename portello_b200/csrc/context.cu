@@ -791,8 +791,10 @@ static std::vector<uint32_t> bgzf_tables() {
         for (int k = 0; k < 8; ++k) c = (c & 1u) ? (c >> 1) ^ 0xEDB88320u : c >> 1;
         t[i] = c;
     }
+    for (int s = 1; s < 4; ++s)  // slice-by-4: T_s[i] = T_{s-1}[i] advanced through one more zero byte
+        for (uint32_t i = 0; i < 256; ++i) t[256 * s + i] = (t[256 * (s - 1) + i] >> 8) ^ t[t[256 * (s - 1) + i] & 0xffu];
     for (int k = 0; k < 8; ++k)
-        for (int b = 0; b < 32; ++b) t[256 + 32 * k + b] = crc_zero_bytes(t.data(), 1u << b, 255ull << k);
+        for (int b = 0; b < 32; ++b) t[1024 + 32 * k + b] = crc_zero_bytes(t.data(), 1u << b, 256ull << k);
     return t;
 }
 

@@ -655,14 +655,14 @@ void launch_bam_write(const BamAsmArgs& A, cudaStream_t st, cudaStream_t st_meta
 // =================================================================================================== BGZF framing, level 0
 namespace {
 __global__ void __launch_bounds__(256) bgzf_store_kernel(BgzfArgs A) {
-    extern __shared__ __align__(16) uint8_t bgzf_smem[];
+    extern __shared__ __align__(16) uint32_t bgzf_smem[];
     bgzf_store_block_body(A, blockIdx.x, threadIdx.x, bgzf_smem);
 }
 }  // namespace
 
 void launch_bgzf_store(const BgzfArgs& A, cudaStream_t st, uint64_t* launches) {
     if (!A.n_blocks) return;
-    const int smem = int(kBgzfIn + 48u + (kBgzfTableWords + 8u) * 4u);
+    const int smem = int(kBgzfSmemBytes);
     static bool configured = false;  // (one device per process)
     if (!configured) {
         cudaFuncSetAttribute(bgzf_store_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
