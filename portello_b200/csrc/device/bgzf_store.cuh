@@ -25,7 +25,9 @@ namespace ptl {
 
 constexpr uint32_t kBgzfIn = 0xff00u;             // payload bytes of a full block (htslib BGZF_BLOCK_SIZE)
 constexpr uint32_t kBgzfOverhead = 18u + 5u + 8u;  // gzip header + stored-block header + CRC32 + ISIZE
-constexpr uint32_t kBgzfTableWords = 4u * 256u + 8u * 32u;  // slice-by-4 CRC tables, then the shift matrices
+// slice-by-4 CRC tables [4][256]; nibble tables [6][8][16] of the zero-byte shifts by 128 B (the two chains of a thread)
+// and by 256 * 2^k B, k = 0..4 (the warp levels of the tree); bit matrices [3][32] for k = 5..7 (the block levels)
+constexpr uint32_t kBgzfNibble = 1024u, kBgzfMatrix = kBgzfNibble + 6u * 128u, kBgzfTableWords = kBgzfMatrix + 3u * 32u;
 constexpr uint32_t kBgzfEnd = kBgzfIn + 16u;       // the data ENDS at this (16-byte aligned) logical byte of the staging buffer
 // One padding word per 64 data words: the 256 CRC slices start 64 words apart, which would put all lanes of a warp on one
 // shared-memory bank; with the padding they are 65 words apart.
@@ -37,12 +39,19 @@ struct BgzfArgs {
     const uint8_t* in;       // the stream (device); readable 64 KB in front (never used as data) and 32 bytes behind
     uint64_t n;              // stream bytes
     uint8_t* out;            // n + 31 * n_blocks bytes
-    const uint32_t* tables;  // [4][256] CRC tables (slice-by-4), [8][32] shift matrices Z^(256 * 2^k bytes)
+    const uint32_t* tables;  // kBgzfTableWords words (layout above)
     uint32_t init_full;      // Z^0xff00(0xffffffff)
     uint32_t init_last;      // Z^(bytes of the last block)(0xffffffff)
     uint64_t n_blocks;
 };
 
+// Z^m(v) from eight 16-entry tables, one per nibble of v (the map is linear over GF(2))
+__device__ __forceinline__ uint32_t gf2_apply_nibbles(const uint32_t* __restrict__ t, uint32_t v) {
+    uint32_t r = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r ^= t[16 * j + ((v >> (4 * j)) & 15u)];
+    return r;
+}
 __device__ __forceinline__ uint32_t gf2_apply(const uint32_t* __restrict__ m, uint32_t v) {
     uint32_t r = 0;
 #pragma unroll
@@ -97,21 +106,30 @@ __device__ __forceinline__ void bgzf_store_block_body(const BgzfArgs& A, uint64_
         for (int i = 0; i < 23; ++i) dst[i] = h[i];
     }
     __syncthreads();
-    // ---- 2. zero-state CRC of this thread's 64 words (slice-by-4), slices counted back from the end of the data
+    // ---- 2. zero-state CRC of this thread's 64 words (slice-by-4), slices counted back from the end of the data; the two
+    //         halves of a slice run as two independent chains (the table lookups of one chain are a dependent sequence)
     const int32_t lw_end = int32_t(kBgzfEnd / 4u) - 64 * int32_t(255u - tid);
-    int32_t lw = max(lw_end - 64, int32_t(4u * c0));
-    uint32_t crc = 0;
-    for (; lw < lw_end; ++lw) {
+    const int32_t lw_min = int32_t(4u * c0);
+    uint32_t crc_a = 0, crc_b = 0;
+    auto step = [&](uint32_t crc, int32_t lw) {
+        if (lw < lw_min) return crc;  // (in front of the data: zero bytes on a zero state)
         crc ^= sm[bgzf_pw(uint32_t(lw))];
-        crc = tab[768u + (crc & 0xffu)] ^ tab[512u + ((crc >> 8) & 0xffu)] ^ tab[256u + ((crc >> 16) & 0xffu)] ^ tab[crc >> 24];
+        return tab[768u + (crc & 0xffu)] ^ tab[512u + ((crc >> 8) & 0xffu)] ^ tab[256u + ((crc >> 16) & 0xffu)] ^ tab[crc >> 24];
+    };
+    if (lw_end > lw_min) {
+#pragma unroll 4
+        for (int32_t i = 0; i < 32; ++i) {
+            crc_a = step(crc_a, lw_end - 64 + i);
+            crc_b = step(crc_b, lw_end - 32 + i);
+        }
     }
+    uint32_t crc = gf2_apply_nibbles(tab + kBgzfNibble, crc_a) ^ crc_b;
     // tree combine: after level k a thread with tid % 2^(k+1) == 0 holds the CRC of 2^(k+1) slices
-    const uint32_t* mat = tab + 1024;
     const uint32_t lane = tid & 31u;
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
         const uint32_t right = __shfl_down_sync(0xffffffffu, crc, 1u << k);
-        if ((lane & ((2u << k) - 1u)) == 0u) crc = gf2_apply(mat + 32 * k, crc) ^ right;
+        if ((lane & ((2u << k) - 1u)) == 0u) crc = gf2_apply_nibbles(tab + kBgzfNibble + 128 * (k + 1), crc) ^ right;
     }
     if (lane == 0) warp_crc[tid >> 5] = crc;
     __syncthreads();
@@ -120,7 +138,7 @@ __device__ __forceinline__ void bgzf_store_block_body(const BgzfArgs& A, uint64_
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             const uint32_t right = __shfl_down_sync(0xffffffffu, crc, 1u << k);
-            if ((tid & ((2u << k) - 1u)) == 0u) crc = gf2_apply(mat + 32 * (5 + k), crc) ^ right;
+            if ((tid & ((2u << k) - 1u)) == 0u) crc = gf2_apply(tab + kBgzfMatrix + 32 * k, crc) ^ right;
         }
         if (tid == 0) {  // ---- 3. footer: CRC32, ISIZE
             const uint32_t full = ((n == kBgzfIn) ? A.init_full : A.init_last) ^ crc ^ 0xffffffffu;

@@ -663,11 +663,7 @@ __global__ void __launch_bounds__(256) bgzf_store_kernel(BgzfArgs A) {
 void launch_bgzf_store(const BgzfArgs& A, cudaStream_t st, uint64_t* launches) {
     if (!A.n_blocks) return;
     const int smem = int(kBgzfSmemBytes);
-    static bool configured = false;  // (one device per process)
-    if (!configured) {
-        cudaFuncSetAttribute(bgzf_store_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        configured = true;
-    }
+    cudaFuncSetAttribute(bgzf_store_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     bgzf_store_kernel<<<unsigned(A.n_blocks), 256, smem, st>>>(A);
     ++*launches;
 }
