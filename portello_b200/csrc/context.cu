@@ -791,16 +791,14 @@ static std::vector<uint32_t> bgzf_tables() {
         for (int k = 0; k < 8; ++k) c = (c & 1u) ? (c >> 1) ^ 0xEDB88320u : c >> 1;
         t[i] = c;
     }
-    for (int s = 1; s < 4; ++s)  // slice-by-4: T_s[i] = T_{s-1}[i] advanced through one more zero byte
-        for (uint32_t i = 0; i < 256; ++i) t[256 * s + i] = (t[256 * (s - 1) + i] >> 8) ^ t[t[256 * (s - 1) + i] & 0xffu];
-    // nibble tables of the shifts by 128 B and by 256 * 2^k B (k = 0..4); bit matrices for k = 5..7
-    for (int lvl = 0; lvl < 6; ++lvl) {
+    // nibble tables of the zero-byte shifts by 128 B and by 256 * 2^k B (k = 0..7), then of the 4-byte word step
+    for (int lvl = 0; lvl < 9; ++lvl) {
         const uint64_t m = lvl == 0 ? 128ull : (256ull << (lvl - 1));
         for (int j = 0; j < 8; ++j)
-            for (uint32_t x = 0; x < 16; ++x) t[kBgzfNibble + 128 * lvl + 16 * j + x] = crc_zero_bytes(t.data(), x << (4 * j), m);
+            for (uint32_t x = 0; x < 16; ++x) t[kBgzfShift + 128 * lvl + 16 * j + x] = crc_zero_bytes(t.data(), x << (4 * j), m);
     }
-    for (int k = 5; k < 8; ++k)
-        for (int b = 0; b < 32; ++b) t[kBgzfMatrix + 32 * (k - 5) + b] = crc_zero_bytes(t.data(), 1u << b, 256ull << k);
+    for (int j = 0; j < 8; ++j)
+        for (uint32_t x = 0; x < 16; ++x) t[kBgzfWord + 16 * j + x] = crc_zero_bytes(t.data(), x << (4 * j), 4);
     return t;
 }
 

@@ -654,7 +654,7 @@ void launch_bam_write(const BamAsmArgs& A, cudaStream_t st, cudaStream_t st_meta
 
 // =================================================================================================== BGZF framing, level 0
 namespace {
-__global__ void __launch_bounds__(256) bgzf_store_kernel(BgzfArgs A) {
+__global__ void __launch_bounds__(256, 4) bgzf_store_kernel(BgzfArgs A) {
     extern __shared__ __align__(16) uint32_t bgzf_smem[];
     bgzf_store_block_body(A, blockIdx.x, threadIdx.x, bgzf_smem);
 }
@@ -662,7 +662,7 @@ __global__ void __launch_bounds__(256) bgzf_store_kernel(BgzfArgs A) {
 
 void launch_bgzf_store(const BgzfArgs& A, cudaStream_t st, uint64_t* launches) {
     if (!A.n_blocks) return;
-    const int smem = int(kBgzfSmemBytes);
+    const int smem = int(kBgzfSmemWords * 4u);
     cudaFuncSetAttribute(bgzf_store_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     bgzf_store_kernel<<<unsigned(A.n_blocks), 256, smem, st>>>(A);
     ++*launches;
