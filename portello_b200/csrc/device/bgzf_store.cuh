@@ -55,6 +55,14 @@ __device__ __forceinline__ uint32_t gf2_apply_nibbles(const uint32_t* __restrict
 }
 
 // blockDim.x == 256; kBgzfSmemWords words of dynamic shared memory
+// the tables into shared memory (once per resident thread block: the kernel is persistent, 22 KB of table stores per
+// 64 KB block of payload were 35 % of its stall samples)
+__device__ __forceinline__ void bgzf_store_init(const BgzfArgs& A, uint32_t tid, uint32_t* sm) {
+    uint32_t* wl = sm + 256 + 9 * 128;
+    for (uint32_t i = tid; i < kBgzfWord; i += 256u) sm[i] = A.tables[i];
+    for (uint32_t i = tid; i < 128u * 32u; i += 256u) wl[i] = A.tables[kBgzfWord + (i >> 5)];
+    __syncthreads();
+}
 __device__ __forceinline__ void bgzf_store_block_body(const BgzfArgs& A, uint64_t b, uint32_t tid, uint32_t* sm) {
     uint32_t* t0 = sm;
     uint32_t* shift = sm + 256;
@@ -66,15 +74,12 @@ __device__ __forceinline__ void bgzf_store_block_body(const BgzfArgs& A, uint64_
     uint8_t* dst = A.out + b * uint64_t(kBgzfIn + kBgzfOverhead);
     uint8_t* data_dst = dst + 23;
     const uint8_t* src = A.in + in_off;
-    for (uint32_t i = tid; i < kBgzfWord; i += 256u) sm[i] = A.tables[i];
-    for (uint32_t i = tid; i < 128u * 32u; i += 256u) wl[i] = A.tables[kBgzfWord + (i >> 5)];
     if (tid == 0) {  // gzip header + the stored-block header (unaligned destination: byte stores)
         const uint32_t bsize1 = n + kBgzfOverhead - 1u;
         const uint8_t h[23] = {0x1f, 0x8b, 0x08, 0x04, 0, 0, 0, 0, 0, 0xff, 0x06, 0, 0x42, 0x43, 0x02, 0, uint8_t(bsize1 & 0xffu), uint8_t(bsize1 >> 8),
                                0x01, uint8_t(n & 0xffu), uint8_t(n >> 8), uint8_t(~n & 0xffu), uint8_t((~n >> 8) & 0xffu)};
         for (int i = 0; i < 23; ++i) dst[i] = h[i];
     }
-    __syncthreads();
     // ---- zero-state CRC of this thread's 256-byte slice, slices counted back from the end of the data; its two halves run
     //      as two independent chains; every thread reads its slice straight from global memory (16 bytes per step: five
     //      aligned words + funnel shifts; a sector is used by two consecutive steps of the same thread)
@@ -147,6 +152,7 @@ __device__ __forceinline__ void bgzf_store_block_body(const BgzfArgs& A, uint64_
     }
     // ---- the payload itself: the record copy of assemble_bam.cuh (aligned 16-byte stores, funnel-shifted source)
     copy_field(data_dst, src, n, tid, 256u);
+    __syncthreads();  // (warp_crc is reused by the next block of this persistent thread block)
 }
 
 }  // namespace ptl

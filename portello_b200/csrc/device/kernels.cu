@@ -656,7 +656,8 @@ void launch_bam_write(const BamAsmArgs& A, cudaStream_t st, cudaStream_t st_meta
 namespace {
 __global__ void __launch_bounds__(256, 4) bgzf_store_kernel(BgzfArgs A) {
     extern __shared__ __align__(16) uint32_t bgzf_smem[];
-    bgzf_store_block_body(A, blockIdx.x, threadIdx.x, bgzf_smem);
+    bgzf_store_init(A, threadIdx.x, bgzf_smem);
+    for (uint64_t b = blockIdx.x; b < A.n_blocks; b += gridDim.x) bgzf_store_block_body(A, b, threadIdx.x, bgzf_smem);
 }
 }  // namespace
 
@@ -664,7 +665,7 @@ void launch_bgzf_store(const BgzfArgs& A, cudaStream_t st, uint64_t* launches) {
     if (!A.n_blocks) return;
     const int smem = int(kBgzfSmemWords * 4u);
     cudaFuncSetAttribute(bgzf_store_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    bgzf_store_kernel<<<unsigned(A.n_blocks), 256, smem, st>>>(A);
+    bgzf_store_kernel<<<unsigned(std::min<uint64_t>(A.n_blocks, 148ull * 4)), 256, smem, st>>>(A);  // persistent: 4 thread blocks per SM
     ++*launches;
 }
 
