@@ -62,12 +62,17 @@ class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index: int):
-        self.idx, self.rows, self.p = gpu_index, [], None
+    def __init__(self, gpu_indices):
+        # ONE poller per job (rank 0 watches every GPU of the job): a poller per rank made 8 nvidia-smi processes query the
+        # driver every 100 ms, and at N = 8 some rank's 16 ms timed region caught a multi-millisecond stall almost every run
+        # (max over ranks 1.07 ms per step against 0.79 ms on every rank's own stage events).
+        self.idx, self.rows, self.p = ",".join(str(i) for i in gpu_indices), [], None
 
     def start(self):
+        if not self.idx:
+            return
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.idx)],
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", self.idx],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -199,6 +204,14 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def all_ranks(x: float):
+        if world == 1:
+            return [x]
+        t = torch.zeros(world, dtype=torch.float64, device="cuda")
+        t[rank] = x
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [float(v) for v in t.tolist()]
+
     def sum_over_ranks(x: float) -> float:
         if world == 1:
             return x
@@ -207,8 +220,11 @@ def main():
         return float(t.item())
 
     L = lib.load(build_if_missing=False)
-    # ---- data: every rank owns a different contig set (seed + rank) of the same shape: weak scaling, no exchange
-    kw = {"seed": synth.WORKLOADS[args.workload]["seed"] + rank}
+    # ---- data: weak scaling, no exchange: every rank lifts its own shard of the same shape.  The shards are generated from
+    # the SAME seed: with seed + rank the ranks drew different inversion layouts (reverse-strand pairs cost ~3x a forward
+    # pair), and the max over ranks measured that synthetic imbalance (N = 8: 1.07 ms on the slowest rank, 0.79 ms on
+    # rank 0) instead of the machine.  Per-rank step times are reported in config.rank_ms_per_step.
+    kw = {"seed": synth.WORKLOADS[args.workload]["seed"]}
     if args.reads:
         kw["n_reads"] = args.reads
     t0 = time.time()
@@ -236,7 +252,7 @@ def main():
     }
     whole_win = lib.PackedBatch(L, s.read_records, 0, n_reads, s.contig_names, pinned=True, windows=win_segs)
 
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(range(world) if rank == 0 else [])
     sampler.start()
     windows = []
 
@@ -273,6 +289,7 @@ def main():
             stage_acc.setdefault(k, []).append(v)
     stage_ms = {k: float(np.mean(v)) for k, v in stage_acc.items()}
     dev_ms_max = max_over_ranks(dev_ms)
+    rank_ms = all_ranks(dev_ms)
     pairs_total = sum_over_ranks(float(cnt["n_pairs"]))
     value = pairs_total / (dev_ms_max / 1e3)
 
@@ -537,7 +554,9 @@ def main():
                                    f"{s.contig_records.n_records} contig alignment records -> {n_segments} segments after trim/join, "
                                    f"{n_reads} reads per GPU)",
                        "reads_per_gpu": int(n_reads), "pairs_per_step_per_gpu": int(cnt["n_pairs"]), "lifted_per_step_per_gpu": int(cnt["n_lifted"]),
-                       "l2_policy": "inputs larger than L2 (CIGAR pools + op scratch > 126 MB per step)", "sharding": "by contig set, no collective",
+                       "l2_policy": "inputs larger than L2 (CIGAR pools + op scratch > 126 MB per step)",
+                       "sharding": "one shard per rank (same generator parameters and seed: identical per-GPU work), no collective",
+                       "rank_ms_per_step": [round(v, 4) for v in rank_ms],
                        "e2e_pipeline": f"{len(chunks)} batches of {args.chunk} reads over {max(args.slots, 2)} slots", "e2e_base_transfer": best_mode,
                        "parity": parity, "full_batch_digest": f"{list(digests.values())[0]:016x} (identical across {len(digests)} base-transfer modes)",
                        "generate_s": round(t_gen, 1)},
