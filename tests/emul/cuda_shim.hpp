@@ -12,9 +12,21 @@
 #define __forceinline__ inline
 #define __restrict__
 #define __launch_bounds__(...)
+#define __noinline__
 
 struct uint2 { uint32_t x, y; };
 inline uint2 make_uint2(uint32_t x, uint32_t y) { return uint2{x, y}; }
+
+struct uint4 { uint32_t x, y, z, w; };  // (no alignment attribute: the host may store it to any address)
+inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
+inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t sh) { return uint32_t(((uint64_t(hi) << 32) | lo) >> (sh & 31u)); }
+inline uint32_t __brev(uint32_t v) { uint32_t r = 0; for (int i = 0; i < 32; ++i) r |= ((v >> i) & 1u) << (31 - i); return r; }
+inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t s) {
+    const uint64_t v = (uint64_t(y) << 32) | x;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; ++i) r |= uint32_t((v >> (8 * ((s >> (4 * i)) & 7u))) & 0xffu) << (8 * i);
+    return r;
+}
 
 using std::max;
 using std::min;

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../portello_b200/csrc/device/pair_bodies.cuh"
+#include "../../portello_b200/csrc/device/assemble_bam.cuh"
 #include "emul_prep.hpp"
 
 using namespace ptl;
@@ -40,6 +41,10 @@ struct EmulSlot {
     ptl_result res{};
     DevTotals totals{};
     bool ran = false;
+    // ptl_emul_assemble_records
+    std::vector<uint32_t> rseg_read;
+    std::vector<uint64_t> bam_begin;
+    std::vector<uint8_t> bam_out;
 };
 
 }  // namespace
@@ -58,6 +63,9 @@ struct ptl_ctx {
     std::vector<TabEntry> table;
     DevStatic S;
     bool have_reference = false, have_segments = false;
+    std::vector<uint64_t> contig_name_off{0}, chrom_name_off{0};
+    std::vector<uint8_t> contig_names, chrom_names;
+    bool have_names = false;
 };
 
 namespace {
@@ -261,6 +269,7 @@ int run_batch(ptl_ctx* ctx, EmulSlot& sl, const ptl_batch* b, uint32_t stage_mas
         res.first_error_read = -1;
         res.first_error_status = 0;
     }
+    sl.rseg_read = rseg_read;
     sl.ran = true;
     return PTL_OK;
 }
@@ -361,6 +370,89 @@ int ptl_emul_slot_counters(ptl_ctx* ctx, int slot, uint64_t* out) {
     if (!sl || !out || !sl->ran) return PTL_ERR_INVALID_ARG;
     const DevTotals& t = sl->totals;
     out[0] = t.n_pairs; out[1] = t.n_lifted; out[2] = t.n_in_ops; out[3] = t.n_cigar_out; out[4] = t.n_base_bytes; out[5] = t.scratch_needed;
+    return PTL_OK;
+}
+
+// Record assembly through the device bodies of assemble_bam.cuh (every "thread" of a block runs in turn: the bodies need no
+// cooperation between threads), byte for byte what ptl_assemble_records launches.
+int ptl_emul_set_names(ptl_ctx* ctx, uint32_t n_contigs, const char* const* contig_names, uint32_t n_chrom, const char* const* chrom_names) {
+    if (!ctx || (n_contigs && !contig_names) || (n_chrom && !chrom_names)) return PTL_ERR_INVALID_ARG;
+    auto pool = [](uint32_t n, const char* const* names, std::vector<uint64_t>& off, std::vector<uint8_t>& bytes) {
+        off.assign(1, 0);
+        bytes.clear();
+        for (uint32_t i = 0; i < n; ++i) {
+            bytes.insert(bytes.end(), names[i], names[i] + std::strlen(names[i]));
+            off.push_back(bytes.size());
+        }
+        bytes.resize(bytes.size() + 16, 0);
+    };
+    pool(n_contigs, contig_names, ctx->contig_name_off, ctx->contig_names);
+    pool(n_chrom, chrom_names, ctx->chrom_name_off, ctx->chrom_names);
+    ctx->have_names = true;
+    return PTL_OK;
+}
+int ptl_emul_assemble_records(ptl_ctx* ctx, int slot, const ptl_read_extras* x, uint32_t /*flags*/, ptl_bam_records* out) {
+    EmulSlot* sl = get_slot(ctx, slot);
+    if (!sl || !x || !out) return PTL_ERR_INVALID_ARG;
+    if (!sl->ran) return fail(ctx, PTL_ERR_STATE, "assemble without a lifted batch");
+    if (!ctx->have_names) return fail(ctx, PTL_ERR_STATE, "ptl_set_names has not been called");
+    const uint32_t n = sl->res.n_reads, n_rec = sl->res.n_records;
+    constexpr size_t kPad = 64;  // the copy loops read a few bytes around a field (inside the device pools)
+    auto padded = [&](const uint8_t* p, size_t bytes) {
+        std::vector<uint8_t> v(bytes + 2 * kPad, 0);
+        if (bytes) std::memcpy(v.data() + kPad, p, bytes);
+        return v;
+    };
+    const std::vector<uint8_t> names = padded(x->names, n ? x->name_off[n] : 0), aux = padded(x->aux, n ? x->aux_off[n] : 0),
+                               qual = padded(x->quals.qual, x->quals.qual_bytes), seq4 = padded(sl->seq4.data(), sl->seq4.size());
+    const std::vector<uint8_t> cig = padded(reinterpret_cast<const uint8_t*>(sl->res.cigar), size_t(sl->res.n_cigar) * 4);
+    std::vector<uint32_t> keep(size_t(n) * 10 + 10), sa_len(n_rec + 1);
+    std::vector<uint4> desc(size_t(n_rec) * 2 + 2);
+    sl->bam_begin.assign(size_t(n_rec) + 1, 0);
+    unsigned int err = 0;
+    BamAsmArgs A{};
+    A.n_reads = n; A.n_records = n_rec;
+    A.seg_is_fwd = ctx->S.seg_is_fwd; A.contig_seg_begin = ctx->S.contig_seg_begin;
+    A.contig_name_off = ctx->contig_name_off.data(); A.contig_names = ctx->contig_names.data(); A.n_contig_names = uint32_t(ctx->contig_name_off.size() - 1);
+    A.chrom_name_off = ctx->chrom_name_off.data(); A.chrom_names = ctx->chrom_names.data(); A.n_chrom_names = uint32_t(ctx->chrom_name_off.size() - 1);
+    A.read_mapq = sl->read_mapq.data(); A.read_seq_len = sl->read_seq_len.data(); A.read_seq_off = sl->read_seq_off.data();
+    A.seq4 = seq4.data() + kPad; A.rseg_contig = sl->rseg_contig.data(); A.rseg_read = sl->rseg_read.data();
+    A.name_off = x->name_off; A.names = names.data() + kPad; A.aux_off = x->aux_off; A.aux = aux.data() + kPad;
+    A.mate_tid = x->mate_tid; A.mate_pos = x->mate_pos; A.tlen = x->tlen; A.qual_off = x->quals.read_qual_off; A.qual = qual.data() + kPad;
+    A.read_rec_begin = sl->res.read_rec_begin; A.rec_status = sl->res.rec_status; A.rec_read_segment = sl->res.rec_read_segment;
+    A.rec_contig_segment = sl->res.rec_contig_segment; A.rec_tid = sl->res.rec_tid; A.rec_pos = sl->res.rec_pos; A.rec_mapq = sl->res.rec_mapq;
+    A.rec_flag = sl->res.rec_flag; A.rec_bin = sl->res.rec_bin; A.rec_need_flip = sl->res.rec_need_flip; A.rec_cigar_begin = sl->res.rec_cigar_begin;
+    A.cigar = reinterpret_cast<const uint32_t*>(cig.data() + kPad);
+    A.read_keep = keep.data(); A.rec_sa_len = sa_len.data(); A.rec_begin = sl->bam_begin.data(); A.rec_desc = desc.data(); A.error = &err;
+    for (uint32_t r = 0; r < n; ++r) bam_read_prep_body(A, r);
+    for (uint32_t k = 0; k < n_rec; ++k) bam_rec_prep_body(A, k);
+    uint64_t run = 0;
+    for (uint32_t k = 0; k < n_rec; ++k) {  // bam_rec_size_kernel + the exclusive scan
+        const BamRecLayout L = bam_rec_layout(A, k);
+        if (L.ps_n > 0xffu || L.sa_n > 0xffffffu) err |= 4u;
+        L.pack(desc.data() + 2 * size_t(k));
+        sl->bam_begin[k] = run;
+        run += L.total;
+    }
+    sl->bam_begin[n_rec] = run;
+    if (err & 1u) return fail(ctx, PTL_ERR_INVALID_ARG, "ptl_set_names: a contig or reference chromosome of this batch has no name");
+    if (err & 2u) return fail(ctx, PTL_ERR_INVALID_ARG, "a lifted CIGAR has more than 65535 ops");
+    if (err & 4u) return fail(ctx, PTL_ERR_INVALID_ARG, "descriptor field overflow");
+    sl->bam_out.assign(run + 2 * kPad, 0x5a);
+    // (the device pool is 256-byte aligned: keep the same alignment so that the 16-byte chunking takes the same paths)
+    uint8_t* base = sl->bam_out.data();
+    base += (256 - (reinterpret_cast<uintptr_t>(base) & 255u)) & 255u;
+    if (size_t(base - sl->bam_out.data()) + run > sl->bam_out.size()) { sl->bam_out.resize(run + 512, 0x5a); base = sl->bam_out.data(); base += (256 - (reinterpret_cast<uintptr_t>(base) & 255u)) & 255u; }
+    A.out = base;
+    for (uint32_t k = 0; k < n_rec; ++k) {
+        for (uint32_t tid = 0; tid < 32; ++tid) bam_write_meta_body(A, k, tid, 32);
+        for (uint32_t tid = 0; tid < 256; ++tid) bam_write_bases_body(A, k, tid, 256);
+    }
+    *out = ptl_bam_records{};
+    out->n_records = n_rec;
+    out->rec_begin = sl->bam_begin.data();
+    out->bytes = base;
+    out->bytes_written = run;
     return PTL_OK;
 }
 

@@ -332,3 +332,33 @@ def test_oracle_rejects_cigars_beyond_u16():
 def test_gpu_rejects_cigars_beyond_u16():
     from portello_b200 import lib
     _check_long_cigar_rejected(lib.GpuContext(0, 1))
+
+
+@pytest.mark.parametrize("case", ["iupac-odd", "tiny"])
+def test_emulated_record_kernels_match_oracle(case):
+    """The device bodies of assemble_bam.cuh compiled for the host (tests/emul, one 'thread' at a time) against the oracle:
+    the aux walk, record sizes, tag text, destination-aligned chunking and the flipped paths, without a GPU."""
+    import emul_lib
+    E = emul_lib.load()
+    if case == "iupac-odd":
+        s, pb = iupac_case(5, n_reads=250)
+    else:
+        s = synth.make("tiny", seed=8, n_reads=500)
+        pb = helpers.pack(s)
+    ectx = abi.Context(E, 0, 1)
+    ectx.set_reference(helpers.reference_arrays(s))
+    ectx.set_contig_records(s.contig_records)
+    octx = helpers.oracle_context(s)
+    re_ = helpers.lift_c(ectx, pb.c, allow_panic=True)
+    ro = helpers.lift_c(octx, pb.c, allow_panic=True)
+    assert re_.diff(ro) is None
+    x, _, _ = make_extras(s, pb, 2)
+    for c in (ectx, octx):
+        c.set_names(s.contig_names, s.chrom_names)
+    _, (rbo, byo) = octx.assemble_records(x)
+    _, (rbe, bye) = ectx.assemble_records(x)
+    assert np.array_equal(rbo, rbe)
+    if not np.array_equal(byo, bye):
+        i = int(np.flatnonzero(byo != bye)[0])
+        k = int(np.searchsorted(rbo, i, side="right") - 1)
+        raise AssertionError(f"record {k} differs at byte {i - int(rbo[k])} of {int(rbo[k + 1] - rbo[k])}")
