@@ -574,6 +574,7 @@ int ptl_oracle_assemble_records(ptl_ctx* ctx, int slot, const ptl_read_extras* x
         const uint8_t* q = x->quals.qual + x->quals.read_qual_off[r];
         const uint8_t* name = x->names + x->name_off[r];
         const size_t name_n = size_t(x->name_off[r + 1] - x->name_off[r]);
+        if (name_n > 254) return fail(ctx, PTL_ERR_STATE, "a read name longer than 254 bytes (BAM l_read_name is a u8)");
         for (uint32_t k = k0; k < k1; ++k) {
             const bool lifted = sl.rec_status[k] == 1;
             std::vector<uint8_t> a = kept;

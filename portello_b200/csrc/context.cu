@@ -969,6 +969,7 @@ int ptl_assemble_records(ptl_ctx* ctx, int slot, const ptl_read_extras* x, uint3
         if (err & 1u) throw std::runtime_error("ptl_set_names: a contig or reference chromosome of this batch has no name");
         if (err & 2u) throw std::runtime_error("a lifted CIGAR has more than 65535 ops (BAM needs a CG tag for it: out of scope)");
         if (err & 4u) throw std::runtime_error("a contig name longer than 248 bytes or more than 16 MB of SA text in one record");
+        if (err & 8u) throw std::runtime_error("a read name longer than 254 bytes (BAM l_read_name is a u8)");
         const uint64_t total = sl->hb_rec_begin.as<uint64_t>()[n_rec];
         sl->b_out.ensure(kBamFront + total + 64, st);  // (headroom in front: ptl_bgzf_store_records puts its prefix there)
         A.out = sl->b_out.as<uint8_t>() + kBamFront;

@@ -70,7 +70,7 @@ struct BamAsmArgs {
     uint4* rec_desc;         // [n_records][2] BamRecLayout of the record, computed once by bam_rec_size (the writer's prologue
                              //                is then two dependent loads deep instead of five)
     uint8_t* out;
-    unsigned int* error;     // bit 0: a name is missing, bit 1: a CIGAR has more than 65535 ops
+    unsigned int* error;     // bit 0: a name is missing, 1: a CIGAR has more than 65535 ops, 2: descriptor field overflow, 3: qname > 254 bytes
 };
 
 __device__ __forceinline__ uint32_t dec_digits(uint64_t v) {
@@ -386,7 +386,7 @@ __device__ __forceinline__ void bam_write_meta_body(const BamAsmArgs& A, uint32_
         const uint32_t h[9] = {uint32_t(L.total - 4),
                                uint32_t(A.rec_tid[k]),
                                uint32_t(int32_t(A.rec_pos[k])),
-                               (L.name_n + 1u) | (uint32_t(A.rec_mapq[k]) << 8) | (uint32_t(A.rec_bin[k]) << 16),
+                               ((L.name_n + 1u) & 0xffu) | (uint32_t(A.rec_mapq[k]) << 8) | (uint32_t(A.rec_bin[k]) << 16),
                                L.n_cigar | (uint32_t(A.rec_flag[k]) << 16),
                                L.l_seq,
                                uint32_t(A.mate_tid[r]),

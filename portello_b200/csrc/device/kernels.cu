@@ -625,6 +625,7 @@ __global__ void __launch_bounds__(128) bam_rec_size_kernel(BamAsmArgs A) {
     if (k == A.n_records) { A.rec_begin[k] = 0ull; return; }
     const BamRecLayout L = bam_rec_layout(A, k);
     if (L.ps_n > 0xffu || L.sa_n > 0xffffffu) atomicOr(A.error, 4u);  // (descriptor field widths: a 255-byte contig name, 16 MB of SA text)
+    if (L.name_n > 254u) atomicOr(A.error, 8u);                        // (l_read_name is a u8 that counts the NUL)
     L.pack(A.rec_desc + 2 * size_t(k));
     A.rec_begin[k] = L.total;
 }

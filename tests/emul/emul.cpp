@@ -430,6 +430,7 @@ int ptl_emul_assemble_records(ptl_ctx* ctx, int slot, const ptl_read_extras* x, 
     for (uint32_t k = 0; k < n_rec; ++k) {  // bam_rec_size_kernel + the exclusive scan
         const BamRecLayout L = bam_rec_layout(A, k);
         if (L.ps_n > 0xffu || L.sa_n > 0xffffffu) err |= 4u;
+        if (L.name_n > 254u) err |= 8u;
         L.pack(desc.data() + 2 * size_t(k));
         sl->bam_begin[k] = run;
         run += L.total;
@@ -438,6 +439,7 @@ int ptl_emul_assemble_records(ptl_ctx* ctx, int slot, const ptl_read_extras* x, 
     if (err & 1u) return fail(ctx, PTL_ERR_INVALID_ARG, "ptl_set_names: a contig or reference chromosome of this batch has no name");
     if (err & 2u) return fail(ctx, PTL_ERR_INVALID_ARG, "a lifted CIGAR has more than 65535 ops");
     if (err & 4u) return fail(ctx, PTL_ERR_INVALID_ARG, "descriptor field overflow");
+    if (err & 8u) return fail(ctx, PTL_ERR_INVALID_ARG, "a read name longer than 254 bytes");
     sl->bam_out.assign(run + 2 * kPad, 0x5a);
     // (the device pool is 256-byte aligned: keep the same alignment so that the 16-byte chunking takes the same paths)
     uint8_t* base = sl->bam_out.data();

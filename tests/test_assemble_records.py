@@ -362,3 +362,32 @@ def test_emulated_record_kernels_match_oracle(case):
         i = int(np.flatnonzero(byo != bye)[0])
         k = int(np.searchsorted(rbo, i, side="right") - 1)
         raise AssertionError(f"record {k} differs at byte {i - int(rbo[k])} of {int(rbo[k + 1] - rbo[k])}")
+
+
+def _long_name_rejected(ctx, s, pb):
+    helpers.lift_c(ctx, pb.c)
+    x, _, _ = make_extras(s, pb, 1)
+    n = pb.c.n_reads
+    x["name_off"] = np.arange(n + 1, dtype=np.uint64) * np.uint64(300)       # 300-byte qnames: l_read_name is a u8
+    x["names"] = np.full(300 * n + 16, ord("q"), np.uint8)
+    ctx.set_names(s.contig_names, s.chrom_names)
+    with pytest.raises(abi.PtlError, match="254"):
+        ctx.assemble_records(x)
+
+
+def test_read_names_beyond_u8_are_rejected():
+    import emul_lib
+    s = synth.make("tiny", seed=3, n_reads=20)
+    pb = helpers.pack(s)
+    _long_name_rejected(helpers.oracle_context(s), s, pb)
+    ectx = abi.Context(emul_lib.load(), 0, 1)
+    ectx.set_reference(helpers.reference_arrays(s))
+    ectx.set_contig_records(s.contig_records)
+    _long_name_rejected(ectx, s, pb)
+
+
+@pytest.mark.gpu
+def test_gpu_read_names_beyond_u8_are_rejected():
+    s = synth.make("tiny", seed=3, n_reads=20)
+    pb = helpers.pack(s)
+    _long_name_rejected(helpers.gpu_context(s), s, pb)
