@@ -19,6 +19,7 @@
 #include "device/assemble.cuh"
 #include "device/assemble_bam.cuh"
 #include "device/bgzf_store.cuh"
+#include "host/bgzf_tables.hpp"
 #include "device/kernels.hpp"
 #include "host/contig_prep.hpp"
 
@@ -778,29 +779,6 @@ int ptl_assemble_bases(ptl_ctx* ctx, int slot, const ptl_read_quals* quals, uint
 }
 // Records are assembled kBamFront bytes into their buffer, so that a stream prefix (the BAM header) can sit right in front.
 constexpr uint64_t kBamFront = 1ull << 16;
-
-// CRC-32 (IEEE 802.3, reflected) table and the GF(2) matrices of "advance the state through 255 * 2^k zero bytes"
-static uint32_t crc_zero_bytes(const uint32_t* t, uint32_t v, uint64_t n) {
-    for (uint64_t i = 0; i < n; ++i) v = t[v & 0xffu] ^ (v >> 8);
-    return v;
-}
-static std::vector<uint32_t> bgzf_tables() {
-    std::vector<uint32_t> t(kBgzfTableWords);
-    for (uint32_t i = 0; i < 256; ++i) {
-        uint32_t c = i;
-        for (int k = 0; k < 8; ++k) c = (c & 1u) ? (c >> 1) ^ 0xEDB88320u : c >> 1;
-        t[i] = c;
-    }
-    // nibble tables of the zero-byte shifts by 128 B and by 256 * 2^k B (k = 0..7), then of the 4-byte word step
-    for (int lvl = 0; lvl < 9; ++lvl) {
-        const uint64_t m = lvl == 0 ? 128ull : (256ull << (lvl - 1));
-        for (int j = 0; j < 8; ++j)
-            for (uint32_t x = 0; x < 16; ++x) t[kBgzfShift + 128 * lvl + 16 * j + x] = crc_zero_bytes(t.data(), x << (4 * j), m);
-    }
-    for (int j = 0; j < 8; ++j)
-        for (uint32_t x = 0; x < 16; ++x) t[kBgzfWord + 16 * j + x] = crc_zero_bytes(t.data(), x << (4 * j), 4);
-    return t;
-}
 
 // BGZF framing on the device, level 0: see include/portello_b200.h.
 int ptl_bgzf_store_records(ptl_ctx* ctx, int slot, const uint8_t* prefix, uint64_t prefix_bytes, uint32_t flags, ptl_bgzf_stream* out) {

@@ -15,9 +15,21 @@
 #define __forceinline__ inline
 #define __restrict__
 #define __launch_bounds__(...)
+#define __noinline__
 
 struct uint2 { uint32_t x, y; };
 inline uint2 make_uint2(uint32_t x, uint32_t y) { return uint2{x, y}; }
+
+struct uint4 { uint32_t x, y, z, w; };  // (no alignment attribute: the host may store it to any address)
+inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
+inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t sh) { return uint32_t(((uint64_t(hi) << 32) | lo) >> (sh & 31u)); }
+inline uint32_t __brev(uint32_t v) { uint32_t r = 0; for (int i = 0; i < 32; ++i) r |= ((v >> i) & 1u) << (31 - i); return r; }
+inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t s) {
+    const uint64_t v = (uint64_t(y) << 32) | x;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; ++i) r |= uint32_t((v >> (8 * ((s >> (4 * i)) & 7u))) & 0xffu) << (8 * i);
+    return r;
+}
 
 using std::max;
 using std::min;
@@ -30,6 +42,7 @@ struct Warp {
 inline thread_local Warp* tl_warp = nullptr;
 inline thread_local uint32_t tl_lane = 0;
 inline thread_local uint32_t tl_parity = 0;
+inline thread_local std::barrier<>* tl_block = nullptr;  // __syncthreads of a multi-warp block (emul_bgzf.cpp)
 
 // deposit `v`, wait for all lanes, return the whole slot array of this collective
 inline const uint64_t* exchange(uint64_t v) {
@@ -64,6 +77,7 @@ inline unsigned __ballot_sync(unsigned, bool pred) {
 }
 inline bool __any_sync(unsigned mask, bool pred) { return __ballot_sync(mask, pred) != 0u; }
 inline void __syncwarp() { warp_emul::exchange(0); }
+inline void __syncthreads() { warp_emul::tl_block->arrive_and_wait(); }
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __clz(unsigned v) { return v ? __builtin_clz(v) : 32; }
 inline int __ffs(unsigned v) { return __builtin_ffs(int(v)); }
@@ -79,5 +93,6 @@ template <class T> inline void ptl_assert_uniform(T v, const char* what, int lin
 #define PTL_ASSERT_UNIFORM(v) ptl_assert_uniform((v), #v, __LINE__)
 
 // only lane 0 of a warp calls these, and the emulation runs one warp at a time
+inline unsigned int atomicOr(unsigned int* p, unsigned int v) { const unsigned int o = *p; *p |= v; return o; }
 inline unsigned int atomicAdd(unsigned int* p, unsigned int v) { const unsigned int o = *p; *p += v; return o; }
 inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { const unsigned long long o = *p; *p += v; return o; }

@@ -169,3 +169,24 @@ def test_bgzf_level0_model_is_valid_gzip():
     data = bytes(np.random.default_rng(3).integers(0, 256, 200_001, dtype=np.uint8))
     assert gzip.decompress(bgzf_level0_model(data, True)) == data
     assert [len(p) for _, _, p in blocks(bgzf_level0_model(data, True))] == [0xff00, 0xff00, 0xff00, 200_001 - 3 * 0xff00, 0]
+
+
+@pytest.mark.parametrize("n,misalign", [(1, 0), (100, 3), (0xff00 - 1, 0), (0xff00, 0), (0xff00, 5), (0xff00 + 1, 16), (200_001, 0), (200_001, 7)])
+def test_emulated_bgzf_kernel_matches_model(n, misalign):
+    """bgzf_store_kernel (slice CRCs through per-lane nibble tables, GF(2) shift-table combine tree, destination-aligned copy)
+    run by 256 host threads in lock step (tests/emul), against the Python model and python's gzip: CPU coverage of the CRC
+    arithmetic; `misalign` moves the stream off its 16-byte alignment (the funnel-shift load path)."""
+    import emul_lib
+    E = emul_lib.load().dll
+    E.ptl_emul_bgzf_store.restype = C.c_int64
+    E.ptl_emul_bgzf_store.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.c_void_p, C.c_uint64]
+    rng = np.random.default_rng(n + misalign)
+    buf = np.zeros(n + 64, np.uint8)
+    off = (16 - buf.ctypes.data % 16) % 16 + misalign
+    data = rng.integers(0, 256, n, dtype=np.uint8)
+    buf[off: off + n] = data
+    out = np.zeros(n + 31 * ((n + 0xff00 - 1) // 0xff00) + 28 + 64, np.uint8)
+    got = E.ptl_emul_bgzf_store(buf.ctypes.data + off, n, 1, out.ctypes.data + 1, out.size - 1)  # (odd destination on purpose)
+    z = out[1: 1 + got].tobytes()
+    assert z == bgzf_level0_model(data.tobytes(), True)
+    assert gzip.decompress(z) == data.tobytes()
