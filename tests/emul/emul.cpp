@@ -16,6 +16,8 @@
 
 using namespace ptl;
 
+// emul_warp.cpp: table_build_kernel under the 32-lane lock-step shim
+void emul_table_build_warp(const ptl::DevStatic& S, uint32_t* counts, ptl::TabEntry* out);
 // emul_warp.cpp: lift_long_pairs_kernel under the 32-lane lock-step shim
 void emul_lift_long_pairs(const ptl::DevStatic& S, const ptl::DevBatch& B, const ptl::DevWork& W, ptl::DevTotals* T, uint32_t stage_mask);
 
@@ -371,6 +373,23 @@ int ptl_emul_slot_counters(ptl_ctx* ctx, int slot, uint64_t* out) {
     const DevTotals& t = sl->totals;
     out[0] = t.n_pairs; out[1] = t.n_lifted; out[2] = t.n_in_ops; out[3] = t.n_cigar_out; out[4] = t.n_base_bytes; out[5] = t.scratch_needed;
     return PTL_OK;
+}
+
+// The installed segment tables rebuilt by the warp-cooperative kernel body (32 lanes in lock step) and compared with the scalar
+// build: returns the number of differing words (counts and entries), 0 = identical.
+int64_t ptl_emul_table_build_warp_mismatches(ptl_ctx* ctx) {
+    if (!ctx || !ctx->have_segments) return -1;
+    const uint32_t ns = ctx->S.n_segments;
+    std::vector<uint32_t> counts(size_t(ns) + 1, 0);
+    emul_table_build_warp(ctx->S, counts.data(), nullptr);
+    int64_t bad = 0;
+    for (uint32_t g = 0; g < ns; ++g) bad += counts[g] != ctx->tab_begin[g + 1] - ctx->tab_begin[g];
+    if (bad) return bad;
+    std::vector<TabEntry> t(ctx->table.size(), TabEntry{0xdeadbeefu, 0, 0, 0});
+    emul_table_build_warp(ctx->S, nullptr, t.data());
+    for (uint32_t i = 0; i < ctx->tab_begin[ns]; ++i)
+        bad += t[i].key != ctx->table[i].key || t[i].val != ctx->table[i].val || t[i].gap != ctx->table[i].gap;
+    return bad;
 }
 
 // Record assembly through the device bodies of assemble_bam.cuh (every "thread" of a block runs in turn: the bodies need no

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "../../portello_b200/csrc/device/lift_warp.cuh"
+#include "../../portello_b200/csrc/device/table_warp.cuh"
 
 void emul_lift_long_pairs(const ptl::DevStatic& S, const ptl::DevBatch& B, const ptl::DevWork& W, ptl::DevTotals* T, uint32_t stage_mask) {
     const uint32_t n_long = std::min<uint32_t>(T->n_long, W.pair_cap);
@@ -24,6 +25,20 @@ void emul_lift_long_pairs(const ptl::DevStatic& S, const ptl::DevBatch& B, const
                 if (t < n_long) ptl::lift_long_pair_body(S, B, W, T, W.long_list[t], lane, stage_mask);
                 else ptl::simplify_warp_pair_body(S, B, W, T, W.simplify_list[t - n_long], lane);
             }
+        });
+    for (auto& th : lanes) th.join();
+}
+
+// table_build_kernel (one warp per segment, lanes over CIGAR ops): count pass into `counts` (out == nullptr) or fill pass.
+void emul_table_build_warp(const ptl::DevStatic& S, uint32_t* counts, ptl::TabEntry* out) {
+    warp_emul::Warp warp;
+    std::vector<std::thread> lanes;
+    for (uint32_t lane = 0; lane < 32; ++lane)
+        lanes.emplace_back([&, lane] {
+            warp_emul::tl_warp = &warp;
+            warp_emul::tl_lane = lane;
+            warp_emul::tl_parity = 0;
+            for (uint32_t g = 0; g < S.n_segments; ++g) ptl::table_build_warp_body(S, g, lane, counts, out);
         });
     for (auto& th : lanes) th.join();
 }

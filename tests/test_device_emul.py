@@ -329,3 +329,16 @@ def test_emulated_warp_left_shift_vectors(emul, v):
     assert long_pairs(emul, ctx) == 1
     assert res.n_records == 1 and int(res.rec_need_flip[0]) == 0
     assert (int(res.rec_pos[0]), res.record_cigar(0)) == (v["expect"]["pos"], v["expect"]["cigar"]), v["src"]
+
+
+@pytest.mark.parametrize("name,kw", [("tiny", {}), ("config1", {"n_reads": 50}), ("stress", {"n_reads": 50})])
+def test_emulated_warp_table_build_matches_scalar(emul, name, kw):
+    """table_build_kernel's body (one warp per segment, lanes over CIGAR ops, warp scans, overwrite prefix count) run by 32
+    host threads in lock step must produce the same counts and entries as the scalar build the rest of the emulation (and
+    the oracle comparison of test_emulated_tables_and_gaps) uses."""
+    import ctypes as C
+    s = synth.make(name, **kw)
+    ctx = emul_context(emul, s)
+    fn = emul.dll.ptl_emul_table_build_warp_mismatches
+    fn.restype, fn.argtypes = C.c_int64, [C.c_void_p]
+    assert fn(ctx.h) == 0
