@@ -1,3 +1,4 @@
+// Warp-cooperative bodies of the setup / enumeration kernels.
 // a7, warp-cooperative: the flat ReadToRefTreeMap of one contig->reference segment built by ONE WARP, lanes over CIGAR ops.
 // Kept in a header so that tests/emul can run it with 32 host threads in lock step against the scalar statement of the
 // algorithm (pair_bodies.cuh: table_build_body).  See kernels.cu for the description.
@@ -97,6 +98,62 @@ __device__ __forceinline__ void table_build_warp_body(const DevStatic& S, uint32
         ++n_close;
     }
     if (!out && lane == 0) counts[g] = 2u * n_close - n_over;
+}
+
+
+// a3 (count) of read r by one WARP (lanes over the CIGAR ops and over the contig's segments): same results as
+// pair_count_body in pair_bodies.cuh.  Here, in a header, so that tests/emul can run it in lock step against the scalar body.
+__device__ __forceinline__ void pair_count_warp_body(const DevStatic& S, const DevBatch& B, const DevWork& W, DevTotals* T, uint32_t r, uint32_t lane) {
+
+    const uint32_t s0 = B.read_seg_begin[r], s1 = B.read_seg_begin[r + 1];
+    bool bad = s0 > s1 || s1 > B.n_rsegs || B.read_seq_off[r] + (uint64_t(B.read_seq_len[r]) + 1u) / 2u > B.seq4_bytes;
+    for (uint32_t s = s0; s < s1 && s < B.n_rsegs; ++s) {
+        if (lane == 0) W.rseg_read[s] = r;
+        const uint64_t c0 = B.rseg_cigar_begin[s];
+        const uint32_t n = B.rseg_cigar_len[s];
+        const int64_t pos = B.rseg_pos[s];
+        if (bad || B.rseg_contig[s] >= S.n_contigs || c0 + n > B.n_cigar || pos < 0 || pos > 0x7fffffffLL) {
+            bad = true;
+            if (lane == 0) {
+                W.rseg_ref_len[s] = 0;
+                W.rseg_n_id[s] = 0;
+                W.rseg_read_len[s] = 0;
+                W.rseg_pair_begin[s] = 0;
+            }
+            continue;
+        }
+        const uint32_t* c = B.cigar + c0;
+        unsigned long long ref_len = 0;
+        uint32_t n_id = 0, read_len = 0;
+        for (uint32_t i = lane; i < n; i += 32u) {
+            const uint32_t x = c[i];
+            ref_len += op_ref_adv(x);
+            read_len += op_read_adv(x);
+            n_id += op_is_match(x & 0xfu) ? 0u : 1u;
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            ref_len += __shfl_xor_sync(FULL, ref_len, d);
+            read_len += __shfl_xor_sync(FULL, read_len, d);
+            n_id += __shfl_xor_sync(FULL, n_id, d);
+        }
+        const int64_t start = pos, end = start + int64_t(ref_len);
+        const uint32_t ctg = B.rseg_contig[s];
+        uint32_t cnt = 0;
+        const uint32_t g1 = S.contig_seg_begin[ctg + 1];
+        for (uint32_t g0 = S.contig_seg_begin[ctg]; g0 < g1; g0 += 32u) {
+            const uint32_t g = g0 + lane;
+            const bool hit = g < g1 && end >= int64_t(S.seg_so_start[g]) && start < int64_t(S.seg_so_end[g]);
+            cnt += __popc(__ballot_sync(FULL, hit));
+        }
+        if (lane == 0) {
+            W.rseg_ref_len[s] = int64_t(ref_len);
+            W.rseg_n_id[s] = n_id;
+            W.rseg_read_len[s] = read_len;
+            W.rseg_pair_begin[s] = cnt;
+        }
+    }
+    if (bad && lane == 0) atomicOr(&T->overflow, OVF_INVALID);
 }
 
 }  // namespace ptl

@@ -16,6 +16,8 @@
 
 using namespace ptl;
 
+// emul_warp.cpp: pair_count_warp_kernel under the 32-lane lock-step shim
+void emul_pair_count_warp(const ptl::DevStatic& S, const ptl::DevBatch& B, const ptl::DevWork& W, ptl::DevTotals* T);
 // emul_warp.cpp: table_build_kernel under the 32-lane lock-step shim
 void emul_table_build_warp(const ptl::DevStatic& S, uint32_t* counts, ptl::TabEntry* out);
 // emul_warp.cpp: lift_long_pairs_kernel under the 32-lane lock-step shim
@@ -55,6 +57,7 @@ struct ptl_ctx {
     std::string err;
     std::vector<EmulSlot> slots;
     uint32_t long_pair_ops = 64;
+    bool check_warp_count = false;  // ptl_emul_check_warp_pair_count
     // static state
     std::vector<uint8_t> ref;
     std::vector<uint64_t> chrom_off;
@@ -178,6 +181,19 @@ int run_batch(ptl_ctx* ctx, EmulSlot& sl, const ptl_batch* b, uint32_t stage_mas
     W.rseg_read = rseg_read.data(); W.rseg_pair_begin = rseg_pair_begin.data(); W.rseg_ref_len = rseg_ref_len.data();
     W.rseg_n_id = rseg_n_id.data(); W.rseg_read_len = rseg_read_len.data();
     for (uint32_t r = 0; r < n; ++r) pair_count_body(S, B, W, &T, r);
+    if (ctx->check_warp_count) {  // the warp-cooperative count (long-read batches on the device) must write the same arrays
+        std::vector<uint32_t> r2(ns + 1), pb2(size_t(ns) + 1, 0), id2(ns + 1), rl2(ns + 1);
+        std::vector<int64_t> ref2(ns + 1);
+        DevWork W2 = W;
+        W2.rseg_read = r2.data(); W2.rseg_pair_begin = pb2.data(); W2.rseg_ref_len = ref2.data(); W2.rseg_n_id = id2.data(); W2.rseg_read_len = rl2.data();
+        DevTotals T2;
+        totals_reset(&T2);
+        emul_pair_count_warp(S, B, W2, &T2);
+        for (uint32_t s2 = 0; s2 < ns; ++s2)
+            if (r2[s2] != rseg_read[s2] || pb2[s2] != rseg_pair_begin[s2] || id2[s2] != rseg_n_id[s2] || rl2[s2] != rseg_read_len[s2] || ref2[s2] != rseg_ref_len[s2])
+                return fail(ctx, PTL_ERR_STATE, "pair_count_warp_body differs from pair_count_body at read segment " + std::to_string(s2));
+        if ((T2.overflow ^ T.overflow) & OVF_INVALID) return fail(ctx, PTL_ERR_STATE, "pair_count_warp_body: validity flag differs");
+    }
     rseg_pair_begin[ns] = 0;
     exclusive_scan(rseg_pair_begin.data(), size_t(ns) + 1);
     const uint32_t np = rseg_pair_begin[ns];
@@ -372,6 +388,13 @@ int ptl_emul_slot_counters(ptl_ctx* ctx, int slot, uint64_t* out) {
     if (!sl || !out || !sl->ran) return PTL_ERR_INVALID_ARG;
     const DevTotals& t = sl->totals;
     out[0] = t.n_pairs; out[1] = t.n_lifted; out[2] = t.n_in_ops; out[3] = t.n_cigar_out; out[4] = t.n_base_bytes; out[5] = t.scratch_needed;
+    return PTL_OK;
+}
+
+// Every following batch also runs the warp-cooperative pair count and compares it with the scalar one (submit fails on a difference).
+int ptl_emul_check_warp_pair_count(ptl_ctx* ctx, int enable) {
+    if (!ctx) return PTL_ERR_INVALID_ARG;
+    ctx->check_warp_count = enable != 0;
     return PTL_OK;
 }
 

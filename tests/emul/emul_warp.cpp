@@ -42,3 +42,17 @@ void emul_table_build_warp(const ptl::DevStatic& S, uint32_t* counts, ptl::TabEn
         });
     for (auto& th : lanes) th.join();
 }
+
+// pair_count_warp_kernel: every read counted by one warp (32 lanes in lock step)
+void emul_pair_count_warp(const ptl::DevStatic& S, const ptl::DevBatch& B, const ptl::DevWork& W, ptl::DevTotals* T) {
+    warp_emul::Warp warp;
+    std::vector<std::thread> lanes;
+    for (uint32_t lane = 0; lane < 32; ++lane)
+        lanes.emplace_back([&, lane] {
+            warp_emul::tl_warp = &warp;
+            warp_emul::tl_lane = lane;
+            warp_emul::tl_parity = 0;
+            for (uint32_t r = 0; r < B.n_reads; ++r) ptl::pair_count_warp_body(S, B, W, T, r, lane);
+        });
+    for (auto& th : lanes) th.join();
+}

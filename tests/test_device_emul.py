@@ -342,3 +342,23 @@ def test_emulated_warp_table_build_matches_scalar(emul, name, kw):
     fn = emul.dll.ptl_emul_table_build_warp_mismatches
     fn.restype, fn.argtypes = C.c_int64, [C.c_void_p]
     assert fn(ctx.h) == 0
+
+
+@pytest.mark.parametrize("name,kw", [("tiny", dict(n_reads=400)), ("stress", dict(n_reads=60))])
+def test_emulated_warp_pair_count_matches_scalar(emul, name, kw):
+    """pair_count_warp_kernel's body (a warp per read: long-read batches on the device) against the per-thread body, on valid
+    batches and on the malformed ones (the validity flag must agree too)."""
+    import ctypes as C
+    s = synth.make(name, **kw)
+    ctx = emul_context(emul, s)
+    fn = emul.dll.ptl_emul_check_warp_pair_count
+    fn.restype, fn.argtypes = C.c_int, [C.c_void_p, C.c_int]
+    assert fn(ctx.h, 1) == 0
+    pb = helpers.pack(s)
+    res = helpers.lift_c(ctx, pb.c, allow_panic=True)   # submit fails with PTL_ERR_STATE if the two counts differ
+    assert res.n_pairs > 0
+    if name == "tiny":
+        for what, b in helpers.malformed_batches(s):
+            with pytest.raises(abi.PtlError) as e:
+                helpers.lift_c(ctx, b)
+            assert "differs" not in str(e.value), what
