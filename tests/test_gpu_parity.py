@@ -26,7 +26,9 @@ def both(s, stage_mask=abi.STAGE_ALL, first=0, count=None, long_ops=None):
     ("tiny", dict(seed=11, chrom_len=3_000_000, contigs_per_chrom=3, junction_per_mb=8, n_reads=20000)),
     ("config1", {}),
     ("stress", dict(n_reads=1500)),
-], ids=["tiny", "tiny-junctions", "config1", "stress"])
+    # ~190 ops per read: the warp-per-read pair count with 4 reads per warp in the record emission (96 < mean ops <= 256)
+    ("stress", dict(n_reads=1200, read_len_mean=17000, read_len_sd=2000, read_len_min=10000, read_len_max=24000)),
+], ids=["tiny", "tiny-junctions", "config1", "stress", "stress-17kb"])
 @pytest.mark.parametrize("long_ops", [None, 0, 1 << 30], ids=["default", "warp-all", "thread-all"])
 def test_full_path_parity(name, kw, long_ops):
     """long_ops: which pairs take the warp-cooperative liftover (default: CIGARs over 64 ops; 0: all; 2^30: none)."""
