@@ -426,10 +426,11 @@ int ptl_oracle_assemble_bases(ptl_ctx* ctx, int slot, const ptl_read_quals* qual
     if (!sl.submitted) return fail(ctx, PTL_ERR_STATE, "assemble without a lifted batch");
     const ptl_batch& b = sl.batch;
     const uint32_t n_rec = sl.res.n_records;
-    // read of every read segment (CSR inverse)
-    std::vector<uint32_t> rseg_read(b.n_read_segments);
+    // read of every record (every record of a read is a clone of the same input record, :105-117; a read without any
+    // split segment still yields its unmapped fallback, so go through the record CSR, not through the segment index)
+    std::vector<uint32_t> rec_read(n_rec);
     for (uint32_t r = 0; r < b.n_reads; ++r)
-        for (uint32_t s = b.read_seg_begin[r]; s < b.read_seg_begin[r + 1]; ++s) rseg_read[s] = r;
+        for (uint32_t k = sl.res.read_rec_begin[r]; k < sl.res.read_rec_begin[r + 1]; ++k) rec_read[k] = r;
     auto encode = [](uint8_t c) -> uint8_t {  // htslib seq_nt16_table
         switch (c) {
             case '=': return 0; case 'A': case 'a': return 1; case 'C': case 'c': return 2; case 'M': case 'm': return 3;
@@ -441,14 +442,14 @@ int ptl_oracle_assemble_bases(ptl_ctx* ctx, int slot, const ptl_read_quals* qual
     sl.asm_seq_begin.assign(size_t(n_rec) + 1, 0);
     sl.asm_qual_begin.assign(size_t(n_rec) + 1, 0);
     for (uint32_t k = 0; k < n_rec; ++k) {
-        const uint64_t len = b.read_seq_len[rseg_read[sl.rec_read_segment[k]]];
+        const uint64_t len = b.read_seq_len[rec_read[k]];
         sl.asm_seq_begin[k + 1] = sl.asm_seq_begin[k] + ((((len + 1) >> 1) + 15) & ~15ull);
         sl.asm_qual_begin[k + 1] = sl.asm_qual_begin[k] + ((len + 15) & ~15ull);
     }
     sl.asm_seq4.assign(sl.asm_seq_begin[n_rec], 0);
     sl.asm_qual.assign(sl.asm_qual_begin[n_rec], 0);
     for (uint32_t k = 0; k < n_rec; ++k) {
-        const uint32_t r = rseg_read[sl.rec_read_segment[k]];
+        const uint32_t r = rec_read[k];
         const uint64_t len = b.read_seq_len[r];
         const uint8_t* seq4 = b.seq4 + b.read_seq_off[r];
         const uint8_t* q = quals->qual + quals->read_qual_off[r];

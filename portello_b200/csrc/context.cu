@@ -9,6 +9,7 @@
 #include <cstdlib>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdint>
 #include <cstring>
@@ -96,11 +97,12 @@ struct Slot {
     HBuf ha_seq_begin, ha_qual_begin, ha_out_seq, ha_out_qual;
     cudaEvent_t a_ev[2] = {nullptr, nullptr};
     uint64_t a_qual_bytes = 0;
+    uint32_t a_qual_n_reads = 0;      // reads the resident qualities were uploaded for (0: none; cleared by a new batch)
     // record assembly, whole BAM records (ptl_assemble_records): uploaded names / aux / mate fields, work arrays, output
     DBuf b_name_off, b_names, b_aux_off, b_aux, b_mate_tid, b_mate_pos, b_tlen, b_keep, b_sa_len, b_rec_begin, b_rec_desc, b_out, b_err;
     HBuf hb_rec_begin, hb_out, hb_err;
     bool b_resident = false;
-    uint64_t b_in_bytes = 0;
+    uint64_t b_in_bytes = 0, b_name_bytes = 0, b_aux_bytes = 0;
     uint64_t b_total = 0;             // bytes of the records assembled last (they start kBamFront bytes into b_out)
     DBuf z_out;                       // ptl_bgzf_store_records
     HBuf hz_out;
@@ -128,7 +130,7 @@ struct ptl_ctx {
     std::string err;
     std::vector<Slot> slots;
     cudaStream_t setup_stream = nullptr;
-    uint64_t launches = 0;
+    std::atomic<uint64_t> launches{0};  // bumped from any slot's driving thread
     bool zero_copy_seq = false;
     uint32_t long_pair_ops = 64;  // ptl_set_long_pair_ops
     // static state
@@ -144,6 +146,16 @@ struct ptl_ctx {
 };
 
 namespace {
+
+// Launch wrappers count into a plain local; the total is added to the ctx counter atomically when the scope ends
+// (distinct slots may be driven from distinct host threads).
+struct LaunchTally {
+    std::atomic<uint64_t>& total;
+    uint64_t n = 0;
+    explicit LaunchTally(ptl_ctx* ctx) : total(ctx->launches) {}
+    ~LaunchTally() { total.fetch_add(n, std::memory_order_relaxed); }
+    operator uint64_t*() { return &n; }
+};
 
 int fail(ptl_ctx* ctx, int code, const std::string& msg) {
     if (ctx) ctx->err = msg;
@@ -215,10 +227,10 @@ void install_segments(ptl_ctx* ctx, std::vector<HostContig>& contigs) {
     ctx->h_tab_begin.assign(size_t(ns) + 1, 0);
     if (ns) {
         launch_table_build(S, ctx->s_tab_begin.as<uint32_t>(), nullptr, st);
-        ++ctx->launches;
+        ctx->launches.fetch_add(1, std::memory_order_relaxed);
         DBuf tmp;
         tmp.ensure(scan_tmp_bytes(ns + 1), st);
-        exclusive_scan_inplace<uint32_t>(ctx->s_tab_begin.as<uint32_t>(), uint64_t(ns) + 1, tmp.p, tmp.cap, st, &ctx->launches);
+        exclusive_scan_inplace<uint32_t>(ctx->s_tab_begin.as<uint32_t>(), uint64_t(ns) + 1, tmp.p, tmp.cap, st, LaunchTally(ctx));
         CK(cudaMemcpyAsync(ctx->h_tab_begin.data(), ctx->s_tab_begin.p, (size_t(ns) + 1) * 4, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         tmp.release();
@@ -226,7 +238,7 @@ void install_segments(ptl_ctx* ctx, std::vector<HostContig>& contigs) {
         ctx->s_table.ensure(std::max<size_t>(total, 1) * sizeof(TabEntry), st);
         S.table = ctx->s_table.as<TabEntry>();
         launch_table_build(S, nullptr, ctx->s_table.as<TabEntry>(), st);
-        ++ctx->launches;
+        ctx->launches.fetch_add(1, std::memory_order_relaxed);
     }
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
@@ -308,6 +320,10 @@ void upload_batch(ptl_ctx* ctx, Slot& sl, const ptl_batch* b) {
     sl.n_cigar_in = b->n_cigar;
     sl.uploaded = true;
     sl.ran = false;
+    // names / aux / qualities / assembled records on the slot belong to the previous batch
+    sl.b_resident = false;
+    sl.b_total = 0;
+    sl.a_qual_n_reads = 0;
 }
 
 void size_work(Slot& sl, uint32_t want_pairs, uint64_t want_scratch, uint64_t want_arena) {
@@ -386,7 +402,7 @@ uint64_t predicted_result_bytes(const Slot& sl) {
 // (ptl_lift_run: the device-resident path).
 void enqueue_run(ptl_ctx* ctx, Slot& sl, bool with_results) {
     launch_lift(ctx->S, sl.B, sl.W, sl.r_arena.as<char>(), sl.arena_cap, sl.w_totals.as<DevTotals>(), sl.stage_mask, sl.w_scan_tmp.p,
-                sl.w_scan_tmp.cap, sl.stream, &ctx->launches, sl.have_events ? &sl.ev : nullptr);
+                sl.w_scan_tmp.cap, sl.stream, LaunchTally(ctx), sl.have_events ? &sl.ev : nullptr);
     sl.copied_bytes = with_results ? predicted_result_bytes(sl) : kResultHeaderBytes;
     CK(cudaMemcpyAsync(sl.h_arena.p, sl.r_arena.p, sl.copied_bytes, cudaMemcpyDeviceToHost, sl.stream));
     sl.with_results = with_results;
@@ -698,7 +714,7 @@ int ptl_slot_kernel_times(ptl_ctx* ctx, int slot, int cap, const char** names, f
     }
     return n;
 }
-uint64_t ptl_launch_count(const ptl_ctx* ctx) { return ctx ? ctx->launches : 0; }
+uint64_t ptl_launch_count(const ptl_ctx* ctx) { return ctx ? ctx->launches.load(std::memory_order_relaxed) : 0; }
 // Record assembly, bases: see include/portello_b200.h.
 int ptl_assemble_bases(ptl_ctx* ctx, int slot, const ptl_read_quals* quals, uint32_t flags, ptl_record_bases* out) {
     Slot* sl = get_slot(ctx, slot);
@@ -716,8 +732,9 @@ int ptl_assemble_bases(ptl_ctx* ctx, int slot, const ptl_read_quals* quals, uint
             if (quals->qual_bytes) CK(cudaMemcpyAsync(sl->a_qual.p, quals->qual, quals->qual_bytes, cudaMemcpyHostToDevice, st));
             upload(sl->a_qual_off, quals->read_qual_off, n, st);
             sl->a_qual_bytes = quals->qual_bytes;
-        } else if (!sl->a_qual.p) {
-            throw std::runtime_error("PTL_ASM_RESIDENT_QUAL without a previous upload on this slot");
+            sl->a_qual_n_reads = n;
+        } else if (!sl->a_qual.p || sl->a_qual_n_reads != n) {
+            throw std::runtime_error("PTL_ASM_RESIDENT_QUAL without a previous upload for this batch on this slot");
         }
         const ResultLayout L = result_layout(n, t.n_records, t.n_cigar_out);
         const DevResult R = DevResult::view(sl->r_arena.as<char>(), L);
@@ -725,13 +742,19 @@ int ptl_assemble_bases(ptl_ctx* ctx, int slot, const ptl_read_quals* quals, uint
         sl->a_seq_begin.ensure((size_t(n_rec) + 1) * 8, st);
         sl->a_qual_begin.ensure((size_t(n_rec) + 1) * 8, st);
         sl->w_scan_tmp.ensure(scan_tmp_bytes(uint64_t(n_rec) + 1), st);
-        launch_assemble_sizes(n_rec, R.rec_read_segment, sl->W.rseg_read, sl->B.read_seq_len, sl->a_rec_read.as<uint32_t>(), sl->a_seq_begin.as<uint64_t>(),
-                              sl->a_qual_begin.as<uint64_t>(), sl->w_scan_tmp.p, sl->w_scan_tmp.cap, st, &ctx->launches);
+        sl->b_err.ensure(4, st);
+        CK(cudaMemsetAsync(sl->b_err.p, 0, 4, st));
+        launch_assemble_sizes(n_rec, n, R.read_rec_begin, sl->B.read_seq_len, sl->a_qual_off.as<uint64_t>(), sl->a_qual_bytes, sl->a_rec_read.as<uint32_t>(),
+                              sl->a_seq_begin.as<uint64_t>(), sl->a_qual_begin.as<uint64_t>(), sl->b_err.as<unsigned int>(), sl->w_scan_tmp.p,
+                              sl->w_scan_tmp.cap, st, LaunchTally(ctx));
         sl->ha_seq_begin.ensure((size_t(n_rec) + 1) * 8);
         sl->ha_qual_begin.ensure((size_t(n_rec) + 1) * 8);
+        sl->hb_err.ensure(4);
         CK(cudaMemcpyAsync(sl->ha_seq_begin.p, sl->a_seq_begin.p, (size_t(n_rec) + 1) * 8, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(sl->ha_qual_begin.p, sl->a_qual_begin.p, (size_t(n_rec) + 1) * 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(sl->hb_err.p, sl->b_err.p, 4, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));  // the output sizes are only known now
+        if (*sl->hb_err.as<unsigned int>() & 16u) throw std::runtime_error("ptl_read_quals: a quality range lies outside the pool");
         const uint64_t seq_total = sl->ha_seq_begin.as<uint64_t>()[n_rec], qual_total = sl->ha_qual_begin.as<uint64_t>()[n_rec];
         sl->a_out_seq.ensure(std::max<uint64_t>(seq_total, 16), st);
         sl->a_out_qual.ensure(std::max<uint64_t>(qual_total, 16), st);
@@ -750,7 +773,7 @@ int ptl_assemble_bases(ptl_ctx* ctx, int slot, const ptl_read_quals* quals, uint
         A.out_qual = sl->a_out_qual.as<uint8_t>();
         if (!sl->a_ev[0]) { CK(cudaEventCreate(&sl->a_ev[0])); CK(cudaEventCreate(&sl->a_ev[1])); }
         CK(cudaEventRecord(sl->a_ev[0], st));
-        launch_assemble_records(A, st, &ctx->launches);
+        launch_assemble_records(A, st, LaunchTally(ctx));
         CK(cudaEventRecord(sl->a_ev[1], st));
         if (!(flags & PTL_ASM_NO_DOWNLOAD)) {
             sl->ha_out_seq.ensure(std::max<uint64_t>(seq_total, 4));
@@ -807,7 +830,7 @@ int ptl_bgzf_store_records(ptl_ctx* ctx, int slot, const uint8_t* prefix, uint64
         A.init_last = crc_zero_bytes(tables.data(), 0xffffffffu, n_blocks ? n - (n_blocks - 1) * kBgzfIn : 0);
         if (!sl->a_ev[0]) { CK(cudaEventCreate(&sl->a_ev[0])); CK(cudaEventCreate(&sl->a_ev[1])); }
         CK(cudaEventRecord(sl->a_ev[0], st));
-        launch_bgzf_store(A, st, &ctx->launches);
+        launch_bgzf_store(A, st, LaunchTally(ctx));
         CK(cudaEventRecord(sl->a_ev[1], st));
         if (flags & PTL_BGZF_EOF) CK(cudaMemcpyAsync(sl->z_out.as<uint8_t>() + framed, kEof, sizeof(kEof), cudaMemcpyHostToDevice, st));
         *out = ptl_bgzf_stream{};
@@ -880,8 +903,11 @@ int ptl_assemble_records(ptl_ctx* ctx, int slot, const ptl_read_extras* x, uint3
             if (x->quals.qual_bytes) CK(cudaMemcpyAsync(sl->a_qual.p, x->quals.qual, x->quals.qual_bytes, cudaMemcpyHostToDevice, st));
             upload(sl->a_qual_off, x->quals.read_qual_off, n, st);
             sl->a_qual_bytes = x->quals.qual_bytes;
+            sl->a_qual_n_reads = n;
             sl->b_resident = true;
             sl->b_in_bytes = name_bytes + aux_bytes;
+            sl->b_name_bytes = name_bytes;
+            sl->b_aux_bytes = aux_bytes;
         } else if (!sl->b_resident) {
             throw std::runtime_error("PTL_ASM_RESIDENT_QUAL without a previous ptl_assemble_records upload on this slot");
         }
@@ -920,6 +946,9 @@ int ptl_assemble_records(ptl_ctx* ctx, int slot, const ptl_read_extras* x, uint3
         A.tlen = sl->b_tlen.as<int32_t>();
         A.qual_off = sl->a_qual_off.as<uint64_t>();
         A.qual = sl->a_qual.as<uint8_t>();
+        A.names_bytes = sl->b_name_bytes;
+        A.aux_bytes = sl->b_aux_bytes;
+        A.qual_bytes = sl->a_qual_bytes;
         A.read_rec_begin = R.read_rec_begin;
         A.rec_status = R.rec_status;
         A.rec_read_segment = R.rec_read_segment;
@@ -937,13 +966,14 @@ int ptl_assemble_records(ptl_ctx* ctx, int slot, const ptl_read_extras* x, uint3
         A.rec_begin = sl->b_rec_begin.as<uint64_t>();
         A.rec_desc = sl->b_rec_desc.as<uint4>();
         A.error = sl->b_err.as<unsigned int>();
-        launch_bam_sizes(A, sl->w_scan_tmp.p, sl->w_scan_tmp.cap, st, &ctx->launches);
+        launch_bam_sizes(A, sl->w_scan_tmp.p, sl->w_scan_tmp.cap, st, LaunchTally(ctx));
         sl->hb_rec_begin.ensure((size_t(n_rec) + 1) * 8);
         sl->hb_err.ensure(4);
         CK(cudaMemcpyAsync(sl->hb_rec_begin.p, sl->b_rec_begin.p, (size_t(n_rec) + 1) * 8, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(sl->hb_err.p, sl->b_err.p, 4, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));  // the output size is only known now
         const unsigned err = *sl->hb_err.as<unsigned int>();
+        if (err & 16u) throw std::runtime_error("ptl_read_extras: a name / aux / quality offset is not monotonic or lies outside its pool");
         if (err & 1u) throw std::runtime_error("ptl_set_names: a contig or reference chromosome of this batch has no name");
         if (err & 2u) throw std::runtime_error("a lifted CIGAR has more than 65535 ops (BAM needs a CG tag for it: out of scope)");
         if (err & 4u) throw std::runtime_error("a contig name longer than 248 bytes or more than 16 MB of SA text in one record");
@@ -961,7 +991,7 @@ int ptl_assemble_records(ptl_ctx* ctx, int slot, const ptl_read_extras* x, uint3
         CK(cudaEventRecord(sl->a_ev[0], st));
         CK(cudaEventRecord(sl->b_fork, st));
         CK(cudaStreamWaitEvent(sl->b_stream, sl->b_fork, 0));
-        launch_bam_write(A, st, sl->b_stream, &ctx->launches);
+        launch_bam_write(A, st, sl->b_stream, LaunchTally(ctx));
         CK(cudaEventRecord(sl->b_join, sl->b_stream));
         CK(cudaStreamWaitEvent(st, sl->b_join, 0));
         CK(cudaEventRecord(sl->a_ev[1], st));

@@ -50,6 +50,7 @@ struct BamAsmArgs {
     const int32_t* tlen;
     const uint64_t* qual_off;
     const uint8_t* qual;
+    uint64_t names_bytes, aux_bytes, qual_bytes;  // pool sizes: the offsets above are validated against them (bam_read_prep)
     // result of the liftover (views into the slot's result arena)
     const uint32_t* read_rec_begin;
     const int8_t* rec_status;
@@ -70,7 +71,8 @@ struct BamAsmArgs {
     uint4* rec_desc;         // [n_records][2] BamRecLayout of the record, computed once by bam_rec_size (the writer's prologue
                              //                is then two dependent loads deep instead of five)
     uint8_t* out;
-    unsigned int* error;     // bit 0: a name is missing, 1: a CIGAR has more than 65535 ops, 2: descriptor field overflow, 3: qname > 254 bytes
+    unsigned int* error;     // bit 0: a name is missing, 1: a CIGAR has more than 65535 ops, 2: descriptor field overflow, 3: qname > 254 bytes,
+                             // bit 4: an offset of the extras (names / aux / qualities) lies outside its pool
 };
 
 __device__ __forceinline__ uint32_t dec_digits(uint64_t v) {
@@ -128,6 +130,19 @@ __device__ __forceinline__ uint32_t aux_field_size(const uint8_t* aux, uint32_t 
 // clone_record (:105-117): remove_aux_if_found(NM), (SA), (PS), (ZM), each the FIRST field of that name.  One walk finds
 // all four (removing one field does not change which field of another name comes first).
 __device__ __forceinline__ void bam_read_prep_body(const BamAsmArgs& A, uint32_t r) {
+    // The extras are caller memory: an offset outside its pool must be reported, never dereferenced (the writers only run
+    // after the host has seen a clean error word).
+    {
+        const uint64_t n0 = A.name_off[r], n1 = A.name_off[r + 1], a0 = A.aux_off[r], a1 = A.aux_off[r + 1], q0 = A.qual_off[r];
+        const bool bad = n0 > n1 || n1 > A.names_bytes || a0 > a1 || a1 > A.aux_bytes || a1 - a0 > 0x7fffffffull ||
+                         q0 > A.qual_bytes || uint64_t(A.read_seq_len[r]) > A.qual_bytes - q0;
+        if (bad) {
+            atomicOr(A.error, 16u);
+            uint32_t* keep = A.read_keep + size_t(r) * 10;
+            for (int j = 0; j < 10; ++j) keep[j] = 0u;
+            return;
+        }
+    }
     const uint8_t* aux = A.aux + A.aux_off[r];
     const uint32_t n = uint32_t(A.aux_off[r + 1] - A.aux_off[r]);
     uint32_t cut_a[4], cut_e[4];

@@ -444,13 +444,23 @@ void launch_lift(const DevStatic& S, const DevBatch& B, const DevWork& W, char* 
 
 // =================================================================================================== record assembly
 namespace {
-__global__ void __launch_bounds__(256) assemble_sizes_kernel(uint32_t n_records, const uint32_t* rec_read_segment, const uint32_t* rseg_read,
-                                                             const uint32_t* read_seq_len, uint32_t* rec_read, uint64_t* seq_begin, uint64_t* qual_begin) {
+__global__ void __launch_bounds__(256) assemble_sizes_kernel(uint32_t n_records, uint32_t n_reads, const uint32_t* read_rec_begin,
+                                                             const uint32_t* read_seq_len, const uint64_t* read_qual_off, uint64_t qual_bytes,
+                                                             uint32_t* rec_read, uint64_t* seq_begin, uint64_t* qual_begin, unsigned int* error) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k > n_records) return;
     if (k == n_records) { seq_begin[k] = 0; qual_begin[k] = 0; return; }
-    const uint32_t r = rseg_read[rec_read_segment[k]];
+    // the read that owns record k: last r with read_rec_begin[r] <= k (as bam_rec_layout; the fallback record of a read
+    // without segments has no rec_read_segment of its own to go through)
+    uint32_t lo = 0, hi = n_reads;
+    while (hi - lo > 1u) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (read_rec_begin[mid] <= k) lo = mid; else hi = mid;
+    }
+    const uint32_t r = lo;
     const uint64_t len = read_seq_len[r];
+    // caller memory: a quality range outside the pool is reported, never read (the writer only runs on a clean error word)
+    if (k == read_rec_begin[r] && (read_qual_off[r] > qual_bytes || len > qual_bytes - read_qual_off[r])) atomicOr(error, 16u);
     rec_read[k] = r;
     seq_begin[k] = (((len + 1) >> 1) + 15) & ~15ull;
     qual_begin[k] = (len + 15) & ~15ull;
@@ -459,10 +469,11 @@ __global__ void __launch_bounds__(256) assemble_sizes_kernel(uint32_t n_records,
 __global__ void __launch_bounds__(256) assemble_records_kernel(AsmArgs A) { assemble_record_body(A, blockIdx.x, threadIdx.x, blockDim.x); }
 }  // namespace
 
-void launch_assemble_sizes(uint32_t n_records, const uint32_t* rec_read_segment, const uint32_t* rseg_read, const uint32_t* read_seq_len,
-                           uint32_t* rec_read, uint64_t* seq_begin, uint64_t* qual_begin, void* scan_tmp, size_t scan_tmp_bytes_, cudaStream_t st,
-                           uint64_t* launches) {
-    assemble_sizes_kernel<<<(n_records + 1 + 255) / 256, 256, 0, st>>>(n_records, rec_read_segment, rseg_read, read_seq_len, rec_read, seq_begin, qual_begin);
+void launch_assemble_sizes(uint32_t n_records, uint32_t n_reads, const uint32_t* read_rec_begin, const uint32_t* read_seq_len,
+                           const uint64_t* read_qual_off, uint64_t qual_bytes, uint32_t* rec_read, uint64_t* seq_begin, uint64_t* qual_begin,
+                           unsigned int* error, void* scan_tmp, size_t scan_tmp_bytes_, cudaStream_t st, uint64_t* launches) {
+    assemble_sizes_kernel<<<(n_records + 1 + 255) / 256, 256, 0, st>>>(n_records, n_reads, read_rec_begin, read_seq_len, read_qual_off, qual_bytes, rec_read,
+                                                                        seq_begin, qual_begin, error);
     ++*launches;
     exclusive_scan_inplace<uint64_t>(seq_begin, uint64_t(n_records) + 1, scan_tmp, scan_tmp_bytes_, st, launches, nullptr);
     exclusive_scan_inplace<uint64_t>(qual_begin, uint64_t(n_records) + 1, scan_tmp, scan_tmp_bytes_, st, launches, nullptr);

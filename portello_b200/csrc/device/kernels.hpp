@@ -30,9 +30,9 @@ void launch_lift(const DevStatic& S, const DevBatch& B, const DevWork& W, char* 
 // Record assembly, bases (assemble.cuh).  Sizes: per record the 4-byte-rounded byte counts of its bases and qualities into
 // seq_begin / qual_begin ([n_records+1], then exclusive scans), and the record's read index into rec_read.
 struct AsmArgs;
-void launch_assemble_sizes(uint32_t n_records, const uint32_t* rec_read_segment, const uint32_t* rseg_read, const uint32_t* read_seq_len,
-                           uint32_t* rec_read, uint64_t* seq_begin, uint64_t* qual_begin, void* scan_tmp, size_t scan_tmp_bytes, cudaStream_t st,
-                           uint64_t* launches);
+void launch_assemble_sizes(uint32_t n_records, uint32_t n_reads, const uint32_t* read_rec_begin, const uint32_t* read_seq_len,
+                           const uint64_t* read_qual_off, uint64_t qual_bytes, uint32_t* rec_read, uint64_t* seq_begin, uint64_t* qual_begin,
+                           unsigned int* error, void* scan_tmp, size_t scan_tmp_bytes, cudaStream_t st, uint64_t* launches);
 void launch_assemble_records(const AsmArgs& A, cudaStream_t st, uint64_t* launches);
 
 // Record assembly, whole BAM records (assemble_bam.cuh): sizes (aux walk per read, SA entry length per record, record

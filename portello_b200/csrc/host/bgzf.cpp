@@ -52,7 +52,7 @@ uint64_t ptl_bgzf_bound(uint64_t n) {
 }
 
 int64_t ptl_bgzf_compress(const uint8_t* in, uint64_t n, int level, int n_threads, int append_eof, uint8_t* out, uint64_t cap) {
-    if ((n && !in) || !out || level < 0 || level > 9) return PTL_ERR_INVALID_ARG;
+    if ((n && !in) || !out || level < 0 || level > 9) return -int64_t(PTL_ERR_INVALID_ARG);
     const uint64_t blocks = (n + kBlockIn - 1) / kBlockIn;
     std::vector<std::vector<uint8_t>> z(blocks);
     std::atomic<uint64_t> next{0};
@@ -70,15 +70,15 @@ int64_t ptl_bgzf_compress(const uint8_t* in, uint64_t n, int level, int n_thread
     for (int t = 1; t < nt; ++t) pool.emplace_back(work);
     work();
     for (auto& t : pool) t.join();
-    if (err) return PTL_ERR_INVALID_ARG;
+    if (err) return -int64_t(PTL_ERR_INPUT);  // zlib failure
     uint64_t at = 0;
     for (const auto& b : z) {
-        if (at + b.size() > cap) return PTL_ERR_INVALID_ARG;
+        if (at + b.size() > cap) return -int64_t(PTL_ERR_INVALID_ARG);
         std::memcpy(out + at, b.data(), b.size());
         at += b.size();
     }
     if (append_eof) {
-        if (at + sizeof(kEof) > cap) return PTL_ERR_INVALID_ARG;
+        if (at + sizeof(kEof) > cap) return -int64_t(PTL_ERR_INVALID_ARG);
         std::memcpy(out + at, kEof, sizeof(kEof));
         at += sizeof(kEof);
     }
@@ -86,7 +86,7 @@ int64_t ptl_bgzf_compress(const uint8_t* in, uint64_t n, int level, int n_thread
 }
 
 int64_t ptl_bam_header(const char* sam_text, uint32_t n_ref, const char* const* ref_names, const uint64_t* ref_len, uint8_t* out, uint64_t cap) {
-    if ((n_ref && (!ref_names || !ref_len)) || !out) return PTL_ERR_INVALID_ARG;
+    if ((n_ref && (!ref_names || !ref_len)) || !out) return -int64_t(PTL_ERR_INVALID_ARG);
     std::vector<uint8_t> v;
     auto u32 = [&](uint32_t x) { for (int b = 0; b < 4; ++b) v.push_back(uint8_t(x >> (8 * b))); };
     const std::string text = sam_text ? sam_text : "";
@@ -95,14 +95,14 @@ int64_t ptl_bam_header(const char* sam_text, uint32_t n_ref, const char* const* 
     v.insert(v.end(), text.begin(), text.end());
     u32(n_ref);
     for (uint32_t i = 0; i < n_ref; ++i) {
-        if (!ref_names[i] || ref_len[i] > 0x7fffffffull) return PTL_ERR_INVALID_ARG;
+        if (!ref_names[i] || ref_len[i] > 0x7fffffffull) return -int64_t(PTL_ERR_INVALID_ARG);
         const std::string nm = ref_names[i];
         u32(uint32_t(nm.size() + 1));
         v.insert(v.end(), nm.begin(), nm.end());
         v.push_back(0);
         u32(uint32_t(ref_len[i]));
     }
-    if (v.size() > cap) return PTL_ERR_INVALID_ARG;
+    if (v.size() > cap) return -int64_t(PTL_ERR_INVALID_ARG);
     std::memcpy(out, v.data(), v.size());
     return int64_t(v.size());
 }

@@ -461,6 +461,7 @@ int ptl_emul_assemble_records(ptl_ctx* ctx, int slot, const ptl_read_extras* x, 
     A.seq4 = seq4.data() + kPad; A.rseg_contig = sl->rseg_contig.data(); A.rseg_read = sl->rseg_read.data();
     A.name_off = x->name_off; A.names = names.data() + kPad; A.aux_off = x->aux_off; A.aux = aux.data() + kPad;
     A.mate_tid = x->mate_tid; A.mate_pos = x->mate_pos; A.tlen = x->tlen; A.qual_off = x->quals.read_qual_off; A.qual = qual.data() + kPad;
+    A.names_bytes = n ? x->name_off[n] : 0; A.aux_bytes = n ? x->aux_off[n] : 0; A.qual_bytes = x->quals.qual_bytes;
     A.read_rec_begin = sl->res.read_rec_begin; A.rec_status = sl->res.rec_status; A.rec_read_segment = sl->res.rec_read_segment;
     A.rec_contig_segment = sl->res.rec_contig_segment; A.rec_tid = sl->res.rec_tid; A.rec_pos = sl->res.rec_pos; A.rec_mapq = sl->res.rec_mapq;
     A.rec_flag = sl->res.rec_flag; A.rec_bin = sl->res.rec_bin; A.rec_need_flip = sl->res.rec_need_flip; A.rec_cigar_begin = sl->res.rec_cigar_begin;
@@ -478,6 +479,7 @@ int ptl_emul_assemble_records(ptl_ctx* ctx, int slot, const ptl_read_extras* x, 
         run += L.total;
     }
     sl->bam_begin[n_rec] = run;
+    if (err & 16u) return fail(ctx, PTL_ERR_INVALID_ARG, "ptl_read_extras: an offset lies outside its pool");
     if (err & 1u) return fail(ctx, PTL_ERR_INVALID_ARG, "ptl_set_names: a contig or reference chromosome of this batch has no name");
     if (err & 2u) return fail(ctx, PTL_ERR_INVALID_ARG, "a lifted CIGAR has more than 65535 ops");
     if (err & 4u) return fail(ctx, PTL_ERR_INVALID_ARG, "descriptor field overflow");

@@ -118,3 +118,58 @@ def test_gpu_assemble_matches_oracle(case):
     assert none is None and o2.n_records == og.n_records and o2.kernel_ms > 0
     if case == "iupac-odd":
         check_against_model(gctx, pb, rg, qual, off)
+
+
+def _with_segmentless_reads(pb, every=7):
+    """The packed batch as numpy with the segments of every `every`-th read removed (such a read yields only the unmapped
+    fallback record; its rec_read_segment cannot identify it)."""
+    b = pb.c
+    n, ns = b.n_reads, b.n_read_segments
+    g = lambda p, k: np.ctypeslib.as_array(p, (k,)).copy()
+    seg_begin = g(b.read_seg_begin, n + 1).astype(np.int64)
+    drop_read = (np.arange(n) % every) == 3
+    keep_seg = ~np.repeat(drop_read, np.diff(seg_begin))
+    cnt = np.where(drop_read, 0, np.diff(seg_begin))
+    new_begin = np.zeros(n + 1, np.uint32)
+    new_begin[1:] = np.cumsum(cnt)
+    return abi.Batch(read_flag=g(b.read_flag, n), read_mapq=g(b.read_mapq, n), read_bin=g(b.read_bin, n), read_seq_len=g(b.read_seq_len, n),
+                     read_seq_off=g(b.read_seq_off, n), read_seg_begin=new_begin, rseg_contig=g(b.rseg_contig, ns)[keep_seg],
+                     rseg_pos=g(b.rseg_pos, ns)[keep_seg], rseg_is_fwd=g(b.rseg_is_fwd, ns)[keep_seg],
+                     rseg_cigar_begin=g(b.rseg_cigar_begin, ns)[keep_seg], rseg_cigar_len=g(b.rseg_cigar_len, ns)[keep_seg],
+                     cigar=g(b.cigar, int(b.n_cigar)), seq4=g(b.seq4, int(b.seq4_bytes))), drop_read
+
+
+def _check_segmentless(ctx, batch, drop_read, qual, off):
+    res = ctx.lift(batch, allow_panic=True)
+    _, (sb, seq, qb, ql) = ctx.assemble_bases(qual, off)
+    rec_read = np.repeat(np.arange(batch.n_reads), np.diff(res.read_rec_begin.astype(np.int64)))
+    assert (np.diff(res.read_rec_begin.astype(np.int64))[drop_read] == 1).all()
+    for k in np.flatnonzero(drop_read[rec_read]):
+        r = int(rec_read[k])
+        n = int(batch.read_seq_len[r])
+        assert int(qb[k + 1] - qb[k]) == (n + 15) // 16 * 16, "fallback record sized from another read"
+        q = qual[int(off[r]): int(off[r]) + n]
+        got = ql[int(qb[k]): int(qb[k]) + n]
+        assert np.array_equal(got, q[::-1] if res.rec_need_flip[k] else q), f"record {k}: qualities of another read"
+    return res, (sb, seq, qb, ql)
+
+
+def test_oracle_assemble_read_without_segments():
+    s = synth.make("tiny", seed=6, n_reads=300)
+    pb = helpers.pack(s)
+    batch, drop_read = _with_segmentless_reads(pb)
+    qual, off = make_quals(pb.c, 3)
+    _check_segmentless(helpers.oracle_context(s), batch, drop_read, qual, off)
+
+
+@pytest.mark.gpu
+def test_gpu_assemble_read_without_segments():
+    s = synth.make("tiny", seed=6, n_reads=300)
+    pb = helpers.pack(s)
+    batch, drop_read = _with_segmentless_reads(pb)
+    qual, off = make_quals(pb.c, 3)
+    ro, po = _check_segmentless(helpers.oracle_context(s), batch, drop_read, qual, off)
+    rg, pg = _check_segmentless(helpers.gpu_context(s), batch, drop_read, qual, off)
+    assert rg.diff(ro) is None
+    for a, b2 in zip(po, pg):
+        assert np.array_equal(a, b2)

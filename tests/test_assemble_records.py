@@ -391,3 +391,50 @@ def test_gpu_read_names_beyond_u8_are_rejected():
     s = synth.make("tiny", seed=3, n_reads=20)
     pb = helpers.pack(s)
     _long_name_rejected(helpers.gpu_context(s), s, pb)
+
+
+@pytest.mark.gpu
+def test_gpu_malformed_extras_are_rejected_not_dereferenced():
+    """The extras are caller memory: an offset outside its pool is PTL_ERR_INVALID_ARG, and the context survives (no sticky
+    CUDA fault) -- the next well-formed call on the same slot succeeds."""
+    s = synth.make("tiny", seed=3, n_reads=200)
+    pb = helpers.pack(s)
+    gctx = helpers.gpu_context(s)
+    gctx.set_names(s.contig_names, s.chrom_names)
+    helpers.lift_c(gctx, pb.c)
+    x, _, _ = make_extras(s, pb, 1)
+    n = pb.c.n_reads
+
+    def broken(field, idx, value):
+        y = dict(x)
+        y[field] = np.array(x[field], copy=True)
+        y[field][idx] = value
+        return y
+
+    for y in (broken("aux_off", 5, 1 << 40), broken("name_off", 7, int(x["name_off"][8]) + 1), broken("qual_off", n - 1, len(x["qual"]) - 3),
+              broken("aux_off", 3, int(x["aux_off"][2]) - 1 if int(x["aux_off"][2]) else 1 << 33)):
+        with pytest.raises(abi.PtlError) as e:
+            gctx.assemble_records(y)
+        assert e.value.code == abi.PTL_ERR_INVALID_ARG, e.value
+    with pytest.raises(abi.PtlError):
+        gctx.assemble_bases(x["qual"], broken("qual_off", 0, len(x["qual"]))["qual_off"])
+    _, (rb, by) = gctx.assemble_records(x)  # still alive
+    assert int(rb[-1]) == by.size > 0
+
+
+@pytest.mark.gpu
+def test_gpu_stale_extras_are_not_reused_for_a_new_batch():
+    """PTL_ASM_RESIDENT_QUAL after ANOTHER batch on the slot must fail (names / aux / qualities belong to the old reads)."""
+    s = synth.make("tiny", seed=4, n_reads=400)
+    pa, pb2 = helpers.pack(s, 0, 150), helpers.pack(s, 150, 250)
+    gctx = helpers.gpu_context(s)
+    gctx.set_names(s.contig_names, s.chrom_names)
+    helpers.lift_c(gctx, pa.c)
+    x, _, _ = make_extras(s, pa, 1)
+    gctx.assemble_records(x)
+    gctx.assemble_records(None, flags=abi.ASM_RESIDENT_QUAL)
+    helpers.lift_c(gctx, pb2.c)
+    for call in (lambda: gctx.assemble_records(None, flags=abi.ASM_RESIDENT_QUAL), lambda: gctx.bgzf_store_records(b""),
+                 lambda: gctx.assemble_bases(None, None, flags=abi.ASM_RESIDENT_QUAL)):
+        with pytest.raises(abi.PtlError):
+            call()

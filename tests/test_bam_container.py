@@ -3,6 +3,7 @@ host code written from the SAM specification (no htslib).  Checked against Pytho
 implementation of the same RFC 1952 framing) and by parsing the result back."""
 import ctypes as C
 import gzip
+import os
 import struct
 import zlib
 
@@ -190,3 +191,21 @@ def test_emulated_bgzf_kernel_matches_model(n, misalign):
     z = out[1: 1 + got].tobytes()
     assert z == bgzf_level0_model(data.tobytes(), True)
     assert gzip.decompress(z) == data.tobytes()
+
+
+def test_container_errors_are_negative():
+    """include/portello_b200.h: both calls return the bytes written or a NEGATIVE PTL_ERR_* code (a positive error code would
+    read as a 1-byte success)."""
+    d = _fns()
+    data = np.frombuffer(os.urandom(200_000), np.uint8)
+    out = np.zeros(int(d.ptl_bgzf_bound(data.size)), np.uint8)
+    assert d.ptl_bgzf_compress(data.ctypes.data, data.size, 6, 2, 1, out.ctypes.data, 1000) < 0          # cap too small
+    n_ok = d.ptl_bgzf_compress(data.ctypes.data, data.size, 6, 2, 1, out.ctypes.data, out.size)
+    assert n_ok > 28
+    assert d.ptl_bgzf_compress(data.ctypes.data, data.size, 6, 2, 1, out.ctypes.data, n_ok - 1) < 0      # no room for the EOF marker
+    assert d.ptl_bgzf_compress(data.ctypes.data, data.size, 11, 2, 1, out.ctypes.data, out.size) < 0     # bad level
+    names = (C.c_char_p * 1)(b"chr1")
+    hb = np.zeros(64, np.uint8)
+    assert d.ptl_bam_header(b"@HD\n", 1, names, (C.c_uint64 * 1)(1 << 31), hb.ctypes.data, hb.size) < 0  # l_ref > int32
+    assert d.ptl_bam_header(b"@HD\n", 1, names, (C.c_uint64 * 1)(1000), hb.ctypes.data, 8) < 0           # cap too small
+    assert d.ptl_bam_header(b"@HD\n", 1, names, (C.c_uint64 * 1)(1000), hb.ctypes.data, hb.size) > 0
