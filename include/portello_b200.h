@@ -252,7 +252,8 @@ typedef struct {
     const uint64_t* rec_qual_begin;  /* [n_records+1] byte offsets into qual; every record starts 16-byte aligned, zero padded */
     const uint8_t* qual;
     float kernel_ms;                 /* device time of the assembly kernel (CUDA events on the slot stream) */
-    uint64_t bytes_read, bytes_written;  /* algorithmic bytes of that kernel: bases + qualities in, bases + qualities out */
+    uint64_t bytes_read;
+    uint64_t bytes_written;  /* algorithmic bytes of that kernel: bases + qualities in, bases + qualities out */
 } ptl_record_bases;
 /* flags: PTL_ASM_RESIDENT_QUAL = the qualities uploaded by the previous call on this slot are reused (no H2D);
  *        PTL_ASM_NO_DOWNLOAD   = results stay on the device (out->seq4 / out->qual are NULL): kernel timing only. */
@@ -290,7 +291,8 @@ typedef struct {
     const uint64_t* rec_begin;       /* [n_records+1] byte offsets into bytes; record k = block_size (u32) + block_size bytes */
     const uint8_t* bytes;
     float kernel_ms;                 /* device time of the record-writing kernel (CUDA events on the slot stream) */
-    uint64_t bytes_read, bytes_written;  /* algorithmic bytes of that kernel: every input byte of a record once, every output byte once */
+    uint64_t bytes_read;
+    uint64_t bytes_written;  /* algorithmic bytes of that kernel: every input byte of a record once, every output byte once */
 } ptl_bam_records;
 /* flags: PTL_ASM_RESIDENT_QUAL = everything uploaded by the previous call on this slot is reused (no H2D; extras may be NULL);
  *        PTL_ASM_NO_DOWNLOAD   = results stay on the device (out->bytes is NULL): kernel timing only. */
@@ -322,7 +324,8 @@ typedef struct {
     const uint8_t* bytes;           /* NULL with PTL_ASM_NO_DOWNLOAD */
     uint64_t n_blocks;
     float kernel_ms;                /* device time of the framing kernel (CUDA events on the slot stream) */
-    uint64_t bytes_read, bytes_written;  /* algorithmic bytes: the stream once in, the framed stream once out */
+    uint64_t bytes_read;
+    uint64_t bytes_written;  /* algorithmic bytes: the stream once in, the framed stream once out */
 } ptl_bgzf_stream;
 int ptl_bgzf_store_records(ptl_ctx* ctx, int slot, const uint8_t* prefix, uint64_t prefix_bytes, uint32_t flags, ptl_bgzf_stream* out);
 
