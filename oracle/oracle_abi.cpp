@@ -869,6 +869,81 @@ int ptl_oracle_split_segments(uint32_t n_names, const char* const* names, int32_
     }
 }
 
+// The head of the reference's record loop (src/read_alignment_scanner.rs:393-421) for records [first, first + count):
+// skip supplementary records, get_seq_order_read_split_segments for the others -> one ptl_batch, so that the CPU arm of
+// the bench (bench.py --impl reference) needs nothing of the product library.  Same output layout as ptl_pack_batch.
+struct ptl_oracle_packed {
+    std::vector<uint16_t> read_flag, read_bin;
+    std::vector<uint8_t> read_mapq, rseg_is_fwd;
+    std::vector<uint32_t> read_seq_len, read_seg_begin, rseg_contig, rseg_cigar_len, cigar, record_index;
+    std::vector<uint64_t> read_seq_off, rseg_cigar_begin;
+    std::vector<int64_t> rseg_pos;
+    ptl_batch view{};
+};
+static thread_local std::string g_pack_err;
+const char* ptl_oracle_pack_last_error(void) { return g_pack_err.c_str(); }
+int ptl_oracle_pack_batch(const ptl_read_records* recs, uint32_t first, uint32_t count, uint32_t n_names, const char* const* names, int n_threads,
+                          ptl_oracle_packed** out) {
+    if (!recs || !out || first > recs->n_reads || count > recs->n_reads - first) return PTL_ERR_INVALID_ARG;
+    NameIndex idx;
+    for (uint32_t i = 0; i < n_names; ++i) idx[names[i]] = i;
+    struct Part { std::vector<std::vector<SeqOrderSplitReadSegment>> segs; std::vector<uint32_t> rec; std::string err; };
+    const uint32_t chunk = 4096, n_chunks = (count + chunk - 1) / chunk;
+    std::vector<Part> parts(n_chunks);
+    std::atomic<uint32_t> next{0};
+    auto worker = [&]() {
+        for (;;) {
+            const uint32_t c = next.fetch_add(1);
+            if (c >= n_chunks) break;
+            Part& P = parts[c];
+            try {
+                for (uint32_t r = first + c * chunk; r < std::min(first + count, first + (c + 1) * chunk); ++r) {
+                    if (recs->flag[r] & 0x800) continue;  // supplementary records are skipped (:404)
+                    AlnRecord rec;
+                    rec.tid = recs->tid[r]; rec.pos = recs->pos[r]; rec.flag = recs->flag[r]; rec.mapq = recs->mapq[r];
+                    rec.cigar = decode_cigar(recs->cigar + recs->cigar_begin[r], uint32_t(recs->cigar_begin[r + 1] - recs->cigar_begin[r]));
+                    if (recs->sa_tag && recs->sa_tag[r]) { rec.has_sa = true; rec.sa = recs->sa_tag[r]; }
+                    P.segs.push_back(get_seq_order_read_split_segments(idx, rec));
+                    P.rec.push_back(r);
+                }
+            } catch (const Panic& p) { P.err = p.what(); }
+        }
+    };
+    const int nt = std::max(1, std::min<int>(n_threads, int(n_chunks)));
+    if (nt == 1) worker();
+    else { std::vector<std::thread> th; for (int t = 0; t < nt; ++t) th.emplace_back(worker); for (auto& t : th) t.join(); }
+    for (const auto& P : parts) if (!P.err.empty()) { g_pack_err = P.err; return PTL_ERR_INPUT; }
+    auto* pk = new ptl_oracle_packed();
+    pk->read_seg_begin.push_back(0);
+    for (const auto& P : parts)
+        for (size_t i = 0; i < P.rec.size(); ++i) {
+            const uint32_t r = P.rec[i];
+            pk->record_index.push_back(r);
+            pk->read_flag.push_back(recs->flag[r]); pk->read_mapq.push_back(recs->mapq[r]); pk->read_bin.push_back(recs->bin[r]);
+            pk->read_seq_len.push_back(recs->seq_len[r]); pk->read_seq_off.push_back(recs->seq_off[r]);
+            for (const auto& sg : P.segs[i]) {
+                pk->rseg_contig.push_back(uint32_t(sg.chrom_index)); pk->rseg_pos.push_back(sg.pos); pk->rseg_is_fwd.push_back(sg.is_fwd_strand);
+                pk->rseg_cigar_begin.push_back(pk->cigar.size()); pk->rseg_cigar_len.push_back(uint32_t(sg.cigar.size()));
+                for (const auto& c : sg.cigar) pk->cigar.push_back(encode(c));
+            }
+            pk->read_seg_begin.push_back(uint32_t(pk->rseg_contig.size()));
+        }
+    ptl_batch& b = pk->view;
+    b.n_reads = uint32_t(pk->read_flag.size());
+    b.read_flag = pk->read_flag.data(); b.read_mapq = pk->read_mapq.data(); b.read_bin = pk->read_bin.data();
+    b.read_seq_len = pk->read_seq_len.data(); b.read_seq_off = pk->read_seq_off.data(); b.read_seg_begin = pk->read_seg_begin.data();
+    b.n_read_segments = uint32_t(pk->rseg_contig.size());
+    b.rseg_contig = pk->rseg_contig.data(); b.rseg_pos = pk->rseg_pos.data(); b.rseg_is_fwd = pk->rseg_is_fwd.data();
+    b.rseg_cigar_begin = pk->rseg_cigar_begin.data(); b.rseg_cigar_len = pk->rseg_cigar_len.data();
+    b.cigar = pk->cigar.data(); b.n_cigar = pk->cigar.size();
+    b.seq4 = recs->seq4; b.seq4_bytes = recs->seq4_bytes;
+    *out = pk;
+    return PTL_OK;
+}
+void ptl_oracle_packed_view(const ptl_oracle_packed* p, ptl_batch* out) { *out = p->view; }
+const uint32_t* ptl_oracle_packed_record_index(const ptl_oracle_packed* p) { return p->record_index.data(); }
+void ptl_oracle_packed_free(ptl_oracle_packed* p) { delete p; }
+
 // SA:Z text, same contract as ptl_format_sa_tags.
 int ptl_oracle_format_sa_tags(const ptl_result* res, uint32_t n_chrom, const char* const* chrom_names, char* buf,
                               uint64_t cap, uint64_t* sa_begin, uint64_t* need) {

@@ -35,6 +35,7 @@ typedef struct ptl_synth_params {
     double read_clip_frac;         /* reads with a soft-clipped end */
     double read_sa_frac;           /* reads carrying 1-2 SA segments */
     uint32_t n_threads;            /* 0 = hardware concurrency */
+    uint32_t defer_reads;          /* 1: only PLAN the reads at creation (ptl_synth_plan_*); ptl_synth_generate_reads makes them */
 } ptl_synth_params;
 
 typedef struct ptl_synth ptl_synth;
@@ -54,6 +55,20 @@ void ptl_synth_contig_records(const ptl_synth* s, ptl_contig_records* out);
 void ptl_synth_read_records(const ptl_synth* s, ptl_read_records* out);
 /* As ptl_synth_create, but the big packed-bases pool is allocated with `alloc` (e.g. ptl_host_alloc for pinned memory). */
 ptl_synth* ptl_synth_create_into(const ptl_synth_params* p, void* (*alloc)(size_t), void (*dealloc)(void*));
+
+
+/* The read set is planned up front and generated on demand, so that a whole-genome set (6 M reads, 45 GB of packed bases)
+ * can be produced shard by shard: read i of the BAM order depends only on (seed, plan[i]).
+ * Plan = the reads in coordinate-sorted BAM order: contig index and record position (what assigns a read to one of the
+ * reference's (contig x <= 20 Mb window) work units, src/read_alignment_scanner.rs:403-406,508-534). */
+uint64_t ptl_synth_n_planned(const ptl_synth* s);
+const uint32_t* ptl_synth_plan_contig(const ptl_synth* s);
+const int64_t* ptl_synth_plan_pos(const ptl_synth* s);
+/* (Re)generate the read records of `n_ranges` ranges [first[i], first[i] + count[i]) of the BAM order, concatenated in
+ * the order given; replaces what ptl_synth_read_records returns (earlier views become invalid).  Returns 0 on success. */
+int ptl_synth_generate_reads(ptl_synth* s, uint32_t n_ranges, const uint64_t* first, const uint64_t* count);
+/* Contig lengths (the read->assembly BAM header). */
+const uint64_t* ptl_synth_contig_len(const ptl_synth* s);
 
 #ifdef __cplusplus
 }

@@ -335,7 +335,12 @@ struct ReadSeed { uint32_t contig; int64_t start; uint64_t id; };
 
 struct ptl_synth {
     ptl_synth_params P;
+    void* (*alloc)(size_t) = nullptr;
     void (*dealloc)(void*) = nullptr;
+    // read plan: every read of the set in BAM order (generated on demand)
+    std::vector<ReadSeed> seeds;
+    std::vector<uint32_t> plan_contig;
+    std::vector<int64_t> plan_pos;
     // reference
     std::vector<std::vector<uint8_t>> chroms;
     std::vector<uint64_t> chrom_len;
@@ -674,14 +679,15 @@ void gen_read(const ptl_synth& s, const ReadSeed& seed, ReadOut& out, PartOut& p
     out.bin = reg2bin(out.pos, std::max(end, out.pos + 1));
 }
 
-void make_reads(ptl_synth& s, uint32_t nt, void* (*alloc)(size_t)) {
+// The whole read set in coordinate-sorted BAM order: sample loci, sort (a read's record position is its sampled start).
+void plan_reads(ptl_synth& s) {
     const auto& P = s.P;
     const uint64_t n = P.n_reads;
-    // sample loci, sort like a coordinate-sorted BAM
     std::vector<double> cum(s.contigs.size());
     double tot = 0;
     for (size_t i = 0; i < s.contigs.size(); ++i) { tot += double(s.contigs[i].C.size()); cum[i] = tot; }
-    std::vector<ReadSeed> seeds(n);
+    std::vector<ReadSeed>& seeds = s.seeds;
+    seeds.resize(n);
     {
         Rng rng(P.seed, 0x500000000ull);
         for (uint64_t i = 0; i < n; ++i) {
@@ -695,6 +701,18 @@ void make_reads(ptl_synth& s, uint32_t nt, void* (*alloc)(size_t)) {
     std::sort(seeds.begin(), seeds.end(), [](const ReadSeed& a, const ReadSeed& b) {
         return a.contig != b.contig ? a.contig < b.contig : (a.start != b.start ? a.start < b.start : a.id < b.id);
     });
+    s.plan_contig.resize(n);
+    s.plan_pos.resize(n);
+    for (uint64_t i = 0; i < n; ++i) { s.plan_contig[i] = seeds[i].contig; s.plan_pos[i] = seeds[i].start; }
+}
+
+// Generate the reads of the given ranges of the plan (concatenated) into the flat read-record arrays.
+void make_reads(ptl_synth& s, uint32_t nt, const std::vector<std::pair<uint64_t, uint64_t>>& ranges) {
+    std::vector<uint64_t> pick;  // plan index of every generated read
+    for (const auto& r : ranges)
+        for (uint64_t i = r.first; i < r.first + r.second; ++i) pick.push_back(i);
+    const uint64_t n = pick.size();
+    const std::vector<ReadSeed>& seeds = s.seeds;
     // generate in chunks
     const uint64_t chunk = 2048;
     const uint64_t n_chunks = (n + chunk - 1) / chunk;
@@ -705,15 +723,17 @@ void make_reads(ptl_synth& s, uint32_t nt, void* (*alloc)(size_t)) {
         std::vector<uint64_t> seq_bytes;
     };
     std::vector<Chunk> chunks(n_chunks);
-    s.rr_tid.resize(n); s.rr_pos.resize(n); s.rr_flag.resize(n); s.rr_bin.resize(n); s.rr_mapq.resize(n);
-    s.rr_seq_len.resize(n); s.rr_seq_off.resize(n); s.rr_cigar_begin.resize(n + 1); s.rr_sa_s.resize(n); s.rr_sa.assign(n, nullptr);
+    if (s.rr_seq4 && s.dealloc) s.dealloc(s.rr_seq4);
+    s.rr_seq4 = nullptr;
+    s.rr_tid.assign(n, 0); s.rr_pos.assign(n, 0); s.rr_flag.assign(n, 0); s.rr_bin.assign(n, 0); s.rr_mapq.assign(n, 0);
+    s.rr_seq_len.assign(n, 0); s.rr_seq_off.assign(n, 0); s.rr_cigar_begin.assign(n + 1, 0); s.rr_sa_s.assign(n, std::string()); s.rr_sa.assign(n, nullptr);
     parallel_for(n_chunks, nt, [&](uint64_t ci) {
         Chunk& ch = chunks[ci];
         ReadOut ro;
         PartOut p0, p1;
         const uint64_t r0 = ci * chunk, r1 = std::min(n, r0 + chunk);
         for (uint64_t r = r0; r < r1; ++r) {
-            gen_read(s, seeds[r], ro, p0, p1);
+            gen_read(s, seeds[pick[r]], ro, p0, p1);
             s.rr_tid[r] = ro.tid; s.rr_pos[r] = ro.pos; s.rr_flag[r] = ro.flag; s.rr_bin[r] = ro.bin; s.rr_mapq[r] = ro.mapq;
             const uint32_t L = uint32_t(ro.bases.size());
             s.rr_seq_len[r] = L;
@@ -736,7 +756,7 @@ void make_reads(ptl_synth& s, uint32_t nt, void* (*alloc)(size_t)) {
         cig_base[c + 1] = cig_base[c] + chunks[c].cigar.size();
     }
     s.rr_seq4_bytes = seq_base[n_chunks];
-    s.rr_seq4 = static_cast<uint8_t*>(alloc(std::max<uint64_t>(s.rr_seq4_bytes, 16)));
+    s.rr_seq4 = static_cast<uint8_t*>(s.alloc(std::max<uint64_t>(s.rr_seq4_bytes, 16)));
     s.rr_cigar.resize(cig_base[n_chunks]);
     parallel_for(n_chunks, nt, [&](uint64_t c) {
         Chunk& ch = chunks[c];
@@ -756,6 +776,8 @@ void make_reads(ptl_synth& s, uint32_t nt, void* (*alloc)(size_t)) {
     s.rr_cigar_begin[n] = cig_base[n_chunks];
     for (uint64_t r = 0; r < n; ++r) if (!s.rr_sa_s[r].empty()) s.rr_sa[r] = s.rr_sa_s[r].c_str();
 }
+
+uint32_t thread_count(const ptl_synth_params& P) { return P.n_threads ? P.n_threads : std::max(1u, std::thread::hardware_concurrency()); }
 
 }  // namespace
 
@@ -791,6 +813,7 @@ ptl_synth* ptl_synth_create_into(const ptl_synth_params* p, void* (*alloc)(size_
     if (!p || !p->n_chrom || p->chrom_len < 200000 || !p->haplotypes || !p->contigs_per_chrom) return nullptr;
     auto* s = new ptl_synth();
     s->P = *p;
+    s->alloc = alloc;
     s->dealloc = dealloc;
     uint32_t nt = p->n_threads ? p->n_threads : std::max(1u, std::thread::hardware_concurrency());
     for (uint32_t c = 0; c < p->n_chrom; ++c) s->chrom_name_s.push_back("chr" + std::to_string(c + 1));
@@ -837,7 +860,8 @@ ptl_synth* ptl_synth_create_into(const ptl_synth_params* p, void* (*alloc)(size_
         s->chrom_ptr.push_back(s->chroms[c].data());
         s->chrom_name.push_back(s->chrom_name_s[c].c_str());
     }
-    make_reads(*s, nt, alloc);
+    plan_reads(*s);
+    if (!p->defer_reads) make_reads(*s, nt, {{0, p->n_reads}});
     return s;
 }
 ptl_synth* ptl_synth_create(const ptl_synth_params* p) { return ptl_synth_create_into(p, std::malloc, std::free); }
@@ -868,6 +892,23 @@ void ptl_synth_contig_records(const ptl_synth* s, ptl_contig_records* o) {
     o->contig_names = s->contig_name.data();
     o->n_ref_chrom = uint32_t(s->chroms.size());
     o->ref_chrom_names = s->chrom_name.data();
+}
+uint64_t ptl_synth_n_planned(const ptl_synth* s) { return s->seeds.size(); }
+const uint32_t* ptl_synth_plan_contig(const ptl_synth* s) { return s->plan_contig.data(); }
+const int64_t* ptl_synth_plan_pos(const ptl_synth* s) { return s->plan_pos.data(); }
+const uint64_t* ptl_synth_contig_len(const ptl_synth* s) { return s->contig_len.data(); }
+int ptl_synth_generate_reads(ptl_synth* s, uint32_t n_ranges, const uint64_t* first, const uint64_t* count) {
+    if (!s || (n_ranges && (!first || !count))) return 1;
+    std::vector<std::pair<uint64_t, uint64_t>> ranges;
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < n_ranges; ++i) {
+        if (first[i] > s->seeds.size() || count[i] > s->seeds.size() - first[i]) return 1;
+        ranges.emplace_back(first[i], count[i]);
+        total += count[i];
+    }
+    if (total > 0xffffffffull) return 1;
+    make_reads(*s, thread_count(s->P), ranges);
+    return 0;
 }
 void ptl_synth_read_records(const ptl_synth* s, ptl_read_records* o) {
     o->n_reads = uint32_t(s->rr_tid.size());

@@ -27,9 +27,10 @@ class Unit:
     n_reads: int
 
 
-def window_units(contig_len, read_tid, read_pos, segment_size: int = SEGMENT_SIZE) -> List[Unit]:
-    """Split every contig into the reference's windows and locate each window's records (sorted input)."""
-    L = lib.load()
+def window_units(contig_len, read_tid, read_pos, segment_size: int = SEGMENT_SIZE, region_segments=None) -> List[Unit]:
+    """Split every contig into the reference's windows and locate each window's records (sorted input).
+    `region_segments(size, segment_size) -> [(begin, end)]` defaults to the product's ptl_region_segments."""
+    region_segments = region_segments or lib.load().region_segments
     read_tid = np.asarray(read_tid, dtype=np.int64)
     read_pos = np.asarray(read_pos, dtype=np.int64)
     key = read_tid * (1 << 40) + read_pos
@@ -38,7 +39,7 @@ def window_units(contig_len, read_tid, read_pos, segment_size: int = SEGMENT_SIZ
     for c, clen in enumerate(contig_len):
         if int(clen) == 0:
             continue
-        for b, e in L.region_segments(int(clen), segment_size):
+        for b, e in region_segments(int(clen), segment_size):
             lo = int(np.searchsorted(key, c * (1 << 40) + b, side="left"))
             hi = int(np.searchsorted(key, c * (1 << 40) + e, side="left"))
             units.append(Unit(c, b, e, lo, hi - lo))
@@ -48,3 +49,11 @@ def window_units(contig_len, read_tid, read_pos, segment_size: int = SEGMENT_SIZ
 def assign(units: List[Unit], n_ranks: int) -> np.ndarray:
     """owner[i] = rank that lifts unit i (LPT on read counts; deterministic)."""
     return lib.load().shard_units([max(u.n_reads, 0) for u in units], n_ranks)
+
+
+def rank_ranges(units: List[Unit], owner, rank: int):
+    """The record ranges [(first_read, n_reads), ...] of the units `rank` owns, in unit order (= the order in which the
+    host concatenates results: the reference's record order), and the global index of every record of the shard."""
+    ranges = [(u.first_read, u.n_reads) for ui, u in enumerate(units) if int(owner[ui]) == rank and u.n_reads > 0]
+    gri = np.concatenate([np.arange(a, a + n, dtype=np.int64) for a, n in ranges]) if ranges else np.zeros(0, np.int64)
+    return ranges, gri

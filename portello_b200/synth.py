@@ -18,6 +18,7 @@ class SynthParams(C.Structure):
         ("junction_per_mb", C.c_double), ("n_reads", C.c_uint64), ("read_len_mean", C.c_double), ("read_len_sd", C.c_double),
         ("read_len_min", C.c_uint32), ("read_len_max", C.c_uint32), ("read_sub_rate", C.c_double), ("read_indel_rate", C.c_double),
         ("read_cluster_frac", C.c_double), ("read_clip_frac", C.c_double), ("read_sa_frac", C.c_double), ("n_threads", C.c_uint32),
+        ("defer_reads", C.c_uint32),
     ]
 
 
@@ -50,6 +51,16 @@ def _load():
         d.ptl_synth_contig_names.argtypes = [C.c_void_p]
         d.ptl_synth_contig_records.argtypes = [C.c_void_p, C.POINTER(ContigRecordsC)]
         d.ptl_synth_read_records.argtypes = [C.c_void_p, C.POINTER(ReadRecordsC)]
+        d.ptl_synth_n_planned.restype = C.c_uint64
+        d.ptl_synth_n_planned.argtypes = [C.c_void_p]
+        d.ptl_synth_plan_contig.restype = C.POINTER(C.c_uint32)
+        d.ptl_synth_plan_contig.argtypes = [C.c_void_p]
+        d.ptl_synth_plan_pos.restype = C.POINTER(C.c_int64)
+        d.ptl_synth_plan_pos.argtypes = [C.c_void_p]
+        d.ptl_synth_contig_len.restype = u64p
+        d.ptl_synth_contig_len.argtypes = [C.c_void_p]
+        d.ptl_synth_generate_reads.restype = C.c_int
+        d.ptl_synth_generate_reads.argtypes = [C.c_void_p, C.c_uint32, u64p, u64p]
         _dll = d
     return _dll
 
@@ -73,6 +84,11 @@ WORKLOADS = {
     "stress": dict(seed=5005, n_chrom=1, chrom_len=8_000_000, haplotypes=2, contigs_per_chrom=40, junction_per_mb=6.0,
                    sv_per_mb=6.0, rev_contig_frac=0.5, n_reads=20_000, read_len_mean=100_000, read_len_sd=15_000,
                    read_len_min=20_000, read_len_max=150_000, read_indel_rate=5e-3, read_cluster_frac=0.3, read_sa_frac=0.1),
+    # configs[4] at the size SURVEY.md §8d states: 64 Mb reference, ~2000 contigs of 20-200 kb (two haplotypes, random cuts), half of
+    # them reverse-strand, 200k x 100 kb reads (cut at contig ends), indel rate 5e-3 with 30 % adjacent I/D clusters, 10 % with SA
+    "stress_full": dict(seed=5005, n_chrom=1, chrom_len=64_000_000, haplotypes=2, contigs_per_chrom=1000, junction_per_mb=20.0,
+                        sv_per_mb=6.0, rev_contig_frac=0.5, n_reads=200_000, read_len_mean=100_000, read_len_sd=15_000,
+                        read_len_min=20_000, read_len_max=150_000, read_indel_rate=5e-3, read_cluster_frac=0.3, read_sa_frac=0.1),
 }
 
 
@@ -108,6 +124,34 @@ class Synth:
         d.ptl_synth_contig_records(self.h, C.byref(self.contig_records))
         self.read_records = ReadRecordsC()
         d.ptl_synth_read_records(self.h, C.byref(self.read_records))
+
+    # ---- the planned read set (BAM order) and shard-wise generation
+    def plan(self):
+        """(contig index, record position) of EVERY read of the set in coordinate-sorted BAM order (numpy views)."""
+        import numpy as np
+
+        d = _load()
+        n = int(d.ptl_synth_n_planned(self.h))
+        if n == 0:
+            return np.zeros(0, np.uint32), np.zeros(0, np.int64)
+        return np.ctypeslib.as_array(d.ptl_synth_plan_contig(self.h), (n,)), np.ctypeslib.as_array(d.ptl_synth_plan_pos(self.h), (n,))
+
+    def contig_lengths(self):
+        import numpy as np
+
+        return np.ctypeslib.as_array(_load().ptl_synth_contig_len(self.h), (self.n_contigs,))
+
+    def generate_reads(self, ranges):
+        """Generate the reads of `ranges` = [(first, count), ...] of the BAM order (concatenated); self.read_records then
+        views them (the previous read records are released)."""
+        import numpy as np
+
+        first = np.ascontiguousarray([r[0] for r in ranges], np.uint64)
+        count = np.ascontiguousarray([r[1] for r in ranges], np.uint64)
+        rc = _load().ptl_synth_generate_reads(self.h, len(ranges), first.ctypes.data_as(u64p), count.ctypes.data_as(u64p))
+        if rc != 0:
+            raise ValueError("ptl_synth_generate_reads: range outside the planned read set")
+        _load().ptl_synth_read_records(self.h, C.byref(self.read_records))
 
     def reference_arrays(self):
         """The chromosomes as borrowed numpy uint8 views (valid while this object lives)."""

@@ -66,6 +66,13 @@ class OracleLib(LiftLib):
         d.ptl_oracle_split_segments.restype = C.c_int
         d.ptl_oracle_split_segments.argtypes = [C.c_uint32, C.POINTER(C.c_char_p), C.c_int32, C.c_int64, C.c_uint16, C.c_uint8, u32p, C.c_uint32, C.c_char_p, C.c_uint32, C.c_uint32, C.POINTER(SplitSegmentsC), u32p, u32p]
         d.ptl_oracle_split_last_error.restype = C.c_char_p
+        d.ptl_oracle_pack_batch.restype = C.c_int
+        d.ptl_oracle_pack_batch.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_char_p), C.c_int, C.POINTER(C.c_void_p)]
+        d.ptl_oracle_packed_view.argtypes = [C.c_void_p, C.POINTER(abi.BatchC)]
+        d.ptl_oracle_packed_record_index.restype = C.POINTER(C.c_uint32)
+        d.ptl_oracle_packed_record_index.argtypes = [C.c_void_p]
+        d.ptl_oracle_packed_free.argtypes = [C.c_void_p]
+        d.ptl_oracle_pack_last_error.restype = C.c_char_p
         d.ptl_oracle_format_sa_tags.restype = C.c_int
         d.ptl_oracle_format_sa_tags.argtypes = [C.POINTER(ResultC), C.c_uint32, C.POINTER(C.c_char_p), C.c_char_p, C.c_uint64, u64p, u64p]
 
@@ -221,6 +228,35 @@ def split_segments_call(fn, errfn, names, tid, pos, flag, mapq, cigar, sa, cap_s
 
 
 _lib = None
+
+
+class OraclePackedBatch:
+    """The oracle's own record-loop head (skip supplementary, get_seq_order_read_split_segments): records -> ptl_batch.
+    Lets the CPU arm of the bench run without the product library."""
+
+    def __init__(self, recs_c, first, count, contig_names, threads=1):
+        self.O = load()
+        self.h = C.c_void_p()
+        names = (C.c_char_p * max(len(contig_names), 1))(*[n.encode() for n in contig_names])
+        rc = self.O.dll.ptl_oracle_pack_batch(C.byref(recs_c), first, count, len(contig_names), names, threads, C.byref(self.h))
+        if rc != 0:
+            raise abi.PtlError(rc, self.O.dll.ptl_oracle_pack_last_error().decode())
+        self.c = abi.BatchC()
+        self.O.dll.ptl_oracle_packed_view(self.h, C.byref(self.c))
+        self.c._owner = self
+        self._recs = recs_c
+
+    def record_index(self):
+        p = self.O.dll.ptl_oracle_packed_record_index(self.h)
+        return np.ctypeslib.as_array(p, (self.c.n_reads,)).copy() if self.c.n_reads else np.zeros(0, np.uint32)
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.O.dll.ptl_oracle_packed_free(self.h)
+                self.h = C.c_void_p()
+        except Exception:
+            pass
 
 
 def load() -> OracleLib:

@@ -230,3 +230,76 @@ def test_malformed_batches_are_rejected_not_dereferenced():
         assert e.value.code == abi.PTL_ERR_INVALID_ARG, what
     ok = helpers.lift_c(gctx, helpers.pack(s).c)
     assert ok.diff(helpers.lift_c(helpers.oracle_context(s), helpers.pack(s).c)) is None
+
+
+def _full_digest_parity(s, chunk, threads=16, windows=True):
+    """100 % of the records of `s`, chunk by chunk over two slots: digest of the CUDA result == digest of the oracle's
+    (the reference's own whole-run assertion is per pair, src/read_alignment_scanner.rs:204-229; this is per record)."""
+    from portello_b200.digest import Digest
+    n = s.read_records.n_reads
+    gctx = helpers.gpu_context(s, n_slots=2)
+    octx = helpers.oracle_context(s, threads=threads)
+    segs = gctx.get_contig_segments() if windows else None
+    dg, do = Digest(), Digest()
+    n_pairs = n_lifted = 0
+    for a in range(0, n, chunk):
+        pb = helpers.pack(s, a, min(chunk, n - a), windows=segs)
+        sb = np.ctypeslib.as_array(pb.c.read_seg_begin, (pb.c.n_reads + 1,))
+        gri = np.arange(a, a + pb.c.n_reads)
+        gctx.submit_c(pb.c, 0)
+        ro = helpers.lift_c(octx, pb.c)
+        rg = abi.Result.from_c(gctx.wait_c(0), copy=False)
+        assert rg.n_errors == 0 and ro.n_errors == 0
+        dg.add(rg, sb, gri)
+        do.add(ro, sb, gri)
+        assert dg == do, f"chunk at read {a}: CUDA {dg.hex()} != oracle {do.hex()}"
+        n_pairs += rg.n_pairs
+        n_lifted += rg.n_lifted
+    assert dg.n_reads == n and n_lifted > 0.9 * n
+    return dg, n_pairs
+
+
+def test_whole_genome_config_full_digest_parity():
+    """BASELINE.json configs[2] shape (24 x 130 Mb, ~1000 contigs -> ~2200 segments, 45 % reverse-strand), 2,000,000 reads:
+    every record of every read against the oracle."""
+    s = synth.make("wg", n_reads=2_000_000)
+    dg, n_pairs = _full_digest_parity(s, 250_000)
+    assert n_pairs >= 2_000_000
+
+
+def test_stress_config_full_scale_full_digest_parity():
+    """BASELINE.json configs[4] at the stated size: 64 Mb, ~2000 contigs, 200,000 reads of up to 100 kb with
+    dense clustered indels and SA segments: every record against the oracle."""
+    s = synth.make("stress_full")
+    assert s.n_contigs >= 1500
+    dg, n_pairs = _full_digest_parity(s, 50_000)
+    assert n_pairs >= 200_000
+
+
+def test_two_host_threads_drive_two_slots():
+    """include/portello_b200.h: distinct slots may be driven from distinct host threads.  Two threads, one slot each,
+    interleaved batches of different shapes; every result must equal the single-threaded one."""
+    import threading
+    s = synth.make("tiny", seed=31, n_reads=8000)
+    gctx = helpers.gpu_context(s, n_slots=2)
+    packs = [helpers.pack(s, a, n) for a, n in ((0, 3000), (3000, 500), (3500, 2500), (6000, 2000), (100, 4000), (7000, 1000))]
+    want = [helpers.lift_c(gctx, p.c) for p in packs]
+    l0 = gctx.launch_count()
+    errors, got = [], {}
+
+    def worker(slot):
+        try:
+            for rep in range(4):
+                for i in range(slot, len(packs), 2):
+                    got[(slot, rep, i)] = helpers.lift_c(gctx, packs[i].c, slot=slot)
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    th = [threading.Thread(target=worker, args=(k,)) for k in (0, 1)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errors, errors
+    for (slot, rep, i), r in got.items():
+        assert r.diff(want[i]) is None, (slot, rep, i)
+    per_batch = (gctx.launch_count() - l0) / (4 * len(packs))
+    assert per_batch == int(per_batch) and per_batch > 5  # the launch counter is atomic: no lost increments
