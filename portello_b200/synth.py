@@ -84,9 +84,9 @@ WORKLOADS = {
     "stress": dict(seed=5005, n_chrom=1, chrom_len=8_000_000, haplotypes=2, contigs_per_chrom=40, junction_per_mb=6.0,
                    sv_per_mb=6.0, rev_contig_frac=0.5, n_reads=20_000, read_len_mean=100_000, read_len_sd=15_000,
                    read_len_min=20_000, read_len_max=150_000, read_indel_rate=5e-3, read_cluster_frac=0.3, read_sa_frac=0.1),
-    # configs[4] at the size SURVEY.md §8d states: 64 Mb reference, ~2000 contigs of 20-200 kb (two haplotypes, random cuts), half of
+    # configs[4] at the size SURVEY.md §8d states: 64 Mb reference, ~1700 contigs (median 46 kb; two haplotypes, random cuts), half of
     # them reverse-strand, 200k x 100 kb reads (cut at contig ends), indel rate 5e-3 with 30 % adjacent I/D clusters, 10 % with SA
-    "stress_full": dict(seed=5005, n_chrom=1, chrom_len=64_000_000, haplotypes=2, contigs_per_chrom=1000, junction_per_mb=20.0,
+    "stress_full": dict(seed=5005, n_chrom=1, chrom_len=64_000_000, haplotypes=2, contigs_per_chrom=1600, junction_per_mb=20.0,
                         sv_per_mb=6.0, rev_contig_frac=0.5, n_reads=200_000, read_len_mean=100_000, read_len_sd=15_000,
                         read_len_min=20_000, read_len_max=150_000, read_indel_rate=5e-3, read_cluster_frac=0.3, read_sa_frac=0.1),
 }

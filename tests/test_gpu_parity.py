@@ -271,7 +271,7 @@ def test_stress_config_full_scale_full_digest_parity():
     """BASELINE.json configs[4] at the stated size: 64 Mb, ~2000 contigs, 200,000 reads of up to 100 kb with
     dense clustered indels and SA segments: every record against the oracle."""
     s = synth.make("stress_full")
-    assert s.n_contigs >= 1500
+    assert 1500 <= s.n_contigs <= 2200
     dg, n_pairs = _full_digest_parity(s, 50_000)
     assert n_pairs >= 200_000
 
