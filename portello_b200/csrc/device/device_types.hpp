@@ -101,14 +101,24 @@ struct DevWork {
     uint64_t* pair_out_off = nullptr;    // where the final ops of the pair start in scratch
     uint32_t* simplify_list = nullptr;   // [pair_cap] pairs whose lifted CIGAR needs simplify_alignment_indels
     uint32_t* long_list = nullptr;       // [pair_cap] pairs whose liftover runs warp-cooperatively (status ST_PENDING_LIFT)
+    uint32_t* pair_order = nullptr;      // [pair_cap] work order of lift_pairs_kernel (pair_order_kernel)
     uint32_t long_ops = 64;              // a pair with more CIGAR ops than this goes to long_list
-    // scratch op slots
+    // scratch op slots, followed in the same allocation by the dense output region of the lift kernel: tile t (32 pairs)
+    // of lift_pairs_kernel owns scratch[dense_off + t * kLiftTileOut, + kLiftTileOut) and packs the lifted CIGARs of its
+    // pairs there back to back (pair_out_off is an offset into `scratch` either way)
     uint64_t scratch_cap = 0;            // in ops
     uint32_t* scratch = nullptr;
+    uint64_t dense_off = 0;              // in ops
     // per read
     uint2* read_counts = nullptr;        // [n_reads+1] (.x records, .y ops) -> exclusive scan
     uint32_t* read_primary = nullptr;    // pair index chosen as primary, ~0 if none lifted
 };
+
+// lift_pairs_kernel: the dense output region of a tile of 32 pairs, in ops
+#ifndef LIFT_TILE_OUT
+#define LIFT_TILE_OUT 1536
+#endif
+constexpr uint32_t kLiftTileOut = LIFT_TILE_OUT;
 
 // ---- results of one batch: ONE compact arena (device), copied to the host with a single DMA ------------------------
 // [header: DevTotals, 128 B][read_rec_begin][rec_cigar_begin][rec_pos][rec_read_segment][rec_contig_segment][rec_tid]

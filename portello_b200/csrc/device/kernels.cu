@@ -229,33 +229,131 @@ __global__ void __launch_bounds__(128) pair_fill_kernel(DevStatic S, DevBatch B,
     if (s < B.n_rsegs) pair_fill_body(S, B, W, s);
 }
 
-// a4 + a5 + a6 + a8: one thread per pair; the stages are warp-collective (all 32 lanes enter).
-#ifndef LIFT_BLOCK
-#define LIFT_BLOCK 128
+// Work order of the lift kernel.  A warp of lift_pairs_kernel runs as long as its longest lane (natural order: 38 events
+// for a mean of 22, ncu r04a: 15 of 32 lanes active), so the pairs of every group of kOrderGroup CONSECUTIVE pairs
+// (adjacent CIGARs and overlapping table ranges: they stay hot in L2 and mostly in one L1) are bucket-sorted by work
+// (strand of the contig segment, CIGAR length) and handed to the lift kernel as tiles of 32 pairs of near-equal length.
+// Each tile is its own 32-thread block there, so a short tile gives its SM slot back as soon as it is done (sorting the
+// warps of a 128-thread block changed nothing: the block lives as long as its longest warp; sorting the whole batch cost
+// the L1 locality, profiles/r03a).
+#ifndef LIFT_SORT
+#define LIFT_SORT 1
+#endif
+#ifndef LIFT_ORDER_GROUP
+#define LIFT_ORDER_GROUP 512
+#endif
+constexpr uint32_t kOrderGroup = LIFT_ORDER_GROUP;
+constexpr uint32_t kOrderBuckets = 64;  // (reverse strand ? 32 : 0) + min(ops / 2, 31); parked / trivial pairs in bucket 0
+__global__ void __launch_bounds__(256) pair_order_kernel(DevStatic S, DevBatch B, DevWork W, const DevTotals* T) {
+    __shared__ uint32_t hist[kOrderBuckets];
+    const uint32_t n_pairs = min(uint32_t(T->n_pairs), W.pair_cap);
+    const uint32_t base = blockIdx.x * kOrderGroup;
+    if (base >= n_pairs) return;
+    const uint32_t cnt = min(kOrderGroup, n_pairs - base);
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    if (threadIdx.x < kOrderBuckets) hist[threadIdx.x] = 0u;
+    __syncthreads();
+    constexpr uint32_t kPer = kOrderGroup / 256;
+    uint32_t key[kPer], rank[kPer];
+#pragma unroll
+    for (uint32_t k = 0; k < kPer; ++k) {
+        const uint32_t i = threadIdx.x + k * 256u;
+        key[k] = 0u;
+        rank[k] = 0u;
+        if (i < cnt) {
+            const uint32_t n = B.rseg_cigar_len[W.pair_rseg[base + i]];
+            const bool rev = S.seg_is_fwd[W.pair_seg[base + i]] == 0;
+            key[k] = (n > W.long_ops) ? 0u : (rev ? 32u : 0u) + min(n >> 1, 31u);
+            rank[k] = atomicAdd(&hist[key[k]], 1u);
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {  // exclusive prefix over the buckets in DESCENDING key order: lane owns keys 63 - lane and 31 - lane
+        const uint32_t hi = hist[63u - lane], lo = hist[31u - lane];
+        uint32_t inc_hi = hi, inc_lo = lo;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t a = __shfl_up_sync(FULL, inc_hi, d), b2 = __shfl_up_sync(FULL, inc_lo, d);
+            if (int(lane) >= d) { inc_hi += a; inc_lo += b2; }
+        }
+        const uint32_t total_hi = __shfl_sync(FULL, inc_hi, 31);
+        hist[63u - lane] = inc_hi - hi;
+        hist[31u - lane] = total_hi + inc_lo - lo;
+    }
+    __syncthreads();
+#pragma unroll
+    for (uint32_t k = 0; k < kPer; ++k) {
+        const uint32_t i = threadIdx.x + k * 256u;
+        if (i < cnt) W.pair_order[base + hist[key[k]] + rank[k]] = base + i;
+    }
+}
+
+// a4 + a5 + a6 + a8: one thread per pair, one warp (= one block) per tile of 32 pairs; the stages are warp-collective.
+// The lifted CIGARs of a tile are written to a shared-memory pool (StagePool), then moved by the warp, as one flat index
+// space with coalesced stores, into the tile's dense output region: the thread-private, 7x-sparse scratch slots are no
+// longer written for them (ncu r04a: DRAM traffic 2.6x the algorithmic bytes), and the record emission reads dense CIGARs.
+#ifndef LIFT_STAGE_WORDS
+#define LIFT_STAGE_WORDS 1024  // shared-memory words per tile for the staged outputs (32 per lane)
 #endif
 #ifndef LIFT_MIN_BLOCKS
-#define LIFT_MIN_BLOCKS 8  // 64 registers, 32 warps per SM (sweep in profiles/: 8 -> 0.558 ms, 1 -> 0.579 ms, 12 spills)
+#define LIFT_MIN_BLOCKS 32  // 64 registers: 32 tiles per SM
 #endif
 template <bool kAllStages>
-__global__ void __launch_bounds__(LIFT_BLOCK, LIFT_MIN_BLOCKS) lift_pairs_kernel(DevStatic S, DevBatch B, DevWork W, DevTotals* T, uint32_t stage_mask) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(32, LIFT_MIN_BLOCKS) lift_pairs_kernel(DevStatic S, DevBatch B, DevWork W, DevTotals* T, uint32_t stage_mask) {
+    __shared__ uint32_t stage_pool[LIFT_STAGE_WORDS ? LIFT_STAGE_WORDS : 1];
     const uint32_t n_pairs = min(uint32_t(T->n_pairs), W.pair_cap);
-    if (i == 0) T->scratch_needed = W.pair_slot_begin[n_pairs];  // total op slots of the batch (capacity feedback)
-    if (blockIdx.x * blockDim.x >= n_pairs) return;  // (block-uniform; the grid covers the pair capacity)
+    if (blockIdx.x == 0 && threadIdx.x == 0) T->scratch_needed = W.pair_slot_begin[n_pairs];  // total op slots of the batch (capacity feedback)
+    const uint32_t i = blockIdx.x * 32u + threadIdx.x;
+    if (blockIdx.x * 32u >= n_pairs) return;  // (block-uniform; the grid covers the pair capacity)
+    const uint32_t lane = threadIdx.x;
     const bool valid = i < n_pairs;
-    // natural pair order: the lanes of a warp own consecutive read segments, whose CIGARs are adjacent in the pool and
-    // whose table ranges overlap (a work-sorted order ran 33 % slower: L1 hit rate 77 % -> 54 %, profiles/r03a; ranking only
-    // the pairs of a block by work changed nothing at 128 threads and lost 5-12 % at 256-512)
-    const uint32_t p = valid ? i : 0u;
+    const uint32_t p = valid ? (LIFT_SORT ? W.pair_order[i] : i) : 0u;
     uint32_t a = 0, b = 0;
-    lift_pair_body<kAllStages>(S, B, W, T, p, valid, stage_mask, a, b);
+    const StagePool stage{LIFT_STAGE_WORDS ? stage_pool : nullptr, LIFT_STAGE_WORDS};
+    const LiftOut out = lift_pair_body<kAllStages>(S, B, W, T, p, valid, stage_mask, a, b, stage);
+    // ---- staged outputs of the tile -> its dense region (coalesced), or the pairs' own slots if it does not fit
+    if (__any_sync(FULL, out.staged)) {
+        const uint32_t n = out.staged ? out.n : 0u;
+        uint32_t incl = n;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(FULL, incl, d);
+            if (int(lane) >= d) incl += o;
+        }
+        const uint32_t total = __shfl_sync(FULL, incl, 31);
+        const uint32_t excl = incl - n;
+        const uint64_t dense_at = W.dense_off + uint64_t(blockIdx.x) * kLiftTileOut;
+        if (total <= kLiftTileOut) {
+            if (out.staged) W.pair_out_off[p] = dense_at + excl;
+            const uint32_t src_off = out.staged ? uint32_t(out.src - stage.pool) : 0u;
+            uint32_t* const dense = W.scratch + dense_at;
+            __syncwarp();
+            for (uint32_t j0 = 0; j0 < total; j0 += 32u) {
+                const uint32_t j = j0 + lane;
+                uint32_t lo = 0, hi = 31;  // owner = last lane whose exclusive prefix <= j
+#pragma unroll
+                for (int it = 0; it < 5; ++it) {
+                    const uint32_t mid = (lo + hi + 1u) >> 1;
+                    const uint32_t ex_mid = __shfl_sync(FULL, excl, mid);
+                    if (ex_mid <= j) lo = mid; else hi = mid - 1u;
+                }
+                const uint32_t s2 = __shfl_sync(FULL, src_off, lo);
+                const uint32_t e2 = __shfl_sync(FULL, excl, lo);
+                if (j < total) dense[j] = stage.pool[s2 + (j - e2)];
+            }
+        } else if (out.staged) {  // (a tile of long CIGARs)
+            uint32_t* dst = W.scratch + out.slot0;
+            for (uint32_t j = 0; j < n; ++j) dst[j] = out.src[j];
+            W.pair_out_off[p] = out.slot0;
+        }
+    }
     // roofline arithmetic: input ops walked + base bytes compared (warp-aggregated atomics)
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
         a += __shfl_down_sync(FULL, a, d);
         b += __shfl_down_sync(FULL, b, d);
     }
-    if ((threadIdx.x & 31) == 0) {
+    if (lane == 0) {
         if (a) atomicAdd(&T->n_in_ops, (unsigned long long)a);
         if (b) atomicAdd(&T->n_base_bytes, (unsigned long long)b);
     }
@@ -268,9 +366,12 @@ __global__ void __launch_bounds__(LIFT_BLOCK, LIFT_MIN_BLOCKS) lift_pairs_kernel
 #ifndef LIFT_LONG_MIN_BLOCKS
 #define LIFT_LONG_MIN_BLOCKS 6  // 80 registers, no spills (sweep on the stress workload: 4 -> 1.50 ms, 6 -> 1.43 ms, 8 spills -> 1.37 ms)
 #endif
+#ifndef SIMPLIFY_THREAD
+#define SIMPLIFY_THREAD 1  // 1: the simplify worklist runs one thread per pair (simplify_pairs_kernel); 0: one warp per pair, in warp_pairs_kernel
+#endif
 __global__ void __launch_bounds__(128, LIFT_LONG_MIN_BLOCKS) warp_pairs_kernel(DevStatic S, DevBatch B, DevWork W, DevTotals* T, uint32_t stage_mask) {
     const uint32_t n_long = min(T->n_long, W.pair_cap);
-    const uint32_t n_simp = ((stage_mask & 6u) == 6u) ? min(T->n_simplify, W.pair_cap) : 0u;  // (long pairs simplify inline)
+    const uint32_t n_simp = (!SIMPLIFY_THREAD && (stage_mask & 6u) == 6u) ? min(T->n_simplify, W.pair_cap) : 0u;  // (long pairs simplify inline)
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
@@ -278,6 +379,18 @@ __global__ void __launch_bounds__(128, LIFT_LONG_MIN_BLOCKS) warp_pairs_kernel(D
         if (t < n_long) lift_long_pair_body(S, B, W, T, W.long_list[t], lane, stage_mask);
         else simplify_warp_pair_body(S, B, W, T, W.simplify_list[t - n_long], lane);
     }
+}
+
+// a9 over the simplify worklist, one thread per listed pair (pair_bodies.cuh: simplify_thread_pair_body).
+__global__ void __launch_bounds__(128) simplify_pairs_kernel(DevStatic S, DevBatch B, DevWork W, DevTotals* T) {
+    const uint32_t n_simp = min(T->n_simplify, W.pair_cap);
+    if (blockIdx.x * blockDim.x >= n_simp) return;  // (block-uniform; the grid covers the pair capacity)
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t b = 0;
+    simplify_thread_pair_body(S, B, W, T, i, i < n_simp, b);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) b += __shfl_down_sync(FULL, b, d);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(&T->n_base_bytes, (unsigned long long)b);
 }
 
 // a10 (field part).  One thread per read.
@@ -421,14 +534,22 @@ void launch_lift(const DevStatic& S, const DevBatch& B, const DevWork& W, char* 
     ++*launches;
     // the pair count is only known on the device: scan / launch over the capacity, kernels clamp to n_pairs
     exclusive_scan_inplace<uint64_t>(W.pair_slot_begin, uint64_t(W.pair_cap) + 1, scan_tmp, scan_tmp_bytes_, st, launches, &T->n_pairs);
+    if (LIFT_SORT) {
+        pair_order_kernel<<<(W.pair_cap + kOrderGroup - 1) / kOrderGroup, 256, 0, st>>>(S, B, W, T);
+        ++*launches;
+    }
     mark(1);
-    if (stage_mask == 7u) lift_pairs_kernel<true><<<(W.pair_cap + LIFT_BLOCK - 1) / LIFT_BLOCK, LIFT_BLOCK, 0, st>>>(S, B, W, T, stage_mask);
-    else lift_pairs_kernel<false><<<(W.pair_cap + LIFT_BLOCK - 1) / LIFT_BLOCK, LIFT_BLOCK, 0, st>>>(S, B, W, T, stage_mask);
+    if (stage_mask == 7u) lift_pairs_kernel<true><<<(W.pair_cap + 31u) / 32u, 32, 0, st>>>(S, B, W, T, stage_mask);
+    else lift_pairs_kernel<false><<<(W.pair_cap + 31u) / 32u, 32, 0, st>>>(S, B, W, T, stage_mask);
     ++*launches;
     if ((stage_mask & 2u) || stage_mask == 1u) {
         const unsigned blocks = unsigned(std::min<uint64_t>((uint64_t(W.pair_cap) + 3) / 4, 148ull * 16));
         warp_pairs_kernel<<<blocks, 128, 0, st>>>(S, B, W, T, stage_mask);
         ++*launches;
+        if (SIMPLIFY_THREAD && (stage_mask & 6u) == 6u) {
+            simplify_pairs_kernel<<<(W.pair_cap + 127u) / 128u, 128, 0, st>>>(S, B, W, T);
+            ++*launches;
+        }
     }
     mark(2);
     read_finalize_kernel<<<(B.n_reads + 1 + 127) / 128, 128, 0, st>>>(S, B, W, T, do_finish);

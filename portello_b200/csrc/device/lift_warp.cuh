@@ -811,7 +811,9 @@ __device__ __forceinline__ void simplify_warp_pair_body(const DevStatic& S, cons
     const int64_t rpos = W.pair_pos[p];
     PairCounters cnt;
     WarpSink simp(buf_a, cap_a - 3u * n_clus_cap);
-    int status = warp_simplify(buf_b, W.pair_n_out[p], rpos, S.ref + S.chrom_off[chrom], S.chrom_off[chrom + 1] - S.chrom_off[chrom], read, buf_a,
+    // the lifted CIGAR: where lift_pairs_kernel left it (the pair's slot, or the dense region of its block)
+    const uint32_t* lifted = W.scratch + W.pair_out_off[p];
+    int status = warp_simplify(lifted, W.pair_n_out[p], rpos, S.ref + S.chrom_off[chrom], S.chrom_off[chrom + 1] - S.chrom_off[chrom], read, buf_a,
                                simp.cap, rec, n_clus_cap, simp, lane, cnt);
     simp.finish(lane);
     if (!status && simp.overflow) status = ST_ERR_CAPACITY;

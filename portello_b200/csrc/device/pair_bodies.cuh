@@ -161,9 +161,27 @@ __device__ __forceinline__ void pair_fill_body(const DevStatic& S, const DevBatc
 // Adds the pair's roofline counters (input ops walked, base bytes compared) to n_in_ops / n_base_bytes.
 // kAllStages: the production instantiation (stage_mask == PTL_STAGE_ALL); the stage-test paths (a stage switched off,
 // simplify inline, verbatim hand-back) compile away, which is worth registers in the hot kernel.
+//
+// Staging (the CUDA kernel only; `pool == nullptr` keeps every buffer in the pair's own scratch slot, which is what the
+// host emulation runs): the lifted CIGAR of the 32 pairs of a warp is written into a shared-memory pool, lanes taking
+// consecutive pieces of it sized by their slot bound (a warp scan); a pair whose piece does not fit keeps its global slot.
+// The caller then moves the staged outputs of the warp into a dense region with coalesced stores (LiftOut says where the
+// pair's final ops are), so that the record emission reads dense, adjacent CIGARs instead of 7x-sparse scratch slots.
+struct StagePool {
+    uint32_t* pool = nullptr;  // shared memory, one per warp
+    uint32_t words = 0;
+};
+struct LiftOut {
+    bool staged = false;            // the final ops sit in the pool: the caller must store them and set pair_out_off
+    uint32_t n = 0;                 // number of final ops (0 unless the pair was lifted here)
+    const uint32_t* src = nullptr;  // where they are (pool or slot)
+    uint64_t slot0 = 0;             // the pair's scratch slot (spill target), capacity cap_b ops
+    uint32_t cap_b = 0;
+};
 template <bool kAllStages>
-__device__ __forceinline__ void lift_pair_body(const DevStatic& S, const DevBatch& B, const DevWork& W, DevTotals* T, uint32_t p, bool valid,
-                                               uint32_t stage_mask_in, uint32_t& n_in_ops, uint32_t& n_base_bytes) {
+__device__ __forceinline__ LiftOut lift_pair_body(const DevStatic& S, const DevBatch& B, const DevWork& W, DevTotals* T, uint32_t p, bool valid,
+                                                  uint32_t stage_mask_in, uint32_t& n_in_ops, uint32_t& n_base_bytes,
+                                                  const StagePool stage = StagePool{}) {
     const uint32_t stage_mask = kAllStages ? 7u : stage_mask_in;
     PairCounters cnt;
     int status = ST_NONE, err = 0;
@@ -257,8 +275,24 @@ __device__ __forceinline__ void lift_pair_body(const DevStatic& S, const DevBatc
     // ---- a6: liftover (:179-183) + length check (:204-229).  The lifted CIGAR consumes exactly the read bases of the
     //      segment CIGAR (every read-consuming op is re-emitted as M/I/S; the left shift preserves them too), so the
     //      reference's check `seq_len == read length of the lifted CIGAR` is decided by the input CIGAR's read length.
+    uint32_t* lift_buf = buf_b;
+    bool staged = false;
+    if (stage.pool) {  // (warp-uniform branch; every lane takes part in the scan)
+        const bool want = usable && !err && (stage_mask & 2u);
+        const uint32_t need = want ? cap_b : 0u;
+        uint32_t incl = need;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(FULL, incl, d);
+            if (int(threadIdx.x & 31u) >= d) incl += o;
+        }
+        if (want && incl <= stage.words) {
+            lift_buf = stage.pool + (incl - need);
+            staged = true;
+        }
+    }
     if (usable && !err && (stage_mask & 2u)) {
-        OpSink sink(buf_b, cap_b);
+        OpSink sink(lift_buf, cap_b);
         int64_t lifted_pos = 0;
         const bool some = run_liftover(cur, cpos, S.table, S.seg_tab_begin[g], S.seg_tab_begin[g + 1], W.pair_tab_lo[p], sink, &lifted_pos);
         if (sink.overflow) err = ST_ERR_CAPACITY;
@@ -269,7 +303,7 @@ __device__ __forceinline__ void lift_pair_body(const DevStatic& S, const DevBatc
         simplify_is_identity = !sink.mixed_cluster;
         span = sink.ref_span;
         rpos = lifted_pos;
-        cur = OpSource{buf_b, sink.n, false};
+        cur = OpSource{lift_buf, sink.n, false};
         cur_is_a = false;
         cur_is_raw = false;
     }
@@ -319,6 +353,7 @@ __device__ __forceinline__ void lift_pair_body(const DevStatic& S, const DevBatc
         for (uint32_t i = 0; i < n; ++i) { const uint32_t c = cur.get(i); buf_a[i] = c; span += op_ref_adv(c); }
         cur = OpSource{buf_a, n, false};
     }
+    LiftOut out;
     if (parked) {
         W.pair_status[p] = int8_t(ST_PENDING_LIFT);
         W.pair_flip[p] = need_flip;
@@ -332,8 +367,64 @@ __device__ __forceinline__ void lift_pair_body(const DevStatic& S, const DevBatc
         W.pair_flip[p] = need_flip;
         W.pair_pos[p] = ok ? rpos : 0;
         W.pair_n_out[p] = ok ? cur.n : 0u;
-        W.pair_out_off[p] = ok ? uint64_t(cur.p - W.scratch) : slot0;
+        // final ops in the pool (cur.p == lift_buf when the liftover was the last stage to run here): the caller stores them
+        out.staged = ok && staged && cur.p == lift_buf;
+        if (!out.staged) W.pair_out_off[p] = (ok && !staged) ? uint64_t(cur.p - W.scratch) : slot0;
         W.pair_bin[p] = ok ? reg2bin(rpos, rpos + int64_t(span)) : uint16_t(0);  // bam_reg2bin(pos, end) (:278-279)
+        out.n = ok ? cur.n : 0u;
+        out.src = cur.p;
+        out.slot0 = slot0;
+        out.cap_b = cap_b;
+    }
+    n_base_bytes += cnt.base_bytes;
+    return out;
+}
+
+// a9 for a pair parked on the simplify worklist by lift_pair_body (its lifted CIGAR holds a mixed I/D run), ONE THREAD per
+// listed pair: the worklist is dense, so every lane of a warp has work (the same stage inline in the lift kernel ran at 1.9
+// active lanes, and a warp per pair spent 32 lanes on ~22 ops).  Warp-collective (run_simplify_warp: the base probes of
+// the k-th mixed cluster of all lanes are issued together).  `i` indexes simplify_list; lanes past its end carry active = false.
+__device__ __forceinline__ void simplify_thread_pair_body(const DevStatic& S, const DevBatch& B, const DevWork& W, DevTotals* T, uint32_t i,
+                                                          bool active, uint32_t& n_base_bytes) {
+    uint32_t p = 0, cap_a = 0, cap_b = 0, n_rec = 0;
+    uint64_t slot0 = 0;
+    uint32_t* buf_a = nullptr;
+    uint32_t* rec = nullptr;
+    OpSource cur{nullptr, 0, false};
+    ReadBases read{nullptr, 0, false};
+    const uint8_t* ref = nullptr;
+    uint64_t ref_len = 0;
+    int64_t rpos = 0;
+    if (active) {
+        p = W.simplify_list[i];
+        const uint32_t s = W.pair_rseg[p], g = W.pair_seg[p];
+        const uint32_t r = W.rseg_read[s];
+        slot0 = W.pair_slot_begin[p];
+        cap_b = W.pair_cap_b[p];
+        cap_a = uint32_t(W.pair_slot_begin[p + 1] - slot0) - cap_b;
+        buf_a = W.scratch + slot0 + cap_b;
+        // buffer A: [simplified ops | 4 words per mixed cluster]; sized by pair_fill_body from (n_id + n_keys) possible clusters
+        n_rec = 4u * ((cap_a - cap_b - 8u) / 6u);
+        rec = buf_a + (cap_a - n_rec);
+        cur = OpSource{W.scratch + W.pair_out_off[p], W.pair_n_out[p], false};  // where lift_pairs_kernel left the lifted CIGAR
+        read = ReadBases{B.seq4 + B.read_seq_off[r], B.read_seq_len[r], W.pair_flip[p] != 0};
+        const int32_t chrom = S.seg_chrom[g];
+        ref = S.ref + S.chrom_off[chrom];
+        ref_len = S.chrom_off[chrom + 1] - S.chrom_off[chrom];
+        rpos = W.pair_pos[p];
+    }
+    PairCounters cnt;
+    int err = 0;
+    OpSink sink(buf_a, active ? cap_a - n_rec : 0u);
+    const int64_t out_pos = run_simplify_warp(active, cur, rpos, ref, ref_len, read, rec, sink, cnt, err);
+    if (active) {
+        int status = err;
+        if (!status && sink.overflow) status = ST_ERR_CAPACITY;
+        W.pair_status[p] = int8_t(status ? status : ST_LIFTED);
+        W.pair_pos[p] = status ? 0 : out_pos;
+        W.pair_n_out[p] = status ? 0u : sink.n;
+        W.pair_out_off[p] = slot0 + cap_b;
+        W.pair_bin[p] = status ? uint16_t(0) : reg2bin(out_pos, out_pos + int64_t(sink.ref_span));
     }
     n_base_bytes += cnt.base_bytes;
 }

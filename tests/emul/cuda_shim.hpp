@@ -32,6 +32,9 @@ using std::max;
 using std::min;
 
 inline bool __any_sync(unsigned, bool pred) { return pred; }
+inline uint32_t __shfl_up_sync(unsigned, uint32_t v, int) { return v; }  // (one lane: callers guard the use with lane >= delta)
+struct EmulDim3 { uint32_t x = 0, y = 0, z = 0; };
+static const EmulDim3 threadIdx{};  // the single lane of the shim is lane 0
 
 inline unsigned int atomicAdd(unsigned int* p, unsigned int v) { const unsigned int o = *p; *p += v; return o; }
 inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { const unsigned long long o = *p; *p += v; return o; }

@@ -228,6 +228,11 @@ int run_batch(ptl_ctx* ctx, EmulSlot& sl, const ptl_batch* b, uint32_t stage_mas
     T.n_in_ops = in_ops;
     T.n_base_bytes = base_bytes;
     if ((stage_mask & 2u) || stage_mask == 1u) emul_lift_long_pairs(S, B, W, &T, stage_mask);  // warp_pairs_kernel
+    if ((stage_mask & 6u) == 6u) {  // simplify_pairs_kernel: one thread per listed pair (even entries; see emul_warp.cpp)
+        uint32_t bb = 0;
+        for (uint32_t i = 0; i < std::min<uint32_t>(T.n_simplify, W.pair_cap); i += 2) simplify_thread_pair_body(S, B, W, &T, i, true, bb);
+        T.n_base_bytes += bb;
+    }
 
     // ---- read_finalize -> scan -> emit_records
     std::vector<uint2> read_counts(size_t(n) + 1, make_uint2(0, 0));

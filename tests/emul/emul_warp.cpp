@@ -23,7 +23,9 @@ void emul_lift_long_pairs(const ptl::DevStatic& S, const ptl::DevBatch& B, const
             warp_emul::tl_parity = 0;
             for (uint32_t t = 0; t < n_long + n_simp; ++t) {
                 if (t < n_long) ptl::lift_long_pair_body(S, B, W, T, W.long_list[t], lane, stage_mask);
-                else ptl::simplify_warp_pair_body(S, B, W, T, W.simplify_list[t - n_long], lane);
+                // (odd worklist entries: the warp-per-pair formulation; emul.cpp runs the even ones through the thread-per-pair
+                //  body the product launches, so both formulations of a9 stay covered against the oracle)
+                else if ((t - n_long) & 1u) ptl::simplify_warp_pair_body(S, B, W, T, W.simplify_list[t - n_long], lane);
             }
         });
     for (auto& th : lanes) th.join();
