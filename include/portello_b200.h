@@ -432,6 +432,67 @@ void ptl_region_segments(uint64_t size, uint64_t segment_size, uint64_t* begin, 
 /* Greedy LPT bin-packing of units (weights = read counts) onto n_ranks; owner[i] = rank of unit i. Deterministic. */
 void ptl_shard_units(uint32_t n_units, const uint64_t* weight, uint32_t n_ranks, uint32_t* owner);
 
+/* ---------------------------------------------------------------- BAM / BGZF / BAI input without htslib (input half; host C++ + zlib)
+ *
+ * What the reference gets from rust-htslib on its input side: bam::IndexedReader::from_path, fetch(Region) / fetch(Unmapped)
+ * and the read loop (src/read_alignment_scanner.rs:382-393,537-559; src/contig_alignment_scanner/mod.rs:196-203), the
+ * header as a ChromList (lib/rust-vc-utils/src/chrom_list.rs:26-44) and the EOF-marker check (bam_reader_utils.rs:29).
+ * Written from the SAM specification (4.1 BGZF, 4.2 BAM, 5.2 BAI).  A ptl_bam_file is immutable once opened: any number of
+ * threads may fetch from it concurrently, which replaces the per-thread reader set of src/worker_thread_data.rs:8-30.
+ * BAM + .bai only (CRAM and .csi are not supported). */
+typedef struct ptl_bam_file ptl_bam_file;
+typedef struct ptl_decoded_batch ptl_decoded_batch;
+enum {
+    PTL_FETCH_ALL = -2,        /* every record of the file, in file order */
+    PTL_FETCH_UNMAPPED = -1    /* FetchDefinition::Unmapped: the unplaced reads behind the last mapped one (:546) */
+};
+enum {
+    PTL_BAM_START_IN_REGION = 1,        /* keep only records whose pos lies in [begin, end) (:403-406; mod.rs:213-217) */
+    PTL_BAM_SKIP_SUPPLEMENTARY = 2,     /* (:404) */
+    PTL_BAM_SKIP_UNMAPPED_SECONDARY = 4, /* (mod.rs:208) */
+    PTL_BAM_ONLY_UNMAPPED = 8,          /* (:550-552) */
+    PTL_BAM_KEEP_RAW = 16               /* also keep the undecoded record bytes (unmapped pass-through, :554) */
+};
+int ptl_bam_open(const char* path, ptl_bam_file** out);
+void ptl_bam_close(ptl_bam_file* f);
+const char* ptl_bam_last_error(void);                       /* thread-local message of the last failing ptl_bam_* / ptl_fasta_* call */
+uint32_t ptl_bam_n_ref(const ptl_bam_file* f);
+const char* ptl_bam_ref_name(const ptl_bam_file* f, uint32_t i);
+uint64_t ptl_bam_ref_len(const ptl_bam_file* f, uint32_t i);
+const char* ptl_bam_header_text(const ptl_bam_file* f);
+int ptl_bam_has_index(const ptl_bam_file* f);
+int ptl_bam_has_eof_marker(const ptl_bam_file* f);          /* assert_bam_eof */
+/* Records overlapping [begin, end) of reference `tid` in file order (= fetch + read loop), or PTL_FETCH_*; decoded into
+ * the SoA the packer and the record assembly take.  A CIGAR with more than 65535 ops is restored from its CG:B,I tag. */
+int ptl_bam_fetch(const ptl_bam_file* f, int32_t tid, int64_t begin, int64_t end, uint32_t filter, ptl_decoded_batch** out);
+void ptl_decoded_view(const ptl_decoded_batch* d, ptl_read_records* recs, ptl_read_extras* extras);
+/* PTL_BAM_KEEP_RAW: record k = bytes[rec_off[k] .. rec_off[k+1]) (block_size + record), ready for a BGZF writer. */
+const uint8_t* ptl_decoded_raw(const ptl_decoded_batch* d, const uint64_t** rec_off, uint64_t* n_bytes);
+void ptl_decoded_free(ptl_decoded_batch* d);
+/* samtools-index equivalent (coordinate-sorted BAM -> .bai with the linear index and the metadata pseudo-bins). */
+int ptl_bam_index_build(const char* bam_path, const char* bai_path);
+
+/* ---------------------------------------------------------------- Phase A on real input
+ *
+ * get_genome_ref_from_fasta (lib/rust-vc-utils/src/genome_ref.rs:43-79): record id = header up to the first white space,
+ * bases upper-cased, nothing else changed. */
+typedef struct ptl_fasta ptl_fasta;
+int ptl_fasta_load(const char* path, int n_threads, ptl_fasta** out);
+uint32_t ptl_fasta_n(const ptl_fasta* f);
+const char* ptl_fasta_name(const ptl_fasta* f, uint32_t i);
+const uint8_t* ptl_fasta_seq(const ptl_fasta* f, uint32_t i, uint64_t* len);
+void ptl_fasta_free(ptl_fasta* f);
+/* The record loop of scan_contig_bam (src/contig_alignment_scanner/mod.rs:186-240,290-354): every reference chromosome of
+ * the contig->reference BAM in <= 20 Mb windows on n_threads threads, records that START in their window, unmapped and
+ * secondary records skipped, qname -> assembly contig index through `contig_names` (the read->assembly BAM header; an
+ * unknown name is PTL_ERR_INPUT where the reference panics), bases of primary records decoded to ASCII.  The result views
+ * as the ptl_contig_records that ptl_set_contig_records / ptl_prepare_contig_records take. */
+typedef struct ptl_contig_scan ptl_contig_scan;
+int ptl_scan_contig_bam(const ptl_bam_file* contig_bam, uint32_t n_contigs, const char* const* contig_names, const uint64_t* contig_len,
+                        int n_threads, ptl_contig_scan** out);
+void ptl_contig_scan_view(const ptl_contig_scan* s, ptl_contig_records* out);
+void ptl_contig_scan_free(ptl_contig_scan* s);
+
 /* BAM bin, = bam_reg2bin (lib/rust-vc-utils/src/bam_utils/util.rs:10-35). */
 uint16_t ptl_reg2bin(int64_t begin, int64_t end);
 

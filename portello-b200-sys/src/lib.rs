@@ -34,6 +34,13 @@ pub const PTL_STAGE_ALL: u32 = 7;
 pub const PTL_WIN_NONE: i32 = 0;
 pub const PTL_WIN_ALL: i32 = 1;
 pub const PTL_WIN_REVERSE_PAIRS: i32 = 2;
+pub const PTL_FETCH_ALL: i32 = -2;
+pub const PTL_FETCH_UNMAPPED: i32 = -1;
+pub const PTL_BAM_START_IN_REGION: u32 = 1;
+pub const PTL_BAM_SKIP_SUPPLEMENTARY: u32 = 2;
+pub const PTL_BAM_SKIP_UNMAPPED_SECONDARY: u32 = 4;
+pub const PTL_BAM_ONLY_UNMAPPED: u32 = 8;
+pub const PTL_BAM_KEEP_RAW: u32 = 16;
 
 // ---------------------------------------------------------------- structs
 #[repr(C)]
@@ -48,6 +55,26 @@ pub struct ptl_prepared_contigs {
 
 #[repr(C)]
 pub struct ptl_packed_batch {
+    _private: [u8; 0],
+}
+
+#[repr(C)]
+pub struct ptl_bam_file {
+    _private: [u8; 0],
+}
+
+#[repr(C)]
+pub struct ptl_decoded_batch {
+    _private: [u8; 0],
+}
+
+#[repr(C)]
+pub struct ptl_fasta {
+    _private: [u8; 0],
+}
+
+#[repr(C)]
+pub struct ptl_contig_scan {
     _private: [u8; 0],
 }
 
@@ -277,5 +304,27 @@ extern "C" {
     pub fn ptl_region_segment_count(size: u64, segment_size: u64) -> u32;
     pub fn ptl_region_segments(size: u64, segment_size: u64, begin: *mut u64, end: *mut u64);
     pub fn ptl_shard_units(n_units: u32, weight: *const u64, n_ranks: u32, owner: *mut u32);
+    pub fn ptl_bam_open(path: *const c_char, out: *mut *mut ptl_bam_file) -> c_int;
+    pub fn ptl_bam_close(f: *mut ptl_bam_file);
+    pub fn ptl_bam_last_error() -> *const c_char;
+    pub fn ptl_bam_n_ref(f: *const ptl_bam_file) -> u32;
+    pub fn ptl_bam_ref_name(f: *const ptl_bam_file, i: u32) -> *const c_char;
+    pub fn ptl_bam_ref_len(f: *const ptl_bam_file, i: u32) -> u64;
+    pub fn ptl_bam_header_text(f: *const ptl_bam_file) -> *const c_char;
+    pub fn ptl_bam_has_index(f: *const ptl_bam_file) -> c_int;
+    pub fn ptl_bam_has_eof_marker(f: *const ptl_bam_file) -> c_int;
+    pub fn ptl_bam_fetch(f: *const ptl_bam_file, tid: i32, begin: i64, end: i64, filter: u32, out: *mut *mut ptl_decoded_batch) -> c_int;
+    pub fn ptl_decoded_view(d: *const ptl_decoded_batch, recs: *mut ptl_read_records, extras: *mut ptl_read_extras);
+    pub fn ptl_decoded_raw(d: *const ptl_decoded_batch, rec_off: *mut *const u64, n_bytes: *mut u64) -> *const u8;
+    pub fn ptl_decoded_free(d: *mut ptl_decoded_batch);
+    pub fn ptl_bam_index_build(bam_path: *const c_char, bai_path: *const c_char) -> c_int;
+    pub fn ptl_fasta_load(path: *const c_char, n_threads: c_int, out: *mut *mut ptl_fasta) -> c_int;
+    pub fn ptl_fasta_n(f: *const ptl_fasta) -> u32;
+    pub fn ptl_fasta_name(f: *const ptl_fasta, i: u32) -> *const c_char;
+    pub fn ptl_fasta_seq(f: *const ptl_fasta, i: u32, len: *mut u64) -> *const u8;
+    pub fn ptl_fasta_free(f: *mut ptl_fasta);
+    pub fn ptl_scan_contig_bam(contig_bam: *const ptl_bam_file, n_contigs: u32, contig_names: *const *const c_char, contig_len: *const u64, n_threads: c_int, out: *mut *mut ptl_contig_scan) -> c_int;
+    pub fn ptl_contig_scan_view(s: *const ptl_contig_scan, out: *mut ptl_contig_records);
+    pub fn ptl_contig_scan_free(s: *mut ptl_contig_scan);
     pub fn ptl_reg2bin(begin: i64, end: i64) -> u16;
 }

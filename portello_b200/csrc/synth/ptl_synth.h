@@ -67,6 +67,12 @@ const int64_t* ptl_synth_plan_pos(const ptl_synth* s);
 /* (Re)generate the read records of `n_ranges` ranges [first[i], first[i] + count[i]) of the BAM order, concatenated in
  * the order given; replaces what ptl_synth_read_records returns (earlier views become invalid).  Returns 0 on success. */
 int ptl_synth_generate_reads(ptl_synth* s, uint32_t n_ranges, const uint64_t* first, const uint64_t* count);
+/* The data as an UNCOMPRESSED BAM byte stream (header + records; frame it with ptl_bgzf_compress, index it with
+ * ptl_bam_index_build): which = 0 the contig->reference alignments (minimap2 --eqx style; CIGARs over 65535 ops use the
+ * CG:B,I placeholder form), which = 1 the read->contig alignments currently generated (names "synth/<index>/ccs", random
+ * qualities, NM / np / SA / RG tags) followed by n_unmapped unplaced reads.  Free with ptl_synth_free_bytes. */
+uint8_t* ptl_synth_bam_stream(const ptl_synth* s, int which, uint32_t n_unmapped, uint64_t* n_bytes);
+void ptl_synth_free_bytes(uint8_t* p);
 /* Contig lengths (the read->assembly BAM header). */
 const uint64_t* ptl_synth_contig_len(const ptl_synth* s);
 

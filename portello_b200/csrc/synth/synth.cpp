@@ -376,6 +376,7 @@ struct ptl_synth {
     std::vector<uint32_t> rr_cigar;
     std::vector<std::string> rr_sa_s;
     std::vector<const char*> rr_sa;
+    std::vector<uint64_t> rr_plan_index;  // index of each generated read in the planned BAM order (its name)
 };
 
 namespace {
@@ -712,6 +713,7 @@ void make_reads(ptl_synth& s, uint32_t nt, const std::vector<std::pair<uint64_t,
     for (const auto& r : ranges)
         for (uint64_t i = r.first; i < r.first + r.second; ++i) pick.push_back(i);
     const uint64_t n = pick.size();
+    s.rr_plan_index = pick;
     const std::vector<ReadSeed>& seeds = s.seeds;
     // generate in chunks
     const uint64_t chunk = 2048;
@@ -910,6 +912,151 @@ int ptl_synth_generate_reads(ptl_synth* s, uint32_t n_ranges, const uint64_t* fi
     make_reads(*s, thread_count(s->P), ranges);
     return 0;
 }
+// ---- the same data as BAM byte streams (uncompressed; the caller frames them as BGZF and indexes them), so that the
+//      file-level path (BGZF inflate, BAM decode, index fetch, the command-line tool) runs on exactly the records the
+//      in-memory path gets, and so that the real portello can be run on the same files elsewhere.
+namespace {
+struct ByteSink {
+    std::vector<uint8_t> v;
+    void u8(uint8_t x) { v.push_back(x); }
+    void u16(uint16_t x) { v.push_back(uint8_t(x)); v.push_back(uint8_t(x >> 8)); }
+    void u32(uint32_t x) { for (int b = 0; b < 4; ++b) v.push_back(uint8_t(x >> (8 * b))); }
+    void bytes(const void* p, size_t n) { const uint8_t* q = static_cast<const uint8_t*>(p); v.insert(v.end(), q, q + n); }
+    void str(const std::string& t) { bytes(t.data(), t.size()); }
+};
+void bam_header(ByteSink& o, const std::string& text, const std::vector<std::string>& names, const std::vector<uint64_t>& lens) {
+    o.bytes("BAM\1", 4);
+    o.u32(uint32_t(text.size()));
+    o.str(text);
+    o.u32(uint32_t(names.size()));
+    for (size_t i = 0; i < names.size(); ++i) {
+        o.u32(uint32_t(names[i].size() + 1));
+        o.str(names[i]);
+        o.u8(0);
+        o.u32(uint32_t(lens[i]));
+    }
+}
+// one record; `seq4` = packed bases (l_seq of them), `qual` = l_seq bytes or nullptr (0xff), `aux` = raw aux block.
+// A CIGAR with more than 65535 ops is written the way htslib writes it: a `<l_seq>S<ref_len>N` placeholder + CG:B,I.
+void bam_record(ByteSink& o, int32_t tid, int64_t pos, uint8_t mapq, uint16_t flag, const std::string& name, const uint32_t* cigar, size_t n_cigar,
+                const uint8_t* seq4, uint32_t l_seq, const uint8_t* qual, const std::vector<uint8_t>& aux) {
+    uint64_t ref_len = 0;
+    for (size_t i = 0; i < n_cigar; ++i) if ((0x18dU >> (cigar[i] & 0xf)) & 1u) ref_len += cigar[i] >> 4;
+    const bool big = n_cigar > 65535;
+    const size_t n_cig_field = big ? 2 : n_cigar;
+    const size_t size = 32 + name.size() + 1 + 4 * n_cig_field + (size_t(l_seq) + 1) / 2 + l_seq + aux.size() + (big ? 8 + 4 * n_cigar : 0);
+    o.u32(uint32_t(size));
+    o.u32(uint32_t(tid));
+    o.u32(uint32_t(int32_t(pos)));
+    o.u8(uint8_t(name.size() + 1));
+    o.u8(mapq);
+    o.u16((flag & 0x4) ? 4680 : reg2bin(pos, pos + int64_t(std::max<uint64_t>(ref_len, 1))));
+    o.u16(uint16_t(n_cig_field));
+    o.u16(flag);
+    o.u32(l_seq);
+    o.u32(uint32_t(-1));
+    o.u32(uint32_t(-1));
+    o.u32(0);
+    o.str(name);
+    o.u8(0);
+    if (big) { o.u32((l_seq << 4) | S); o.u32(uint32_t(ref_len << 4) | 3u); }
+    else for (size_t i = 0; i < n_cigar; ++i) o.u32(cigar[i]);
+    o.bytes(seq4, (size_t(l_seq) + 1) / 2);
+    if (qual) o.bytes(qual, l_seq);
+    else o.v.insert(o.v.end(), l_seq, uint8_t(0xff));
+    o.bytes(aux.data(), aux.size());
+    if (big) {
+        o.bytes("CGBI", 4);
+        o.u32(uint32_t(n_cigar));
+        for (size_t i = 0; i < n_cigar; ++i) o.u32(cigar[i]);
+    }
+}
+void aux_z(std::vector<uint8_t>& a, const char* tag, const std::string& v) {
+    a.push_back(uint8_t(tag[0])); a.push_back(uint8_t(tag[1])); a.push_back('Z');
+    a.insert(a.end(), v.begin(), v.end());
+    a.push_back(0);
+}
+void aux_i(std::vector<uint8_t>& a, const char* tag, int32_t v) {
+    a.push_back(uint8_t(tag[0])); a.push_back(uint8_t(tag[1])); a.push_back('i');
+    for (int b = 0; b < 4; ++b) a.push_back(uint8_t(uint32_t(v) >> (8 * b)));
+}
+}  // namespace
+
+uint8_t* ptl_synth_bam_stream(const ptl_synth* s, int which, uint32_t n_unmapped, uint64_t* n_bytes) {
+    if (!s || !n_bytes) return nullptr;
+    ByteSink o;
+    if (which == 0) {  // contig -> reference (minimap2 --eqx style: primary soft-clipped with SA + bases, supplementary hard-clipped)
+        std::string text = "@HD\tVN:1.6\tSO:coordinate\n";
+        std::vector<std::string> names;
+        for (size_t c = 0; c < s->chroms.size(); ++c) {
+            names.push_back(s->chrom_name_s[c]);
+            text += "@SQ\tSN:" + s->chrom_name_s[c] + "\tLN:" + std::to_string(s->chrom_len[c]) + "\n";
+        }
+        bam_header(o, text, names, s->chrom_len);
+        for (size_t i = 0; i < s->cr_contig.size(); ++i) {
+            std::vector<uint8_t> aux, seq4;
+            aux_i(aux, "NM", 0);
+            if (s->cr_sa[i]) aux_z(aux, "SA", s->cr_sa[i]);
+            uint32_t l_seq = 0;
+            if (s->cr_seq[i]) {
+                const std::vector<uint8_t>& q = s->cr_seq_s[i];
+                l_seq = uint32_t(q.size());
+                seq4.assign((q.size() + 1) / 2, 0);
+                for (size_t k = 0; k < q.size(); ++k) seq4[k >> 1] |= uint8_t(code4(q[k]) << ((k & 1) ? 0 : 4));
+            }
+            bam_record(o, s->cr_tid[i], s->cr_pos[i], s->cr_mapq[i], s->cr_flag[i], s->contigs[s->cr_contig[i]].name,
+                       s->cr_cigar.data() + s->cr_cigar_begin[i], size_t(s->cr_cigar_begin[i + 1] - s->cr_cigar_begin[i]), seq4.data(), l_seq, nullptr, aux);
+        }
+    } else {  // read -> contig (pbmm2 style), the reads currently generated, then n_unmapped unplaced reads
+        std::string text = "@HD\tVN:1.6\tSO:coordinate\n";
+        std::vector<std::string> names;
+        for (size_t c = 0; c < s->contigs.size(); ++c) {
+            names.push_back(s->contigs[c].name);
+            text += "@SQ\tSN:" + s->contigs[c].name + "\tLN:" + std::to_string(s->contig_len[c]) + "\n";
+        }
+        bam_header(o, text, names, s->contig_len);
+        const size_t n = s->rr_tid.size();
+        std::vector<uint8_t> qual;
+        for (size_t r = 0; r < n; ++r) {
+            const uint32_t L = s->rr_seq_len[r];
+            Rng rng(s->P.seed, 0x600000000ull + s->rr_plan_index[r]);
+            qual.resize(L);
+            for (uint32_t k = 0; k < L;) {
+                uint64_t w = rng.next();
+                for (int j = 0; j < 10 && k < L; ++j, ++k, w >>= 6) qual[k] = uint8_t((w & 63) % 94);
+            }
+            std::vector<uint8_t> aux;
+            aux_i(aux, "NM", int32_t(rng.below(40)));
+            aux_i(aux, "np", int32_t(4 + rng.below(20)));
+            if (s->rr_sa[r]) aux_z(aux, "SA", s->rr_sa[r]);
+            aux_z(aux, "RG", "synth");
+            bam_record(o, s->rr_tid[r], s->rr_pos[r], s->rr_mapq[r], s->rr_flag[r], "synth/" + std::to_string(s->rr_plan_index[r]) + "/ccs",
+                       s->rr_cigar.data() + s->rr_cigar_begin[r], size_t(s->rr_cigar_begin[r + 1] - s->rr_cigar_begin[r]),
+                       s->rr_seq4 + s->rr_seq_off[r], L, qual.data(), aux);
+        }
+        for (uint32_t u = 0; u < n_unmapped; ++u) {
+            Rng rng(s->P.seed, 0x700000000ull + u);
+            const uint32_t L = 500 + uint32_t(rng.below(3000));
+            std::vector<uint8_t> seq4((L + 1) / 2, 0);
+            qual.resize(L);
+            for (uint32_t k = 0; k < L; ++k) {
+                seq4[k >> 1] |= uint8_t(code4(rand_base(rng)) << ((k & 1) ? 0 : 4));
+                qual[k] = uint8_t(rng.below(94));
+            }
+            std::vector<uint8_t> aux;
+            aux_i(aux, "np", int32_t(3 + rng.below(9)));
+            aux_z(aux, "RG", "synth");
+            bam_record(o, -1, -1, 0, 4, "synth/unmapped" + std::to_string(u) + "/ccs", nullptr, 0, seq4.data(), L, qual.data(), aux);
+        }
+    }
+    uint8_t* out = static_cast<uint8_t*>(std::malloc(std::max<size_t>(o.v.size(), 1)));
+    if (!out) return nullptr;
+    std::memcpy(out, o.v.data(), o.v.size());
+    *n_bytes = o.v.size();
+    return out;
+}
+void ptl_synth_free_bytes(uint8_t* p) { std::free(p); }
+
 void ptl_synth_read_records(const ptl_synth* s, ptl_read_records* o) {
     o->n_reads = uint32_t(s->rr_tid.size());
     o->tid = s->rr_tid.data();

@@ -59,6 +59,9 @@ def _load():
         d.ptl_synth_plan_pos.argtypes = [C.c_void_p]
         d.ptl_synth_contig_len.restype = u64p
         d.ptl_synth_contig_len.argtypes = [C.c_void_p]
+        d.ptl_synth_bam_stream.restype = C.POINTER(C.c_uint8)
+        d.ptl_synth_bam_stream.argtypes = [C.c_void_p, C.c_int, C.c_uint32, u64p]
+        d.ptl_synth_free_bytes.argtypes = [C.POINTER(C.c_uint8)]
         d.ptl_synth_generate_reads.restype = C.c_int
         d.ptl_synth_generate_reads.argtypes = [C.c_void_p, C.c_uint32, u64p, u64p]
         _dll = d
@@ -169,6 +172,21 @@ class Synth:
             self.close()
         except Exception:
             pass
+
+
+def bam_stream(s: "Synth", which: int, n_unmapped: int = 0):
+    """The data set as an uncompressed BAM byte stream (numpy uint8): which = 0 contig->reference, 1 read->contig."""
+    import numpy as np
+
+    d = _load()
+    n = C.c_uint64()
+    p = d.ptl_synth_bam_stream(s.h, which, n_unmapped, C.byref(n))
+    if not p:
+        raise MemoryError("ptl_synth_bam_stream failed")
+    try:
+        return np.ctypeslib.as_array(p, (int(n.value),)).copy()
+    finally:
+        d.ptl_synth_free_bytes(p)
 
 
 def make(name_or_kw, host_alloc=None, host_free=None, **override) -> Synth:

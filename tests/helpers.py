@@ -103,3 +103,16 @@ LETTER_MAP = str.maketrans({"A": "A", "B": "C", "C": "G", "D": "T", "E": "M", "F
 
 def relabel(s: str) -> str:
     return s.translate(LETTER_MAP)
+
+
+def bam_header_bytes(text: str, names, lens) -> bytes:
+    """ptl_bam_header: the uncompressed BAM header block."""
+    d = lib.load().dll
+    d.ptl_bam_header.restype = C.c_int64
+    d.ptl_bam_header.argtypes = [C.c_char_p, C.c_uint32, C.POINTER(C.c_char_p), C.POINTER(C.c_uint64), C.c_void_p, C.c_uint64]
+    arr = (C.c_char_p * max(len(names), 1))(*[n.encode() for n in names])
+    ln = (C.c_uint64 * max(len(lens), 1))(*lens)
+    out = np.zeros(len(text) + 64 + sum(len(n) + 16 for n in names), np.uint8)
+    n = d.ptl_bam_header(text.encode(), len(names), arr, ln, out.ctypes.data, out.size)
+    assert n >= 0, n
+    return out[:n].tobytes()
