@@ -390,6 +390,11 @@ enum { PTL_WIN_NONE = 0, PTL_WIN_ALL = 1, PTL_WIN_REVERSE_PAIRS = 2 };
 int ptl_pack_batch_ex(const ptl_read_records* recs, uint32_t first, uint32_t count, uint32_t n_contigs,
                       const char* const* contig_names, int pinned, int window_mode, const ptl_contig_segments* segs,
                       ptl_packed_batch** out);
+/* As ptl_pack_batch_ex, into an EXISTING packed batch whose arena is reused when it is large enough (same pinned-ness):
+ * a streaming host keeps a few packed batches and repacks them, instead of allocating pinned memory per batch.  Distinct
+ * packed batches may be packed from distinct host threads concurrently (one packer thread per slot or window). */
+int ptl_pack_batch_into(ptl_packed_batch* reuse, const ptl_read_records* recs, uint32_t first, uint32_t count, uint32_t n_contigs,
+                        const char* const* contig_names, int window_mode, const ptl_contig_segments* segs);
 void ptl_packed_batch_view(const ptl_packed_batch* p, ptl_batch* out);
 /* [view.n_reads] index of each batch read in `recs` (supplementary records are dropped by the packer). */
 const uint32_t* ptl_packed_batch_record_index(const ptl_packed_batch* p);

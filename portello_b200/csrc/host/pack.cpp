@@ -157,6 +157,7 @@ size_t align_up(size_t x) { return (x + 255) & ~size_t(255); }
 
 struct ptl_packed_batch {
     void* arena = nullptr;
+    size_t arena_cap = 0;
     bool pinned = false;
     ptl_batch view{};
     std::vector<uint32_t> record_index;  // batch read -> index into the source records
@@ -209,11 +210,13 @@ int ptl_pack_batch(const ptl_read_records* recs, uint32_t first, uint32_t count,
     return ptl_pack_batch_ex(recs, first, count, n_contigs, contig_names, pinned, PTL_WIN_NONE, nullptr, out);
 }
 
-int ptl_pack_batch_ex(const ptl_read_records* recs, uint32_t first, uint32_t count, uint32_t n_contigs,
-                      const char* const* contig_names, int pinned, int window_mode, const ptl_contig_segments* wsegs, ptl_packed_batch** out) {
-    if (!recs || !out || uint64_t(first) + count > recs->n_reads) return PTL_ERR_INVALID_ARG;
+// Packs into `pb`, reusing its arena when it is large enough (a streaming host repacks the same few buffers).
+static int pack_impl(const ptl_read_records* recs, uint32_t first, uint32_t count, uint32_t n_contigs, const char* const* contig_names, int window_mode,
+                     const ptl_contig_segments* wsegs, ptl_packed_batch* pb) {
+    if (!recs || !pb || uint64_t(first) + count > recs->n_reads) return PTL_ERR_INVALID_ARG;
     if (window_mode < PTL_WIN_NONE || window_mode > PTL_WIN_REVERSE_PAIRS || (window_mode == PTL_WIN_REVERSE_PAIRS && !wsegs)) return PTL_ERR_INVALID_ARG;
     const bool contig_wants_windows = window_mode != PTL_WIN_NONE;
+    const bool pinned = pb->pinned;
     try {
         NameMap names(n_contigs, contig_names);
         // pass 1: parse SA tags (rare), collect segment lists
@@ -283,14 +286,17 @@ int ptl_pack_batch_ex(const ptl_read_records* recs, uint32_t first, uint32_t cou
                      o_sb = take((n + 1) * 4), o_ctg = take(ns * 4), o_pos = take(ns * 8), o_fwd = take(ns), o_cb = take(ns * 8),
                      o_cl = take(ns * 4), o_cig = take(n_cig * 4);
         const size_t o_wb = contig_wants_windows ? take((size_t(ns) + 1) * 4) : 0, o_win = contig_wants_windows ? take(n_win * 8) : 0;
-        auto* pb = new ptl_packed_batch();
-        pb->pinned = pinned != 0;
-        pb->arena = pinned ? ptl_host_alloc(std::max<size_t>(off, 256)) : std::malloc(std::max<size_t>(off, 256));
-        if (!pb->arena) {
-            delete pb;
-            g_pack_err = pinned ? "pinned allocation failed (no CUDA device?)" : "out of memory";
-            return PTL_ERR_CUDA;
+        if (off > pb->arena_cap) {
+            if (pb->arena) { if (pinned) ptl_host_free(pb->arena); else std::free(pb->arena); }
+            const size_t want = std::max<size_t>(off + off / 8, 256);
+            pb->arena = pinned ? ptl_host_alloc(want) : std::malloc(want);
+            pb->arena_cap = pb->arena ? want : 0;
+            if (!pb->arena) {
+                g_pack_err = pinned ? "pinned allocation failed (no CUDA device?)" : "out of memory";
+                return PTL_ERR_CUDA;
+            }
         }
+        pb->view = ptl_batch{};
         char* a = static_cast<char*>(pb->arena);
         auto* flag = reinterpret_cast<uint16_t*>(a + o_flag);
         auto* mapq = reinterpret_cast<uint8_t*>(a + o_mapq);
@@ -353,6 +359,35 @@ int ptl_pack_batch_ex(const ptl_read_records* recs, uint32_t first, uint32_t cou
                     uint64_t* w = win + win_begin[k];
                     uint32_t read_head = 0, blk_read = 0, ins = 0;
                     bool in_indel = false;
+                    // The bases of a cluster sit in a cache line nobody has touched yet (7.5 KB of packed bases per read,
+                    // one line per cluster): a first walk only finds where the clusters end and prefetches those lines,
+                    // so that the misses of a segment overlap instead of queueing up one per cluster.
+                    {
+                        uint32_t rh = 0, br = 0, in2 = 0;
+                        bool open = false;
+                        auto touch = [&]() {
+                            const uint32_t read_end = br + in2;
+                            if (read_end > 0 && read_end <= len) {
+                                const uint32_t idx = read_end - 1u, j = flip ? len - 1u - idx : idx;
+                                __builtin_prefetch(sq + (j >> 1));
+                            }
+                            open = false;
+                            in2 = 0;
+                        };
+                        for (uint32_t t = g.cig_len; t-- > 0;) {
+                            const uint32_t x = c[t], op = op_of(x), l = len_of(x);
+                            if (op == OP_I || op == OP_D) {
+                                if (l > 0) {
+                                    if (!open) { open = true; br = rh; }
+                                    if (op == OP_I) in2 += l;
+                                }
+                            } else if (open) {
+                                touch();
+                            }
+                            rh += uint32_t(read_adv(x));
+                        }
+                        if (open) touch();
+                    }
                     auto close = [&]() {
                         const uint32_t read_end = blk_read + ins;
                         uint64_t bits = 0;
@@ -397,12 +432,29 @@ int ptl_pack_batch_ex(const ptl_read_records* recs, uint32_t first, uint32_t cou
         v.seq4_bytes = seq_hi - seq_lo;
         pb->record_index = std::move(kept);
         pb->n_skipped_supplementary = skipped;
-        *out = pb;
         return PTL_OK;
     } catch (const InputError& e) {
         g_pack_err = e.what();
         return PTL_ERR_INPUT;
     }
+}
+
+int ptl_pack_batch_ex(const ptl_read_records* recs, uint32_t first, uint32_t count, uint32_t n_contigs,
+                      const char* const* contig_names, int pinned, int window_mode, const ptl_contig_segments* wsegs, ptl_packed_batch** out) {
+    if (!out) return PTL_ERR_INVALID_ARG;
+    auto* pb = new ptl_packed_batch();
+    pb->pinned = pinned != 0;
+    const int rc = pack_impl(recs, first, count, n_contigs, contig_names, window_mode, wsegs, pb);
+    if (rc != PTL_OK) {
+        ptl_packed_batch_free(pb);
+        return rc;
+    }
+    *out = pb;
+    return PTL_OK;
+}
+int ptl_pack_batch_into(ptl_packed_batch* reuse, const ptl_read_records* recs, uint32_t first, uint32_t count, uint32_t n_contigs,
+                        const char* const* contig_names, int window_mode, const ptl_contig_segments* wsegs) {
+    return pack_impl(recs, first, count, n_contigs, contig_names, window_mode, wsegs, reuse);
 }
 void ptl_packed_batch_view(const ptl_packed_batch* p, ptl_batch* out) { *out = p->view; }
 const uint32_t* ptl_packed_batch_record_index(const ptl_packed_batch* p) { return p->record_index.data(); }

@@ -79,6 +79,9 @@ class ProductLib(LiftLib):
         d.ptl_pack_batch_ex.restype = C.c_int
         d.ptl_pack_batch_ex.argtypes = [C.POINTER(ReadRecordsC), C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_char_p), C.c_int, C.c_int,
                                         C.POINTER(ContigSegmentsC), C.POINTER(C.c_void_p)]
+        d.ptl_pack_batch_into.restype = C.c_int
+        d.ptl_pack_batch_into.argtypes = [C.c_void_p, C.POINTER(ReadRecordsC), C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_char_p), C.c_int,
+                                          C.POINTER(ContigSegmentsC)]
         d.ptl_packed_batch_view.argtypes = [C.c_void_p, C.POINTER(BatchC)]
         d.ptl_packed_batch_record_index.restype = u32p
         d.ptl_packed_batch_record_index.argtypes = [C.c_void_p]
@@ -179,6 +182,23 @@ class PackedBatch:
         lib.dll.ptl_packed_batch_view(self.h, C.byref(self.c))
         self.c._owner = self  # the view must keep the arena alive (`pack(...).c` would otherwise dangle)
         self._recs = recs_c  # the batch borrows seq4
+        self._names = names
+        self._segs_c = None if windows is None or windows is True else segs_c
+        self._mode = 0 if windows is None else 1 if windows is True else 2
+        self._windows = windows  # (segs_c points into its arrays)
+
+    def repack(self, first: int, count: int, recs_c: ReadRecordsC = None):
+        """ptl_pack_batch_into: pack other records into this batch's arena (reused when large enough).  Callable from any
+        thread (the C call releases the GIL); distinct PackedBatch objects may be repacked concurrently."""
+        recs_c = recs_c if recs_c is not None else self._recs
+        rc = self.lib.dll.ptl_pack_batch_into(self.h, C.byref(recs_c), first, count, len(self._names), self._names, self._mode,
+                                              C.byref(self._segs_c) if self._segs_c is not None else None)
+        if rc != 0:
+            raise PtlError(rc, self.lib.dll.ptl_pack_last_error().decode())
+        self._recs = recs_c
+        self.lib.dll.ptl_packed_batch_view(self.h, C.byref(self.c))
+        self.c._owner = self
+        return self
 
     def record_index(self) -> np.ndarray:
         p = self.lib.dll.ptl_packed_batch_record_index(self.h)
