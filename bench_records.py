@@ -141,4 +141,85 @@ def measure(args, ctx, s, L, ch, peak):
                                        "check": f"python gzip reads the framed stream of {sub.c.n_reads} reads back to the record bytes"}}
 
 
-    return {"assemble_bases": assemble, "assemble_records": assemble_rec}
+    return {"assemble_bases": assemble, "assemble_records": assemble_rec, "e2e_records": measure_e2e_records(args, ctx, s, L, extras_for)}
+
+
+def pinned_array(L, nbytes):
+    import ctypes as C
+    p = L.dll.ptl_host_alloc(max(int(nbytes), 64))
+    if not p:
+        raise MemoryError("ptl_host_alloc failed")
+    return np.ctypeslib.as_array((C.c_uint8 * int(nbytes)).from_address(p)), p
+
+
+def measure_e2e_records(args, ctx, s, L, extras_for, n_chunks=6, chunk=65536):
+    """The record path end to end (src/read_alignment_scanner.rs:61-78,105-133,245-282,482-487): DECODED records (packed bases,
+    qualities, names, aux) in pinned host memory -> H2D -> lift -> record assembly -> level-0 BGZF framing + CRC on the
+    device -> D2H of the framed bytes, every copy inside the timed region; three host threads, one per batch slot."""
+    import threading
+    from portello_b200 import abi, lib
+
+    n_reads = s.read_records.n_reads
+    chunk = min(chunk, n_reads)
+    n_chunks = max(1, min(n_chunks, n_reads // chunk))
+    ctx.set_seq_zero_copy(False)  # the assembly streams the bases from HBM: they are uploaded with the batch
+    packs, extras, keep = [], [], []
+    tile = np.random.default_rng(1).integers(0, 94, 1 << 24, dtype=np.uint8)
+    in_bytes = 0
+    for k in range(n_chunks):
+        pb = lib.PackedBatch(L, s.read_records, k * chunk, chunk, s.contig_names, pinned=True)
+        seq_len = np.ctypeslib.as_array(pb.c.read_seq_len, (pb.c.n_reads,)).astype(np.int64)
+        qoff = np.zeros(pb.c.n_reads, np.uint64)
+        qoff[1:] = np.cumsum(seq_len[:-1])
+        x = extras_for(int(pb.c.n_reads), seq_len, None, qoff)
+        qual, qp = pinned_array(L, int(seq_len.sum()) + 64)
+        qual[:] = np.resize(tile, qual.size)
+        x["qual"] = qual
+        for f in ("names", "aux"):  # pinned copies of the pools
+            a, ap = pinned_array(L, x[f].size)
+            a[:] = x[f]
+            x[f] = a
+            keep.append(ap)
+        keep.append(qp)
+        packs.append(pb)
+        extras.append(x)
+        in_bytes += int(pb.c.seq4_bytes) + qual.size + x["names"].size + x["aux"].size + int(pb.c.n_cigar) * 4 + int(pb.c.n_reads) * 40
+    ctx.set_names(s.contig_names, s.chrom_names)
+    out_bytes = [0] * n_chunks
+    n_records = [0] * n_chunks
+    errors = []
+
+    def worker(slot, reps):
+        try:
+            for _ in range(reps):
+                for k in range(slot, n_chunks, 3):
+                    ctx.submit_c(packs[k].c, slot)
+                    ctx.wait_c(slot)
+                    o, _ = ctx.assemble_records(extras[k], slot, flags=abi.ASM_NO_DOWNLOAD)
+                    z, zb = ctx.bgzf_store_records(b"", slot, flags=0, copy=False)
+                    out_bytes[k] = int(z.n_bytes)
+                    n_records[k] = int(o.n_records)
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    def run(reps):
+        th = [threading.Thread(target=worker, args=(sl, reps)) for sl in range(3)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        if errors:
+            raise errors[0]
+
+    run(1)
+    reps = max(1, min(args.steps, 3))
+    t0 = time.perf_counter()
+    run(reps)
+    dt = (time.perf_counter() - t0) / reps
+    for p in keep:
+        L.dll.ptl_host_free(p)
+    recs = sum(n_records)
+    return {"what": "decoded records (packed bases, qualities, names, aux) in pinned host memory -> lift -> ptl_assemble_records -> "
+                    "ptl_bgzf_store_records -> level-0 BGZF bytes on the host; H2D and D2H inside the timed region, one host thread per slot",
+            "reads_per_pass": n_chunks * chunk, "records_per_pass": recs, "ms_per_pass": dt * 1e3, "records_per_s": recs / dt,
+            "h2d_bytes_per_pass": in_bytes, "d2h_bytes_per_pass": sum(out_bytes),
+            "pcie_gbs": {"h2d": round(in_bytes / dt / 1e9, 2), "d2h": round(sum(out_bytes) / dt / 1e9, 2)},
+            "bound": "PCIe: ~23 KB in and ~23 KB out per read; the kernels of a pass take a few ms"}

@@ -577,14 +577,15 @@ class Context:
         by = np.ctypeslib.as_array(out.bytes, (max(int(rb[n]), 1),))[: int(rb[n])].copy() if n else np.zeros(0, np.uint8)
         return out, (rb, by)
 
-    def bgzf_store_records(self, prefix: bytes = b"", slot: int = 0, flags: int = 0):
+    def bgzf_store_records(self, prefix: bytes = b"", slot: int = 0, flags: int = 0, copy: bool = True):
         """ptl_bgzf_store_records: [prefix | records of the slot's last assemble_records] as level-0 BGZF.  Returns
-        (BgzfStreamC, bytes) -- bytes is None with ASM_NO_DOWNLOAD."""
+        (BgzfStreamC, bytes) -- bytes is None with ASM_NO_DOWNLOAD, or with copy=False (the stream then stays in the slot's
+        pinned buffer, out.bytes)."""
         fn = getattr(self.lib.dll, self.lib.prefix + "bgzf_store_records")
         fn.restype, fn.argtypes = C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_uint64, C.c_uint32, C.POINTER(BgzfStreamC)]
         out = BgzfStreamC()
         self._check(fn(self.h, slot, prefix if prefix else None, len(prefix), flags, C.byref(out)))
-        if flags & ASM_NO_DOWNLOAD:
+        if (flags & ASM_NO_DOWNLOAD) or not copy:
             return out, None
         return out, bytes(np.ctypeslib.as_array(out.bytes, (max(int(out.n_bytes), 1),))[: int(out.n_bytes)])
 
