@@ -292,6 +292,9 @@ __global__ void __launch_bounds__(256) pair_order_kernel(DevStatic S, DevBatch B
 // The lifted CIGARs of a tile are written to a shared-memory pool (StagePool), then moved by the warp, as one flat index
 // space with coalesced stores, into the tile's dense output region: the thread-private, 7x-sparse scratch slots are no
 // longer written for them (ncu r04a: DRAM traffic 2.6x the algorithmic bytes), and the record emission reads dense CIGARs.
+#ifndef LIFT_COPY_FLAT
+#define LIFT_COPY_FLAT 0
+#endif
 #ifndef LIFT_STAGE_WORDS
 #define LIFT_STAGE_WORDS 1024  // shared-memory words per tile for the staged outputs (32 per lane)
 #endif
@@ -328,6 +331,7 @@ __global__ void __launch_bounds__(32, LIFT_MIN_BLOCKS) lift_pairs_kernel(DevStat
             const uint32_t src_off = out.staged ? uint32_t(out.src - stage.pool) : 0u;
             uint32_t* const dense = W.scratch + dense_at;
             __syncwarp();
+#if LIFT_COPY_FLAT
             for (uint32_t j0 = 0; j0 < total; j0 += 32u) {
                 const uint32_t j = j0 + lane;
                 uint32_t lo = 0, hi = 31;  // owner = last lane whose exclusive prefix <= j
@@ -341,6 +345,16 @@ __global__ void __launch_bounds__(32, LIFT_MIN_BLOCKS) lift_pairs_kernel(DevStat
                 const uint32_t e2 = __shfl_sync(FULL, excl, lo);
                 if (j < total) dense[j] = stage.pool[s2 + (j - e2)];
             }
+#else
+            // one source lane at a time, its ops spread over the lanes: coalesced both ways, 3 shuffles + a short loop per
+            // pair (a flat index space with an owner search per 32 words cost 875 warp instructions per tile, ncu r05b)
+            for (uint32_t sl = 0; sl < 32u; ++sl) {
+                const uint32_t n_s = __shfl_sync(FULL, n, sl);
+                const uint32_t s2 = __shfl_sync(FULL, src_off, sl);
+                const uint32_t e2 = __shfl_sync(FULL, excl, sl);
+                for (uint32_t j = lane; j < n_s; j += 32u) dense[e2 + j] = stage.pool[s2 + j];
+            }
+#endif
         } else if (out.staged) {  // (a tile of long CIGARs)
             uint32_t* dst = W.scratch + out.slot0;
             for (uint32_t j = 0; j < n; ++j) dst[j] = out.src[j];

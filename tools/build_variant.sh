@@ -12,5 +12,6 @@ nvcc $F "$@" -c $C/device/kernels.cu -o $O/kernels.o
 nvcc $F "$@" -c $C/context.cu -o $O/context.o
 g++ -O3 -std=c++17 -fPIC -pthread -c $C/host/pack.cpp -o $O/pack.o
 g++ -O3 -std=c++17 -fPIC -pthread -c $C/host/contig_prep.cpp -o $O/contig_prep.o
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $ROOT/gpurun_variants/libportello_b200_$TAG.so $O/kernels.o $O/context.o $O/pack.o $O/contig_prep.o -cudart static
+for f in bgzf bam_io bam_abi; do g++ -O3 -std=c++17 -fPIC -pthread -c $C/host/$f.cpp -o $O/$f.o; done
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $ROOT/gpurun_variants/libportello_b200_$TAG.so $O/kernels.o $O/context.o $O/pack.o $O/contig_prep.o $O/bgzf.o $O/bam_io.o $O/bam_abi.o -cudart static -lz
 rm -rf $O

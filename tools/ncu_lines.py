@@ -22,6 +22,9 @@ for i, h in enumerate(hdr):
         print(f"{h:72s} {vals[i]:>16s} {units[i]}")
 src = subprocess.run(["ncu", "-i", rep, *KFILT, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
+second = next((i for i, r in enumerate(rows[1:], 1) if r and r[0] == "Kernel Name"), None)
+if second:
+    rows = rows[:second]  # (several launches of the kernel in the capture: the first one)
 shdr = rows[1]
 ix = {h: i for i, h in enumerate(shdr)}
 data = rows[2:]
