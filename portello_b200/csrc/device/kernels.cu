@@ -293,7 +293,8 @@ __global__ void __launch_bounds__(256) pair_order_kernel(DevStatic S, DevBatch B
 // space with coalesced stores, into the tile's dense output region: the thread-private, 7x-sparse scratch slots are no
 // longer written for them (ncu r04a: DRAM traffic 2.6x the algorithmic bytes), and the record emission reads dense CIGARs.
 #ifndef LIFT_COPY_FLAT
-#define LIFT_COPY_FLAT 0
+#define LIFT_COPY_FLAT 1  // 0: one source lane at a time (4x fewer instructions, but 32 dependent rounds per tile: 2 % slower - the kernel is bound by the
+                         // length of a warp's dependent chain, not by issue slots)
 #endif
 #ifndef LIFT_STAGE_WORDS
 #define LIFT_STAGE_WORDS 1024  // shared-memory words per tile for the staged outputs (32 per lane)
@@ -346,8 +347,7 @@ __global__ void __launch_bounds__(32, LIFT_MIN_BLOCKS) lift_pairs_kernel(DevStat
                 if (j < total) dense[j] = stage.pool[s2 + (j - e2)];
             }
 #else
-            // one source lane at a time, its ops spread over the lanes: coalesced both ways, 3 shuffles + a short loop per
-            // pair (a flat index space with an owner search per 32 words cost 875 warp instructions per tile, ncu r05b)
+            // one source lane at a time, its ops spread over the lanes: coalesced both ways, 3 shuffles + a short loop per pair
             for (uint32_t sl = 0; sl < 32u; ++sl) {
                 const uint32_t n_s = __shfl_sync(FULL, n, sl);
                 const uint32_t s2 = __shfl_sync(FULL, src_off, sl);
