@@ -328,6 +328,13 @@ typedef struct {
     uint64_t bytes_written;  /* algorithmic bytes: the stream once in, the framed stream once out */
 } ptl_bgzf_stream;
 int ptl_bgzf_store_records(ptl_ctx* ctx, int slot, const uint8_t* prefix, uint64_t prefix_bytes, uint32_t flags, ptl_bgzf_stream* out);
+/* ptl_assemble_records + ptl_bgzf_store_records in ONE pass: [prefix | every output record of the slot's last batch] as
+ * level-0 BGZF, byte-identical to calling the two, but the record stream is never materialised: the payload of every BGZF
+ * block is produced straight from the packed bases / qualities / names / aux of the reads (and the liftover result) and
+ * its CRC from what the block has just written, so the device moves every byte once instead of twice.
+ * `extras`, PTL_ASM_RESIDENT_QUAL and PTL_ASM_NO_DOWNLOAD as in ptl_assemble_records; PTL_BGZF_EOF appends the EOF marker. */
+int ptl_frame_records(ptl_ctx* ctx, int slot, const ptl_read_extras* extras, const uint8_t* prefix, uint64_t prefix_bytes, uint32_t flags,
+                      ptl_bgzf_stream* out);
 
 /* cudaStream_t of a slot (as void*), so callers can bracket work with their own CUDA events. */
 void* ptl_slot_stream(ptl_ctx* ctx, int slot);

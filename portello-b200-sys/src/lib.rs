@@ -285,6 +285,7 @@ extern "C" {
     pub fn ptl_bgzf_bound(n: u64) -> u64;
     pub fn ptl_bgzf_compress(in_: *const u8, n: u64, level: c_int, n_threads: c_int, append_eof: c_int, out: *mut u8, cap: u64) -> i64;
     pub fn ptl_bgzf_store_records(ctx: *mut ptl_ctx, slot: c_int, prefix: *const u8, prefix_bytes: u64, flags: u32, out: *mut ptl_bgzf_stream) -> c_int;
+    pub fn ptl_frame_records(ctx: *mut ptl_ctx, slot: c_int, extras: *const ptl_read_extras, prefix: *const u8, prefix_bytes: u64, flags: u32, out: *mut ptl_bgzf_stream) -> c_int;
     pub fn ptl_slot_stream(ctx: *mut ptl_ctx, slot: c_int) -> *mut c_void;
     pub fn ptl_slot_kernel_times(ctx: *mut ptl_ctx, slot: c_int, cap: c_int, names: *mut *const c_char, ms: *mut f32) -> c_int;
     pub fn ptl_launch_count(ctx: *const ptl_ctx) -> u64;
@@ -295,6 +296,7 @@ extern "C" {
     pub fn ptl_host_free(p: *mut c_void);
     pub fn ptl_pack_batch(recs: *const ptl_read_records, first: u32, count: u32, n_contigs: u32, contig_names: *const *const c_char, pinned: c_int, out: *mut *mut ptl_packed_batch) -> c_int;
     pub fn ptl_pack_batch_ex(recs: *const ptl_read_records, first: u32, count: u32, n_contigs: u32, contig_names: *const *const c_char, pinned: c_int, window_mode: c_int, segs: *const ptl_contig_segments, out: *mut *mut ptl_packed_batch) -> c_int;
+    pub fn ptl_pack_batch_into(reuse: *mut ptl_packed_batch, recs: *const ptl_read_records, first: u32, count: u32, n_contigs: u32, contig_names: *const *const c_char, window_mode: c_int, segs: *const ptl_contig_segments) -> c_int;
     pub fn ptl_packed_batch_view(p: *const ptl_packed_batch, out: *mut ptl_batch);
     pub fn ptl_packed_batch_record_index(p: *const ptl_packed_batch) -> *const u32;
     pub fn ptl_packed_batch_free(p: *mut ptl_packed_batch);

@@ -551,23 +551,26 @@ class Context:
         b = (C.c_char_p * max(len(chrom_names), 1))(*[n.encode() for n in chrom_names])
         self._check(fn(self.h, len(contig_names), a, len(chrom_names), b))
 
+    def _extras_c(self, extras: dict, slot: int) -> ReadExtrasC:
+        x = ReadExtrasC()
+        k = {
+            "name_off": _arr(extras["name_off"], np.uint64), "names": _arr(extras["names"], np.uint8),
+            "aux_off": _arr(extras["aux_off"], np.uint64), "aux": _arr(extras["aux"], np.uint8),
+            "mate_tid": _arr(extras["mate_tid"], np.int32), "mate_pos": _arr(extras["mate_pos"], np.int32),
+            "tlen": _arr(extras["tlen"], np.int32), "qual": _arr(extras["qual"], np.uint8), "qual_off": _arr(extras["qual_off"], np.uint64),
+        }
+        self._keep[("extras", slot)] = k
+        x.name_off, x.names, x.aux_off, x.aux = _ptr(k["name_off"], u64p), _ptr(k["names"], u8p), _ptr(k["aux_off"], u64p), _ptr(k["aux"], u8p)
+        x.mate_tid, x.mate_pos, x.tlen = _ptr(k["mate_tid"], i32p), _ptr(k["mate_pos"], i32p), _ptr(k["tlen"], i32p)
+        x.quals.qual, x.quals.read_qual_off, x.quals.qual_bytes = _ptr(k["qual"], u8p), _ptr(k["qual_off"], u64p), k["qual"].size
+        return x
+
     def assemble_records(self, extras: Optional[dict], slot: int = 0, flags: int = 0):
         """ptl_assemble_records on the slot's last lifted batch.  `extras`: dict with name_off, names, aux_off, aux, mate_tid,
         mate_pos, tlen, qual, qual_off (numpy).  Returns (BamRecordsC, (rec_begin, bytes)) -- the pair is None with ASM_NO_DOWNLOAD."""
         fn = getattr(self.lib.dll, self.lib.prefix + "assemble_records")
         fn.restype, fn.argtypes = C.c_int, [C.c_void_p, C.c_int, C.POINTER(ReadExtrasC), C.c_uint32, C.POINTER(BamRecordsC)]
-        x = ReadExtrasC()
-        if extras is not None:
-            k = {
-                "name_off": _arr(extras["name_off"], np.uint64), "names": _arr(extras["names"], np.uint8),
-                "aux_off": _arr(extras["aux_off"], np.uint64), "aux": _arr(extras["aux"], np.uint8),
-                "mate_tid": _arr(extras["mate_tid"], np.int32), "mate_pos": _arr(extras["mate_pos"], np.int32),
-                "tlen": _arr(extras["tlen"], np.int32), "qual": _arr(extras["qual"], np.uint8), "qual_off": _arr(extras["qual_off"], np.uint64),
-            }
-            self._keep[("extras", slot)] = k
-            x.name_off, x.names, x.aux_off, x.aux = _ptr(k["name_off"], u64p), _ptr(k["names"], u8p), _ptr(k["aux_off"], u64p), _ptr(k["aux"], u8p)
-            x.mate_tid, x.mate_pos, x.tlen = _ptr(k["mate_tid"], i32p), _ptr(k["mate_pos"], i32p), _ptr(k["tlen"], i32p)
-            x.quals.qual, x.quals.read_qual_off, x.quals.qual_bytes = _ptr(k["qual"], u8p), _ptr(k["qual_off"], u64p), k["qual"].size
+        x = self._extras_c(extras, slot) if extras is not None else ReadExtrasC()
         out = BamRecordsC()
         self._check(fn(self.h, slot, C.byref(x) if extras is not None else None, flags, C.byref(out)))
         if flags & ASM_NO_DOWNLOAD:
@@ -576,6 +579,17 @@ class Context:
         rb = np.ctypeslib.as_array(out.rec_begin, (n + 1,)).copy()
         by = np.ctypeslib.as_array(out.bytes, (max(int(rb[n]), 1),))[: int(rb[n])].copy() if n else np.zeros(0, np.uint8)
         return out, (rb, by)
+
+    def frame_records(self, extras: Optional[dict], prefix: bytes = b"", slot: int = 0, flags: int = 0, copy: bool = True):
+        """ptl_frame_records: assemble + frame in one pass.  Returns (BgzfStreamC, bytes or None)."""
+        fn = getattr(self.lib.dll, self.lib.prefix + "frame_records")
+        fn.restype, fn.argtypes = C.c_int, [C.c_void_p, C.c_int, C.POINTER(ReadExtrasC), C.c_char_p, C.c_uint64, C.c_uint32, C.POINTER(BgzfStreamC)]
+        x = self._extras_c(extras, slot) if extras is not None else None
+        out = BgzfStreamC()
+        self._check(fn(self.h, slot, C.byref(x) if x is not None else None, prefix if prefix else None, len(prefix), flags, C.byref(out)))
+        if (flags & ASM_NO_DOWNLOAD) or not copy:
+            return out, None
+        return out, bytes(np.ctypeslib.as_array(out.bytes, (max(int(out.n_bytes), 1),))[: int(out.n_bytes)])
 
     def bgzf_store_records(self, prefix: bytes = b"", slot: int = 0, flags: int = 0, copy: bool = True):
         """ptl_bgzf_store_records: [prefix | records of the slot's last assemble_records] as level-0 BGZF.  Returns

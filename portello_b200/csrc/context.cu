@@ -104,7 +104,7 @@ struct Slot {
     bool b_resident = false;
     uint64_t b_in_bytes = 0, b_name_bytes = 0, b_aux_bytes = 0;
     uint64_t b_total = 0;             // bytes of the records assembled last (they start kBamFront bytes into b_out)
-    DBuf z_out;                       // ptl_bgzf_store_records
+    DBuf z_out, z_prefix;             // ptl_bgzf_store_records / ptl_frame_records
     HBuf hz_out;
     cudaStream_t b_stream = nullptr;  // the meta kernel of the record assembly runs beside the streaming kernel
     cudaEvent_t b_fork = nullptr, b_join = nullptr;
@@ -571,7 +571,7 @@ void ptl_destroy(ptl_ctx* ctx) {
                         &sl.w_pair_slot_begin, &sl.w_pair_status, &sl.w_pair_flip, &sl.w_pair_pos, &sl.w_pair_n_out, &sl.w_pair_bin, &sl.w_pair_out_off, &sl.w_simplify_list, &sl.w_long_list, &sl.w_pair_order,
                         &sl.w_scratch, &sl.w_read_counts, &sl.w_read_primary, &sl.w_scan_tmp, &sl.w_totals, &sl.r_arena, &sl.a_qual, &sl.a_qual_off,
                         &sl.a_rec_read, &sl.a_seq_begin, &sl.a_qual_begin, &sl.a_out_seq, &sl.a_out_qual, &sl.b_name_off, &sl.b_names, &sl.b_aux_off,
-                        &sl.b_aux, &sl.b_mate_tid, &sl.b_mate_pos, &sl.b_tlen, &sl.b_keep, &sl.b_sa_len, &sl.b_rec_begin, &sl.b_rec_desc, &sl.b_out, &sl.b_err, &sl.z_out})
+                        &sl.b_aux, &sl.b_mate_tid, &sl.b_mate_pos, &sl.b_tlen, &sl.b_keep, &sl.b_sa_len, &sl.b_rec_begin, &sl.b_rec_desc, &sl.b_out, &sl.b_err, &sl.z_out, &sl.z_prefix})
             b->release();
         sl.h_arena.release();
         for (HBuf* b : {&sl.ha_seq_begin, &sl.ha_qual_begin, &sl.ha_out_seq, &sl.ha_out_qual, &sl.hb_rec_begin, &sl.hb_out, &sl.hb_err, &sl.hz_out}) b->release();
@@ -880,10 +880,15 @@ int ptl_set_names(ptl_ctx* ctx, uint32_t n_contigs, const char* const* contig_na
         return PTL_OK;
     });
 }
-int ptl_assemble_records(ptl_ctx* ctx, int slot, const ptl_read_extras* x, uint32_t flags, ptl_bam_records* out) {
+// ptl_assemble_records (zout == nullptr: the records as a byte stream) and ptl_frame_records (zout != nullptr: the same
+// records, never materialised, straight into level-0 BGZF blocks behind `prefix`).
+static int assemble_impl(ptl_ctx* ctx, int slot, const ptl_read_extras* x, uint32_t flags, ptl_bam_records* out, const uint8_t* prefix,
+                         uint64_t prefix_bytes, ptl_bgzf_stream* zout) {
     Slot* sl = get_slot(ctx, slot);
-    if (!sl || !out || (!x && !(flags & PTL_ASM_RESIDENT_QUAL))) return PTL_ERR_INVALID_ARG;
-    if (!sl->ran) return fail(ctx, PTL_ERR_STATE, "ptl_assemble_records without a lifted batch on the slot");
+    ptl_bam_records out_local{};
+    if (zout && !out) out = &out_local;
+    if (!sl || !out || (!x && !(flags & PTL_ASM_RESIDENT_QUAL)) || (prefix_bytes && !prefix) || prefix_bytes > kBamFront / 2) return PTL_ERR_INVALID_ARG;
+    if (!sl->ran) return fail(ctx, PTL_ERR_STATE, "record assembly without a lifted batch on the slot");
     if (!ctx->have_names) return fail(ctx, PTL_ERR_STATE, "ptl_set_names has not been called");
     return guarded(ctx, [&]() {
         finish_batch(ctx, *sl);
@@ -992,6 +997,50 @@ int ptl_assemble_records(ptl_ctx* ctx, int slot, const ptl_read_extras* x, uint3
             CK(cudaEventCreateWithFlags(&sl->b_fork, cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&sl->b_join, cudaEventDisableTiming));
         }
+        if (zout) {  // ---- fused: small fields into the sparse scratch, then the payload of every BGZF block straight from the sources
+            static const std::vector<uint32_t> tables = bgzf_tables();
+            if (!ctx->s_bgzf_tables.p) upload(ctx->s_bgzf_tables, tables.data(), tables.size(), st);
+            sl->z_prefix.ensure(std::max<uint64_t>(prefix_bytes, 16) + 64, st);
+            if (prefix_bytes) CK(cudaMemcpyAsync(sl->z_prefix.p, prefix, prefix_bytes, cudaMemcpyHostToDevice, st));
+            const uint64_t zn = prefix_bytes + total;
+            const uint64_t n_blocks = (zn + kBgzfIn - 1) / kBgzfIn;
+            const uint64_t framed = zn + uint64_t(kBgzfOverhead) * n_blocks;
+            static const uint8_t kEof[28] = {0x1f, 0x8b, 0x08, 0x04, 0, 0, 0, 0, 0, 0xff, 0x06, 0, 0x42, 0x43, 0x02, 0, 0x1b, 0, 0x03, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+            const uint64_t ztotal = framed + ((flags & PTL_BGZF_EOF) ? sizeof(kEof) : 0);
+            sl->z_out.ensure(ztotal + 64, st);
+            FrameArgs F{};
+            F.A = A;
+            F.prefix = sl->z_prefix.as<uint8_t>();
+            F.prefix_bytes = prefix_bytes;
+            F.Z.in = nullptr;
+            F.Z.n = zn;
+            F.Z.out = sl->z_out.as<uint8_t>();
+            F.Z.tables = ctx->s_bgzf_tables.as<uint32_t>();
+            F.Z.n_blocks = n_blocks;
+            F.Z.init_full = crc_zero_bytes(tables.data(), 0xffffffffu, kBgzfIn);
+            F.Z.init_last = crc_zero_bytes(tables.data(), 0xffffffffu, n_blocks ? zn - (n_blocks - 1) * kBgzfIn : 0);
+            CK(cudaEventRecord(sl->a_ev[0], st));
+            launch_bam_frame(F, st, LaunchTally(ctx));
+            CK(cudaEventRecord(sl->a_ev[1], st));
+            if (flags & PTL_BGZF_EOF) CK(cudaMemcpyAsync(sl->z_out.as<uint8_t>() + framed, kEof, sizeof(kEof), cudaMemcpyHostToDevice, st));
+            *zout = ptl_bgzf_stream{};
+            if (!(flags & PTL_ASM_NO_DOWNLOAD)) {
+                sl->hz_out.ensure(ztotal + 64);
+                if (ztotal) CK(cudaMemcpyAsync(sl->hz_out.p, sl->z_out.p, ztotal, cudaMemcpyDeviceToHost, st));
+                zout->bytes = sl->hz_out.as<uint8_t>();
+            }
+            CK(cudaStreamSynchronize(st));
+            CK(cudaGetLastError());
+            CK(cudaEventElapsedTime(&zout->kernel_ms, sl->a_ev[0], sl->a_ev[1]));
+            zout->n_bytes = ztotal;
+            zout->n_blocks = n_blocks;
+            // algorithmic bytes: every input byte of a record once (+ the prefix), the framed stream once
+            zout->bytes_read = zn - std::min<uint64_t>(total, 36ull * n_rec);
+            zout->bytes_written = framed;
+            out->rec_begin = sl->hb_rec_begin.as<uint64_t>();
+            sl->b_total = 0;  // (no assembled record stream exists on the slot: ptl_bgzf_store_records has nothing to frame)
+            return PTL_OK;
+        }
         CK(cudaEventRecord(sl->a_ev[0], st));
         CK(cudaEventRecord(sl->b_fork, st));
         CK(cudaStreamWaitEvent(sl->b_stream, sl->b_fork, 0));
@@ -1014,6 +1063,14 @@ int ptl_assemble_records(ptl_ctx* ctx, int slot, const ptl_read_extras* x, uint3
         out->bytes_read = total - std::min<uint64_t>(total, 36ull * n_rec);
         return PTL_OK;
     });
+}
+int ptl_assemble_records(ptl_ctx* ctx, int slot, const ptl_read_extras* x, uint32_t flags, ptl_bam_records* out) {
+    if (!out) return PTL_ERR_INVALID_ARG;
+    return assemble_impl(ctx, slot, x, flags, out, nullptr, 0, nullptr);
+}
+int ptl_frame_records(ptl_ctx* ctx, int slot, const ptl_read_extras* x, const uint8_t* prefix, uint64_t prefix_bytes, uint32_t flags, ptl_bgzf_stream* out) {
+    if (!out) return PTL_ERR_INVALID_ARG;
+    return assemble_impl(ctx, slot, x, flags, nullptr, prefix, prefix_bytes, out);
 }
 int ptl_set_long_pair_ops(ptl_ctx* ctx, uint32_t n_ops) {
     if (!ctx) return PTL_ERR_INVALID_ARG;

@@ -63,23 +63,22 @@ __device__ __forceinline__ void bgzf_store_init(const BgzfArgs& A, uint32_t tid,
     for (uint32_t i = tid; i < 128u * 32u; i += 256u) wl[i] = A.tables[kBgzfWord + (i >> 5)];
     __syncthreads();
 }
-__device__ __forceinline__ void bgzf_store_block_body(const BgzfArgs& A, uint64_t b, uint32_t tid, uint32_t* sm) {
-    uint32_t* t0 = sm;
-    uint32_t* shift = sm + 256;
-    uint32_t* wl = shift + 9 * 128;  // per-lane word-step tables: entry e of lane l at wl[32 e + l]
-    uint32_t* warp_crc = wl + 128 * 32;
-    const uint32_t lane = tid & 31u;
-    const uint64_t in_off = b * kBgzfIn;
-    const uint32_t n = uint32_t(min(uint64_t(kBgzfIn), A.n - in_off));
-    uint8_t* dst = A.out + b * uint64_t(kBgzfIn + kBgzfOverhead);
-    uint8_t* data_dst = dst + 23;
-    const uint8_t* src = A.in + in_off;
-    if (tid == 0) {  // gzip header + the stored-block header (unaligned destination: byte stores)
+// gzip header + the stored-block header of a block with n payload bytes (unaligned destination: byte stores by one thread)
+__device__ __forceinline__ void bgzf_write_header(uint8_t* dst, uint32_t n, uint32_t tid) {
+    if (tid == 0) {
         const uint32_t bsize1 = n + kBgzfOverhead - 1u;
         const uint8_t h[23] = {0x1f, 0x8b, 0x08, 0x04, 0, 0, 0, 0, 0, 0xff, 0x06, 0, 0x42, 0x43, 0x02, 0, uint8_t(bsize1 & 0xffu), uint8_t(bsize1 >> 8),
                                0x01, uint8_t(n & 0xffu), uint8_t(n >> 8), uint8_t(~n & 0xffu), uint8_t((~n >> 8) & 0xffu)};
         for (int i = 0; i < 23; ++i) dst[i] = h[i];
     }
+}
+// CRC-32 of the n payload bytes at `src` (block-cooperative, 256 threads) and the footer (CRC32, ISIZE) behind data_dst.
+__device__ __forceinline__ void bgzf_crc_and_footer(const BgzfArgs& A, const uint8_t* src, uint32_t n, uint8_t* data_dst, uint32_t tid, uint32_t* sm) {
+    uint32_t* t0 = sm;
+    uint32_t* shift = sm + 256;
+    uint32_t* wl = shift + 9 * 128;  // per-lane word-step tables: entry e of lane l at wl[32 e + l]
+    uint32_t* warp_crc = wl + 128 * 32;
+    const uint32_t lane = tid & 31u;
     // ---- zero-state CRC of this thread's 256-byte slice, slices counted back from the end of the data; its two halves run
     //      as two independent chains; every thread reads its slice straight from global memory (16 bytes per step: five
     //      aligned words + funnel shifts; a sector is used by two consecutive steps of the same thread)
@@ -150,8 +149,94 @@ __device__ __forceinline__ void bgzf_store_block_body(const BgzfArgs& A, uint64_
             for (int i = 0; i < 4; ++i) { f[i] = uint8_t(full >> (8 * i)); f[4 + i] = uint8_t(n >> (8 * i)); }
         }
     }
+}
+__device__ __forceinline__ void bgzf_store_block_body(const BgzfArgs& A, uint64_t b, uint32_t tid, uint32_t* sm) {
+    const uint64_t in_off = b * kBgzfIn;
+    const uint32_t n = uint32_t(min(uint64_t(kBgzfIn), A.n - in_off));
+    uint8_t* dst = A.out + b * uint64_t(kBgzfIn + kBgzfOverhead);
+    uint8_t* data_dst = dst + 23;
+    const uint8_t* src = A.in + in_off;
+    bgzf_write_header(dst, n, tid);
+    bgzf_crc_and_footer(A, src, n, data_dst, tid, sm);
     // ---- the payload itself: the record copy of assemble_bam.cuh (aligned 16-byte stores, funnel-shifted source)
     copy_field(data_dst, src, n, tid, 256u);
+    __syncthreads();  // (warp_crc is reused by the next block of this persistent thread block)
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Fused record assembly + framing (ptl_frame_records): the payload of BGZF block b is produced STRAIGHT FROM THE SOURCES
+// (packed bases and qualities of the reads, re-oriented for flipped records; the few hundred bytes of core / name / CIGAR /
+// aux / tag text of every record come from the sparse scratch bam_write_meta_kernel fills), so the assembled record stream
+// is never written and read back: 3 GB in, 3 GB out per 131 k reads instead of 12 GB over two kernels.  The block then
+// reads its own 64 KB back (from L2: it has just written them) for the CRC.
+struct FrameArgs {
+    BgzfArgs Z;            // Z.in is unused; Z.n = prefix_bytes + the record bytes
+    BamAsmArgs A;          // A.out = the sparse scratch with the small fields of every record at its stream offset
+    const uint8_t* prefix; // device copy of the stream prefix (the BAM header), may be nullptr
+    uint64_t prefix_bytes;
+};
+__device__ __forceinline__ void bgzf_frame_block_body(const FrameArgs& F, uint64_t b, uint32_t tid, uint32_t* sm) {
+    const BamAsmArgs& A = F.A;
+    const uint64_t x0 = b * kBgzfIn;
+    const uint32_t n = uint32_t(min(uint64_t(kBgzfIn), F.Z.n - x0));
+    const uint64_t x1 = x0 + n;
+    uint8_t* dst = F.Z.out + b * uint64_t(kBgzfIn + kBgzfOverhead);
+    uint8_t* data_dst = dst + 23;
+    bgzf_write_header(dst, n, tid);
+    if (x0 < F.prefix_bytes) copy_field(data_dst, F.prefix + x0, uint32_t((x1 < F.prefix_bytes ? x1 : F.prefix_bytes) - x0), tid, 256u);
+    if (x1 > F.prefix_bytes && A.n_records) {
+        // record-space range [r0, r1) of this block; first record = last k with rec_begin[k] <= r0 (the same search in every thread)
+        const uint64_t xs = x0 > F.prefix_bytes ? x0 : F.prefix_bytes;
+        const uint64_t r0 = xs - F.prefix_bytes, r1 = x1 - F.prefix_bytes;
+        uint8_t* const out0 = data_dst + (xs - x0);  // where record-space byte r0 goes
+        uint32_t lo = 0, hi = A.n_records;
+        while (hi - lo > 1u) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (A.rec_begin[mid] <= r0) lo = mid; else hi = mid;
+        }
+        for (uint32_t k = lo; k < A.n_records; ++k) {
+            const uint64_t rb = A.rec_begin[k];
+            if (rb >= r1) break;
+            const BamRecLayout L = BamRecLayout::unpack(A.rec_desc + 2 * size_t(k));
+            const uint64_t o_seq = 36ull + L.name_n + 1 + 4ull * L.n_cigar, o_qual = o_seq + L.seq_bytes, o_aux = o_qual + L.l_seq;
+            const bool flip = A.rec_need_flip[k] != 0;
+            const uint8_t* src_s = A.seq4 + A.read_seq_off[L.r];
+            const uint8_t* src_q = A.qual + A.qual_off[L.r];
+            const int64_t len = L.l_seq;
+            // the four fields of the record, each clipped to [r0, r1): [fa, fb) in record coordinates
+            auto clip = [&](uint64_t fa, uint64_t fb, uint64_t& ia, uint64_t& ib) {
+                const uint64_t lo_c = r0 > rb ? r0 - rb : 0ull, hi_c = r1 - rb;
+                ia = fa > lo_c ? fa : lo_c;
+                ib = fb < hi_c ? fb : hi_c;
+                return ia < ib;
+            };
+            uint64_t ia, ib;
+            if (clip(0, o_seq, ia, ib)) copy_field(out0 + (rb + ia - r0), A.out + rb + ia, uint32_t(ib - ia), tid, 256u);
+            if (clip(o_seq, o_qual, ia, ib)) {
+                uint8_t* d = out0 + (rb + ia - r0);
+                const int64_t off = int64_t(ia - o_seq);
+                if (!flip) copy_field(d, src_s + off, uint32_t(ib - ia), tid, 256u);
+                else emit_field(d, int64_t(ib - ia), tid, 256u, [&](int64_t o) { return revcomp_chunk(src_s, len, o + off); });
+            }
+            if (clip(o_qual, o_aux, ia, ib)) {
+                uint8_t* d = out0 + (rb + ia - r0);
+                const int64_t off = int64_t(ia - o_qual);
+                if (!flip) copy_field(d, src_q + off, uint32_t(ib - ia), tid, 256u);
+                else emit_field(d, int64_t(ib - ia), tid, 256u, [&](int64_t o) {
+                    const uint4 s = window128_lean(src_q, len - 16 - (o + off), len);  // the 16 bytes in front of the mirrored position
+                    uint4 v;
+                    v.x = __byte_perm(s.w, 0u, 0x0123u);
+                    v.y = __byte_perm(s.z, 0u, 0x0123u);
+                    v.z = __byte_perm(s.y, 0u, 0x0123u);
+                    v.w = __byte_perm(s.x, 0u, 0x0123u);
+                    return v;
+                });
+            }
+            if (clip(o_aux, L.total, ia, ib)) copy_field(out0 + (rb + ia - r0), A.out + rb + ia, uint32_t(ib - ia), tid, 256u);
+        }
+    }
+    __syncthreads();  // the payload is complete (and visible to the block) before its CRC is read back
+    bgzf_crc_and_footer(F.Z, data_dst, n, data_dst, tid, sm);
     __syncthreads();  // (warp_crc is reused by the next block of this persistent thread block)
 }
 

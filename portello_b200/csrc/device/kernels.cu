@@ -673,6 +673,28 @@ __global__ void __launch_bounds__(256, 4) bgzf_store_kernel(BgzfArgs A) {
 }
 }  // namespace
 
+namespace {
+__global__ void __launch_bounds__(256, 4) bam_frame_kernel(FrameArgs F) {
+    extern __shared__ __align__(16) uint32_t bgzf_smem[];
+    bgzf_store_init(F.Z, threadIdx.x, bgzf_smem);
+    for (uint64_t b = blockIdx.x; b < F.Z.n_blocks; b += gridDim.x) bgzf_frame_block_body(F, b, threadIdx.x, bgzf_smem);
+}
+}  // namespace
+
+// ptl_frame_records: the small fields of every record into the sparse scratch (one warp per record), then one persistent
+// thread block per BGZF block producing its payload from the sources and its CRC from what it has just written.
+void launch_bam_frame(const FrameArgs& F, cudaStream_t st, uint64_t* launches) {
+    if (F.A.n_records) {
+        bam_write_meta_kernel<<<(F.A.n_records + 3) / 4, 128, 0, st>>>(F.A);
+        ++*launches;
+    }
+    if (!F.Z.n_blocks) return;
+    const int smem = int(kBgzfSmemWords * 4u);
+    cudaFuncSetAttribute(bam_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    bam_frame_kernel<<<unsigned(std::min<uint64_t>(F.Z.n_blocks, 148ull * 4)), 256, smem, st>>>(F);
+    ++*launches;
+}
+
 void launch_bgzf_store(const BgzfArgs& A, cudaStream_t st, uint64_t* launches) {
     if (!A.n_blocks) return;
     const int smem = int(kBgzfSmemWords * 4u);

@@ -44,5 +44,8 @@ void launch_bam_write(const BamAsmArgs& A, cudaStream_t st, cudaStream_t st_meta
 // BGZF framing at compression level 0 (bgzf_store.cuh): one thread block per BGZF block.
 struct BgzfArgs;
 void launch_bgzf_store(const BgzfArgs& A, cudaStream_t st, uint64_t* launches);
+// Fused record assembly + framing (bgzf_store.cuh: bgzf_frame_block_body).
+struct FrameArgs;
+void launch_bam_frame(const FrameArgs& F, cudaStream_t st, uint64_t* launches);
 
 }  // namespace ptl

@@ -438,3 +438,37 @@ def test_gpu_stale_extras_are_not_reused_for_a_new_batch():
                  lambda: gctx.assemble_bases(None, None, flags=abi.ASM_RESIDENT_QUAL)):
         with pytest.raises(abi.PtlError):
             call()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["iupac-odd", "tiny", "config1", "wg-flips"])
+def test_gpu_frame_records_equals_assemble_then_store(case):
+    """ptl_frame_records (record assembly fused with level-0 BGZF framing: the record stream is never materialised) must be
+    byte-identical to ptl_assemble_records + ptl_bgzf_store_records, for every prefix length / EOF choice, and gunzip to
+    the records."""
+    import gzip
+    if case == "iupac-odd":
+        s, pb = iupac_case(13, n_reads=2500)   # records of 1..900 bases: many records per BGZF block
+    elif case == "wg-flips":
+        s = synth.make("tiny", seed=19, n_reads=3000, rev_contig_frac=0.9, read_len_mean=9000, read_len_sd=2500, read_len_min=2000, read_len_max=15000)
+        pb = helpers.pack(s)
+    else:
+        s = synth.make(case, **({"n_reads": 3000} if case == "config1" else {}))
+        pb = helpers.pack(s)
+    gctx = helpers.gpu_context(s)
+    gctx.set_names(s.contig_names, s.chrom_names)
+    helpers.lift_c(gctx, pb.c, allow_panic=True)
+    x, _, _ = make_extras(s, pb, 9)
+    _, (rb, by) = gctx.assemble_records(x)
+    hdr = helpers.bam_header_bytes("@HD\tVN:1.6\tSO:unsorted\n", s.chrom_names, [int(s.chrom_len[i]) for i in range(s.n_chrom)])
+    for prefix, flags in ((b"", 0), (hdr, abi.BGZF_EOF), (b"x" * 12345, 0), (b"y" * 7, abi.BGZF_EOF)):
+        gctx.assemble_records(x)
+        _, want = gctx.bgzf_store_records(prefix, flags=flags)
+        helpers.lift_c(gctx, pb.c, allow_panic=True)   # a fresh batch on the slot: nothing of the two-call path is left over
+        z, got = gctx.frame_records(x, prefix, flags=flags)
+        assert got == want, (case, len(prefix), flags, len(got), len(want), next((i for i, (a, b) in enumerate(zip(got, want)) if a != b), None))
+        assert gzip.decompress(got) == prefix + by.tobytes()
+        assert z.n_blocks == (len(prefix) + by.size + 0xff00 - 1) // 0xff00 and z.kernel_ms > 0
+    # resident inputs, no download: the timing mode of the bench
+    z2, none = gctx.frame_records(None, b"", flags=abi.ASM_RESIDENT_QUAL | abi.ASM_NO_DOWNLOAD)
+    assert none is None and z2.n_bytes > by.size
