@@ -105,6 +105,13 @@ def measure(args, ctx, s, L, ch, peak):
             zs.append(float(zo.kernel_ms))
         z_ms = float(np.mean(zs[max(args.warmup, 3):]))
         z_bytes = int(zo.bytes_read + zo.bytes_written)
+        # the same in ONE pass (ptl_frame_records): records never materialised, every byte moved once
+        fs = []
+        for _ in range(max(args.warmup, 3) + args.steps):
+            fo, _ = ctx.frame_records(None, b"", 0, flags=abi.ASM_RESIDENT_QUAL | abi.ASM_NO_DOWNLOAD)
+            fs.append(float(fo.kernel_ms))
+        f_ms = float(np.mean(fs[max(args.warmup, 3):]))
+        f_bytes = int(fo.bytes_read + fo.bytes_written)
         xs = extras_for(int(sub.c.n_reads), sl_len, sq, so)
         octx_a.set_names(s.contig_names, s.chrom_names)
         t0 = time.perf_counter()
@@ -116,6 +123,10 @@ def measure(args, ctx, s, L, ch, peak):
             raise SystemExit("PARITY FAILURE vs oracle in ptl_assemble_records on the bench workload")
         import gzip
         _, zb = ctx.bgzf_store_records(b"", 1, flags=abi.BGZF_EOF)
+        helpers.lift_c(ctx, sub.c, slot=1)
+        _, zf = ctx.frame_records(xs, b"", 1, flags=abi.BGZF_EOF)
+        if zf != zb:
+            raise SystemExit("ptl_frame_records differs from ptl_assemble_records + ptl_bgzf_store_records on the bench workload")
         if gzip.decompress(zb) != byg.tobytes():
             raise SystemExit("ptl_bgzf_store_records: the framed stream does not decompress to the records")
         r_traffic = None
@@ -138,7 +149,13 @@ def measure(args, ctx, s, L, ch, peak):
                                        "(the reference's stdout mode, src/read_alignment_scanner.rs:66-71)", "blocks": int(zo.n_blocks), "kernel_ms": z_ms,
                                        "roofline": {"bound": "hbm", "achieved": z_bytes / (z_ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
                                                     "frac": z_bytes / (z_ms / 1e3) / 1e9 / peak, "algorithmic_bytes_per_launch": z_bytes, "traffic": None},
-                                       "check": f"python gzip reads the framed stream of {sub.c.n_reads} reads back to the record bytes"}}
+                                       "check": f"python gzip reads the framed stream of {sub.c.n_reads} reads back to the record bytes"},
+                        "frame_records": {"kernel": "bam_write_meta_kernel + bam_frame_kernel", "what": "ptl_frame_records: assembly fused with the level-0 framing; "
+                                          "the payload of every BGZF block straight from the sources, CRC32 from the block's own output (L2)",
+                                          "kernel_ms": f_ms, "vs_two_pass_ms": r_ms + z_ms, "records_per_s": o.n_records / (f_ms / 1e3),
+                                          "roofline": {"bound": "hbm", "achieved": f_bytes / (f_ms / 1e3) / 1e9, "peak": peak, "unit": "GB/s",
+                                                       "frac": f_bytes / (f_ms / 1e3) / 1e9 / peak, "algorithmic_bytes_per_launch": f_bytes, "traffic": None},
+                                          "check": "byte-identical to assemble + store on this slice"}}
 
 
     return {"assemble_bases": assemble, "assemble_records": assemble_rec, "e2e_records": measure_e2e_records(args, ctx, s, L, extras_for)}

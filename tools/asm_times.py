@@ -18,4 +18,4 @@ bench_records.measure_e2e_records = lambda *a, **k: None
 r = bench_records.measure(args, ctx, s, L, ch, peak)
 a = r["assemble_records"]
 print(os.path.basename(os.environ.get("PORTELLO_B200_LIB", "default")), wl, "bam_write ms", round(a["kernel_ms"], 4), "frac", round(a["roofline"]["frac"], 3),
-      "bgzf ms", round(a["bgzf_store"]["kernel_ms"], 4), "bases ms", round(r["assemble_bases"]["kernel_ms"], 4), "flipped", r["assemble_bases"]["flipped_records"])
+      "bgzf ms", round(a["bgzf_store"]["kernel_ms"], 4), "FUSED ms", round(a["frame_records"]["kernel_ms"], 4), "frac", round(a["frame_records"]["roofline"]["frac"], 3), "bases ms", round(r["assemble_bases"]["kernel_ms"], 4), "flipped", r["assemble_bases"]["flipped_records"])
