@@ -175,67 +175,182 @@ struct FrameArgs {
     const uint8_t* prefix; // device copy of the stream prefix (the BAM header), may be nullptr
     uint64_t prefix_bytes;
 };
+// A run = a maximal stretch of the block's payload that comes from ONE source field: the prefix, the small fields of a
+// record (from the sparse scratch), its packed bases or its qualities (plain, or re-oriented for a flipped record).
+// Warp 0 builds the table of the block's runs in shared memory (lanes over records: the descriptor loads of up to 32
+// records are in flight together), then ALL threads walk the block's destination-aligned 16-byte chunks as one flat index
+// space, so that every load of the block is independent of every other (one copy_field call per field, one after the
+// other, left each block waiting through a dozen dependent DRAM round trips: 6.2 ms per 47 k blocks instead of 3.8 ms for
+// the two separate kernels).
+struct FrameRun {
+    int32_t begin;       // payload offset of the run's first byte (may be negative: the field starts in the previous block)
+    uint32_t len;        // bytes of the run inside [0, n)... counted from `begin` (clipped only at the far end)
+    uint32_t kind;       // 0 plain copy, 1 reverse-complemented packed bases, 2 reversed qualities
+    uint32_t l_seq;      // kinds 1, 2: bases of the read
+    const uint8_t* src;  // kind 0: source byte of payload offset `begin`; kinds 1, 2: the read's packed bases / qualities
+    int64_t off;         // kinds 1, 2: field offset of the run's first byte
+};
+constexpr uint32_t kFrameMaxRuns = 132;  // 32 records x 4 fields + the prefix (+ slack)
+constexpr uint32_t kFrameSmemWords = kBgzfSmemWords + kFrameMaxRuns * (sizeof(FrameRun) / 4u) + 8u;
+
+// 16 bytes of run r at run-relative offset o (bytes outside the run: unspecified), bounds-guarded
+__device__ __forceinline__ uint4 frame_produce_guarded(const FrameRun& r, int64_t o) {
+    if (r.kind == 0u) return window128_guarded(r.src, o, int64_t(r.len));
+    const int64_t len = r.l_seq;
+    if (r.kind == 1u) return revcomp_chunk(r.src, len, o + r.off);
+    const uint4 q = window128_lean(r.src, len - 16 - (o + r.off), len);
+    uint4 v;
+    v.x = __byte_perm(q.w, 0u, 0x0123u);
+    v.y = __byte_perm(q.z, 0u, 0x0123u);
+    v.z = __byte_perm(q.y, 0u, 0x0123u);
+    v.w = __byte_perm(q.x, 0u, 0x0123u);
+    return v;
+}
+
 __device__ __forceinline__ void bgzf_frame_block_body(const FrameArgs& F, uint64_t b, uint32_t tid, uint32_t* sm) {
     const BamAsmArgs& A = F.A;
+    FrameRun* runs = reinterpret_cast<FrameRun*>(sm + kBgzfSmemWords);
+    uint32_t* ctl = sm + kBgzfSmemWords + kFrameMaxRuns * (sizeof(FrameRun) / 4u);  // [0] runs of this pass, [1] next record, [2] done
     const uint64_t x0 = b * kBgzfIn;
     const uint32_t n = uint32_t(min(uint64_t(kBgzfIn), F.Z.n - x0));
     const uint64_t x1 = x0 + n;
     uint8_t* dst = F.Z.out + b * uint64_t(kBgzfIn + kBgzfOverhead);
     uint8_t* data_dst = dst + 23;
+    const uint32_t lane = tid & 31u;
     bgzf_write_header(dst, n, tid);
-    if (x0 < F.prefix_bytes) copy_field(data_dst, F.prefix + x0, uint32_t((x1 < F.prefix_bytes ? x1 : F.prefix_bytes) - x0), tid, 256u);
-    if (x1 > F.prefix_bytes && A.n_records) {
-        // record-space range [r0, r1) of this block; first record = last k with rec_begin[k] <= r0 (the same search in every thread)
-        const uint64_t xs = x0 > F.prefix_bytes ? x0 : F.prefix_bytes;
-        const uint64_t r0 = xs - F.prefix_bytes, r1 = x1 - F.prefix_bytes;
-        uint8_t* const out0 = data_dst + (xs - x0);  // where record-space byte r0 goes
-        uint32_t lo = 0, hi = A.n_records;
-        while (hi - lo > 1u) {
-            const uint32_t mid = (lo + hi) >> 1;
-            if (A.rec_begin[mid] <= r0) lo = mid; else hi = mid;
-        }
-        for (uint32_t k = lo; k < A.n_records; ++k) {
-            const uint64_t rb = A.rec_begin[k];
-            if (rb >= r1) break;
-            const BamRecLayout L = BamRecLayout::unpack(A.rec_desc + 2 * size_t(k));
-            const uint64_t o_seq = 36ull + L.name_n + 1 + 4ull * L.n_cigar, o_qual = o_seq + L.seq_bytes, o_aux = o_qual + L.l_seq;
-            const bool flip = A.rec_need_flip[k] != 0;
-            const uint8_t* src_s = A.seq4 + A.read_seq_off[L.r];
-            const uint8_t* src_q = A.qual + A.qual_off[L.r];
-            const int64_t len = L.l_seq;
-            // the four fields of the record, each clipped to [r0, r1): [fa, fb) in record coordinates
-            auto clip = [&](uint64_t fa, uint64_t fb, uint64_t& ia, uint64_t& ib) {
-                const uint64_t lo_c = r0 > rb ? r0 - rb : 0ull, hi_c = r1 - rb;
-                ia = fa > lo_c ? fa : lo_c;
-                ib = fb < hi_c ? fb : hi_c;
-                return ia < ib;
-            };
-            uint64_t ia, ib;
-            if (clip(0, o_seq, ia, ib)) copy_field(out0 + (rb + ia - r0), A.out + rb + ia, uint32_t(ib - ia), tid, 256u);
-            if (clip(o_seq, o_qual, ia, ib)) {
-                uint8_t* d = out0 + (rb + ia - r0);
-                const int64_t off = int64_t(ia - o_seq);
-                if (!flip) copy_field(d, src_s + off, uint32_t(ib - ia), tid, 256u);
-                else emit_field(d, int64_t(ib - ia), tid, 256u, [&](int64_t o) { return revcomp_chunk(src_s, len, o + off); });
+    // record-space range of this block
+    const bool has_recs = x1 > F.prefix_bytes && A.n_records;
+    const uint64_t xs = x0 > F.prefix_bytes ? x0 : F.prefix_bytes;
+    const uint64_t r0 = xs - F.prefix_bytes, r1 = has_recs ? x1 - F.prefix_bytes : 0ull;
+    const int64_t rec_shift = int64_t(F.prefix_bytes) - int64_t(x0);  // payload offset = record-space offset + rec_shift
+    uint32_t k_next = 0;
+    bool first_pass = true;
+    for (;;) {
+        // ---- warp 0: the runs of up to 32 records (and the prefix on the first pass)
+        if (tid < 32u) {
+            uint32_t base = 0;
+            if (first_pass) {
+                if (x0 < F.prefix_bytes) {
+                    if (lane == 0) runs[0] = FrameRun{0, uint32_t((x1 < F.prefix_bytes ? x1 : F.prefix_bytes) - x0), 0u, 0u, F.prefix + x0, 0};
+                    base = 1;
+                }
+                if (has_recs) {  // first record = last k with rec_begin[k] <= r0: a 32-ary search, one probe per lane and round
+                    uint32_t lo = 0, hi = A.n_records;  // invariant: rec_begin[lo] <= r0 < rec_begin[hi] (rec_begin[n_records] = total > r0)
+                    while (hi - lo > 1u) {
+                        const uint32_t step = (hi - lo + 31u) / 32u;
+                        const uint32_t probe = lo + lane * step;
+                        const bool le = probe < hi && A.rec_begin[probe] <= r0;
+                        const uint32_t m = __ballot_sync(0xffffffffu, le);  // (lane 0 probes lo: always set)
+                        const uint32_t top = 31u - uint32_t(__clz(int(m)));
+                        const uint32_t nlo = lo + top * step;
+                        hi = min(hi, nlo + step);
+                        lo = nlo;
+                    }
+                    k_next = lo;
+                }
             }
-            if (clip(o_qual, o_aux, ia, ib)) {
-                uint8_t* d = out0 + (rb + ia - r0);
-                const int64_t off = int64_t(ia - o_qual);
-                if (!flip) copy_field(d, src_q + off, uint32_t(ib - ia), tid, 256u);
-                else emit_field(d, int64_t(ib - ia), tid, 256u, [&](int64_t o) {
-                    const uint4 s = window128_lean(src_q, len - 16 - (o + off), len);  // the 16 bytes in front of the mirrored position
+            uint32_t cnt = 0;
+            FrameRun mine[4];
+            bool started = false;
+            if (has_recs) {
+                const uint32_t k = k_next + lane;
+                if (k < A.n_records) {
+                    const uint64_t rb = A.rec_begin[k];
+                    if (rb < r1) {
+                        started = true;
+                        const BamRecLayout L = BamRecLayout::unpack(A.rec_desc + 2 * size_t(k));
+                        const uint64_t o_seq = 36ull + L.name_n + 1 + 4ull * L.n_cigar, o_qual = o_seq + L.seq_bytes, o_aux = o_qual + L.l_seq;
+                        const bool flip = A.rec_need_flip[k] != 0;
+                        const uint8_t* src_s = A.seq4 + A.read_seq_off[L.r];
+                        const uint8_t* src_q = A.qual + A.qual_off[L.r];
+                        const uint64_t fa[5] = {0, o_seq, o_qual, o_aux, L.total};
+#pragma unroll
+                        for (int f = 0; f < 4; ++f) {
+                            const uint64_t lo_c = r0 > rb ? r0 - rb : 0ull, hi_c = r1 - rb;
+                            const uint64_t ia = fa[f] > lo_c ? fa[f] : lo_c, ib = fa[f + 1] < hi_c ? fa[f + 1] : hi_c;
+                            if (ia >= ib) continue;
+                            FrameRun r;
+                            r.begin = int32_t(int64_t(rb + ia) + rec_shift);
+                            r.len = uint32_t(ib - ia);
+                            r.l_seq = L.l_seq;
+                            if (f == 0 || f == 3) { r.kind = 0u; r.src = A.out + rb + ia; r.off = 0; }
+                            else if (f == 1) { r.kind = flip ? 1u : 0u; r.src = flip ? src_s : src_s + (ia - o_seq); r.off = int64_t(ia - o_seq); }
+                            else { r.kind = flip ? 2u : 0u; r.src = flip ? src_q : src_q + (ia - o_qual); r.off = int64_t(ia - o_qual); }
+                            mine[cnt++] = r;
+                        }
+                    }
+                }
+            }
+            uint32_t incl = cnt;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+                if (int(lane) >= d) incl += o;
+            }
+            const uint32_t at = base + incl - cnt;
+            for (uint32_t i = 0; i < cnt; ++i) runs[at + i] = mine[i];
+            const uint32_t n_started = uint32_t(__popc(__ballot_sync(0xffffffffu, started)));
+            if (lane == 31u) {
+                ctl[0] = base + incl;
+                ctl[1] = k_next + n_started;
+                // done: fewer than 32 records started here, or the next record begins behind the block
+                const uint32_t kn = k_next + n_started;
+                ctl[2] = (!has_recs || n_started < 32u || kn >= A.n_records || A.rec_begin[kn] >= r1) ? 1u : 0u;
+            }
+        }
+        __syncthreads();
+        const uint32_t n_runs = ctl[0];
+        const bool done = ctl[2] != 0u;
+        k_next = ctl[1];
+        // ---- all threads: the destination-aligned 16-byte chunks that touch the runs of this pass
+        if (n_runs) {
+            const int32_t span0 = max(runs[0].begin, 0);
+            const int32_t span1 = min(int32_t(n), runs[n_runs - 1].begin + int32_t(runs[n_runs - 1].len));
+            const int32_t a0 = int32_t(reinterpret_cast<uint64_t>(data_dst) & 15ull);  // chunk c covers payload [16 c - a0, + 16)
+            const int32_t c0 = (span0 + a0) >> 4, c1 = (span1 + a0 + 15) >> 4;
+            uint32_t ri = 0;
+            for (int32_t c = c0 + int32_t(tid); c < c1; c += 256) {
+                const int32_t o = 16 * c - a0;
+                while (ri + 1u < n_runs && runs[ri + 1u].begin <= o) ++ri;
+                const FrameRun r = runs[ri];
+                const int32_t rel = o - r.begin;
+                if (rel >= 0 && rel + 16 <= int32_t(r.len) && o >= span0 && o + 16 <= span1) {  // (almost every chunk)
                     uint4 v;
-                    v.x = __byte_perm(s.w, 0u, 0x0123u);
-                    v.y = __byte_perm(s.z, 0u, 0x0123u);
-                    v.z = __byte_perm(s.y, 0u, 0x0123u);
-                    v.w = __byte_perm(s.x, 0u, 0x0123u);
-                    return v;
-                });
+                    if (r.kind == 0u) {
+                        v = window128_body(r.src + rel);
+                    } else if (r.kind == 1u) {
+                        v = revcomp_chunk(r.src, int64_t(r.l_seq), int64_t(rel) + r.off);
+                    } else {
+                        const int64_t len = r.l_seq;
+                        const uint4 q = window128_lean(r.src, len - 16 - (int64_t(rel) + r.off), len);
+                        v.x = __byte_perm(q.w, 0u, 0x0123u);
+                        v.y = __byte_perm(q.z, 0u, 0x0123u);
+                        v.z = __byte_perm(q.y, 0u, 0x0123u);
+                        v.w = __byte_perm(q.x, 0u, 0x0123u);
+                    }
+                    *reinterpret_cast<uint4*>(data_dst + o) = v;
+                } else {  // a chunk across a run boundary (or at an end of the payload): every run that touches it stores its own bytes
+                    for (uint32_t rj = ri; rj < n_runs && runs[rj].begin < o + 16; ++rj) {
+                        const FrameRun q = runs[rj];
+                        const int64_t rl = int64_t(o) - q.begin;
+                        if (rl + 16 <= 0) continue;
+                        // bytes of the run inside [0, n) only (a run never reaches past n; it may start before 0)
+                        const uint4 v = frame_produce_guarded(q, rl);
+                        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                        for (int t = 0; t < 16; ++t) {
+                            const int64_t pr = rl + t;           // run-relative
+                            const int32_t pp = o + t;            // payload
+                            if (pr >= 0 && pr < int64_t(q.len) && pp >= 0 && pp < int32_t(n)) data_dst[pp] = uint8_t(w[t >> 2] >> (8 * (t & 3)));
+                        }
+                    }
+                }
             }
-            if (clip(o_aux, L.total, ia, ib)) copy_field(out0 + (rb + ia - r0), A.out + rb + ia, uint32_t(ib - ia), tid, 256u);
         }
+        __syncthreads();  // (the table is rebuilt by the next pass; after the last pass: the payload is complete and visible)
+        first_pass = false;
+        if (done) break;
     }
-    __syncthreads();  // the payload is complete (and visible to the block) before its CRC is read back
     bgzf_crc_and_footer(F.Z, data_dst, n, data_dst, tid, sm);
     __syncthreads();  // (warp_crc is reused by the next block of this persistent thread block)
 }

@@ -689,7 +689,7 @@ void launch_bam_frame(const FrameArgs& F, cudaStream_t st, uint64_t* launches) {
         ++*launches;
     }
     if (!F.Z.n_blocks) return;
-    const int smem = int(kBgzfSmemWords * 4u);
+    const int smem = int(kFrameSmemWords * 4u);
     cudaFuncSetAttribute(bam_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     bam_frame_kernel<<<unsigned(std::min<uint64_t>(F.Z.n_blocks, 148ull * 4)), 256, smem, st>>>(F);
     ++*launches;
