@@ -308,39 +308,59 @@ __device__ __forceinline__ void bgzf_frame_block_body(const FrameArgs& F, uint64
             const int32_t span1 = min(int32_t(n), runs[n_runs - 1].begin + int32_t(runs[n_runs - 1].len));
             const int32_t a0 = int32_t(reinterpret_cast<uint64_t>(data_dst) & 15ull);  // chunk c covers payload [16 c - a0, + 16)
             const int32_t c0 = (span0 + a0) >> 4, c1 = (span1 + a0 + 15) >> 4;
+            // four chunks of a thread in flight: all their loads are issued before the first store (one chunk at a time
+            // left a single DRAM round trip per thread in flight: 2.4 TB/s at best)
             uint32_t ri = 0;
-            for (int32_t c = c0 + int32_t(tid); c < c1; c += 256) {
-                const int32_t o = 16 * c - a0;
-                while (ri + 1u < n_runs && runs[ri + 1u].begin <= o) ++ri;
-                const FrameRun r = runs[ri];
-                const int32_t rel = o - r.begin;
-                if (rel >= 0 && rel + 16 <= int32_t(r.len) && o >= span0 && o + 16 <= span1) {  // (almost every chunk)
-                    uint4 v;
-                    if (r.kind == 0u) {
-                        v = window128_body(r.src + rel);
-                    } else if (r.kind == 1u) {
-                        v = revcomp_chunk(r.src, int64_t(r.l_seq), int64_t(rel) + r.off);
-                    } else {
-                        const int64_t len = r.l_seq;
-                        const uint4 q = window128_lean(r.src, len - 16 - (int64_t(rel) + r.off), len);
-                        v.x = __byte_perm(q.w, 0u, 0x0123u);
-                        v.y = __byte_perm(q.z, 0u, 0x0123u);
-                        v.z = __byte_perm(q.y, 0u, 0x0123u);
-                        v.w = __byte_perm(q.x, 0u, 0x0123u);
+            for (int32_t c = c0 + int32_t(tid); c < c1; c += 4 * 256) {
+                uint4 v[4];
+                int32_t o[4];
+                uint32_t rix[4];
+                bool valid[4], fast[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int32_t cc = c + 256 * u;
+                    valid[u] = cc < c1;
+                    o[u] = 16 * cc - a0;
+                    fast[u] = false;
+                    if (valid[u]) {
+                        while (ri + 1u < n_runs && runs[ri + 1u].begin <= o[u]) ++ri;
+                        rix[u] = ri;
+                        const FrameRun r = runs[ri];
+                        const int32_t rel = o[u] - r.begin;
+                        if (rel >= 0 && rel + 16 <= int32_t(r.len) && o[u] >= span0 && o[u] + 16 <= span1) {  // (almost every chunk)
+                            fast[u] = true;
+                            if (r.kind == 0u) {
+                                v[u] = window128_body(r.src + rel);
+                            } else if (r.kind == 1u) {
+                                v[u] = revcomp_chunk(r.src, int64_t(r.l_seq), int64_t(rel) + r.off);
+                            } else {
+                                const int64_t len = r.l_seq;
+                                const uint4 q = window128_lean(r.src, len - 16 - (int64_t(rel) + r.off), len);
+                                v[u].x = __byte_perm(q.w, 0u, 0x0123u);
+                                v[u].y = __byte_perm(q.z, 0u, 0x0123u);
+                                v[u].z = __byte_perm(q.y, 0u, 0x0123u);
+                                v[u].w = __byte_perm(q.x, 0u, 0x0123u);
+                            }
+                        }
                     }
-                    *reinterpret_cast<uint4*>(data_dst + o) = v;
-                } else {  // a chunk across a run boundary (or at an end of the payload): every run that touches it stores its own bytes
-                    for (uint32_t rj = ri; rj < n_runs && runs[rj].begin < o + 16; ++rj) {
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (fast[u]) *reinterpret_cast<uint4*>(data_dst + o[u]) = v[u];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (!valid[u] || fast[u]) continue;
+                    // a chunk across a run boundary (or at an end of the payload): every run that touches it stores its own bytes
+                    for (uint32_t rj = rix[u]; rj < n_runs && runs[rj].begin < o[u] + 16; ++rj) {
                         const FrameRun q = runs[rj];
-                        const int64_t rl = int64_t(o) - q.begin;
+                        const int64_t rl = int64_t(o[u]) - q.begin;
                         if (rl + 16 <= 0) continue;
-                        // bytes of the run inside [0, n) only (a run never reaches past n; it may start before 0)
-                        const uint4 v = frame_produce_guarded(q, rl);
-                        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+                        const uint4 w4 = frame_produce_guarded(q, rl);
+                        const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
                         for (int t = 0; t < 16; ++t) {
                             const int64_t pr = rl + t;           // run-relative
-                            const int32_t pp = o + t;            // payload
+                            const int32_t pp = o[u] + t;         // payload
                             if (pr >= 0 && pr < int64_t(q.len) && pp >= 0 && pp < int32_t(n)) data_dst[pp] = uint8_t(w[t >> 2] >> (8 * (t & 3)));
                         }
                     }
