@@ -450,10 +450,10 @@ def test_gpu_frame_records_equals_assemble_then_store(case):
     if case == "iupac-odd":
         s, pb = iupac_case(13, n_reads=2500)   # records of 1..900 bases: many records per BGZF block
     elif case == "wg-flips":
-        s = synth.make("tiny", seed=19, n_reads=3000, rev_contig_frac=0.9, read_len_mean=9000, read_len_sd=2500, read_len_min=2000, read_len_max=15000)
+        s = synth.make("tiny", seed=19, n_reads=900, rev_contig_frac=0.9, read_len_mean=9000, read_len_sd=2500, read_len_min=2000, read_len_max=15000)
         pb = helpers.pack(s)
     else:
-        s = synth.make(case, **({"n_reads": 3000} if case == "config1" else {}))
+        s = synth.make(case, **({"n_reads": 600} if case == "config1" else {}))
         pb = helpers.pack(s)
     gctx = helpers.gpu_context(s)
     gctx.set_names(s.contig_names, s.chrom_names)

@@ -79,3 +79,56 @@ def test_two_rank_sharding_matches_single_process_cpu(tmp_path):
 @pytest.mark.gpu
 def test_two_rank_sharding_matches_single_process_gpu(tmp_path):
     _run(tmp_path, use_gpu=True)
+
+
+def _bench_module():
+    import importlib.util
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_for_tests", os.path.join(root, "bench.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["bench_for_tests"] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _shard_digest_worker(rank, world, port, out_path):
+    """bench.py's own N > 1 flow on CPU: plan the whole read set, split it by the reference's work units (LPT), generate and
+    lift ONLY this rank's units (the oracle stands in for the GPU), digest the shard with global read indices, gather the
+    digests on the control plane: their sum must be the digest of the unsharded run."""
+    import argparse
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from portello_b200.digest import Digest
+        bench = _bench_module()
+        args = argparse.Namespace(workload="tiny", reads=2000)
+        s, gri, units, owner, loads = bench.make_shard(args, rank, world, assign=shard.assign)
+        assert s.read_records.n_reads == len(gri) == int(loads[rank])
+        pb = helpers.pack(s)
+        r = helpers.lift_c(helpers.oracle_context(s, threads=1), pb.c)
+        d = Digest().add(r, np.ctypeslib.as_array(pb.c.read_seg_begin, (pb.c.n_reads + 1,)), gri)
+        parts = [None] * world
+        dist.all_gather_object(parts, d.as_tuple())
+        if rank == 0:
+            tot = Digest()
+            for p in parts:
+                o = Digest()
+                o.acc, o.n_records, o.n_ops, o.n_reads = p
+                tot.merge(o)
+            s1, gri1, _, _, _ = bench.make_shard(args, 0, 1)
+            pb1 = helpers.pack(s1)
+            r1 = helpers.lift_c(helpers.oracle_context(s1, threads=1), pb1.c)
+            whole = Digest().add(r1, np.ctypeslib.as_array(pb1.c.read_seg_begin, (pb1.c.n_reads + 1,)), gri1)
+            with open(out_path, "w") as fh:
+                fh.write(f"{int(tot == whole)} {tot.n_reads} {int(loads.min())} {int(loads.max())}")
+    finally:
+        dist.destroy_process_group()
+
+
+def test_bench_sharding_digest_is_the_unsharded_digest(tmp_path):
+    out = str(tmp_path / "digest.txt")
+    mp.spawn(_shard_digest_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    ok, n, lo, hi = map(int, open(out).read().split())
+    assert ok == 1 and n == 2000
+    assert lo + hi == 2000 and hi <= 1.5 * lo
