@@ -72,12 +72,43 @@ __device__ __forceinline__ void bgzf_write_header(uint8_t* dst, uint32_t n, uint
         for (int i = 0; i < 23; ++i) dst[i] = h[i];
     }
 }
+// The zero-state CRCs of the 256 slices (slice of thread t ends 256 (255 - t) bytes before the end of the sliced data) ->
+// the block's CRC-32 and the footer.  `tail_len` (< 16) bytes with zero-state CRC `tail_crc` may follow the sliced data.
+__device__ __forceinline__ void bgzf_crc_combine_footer(const BgzfArgs& A, uint32_t crc, uint32_t n, uint8_t* data_dst, uint32_t tid, uint32_t* sm,
+                                                        uint32_t tail_len, uint32_t tail_crc) {
+    uint32_t* t0 = sm;
+    uint32_t* shift = sm + 256;
+    uint32_t* warp_crc = shift + 9 * 128 + 128 * 32;
+    const uint32_t lane = tid & 31u;
+    // tree combine: after level k a thread with tid % 2^(k+1) == 0 holds the CRC of 2^(k+1) slices
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        const uint32_t right = __shfl_down_sync(0xffffffffu, crc, 1u << k);
+        if ((lane & ((2u << k) - 1u)) == 0u) crc = gf2_apply_nibbles(shift + 128 * (k + 1), crc) ^ right;
+    }
+    if (lane == 0) warp_crc[tid >> 5] = crc;
+    __syncthreads();
+    if (tid < 32u) {
+        crc = tid < 8u ? warp_crc[tid] : 0u;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const uint32_t right = __shfl_down_sync(0xffffffffu, crc, 1u << k);
+            if ((tid & ((2u << k) - 1u)) == 0u) crc = gf2_apply_nibbles(shift + 128 * (6 + k), crc) ^ right;
+        }
+        if (tid == 0) {  // footer: CRC32, ISIZE
+            for (uint32_t i = 0; i < tail_len; ++i) crc = t0[crc & 0xffu] ^ (crc >> 8);  // through tail_len zero bytes
+            crc ^= tail_crc;
+            const uint32_t full = ((n == kBgzfIn) ? A.init_full : A.init_last) ^ crc ^ 0xffffffffu;
+            uint8_t* f = data_dst + n;
+            for (int i = 0; i < 4; ++i) { f[i] = uint8_t(full >> (8 * i)); f[4 + i] = uint8_t(n >> (8 * i)); }
+        }
+    }
+}
 // CRC-32 of the n payload bytes at `src` (block-cooperative, 256 threads) and the footer (CRC32, ISIZE) behind data_dst.
 __device__ __forceinline__ void bgzf_crc_and_footer(const BgzfArgs& A, const uint8_t* src, uint32_t n, uint8_t* data_dst, uint32_t tid, uint32_t* sm) {
     uint32_t* t0 = sm;
     uint32_t* shift = sm + 256;
     uint32_t* wl = shift + 9 * 128;  // per-lane word-step tables: entry e of lane l at wl[32 e + l]
-    uint32_t* warp_crc = wl + 128 * 32;
     const uint32_t lane = tid & 31u;
     // ---- zero-state CRC of this thread's 256-byte slice, slices counted back from the end of the data; its two halves run
     //      as two independent chains; every thread reads its slice straight from global memory (16 bytes per step: five
@@ -127,28 +158,7 @@ __device__ __forceinline__ void bgzf_crc_and_footer(const BgzfArgs& A, const uin
             crc_b = chain(mid, s_end);
         }
     }
-    uint32_t crc = gf2_apply_nibbles(shift, crc_a) ^ crc_b;  // (|B| = 128 whenever A is not empty)
-    // tree combine: after level k a thread with tid % 2^(k+1) == 0 holds the CRC of 2^(k+1) slices
-#pragma unroll
-    for (int k = 0; k < 5; ++k) {
-        const uint32_t right = __shfl_down_sync(0xffffffffu, crc, 1u << k);
-        if ((lane & ((2u << k) - 1u)) == 0u) crc = gf2_apply_nibbles(shift + 128 * (k + 1), crc) ^ right;
-    }
-    if (lane == 0) warp_crc[tid >> 5] = crc;
-    __syncthreads();
-    if (tid < 32u) {
-        crc = tid < 8u ? warp_crc[tid] : 0u;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const uint32_t right = __shfl_down_sync(0xffffffffu, crc, 1u << k);
-            if ((tid & ((2u << k) - 1u)) == 0u) crc = gf2_apply_nibbles(shift + 128 * (6 + k), crc) ^ right;
-        }
-        if (tid == 0) {  // footer: CRC32, ISIZE
-            const uint32_t full = ((n == kBgzfIn) ? A.init_full : A.init_last) ^ crc ^ 0xffffffffu;
-            uint8_t* f = data_dst + n;
-            for (int i = 0; i < 4; ++i) { f[i] = uint8_t(full >> (8 * i)); f[4 + i] = uint8_t(n >> (8 * i)); }
-        }
-    }
+    bgzf_crc_combine_footer(A, gf2_apply_nibbles(shift, crc_a) ^ crc_b, n, data_dst, tid, sm, 0u, 0u);  // (|B| = 128 whenever A is not empty)
 }
 __device__ __forceinline__ void bgzf_store_block_body(const BgzfArgs& A, uint64_t b, uint32_t tid, uint32_t* sm) {
     const uint64_t in_off = b * kBgzfIn;
@@ -205,6 +215,146 @@ __device__ __forceinline__ uint4 frame_produce_guarded(const FrameRun& r, int64_
     v.z = __byte_perm(q.y, 0u, 0x0123u);
     v.w = __byte_perm(q.x, 0u, 0x0123u);
     return v;
+}
+
+// ---- single pass: produce -> CRC -> store, every byte handled once (blocks whose runs all fit the table) ----------------
+__device__ __forceinline__ uint32_t crc_word_step(const uint32_t* __restrict__ wl, uint32_t lane, uint32_t crc, uint32_t w) {
+    crc ^= w;
+    uint32_t r = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r ^= wl[32u * (16u * j + ((crc >> (4 * j)) & 15u)) + lane];
+    return r;
+}
+__device__ __forceinline__ uint32_t crc_chunk(const uint32_t* __restrict__ wl, uint32_t lane, uint32_t crc, const uint4& v) {
+    return crc_word_step(wl, lane, crc_word_step(wl, lane, crc_word_step(wl, lane, crc_word_step(wl, lane, crc, v.x), v.y), v.z), v.w);
+}
+// 16 payload bytes at payload offset o (0 <= o, o + 16 <= n) from the run table; `ri` = a cursor that only moves forward
+__device__ __forceinline__ uint4 frame_chunk(const FrameRun* __restrict__ runs, uint32_t n_runs, uint32_t& ri, int32_t o) {
+    while (ri + 1u < n_runs && runs[ri + 1u].begin <= o) ++ri;
+    const FrameRun r = runs[ri];
+    const int32_t rel = o - r.begin;
+    if (rel >= 0 && rel + 16 <= int32_t(r.len)) {
+        if (r.kind == 0u) return (rel + 20 <= int32_t(r.len)) ? window128_body(r.src + rel) : window128_guarded(r.src, rel, int64_t(r.len));
+        return frame_produce_guarded(r, rel);
+    }
+    uint32_t w[4] = {0u, 0u, 0u, 0u};  // across a run boundary: every run that touches the chunk contributes its own bytes
+    for (uint32_t rj = ri; rj < n_runs && runs[rj].begin < o + 16; ++rj) {
+        const FrameRun q = runs[rj];
+        const int64_t rl = int64_t(o) - q.begin;
+        if (rl + 16 <= 0) continue;
+        const uint4 v = frame_produce_guarded(q, rl);
+        const uint32_t x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+            const int64_t pr = rl + t;
+            if (pr >= 0 && pr < int64_t(q.len)) w[t >> 2] |= ((x[t >> 2] >> (8 * (t & 3))) & 0xffu) << (8 * (t & 3));
+        }
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+// one payload byte (the < 16 bytes in front of the first aligned chunk and behind the last one)
+__device__ __forceinline__ uint32_t frame_byte(const FrameRun* __restrict__ runs, uint32_t n_runs, int32_t p) {
+    uint32_t ri = 0;
+    while (ri + 1u < n_runs && runs[ri + 1u].begin <= p) ++ri;
+    return frame_produce_guarded(runs[ri], int64_t(p) - runs[ri].begin).x & 0xffu;
+}
+// two aligned 16-byte loads -> the 16 bytes at byte offset 4 WS + bs / 8 of their 32
+template <int WS>
+__device__ __forceinline__ uint4 shift128(const uint4& a, const uint4& b, uint32_t bs) {
+    uint32_t x0, x1, x2, x3, x4;
+    if (WS == 0) { x0 = a.x; x1 = a.y; x2 = a.z; x3 = a.w; x4 = b.x; }
+    else if (WS == 1) { x0 = a.y; x1 = a.z; x2 = a.w; x3 = b.x; x4 = b.y; }
+    else if (WS == 2) { x0 = a.z; x1 = a.w; x2 = b.x; x3 = b.y; x4 = b.z; }
+    else { x0 = a.w; x1 = b.x; x2 = b.y; x3 = b.z; x4 = b.w; }
+    return make_uint4(__funnelshift_r(x0, x1, bs), __funnelshift_r(x1, x2, bs), __funnelshift_r(x2, x3, bs), __funnelshift_r(x3, x4, bs));
+}
+// a full 256-byte slice that is a plain copy of one source: its two halves as two interleaved chains, ONE new aligned
+// 128-bit load per chunk and chain (thread-contiguous addresses: a 32-bit-word window costs five L1 wavefronts per lane
+// and chunk, which is what made the re-reading CRC phase L1-bound)
+template <int WS>
+__device__ __forceinline__ void frame_slice_plain(const uint4* __restrict__ base, uint32_t bs, uint4* __restrict__ d, const uint32_t* __restrict__ wl,
+                                                  uint32_t lane, uint32_t& crc_a, uint32_t& crc_b) {
+    uint4 pa = base[0], pb = base[8];
+#pragma unroll 2
+    for (int i = 0; i < 8; ++i) {
+        const uint4 na = base[i + 1], nb = base[i + 9];
+        const uint4 va = shift128<WS>(pa, na, bs), vb = shift128<WS>(pb, nb, bs);
+        d[i] = va;
+        d[i + 8] = vb;
+        crc_a = crc_word_step(wl, lane, crc_a, va.x); crc_b = crc_word_step(wl, lane, crc_b, vb.x);
+        crc_a = crc_word_step(wl, lane, crc_a, va.y); crc_b = crc_word_step(wl, lane, crc_b, vb.y);
+        crc_a = crc_word_step(wl, lane, crc_a, va.z); crc_b = crc_word_step(wl, lane, crc_b, vb.z);
+        crc_a = crc_word_step(wl, lane, crc_a, va.w); crc_b = crc_word_step(wl, lane, crc_b, vb.w);
+        pa = na;
+        pb = nb;
+    }
+}
+__device__ __forceinline__ void bgzf_frame_single_pass(const FrameArgs& F, const FrameRun* __restrict__ runs, uint32_t n_runs, uint32_t n, uint8_t* data_dst,
+                                                       uint32_t tid, uint32_t* sm) {
+    const uint32_t* t0 = sm;
+    const uint32_t* shift = sm + 256;
+    const uint32_t* wl = shift + 9 * 128;
+    const uint32_t lane = tid & 31u;
+    // slices are counted back from the last 16-byte boundary of the DESTINATION inside the payload, so that every chunk is
+    // an aligned store; the < 16 bytes behind it are folded in by thread 0 (bgzf_crc_combine_footer)
+    const int32_t a0 = int32_t(reinterpret_cast<uint64_t>(data_dst) & 15ull);
+    int32_t tail = (int32_t(n) + a0) & 15;
+    if (tail > int32_t(n)) tail = int32_t(n);
+    const int32_t e_al = int32_t(n) - tail;
+    const int32_t s_end = e_al - 256 * int32_t(255u - tid);
+    const int32_t s_begin = max(s_end - 256, 0);
+    uint32_t crc_a = 0, crc_b = 0;
+    auto range = [&](int32_t p0, int32_t p1, uint32_t crc) {  // produce, store and CRC payload [p0, p1); p1 is chunk-aligned
+        int32_t p = p0;
+        for (; p < p1 && ((p + a0) & 15); ++p) {  // (only in front of the very first chunk of the block)
+            const uint32_t bv = frame_byte(runs, n_runs, p);
+            data_dst[p] = uint8_t(bv);
+            crc = t0[(crc ^ bv) & 0xffu] ^ (crc >> 8);
+        }
+        uint32_t ri = 0;
+        for (; p + 16 <= p1; p += 16) {
+            const uint4 v = frame_chunk(runs, n_runs, ri, p);
+            *reinterpret_cast<uint4*>(data_dst + p) = v;
+            crc = crc_chunk(wl, lane, crc, v);
+        }
+        return crc;
+    };
+    if (s_end > 0) {
+        bool fast = false;
+        if (s_end - s_begin == 256) {
+            uint32_t ri = 0;
+            while (ri + 1u < n_runs && runs[ri + 1u].begin <= s_begin) ++ri;
+            const FrameRun r = runs[ri];
+            const int32_t rel = s_begin - r.begin;
+            if (r.kind == 0u && rel >= 0 && rel + 256 + 32 <= int32_t(r.len)) {  // (+ 32: the look-ahead load stays inside the run)
+                fast = true;
+                const uint64_t sa = reinterpret_cast<uint64_t>(r.src + rel);
+                const uint4* base = reinterpret_cast<const uint4*>(sa & ~15ull);
+                const uint32_t bs = uint32_t(sa & 3ull) * 8u;
+                uint4* d = reinterpret_cast<uint4*>(data_dst + s_begin);
+                switch (uint32_t(sa & 15ull) >> 2) {
+                    case 0: frame_slice_plain<0>(base, bs, d, wl, lane, crc_a, crc_b); break;
+                    case 1: frame_slice_plain<1>(base, bs, d, wl, lane, crc_a, crc_b); break;
+                    case 2: frame_slice_plain<2>(base, bs, d, wl, lane, crc_a, crc_b); break;
+                    default: frame_slice_plain<3>(base, bs, d, wl, lane, crc_a, crc_b); break;
+                }
+            }
+        }
+        if (!fast) {
+            const int32_t mid = (s_end - s_begin == 256) ? s_begin + 128 : max(s_end - 128, s_begin);
+            crc_a = range(s_begin, mid, 0u);
+            crc_b = range(mid, s_end, 0u);
+        }
+    }
+    uint32_t tail_crc = 0;
+    if (tid == 0) {
+        for (int32_t p = e_al; p < int32_t(n); ++p) {
+            const uint32_t bv = frame_byte(runs, n_runs, p);
+            data_dst[p] = uint8_t(bv);
+            tail_crc = t0[(tail_crc ^ bv) & 0xffu] ^ (tail_crc >> 8);
+        }
+    }
+    bgzf_crc_combine_footer(F.Z, gf2_apply_nibbles(shift, crc_a) ^ crc_b, n, data_dst, tid, sm, uint32_t(tail), tail_crc);
 }
 
 __device__ __forceinline__ void bgzf_frame_block_body(const FrameArgs& F, uint64_t b, uint32_t tid, uint32_t* sm) {
@@ -302,6 +452,13 @@ __device__ __forceinline__ void bgzf_frame_block_body(const FrameArgs& F, uint64
         const uint32_t n_runs = ctl[0];
         const bool done = ctl[2] != 0u;
         k_next = ctl[1];
+#ifndef FRAME_TWO_PHASE
+        if (first_pass && done) {  // every run of the block is in the table (any block of real data: <= 32 records)
+            bgzf_frame_single_pass(F, runs, n_runs, n, data_dst, tid, sm);
+            __syncthreads();  // (the table and warp_crc are reused by the next block of this persistent thread block)
+            return;
+        }
+#endif
         // ---- all threads: the destination-aligned 16-byte chunks that touch the runs of this pass
         if (n_runs) {
             const int32_t span0 = max(runs[0].begin, 0);
