@@ -204,7 +204,9 @@ constexpr uint32_t kFrameMaxRuns = 132;  // 32 records x 4 fields + the prefix (
 constexpr uint32_t kFrameSmemWords = kBgzfSmemWords + kFrameMaxRuns * (sizeof(FrameRun) / 4u) + 8u;
 
 // 16 bytes of run r at run-relative offset o (bytes outside the run: unspecified), bounds-guarded
-__device__ __forceinline__ uint4 frame_produce_guarded(const FrameRun& r, int64_t o) {
+// (the rare paths are kept out of line: fully inlined the kernel was 12 k instructions, 200 KB of code, and ran 3x slower
+//  than the two-pass path on instruction fetch alone)
+static __device__ __noinline__ uint4 frame_produce_guarded(const FrameRun& r, int64_t o) {
     if (r.kind == 0u) return window128_guarded(r.src, o, int64_t(r.len));
     const int64_t len = r.l_seq;
     if (r.kind == 1u) return revcomp_chunk(r.src, len, o + r.off);
@@ -217,6 +219,86 @@ __device__ __forceinline__ uint4 frame_produce_guarded(const FrameRun& r, int64_
     return v;
 }
 
+// ---- the run table of (a pass over) one block: warp 0, lanes over records -------------------------------------------
+// Fills runs[] with the prefix run (first pass) and the runs of up to 32 records from k_next on; ctl[0] = runs,
+// ctl[1] = next record, ctl[2] = 1 when no record of the block is left.
+static __device__ __noinline__ void frame_build_runs(const FrameArgs& F, uint64_t x0, uint64_t x1, bool first_pass, uint32_t k_next, FrameRun* runs,
+                                                     uint32_t* ctl, uint32_t lane) {
+    const BamAsmArgs& A = F.A;
+    const bool has_recs = x1 > F.prefix_bytes && A.n_records;
+    const uint64_t xs = x0 > F.prefix_bytes ? x0 : F.prefix_bytes;
+    const uint64_t r0 = xs - F.prefix_bytes, r1 = has_recs ? x1 - F.prefix_bytes : 0ull;
+    const int64_t rec_shift = int64_t(F.prefix_bytes) - int64_t(x0);  // payload offset = record-space offset + rec_shift
+    uint32_t base = 0;
+    if (first_pass) {
+        if (x0 < F.prefix_bytes) {
+            if (lane == 0) runs[0] = FrameRun{0, uint32_t((x1 < F.prefix_bytes ? x1 : F.prefix_bytes) - x0), 0u, 0u, F.prefix + x0, 0};
+            base = 1;
+        }
+        if (has_recs) {  // first record = last k with rec_begin[k] <= r0: a 32-ary search, one probe per lane and round
+            uint32_t lo = 0, hi = A.n_records;  // invariant: rec_begin[lo] <= r0 < rec_begin[hi] (rec_begin[n_records] = total > r0)
+            while (hi - lo > 1u) {
+                const uint32_t step = (hi - lo + 31u) / 32u;
+                const uint32_t probe = lo + lane * step;
+                const bool le = probe < hi && A.rec_begin[probe] <= r0;
+                const uint32_t m = __ballot_sync(0xffffffffu, le);  // (lane 0 probes lo: always set)
+                const uint32_t top = 31u - uint32_t(__clz(int(m)));
+                const uint32_t nlo = lo + top * step;
+                hi = min(hi, nlo + step);
+                lo = nlo;
+            }
+            k_next = lo;
+        }
+    }
+    uint32_t cnt = 0;
+    FrameRun mine[4];
+    bool started = false;
+    if (has_recs) {
+        const uint32_t k = k_next + lane;
+        if (k < A.n_records) {
+            const uint64_t rb = A.rec_begin[k];
+            if (rb < r1) {
+                started = true;
+                const BamRecLayout L = BamRecLayout::unpack(A.rec_desc + 2 * size_t(k));
+                const uint64_t o_seq = 36ull + L.name_n + 1 + 4ull * L.n_cigar, o_qual = o_seq + L.seq_bytes, o_aux = o_qual + L.l_seq;
+                const bool flip = A.rec_need_flip[k] != 0;
+                const uint8_t* src_s = A.seq4 + A.read_seq_off[L.r];
+                const uint8_t* src_q = A.qual + A.qual_off[L.r];
+                const uint64_t fa[5] = {0, o_seq, o_qual, o_aux, L.total};
+#pragma unroll
+                for (int f = 0; f < 4; ++f) {
+                    const uint64_t lo_c = r0 > rb ? r0 - rb : 0ull, hi_c = r1 - rb;
+                    const uint64_t ia = fa[f] > lo_c ? fa[f] : lo_c, ib = fa[f + 1] < hi_c ? fa[f + 1] : hi_c;
+                    if (ia >= ib) continue;
+                    FrameRun r;
+                    r.begin = int32_t(int64_t(rb + ia) + rec_shift);
+                    r.len = uint32_t(ib - ia);
+                    r.l_seq = L.l_seq;
+                    if (f == 0 || f == 3) { r.kind = 0u; r.src = A.out + rb + ia; r.off = 0; }
+                    else if (f == 1) { r.kind = flip ? 1u : 0u; r.src = flip ? src_s : src_s + (ia - o_seq); r.off = int64_t(ia - o_seq); }
+                    else { r.kind = flip ? 2u : 0u; r.src = flip ? src_q : src_q + (ia - o_qual); r.off = int64_t(ia - o_qual); }
+                    mine[cnt++] = r;
+                }
+            }
+        }
+    }
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (int(lane) >= d) incl += o;
+    }
+    const uint32_t at = base + incl - cnt;
+    for (uint32_t i = 0; i < cnt; ++i) runs[at + i] = mine[i];
+    const uint32_t n_started = uint32_t(__popc(__ballot_sync(0xffffffffu, started)));
+    if (lane == 31u) {
+        const uint32_t kn = k_next + n_started;
+        ctl[0] = base + incl;
+        ctl[1] = kn;
+        ctl[2] = (!has_recs || n_started < 32u || kn >= A.n_records || A.rec_begin[kn] >= r1) ? 1u : 0u;
+    }
+}
+
 // ---- single pass: produce -> CRC -> store, every byte handled once (blocks whose runs all fit the table) ----------------
 __device__ __forceinline__ uint32_t crc_word_step(const uint32_t* __restrict__ wl, uint32_t lane, uint32_t crc, uint32_t w) {
     crc ^= w;
@@ -225,16 +307,13 @@ __device__ __forceinline__ uint32_t crc_word_step(const uint32_t* __restrict__ w
     for (int j = 0; j < 8; ++j) r ^= wl[32u * (16u * j + ((crc >> (4 * j)) & 15u)) + lane];
     return r;
 }
-__device__ __forceinline__ uint32_t crc_chunk(const uint32_t* __restrict__ wl, uint32_t lane, uint32_t crc, const uint4& v) {
-    return crc_word_step(wl, lane, crc_word_step(wl, lane, crc_word_step(wl, lane, crc_word_step(wl, lane, crc, v.x), v.y), v.z), v.w);
-}
 // 16 payload bytes at payload offset o (0 <= o, o + 16 <= n) from the run table; `ri` = a cursor that only moves forward
-__device__ __forceinline__ uint4 frame_chunk(const FrameRun* __restrict__ runs, uint32_t n_runs, uint32_t& ri, int32_t o) {
+static __device__ __noinline__ uint4 frame_chunk(const FrameRun* __restrict__ runs, uint32_t n_runs, uint32_t& ri, int32_t o) {
     while (ri + 1u < n_runs && runs[ri + 1u].begin <= o) ++ri;
     const FrameRun r = runs[ri];
     const int32_t rel = o - r.begin;
     if (rel >= 0 && rel + 16 <= int32_t(r.len)) {
-        if (r.kind == 0u) return (rel + 20 <= int32_t(r.len)) ? window128_body(r.src + rel) : window128_guarded(r.src, rel, int64_t(r.len));
+        if (r.kind == 0u && rel + 20 <= int32_t(r.len)) return window128_body(r.src + rel);
         return frame_produce_guarded(r, rel);
     }
     uint32_t w[4] = {0u, 0u, 0u, 0u};  // across a run boundary: every run that touches the chunk contributes its own bytes
@@ -253,97 +332,93 @@ __device__ __forceinline__ uint4 frame_chunk(const FrameRun* __restrict__ runs, 
     return make_uint4(w[0], w[1], w[2], w[3]);
 }
 // one payload byte (the < 16 bytes in front of the first aligned chunk and behind the last one)
-__device__ __forceinline__ uint32_t frame_byte(const FrameRun* __restrict__ runs, uint32_t n_runs, int32_t p) {
+static __device__ __noinline__ uint32_t frame_byte(const FrameRun* __restrict__ runs, uint32_t n_runs, int32_t p) {
     uint32_t ri = 0;
     while (ri + 1u < n_runs && runs[ri + 1u].begin <= p) ++ri;
     return frame_produce_guarded(runs[ri], int64_t(p) - runs[ri].begin).x & 0xffu;
 }
-// two aligned 16-byte loads -> the 16 bytes at byte offset 4 WS + bs / 8 of their 32
-template <int WS>
-__device__ __forceinline__ uint4 shift128(const uint4& a, const uint4& b, uint32_t bs) {
-    uint32_t x0, x1, x2, x3, x4;
-    if (WS == 0) { x0 = a.x; x1 = a.y; x2 = a.z; x3 = a.w; x4 = b.x; }
-    else if (WS == 1) { x0 = a.y; x1 = a.z; x2 = a.w; x3 = b.x; x4 = b.y; }
-    else if (WS == 2) { x0 = a.z; x1 = a.w; x2 = b.x; x3 = b.y; x4 = b.z; }
-    else { x0 = a.w; x1 = b.x; x2 = b.y; x3 = b.z; x4 = b.w; }
+// two aligned 16-byte loads -> the 16 bytes at byte offset 4 ws + bs / 8 of their 32
+__device__ __forceinline__ uint4 shift128(const uint4& a, const uint4& b, uint32_t ws, uint32_t bs) {
+    const uint32_t x0 = ws == 0u ? a.x : ws == 1u ? a.y : ws == 2u ? a.z : a.w;
+    const uint32_t x1 = ws == 0u ? a.y : ws == 1u ? a.z : ws == 2u ? a.w : b.x;
+    const uint32_t x2 = ws == 0u ? a.z : ws == 1u ? a.w : ws == 2u ? b.x : b.y;
+    const uint32_t x3 = ws == 0u ? a.w : ws == 1u ? b.x : ws == 2u ? b.y : b.z;
+    const uint32_t x4 = ws == 0u ? b.x : ws == 1u ? b.y : ws == 2u ? b.z : b.w;
     return make_uint4(__funnelshift_r(x0, x1, bs), __funnelshift_r(x1, x2, bs), __funnelshift_r(x2, x3, bs), __funnelshift_r(x3, x4, bs));
 }
-// a full 256-byte slice that is a plain copy of one source: its two halves as two interleaved chains, ONE new aligned
-// 128-bit load per chunk and chain (thread-contiguous addresses: a 32-bit-word window costs five L1 wavefronts per lane
-// and chunk, which is what made the re-reading CRC phase L1-bound)
-template <int WS>
-__device__ __forceinline__ void frame_slice_plain(const uint4* __restrict__ base, uint32_t bs, uint4* __restrict__ d, const uint32_t* __restrict__ wl,
-                                                  uint32_t lane, uint32_t& crc_a, uint32_t& crc_b) {
-    uint4 pa = base[0], pb = base[8];
-#pragma unroll 2
-    for (int i = 0; i < 8; ++i) {
-        const uint4 na = base[i + 1], nb = base[i + 9];
-        const uint4 va = shift128<WS>(pa, na, bs), vb = shift128<WS>(pb, nb, bs);
-        d[i] = va;
-        d[i + 8] = vb;
-        crc_a = crc_word_step(wl, lane, crc_a, va.x); crc_b = crc_word_step(wl, lane, crc_b, vb.x);
-        crc_a = crc_word_step(wl, lane, crc_a, va.y); crc_b = crc_word_step(wl, lane, crc_b, vb.y);
-        crc_a = crc_word_step(wl, lane, crc_a, va.z); crc_b = crc_word_step(wl, lane, crc_b, vb.z);
-        crc_a = crc_word_step(wl, lane, crc_a, va.w); crc_b = crc_word_step(wl, lane, crc_b, vb.w);
-        pa = na;
-        pb = nb;
-    }
-}
+// The block's payload, produced, CRC'd and stored in ONE pass over destination-aligned 256-byte slices (thread t: the slice
+// ending 256 (255 - t) bytes before the last 16-byte boundary of the destination).  A slice that is a plain copy of one
+// source runs its two halves as two interleaved chains with ONE new aligned 128-bit load per chunk and chain
+// (thread-contiguous addresses: a window of five 32-bit words costs five L1 wavefronts per lane and chunk, which made a
+// re-reading CRC phase L1-bound); anything else goes chunk by chunk through frame_chunk.
 __device__ __forceinline__ void bgzf_frame_single_pass(const FrameArgs& F, const FrameRun* __restrict__ runs, uint32_t n_runs, uint32_t n, uint8_t* data_dst,
                                                        uint32_t tid, uint32_t* sm) {
     const uint32_t* t0 = sm;
     const uint32_t* shift = sm + 256;
     const uint32_t* wl = shift + 9 * 128;
     const uint32_t lane = tid & 31u;
-    // slices are counted back from the last 16-byte boundary of the DESTINATION inside the payload, so that every chunk is
-    // an aligned store; the < 16 bytes behind it are folded in by thread 0 (bgzf_crc_combine_footer)
     const int32_t a0 = int32_t(reinterpret_cast<uint64_t>(data_dst) & 15ull);
-    int32_t tail = (int32_t(n) + a0) & 15;
+    int32_t tail = (int32_t(n) + a0) & 15;  // the < 16 bytes behind the last boundary: folded in by thread 0 (bgzf_crc_combine_footer)
     if (tail > int32_t(n)) tail = int32_t(n);
     const int32_t e_al = int32_t(n) - tail;
     const int32_t s_end = e_al - 256 * int32_t(255u - tid);
     const int32_t s_begin = max(s_end - 256, 0);
     uint32_t crc_a = 0, crc_b = 0;
-    auto range = [&](int32_t p0, int32_t p1, uint32_t crc) {  // produce, store and CRC payload [p0, p1); p1 is chunk-aligned
-        int32_t p = p0;
-        for (; p < p1 && ((p + a0) & 15); ++p) {  // (only in front of the very first chunk of the block)
-            const uint32_t bv = frame_byte(runs, n_runs, p);
-            data_dst[p] = uint8_t(bv);
-            crc = t0[(crc ^ bv) & 0xffu] ^ (crc >> 8);
-        }
-        uint32_t ri = 0;
-        for (; p + 16 <= p1; p += 16) {
-            const uint4 v = frame_chunk(runs, n_runs, ri, p);
-            *reinterpret_cast<uint4*>(data_dst + p) = v;
-            crc = crc_chunk(wl, lane, crc, v);
-        }
-        return crc;
-    };
     if (s_end > 0) {
         bool fast = false;
         if (s_end - s_begin == 256) {
             uint32_t ri = 0;
             while (ri + 1u < n_runs && runs[ri + 1u].begin <= s_begin) ++ri;
-            const FrameRun r = runs[ri];
-            const int32_t rel = s_begin - r.begin;
-            if (r.kind == 0u && rel >= 0 && rel + 256 + 32 <= int32_t(r.len)) {  // (+ 32: the look-ahead load stays inside the run)
+            const int32_t rel = s_begin - runs[ri].begin;
+            if (runs[ri].kind == 0u && rel >= 0 && rel + 256 + 32 <= int32_t(runs[ri].len)) {  // (+ 32: the look-ahead load stays inside the run)
                 fast = true;
-                const uint64_t sa = reinterpret_cast<uint64_t>(r.src + rel);
-                const uint4* base = reinterpret_cast<const uint4*>(sa & ~15ull);
-                const uint32_t bs = uint32_t(sa & 3ull) * 8u;
-                uint4* d = reinterpret_cast<uint4*>(data_dst + s_begin);
-                switch (uint32_t(sa & 15ull) >> 2) {
-                    case 0: frame_slice_plain<0>(base, bs, d, wl, lane, crc_a, crc_b); break;
-                    case 1: frame_slice_plain<1>(base, bs, d, wl, lane, crc_a, crc_b); break;
-                    case 2: frame_slice_plain<2>(base, bs, d, wl, lane, crc_a, crc_b); break;
-                    default: frame_slice_plain<3>(base, bs, d, wl, lane, crc_a, crc_b); break;
+                const uint64_t sa = reinterpret_cast<uint64_t>(runs[ri].src + rel);
+                const uint4* __restrict__ base = reinterpret_cast<const uint4*>(sa & ~15ull);
+                const uint32_t ws = uint32_t(sa & 15ull) >> 2, bs = uint32_t(sa & 3ull) * 8u;
+                uint4* __restrict__ d = reinterpret_cast<uint4*>(data_dst + s_begin);
+                uint4 pa = base[0], pb = base[8];
+#pragma unroll 1
+                for (int i = 0; i < 8; ++i) {
+                    const uint4 na = base[i + 1], nb = base[i + 9];
+                    const uint4 va = shift128(pa, na, ws, bs), vb = shift128(pb, nb, ws, bs);
+                    d[i] = va;
+                    d[i + 8] = vb;
+                    crc_a = crc_word_step(wl, lane, crc_a, va.x); crc_b = crc_word_step(wl, lane, crc_b, vb.x);
+                    crc_a = crc_word_step(wl, lane, crc_a, va.y); crc_b = crc_word_step(wl, lane, crc_b, vb.y);
+                    crc_a = crc_word_step(wl, lane, crc_a, va.z); crc_b = crc_word_step(wl, lane, crc_b, vb.z);
+                    crc_a = crc_word_step(wl, lane, crc_a, va.w); crc_b = crc_word_step(wl, lane, crc_b, vb.w);
+                    pa = na;
+                    pb = nb;
                 }
             }
         }
-        if (!fast) {
+        if (!fast) {  // chain A over [s_begin, mid), chain B over [mid, s_end), one after the other
             const int32_t mid = (s_end - s_begin == 256) ? s_begin + 128 : max(s_end - 128, s_begin);
-            crc_a = range(s_begin, mid, 0u);
-            crc_b = range(mid, s_end, 0u);
+            uint32_t ri = 0;
+            int32_t p = s_begin;
+            for (; p < mid && ((p + a0) & 15); ++p) {  // (only in front of the very first chunk of the block)
+                const uint32_t bv = frame_byte(runs, n_runs, p);
+                data_dst[p] = uint8_t(bv);
+                crc_a = t0[(crc_a ^ bv) & 0xffu] ^ (crc_a >> 8);
+            }
+#pragma unroll 1
+            for (; p < s_end; p += 16) {
+                if (p < mid || ((p + a0) & 15) == 0) {
+                    if ((p + a0) & 15) {  // (A empty and the block starts unaligned: the odd bytes belong to chain B)
+                        for (; p < s_end && ((p + a0) & 15); ++p) {
+                            const uint32_t bv = frame_byte(runs, n_runs, p);
+                            data_dst[p] = uint8_t(bv);
+                            crc_b = t0[(crc_b ^ bv) & 0xffu] ^ (crc_b >> 8);
+                        }
+                        if (p >= s_end) break;
+                    }
+                    const uint4 v = frame_chunk(runs, n_runs, ri, p);
+                    *reinterpret_cast<uint4*>(data_dst + p) = v;
+                    uint32_t c = (p < mid) ? crc_a : crc_b;
+                    c = crc_word_step(wl, lane, crc_word_step(wl, lane, crc_word_step(wl, lane, crc_word_step(wl, lane, c, v.x), v.y), v.z), v.w);
+                    if (p < mid) crc_a = c; else crc_b = c;
+                }
+            }
         }
     }
     uint32_t tail_crc = 0;
@@ -357,8 +432,47 @@ __device__ __forceinline__ void bgzf_frame_single_pass(const FrameArgs& F, const
     bgzf_crc_combine_footer(F.Z, gf2_apply_nibbles(shift, crc_a) ^ crc_b, n, data_dst, tid, sm, uint32_t(tail), tail_crc);
 }
 
+// ---- the general path (a block with more than 32 records, i.e. records of a few hundred bytes): pass after pass, every
+//      run stores its own bytes of every chunk it touches, then the block reads its payload back for the CRC
+static __device__ __noinline__ void bgzf_frame_general(const FrameArgs& F, uint64_t x0, uint64_t x1, FrameRun* runs, uint32_t* ctl, uint32_t n,
+                                                       uint8_t* data_dst, uint32_t tid, uint32_t* sm) {
+    for (;;) {  // (entered with the table of the first pass built)
+        const uint32_t n_runs = ctl[0];
+        const bool done = ctl[2] != 0u;
+        const uint32_t k_next = ctl[1];
+        if (n_runs) {
+            const int32_t span0 = max(runs[0].begin, 0);
+            const int32_t span1 = min(int32_t(n), runs[n_runs - 1].begin + int32_t(runs[n_runs - 1].len));
+            const int32_t a0 = int32_t(reinterpret_cast<uint64_t>(data_dst) & 15ull);  // chunk c covers payload [16 c - a0, + 16)
+            const int32_t c0 = (span0 + a0) >> 4, c1 = (span1 + a0 + 15) >> 4;
+            uint32_t ri = 0;
+            for (int32_t c = c0 + int32_t(tid); c < c1; c += 256) {
+                const int32_t o = 16 * c - a0;
+                while (ri + 1u < n_runs && runs[ri + 1u].begin <= o) ++ri;
+                for (uint32_t rj = ri; rj < n_runs && runs[rj].begin < o + 16; ++rj) {
+                    const FrameRun q = runs[rj];
+                    const int64_t rl = int64_t(o) - q.begin;
+                    if (rl + 16 <= 0) continue;
+                    const uint4 v = frame_produce_guarded(q, rl);
+                    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int t = 0; t < 16; ++t) {
+                        const int64_t pr = rl + t;  // run-relative
+                        const int32_t pp = o + t;   // payload
+                        if (pr >= 0 && pr < int64_t(q.len) && pp >= 0 && pp < int32_t(n)) data_dst[pp] = uint8_t(w[t >> 2] >> (8 * (t & 3)));
+                    }
+                }
+            }
+        }
+        __syncthreads();  // (the table is rebuilt by the next pass; after the last pass: the payload is complete and visible)
+        if (done) break;
+        if (tid < 32u) frame_build_runs(F, x0, x1, false, k_next, runs, ctl, tid);
+        __syncthreads();
+    }
+    bgzf_crc_and_footer(F.Z, data_dst, n, data_dst, tid, sm);
+}
+
 __device__ __forceinline__ void bgzf_frame_block_body(const FrameArgs& F, uint64_t b, uint32_t tid, uint32_t* sm) {
-    const BamAsmArgs& A = F.A;
     FrameRun* runs = reinterpret_cast<FrameRun*>(sm + kBgzfSmemWords);
     uint32_t* ctl = sm + kBgzfSmemWords + kFrameMaxRuns * (sizeof(FrameRun) / 4u);  // [0] runs of this pass, [1] next record, [2] done
     const uint64_t x0 = b * kBgzfIn;
@@ -366,170 +480,15 @@ __device__ __forceinline__ void bgzf_frame_block_body(const FrameArgs& F, uint64
     const uint64_t x1 = x0 + n;
     uint8_t* dst = F.Z.out + b * uint64_t(kBgzfIn + kBgzfOverhead);
     uint8_t* data_dst = dst + 23;
-    const uint32_t lane = tid & 31u;
     bgzf_write_header(dst, n, tid);
-    // record-space range of this block
-    const bool has_recs = x1 > F.prefix_bytes && A.n_records;
-    const uint64_t xs = x0 > F.prefix_bytes ? x0 : F.prefix_bytes;
-    const uint64_t r0 = xs - F.prefix_bytes, r1 = has_recs ? x1 - F.prefix_bytes : 0ull;
-    const int64_t rec_shift = int64_t(F.prefix_bytes) - int64_t(x0);  // payload offset = record-space offset + rec_shift
-    uint32_t k_next = 0;
-    bool first_pass = true;
-    for (;;) {
-        // ---- warp 0: the runs of up to 32 records (and the prefix on the first pass)
-        if (tid < 32u) {
-            uint32_t base = 0;
-            if (first_pass) {
-                if (x0 < F.prefix_bytes) {
-                    if (lane == 0) runs[0] = FrameRun{0, uint32_t((x1 < F.prefix_bytes ? x1 : F.prefix_bytes) - x0), 0u, 0u, F.prefix + x0, 0};
-                    base = 1;
-                }
-                if (has_recs) {  // first record = last k with rec_begin[k] <= r0: a 32-ary search, one probe per lane and round
-                    uint32_t lo = 0, hi = A.n_records;  // invariant: rec_begin[lo] <= r0 < rec_begin[hi] (rec_begin[n_records] = total > r0)
-                    while (hi - lo > 1u) {
-                        const uint32_t step = (hi - lo + 31u) / 32u;
-                        const uint32_t probe = lo + lane * step;
-                        const bool le = probe < hi && A.rec_begin[probe] <= r0;
-                        const uint32_t m = __ballot_sync(0xffffffffu, le);  // (lane 0 probes lo: always set)
-                        const uint32_t top = 31u - uint32_t(__clz(int(m)));
-                        const uint32_t nlo = lo + top * step;
-                        hi = min(hi, nlo + step);
-                        lo = nlo;
-                    }
-                    k_next = lo;
-                }
-            }
-            uint32_t cnt = 0;
-            FrameRun mine[4];
-            bool started = false;
-            if (has_recs) {
-                const uint32_t k = k_next + lane;
-                if (k < A.n_records) {
-                    const uint64_t rb = A.rec_begin[k];
-                    if (rb < r1) {
-                        started = true;
-                        const BamRecLayout L = BamRecLayout::unpack(A.rec_desc + 2 * size_t(k));
-                        const uint64_t o_seq = 36ull + L.name_n + 1 + 4ull * L.n_cigar, o_qual = o_seq + L.seq_bytes, o_aux = o_qual + L.l_seq;
-                        const bool flip = A.rec_need_flip[k] != 0;
-                        const uint8_t* src_s = A.seq4 + A.read_seq_off[L.r];
-                        const uint8_t* src_q = A.qual + A.qual_off[L.r];
-                        const uint64_t fa[5] = {0, o_seq, o_qual, o_aux, L.total};
-#pragma unroll
-                        for (int f = 0; f < 4; ++f) {
-                            const uint64_t lo_c = r0 > rb ? r0 - rb : 0ull, hi_c = r1 - rb;
-                            const uint64_t ia = fa[f] > lo_c ? fa[f] : lo_c, ib = fa[f + 1] < hi_c ? fa[f + 1] : hi_c;
-                            if (ia >= ib) continue;
-                            FrameRun r;
-                            r.begin = int32_t(int64_t(rb + ia) + rec_shift);
-                            r.len = uint32_t(ib - ia);
-                            r.l_seq = L.l_seq;
-                            if (f == 0 || f == 3) { r.kind = 0u; r.src = A.out + rb + ia; r.off = 0; }
-                            else if (f == 1) { r.kind = flip ? 1u : 0u; r.src = flip ? src_s : src_s + (ia - o_seq); r.off = int64_t(ia - o_seq); }
-                            else { r.kind = flip ? 2u : 0u; r.src = flip ? src_q : src_q + (ia - o_qual); r.off = int64_t(ia - o_qual); }
-                            mine[cnt++] = r;
-                        }
-                    }
-                }
-            }
-            uint32_t incl = cnt;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
-                if (int(lane) >= d) incl += o;
-            }
-            const uint32_t at = base + incl - cnt;
-            for (uint32_t i = 0; i < cnt; ++i) runs[at + i] = mine[i];
-            const uint32_t n_started = uint32_t(__popc(__ballot_sync(0xffffffffu, started)));
-            if (lane == 31u) {
-                ctl[0] = base + incl;
-                ctl[1] = k_next + n_started;
-                // done: fewer than 32 records started here, or the next record begins behind the block
-                const uint32_t kn = k_next + n_started;
-                ctl[2] = (!has_recs || n_started < 32u || kn >= A.n_records || A.rec_begin[kn] >= r1) ? 1u : 0u;
-            }
-        }
-        __syncthreads();
-        const uint32_t n_runs = ctl[0];
-        const bool done = ctl[2] != 0u;
-        k_next = ctl[1];
+    if (tid < 32u) frame_build_runs(F, x0, x1, true, 0u, runs, ctl, tid);
+    __syncthreads();
 #ifndef FRAME_TWO_PHASE
-        if (first_pass && done) {  // every run of the block is in the table (any block of real data: <= 32 records)
-            bgzf_frame_single_pass(F, runs, n_runs, n, data_dst, tid, sm);
-            __syncthreads();  // (the table and warp_crc are reused by the next block of this persistent thread block)
-            return;
-        }
+    if (ctl[2] != 0u) bgzf_frame_single_pass(F, runs, ctl[0], n, data_dst, tid, sm);  // every run of the block is in the table (<= 32 records: any real data)
+    else
 #endif
-        // ---- all threads: the destination-aligned 16-byte chunks that touch the runs of this pass
-        if (n_runs) {
-            const int32_t span0 = max(runs[0].begin, 0);
-            const int32_t span1 = min(int32_t(n), runs[n_runs - 1].begin + int32_t(runs[n_runs - 1].len));
-            const int32_t a0 = int32_t(reinterpret_cast<uint64_t>(data_dst) & 15ull);  // chunk c covers payload [16 c - a0, + 16)
-            const int32_t c0 = (span0 + a0) >> 4, c1 = (span1 + a0 + 15) >> 4;
-            // four chunks of a thread in flight: all their loads are issued before the first store (one chunk at a time
-            // left a single DRAM round trip per thread in flight: 2.4 TB/s at best)
-            uint32_t ri = 0;
-            for (int32_t c = c0 + int32_t(tid); c < c1; c += 4 * 256) {
-                uint4 v[4];
-                int32_t o[4];
-                uint32_t rix[4];
-                bool valid[4], fast[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int32_t cc = c + 256 * u;
-                    valid[u] = cc < c1;
-                    o[u] = 16 * cc - a0;
-                    fast[u] = false;
-                    if (valid[u]) {
-                        while (ri + 1u < n_runs && runs[ri + 1u].begin <= o[u]) ++ri;
-                        rix[u] = ri;
-                        const FrameRun r = runs[ri];
-                        const int32_t rel = o[u] - r.begin;
-                        if (rel >= 0 && rel + 16 <= int32_t(r.len) && o[u] >= span0 && o[u] + 16 <= span1) {  // (almost every chunk)
-                            fast[u] = true;
-                            if (r.kind == 0u) {
-                                v[u] = window128_body(r.src + rel);
-                            } else if (r.kind == 1u) {
-                                v[u] = revcomp_chunk(r.src, int64_t(r.l_seq), int64_t(rel) + r.off);
-                            } else {
-                                const int64_t len = r.l_seq;
-                                const uint4 q = window128_lean(r.src, len - 16 - (int64_t(rel) + r.off), len);
-                                v[u].x = __byte_perm(q.w, 0u, 0x0123u);
-                                v[u].y = __byte_perm(q.z, 0u, 0x0123u);
-                                v[u].z = __byte_perm(q.y, 0u, 0x0123u);
-                                v[u].w = __byte_perm(q.x, 0u, 0x0123u);
-                            }
-                        }
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (fast[u]) *reinterpret_cast<uint4*>(data_dst + o[u]) = v[u];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (!valid[u] || fast[u]) continue;
-                    // a chunk across a run boundary (or at an end of the payload): every run that touches it stores its own bytes
-                    for (uint32_t rj = rix[u]; rj < n_runs && runs[rj].begin < o[u] + 16; ++rj) {
-                        const FrameRun q = runs[rj];
-                        const int64_t rl = int64_t(o[u]) - q.begin;
-                        if (rl + 16 <= 0) continue;
-                        const uint4 w4 = frame_produce_guarded(q, rl);
-                        const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
-#pragma unroll
-                        for (int t = 0; t < 16; ++t) {
-                            const int64_t pr = rl + t;           // run-relative
-                            const int32_t pp = o[u] + t;         // payload
-                            if (pr >= 0 && pr < int64_t(q.len) && pp >= 0 && pp < int32_t(n)) data_dst[pp] = uint8_t(w[t >> 2] >> (8 * (t & 3)));
-                        }
-                    }
-                }
-            }
-        }
-        __syncthreads();  // (the table is rebuilt by the next pass; after the last pass: the payload is complete and visible)
-        first_pass = false;
-        if (done) break;
-    }
-    bgzf_crc_and_footer(F.Z, data_dst, n, data_dst, tid, sm);
-    __syncthreads();  // (warp_crc is reused by the next block of this persistent thread block)
+        bgzf_frame_general(F, x0, x1, runs, ctl, n, data_dst, tid, sm);
+    __syncthreads();  // (the table and warp_crc are reused by the next block of this persistent thread block)
 }
 
 }  // namespace ptl
