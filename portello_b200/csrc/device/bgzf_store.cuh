@@ -395,30 +395,23 @@ __device__ __forceinline__ void bgzf_frame_single_pass(const FrameArgs& F, const
         if (!fast) {  // chain A over [s_begin, mid), chain B over [mid, s_end), one after the other
             const int32_t mid = (s_end - s_begin == 256) ? s_begin + 128 : max(s_end - 128, s_begin);
             uint32_t ri = 0;
-            int32_t p = s_begin;
-            for (; p < mid && ((p + a0) & 15); ++p) {  // (only in front of the very first chunk of the block)
-                const uint32_t bv = frame_byte(runs, n_runs, p);
-                data_dst[p] = uint8_t(bv);
-                crc_a = t0[(crc_a ^ bv) & 0xffu] ^ (crc_a >> 8);
-            }
+            auto range = [&](int32_t p0, int32_t p1, uint32_t crc) {  // produce, store and CRC payload [p0, p1); p1 is chunk-aligned
+                int32_t p = p0;
+                for (; p < p1 && ((p + a0) & 15); ++p) {  // (only in front of the very first chunk of the block)
+                    const uint32_t bv = frame_byte(runs, n_runs, p);
+                    data_dst[p] = uint8_t(bv);
+                    crc = t0[(crc ^ bv) & 0xffu] ^ (crc >> 8);
+                }
 #pragma unroll 1
-            for (; p < s_end; p += 16) {
-                if (p < mid || ((p + a0) & 15) == 0) {
-                    if ((p + a0) & 15) {  // (A empty and the block starts unaligned: the odd bytes belong to chain B)
-                        for (; p < s_end && ((p + a0) & 15); ++p) {
-                            const uint32_t bv = frame_byte(runs, n_runs, p);
-                            data_dst[p] = uint8_t(bv);
-                            crc_b = t0[(crc_b ^ bv) & 0xffu] ^ (crc_b >> 8);
-                        }
-                        if (p >= s_end) break;
-                    }
+                for (; p + 16 <= p1; p += 16) {
                     const uint4 v = frame_chunk(runs, n_runs, ri, p);
                     *reinterpret_cast<uint4*>(data_dst + p) = v;
-                    uint32_t c = (p < mid) ? crc_a : crc_b;
-                    c = crc_word_step(wl, lane, crc_word_step(wl, lane, crc_word_step(wl, lane, crc_word_step(wl, lane, c, v.x), v.y), v.z), v.w);
-                    if (p < mid) crc_a = c; else crc_b = c;
+                    crc = crc_word_step(wl, lane, crc_word_step(wl, lane, crc_word_step(wl, lane, crc_word_step(wl, lane, crc, v.x), v.y), v.z), v.w);
                 }
-            }
+                return crc;
+            };
+            crc_a = range(s_begin, mid, 0u);
+            crc_b = range(mid, s_end, 0u);
         }
     }
     uint32_t tail_crc = 0;
