@@ -307,35 +307,34 @@ __device__ __forceinline__ uint32_t crc_word_step(const uint32_t* __restrict__ w
     for (int j = 0; j < 8; ++j) r ^= wl[32u * (16u * j + ((crc >> (4 * j)) & 15u)) + lane];
     return r;
 }
-// 16 payload bytes at payload offset o (0 <= o, o + 16 <= n) from the run table; `ri` = a cursor that only moves forward
+// 16 payload bytes at payload offset o from the run table (bytes outside the payload come out as zero: the chunks in
+// front of the first and behind the last 16-byte boundary of the destination); `ri` = a cursor that only moves forward
 static __device__ __noinline__ uint4 frame_chunk(const FrameRun* __restrict__ runs, uint32_t n_runs, uint32_t& ri, int32_t o) {
     while (ri + 1u < n_runs && runs[ri + 1u].begin <= o) ++ri;
-    const FrameRun r = runs[ri];
-    const int32_t rel = o - r.begin;
-    if (rel >= 0 && rel + 16 <= int32_t(r.len)) {
-        if (r.kind == 0u && rel + 20 <= int32_t(r.len)) return window128_body(r.src + rel);
-        return frame_produce_guarded(r, rel);
+    {
+        const FrameRun& r = runs[ri];
+        const int32_t rel = o - r.begin;
+        if (rel >= 0 && rel + 16 <= int32_t(r.len)) {
+            if (r.kind == 0u && rel + 20 <= int32_t(r.len)) return window128_body(r.src + rel);
+            return frame_produce_guarded(r, rel);
+        }
     }
     uint32_t w[4] = {0u, 0u, 0u, 0u};  // across a run boundary: every run that touches the chunk contributes its own bytes
     for (uint32_t rj = ri; rj < n_runs && runs[rj].begin < o + 16; ++rj) {
-        const FrameRun q = runs[rj];
-        const int64_t rl = int64_t(o) - q.begin;
-        if (rl + 16 <= 0) continue;
+        const FrameRun& q = runs[rj];
+        const int32_t rl = o - q.begin;
+        const int32_t lo = max(0, -rl), hi = min(16, int32_t(q.len) - rl);  // bytes [lo, hi) of the chunk belong to this run
+        if (lo >= hi) continue;
         const uint4 v = frame_produce_guarded(q, rl);
         const uint32_t x[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int t = 0; t < 16; ++t) {
-            const int64_t pr = rl + t;
-            if (pr >= 0 && pr < int64_t(q.len)) w[t >> 2] |= ((x[t >> 2] >> (8 * (t & 3))) & 0xffu) << (8 * (t & 3));
+        for (int k = 0; k < 4; ++k) {
+            const int32_t blo = min(max(lo - 4 * k, 0), 4), bhi = min(max(hi - 4 * k, 0), 4);
+            const uint32_t m = uint32_t(((1ull << (8 * bhi)) - 1ull) & ~((1ull << (8 * blo)) - 1ull));
+            w[k] |= x[k] & m;
         }
     }
     return make_uint4(w[0], w[1], w[2], w[3]);
-}
-// one payload byte (the < 16 bytes in front of the first aligned chunk and behind the last one)
-static __device__ __noinline__ uint32_t frame_byte(const FrameRun* __restrict__ runs, uint32_t n_runs, int32_t p) {
-    uint32_t ri = 0;
-    while (ri + 1u < n_runs && runs[ri + 1u].begin <= p) ++ri;
-    return frame_produce_guarded(runs[ri], int64_t(p) - runs[ri].begin).x & 0xffu;
 }
 // two aligned 16-byte loads -> the 16 bytes at byte offset 4 ws + bs / 8 of their 32
 __device__ __forceinline__ uint4 shift128(const uint4& a, const uint4& b, uint32_t ws, uint32_t bs) {
@@ -397,10 +396,16 @@ __device__ __forceinline__ void bgzf_frame_single_pass(const FrameArgs& F, const
             uint32_t ri = 0;
             auto range = [&](int32_t p0, int32_t p1, uint32_t crc) {  // produce, store and CRC payload [p0, p1); p1 is chunk-aligned
                 int32_t p = p0;
-                for (; p < p1 && ((p + a0) & 15); ++p) {  // (only in front of the very first chunk of the block)
-                    const uint32_t bv = frame_byte(runs, n_runs, p);
-                    data_dst[p] = uint8_t(bv);
-                    crc = t0[(crc ^ bv) & 0xffu] ^ (crc >> 8);
+                if (p < p1 && ((p + a0) & 15)) {  // (only in front of the very first chunk of the block: p0 == 0)
+                    const int32_t h = min(p1, 16 - a0);  // the bytes [0, h) sit at the end of the virtual chunk [h - 16, h)
+                    const uint4 v = frame_chunk(runs, n_runs, ri, h - 16);
+                    const uint32_t x[4] = {v.x, v.y, v.z, v.w};
+                    for (; p < h; ++p) {
+                        const int32_t t = p - (h - 16);
+                        const uint32_t bv = (x[t >> 2] >> (8 * (t & 3))) & 0xffu;
+                        data_dst[p] = uint8_t(bv);
+                        crc = t0[(crc ^ bv) & 0xffu] ^ (crc >> 8);
+                    }
                 }
 #pragma unroll 1
                 for (; p + 16 <= p1; p += 16) {
@@ -415,10 +420,13 @@ __device__ __forceinline__ void bgzf_frame_single_pass(const FrameArgs& F, const
         }
     }
     uint32_t tail_crc = 0;
-    if (tid == 0) {
-        for (int32_t p = e_al; p < int32_t(n); ++p) {
-            const uint32_t bv = frame_byte(runs, n_runs, p);
-            data_dst[p] = uint8_t(bv);
+    if (tid == 0 && tail > 0) {
+        uint32_t ri = 0;
+        const uint4 v = frame_chunk(runs, n_runs, ri, e_al);  // the virtual chunk [e_al, e_al + 16): its first `tail` bytes exist
+        const uint32_t x[4] = {v.x, v.y, v.z, v.w};
+        for (int32_t t = 0; t < tail; ++t) {
+            const uint32_t bv = (x[t >> 2] >> (8 * (t & 3))) & 0xffu;
+            data_dst[e_al + t] = uint8_t(bv);
             tail_crc = t0[(tail_crc ^ bv) & 0xffu] ^ (tail_crc >> 8);
         }
     }
