@@ -8,7 +8,7 @@ n = int(sys.argv[2]) if len(sys.argv) > 2 else 1_000_000
 s = synth.make(wl, n_reads=n)
 ctx = lib.GpuContext(0, 1)
 ctx.set_reference(helpers.reference_arrays(s)); ctx.set_contig_records(s.contig_records)
-pb = lib.PackedBatch(lib.load(), s.read_records, 0, s.read_records.n_reads, s.contig_names, pinned=True)
+pb = lib.PackedBatch(lib.load(), s.read_records, 0, s.read_records.n_reads, s.contig_names, pinned=True, windows=ctx.get_contig_segments())  # as bench.py packs
 ctx.upload(pb.c, 0)
 for _ in range(3): ctx.run(0)
 ctx.counters(0)
