@@ -132,6 +132,8 @@ def make_shard(args, rank, world, host_alloc=None, host_free=None, region_segmen
     kw = {"defer_reads": 1}
     if args.reads:
         kw["n_reads"] = args.reads
+    if world > 1:
+        kw["n_threads"] = max(1, (os.cpu_count() or 1) // world)  # (every rank builds the reference and the contigs: share the cores)
     s = synth.make(args.workload, host_alloc=host_alloc, host_free=host_free, **kw)
     plan_contig, plan_pos = s.plan()
     units = shard.window_units(s.contig_lengths(), plan_contig, plan_pos, region_segments=region_segments)
