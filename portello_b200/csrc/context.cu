@@ -91,7 +91,7 @@ struct Slot {
         d_rseg_is_fwd, d_rseg_cigar_begin, d_rseg_cigar_len, d_cigar, d_seq4, d_arena, d_win_begin, d_win;
     // work
     DBuf w_rseg_read, w_rseg_pair_begin, w_rseg_ref_len, w_rseg_n_id, w_rseg_read_len, w_pair_cap_b, w_pair_tab_lo, w_pair_rseg, w_pair_seg, w_pair_slot_begin, w_pair_status, w_pair_flip,
-        w_pair_pos, w_pair_n_out, w_pair_bin, w_pair_out_off, w_simplify_list, w_long_list, w_pair_order, w_scratch, w_read_counts, w_read_primary, w_scan_tmp, w_totals;
+        w_pair_pos, w_pair_n_out, w_pair_bin, w_pair_out_off, w_simplify_list, w_long_list, w_pair_order, w_pair_desc, w_pair_desc_rev, w_scratch, w_read_counts, w_read_primary, w_scan_tmp, w_totals;
     // record assembly (ptl_assemble_bases): uploaded qualities, per-record offsets, output pools and their pinned twins
     DBuf a_qual, a_qual_off, a_rec_read, a_seq_begin, a_qual_begin, a_out_seq, a_out_qual;
     HBuf ha_seq_begin, ha_qual_begin, ha_out_seq, ha_out_qual;
@@ -355,6 +355,8 @@ void size_work(Slot& sl, uint32_t want_pairs, uint64_t want_scratch, uint64_t wa
     sl.w_simplify_list.ensure(size_t(pc) * 4, st);
     sl.w_long_list.ensure(size_t(pc) * 4, st);
     sl.w_pair_order.ensure(size_t(pc) * 4, st);
+    sl.w_pair_desc.ensure(size_t(pc) * sizeof(PairDesc), st);
+    sl.w_pair_desc_rev.ensure(size_t(pc) * sizeof(PairDescRev), st);
     W.pair_cap = pc;
     W.pair_rseg = sl.w_pair_rseg.as<uint32_t>();
     W.pair_seg = sl.w_pair_seg.as<uint32_t>();
@@ -370,6 +372,8 @@ void size_work(Slot& sl, uint32_t want_pairs, uint64_t want_scratch, uint64_t wa
     W.simplify_list = sl.w_simplify_list.as<uint32_t>();
     W.long_list = sl.w_long_list.as<uint32_t>();
     W.pair_order = sl.w_pair_order.as<uint32_t>();
+    W.pair_desc = sl.w_pair_desc.as<PairDesc>();
+    W.pair_desc_rev = sl.w_pair_desc_rev.as<PairDescRev>();
     const uint64_t sc = std::max(W.scratch_cap, want_scratch);
     const uint64_t dense = (uint64_t(pc) + 31) / 32 * kLiftTileOut;  // dense output regions of the lift kernel's tiles
     sl.w_scratch.ensure(size_t(sc + dense) * 4, st);
@@ -568,7 +572,7 @@ void ptl_destroy(ptl_ctx* ctx) {
         for (DBuf* b : {&sl.d_read_flag, &sl.d_read_mapq, &sl.d_read_bin, &sl.d_read_seq_len, &sl.d_read_seq_off, &sl.d_read_seg_begin,
                         &sl.d_rseg_contig, &sl.d_rseg_pos, &sl.d_rseg_is_fwd, &sl.d_rseg_cigar_begin, &sl.d_rseg_cigar_len, &sl.d_cigar,
                         &sl.d_seq4, &sl.d_arena, &sl.d_win_begin, &sl.d_win, &sl.w_rseg_read, &sl.w_rseg_pair_begin, &sl.w_rseg_ref_len, &sl.w_rseg_n_id, &sl.w_rseg_read_len, &sl.w_pair_cap_b, &sl.w_pair_tab_lo, &sl.w_pair_rseg, &sl.w_pair_seg,
-                        &sl.w_pair_slot_begin, &sl.w_pair_status, &sl.w_pair_flip, &sl.w_pair_pos, &sl.w_pair_n_out, &sl.w_pair_bin, &sl.w_pair_out_off, &sl.w_simplify_list, &sl.w_long_list, &sl.w_pair_order,
+                        &sl.w_pair_slot_begin, &sl.w_pair_status, &sl.w_pair_flip, &sl.w_pair_pos, &sl.w_pair_n_out, &sl.w_pair_bin, &sl.w_pair_out_off, &sl.w_simplify_list, &sl.w_long_list, &sl.w_pair_order, &sl.w_pair_desc, &sl.w_pair_desc_rev,
                         &sl.w_scratch, &sl.w_read_counts, &sl.w_read_primary, &sl.w_scan_tmp, &sl.w_totals, &sl.r_arena, &sl.a_qual, &sl.a_qual_off,
                         &sl.a_rec_read, &sl.a_seq_begin, &sl.a_qual_begin, &sl.a_out_seq, &sl.a_out_qual, &sl.b_name_off, &sl.b_names, &sl.b_aux_off,
                         &sl.b_aux, &sl.b_mate_tid, &sl.b_mate_pos, &sl.b_tlen, &sl.b_keep, &sl.b_sa_len, &sl.b_rec_begin, &sl.b_rec_desc, &sl.b_out, &sl.b_err, &sl.z_out, &sl.z_prefix})

@@ -78,6 +78,35 @@ struct DevBatch {
 };
 
 
+// What lift_pairs_kernel needs to know about a pair before it can walk it, packed by pair_fill_kernel into ONE 32-byte
+// sector (the lanes of a tile own work-sorted, i.e. scattered, pairs: the same facts read from fifteen separate arrays cost
+// fifteen sectors and a chain of four dependent loads per pair: 20 % of the kernel's stall samples on the whole-genome
+// workload, ncu r06a).  Reverse-strand pairs read a second sector, PairDescRev.
+struct alignas(16) PairDesc {
+    uint64_t cigar_begin;  // first op of the read-segment CIGAR in the batch pool
+    uint32_t n_ops;        // ops of that CIGAR
+    uint32_t cpos;         // where the walk starts, on the strand the segment's table is written in
+    uint32_t tab_lo;       // first table entry with key >= cpos (cursor hint)
+    uint32_t t0, t1;       // the segment's table range
+    uint32_t flags_cap_b;  // bits 0-7: kPd* flags; bits 8-31: capacity of the pair's buffer B (slot bound, ops)
+};
+enum : uint32_t {
+    kPdContigFwd = 1,   // the contig segment is forward-strand
+    kPdNeedFlip = 2,    // need_flipped_read_alignment (src/read_alignment_scanner.rs:153-157)
+    kPdErrBounds = 4,   // the read runs past the end of a reverse-strand contig (negative rev_pos, :166)
+    kPdErrLength = 8,   // read length of the segment CIGAR != seq_len (the reference's assertion, :204-229)
+    kPdNoRevSeq = 16    // reverse-strand segment on a contig without rev_contig_seq (Option::unwrap on None, :174)
+};
+struct alignas(16) PairDescRev {
+    uint64_t seq_off;      // read_seq_off of the read
+    uint64_t rev_off;      // contig_rev_off of the contig (~0 = none)
+    uint32_t contig_len;
+    uint32_t seq_len;
+    uint32_t win_begin;    // indel windows of the read segment: [win_begin, win_begin + n_win) (0, 0 without windows)
+    uint32_t n_win;
+};
+static_assert(sizeof(PairDesc) == 32 && sizeof(PairDescRev) == 32, "one sector each");
+
 // ---- per-batch work arrays ---------------------------------------------------------------------------------------
 struct DevWork {
     // per read segment
@@ -102,6 +131,8 @@ struct DevWork {
     uint32_t* simplify_list = nullptr;   // [pair_cap] pairs whose lifted CIGAR needs simplify_alignment_indels
     uint32_t* long_list = nullptr;       // [pair_cap] pairs whose liftover runs warp-cooperatively (status ST_PENDING_LIFT)
     uint32_t* pair_order = nullptr;      // [pair_cap] work order of lift_pairs_kernel (pair_order_kernel)
+    PairDesc* pair_desc = nullptr;       // [pair_cap] (pair_fill_kernel)
+    PairDescRev* pair_desc_rev = nullptr;  // [pair_cap], written for reverse-strand pairs only
     uint32_t long_ops = 64;              // a pair with more CIGAR ops than this goes to long_list
     // scratch op slots, followed in the same allocation by the dense output region of the lift kernel: tile t (32 pairs)
     // of lift_pairs_kernel owns scratch[dense_off + t * kLiftTileOut, + kLiftTileOut) and packs the lifted CIGARs of its

@@ -149,6 +149,21 @@ __device__ __forceinline__ void pair_fill_body(const DevStatic& S, const DevBatc
             const uint32_t cap_a = cap_b + (n_in > W.long_ops ? 9u * (n_id + n_keys) + 16u : 6u * (n_id + n_keys) + 8u);
             W.pair_cap_b[p] = cap_b;
             W.pair_slot_begin[p] = uint64_t(cap_a) + cap_b;  // [0,cap_b) = buffer B, [cap_b, cap_b+cap_a) = buffer A
+            // everything lift_pairs_kernel needs before the walk, in one sector (two for a reverse-strand pair)
+            const uint32_t r = W.rseg_read[s];
+            const bool rec_rev = (B.read_flag[r] & 0x10) != 0;
+            const bool changes_strand = (rec_rev == (B.rseg_is_fwd[s] != 0));
+            const bool need_flip = (!fwd) != changes_strand;
+            const uint32_t seq_len = B.read_seq_len[r];
+            const uint64_t rev_off = fwd ? 0ull : S.contig_rev_off[ctg];
+            uint32_t flags = (fwd ? kPdContigFwd : 0u) | (need_flip ? kPdNeedFlip : 0u) | (a < 0 ? kPdErrBounds : 0u) |
+                             (W.rseg_read_len[s] != seq_len ? kPdErrLength : 0u) | ((!fwd && rev_off == ~0ull) ? kPdNoRevSeq : 0u);
+            W.pair_desc[p] = PairDesc{B.rseg_cigar_begin[s], n_in, uint32_t(a), tab_lo, t0, t1, flags | (min(cap_b, 0xffffffu) << 8)};
+            if (!fwd) {
+                uint32_t w0 = 0, nw = 0;
+                if (B.rseg_win_begin) { w0 = B.rseg_win_begin[s]; nw = B.rseg_win_begin[s + 1] - w0; }
+                W.pair_desc_rev[p] = PairDescRev{B.read_seq_off[r], rev_off, uint32_t(S.contig_len[ctg]), seq_len, w0, nw};
+            }
         }
         ++p;
     }
@@ -188,46 +203,42 @@ __device__ __forceinline__ LiftOut lift_pair_body(const DevStatic& S, const DevB
     uint32_t cpos = 0;   // position on the contig strand the segment's table is written in
     int64_t rpos = 0;    // position on the reference once lifted
     bool need_flip = false, contig_fwd = true, usable = false;
-    uint32_t s = 0, g = 0, ctg = 0, seq_len = 0, cap_a = 0, cap_b = 0;
+    uint32_t cap_a = 0, cap_b = 0;
     uint32_t* buf_a = nullptr;
     uint32_t* buf_b = nullptr;
     OpSource cur{nullptr, 0, false};
     ReadBases read{nullptr, 0, false};
     uint64_t slot0 = 0;
+    PairDesc d{0, 0, 0, 0, 0, 0, 0};
+    PairDescRev dr{0, ~0ull, 0, 0, 0, 0};
     if (valid) {
-        s = W.pair_rseg[p];
-        g = W.pair_seg[p];
-        const uint32_t r = W.rseg_read[s];
+        // one sector says everything about the pair (pair_fill_body packed it); the slot bounds sit next to each other
+        d = W.pair_desc[p];
         slot0 = W.pair_slot_begin[p];
         const uint64_t slot1 = W.pair_slot_begin[p + 1];
-        contig_fwd = S.seg_is_fwd[g] != 0;
-        const bool rec_rev = (B.read_flag[r] & 0x10) != 0;
-        const bool changes_strand = (rec_rev == (B.rseg_is_fwd[s] != 0));
-        need_flip = (!contig_fwd) != changes_strand;
+        contig_fwd = (d.flags_cap_b & kPdContigFwd) != 0u;
+        need_flip = (d.flags_cap_b & kPdNeedFlip) != 0u;
         if (slot1 > W.scratch_cap) {
             atomicOr(&T->overflow, OVF_SCRATCH);
             err = ST_ERR_CAPACITY;
         } else {
             usable = true;
-            cap_b = W.pair_cap_b[p];
+            cap_b = d.flags_cap_b >> 8;
             cap_a = uint32_t(slot1 - slot0) - cap_b;
             buf_b = W.scratch + slot0;
             buf_a = buf_b + cap_b;
-            ctg = B.rseg_contig[s];
-            seq_len = B.read_seq_len[r];
-            read = ReadBases{B.seq4 + B.read_seq_off[r], seq_len, need_flip};
-            cur = OpSource{B.cigar + B.rseg_cigar_begin[s], B.rseg_cigar_len[s], false};
+            cur = OpSource{B.cigar + d.cigar_begin, d.n_ops, false};
             n_in_ops += cur.n;
-            const int64_t pos = B.rseg_pos[s];  // validated on the host: 0 <= pos < 2^31
             status = ST_LIFTED;
-            if (contig_fwd) {
-                cpos = uint32_t(pos);
-            } else {
-                // reverse-strand contig segment: flip onto the contig's reverse strand (:162-167)
-                const int64_t rev = int64_t(S.contig_len[ctg]) - (pos + W.rseg_ref_len[s]);
-                if (rev < 0) { err = ST_ERR_BOUNDS; usable = false; }  // read runs past the contig end (invalid input)
-                cpos = uint32_t(rev);
+            cpos = d.cpos;  // reverse-strand contig segment: contig_len - end, on the contig's reverse strand (:162-167)
+            if (!contig_fwd) {
+                if (d.flags_cap_b & kPdErrBounds) { err = ST_ERR_BOUNDS; usable = false; }  // read runs past the contig end (invalid input)
                 cur.reversed = true;
+                dr = W.pair_desc_rev[p];
+                read = ReadBases{B.seq4 + dr.seq_off, dr.seq_len, need_flip};
+            } else if (!kAllStages) {  // (stage tests simplify forward pairs inline: they need the read's bases too)
+                const uint32_t r = W.rseg_read[W.pair_rseg[p]];
+                read = ReadBases{B.seq4 + B.read_seq_off[r], B.read_seq_len[r], need_flip};
             }
         }
     }
@@ -245,22 +256,13 @@ __device__ __forceinline__ LiftOut lift_pair_body(const DevStatic& S, const DevB
     // ---- a5: left-shift on the contig's reverse strand (:168-175)
     {
         bool go = usable && !contig_fwd && (stage_mask & 1u);
-        uint64_t rev_off = ~0ull;
-        if (go) {
-            rev_off = S.contig_rev_off[ctg];
-            if (rev_off == ~0ull) { err = ST_ERR_BOUNDS; go = false; usable = false; }  // Option::unwrap on None (:174)
-        }
+        if (go && (d.flags_cap_b & kPdNoRevSeq)) { err = ST_ERR_BOUNDS; go = false; usable = false; }  // Option::unwrap on None (:174)
         if (__any_sync(FULL, go)) {
             OpSink sink(buf_a, go ? cap_a : 0u);
-            const uint64_t* win = nullptr;
-            uint32_t n_win = 0;
-            if (go && B.rseg_win_begin) {
-                const uint32_t w0 = B.rseg_win_begin[s];
-                win = B.indel_win + w0;
-                n_win = B.rseg_win_begin[s + 1] - w0;
-            }
-            const uint32_t shifted = run_left_shift_warp(go, cur, cpos, go ? S.rev_pool + rev_off : nullptr,
-                                                         go ? uint32_t(S.contig_len[ctg]) : 0u, read, win, n_win, buf_b, sink, cnt, err);
+            const uint64_t* win = (go && B.rseg_win_begin) ? B.indel_win + dr.win_begin : nullptr;
+            const uint32_t n_win = (go && B.rseg_win_begin) ? dr.n_win : 0u;
+            const uint32_t shifted = run_left_shift_warp(go, cur, cpos, go ? S.rev_pool + dr.rev_off : nullptr,
+                                                         go ? dr.contig_len : 0u, read, win, n_win, buf_b, sink, cnt, err);
             if (go) {
                 cpos = shifted;
                 span = sink.ref_span;
@@ -294,10 +296,10 @@ __device__ __forceinline__ LiftOut lift_pair_body(const DevStatic& S, const DevB
     if (usable && !err && (stage_mask & 2u)) {
         OpSink sink(lift_buf, cap_b);
         int64_t lifted_pos = 0;
-        const bool some = run_liftover(cur, cpos, S.table, S.seg_tab_begin[g], S.seg_tab_begin[g + 1], W.pair_tab_lo[p], sink, &lifted_pos);
+        const bool some = run_liftover(cur, cpos, S.table, d.t0, d.t1, d.tab_lo, sink, &lifted_pos);
         if (sink.overflow) err = ST_ERR_CAPACITY;
         else if (!some) status = ST_NONE;
-        else if (W.rseg_read_len[s] != seq_len) err = ST_ERR_LENGTH;
+        else if (d.flags_cap_b & kPdErrLength) err = ST_ERR_LENGTH;
         // simplify_alignment_indels rewrites only I/D runs that hold both kinds; on a cleaned + compressed CIGAR without
         // such a run it is the identity (single-kind runs are already one op, edges are already clean), so it is skipped
         simplify_is_identity = !sink.mixed_cluster;
@@ -324,7 +326,7 @@ __device__ __forceinline__ LiftOut lift_pair_body(const DevStatic& S, const DevB
             uint64_t ref_len = 0;
             uint32_t* rec = nullptr;
             if (go) {
-                const int32_t chrom = S.seg_chrom[g];
+                const int32_t chrom = S.seg_chrom[W.pair_seg[p]];
                 ref = S.ref + S.chrom_off[chrom];
                 ref_len = S.chrom_off[chrom + 1] - S.chrom_off[chrom];
                 if (cur_is_a) {  // shift without liftover: move the input out of the way

@@ -210,6 +210,10 @@ int run_batch(ptl_ctx* ctx, EmulSlot& sl, const ptl_batch* b, uint32_t stage_mas
     W.pair_bin = pair_bin.data(); W.pair_out_off = pair_out_off.data(); W.simplify_list = simplify_list.data();
     std::vector<uint32_t> long_list(np + 1);
     W.long_list = long_list.data();
+    std::vector<PairDesc> pair_desc(np + 1);
+    std::vector<PairDescRev> pair_desc_rev(np + 1);
+    W.pair_desc = pair_desc.data();
+    W.pair_desc_rev = pair_desc_rev.data();
     W.long_ops = ctx->long_pair_ops;
     for (uint32_t s = 0; s < ns; ++s) pair_fill_body(S, B, W, s);
     pair_slot_begin[np] = 0;
