@@ -200,3 +200,58 @@ def test_format_sa_tags_matches_oracle_text(oracle):
     first = got[k].split(";")[0].split(",")
     assert first[0] == s.chrom_names[res.rec_tid[j]] and int(first[1]) == int(res.rec_pos[j]) + 1
     assert first[2] == ("-" if res.rec_flag[j] & 0x10 else "+") and first[3] == res.record_cigar(j) and int(first[4]) == int(res.rec_mapq[j])
+
+
+def _batch_arrays(c):
+    g = lambda p, k: np.ctypeslib.as_array(p, (k,)).copy() if k else np.zeros(0)
+    n, ns = c.n_reads, c.n_read_segments
+    out = {"n": (n, ns, int(c.n_cigar))}
+    for f, k in (("read_flag", n), ("read_mapq", n), ("read_bin", n), ("read_seq_len", n), ("read_seq_off", n), ("read_seg_begin", n + 1),
+                 ("rseg_contig", ns), ("rseg_pos", ns), ("rseg_is_fwd", ns), ("rseg_cigar_len", ns)):
+        out[f] = g(getattr(c, f), k)
+    cb, cl = g(c.rseg_cigar_begin, ns), out["rseg_cigar_len"]
+    pool = g(c.cigar, int(c.n_cigar))
+    out["seg_cigars"] = [pool[int(cb[i]): int(cb[i]) + int(cl[i])].tobytes() for i in range(ns)]  # (the pools may be laid out differently)
+    return out
+
+
+def _same(a, b):
+    return a.keys() == b.keys() and all((a[k] == b[k]) if isinstance(a[k], (tuple, list)) else np.array_equal(a[k], b[k]) for k in a)
+
+
+def test_oracle_packer_equals_product_packer():
+    """bench.py --impl reference packs with the oracle's own record-loop head (ptl_oracle_pack_batch) so that it never loads
+    the product library: both packers must produce the same batch."""
+    import oracle_lib
+    s = synth.make("tiny", seed=12, n_reads=2500)
+    pb = helpers.pack(s)
+    ob = oracle_lib.OraclePackedBatch(s.read_records, 0, s.read_records.n_reads, s.contig_names, threads=3)
+    assert _same(_batch_arrays(pb.c), _batch_arrays(ob.c))
+    assert np.array_equal(pb.record_index(), ob.record_index())
+
+
+def test_repacking_a_batch_reuses_its_arena_and_equals_a_fresh_pack():
+    """ptl_pack_batch_into (a streaming host repacks a ring of pinned batches; distinct batches from distinct threads)."""
+    import threading
+    s = synth.make("tiny", seed=13, n_reads=3000)
+    L = lib.load()
+    segs = L.prepare_contig_records(s.contig_records)
+    for windows in (None, segs):
+        fresh = lib.PackedBatch(L, s.read_records, 1000, 1500, s.contig_names, windows=windows)
+        ring = lib.PackedBatch(L, s.read_records, 0, 2900, s.contig_names, windows=windows)   # a larger arena first
+        ring.repack(1000, 1500)
+        a, b = _batch_arrays(fresh.c), _batch_arrays(ring.c)
+        assert _same(a, b)
+        if windows is not None:
+            assert fresh.c.n_indel_win == ring.c.n_indel_win > 0
+            assert np.array_equal(np.ctypeslib.as_array(fresh.c.indel_win, (int(fresh.c.n_indel_win),)), np.ctypeslib.as_array(ring.c.indel_win, (int(ring.c.n_indel_win),)))
+        ring.repack(0, 10)
+        assert ring.c.n_reads == 10
+        ring.repack(0, 3000)  # grows
+        assert _same(_batch_arrays(ring.c), _batch_arrays(lib.PackedBatch(L, s.read_records, 0, 3000, s.contig_names, windows=windows).c))
+    bufs = [lib.PackedBatch(L, s.read_records, 0, 10, s.contig_names, windows=segs) for _ in range(4)]
+    th = [threading.Thread(target=lambda t=t: [bufs[t].repack(i * 250, 250) for i in range(t, 12, 4)]) for t in range(4)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for t in range(4):  # the last chunk each thread packed: 8 + t
+        assert _same(_batch_arrays(bufs[t].c), _batch_arrays(lib.PackedBatch(L, s.read_records, (8 + t) * 250, 250, s.contig_names, windows=segs).c))
