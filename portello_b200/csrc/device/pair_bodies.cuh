@@ -121,6 +121,19 @@ __device__ __forceinline__ void pair_fill_body(const DevStatic& S, const DevBatc
     const int64_t start = B.rseg_pos[s], ref_len = W.rseg_ref_len[s], end = start + ref_len;
     const uint32_t ctg = B.rseg_contig[s];
     const uint32_t n_in = B.rseg_cigar_len[s];
+    // the per-segment facts of the pair descriptors, loaded up front (independent of the table searches below, whose
+    // dependent loads they overlap with; loaded after them they cost pair_fill_kernel 30 % more time)
+    const uint32_t r = W.rseg_read[s];
+    const uint16_t d_flag = B.read_flag[r];
+    const uint32_t d_seq_len = B.read_seq_len[r];
+    const uint64_t d_seq_off = B.read_seq_off[r];
+    const bool d_seg_fwd = B.rseg_is_fwd[s] != 0;
+    const uint32_t d_read_len = W.rseg_read_len[s];
+    const uint64_t d_cigar_begin = B.rseg_cigar_begin[s];
+    const uint64_t d_rev_off = S.contig_rev_off[ctg];
+    const uint32_t d_contig_len = uint32_t(S.contig_len[ctg]);
+    uint32_t d_w0 = 0, d_nw = 0;
+    if (B.rseg_win_begin) { d_w0 = B.rseg_win_begin[s]; d_nw = B.rseg_win_begin[s + 1] - d_w0; }
     for (uint32_t g = S.contig_seg_begin[ctg]; g < S.contig_seg_begin[ctg + 1]; ++g) {
         if (!(end >= int64_t(S.seg_so_start[g]) && start < int64_t(S.seg_so_end[g]))) continue;
         if (p < W.pair_cap) {
@@ -150,20 +163,13 @@ __device__ __forceinline__ void pair_fill_body(const DevStatic& S, const DevBatc
             W.pair_cap_b[p] = cap_b;
             W.pair_slot_begin[p] = uint64_t(cap_a) + cap_b;  // [0,cap_b) = buffer B, [cap_b, cap_b+cap_a) = buffer A
             // everything lift_pairs_kernel needs before the walk, in one sector (two for a reverse-strand pair)
-            const uint32_t r = W.rseg_read[s];
-            const bool rec_rev = (B.read_flag[r] & 0x10) != 0;
-            const bool changes_strand = (rec_rev == (B.rseg_is_fwd[s] != 0));
+            const bool rec_rev = (d_flag & 0x10) != 0;
+            const bool changes_strand = (rec_rev == d_seg_fwd);
             const bool need_flip = (!fwd) != changes_strand;
-            const uint32_t seq_len = B.read_seq_len[r];
-            const uint64_t rev_off = fwd ? 0ull : S.contig_rev_off[ctg];
-            uint32_t flags = (fwd ? kPdContigFwd : 0u) | (need_flip ? kPdNeedFlip : 0u) | (a < 0 ? kPdErrBounds : 0u) |
-                             (W.rseg_read_len[s] != seq_len ? kPdErrLength : 0u) | ((!fwd && rev_off == ~0ull) ? kPdNoRevSeq : 0u);
-            W.pair_desc[p] = PairDesc{B.rseg_cigar_begin[s], n_in, uint32_t(a), tab_lo, t0, t1, flags | (min(cap_b, 0xffffffu) << 8)};
-            if (!fwd) {
-                uint32_t w0 = 0, nw = 0;
-                if (B.rseg_win_begin) { w0 = B.rseg_win_begin[s]; nw = B.rseg_win_begin[s + 1] - w0; }
-                W.pair_desc_rev[p] = PairDescRev{B.read_seq_off[r], rev_off, uint32_t(S.contig_len[ctg]), seq_len, w0, nw};
-            }
+            const uint32_t flags = (fwd ? kPdContigFwd : 0u) | (need_flip ? kPdNeedFlip : 0u) | (a < 0 ? kPdErrBounds : 0u) |
+                                   (d_read_len != d_seq_len ? kPdErrLength : 0u) | ((!fwd && d_rev_off == ~0ull) ? kPdNoRevSeq : 0u);
+            W.pair_desc[p] = PairDesc{d_cigar_begin, n_in, uint32_t(a), tab_lo, t0, t1, flags | (min(cap_b, 0xffffffu) << 8)};
+            if (!fwd) W.pair_desc_rev[p] = PairDescRev{d_seq_off, d_rev_off, d_contig_len, d_seq_len, d_w0, d_nw};
         }
         ++p;
     }
