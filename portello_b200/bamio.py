@@ -219,3 +219,17 @@ def write_dataset(s, out_dir: str, n_unmapped: int = 0, level: int = 1, threads:
         index_bam(p)
         paths["contigs" if which == 0 else "reads"] = p
     return paths
+
+
+if __name__ == "__main__":
+    # python -m portello_b200.bamio <workload> <n_reads> <out_dir> [n_unmapped]: a synthetic data set as the three input files
+    # of portello (and of portello-b200), e.g. to run the real portello on the same inputs on a machine that has it:
+    #   portello --assembly-to-ref <out_dir>/contigs_to_ref.bam --read-to-assembly <out_dir>/reads_to_contigs.bam \
+    #            --ref <out_dir>/ref.fa --remapped-read-output remapped.bam --unassembled-read-output unassembled.bam
+    import sys
+
+    from . import synth as _synth
+
+    wl, n, out = sys.argv[1], int(sys.argv[2]), sys.argv[3]
+    n_un = int(sys.argv[4]) if len(sys.argv) > 4 else n // 200
+    print(write_dataset(_synth.make(wl, n_reads=n), out, n_unmapped=n_un))
