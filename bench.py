@@ -519,6 +519,33 @@ def main():
     rank_e2e_ms = all_ranks(e2e_dt_here * 1e3)
     h2d_here = h2d_bytes(best_mode)
     h2d_total, d2h_total = sum_over_ranks(float(h2d_here)), sum_over_ranks(float(d2h))
+
+    def measure_copy_only(nb_h2d, nb_d2h, reps=5):
+        """The same bytes as one e2e step, as two plain pinned copies (one each way, concurrently) on every rank at once and
+        nothing else: the box's DMA floor for the step.  e2e / this = how much of the step is not PCIe."""
+        hb_in, hb_out = torch.empty(nb_h2d, dtype=torch.uint8).pin_memory(), torch.empty(nb_d2h, dtype=torch.uint8).pin_memory()
+        db_in, db_out = torch.empty(nb_h2d, dtype=torch.uint8, device="cuda"), torch.zeros(nb_d2h, dtype=torch.uint8, device="cuda")
+        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+
+        def once():
+            with torch.cuda.stream(s_in):
+                db_in.copy_(hb_in, non_blocking=True)
+            with torch.cuda.stream(s_out):
+                hb_out.copy_(db_out, non_blocking=True)
+
+        once()
+        torch.cuda.synchronize()
+        barrier()
+        p0 = time.perf_counter()
+        for _ in range(reps):
+            once()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - p0) / reps
+        barrier()
+        return dt
+
+    copy_dt_here = measure_copy_only(int(h2d_here), int(d2h))
+    copy_dt = max_over_ranks(copy_dt_here)
     # ---------------------------------------------------------------- e2e_with_pack: the host packer on the clock
     # decoded records -> ptl_pack_batch_into (split segments, SA parse, indel windows) on P host threads, into a ring of
     # reusable pinned batches, overlapped with submit / wait of earlier chunks (INTEGRATION.md: one packer thread per slot).
@@ -659,6 +686,10 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_total), "d2h_bytes_per_step": int(d2h_total),
                     "ms_per_step": e2e_dt * 1e3,
                     "pcie_gbs_per_rank": {"h2d": round(h2d_here / e2e_dt_here / 1e9, 2), "d2h": round(d2h / e2e_dt_here / 1e9, 2)},
+                    "copy_only": {"ms_per_step": copy_dt * 1e3, "gbs_per_rank": {"h2d": round(h2d_here / copy_dt_here / 1e9, 2), "d2h": round(d2h / copy_dt_here / 1e9, 2)},
+                                  "aggregate_gbs": round((h2d_total + d2h_total) / copy_dt / 1e9, 1), "frac_of_e2e": copy_dt / e2e_dt,
+                                  "what": "the step's H2D and D2H bytes as two plain pinned copies per rank, all ranks at once, nothing else: "
+                                          "the DMA floor of the e2e step on this box"},
                     "alternatives": {k: {"value": pairs_total / v[0], "ms_per_step": v[0] * 1e3, "h2d_bytes_per_step_rank0": int(h2d_bytes(k)), "steps": v[3]}
                                      for k, v in e2e_runs.items()}},
             "e2e_with_pack": e2e_with_pack,

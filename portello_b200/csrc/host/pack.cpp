@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <numeric>
 #include <string>
 #include <unordered_map>
@@ -17,6 +18,13 @@
 #include "host_util.hpp"
 
 using namespace ptl;
+
+#ifndef PTL_PF_HINT
+#define PTL_PF_HINT 3
+#endif
+#ifndef PTL_WIN_AHEAD
+#define PTL_WIN_AHEAD 32
+#endif
 
 namespace {
 
@@ -153,9 +161,73 @@ void split_segments(const NameMap& names, int32_t tid, int64_t pos, uint16_t fla
 
 size_t align_up(size_t x) { return (x + 255) & ~size_t(255); }
 
+// One forward walk of a CIGAR: clip positions as get_read_clip_positions (cigar/mod.rs:85-118), reference span, and --
+// with kClusters -- the read offset at which every I/D cluster (a maximal run of I/D ops with at least one non-empty op,
+// as CigarShiftBuilder forms them, cigar_indel_shifter.rs:63-85) begins, appended to `cluster_read_begin`.
+struct CigarScan { uint64_t left, right, size; int64_t ref; uint32_t n_clusters; };
+// Op kinds change unpredictably along a HiFi CIGAR, so the walk is branch-free; `cluster_read_begin` needs room for n entries.
+template <bool kClusters>
+inline CigarScan scan_cigar(const uint32_t* c, uint32_t n, uint32_t* cluster_read_begin) {
+    constexpr uint32_t kIndelMask = (1u << OP_I) | (1u << OP_D);
+    uint64_t left = 0, right = 0, size = 0, ref = 0;
+    uint32_t in_left = 1, open = 0, n_cl = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t x = c[i], op = op_of(x), l = len_of(x);
+        const uint32_t indel = (kIndelMask >> op) & 1u, clip = (kClipMask >> op) & 1u, nonempty = l != 0;
+        if (kClusters) {
+            cluster_read_begin[n_cl] = uint32_t(size);
+            n_cl += indel & nonempty & (open ^ 1u);
+            open = indel & (open | nonempty);
+        }
+        left += uint64_t(l) & (0 - uint64_t(clip & in_left));
+        right += uint64_t(l) & (0 - uint64_t(clip & (in_left ^ 1u)));
+        in_left &= clip;
+        size += uint64_t(l) & (0 - uint64_t((kReadMask >> op) & 1u));
+        ref += uint64_t(l) & (0 - uint64_t((kRefMask >> op) & 1u));
+    }
+    return {left, size - right, size, int64_t(ref), n_cl};
+}
+
+// The 16 nibbles the shifter may look at for a cluster whose walk starts at read_view[read_end - 1]: nibble q (bits 4q..)
+// is read_view[read_end - 1 - q]; steps outside the read stay 0 (the kernel reports the reference's panic before using them).
+inline uint64_t window_bits(const uint8_t* sq, uint32_t len, uint32_t read_end, bool flip, const uint8_t* pool_end) {
+    if (read_end >= 16u && read_end <= len) {  // 16 steps, all inside the read: two loads instead of 16
+        const uint32_t a = flip ? len - read_end : read_end - 16u;  // lowest of the 16 nibble indices
+        const uint8_t* p = sq + (a >> 1);
+        if (p + 9 <= pool_end) {
+            uint64_t x;
+            std::memcpy(&x, p, 8);
+            if (!flip) {  // descending indices: the byte-swapped word has nibble a (or a - 1) on top and a + 15 (a + 14) at the bottom
+                x = __builtin_bswap64(x);
+                return (a & 1u) ? (x << 4) | uint64_t(p[8] >> 4) : x;
+            }
+            x = ((x & 0x0f0f0f0f0f0f0f0full) << 4) | ((x >> 4) & 0x0f0f0f0f0f0f0f0full);  // ascending: nibbles in index order
+            return (a & 1u) ? (x >> 4) | (uint64_t(p[8] >> 4) << 60) : x;
+        }
+    }
+    uint64_t bits = 0;
+    for (uint32_t q = 0; q < 16 && q < read_end; ++q) {
+        const uint32_t idx = read_end - 1u - q;
+        if (idx >= len) continue;
+        const uint32_t j = flip ? len - 1u - idx : idx;
+        const uint32_t nib = (j & 1u) ? (sq[j >> 1] & 0xfu) : (sq[j >> 1] >> 4);
+        bits |= uint64_t(nib) << (4u * q);
+    }
+    return bits;
+}
+
 }  // namespace
 
+// Scratch of one pack call, kept with the batch so that a ring of reused batches stops allocating.
+struct PackScratch {
+    std::vector<Seg> segs, tmp;
+    std::vector<uint32_t> seg_begin, kept, win_begin, seg_size;
+    std::vector<uint32_t> cluster_read_begin;  // per I/D cluster, CIGAR order: read bases consumed before its first op
+    Ops sa_pool;
+};
+
 struct ptl_packed_batch {
+    PackScratch scratch;
     void* arena = nullptr;
     size_t arena_cap = 0;
     bool pinned = false;
@@ -210,7 +282,9 @@ int ptl_pack_batch(const ptl_read_records* recs, uint32_t first, uint32_t count,
     return ptl_pack_batch_ex(recs, first, count, n_contigs, contig_names, pinned, PTL_WIN_NONE, nullptr, out);
 }
 
-// Packs into `pb`, reusing its arena when it is large enough (a streaming host repacks the same few buffers).
+// Packs into `pb`, reusing its arena and its scratch vectors when they are large enough (a streaming host repacks the
+// same few buffers).  One forward walk per CIGAR yields everything the batch needs from it: clip positions, read and
+// reference spans, and the read offset of every I/D cluster; the window fill then never looks at a CIGAR again.
 static int pack_impl(const ptl_read_records* recs, uint32_t first, uint32_t count, uint32_t n_contigs, const char* const* contig_names, int window_mode,
                      const ptl_contig_segments* wsegs, ptl_packed_batch* pb) {
     if (!recs || !pb || uint64_t(first) + count > recs->n_reads) return PTL_ERR_INVALID_ARG;
@@ -218,13 +292,33 @@ static int pack_impl(const ptl_read_records* recs, uint32_t first, uint32_t coun
     const bool contig_wants_windows = window_mode != PTL_WIN_NONE;
     const bool pinned = pb->pinned;
     try {
-        NameMap names(n_contigs, contig_names);
-        // pass 1: parse SA tags (rare), collect segment lists
-        std::vector<Seg> segs, tmp;
-        std::vector<uint32_t> seg_begin{0}, kept;
-        Ops sa_pool;
+        PackScratch& S = pb->scratch;
+        std::vector<Seg>& segs = S.segs;
+        std::vector<Seg>& tmp = S.tmp;
+        std::vector<uint32_t>& seg_begin = S.seg_begin;
+        std::vector<uint32_t>& kept = S.kept;
+        std::vector<uint32_t>& win_begin = S.win_begin;
+        std::vector<uint32_t>& seg_size = S.seg_size;
+        std::vector<uint32_t>& rb = S.cluster_read_begin;
+        Ops& sa_pool = S.sa_pool;
+        segs.clear(); seg_begin.clear(); kept.clear(); win_begin.clear(); seg_size.clear(); sa_pool.clear();
+        seg_begin.push_back(0);
+        size_t n_rb = 0;  // entries of rb in use (a cluster per op at most: room is made ahead of every walk)
+        auto rb_room = [&](size_t ops) { if (rb.size() < n_rb + ops) rb.resize(std::max(n_rb + ops, rb.size() * 2)); };
+        std::unique_ptr<NameMap> names;  // built on the first SA tag
         const uint64_t cig0 = recs->cigar_begin[first], cig1 = recs->cigar_begin[first + count];
+        const uint32_t prim_ops = uint32_t(cig1 - cig0);
         uint32_t skipped = 0;
+        // The pair test of read_alignment_scanner.rs:80-103 against the reverse-strand segments of the read segment's contig:
+        // only those read segments go through left_shift_indels and want windows.
+        auto wants_windows = [&](uint32_t contig, int64_t start, int64_t end) {
+            if (window_mode != PTL_WIN_REVERSE_PAIRS) return true;
+            if (contig >= wsegs->n_contigs) return false;
+            for (uint32_t q = wsegs->contig_seg_begin[contig]; q < wsegs->contig_seg_begin[contig + 1]; ++q)
+                if (!wsegs->seg_is_fwd[q] && end >= int64_t(wsegs->seg_seq_order_start[q]) && start < int64_t(wsegs->seg_seq_order_end[q])) return true;
+            return false;
+        };
+        // pass 1: segment lists (SA tags are rare), and per segment the read offsets of its I/D clusters
         for (uint32_t r = first; r < first + count; ++r) {
             const uint16_t flag = recs->flag[r];
             if (flag & 0x4) throw InputError("unmapped record in the mapped read scan (assert, read_alignment_scanner.rs:396)");
@@ -232,53 +326,54 @@ static int pack_impl(const ptl_read_records* recs, uint32_t first, uint32_t coun
             const uint32_t* cg = recs->cigar + recs->cigar_begin[r];
             const uint32_t ncg = uint32_t(recs->cigar_begin[r + 1] - recs->cigar_begin[r]);
             const char* sa = recs->sa_tag ? recs->sa_tag[r] : nullptr;
-            const uint32_t pool_before = uint32_t(sa_pool.size());
-            split_segments(names, recs->tid[r], recs->pos[r], flag, recs->mapq[r], cg, ncg, sa, tmp, sa_pool);
-            for (Seg g : tmp) {
-                // rebase CIGAR offsets into the batch pool: [record cigars of the slice][SA cigars]
-                if (g.from_primary) g.cig_off = uint32_t(recs->cigar_begin[r] - cig0);
-                else g.cig_off = uint32_t(cig1 - cig0) + g.cig_off;
-                segs.push_back(g);
+            if (!sa) {
+                // one segment: the primary record itself
+                if (contig_wants_windows) rb_room(ncg);
+                const CigarScan sc = contig_wants_windows ? scan_cigar<true>(cg, ncg, rb.data() + n_rb) : scan_cigar<false>(cg, ncg, nullptr);
+                const bool rev = flag & 0x10;
+                Seg p{};
+                if (!rev) { p.so_start = uint32_t(sc.left); p.so_end = uint32_t(sc.right); }
+                else { p.so_start = uint32_t(sc.size - sc.right); p.so_end = uint32_t(sc.size - sc.left); }
+                if (p.so_start >= p.so_end) throw InputError("Can't parse consistent split read information from SA tag");  // split_read.rs:145-152
+                p.contig = uint32_t(recs->tid[r]);
+                p.pos = recs->pos[r];
+                p.is_fwd = !rev;
+                p.mapq = recs->mapq[r];
+                p.from_primary = 1;
+                p.cig_off = uint32_t(recs->cigar_begin[r] - cig0);
+                p.cig_len = ncg;
+                if (contig_wants_windows) {
+                    win_begin.push_back(uint32_t(n_rb));
+                    if (sc.n_clusters && wants_windows(p.contig, p.pos, p.pos + sc.ref)) n_rb += sc.n_clusters;
+                    seg_size.push_back(uint32_t(sc.size));
+                }
+                segs.push_back(p);
+            } else {
+                if (!names) names.reset(new NameMap(n_contigs, contig_names));
+                split_segments(*names, recs->tid[r], recs->pos[r], flag, recs->mapq[r], cg, ncg, sa, tmp, sa_pool);
+                for (Seg g : tmp) {
+                    if (contig_wants_windows) {
+                        const uint32_t* c = g.from_primary ? cg : sa_pool.data() + g.cig_off;
+                        rb_room(g.cig_len);
+                        const CigarScan sc = scan_cigar<true>(c, g.cig_len, rb.data() + n_rb);
+                        win_begin.push_back(uint32_t(n_rb));
+                        if (sc.n_clusters && wants_windows(g.contig, g.pos, g.pos + sc.ref)) n_rb += sc.n_clusters;
+                        seg_size.push_back(uint32_t(sc.size));
+                    }
+                    // rebase CIGAR offsets into the batch pool: [record cigars of the slice][SA cigars]
+                    if (g.from_primary) g.cig_off = uint32_t(recs->cigar_begin[r] - cig0);
+                    else g.cig_off = prim_ops + g.cig_off;
+                    segs.push_back(g);
+                }
             }
-            (void)pool_before;
+            if (n_rb > 0xffffffffull) throw InputError("too many indel clusters in one batch");
             seg_begin.push_back(uint32_t(segs.size()));
             kept.push_back(r);
         }
         const uint32_t n = uint32_t(kept.size()), ns = uint32_t(segs.size());
         const uint64_t n_cig = (cig1 - cig0) + sa_pool.size();
-        auto seg_cigar = [&](const Seg& g) {
-            return g.cig_off < uint32_t(cig1 - cig0) ? recs->cigar + cig0 + g.cig_off : sa_pool.data() + (g.cig_off - uint32_t(cig1 - cig0));
-        };
-        // indel windows: count the I/D clusters (maximal runs of non-empty I/D ops, as CigarShiftBuilder forms them,
-        // cigar_indel_shifter.rs:63-85) of every segment that wants them
-        std::vector<uint32_t> win_begin;
-        uint64_t n_win = 0;
-        if (contig_wants_windows) {
-            win_begin.assign(size_t(ns) + 1, 0);
-            for (uint32_t k = 0; k < ns; ++k) {
-                win_begin[k] = uint32_t(n_win);
-                const Seg& g = segs[k];
-                const uint32_t* c = seg_cigar(g);
-                if (window_mode == PTL_WIN_REVERSE_PAIRS) {
-                    // the pair test of :80-103 against the reverse-strand segments of the read segment's contig
-                    if (g.contig >= wsegs->n_contigs) continue;
-                    const int64_t start = g.pos, end = g.pos + ref_span(c, g.cig_len);
-                    bool hit = false;
-                    for (uint32_t q = wsegs->contig_seg_begin[g.contig]; q < wsegs->contig_seg_begin[g.contig + 1] && !hit; ++q)
-                        hit = !wsegs->seg_is_fwd[q] && end >= int64_t(wsegs->seg_seq_order_start[q]) && start < int64_t(wsegs->seg_seq_order_end[q]);
-                    if (!hit) continue;
-                }
-                bool in_indel = false;
-                for (uint32_t i = 0; i < g.cig_len; ++i) {
-                    const uint32_t op = op_of(c[i]);
-                    if (op == OP_I || op == OP_D) { if (len_of(c[i]) > 0) in_indel = true; }
-                    else if (in_indel) { ++n_win; in_indel = false; }
-                }
-                if (in_indel) ++n_win;
-                if (n_win > 0xffffffffull) throw InputError("too many indel clusters in one batch");
-            }
-            win_begin[ns] = uint32_t(n_win);
-        }
+        const uint64_t n_win = n_rb;
+        if (contig_wants_windows) win_begin.push_back(uint32_t(n_win));
         // one arena for all small arrays
         size_t off = 0;
         auto take = [&](size_t bytes) { const size_t o = off; off = align_up(off + bytes); return o; };
@@ -343,80 +438,47 @@ static int pack_impl(const ptl_read_records* recs, uint32_t first, uint32_t coun
             // read_view[read_end - 1 - q], q = 0,1,..; read_view is the record's bases, reverse-complemented when
             // need_flipped_read_alignment (:153-157), which for a reverse-strand contig segment is
             // !(record.is_reverse() == segment.is_fwd_strand).  The window stores the BAM nibble of each step.
+            // read_end = (read bases after the cluster) + (its insertions) = size - (read bases before it), so the forward
+            // offsets of pass 1 give every window; a segment's windows are stored last cluster first.
             auto* wb = reinterpret_cast<uint32_t*>(a + o_wb);
             auto* win = reinterpret_cast<uint64_t*>(a + o_win);
             std::memcpy(wb, win_begin.data(), (size_t(ns) + 1) * 4);
+            // The bases of a cluster sit in a cache line nobody has touched yet (7.5 KB of packed bases per read, one line
+            // per cluster), so the fill runs kWinAhead windows behind a cursor that only prefetches: the misses of
+            // neighbouring clusters, segments and reads overlap instead of queueing up one by one.
+            constexpr uint32_t kWinAhead = PTL_WIN_AHEAD;
+            struct Pending { const uint8_t* sq; uint32_t len, read_end, flip; };
+            Pending ring[kWinAhead];
+            uint64_t issued = 0, done = 0;
+            const uint8_t* pool_end = recs->seq4 + recs->seq4_bytes;
+            auto retire = [&]() {
+                const Pending& t = ring[done % kWinAhead];
+                win[done++] = window_bits(t.sq, t.len, t.read_end, t.flip != 0, pool_end);
+            };
             for (uint32_t i = 0; i < n; ++i) {
                 const uint32_t r = kept[i];
                 const uint8_t* sq = recs->seq4 + recs->seq_off[r];
                 const uint32_t len = recs->seq_len[r];
                 const bool rec_rev = (recs->flag[r] & 0x10) != 0;
                 for (uint32_t k = seg_begin[i]; k < seg_begin[i + 1]; ++k) {
-                    if (win_begin[k] == win_begin[k + 1]) continue;
-                    const Seg& g = segs[k];
-                    const bool flip = !(rec_rev == (g.is_fwd != 0));
-                    const uint32_t* c = seg_cigar(g);
-                    uint64_t* w = win + win_begin[k];
-                    uint32_t read_head = 0, blk_read = 0, ins = 0;
-                    bool in_indel = false;
-                    // The bases of a cluster sit in a cache line nobody has touched yet (7.5 KB of packed bases per read,
-                    // one line per cluster): a first walk only finds where the clusters end and prefetches those lines,
-                    // so that the misses of a segment overlap instead of queueing up one per cluster.
-                    {
-                        uint32_t rh = 0, br = 0, in2 = 0;
-                        bool open = false;
-                        auto touch = [&]() {
-                            const uint32_t read_end = br + in2;
-                            if (read_end > 0 && read_end <= len) {
-                                const uint32_t idx = read_end - 1u, j = flip ? len - 1u - idx : idx;
-                                __builtin_prefetch(sq + (j >> 1));
-                            }
-                            open = false;
-                            in2 = 0;
-                        };
-                        for (uint32_t t = g.cig_len; t-- > 0;) {
-                            const uint32_t x = c[t], op = op_of(x), l = len_of(x);
-                            if (op == OP_I || op == OP_D) {
-                                if (l > 0) {
-                                    if (!open) { open = true; br = rh; }
-                                    if (op == OP_I) in2 += l;
-                                }
-                            } else if (open) {
-                                touch();
-                            }
-                            rh += uint32_t(read_adv(x));
+                    const uint32_t w0 = win_begin[k], w1 = win_begin[k + 1];
+                    if (w0 == w1) continue;
+                    const uint32_t flip = !(rec_rev == (segs[k].is_fwd != 0));
+                    const uint32_t size32 = seg_size[k];
+                    for (uint32_t c = w1; c-- > w0;) {
+                        const uint32_t read_end = size32 - rb[c];
+                        if (issued - done == kWinAhead) retire();
+                        ring[issued++ % kWinAhead] = Pending{sq, len, read_end, flip};
+                        if (read_end > 0 && read_end <= len) {
+                            const uint32_t hi = read_end - 1u, lo = read_end >= 16u ? read_end - 16u : 0u;
+                            const uint32_t j0 = flip ? len - 1u - hi : lo, j1 = flip ? len - 1u - lo : hi;
+                            __builtin_prefetch(sq + (j0 >> 1), 0, PTL_PF_HINT);
+                            __builtin_prefetch(sq + (j1 >> 1), 0, PTL_PF_HINT);
                         }
-                        if (open) touch();
                     }
-                    auto close = [&]() {
-                        const uint32_t read_end = blk_read + ins;
-                        uint64_t bits = 0;
-                        for (uint32_t q = 0; q < 16 && q < read_end; ++q) {
-                            const uint32_t idx = read_end - 1u - q;
-                            if (idx >= len) continue;  // out of bounds: the kernel reports the reference's panic before reading
-                            const uint32_t j = flip ? len - 1u - idx : idx;
-                            const uint32_t nib = (j & 1u) ? (sq[j >> 1] & 0xfu) : (sq[j >> 1] >> 4);
-                            bits |= uint64_t(nib) << (4u * q);
-                        }
-                        *w++ = bits;
-                        in_indel = false;
-                        ins = 0;
-                    };
-                    for (uint32_t t = g.cig_len; t-- > 0;) {
-                        const uint32_t x = c[t], op = op_of(x), l = len_of(x);
-                        if (op == OP_I || op == OP_D) {
-                            if (l > 0) {
-                                if (!in_indel) { in_indel = true; blk_read = read_head; }
-                                if (op == OP_I) ins += l;
-                            }
-                        } else if (in_indel) {
-                            close();
-                        }
-                        read_head += uint32_t(read_adv(x));
-                    }
-                    if (in_indel) close();
                 }
             }
+            while (done < issued) retire();
             v.indel_win = win;
             v.rseg_win_begin = wb;
             v.n_indel_win = n_win;
@@ -430,7 +492,7 @@ static int pack_impl(const ptl_read_records* recs, uint32_t first, uint32_t coun
         v.n_cigar = n_cig;
         v.seq4 = recs->seq4 + seq_lo;  // borrowed
         v.seq4_bytes = seq_hi - seq_lo;
-        pb->record_index = std::move(kept);
+        pb->record_index.assign(kept.begin(), kept.end());
         pb->n_skipped_supplementary = skipped;
         return PTL_OK;
     } catch (const InputError& e) {

@@ -255,3 +255,96 @@ def test_repacking_a_batch_reuses_its_arena_and_equals_a_fresh_pack():
     [t.join() for t in th]
     for t in range(4):  # the last chunk each thread packed: 8 + t
         assert _same(_batch_arrays(bufs[t].c), _batch_arrays(lib.PackedBatch(L, s.read_records, (8 + t) * 250, 250, s.contig_names, windows=segs).c))
+
+
+def _records(rows, pool_pad=0):
+    """ptl_read_records from (flag, pos, tid, cigar, seq_len, sa) rows; bases are a fixed pseudo-random nibble stream."""
+    n = len(rows)
+    cig = [abi.cigar_from_string(r[3]).astype(np.uint32) for r in rows]
+    cb = np.zeros(n + 1, np.uint64)
+    cb[1:] = np.cumsum([len(c) for c in cig])
+    seq_len = np.array([r[4] for r in rows], np.uint32)
+    seq_off = np.zeros(n, np.uint64)
+    seq_off[1:] = np.cumsum((seq_len[:-1].astype(np.uint64) + 1) // 2)
+    nbytes = int(seq_off[-1] + (int(seq_len[-1]) + 1) // 2) + pool_pad
+    rng = np.random.default_rng(5)
+    seq4 = (rng.integers(1, 9, nbytes, dtype=np.uint8) << 4 | rng.integers(1, 9, nbytes, dtype=np.uint8)).astype(np.uint8)
+    keep = dict(tid=np.array([r[2] for r in rows], np.int32), pos=np.array([r[1] for r in rows], np.int64), flag=np.array([r[0] for r in rows], np.uint16),
+                mapq=np.full(n, 60, np.uint8), bin=np.zeros(n, np.uint16), seq_len=seq_len, seq_off=seq_off, seq4=seq4, cb=cb,
+                cigar=np.concatenate(cig), sa=(C.c_char_p * n)(*[r[5].encode() if r[5] else None for r in rows]))
+    p = lambda a, t: a.ctypes.data_as(t)
+    rc = lib.ReadRecordsC(n, p(keep["tid"], lib.i32p), p(keep["pos"], lib.i64p), p(keep["flag"], lib.u16p), p(keep["mapq"], lib.u8p), p(keep["bin"], lib.u16p),
+                          p(seq_len, lib.u32p), p(seq_off, lib.u64p), p(seq4, lib.u8p), nbytes, p(cb, lib.u64p), p(keep["cigar"], lib.u32p), keep["sa"])
+    rc._keep = keep
+    return rc
+
+
+def _walk_windows(ops, nib, seq_len, flip):
+    """The definition (read_alignment_scanner.rs:153-167 + cigar_indel_shifter.rs:63-85): clusters of the REVERSED CIGAR; the
+    window holds read_view[read_end - 1 - q], q = 0..15, read_view flipped for a need_flipped_read_alignment pair."""
+    out, read_head, blk, ins, open_ = [], 0, 0, 0, False
+
+    def close():
+        read_end, bits = (blk + ins) & 0xffffffff, 0
+        for q in range(min(16, read_end)):
+            idx = read_end - 1 - q
+            if idx < seq_len:
+                bits |= int(nib[seq_len - 1 - idx if flip else idx]) << (4 * q)
+        out.append(bits)
+
+    for x in reversed([int(v) for v in ops]):
+        op, l = x & 15, x >> 4
+        if op in (1, 2):
+            if l > 0:
+                if not open_:
+                    open_, blk = True, read_head
+                if op == 1:
+                    ins += l
+        elif open_:
+            close()
+            open_, ins = False, 0
+        if op in (0, 1, 4, 5, 7, 8):
+            read_head += l
+    if open_:
+        close()
+    return out
+
+
+def test_indel_windows_equal_the_reversed_cigar_walk():
+    """ptl_pack_batch_ex windows against the definition, walked in Python: both strands of the pair (primary segments are
+    always flipped views, opposite-strand SA segments are not), clusters closer than 16 bases to either read end, leading and
+    trailing clips, empty ops inside and between clusters, a CIGAR longer than the stored bases, and the last read of the pool
+    (the two-load fast path must not read past it)."""
+    rows = [
+        (0, 100, 0, "20=1I30=2D10=1I1D5=", 67, None),
+        (16, 100, 0, "20=1I30=2D10=1I1D5=", 67, None),
+        (0, 50, 1, "3=1I50=", 54, None),                      # cluster 4 bases into the read
+        (0, 50, 1, "50=2I3=", 55, None),                      # ... and 3 bases before its end
+        (0, 70, 0, "5S10=2I40=3D7=3S", 67, None),
+        (16, 70, 0, "4H6S10=2I40=3D7=3S", 72, None),
+        (0, 10, 1, "10=0I1I0D20=0M1D5=0D0I", 36, None),       # empty ops: inside a cluster, closing one, and a cluster of only empty ops
+        (0, 10, 1, "30=1I30=1D30=", 40, None),                # CIGAR says 91 bases, the record holds 40
+        (0, 500, 0, "20=1I19=20S", 60, "ctg1,100,-,20S30=1I9=,60,0;"),   # SA segment on the other strand: not flipped
+        (16, 500, 0, "20=1D20=20S", 60, "ctg1,100,-,40S3=1I16=,60,0;ctg0,900,+,1I39=20S,33,1;"),
+        (0, 20, 0, "1I16=1D17=", 34, None),                   # last read: windows end exactly at the last byte of the pool
+    ]
+    for pad in (0, 16):
+        rc = _records(rows, pool_pad=pad)
+        pb = lib.PackedBatch(lib.load(), rc, 0, len(rows), ["ctg0", "ctg1"], windows=True)
+        b = pb.c
+        assert b.n_reads == len(rows) and b.n_read_segments == len(rows) + 3
+        pool = np.ctypeslib.as_array(b.cigar, (int(b.n_cigar),))
+        win = np.ctypeslib.as_array(b.indel_win, (int(b.n_indel_win),))
+        seq4 = rc._keep["seq4"]
+        n_checked = 0
+        for i in range(b.n_reads):
+            raw = seq4[int(rc._keep["seq_off"][i]):]
+            nib = np.stack([raw >> 4, raw & 15], 1).reshape(-1)
+            for k in range(b.read_seg_begin[i], b.read_seg_begin[i + 1]):
+                ops = pool[int(b.rseg_cigar_begin[k]): int(b.rseg_cigar_begin[k]) + int(b.rseg_cigar_len[k])]
+                flip = not (bool(rows[i][0] & 16) == bool(b.rseg_is_fwd[k]))
+                want = _walk_windows(ops, nib, rows[i][4], flip)
+                got = [int(v) for v in win[b.rseg_win_begin[k]: b.rseg_win_begin[k + 1]]]
+                assert got == want, (i, k, [hex(v) for v in got], [hex(v) for v in want])
+                n_checked += len(want)
+        assert n_checked == b.n_indel_win and n_checked >= 22
