@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--reads", type=int, default=0, help="override the size of the read set (default: the workload's own)")
     ap.add_argument("--chunk", type=int, default=131072, help="reads per submitted batch in the e2e pipeline")
     ap.add_argument("--slots", type=int, default=3, help="batch slots (CUDA streams) of the e2e pipeline")
+    ap.add_argument("--value-slots", type=int, default=0, help="resident sub-batches of the `value` step (0 = by shard size)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-assemble", action="store_true", help="skip the record-assembly measurements")
@@ -238,6 +239,13 @@ def run_reference(args, rank, world):
 
 
 # ------------------------------------------------------------------------------------------------ the native arm
+def value_slots_for(n_reads: int) -> int:
+    """Resident sub-batches of the `value` step.  Three at every shard size: measured on rank-sized shards of the whole-genome
+    set (tools/value_slots_sweep.sh), 0.75 M reads take 0.790 / 0.768 / 0.736 ms as 1 / 2 / 3 sub-batches and 1.5 M reads
+    1.332 / 1.292 / 1.244 ms -- the streams fill each other's kernel tails even when each launch is small."""
+    return 3 if n_reads >= 3 else 1
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -317,7 +325,8 @@ def main():
     t0 = time.time()
     # value: the shard as V resident sub-batches, one per slot, lifted CONCURRENTLY on the slots' streams (every kernel of the
     # path is latency-bound, not throughput-bound: a second and third stream fill the tails; +6 % over one resident batch)
-    V = max(1, min(max(args.slots, 2), 3, n_reads))
+    V = args.value_slots or value_slots_for(n_reads)
+    V = max(1, min(V, max(args.slots, 2), n_reads))
     vb = [(k * (n_reads // V), (n_reads // V) if k < V - 1 else n_reads - (V - 1) * (n_reads // V)) for k in range(V)]
     value_parts = [lib.PackedBatch(L, s.read_records, a, c, s.contig_names, pinned=True, windows=segs) for a, c in vb]
     chunk_sets = {
