@@ -272,8 +272,9 @@ int ptl_assemble_bases(ptl_ctx* ctx, int slot, const ptl_read_quals* quals, uint
  *   reverse_alignment_seq_and_qual when the record was flipped (:125-133, as ptl_assemble_bases);
  *   push_aux SA:Z = "{chrom},{pos+1},{+|-},{CIGAR},{mapq},0;" of every OTHER record of the read, in order (:292-301,349-363);
  *   the unmapped fallback (:317-335): no CIGAR, tid/pos -1, MAPQ 255, original bin, no tag appended.
- * Aux order: surviving input tags, PS, ZM, SA.  A lifted CIGAR with more than 65535 ops is an error (htslib would move
- * it into a CG tag at write time; BAM encoding is out of scope).
+ * Aux order: surviving input tags, PS, ZM, SA.  A lifted CIGAR with more than 65535 ops is written the way htslib's
+ * bam_write1 writes it: n_cigar_op = 2, the CIGAR field holds <l_seq>S<ref_len>N, and the real ops follow every other
+ * tag as CG:B,I (SAM spec 4.2.2); an error only if ref_len >= 2^28 (bam_write1 refuses that record too).
  * Needs ptl_set_names once (contig names of the read->assembly header for PS, reference names for SA). */
 int ptl_set_names(ptl_ctx* ctx, uint32_t n_contigs, const char* const* contig_names, uint32_t n_chrom, const char* const* chrom_names);
 typedef struct {

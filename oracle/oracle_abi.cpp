@@ -598,7 +598,19 @@ int ptl_oracle_assemble_records(ptl_ctx* ctx, int slot, const ptl_read_extras* x
                     a.insert(a.end(), text.begin(), text.end());
                     a.push_back(0);
                 }
-                if (c1 - c0 > 65535) return fail(ctx, PTL_ERR_STATE, "a lifted CIGAR has more than 65535 ops");
+            }
+            // bam_write1 (htslib sam.c; hts-sys 2.2.0 is the reference's pin, Cargo.lock:740): a record with more than 65535
+            // CIGAR ops is written with the placeholder CIGAR <l_seq>S<ref_len>N, n_cigar_op = 2, and the real CIGAR in a
+            // CG:B,I tag behind every other tag (SAM spec 4.2.2); it refuses a reference length the N op cannot hold.
+            const bool long_cigar = lifted && c1 - c0 > 65535;
+            uint64_t cig_ref_len = 0;
+            if (long_cigar) {
+                for (uint64_t i = c0; i < c1; ++i)
+                    if ((0x18du >> (sl.cigar[i] & 0xfu)) & 1u) cig_ref_len += sl.cigar[i] >> 4;  // M D N = X (bam_cigar2rlen)
+                if (cig_ref_len >= (1ull << 28)) return fail(ctx, PTL_ERR_STATE, "a lifted CIGAR with more than 65535 ops spans 2^28 reference bases or more: bam_write1 cannot write it");
+                a.insert(a.end(), {'C', 'G', 'B', 'I'});
+                put_u32(a, uint32_t(c1 - c0));
+                for (uint64_t i = c0; i < c1; ++i) put_u32(a, sl.cigar[i]);
             }
             std::vector<uint8_t> rec;
             put_u32(rec, uint32_t(sl.rec_tid[k]));
@@ -606,7 +618,7 @@ int ptl_oracle_assemble_records(ptl_ctx* ctx, int slot, const ptl_read_extras* x
             rec.push_back(uint8_t(name_n + 1));
             rec.push_back(sl.rec_mapq[k]);
             put_u16(rec, sl.rec_bin[k]);
-            put_u16(rec, uint16_t(lifted ? c1 - c0 : 0));
+            put_u16(rec, uint16_t(long_cigar ? 2 : lifted ? c1 - c0 : 0));
             put_u16(rec, sl.rec_flag[k]);
             put_u32(rec, uint32_t(len));
             put_u32(rec, uint32_t(x->mate_tid[r]));
@@ -614,8 +626,12 @@ int ptl_oracle_assemble_records(ptl_ctx* ctx, int slot, const ptl_read_extras* x
             put_u32(rec, uint32_t(x->tlen[r]));
             rec.insert(rec.end(), name, name + name_n);
             rec.push_back(0);
-            if (lifted)
+            if (long_cigar) {
+                put_u32(rec, (uint32_t(len) << 4) | 4u);
+                put_u32(rec, (uint32_t(cig_ref_len) << 4) | 3u);
+            } else if (lifted) {
                 for (uint64_t i = c0; i < c1; ++i) put_u32(rec, sl.cigar[i]);
+            }
             if (!sl.rec_need_flip[k]) {
                 rec.insert(rec.end(), seq4, seq4 + ((len + 1) >> 1));
                 rec.insert(rec.end(), q, q + len);

@@ -988,7 +988,7 @@ static int assemble_impl(ptl_ctx* ctx, int slot, const ptl_read_extras* x, uint3
         const unsigned err = *sl->hb_err.as<unsigned int>();
         if (err & 16u) throw std::runtime_error("ptl_read_extras: a name / aux / quality offset is not monotonic or lies outside its pool");
         if (err & 1u) throw std::runtime_error("ptl_set_names: a contig or reference chromosome of this batch has no name");
-        if (err & 2u) throw std::runtime_error("a lifted CIGAR has more than 65535 ops (BAM needs a CG tag for it: out of scope)");
+        if (err & 2u) throw std::runtime_error("a lifted CIGAR with more than 65535 ops spans 2^28 reference bases or more: BAM cannot hold it (bam_write1 refuses it too)");
         if (err & 4u) throw std::runtime_error("a contig name longer than 248 bytes or more than 16 MB of SA text in one record");
         if (err & 8u) throw std::runtime_error("a read name longer than 254 bytes (BAM l_read_name is a u8)");
         const uint64_t total = sl->hb_rec_begin.as<uint64_t>()[n_rec];

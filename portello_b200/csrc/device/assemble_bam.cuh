@@ -71,7 +71,7 @@ struct BamAsmArgs {
     uint4* rec_desc;         // [n_records][2] BamRecLayout of the record, computed once by bam_rec_size (the writer's prologue
                              //                is then two dependent loads deep instead of five)
     uint8_t* out;
-    unsigned int* error;     // bit 0: a name is missing, 1: a CIGAR has more than 65535 ops, 2: descriptor field overflow, 3: qname > 254 bytes,
+    unsigned int* error;     // bit 0: a name is missing, 1: a CIGAR of more than 65535 ops spans >= 2^28 reference bases, 2: descriptor field overflow, 3: qname > 254 bytes,
                              // bit 4: an offset of the extras (names / aux / qualities) lies outside its pool
 };
 
@@ -201,6 +201,14 @@ __device__ __forceinline__ uint32_t sa_entry(const BamAsmArgs& A, uint32_t k, ui
     return n;
 }
 
+// bam_cigar2rlen: reference bases of M, D, N, = and X ops
+__device__ __forceinline__ uint64_t cigar_ref_len(const uint32_t* c, uint64_t n) {
+    uint64_t len = 0;
+    for (uint64_t i = 0; i < n; ++i)
+        if ((0x18du >> (c[i] & 0xfu)) & 1u) len += c[i] >> 4;
+    return len;
+}
+
 __device__ __forceinline__ void bam_rec_prep_body(const BamAsmArgs& A, uint32_t k) {
     uint32_t n = 0;
     if (A.rec_status[k] == 1) {
@@ -208,16 +216,30 @@ __device__ __forceinline__ void bam_rec_prep_body(const BamAsmArgs& A, uint32_t 
         const uint32_t ctg = A.rseg_contig[A.rec_read_segment[k]];
         if (tid < 0 || uint32_t(tid) >= A.n_chrom_names || ctg >= A.n_contig_names) atomicOr(A.error, 1u);
         else n = sa_entry(A, k, nullptr);
-        if (A.rec_cigar_begin[k + 1] - A.rec_cigar_begin[k] > 65535ull) atomicOr(A.error, 2u);
+        // more than 65535 ops: the record carries a placeholder CIGAR and a CG:B,I tag (BamRecLayout); bam_write1 refuses it
+        // only when the placeholder's N op cannot hold the reference length
+        const uint64_t c0 = A.rec_cigar_begin[k], c1 = A.rec_cigar_begin[k + 1];
+        if (c1 - c0 > 65535ull && cigar_ref_len(A.cigar + c0, c1 - c0) >= (1ull << 28)) atomicOr(A.error, 2u);
     }
     A.rec_sa_len[k] = n;
 }
 
+// A CIGAR of more than 65535 ops does not fit n_cigar_op: as bam_write1 (htslib sam.c) does, the CIGAR field then holds the
+// two-op placeholder <l_seq>S<ref_len>N and the real ops follow every other tag as CG:B,I (SAM spec 4.2.2).
 struct BamRecLayout {
     uint32_t r, k0, k1;
     uint32_t name_n, n_cigar, l_seq, seq_bytes, keep_n, ps_n, sa_n;  // ps_n / sa_n: payload bytes without tag, type and NUL
     bool lifted;
     uint64_t total;  // block_size + 4
+    __device__ __forceinline__ bool long_cigar() const { return n_cigar > 65535u; }
+    __device__ __forceinline__ uint64_t cigar_field() const { return long_cigar() ? 8ull : 4ull * n_cigar; }          // bytes of the CIGAR field
+    __device__ __forceinline__ uint64_t cg_tail() const { return long_cigar() ? 8ull + 4ull * n_cigar : 0ull; }       // "CGBI" + count + ops
+    __device__ __forceinline__ uint64_t o_seq() const { return 36ull + name_n + 1ull + cigar_field(); }
+    __device__ __forceinline__ uint64_t size() const {
+        uint64_t t = 4 + 32 + uint64_t(name_n) + 1 + cigar_field() + seq_bytes + l_seq + keep_n + cg_tail();
+        if (lifted) t += 3ull + ps_n + 1 + 4 + (sa_n ? 3ull + sa_n + 1 : 0ull);
+        return t;
+    }
     __device__ __forceinline__ void pack(uint4* d) const {
         d[0] = make_uint4(r, k0, k1 - k0, name_n | (lifted ? 0x80000000u : 0u));
         d[1] = make_uint4(n_cigar, l_seq, keep_n, ps_n | (sa_n << 8));
@@ -229,9 +251,7 @@ struct BamRecLayout {
         L.name_n = a.w & 0x7fffffffu; L.lifted = (a.w >> 31) != 0;
         L.n_cigar = b.x; L.l_seq = b.y; L.seq_bytes = (b.y + 1u) >> 1; L.keep_n = b.z;
         L.ps_n = b.w & 0xffu; L.sa_n = b.w >> 8;
-        uint64_t t = 4 + 32 + uint64_t(L.name_n) + 1 + 4ull * L.n_cigar + L.seq_bytes + L.l_seq + L.keep_n;
-        if (L.lifted) t += 3ull + L.ps_n + 1 + 4 + (L.sa_n ? 3ull + L.sa_n + 1 : 0ull);
-        L.total = t;
+        L.total = L.size();
         return L;
     }
 };
@@ -265,9 +285,7 @@ __device__ __forceinline__ BamRecLayout bam_rec_layout(const BamAsmArgs& A, uint
         for (uint32_t j = L.k0; j < L.k1; ++j)
             if (j != k) L.sa_n += A.rec_sa_len[j];
     }
-    uint64_t t = 4 + 32 + uint64_t(L.name_n) + 1 + 4ull * L.n_cigar + L.seq_bytes + L.l_seq + L.keep_n;
-    if (L.lifted) t += 3ull + L.ps_n + 1 + 4 + (L.sa_n ? 3ull + L.sa_n + 1 : 0ull);
-    L.total = t;
+    L.total = L.size();
     return L;
 }
 
@@ -394,21 +412,28 @@ __device__ __forceinline__ void bam_write_meta_body(const BamAsmArgs& A, uint32_
     uint8_t* out = A.out + A.rec_begin[k];
     const uint32_t r = L.r;
     // ---- field offsets
-    const uint64_t o_name = 36, o_cigar = o_name + L.name_n + 1, o_seq = o_cigar + 4ull * L.n_cigar, o_qual = o_seq + L.seq_bytes,
-                   o_aux = o_qual + L.l_seq, o_ps = o_aux + L.keep_n;
+    const uint64_t o_name = 36, o_cigar = o_name + L.name_n + 1, o_seq = L.o_seq(), o_qual = o_seq + L.seq_bytes,
+                   o_aux = o_qual + L.l_seq, o_ps = o_aux + L.keep_n, o_cg = L.total - L.cg_tail();
+    const bool long_cigar = L.long_cigar();
     // ---- block_size + core (36 bytes) and the NUL of the name: one thread, byte stores (unaligned destination)
     if (tid == 0) {
         const uint32_t h[9] = {uint32_t(L.total - 4),
                                uint32_t(A.rec_tid[k]),
                                uint32_t(int32_t(A.rec_pos[k])),
                                ((L.name_n + 1u) & 0xffu) | (uint32_t(A.rec_mapq[k]) << 8) | (uint32_t(A.rec_bin[k]) << 16),
-                               L.n_cigar | (uint32_t(A.rec_flag[k]) << 16),
+                               (long_cigar ? 2u : L.n_cigar) | (uint32_t(A.rec_flag[k]) << 16),
                                L.l_seq,
                                uint32_t(A.mate_tid[r]),
                                uint32_t(A.mate_pos[r]),
                                uint32_t(A.tlen[r])};
         for (int i = 0; i < 36; ++i) out[i] = uint8_t(h[i >> 2] >> (8 * (i & 3)));
         out[o_name + L.name_n] = 0;
+        if (long_cigar) {  // placeholder CIGAR, and the head of the CG tag
+            const uint32_t ref_len = uint32_t(cigar_ref_len(A.cigar + A.rec_cigar_begin[k], L.n_cigar));  // < 2^28 (bam_rec_prep_body)
+            const uint32_t w[4] = {(L.l_seq << 4) | 4u, (ref_len << 4) | 3u, 0x49424743u /* "CGBI" */, L.n_cigar};
+            for (int i = 0; i < 8; ++i) out[o_cigar + i] = uint8_t(w[i >> 2] >> (8 * (i & 3)));
+            for (int i = 0; i < 8; ++i) out[o_cg + i] = uint8_t(w[2 + (i >> 2)] >> (8 * (i & 3)));
+        }
     }
     // ---- PS:Z, ZM:C (:255-269) and SA:Z (:349-363): short text, one thread each
     if (L.lifted && tid == 1 % n_threads) {
@@ -446,7 +471,7 @@ __device__ __forceinline__ void bam_write_meta_body(const BamAsmArgs& A, uint32_
         for (uint32_t i = tid; i < n; i += n_threads) d[i] = src[i];
     };
     copy_small(out + o_name, A.names + A.name_off[r], L.name_n);
-    copy_small(out + o_cigar, reinterpret_cast<const uint8_t*>(A.cigar + A.rec_cigar_begin[k]), 4u * L.n_cigar);
+    copy_small(out + (long_cigar ? o_cg + 8 : o_cigar), reinterpret_cast<const uint8_t*>(A.cigar + A.rec_cigar_begin[k]), 4u * L.n_cigar);
     {
         const uint32_t* keep = A.read_keep + size_t(r) * 10;
         const uint8_t* aux = A.aux + A.aux_off[r];
@@ -466,7 +491,7 @@ __device__ __forceinline__ void bam_write_bases_body(const BamAsmArgs& A, uint32
     uint8_t* out = A.out + A.rec_begin[k];
     const uint32_t r = L.r;
     const bool flip = A.rec_need_flip[k] != 0;
-    const uint64_t o_seq = 36ull + L.name_n + 1 + 4ull * L.n_cigar, o_qual = o_seq + L.seq_bytes;
+    const uint64_t o_seq = L.o_seq(), o_qual = o_seq + L.seq_bytes;
     const uint8_t* src_s = A.seq4 + A.read_seq_off[r];
     const uint8_t* src_q = A.qual + A.qual_off[r];
     if (!flip) {

@@ -260,7 +260,7 @@ static __device__ __noinline__ void frame_build_runs(const FrameArgs& F, uint64_
             if (rb < r1) {
                 started = true;
                 const BamRecLayout L = BamRecLayout::unpack(A.rec_desc + 2 * size_t(k));
-                const uint64_t o_seq = 36ull + L.name_n + 1 + 4ull * L.n_cigar, o_qual = o_seq + L.seq_bytes, o_aux = o_qual + L.l_seq;
+                const uint64_t o_seq = L.o_seq(), o_qual = o_seq + L.seq_bytes, o_aux = o_qual + L.l_seq;
                 const bool flip = A.rec_need_flip[k] != 0;
                 const uint8_t* src_s = A.seq4 + A.read_seq_off[L.r];
                 const uint8_t* src_q = A.qual + A.qual_off[L.r];

@@ -312,26 +312,67 @@ def _long_cigar_case():
     return segs, batch, x
 
 
-def _check_long_cigar_rejected(ctx):
+def _check_long_cigar_goes_to_cg_tag(ctx, octx=None):
+    """bam_write1 (htslib sam.c): n_cigar_op = 2, CIGAR field <l_seq>S<ref_len>N, the real ops in CG:B,I behind every other tag."""
     segs, batch, x = _long_cigar_case()
-    ctx.set_reference([np.frombuffer(b"A" * 40_000, np.uint8).copy()])
-    ctx.set_contig_segments(segs)
-    res = ctx.lift(batch)
-    assert res.n_records == 1 and res.rec_status[0] == 1 and int(res.rec_cigar_begin[1]) == 70_000
-    ctx.set_names(["ctg"], ["chr1"])
-    with pytest.raises(abi.PtlError, match="65535"):
-        ctx.assemble_records(x)
+    want = None
+    for c in (ctx, octx):
+        if c is None:
+            continue
+        c.set_reference([np.frombuffer(b"A" * 40_000, np.uint8).copy()])
+        c.set_contig_segments(segs)
+        res = c.lift(batch)
+        assert res.n_records == 1 and res.rec_status[0] == 1 and int(res.rec_cigar_begin[1]) == 70_000
+        c.set_names(["ctg"], ["chr1"])
+        _, (rb, by) = c.assemble_records(x)
+        rec = bytes(by[int(rb[0]):int(rb[1])])
+        if want is not None:
+            assert rec == want
+        want = rec
+    ops = np.asarray(res.cigar[:70_000], np.uint32)
+    block_size, tid, pos, l_name, mapq, bin_, n_cig, flag, l_seq = struct.unpack_from("<iiiBBHHHi", rec, 0)
+    assert block_size == len(rec) - 4 and n_cig == 2 and l_seq == 70_000 and l_name == 3
+    o = 36 + l_name
+    fake = struct.unpack_from("<2I", rec, o)
+    ref_len = int(sum(int(c) >> 4 for c in ops if (int(c) & 15) in (0, 2, 3, 7, 8)))
+    assert fake == ((l_seq << 4) | 4, (ref_len << 4) | 3)
+    o += 8 + (l_seq + 1) // 2 + l_seq
+    aux = rec[o:]
+    fields = aux_fields(aux)
+    assert [t for t, _, _ in fields] == [b"PS", b"ZM", b"CG"]          # CG is the LAST tag
+    cg = aux[-(8 + 4 * 70_000):]
+    assert cg[:4] == b"CGBI" and struct.unpack_from("<I", cg, 4)[0] == 70_000
+    assert np.array_equal(np.frombuffer(cg[8:], np.uint32), ops)
+    return rec
 
 
-def test_oracle_rejects_cigars_beyond_u16():
+def test_oracle_and_emulation_write_long_cigars_as_cg_tag():
+    import emul_lib
     import oracle_lib
-    _check_long_cigar_rejected(abi.Context(oracle_lib.load(), 0, 1))
+    _check_long_cigar_goes_to_cg_tag(abi.Context(emul_lib.load(), 0, 1), abi.Context(oracle_lib.load(), 0, 1))
 
 
 @pytest.mark.gpu
-def test_gpu_rejects_cigars_beyond_u16():
-    from portello_b200 import lib
-    _check_long_cigar_rejected(lib.GpuContext(0, 1))
+def test_gpu_writes_long_cigars_as_cg_tag(tmp_path):
+    """... and the record, framed by the device (both the two-pass and the fused writer), is restored by the BAM reader."""
+    import oracle_lib
+    from portello_b200 import bamio, lib
+    gctx = lib.GpuContext(0, 1)
+    rec = _check_long_cigar_goes_to_cg_tag(gctx, abi.Context(oracle_lib.load(), 0, 1))
+    segs, batch, x = _long_cigar_case()
+    header = helpers.bam_header_bytes("@HD\tVN:1.6\n", ["chr1"], [40_000])
+    for fused in (False, True):
+        gctx.lift(batch)
+        if fused:
+            _, stream = gctx.frame_records(x, header, flags=abi.BGZF_EOF)
+        else:
+            gctx.assemble_records(x)
+            _, stream = gctx.bgzf_store_records(header, flags=abi.BGZF_EOF)
+        path = tmp_path / f"long_{int(fused)}.bam"
+        path.write_bytes(stream)
+        d = bamio.BamFile(str(path)).fetch(bamio.FETCH_ALL)
+        assert d.c.n_records == 1 and int(d.c.cigar_begin[1]) == 70_000
+        assert np.array_equal(np.ctypeslib.as_array(d.c.cigar, (70_000,)), np.frombuffer(rec[-4 * 70_000:], np.uint32))
 
 
 @pytest.mark.parametrize("case", ["iupac-odd", "tiny"])
