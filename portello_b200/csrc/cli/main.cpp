@@ -17,6 +17,7 @@
 
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -47,6 +48,15 @@ void log_line(const char* level, const std::string& msg) {
     std::fprintf(stderr, "%s[%s][%s] %s\n", ts, kName, level, msg.c_str());
 }
 void info(const std::string& m) { log_line("INFO", m); }
+// PORTELLO_B200_TIMING=1: phase boundaries with the elapsed time, at DEBUG level (not part of the reference's log)
+const std::chrono::steady_clock::time_point g_t0 = std::chrono::steady_clock::now();
+void phase(const char* what) {
+    static const bool on = std::getenv("PORTELLO_B200_TIMING") != nullptr;
+    if (!on) return;
+    char b[160];
+    std::snprintf(b, sizeof b, "%s at +%.3f s", what, std::chrono::duration<double>(std::chrono::steady_clock::now() - g_t0).count());
+    log_line("DEBUG", b);
+}
 void error(const std::string& m) { log_line("ERROR", m); }
 [[noreturn]] void panic(const std::string& m) {
     std::fprintf(stderr, "%s: fatal: %s\n", kName, m.c_str());
@@ -214,10 +224,20 @@ int main(int argc, char** argv) {
     for (const auto& n : ref_names) ref_name_p.push_back(n.c_str());
     for (const auto& n : contig_names) contig_name_p.push_back(n.c_str());
 
+    // Worker threads decode, pack, compress and write (the host-bound stages: one per --threads, as the reference's rayon
+    // pool); the GPU part of a batch borrows one of a few batch slots, which are busy for milliseconds at a time.
+    const int n_workers = std::max(1, st.threads);
+    const int n_slots = std::min(n_workers, 4);
+    // (the CUDA context takes seconds to come up on a cold driver: it does so behind the reference and contig file reads)
+    ptl_ctx* ctx = nullptr;
+    int rc_create = PTL_OK;
+    std::thread ctx_thread([&]() { rc_create = ptl_create(st.gpu, n_slots, &ctx); });
+
     // get_chrom_array (main.rs:24-62)
     info("Reading reference genome from file '" + st.ref + "'");
     ptl_fasta* fasta = nullptr;
     if (ptl_fasta_load(st.ref.c_str(), st.threads, &fasta) != PTL_OK) panic(ptl_bam_last_error());
+    phase("reference loaded");
     std::unordered_map<std::string, uint32_t> fasta_index;
     for (uint32_t i = 0; i < ptl_fasta_n(fasta); ++i) fasta_index.emplace(ptl_fasta_name(fasta, i), i);
     std::vector<const uint8_t*> chrom_seq;
@@ -241,6 +261,7 @@ int main(int argc, char** argv) {
     }
     if (consistency_error) {
         error("Exiting due to one or more reference consistency issues");
+        ctx_thread.join();
         return EX_DATAERR_;
     }
 
@@ -249,24 +270,26 @@ int main(int argc, char** argv) {
     ptl_contig_scan* scan = nullptr;
     if (ptl_scan_contig_bam(contig_bam, uint32_t(contig_names.size()), contig_name_p.data(), contig_len.data(), st.threads, &scan) != PTL_OK)
         panic(ptl_bam_last_error());
+    phase("contig alignment file scanned");
     ptl_contig_records crecs{};
     ptl_contig_scan_view(scan, &crecs);
-    const int n_workers = std::max(1, std::min(st.threads, 8));
-    ptl_ctx* ctx = nullptr;
-    const int rc_create = ptl_create(st.gpu, n_workers, &ctx);
+    ctx_thread.join();
     if (rc_create == PTL_ERR_NO_DEVICE) panic("no usable sm_100 CUDA device: the liftover path has no CPU fallback");
     if (rc_create != PTL_OK) panic("ptl_create failed");
+    phase("device context created");
     if (ptl_set_reference(ctx, uint32_t(ref_names.size()), ref_len.data(), chrom_seq.data()) != PTL_OK) panic(ptl_last_error(ctx));
+    phase("reference on the device");
     info("Clipping repeated contig matches at split alignment segment boundaries");
     info("Joining colinear split alignment segments in each assembly contig");
     if (ptl_set_contig_records(ctx, &crecs) != PTL_OK) panic(ptl_last_error(ctx));
     if (ptl_set_names(ctx, uint32_t(contig_names.size()), contig_name_p.data(), uint32_t(ref_names.size()), ref_name_p.data()) != PTL_OK) panic(ptl_last_error(ctx));
+    phase("contig segments and tables built");
     ptl_contig_scan_free(scan);
     ptl_fasta_free(fasta);  // (the reference bases live on the device now)
 
     // ---- phase B: scan_and_remap_reads (read_alignment_scanner.rs:566-661)
     info("Processing read-to-contig alignment file '" + st.read_to_assembly + "'");
-    const int writer_threads = std::max(1, st.threads / 2);
+    const int writer_threads = std::max(1, st.threads / 2);  // (the unmapped pass-through: one big block of records)
     Writer remapped, unassembled;
     remapped.to_stdout = st.remapped_out == "-";
     remapped.fp = remapped.to_stdout ? stdout : std::fopen(st.remapped_out.c_str(), "wb");
@@ -278,17 +301,41 @@ int main(int argc, char** argv) {
         const std::vector<uint8_t> h1 = output_header(ref_names, ref_len, cmdline, 6);
         unassembled.write(h1.data(), h1.size());
     }
+    // Work units: (contig x window), records assigned by their start (:403-406, :495-535).  The reference's window is 20 Mb;
+    // an assembly too small to give every worker a few of those is cut finer (any partition by start position yields the
+    // same records; the output is unsorted either way).
+    uint64_t total_len = 0;
+    for (uint64_t l : contig_len) total_len += l;
+    const uint64_t window = std::min<uint64_t>(20000000ull, std::max<uint64_t>(1000000ull, total_len / (4ull * uint64_t(n_workers)) + 1));
     struct Unit { uint32_t contig; uint64_t b, e; };
     std::vector<Unit> units;
     for (uint32_t c = 0; c < contig_len.size(); ++c) {
-        const uint32_t n = ptl_region_segment_count(contig_len[c], 20000000ull);
+        const uint32_t n = ptl_region_segment_count(contig_len[c], window);
         std::vector<uint64_t> b(n), e(n);
-        if (n) ptl_region_segments(contig_len[c], 20000000ull, b.data(), e.data());
+        if (n) ptl_region_segments(contig_len[c], window, b.data(), e.data());
         for (uint32_t k = 0; k < n; ++k) units.push_back(Unit{c, b[k], e[k]});
     }
     std::atomic<size_t> next_unit{0};
     std::atomic<uint64_t> n_reads_done{0}, n_pairs{0}, n_lifted{0};
-    auto worker = [&](int slot) {
+    struct SlotPool {
+        std::mutex mu;
+        std::condition_variable cv;
+        std::vector<int> free_slots;
+        int acquire() {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return !free_slots.empty(); });
+            const int s = free_slots.back();
+            free_slots.pop_back();
+            return s;
+        }
+        void release(int s) {
+            { std::lock_guard<std::mutex> lk(mu); free_slots.push_back(s); }
+            cv.notify_one();
+        }
+    } slots;
+    for (int k = 0; k < n_slots; ++k) slots.free_slots.push_back(k);
+    auto worker = [&]() {
+        std::vector<uint8_t> rec_copy;
         for (;;) {
             const size_t u = next_unit.fetch_add(1);
             if (u >= units.size()) return;
@@ -308,6 +355,7 @@ int main(int argc, char** argv) {
                 ptl_batch batch{};
                 ptl_packed_batch_view(pk, &batch);
                 ptl_result res{};
+                const int slot = slots.acquire();
                 if (ptl_lift_submit(ctx, slot, &batch) != PTL_OK) panic(ptl_last_error(ctx));
                 const int rc = ptl_lift_wait(ctx, slot, &res);
                 if (rc == PTL_ERR_LIFT_PANIC)
@@ -322,18 +370,27 @@ int main(int argc, char** argv) {
                 if (remapped.to_stdout) {  // the reference's pipe mode: uncompressed BAM, framed (and CRC'd) on the device
                     ptl_bgzf_stream z{};
                     if (ptl_bgzf_store_records(ctx, slot, nullptr, 0, 0, &z) != PTL_OK) panic(ptl_last_error(ctx));
-                    std::lock_guard<std::mutex> lk(remapped.mu);
-                    remapped.write(z.bytes, z.n_bytes);
-                    remapped.n_records += out.n_records;
+                    {
+                        std::lock_guard<std::mutex> lk(remapped.mu);
+                        remapped.write(z.bytes, z.n_bytes);
+                        remapped.n_records += out.n_records;
+                    }
+                    n_pairs += res.n_pairs;
+                    n_lifted += res.n_lifted;
+                    slots.release(slot);
                 } else {
+                    // the records leave the slot's pinned buffer before the slow part (deflate, one thread per worker)
                     const uint64_t total = out.n_records ? out.rec_begin[out.n_records] : 0;
-                    const std::vector<uint8_t> z = bgzf(out.bytes, total, 6, writer_threads, false);
+                    const uint64_t n_out = out.n_records;
+                    rec_copy.assign(out.bytes, out.bytes + total);
+                    n_pairs += res.n_pairs;
+                    n_lifted += res.n_lifted;
+                    slots.release(slot);
+                    const std::vector<uint8_t> z = bgzf(rec_copy.data(), total, 6, 1, false);
                     std::lock_guard<std::mutex> lk(remapped.mu);  // all records of a read are written together (:482-487)
                     remapped.write(z.data(), z.size());
-                    remapped.n_records += out.n_records;
+                    remapped.n_records += n_out;
                 }
-                n_pairs += res.n_pairs;
-                n_lifted += res.n_lifted;
                 n_reads_done += count;
                 ptl_packed_batch_free(pk);
             }
@@ -356,9 +413,11 @@ int main(int argc, char** argv) {
         ptl_decoded_free(dec);
     });
     std::vector<std::thread> pool;
-    for (int w = 0; w < n_workers; ++w) pool.emplace_back(worker, w);
+    for (int w = 0; w < n_workers; ++w) pool.emplace_back(worker);
     for (auto& t : pool) t.join();
+    phase("mapped reads done");
     unmapped_thread.join();
+    phase("unmapped reads done");
     {
         const std::vector<uint8_t> eof = bgzf(nullptr, 0, 6, 1, true);
         remapped.write(eof.data(), eof.size());

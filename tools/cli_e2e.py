@@ -34,5 +34,8 @@ for mode in ("file", "stdout"):
         raise SystemExit(1)
     out["runs"][mode] = {"wall_s": round(dt, 2), "reads_per_s": round(n / dt), "output_bam_bytes": os.path.getsize(o),
                          "summary": [l for l in r.stderr.decode().splitlines() if "Lifted" in l][-1].split("] ", 1)[-1]}
+    if os.environ.get("CLI_E2E_LOG"):
+        print(f"--- {mode} log", file=sys.stderr)
+        print(r.stderr.decode(), file=sys.stderr)
 subprocess.run(["rm", "-rf", d])
 print(json.dumps(out))
