@@ -357,7 +357,9 @@ int ptl_set_long_pair_ops(ptl_ctx* ctx, uint32_t n_ops);
 
 
 /* Pinned (page-locked, device-mapped) host memory for batches: replaces nothing in the reference, it is the
- * "pinned structure-of-arrays batches" of the north star. */
+ * "pinned structure-of-arrays batches" of the north star.  The size is rounded up to whole 256-byte granules: the
+ * kernels fetch aligned 4 / 8 / 16-byte words around the bytes they need, so a pool they read in place (seq4 in zero-copy
+ * mode) must be readable up to the next 16-byte boundary behind its last byte -- memory from this call always is. */
 void* ptl_host_alloc(size_t bytes);
 void ptl_host_free(void* p);
 

@@ -50,7 +50,7 @@ struct DBuf {
             p = nullptr;
             cap = 0;
         }
-        const size_t want = std::max<size_t>(bytes + bytes / 8, 256);
+        const size_t want = (std::max<size_t>(bytes + bytes / 8, 256) + 255) & ~size_t(255);  // (whole granules, as ptl_host_alloc)
         CK(cudaMalloc(&p, want));
         cap = want;
     }
@@ -70,7 +70,7 @@ struct HBuf {
         if (p) CK(cudaFreeHost(p));
         p = nullptr;
         cap = 0;
-        const size_t want = std::max<size_t>(bytes + bytes / 8, 256);
+        const size_t want = (std::max<size_t>(bytes + bytes / 8, 256) + 255) & ~size_t(255);
         CK(cudaHostAlloc(&p, want, cudaHostAllocPortable));
         cap = want;
     }
@@ -1101,7 +1101,9 @@ int ptl_slot_counters(ptl_ctx* ctx, int slot, uint64_t* out) {
 
 void* ptl_host_alloc(size_t bytes) {
     void* p = nullptr;
-    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) {
+    // whole 256-byte granules: the kernels fetch aligned 4 / 8 / 16-byte words around the bytes they need, and the word around
+    // the last byte of a pool must still be inside its allocation
+    if (cudaHostAlloc(&p, ((bytes ? bytes : 1) + 255) & ~size_t(255), cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) {
         cudaGetLastError();
         return nullptr;
     }
