@@ -54,6 +54,8 @@ def parse():
     ap.add_argument("--workload", default="wg")
     ap.add_argument("--reads", type=int, default=0, help="override the size of the read set (default: the workload's own)")
     ap.add_argument("--chunk", type=int, default=131072, help="reads per submitted batch in the e2e pipeline")
+    ap.add_argument("--pack-chunk", type=int, default=32768, help="reads per packed batch in e2e_with_pack (the packer threads take turns chunk by chunk: "
+                    "47 chunks of 131072 reads on 15 threads are 4 rounds for 3.1 rounds of work)")
     ap.add_argument("--slots", type=int, default=6, help="batch slots (CUDA streams) of the e2e pipeline (3 / 4 / 6 slots: 25.4 / 24.5 / 23.7 ms per step)")
     ap.add_argument("--value-slots", type=int, default=0, help="resident sub-batches of the `value` step (0 = by shard size)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="reads in the cpu_baseline sample (0 = auto)")
@@ -562,8 +564,9 @@ def main():
         import queue
         ctx.set_seq_zero_copy(True)
         n_slots = max(args.slots, 2)
-        bounds = [(a, min(args.chunk, n_reads - a)) for a in range(0, n_reads, args.chunk)]
-        ring = [lib.PackedBatch(L, s.read_records, 0, min(args.chunk, n_reads), s.contig_names, pinned=True, windows=segs) for _ in range(n_slots + n_pack + 1)]
+        pc = max(1, args.pack_chunk)
+        bounds = [(a, min(pc, n_reads - a)) for a in range(0, n_reads, pc)]
+        ring = [lib.PackedBatch(L, s.read_records, 0, min(pc, n_reads), s.contig_names, pinned=True, windows=segs) for _ in range(n_slots + n_pack + 1)]
         pack_s = [0.0] * n_pack
 
         def one_pass():
@@ -627,7 +630,7 @@ def main():
     n_pack = max(1, threads_here - 1)
     pk_dt, pk_rate_thread = measure_e2e_with_pack(n_pack)
     pk_dt_max = max_over_ranks(pk_dt)
-    e2e_with_pack = {"value": pairs_total / pk_dt_max, "unit": UNIT, "ms_per_step": pk_dt_max * 1e3, "packer_threads_per_rank": n_pack,
+    e2e_with_pack = {"value": pairs_total / pk_dt_max, "unit": UNIT, "ms_per_step": pk_dt_max * 1e3, "packer_threads_per_rank": n_pack, "reads_per_packed_batch": args.pack_chunk,
                      "packer_reads_per_s_per_thread": pk_rate_thread, "ratio_to_e2e": (pairs_total / pk_dt_max) / e2e_value,
                      "what": "as e2e, plus the host packer inside the timed region: ptl_pack_batch_into (split segments, SA parse, indel windows) on "
                              "host threads into a ring of reusable pinned batches, overlapped with the GPU; a real run decodes BAM before this, "
