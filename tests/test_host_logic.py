@@ -348,3 +348,58 @@ def test_indel_windows_equal_the_reversed_cigar_walk():
                 assert got == want, (i, k, [hex(v) for v in got], [hex(v) for v in want])
                 n_checked += len(want)
         assert n_checked == b.n_indel_win and n_checked >= 22
+
+
+def _random_cigar(rng, max_ops):
+    """Any op anywhere (clips and pads in the middle, empty ops, I/D runs), biased towards what shapes the packer's scan."""
+    n = int(rng.integers(1, max_ops + 1))
+    ops = rng.choice(np.arange(9), n, p=[0.22, 0.17, 0.17, 0.03, 0.06, 0.03, 0.04, 0.2, 0.08])
+    lens = np.where(rng.random(n) < 0.12, 0, rng.integers(1, 40, n))
+    if rng.random() < 0.5:
+        ops[0], lens[0] = 4, int(rng.integers(0, 30))
+    if rng.random() < 0.5:
+        ops[-1], lens[-1] = int(rng.choice([4, 5])), int(rng.integers(0, 30))
+    return "".join(f"{int(l)}{'MIDNSHP=X'[int(o)]}" for o, l in zip(ops, lens))
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_packer_on_random_cigars_equals_oracle_packer_and_window_walk(seed):
+    """The fused CIGAR walk of ptl_pack_batch_ex (clip positions, spans, cluster offsets in one pass) on CIGARs no aligner
+    writes: same batch as the oracle's record-loop head, same errors, and windows equal to the reversed-CIGAR walk."""
+    rng = np.random.default_rng(seed)
+    rows, n_err = [], 0
+    while len(rows) < 400:
+        cig = _random_cigar(rng, 40)
+        qlen = helpers.cigar_read_len(cig) + (int(rng.integers(-3, 4)) if rng.random() < 0.1 else 0)
+        row = (int(rng.choice([0, 16])), int(rng.integers(0, 5000)), int(rng.integers(0, 2)), cig, max(qlen, 1), None)
+        rc = _records([row])
+        try:
+            want = oracle_lib.OraclePackedBatch(rc, 0, 1, ["ctg0", "ctg1"])
+        except abi.PtlError as e:
+            with pytest.raises(abi.PtlError) as got:      # (no aligned read base between the clips)
+                lib.PackedBatch(lib.load(), rc, 0, 1, ["ctg0", "ctg1"], windows=True)
+            assert str(got.value).split(": ", 1)[-1] == str(e).split(": ", 1)[-1]
+            n_err += 1
+            continue
+        rows.append(row)
+    assert n_err > 0
+    rc = _records(rows)
+    want = oracle_lib.OraclePackedBatch(rc, 0, len(rows), ["ctg0", "ctg1"])
+    pb = lib.PackedBatch(lib.load(), rc, 0, len(rows), ["ctg0", "ctg1"], windows=True)
+    assert _same(_batch_arrays(pb.c), _batch_arrays(want.c))
+    assert _same(_batch_arrays(lib.PackedBatch(lib.load(), rc, 0, len(rows), ["ctg0", "ctg1"]).c), _batch_arrays(want.c))
+    b = pb.c
+    pool = np.ctypeslib.as_array(b.cigar, (int(b.n_cigar),))
+    win = np.ctypeslib.as_array(b.indel_win, (max(int(b.n_indel_win), 1),))
+    seq4 = rc._keep["seq4"]
+    n_win = 0
+    for i in range(b.n_reads):
+        raw = seq4[int(rc._keep["seq_off"][i]):]
+        nib = np.stack([raw >> 4, raw & 15], 1).reshape(-1)
+        for k in range(b.read_seg_begin[i], b.read_seg_begin[i + 1]):
+            ops = pool[int(b.rseg_cigar_begin[k]): int(b.rseg_cigar_begin[k]) + int(b.rseg_cigar_len[k])]
+            flip = not (bool(rows[i][0] & 16) == bool(b.rseg_is_fwd[k]))
+            exp = _walk_windows(ops, nib, rows[i][4], flip)
+            assert [int(v) for v in win[b.rseg_win_begin[k]: b.rseg_win_begin[k + 1]]] == exp, (i, rows[i])
+            n_win += len(exp)
+    assert n_win == b.n_indel_win and n_win > 1000
