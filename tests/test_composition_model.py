@@ -1,0 +1,129 @@
+"""The composition itself, pinned from its DEFINITION rather than from a restatement of the reference's algorithm
+(a4 / a6 had no vector that the builder had not derived from the same reading of the code).
+
+A lifted alignment says, for every read base, which reference base it sits on.  That is decided by the two input
+alignments alone: read base q sits on contig base c (read->contig CIGAR), contig base c sits on reference base r
+(contig->reference CIGAR), so q sits on r -- or on nothing, when c is an insertion / clip of the contig alignment.  The
+model below composes the two per-base maps with dictionaries and knows nothing about tables, blocks, pieces or sinks; the
+liftover stage of every implementation (oracle, the device code compiled for the host, the GPU) must produce a CIGAR
+that induces exactly that map, on forward- and reverse-strand contig segments (for the latter the output is the reverse
+complement of the record: base q of the record is base len-1-q of the output, contig base c is base L-1-c of the strand
+the segment's CIGAR is written on; src/read_alignment_scanner.rs:153-183).  Only the liftover stage runs (no left shift, no
+simplify: those move indels inside repeats, which changes the map without changing the alignment score)."""
+import numpy as np
+import pytest
+
+import helpers
+import oracle_lib
+from portello_b200 import abi
+
+QUERY_OPS, REF_OPS, MATCH_OPS = (0, 1, 4, 5, 7, 8), (0, 2, 3, 7, 8), (0, 7, 8)
+
+
+def aligned_pairs(ops, pos):
+    """(query index, target position) of every aligned base of a CIGAR; and the query length."""
+    q, t, out = 0, pos, []
+    for x in ops:
+        op, l = int(x) & 15, int(x) >> 4
+        if op in MATCH_OPS:
+            out += [(q + i, t + i) for i in range(l)]
+        q += l if op in QUERY_OPS else 0
+        t += l if op in REF_OPS else 0
+    return out, q
+
+
+def compose(read_ops, read_pos, c2r_ops, c2r_pos, c2r_fwd, contig_len):
+    q2c, qlen = aligned_pairs(read_ops, read_pos)
+    c2r = dict(aligned_pairs(c2r_ops, c2r_pos)[0])
+    if c2r_fwd:
+        want = [(q, c2r[c]) for q, c in q2c if c in c2r]
+    else:
+        want = sorted((qlen - 1 - q, c2r[contig_len - 1 - c]) for q, c in q2c if contig_len - 1 - c in c2r)
+    return want, qlen
+
+
+def random_ops(rng, n_blocks, lead_clip, trail_clip, match_ops=(0, 7, 8)):
+    ops = []
+    if lead_clip:
+        ops.append((int(rng.choice([4, 5])), int(rng.integers(1, 40))))
+    for b in range(n_blocks):
+        ops.append((int(rng.choice(match_ops)), int(rng.integers(1, 60))))
+        if b + 1 < n_blocks:
+            kind = rng.random()
+            if kind < 0.4:
+                ops.append((1, int(rng.integers(1, 12))))
+            elif kind < 0.8:
+                ops.append((int(rng.choice([2, 2, 2, 3])), int(rng.integers(1, 12))))
+            elif kind < 0.9:
+                ops += [(1, int(rng.integers(1, 6))), (2, int(rng.integers(1, 6)))]
+            # else: two match ops of (possibly) different kinds next to each other
+    if trail_clip:
+        ops.append((int(rng.choice([4, 5])), int(rng.integers(1, 40))))
+    return np.array([(l << 4) | o for o, l in ops], np.uint32)
+
+
+def cases(seed, n):
+    rng = np.random.default_rng(seed)
+    out = []
+    while len(out) < n:
+        c2r = random_ops(rng, int(rng.integers(1, 25)), rng.random() < 0.5, rng.random() < 0.5)
+        contig_len = sum(int(x) >> 4 for x in c2r if (int(x) & 15) in QUERY_OPS)
+        read = random_ops(rng, int(rng.integers(1, 12)), rng.random() < 0.4, rng.random() < 0.4)
+        span = sum(int(x) >> 4 for x in read if (int(x) & 15) in REF_OPS)
+        if span >= contig_len:
+            continue
+        out.append(dict(c2r=c2r, c2r_pos=int(rng.integers(0, 1000)), c2r_fwd=bool(rng.random() < 0.5), contig_len=contig_len,
+                        read=read, read_pos=int(rng.integers(0, contig_len - span + 1))))
+    return out
+
+
+def check(make_ctx, seed, n=150, long_ops=None):
+    n_lifted = n_rev = n_unaligned = 0
+    for v in cases(seed, n):
+        qlen = sum(int(x) >> 4 for x in v["read"] if (int(x) & 15) in QUERY_OPS)
+        ref_len = v["c2r_pos"] + sum(int(x) >> 4 for x in v["c2r"] if (int(x) & 15) in REF_OPS) + 10
+        rev_seq = None if v["c2r_fwd"] else b"A" * v["contig_len"]
+        segs, batch = helpers.single_pair_case(v["c2r"], v["c2r_pos"], v["c2r_fwd"], v["contig_len"], rev_seq, v["read_pos"], v["read"], [], qlen)
+        ctx = make_ctx()
+        if long_ops is not None:
+            ctx.set_long_pair_ops(long_ops)
+        ctx.set_reference([np.full(ref_len, ord("A"), np.uint8)])
+        ctx.set_contig_segments(segs)
+        res = ctx.lift(batch, stage_mask=abi.STAGE_LIFTOVER)
+        want, _ = compose(v["read"], v["read_pos"], v["c2r"], v["c2r_pos"], v["c2r_fwd"], v["contig_len"])
+        if not want:  # no read base reaches the reference: liftover returns None, nothing is lifted
+            assert res.n_lifted == 0 and not any(int(s) == 1 for s in res.rec_status), v
+            n_unaligned += 1
+            continue
+        assert res.n_records == 1 and res.rec_status[0] == 1, v
+        k0, k1 = int(res.rec_cigar_begin[0]), int(res.rec_cigar_begin[1])
+        got, got_qlen = aligned_pairs(res.cigar[k0:k1], int(res.rec_pos[0]))
+        assert got_qlen == qlen, (v, res.record_cigar(0))
+        assert got == want, (v, res.record_cigar(0), [p for p in zip(got, want) if p[0] != p[1]][:3])
+        assert int(res.rec_pos[0]) == want[0][1]            # the record starts on its first aligned base (leading deletions are dropped)
+        ops = [int(x) & 15 for x in res.cigar[k0:k1]]
+        first_m, last_m = min(i for i, o in enumerate(ops) if o == 0), max(i for i, o in enumerate(ops) if o == 0)
+        assert all(o not in (1, 2) for o in ops[:first_m] + ops[last_m + 1:]), res.record_cigar(0)   # clean edges: no I / D outside the matches (cigar/mod.rs:233-291)
+        assert all(a != b or a == 6 for a, b in zip(ops, ops[1:])) and all(int(x) >> 4 for x in res.cigar[k0:k1])  # compressed (:204-228)
+        n_lifted += 1
+        n_rev += not v["c2r_fwd"]
+    assert n_lifted > n * 0.6 and n_rev > n * 0.2
+    return n_unaligned
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13])
+def test_oracle_liftover_induces_the_composed_base_map(seed):
+    check(lambda: abi.Context(oracle_lib.load(), 0, 1), seed)
+
+
+@pytest.mark.parametrize("long_ops", [None, 0], ids=["thread-per-pair", "warp-per-pair"])
+def test_device_code_liftover_induces_the_composed_base_map(long_ops):
+    import emul_lib
+    check(lambda: abi.Context(emul_lib.load(), 0, 1), 21, n=120, long_ops=long_ops)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("long_ops", [None, 0], ids=["thread-per-pair", "warp-per-pair"])
+def test_gpu_liftover_induces_the_composed_base_map(long_ops):
+    from portello_b200 import lib
+    check(lambda: lib.GpuContext(0, 1), 31, n=150, long_ops=long_ops)
