@@ -127,3 +127,69 @@ def test_device_code_liftover_induces_the_composed_base_map(long_ops):
 def test_gpu_liftover_induces_the_composed_base_map(long_ops):
     from portello_b200 import lib
     check(lambda: lib.GpuContext(0, 1), 31, n=150, long_ops=long_ops)
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# a11 / a12 (contig preparation: record assembly, repeated-match trimming, colinear joining) from what it may and may not do
+
+def _pair_keys(ops, pos, contig_len, reverse, chrom):
+    """One 64-bit key per aligned (contig base, reference base) of a CIGAR, contig base in FORWARD contig coordinates."""
+    keys = []
+    q, t = 0, int(pos)
+    for x in ops:
+        op, l = int(x) & 15, int(x) >> 4
+        if op in MATCH_OPS and l:
+            qi = np.arange(q, q + l, dtype=np.int64)
+            c = (contig_len - 1 - qi) if reverse else qi
+            keys.append((c << 34) | ((np.arange(t, t + l, dtype=np.int64) + (int(chrom) << 28)) << 1) | int(bool(reverse)))
+        q += l if op in QUERY_OPS else 0
+        t += l if op in REF_OPS else 0
+    return (np.concatenate(keys) if keys else np.zeros(0, np.int64)), q
+
+
+@pytest.mark.parametrize("kw", [dict(seed=5), dict(seed=11, chrom_len=3_000_000, contigs_per_chrom=3, junction_per_mb=8),
+                                dict(seed=12, chrom_len=6_000_000, contigs_per_chrom=2, junction_per_mb=6, rev_contig_frac=1.0),
+                                dict(seed=14, chrom_len=4_000_000, contigs_per_chrom=3, junction_per_mb=10, sv_per_mb=20.0)])
+def test_contig_preparation_never_invents_an_alignment(kw):
+    """Trimming may only take aligned bases away (clip_alignment_read_edges), joining may only put an insertion and a
+    deletion between two segments (contig_colinear_segment_joiner.rs:57-122): every (contig base -> reference base, strand)
+    of the prepared segments must be one that some input record of that contig states, every prepared CIGAR must span
+    the whole contig, and what trimming removes is exactly the double cover -- afterwards no contig base is aligned twice."""
+    from portello_b200 import lib, synth
+    s = synth.make("tiny", n_reads=10, **kw)
+    raw, got = s.contig_records, lib.load().prepare_contig_records(s.contig_records)
+    raw_cig = np.ctypeslib.as_array(raw.cigar, (int(raw.cigar_begin[raw.n_records]),))
+    n_seg_total = n_pairs_total = n_joined_gaps = 0
+    for ctg in range(raw.n_contigs):
+        L = int(raw.contig_len[ctg])
+        stated = []
+        for k in range(raw.n_records):
+            if raw.contig_id[k] != ctg or (raw.flag[k] & 0x104):     # other contig / unmapped / secondary
+                continue
+            keys, qlen = _pair_keys(raw_cig[int(raw.cigar_begin[k]): int(raw.cigar_begin[k + 1])], raw.pos[k], L, bool(raw.flag[k] & 0x10), raw.tid[k])
+            assert qlen == L
+            stated.append(keys)
+        stated = np.sort(np.concatenate(stated)) if stated else np.zeros(0, np.int64)
+
+        def is_stated(keys):  # (sorted search: numpy's hash-based unique / isin take seconds per call on millions of keys)
+            at = np.minimum(np.searchsorted(stated, keys), max(len(stated) - 1, 0))
+            return len(stated) > 0 and bool(np.all(stated[at] == keys))
+
+        mine = []
+        for g in range(int(got.contig_seg_begin[ctg]), int(got.contig_seg_begin[ctg + 1])):
+            ops = got.cigar[int(got.seg_cigar_begin[g]): int(got.seg_cigar_begin[g + 1])]
+            keys, qlen = _pair_keys(ops, got.seg_pos[g], L, not got.seg_is_fwd[g], got.seg_chrom_index[g])
+            assert qlen == L, (ctg, g)
+            assert is_stated(keys), (ctg, g)
+            # the segment's seq-order interval is where its aligned bases are (in sequencing order = forward contig coordinates)
+            c = keys >> 34
+            assert int(got.seg_seq_order_start[g]) <= int(c.min()) and int(c.max()) < int(got.seg_seq_order_end[g])
+            mine.append(keys)
+            n_seg_total += 1
+            n_joined_gaps += sum(1 for a, b in zip(ops, ops[1:]) if (int(a) & 15, int(b) & 15) == (1, 2) and (int(b) >> 4) > 50)
+        if mine:
+            allk = np.concatenate(mine)
+            contig_base = allk >> 34
+            assert np.all(np.diff(np.sort(contig_base)) > 0), ctg     # no contig base is aligned twice any more
+            n_pairs_total += len(allk)
+    assert n_seg_total >= raw.n_contigs - 1 and n_pairs_total > 0.5 * int(np.sum(np.ctypeslib.as_array(raw.contig_len, (raw.n_contigs,))))
