@@ -193,3 +193,147 @@ def test_contig_preparation_never_invents_an_alignment(kw):
             assert np.all(np.diff(np.sort(contig_base)) > 0), ctg     # no contig base is aligned twice any more
             n_pairs_total += len(allk)
     assert n_seg_total >= raw.n_contigs - 1 and n_pairs_total > 0.5 * int(np.sum(np.ctypeslib.as_array(raw.contig_len, (raw.n_contigs,))))
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# a5 (left_shift_indels) from what a left shift is: the same alignment columns, indels as far left as the sequences allow
+
+def _columns(ops, pos, read, ref):
+    """Walk an alignment: (number of mismatching match columns, total I, total D, read length, reference end)."""
+    q, t, mism, ins, dele = 0, pos, 0, 0, 0
+    for x in ops:
+        op, l = int(x) & 15, int(x) >> 4
+        if op in MATCH_OPS:
+            mism += sum(1 for i in range(l) if read[q + i] != ref[t + i])
+        ins += l if op == 1 else 0
+        dele += l if op == 2 else 0
+        q += l if op in QUERY_OPS else 0
+        t += l if op in REF_OPS else 0
+    return mism, ins, dele, q, t
+
+
+def _shift_case(rng):
+    """A reference of low complexity behind a unique anchor, and a read derived from it by known edits."""
+    anchor = "".join(rng.choice(list("GT"), 24))
+    body = "".join(rng.choice(list("AC"), int(rng.integers(60, 400)), p=[0.7, 0.3]))
+    ref = anchor + body + anchor[::-1]
+    read, ops, t = [], [], 0
+
+    def match(n, kind=7):
+        nonlocal t
+        read.append(ref[t:t + n])
+        ops.append((kind, n))
+        t += n
+    match(len(anchor))
+    while t < len(anchor) + len(body) - 30:
+        match(int(rng.integers(1, 25)))
+        k = rng.random()
+        n = int(rng.integers(1, 6))
+        if k < 0.4:
+            read.append("".join(rng.choice(list("AC"), n, p=[0.7, 0.3])))
+            ops.append((1, n))
+        elif k < 0.8:
+            ops.append((2, n))
+            t += n
+        elif k < 0.9:     # a mismatch column
+            read.append("G")
+            ops.append((8, 1))
+            t += 1
+        else:             # an insertion right next to a deletion
+            read.append("".join(rng.choice(list("AC"), n)))
+            ops.append((1, n))
+            ops.append((2, n + 1))
+            t += n + 1
+    match(len(ref) - t)
+    return ref, "".join(read), np.array([(l << 4) | o for o, l in ops], np.uint32)
+
+
+def _separated_shift_case(rng):
+    """One indel per low-complexity run, the runs kept apart by unique anchors: clusters never meet, so every indel must end
+    up as far left as its run allows."""
+    ref, read, ops = [], [], []
+
+    def both(sq, kind=7):
+        ref.append(sq)
+        read.append(sq)
+        ops.append((kind, len(sq)))
+    both("".join(rng.choice(list("GT"), 20)))
+    for _ in range(int(rng.integers(2, 9))):
+        run = "".join(rng.choice(list("AC"), int(rng.integers(12, 40)), p=[0.75, 0.25]))
+        cut, n = int(rng.integers(4, len(run) - 4)), int(rng.integers(1, 4))
+        both(run[:cut])
+        if rng.random() < 0.5:
+            read.append("".join(rng.choice(list("AC"), n, p=[0.75, 0.25])))
+            ops.append((1, n))
+            both(run[cut:])
+        else:
+            ref.append(run[cut:cut + n])
+            ops.append((2, n))
+            both(run[cut + n:])
+        both("".join(rng.choice(list("GT"), 14)))
+    merged = []
+    for o, l in ops:    # (adjacent match ops of one kind: one op)
+        if merged and merged[-1][0] == o:
+            merged[-1] = (o, merged[-1][1] + l)
+        elif l:
+            merged.append((o, l))
+    return "".join(ref), "".join(read), np.array([(l << 4) | o for o, l in merged], np.uint32)
+
+
+def _left_shift(make_ctx, ref, read, pos, cig, long_ops):
+    ctx = make_ctx()
+    if long_ops is not None:
+        ctx.set_long_pair_ops(long_ops)
+    L = len(ref)
+    span = sum(int(x) >> 4 for x in cig if (int(x) & 15) in REF_OPS)
+    segs, batch = helpers.single_pair_case(f"{L}=", 0, False, L, ref, L - (pos + span), cig[::-1].copy(), abi.pack_seq4(read), len(read), read_flag=0, rseg_fwd=0)
+    ctx.set_contig_segments(segs)
+    res = ctx.lift(batch, stage_mask=abi.STAGE_LEFT_SHIFT)
+    assert res.n_records == 1
+    return int(res.rec_pos[0]), np.asarray(res.cigar[int(res.rec_cigar_begin[0]): int(res.rec_cigar_begin[1])], np.uint32)
+
+
+def check_left_shift(make_ctx, seed, n, long_ops=None):
+    rng = np.random.default_rng(seed)
+    n_moved = 0
+    for it in range(n):
+        separated = it % 2 == 1
+        ref, read, cig = _separated_shift_case(rng) if separated else _shift_case(rng)
+        pos2, cig2 = _left_shift(make_ctx, ref, read, 0, cig, long_ops)
+        before, after = _columns(cig, 0, read, ref), _columns(cig2, pos2, read, ref)
+        # the same edits on the same bases: read length, reference end, inserted and deleted bases; and no column got worse
+        assert pos2 == 0 and after[3] == before[3] == len(read) and after[4] == before[4] and after[1:3] == before[1:3], (ref, read, abi.cigar_to_string(cig))
+        assert after[0] <= before[0]
+        # (not idempotent, by the reference's design: two clusters that the shift makes adjacent move on as ONE cluster only
+        #  in a second pass, e.g. 12=4D2=1I11= -> 8M4D1I15M -> 7M1I4D16M; so "leftmost" is asked of the cases whose indels
+        #  cannot meet)
+        # leftmost: an insertion or deletion behind a match block cannot move one more base (the homology walk of
+        # indel_breakend_homology.rs:35-49 compares ref[ref_end - 1] with read[read_end - 1])
+        q, t, ops = 0, pos2, [(int(x) & 15, int(x) >> 4) for x in cig2]
+        for i, (op, l) in enumerate(ops):
+            if separated and op in (1, 2):
+                assert i > 0 and ops[i - 1][0] in MATCH_OPS and ops[i + 1][0] in MATCH_OPS
+                ref_end, read_end = t + (l if op == 2 else 0), q + (l if op == 1 else 0)
+                assert ref[ref_end - 1] != read[read_end - 1], (abi.cigar_to_string(cig2), i)
+            q += l if op in QUERY_OPS else 0
+            t += l if op in REF_OPS else 0
+        n_moved += list(cig2) != [int(x) & ~0xf | (0 if (int(x) & 15) in MATCH_OPS else int(x) & 15) for x in cig]
+    assert n_moved > n // 2     # (the inputs are built to have room to move)
+
+
+@pytest.mark.parametrize("seed", [41, 42])
+def test_oracle_left_shift_keeps_the_columns_and_ends_leftmost(seed):
+    check_left_shift(lambda: abi.Context(oracle_lib.load(), 0, 1), seed, 60)
+
+
+@pytest.mark.parametrize("long_ops", [None, 0], ids=["thread-per-pair", "warp-per-pair"])
+def test_device_code_left_shift_keeps_the_columns_and_ends_leftmost(long_ops):
+    import emul_lib
+    check_left_shift(lambda: abi.Context(emul_lib.load(), 0, 1), 43, 40, long_ops)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("long_ops", [None, 0], ids=["thread-per-pair", "warp-per-pair"])
+def test_gpu_left_shift_keeps_the_columns_and_ends_leftmost(long_ops):
+    from portello_b200 import lib
+    check_left_shift(lambda: lib.GpuContext(0, 1), 44, 60, long_ops)
