@@ -337,3 +337,116 @@ def test_device_code_left_shift_keeps_the_columns_and_ends_leftmost(long_ops):
 def test_gpu_left_shift_keeps_the_columns_and_ends_leftmost(long_ops):
     from portello_b200 import lib
     check_left_shift(lambda: lib.GpuContext(0, 1), 44, 60, long_ops)
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# a9 (simplify_alignment_indels) from what it is for: an I/D run that holds both kinds is trimmed of the base pairs that match
+# at its ends, a leftover 1I1D is one (mis)match column, and nothing else moves (src/simplify_alignment_indels.rs:35-156)
+
+def _simplify_case(rng):
+    anchor = "".join(rng.choice(list("GT"), 16))
+    ref, read, ops = [anchor], [anchor], [(7, len(anchor))]
+    for _ in range(int(rng.integers(2, 14))):
+        n = int(rng.integers(2, 30))
+        sq = "".join(rng.choice(list("ACGT"), n))
+        ref.append(sq)
+        read.append(sq)
+        ops.append((int(rng.choice([0, 7])), n))
+        k = rng.random()
+        ni, nd = int(rng.integers(1, 7)), int(rng.integers(1, 7))
+        ins, dele = "".join(rng.choice(list("AC"), ni)), "".join(rng.choice(list("AC"), nd))
+        if k < 0.25:
+            read.append(ins)
+            ops.append((1, ni))
+        elif k < 0.5:
+            ref.append(dele)
+            ops.append((2, nd))
+        else:  # a run with both kinds, in either order, sometimes in three pieces
+            read.append(ins)
+            ref.append(dele)
+            if k < 0.7:
+                ops += [(1, ni), (2, nd)]
+            elif k < 0.9:
+                ops += [(2, nd), (1, ni)]
+            else:
+                a = int(rng.integers(0, ni + 1))
+                ops += [(1, a), (2, nd), (1, ni - a)]
+    ref.append(anchor)
+    read.append(anchor)
+    ops.append((7, len(anchor)))
+    return "".join(ref), "".join(read), np.array([(l << 4) | o for o, l in ops if l], np.uint32)
+
+
+def _clusters(ops, pos):
+    """(ref start, read start, deleted, inserted) of every I/D run of a CIGAR."""
+    q, t, out, cur = 0, pos, [], None
+    for x in ops:
+        op, l = int(x) & 15, int(x) >> 4
+        if op in (1, 2):
+            if cur is None:
+                cur = [t, q, 0, 0]
+            cur[2 if op == 2 else 3] += l
+        elif cur is not None:
+            out.append(tuple(cur))
+            cur = None
+        q += l if op in QUERY_OPS else 0
+        t += l if op in REF_OPS else 0
+    return out + ([tuple(cur)] if cur else [])
+
+
+def check_simplify(make_ctx, seed, n, long_ops=None):
+    rng = np.random.default_rng(seed)
+    n_changed = 0
+    for _ in range(n):
+        ref, read, cig = _simplify_case(rng)
+
+        def run(pos, ops):
+            ctx = make_ctx()
+            if long_ops is not None:
+                ctx.set_long_pair_ops(long_ops)
+            ctx.set_reference([np.frombuffer(ref.encode(), np.uint8)])
+            segs, batch = helpers.single_pair_case(f"{len(ref)}=", 0, True, len(ref), None, pos, ops, abi.pack_seq4(read), len(read))
+            ctx.set_contig_segments(segs)
+            res = ctx.lift(batch, stage_mask=abi.STAGE_SIMPLIFY)
+            assert res.n_records == 1
+            return int(res.rec_pos[0]), np.asarray(res.cigar[int(res.rec_cigar_begin[0]): int(res.rec_cigar_begin[1])], np.uint32)
+
+        pos2, cig2 = run(0, cig)
+        before, after = _columns(cig, 0, read, ref), _columns(cig2, pos2, read, ref)
+        assert pos2 == 0 and after[3] == before[3] == len(read) and after[4] == before[4] == len(ref)
+        # every aligned pair of the input is still there; the new ones sit inside the input's mixed runs
+        old_pairs, new_pairs = set(aligned_pairs(cig, 0)[0]), set(aligned_pairs(cig2, pos2)[0])
+        assert old_pairs <= new_pairs
+        mixed = [c for c in _clusters(cig, 0) if c[2] and c[3]]
+        for q, t in new_pairs - old_pairs:
+            assert any(c[1] <= q < c[1] + c[3] and c[0] <= t < c[0] + c[2] for c in mixed)
+        # what is left of a run with both kinds cannot be trimmed any further, and is not 1I1D
+        for t0, q0, d, i in _clusters(cig2, pos2):
+            if d and i:
+                assert (d, i) != (1, 1)
+                assert ref[t0 + d - 1] != read[q0 + i - 1] and ref[t0] != read[q0], abi.cigar_to_string(cig2)
+        # the trimmed pairs are real matches, except the single column a 1I1D leftover turns into
+        n_mismatch_new = sum(1 for q, t in new_pairs - old_pairs if read[q] != ref[t])
+        assert n_mismatch_new <= len(mixed)
+        pos3, cig3 = run(pos2, cig2)
+        assert pos3 == pos2 and list(cig3) == list(cig2)   # idempotent
+        n_changed += bool(new_pairs - old_pairs)
+    assert n_changed > n // 3
+
+
+@pytest.mark.parametrize("seed", [51, 52])
+def test_oracle_simplify_trims_mixed_runs_and_moves_nothing_else(seed):
+    check_simplify(lambda: abi.Context(oracle_lib.load(), 0, 1), seed, 60)
+
+
+@pytest.mark.parametrize("long_ops", [None, 0], ids=["thread-per-pair", "warp-per-pair"])
+def test_device_code_simplify_trims_mixed_runs_and_moves_nothing_else(long_ops):
+    import emul_lib
+    check_simplify(lambda: abi.Context(emul_lib.load(), 0, 1), 53, 40, long_ops)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("long_ops", [None, 0], ids=["thread-per-pair", "warp-per-pair"])
+def test_gpu_simplify_trims_mixed_runs_and_moves_nothing_else(long_ops):
+    from portello_b200 import lib
+    check_simplify(lambda: lib.GpuContext(0, 1), 54, 60, long_ops)
