@@ -450,3 +450,79 @@ def test_device_code_simplify_trims_mixed_runs_and_moves_nothing_else(long_ops):
 def test_gpu_simplify_trims_mixed_runs_and_moves_nothing_else(long_ops):
     from portello_b200 import lib
     check_simplify(lambda: lib.GpuContext(0, 1), 54, 60, long_ops)
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# a4 / a10 record fields from the strand algebra and the documented rules (docs/methods.md:22-24,43-45; SURVEY parity traps
+# 3, 4, 12): no restatement of finish_remapped_alignment_set, only what its output must look like
+
+def check_record_rules(ctx, s, pb, segs):
+    import oracle_lib as O
+    r = helpers.lift_c(ctx, pb.c, allow_panic=True)
+    b = pb.c
+    g = lambda p, n: np.ctypeslib.as_array(p, (n,))
+    read_flag, rseg_fwd, rseg_ctg = g(b.read_flag, b.n_reads), g(b.rseg_is_fwd, b.n_read_segments), g(b.rseg_contig, b.n_read_segments)
+    read_bin = g(b.read_bin, b.n_reads)
+    n_multi = n_fallback = n_rev = 0
+    for i in range(b.n_reads):
+        k0, k1 = int(r.read_rec_begin[i]), int(r.read_rec_begin[i + 1])
+        lifted = [k for k in range(k0, k1) if r.rec_status[k] == 1]
+        if not lifted:
+            # the unmapped fallback (:317-335): one record, unmapped, no position, MAPQ 255, the input record's bin, no CIGAR
+            assert k1 - k0 == 1 and (r.rec_flag[k0] & 0x4) and not (r.rec_flag[k0] & 0x800)
+            assert (int(r.rec_tid[k0]), int(r.rec_pos[k0]), int(r.rec_mapq[k0])) == (-1, -1, 255) and r.rec_bin[k0] == read_bin[i]
+            assert r.rec_cigar_begin[k0] == r.rec_cigar_begin[k0 + 1]
+            n_fallback += 1
+            continue
+        assert lifted == list(range(k0, k1))
+        keys = []
+        for k in lifted:
+            rs, cs = int(r.rec_read_segment[k]), int(r.rec_contig_segment[k])
+            assert int(b.read_seg_begin[i]) <= rs < int(b.read_seg_begin[i + 1])
+            gseg = int(segs.contig_seg_begin[rseg_ctg[rs]]) + cs
+            assert gseg < int(segs.contig_seg_begin[rseg_ctg[rs] + 1])
+            # strands compose: the read lies reversed on the reference iff it lies on the contig and the contig on the reference
+            # in different orientations; the stored bases are flipped iff that differs from the orientation of the input record
+            on_ref_reverse = bool(rseg_fwd[rs]) != bool(segs.seg_is_fwd[gseg])
+            assert bool(r.rec_flag[k] & 0x10) == on_ref_reverse
+            assert bool(r.rec_need_flip[k]) == (on_ref_reverse != bool(read_flag[i] & 0x10))
+            assert not (r.rec_flag[k] & 0x4)
+            # chromosome and MAPQ are the contig segment's (trap 3: the lifted MAPQ is not the read's)
+            assert int(r.rec_tid[k]) == int(segs.seg_chrom_index[gseg]) and int(r.rec_mapq[k]) == int(segs.seg_mapq[gseg])
+            ops = r.cigar[int(r.rec_cigar_begin[k]): int(r.rec_cigar_begin[k + 1])]
+            end = int(r.rec_pos[k]) + sum(int(x) >> 4 for x in ops if (int(x) & 15) in REF_OPS)
+            assert int(r.rec_bin[k]) == O.load().reg2bin(int(r.rec_pos[k]), end)
+            keys.append((rs, cs))
+            n_rev += on_ref_reverse
+        assert keys == sorted(keys) and len(set(keys)) == len(keys)      # (read segment in sequencing order) x (contig segment index)
+        # trap 4: the primary is the FIRST record with the highest MAPQ; every other record is supplementary
+        mq = [int(r.rec_mapq[k]) for k in lifted]
+        prim = [k for k in lifted if not (r.rec_flag[k] & 0x800)]
+        assert prim == [lifted[mq.index(max(mq))]]
+        n_multi += len(lifted) > 1
+    return n_multi, n_fallback, n_rev
+
+
+def _record_rule_set():
+    from portello_b200 import synth
+    s = synth.make("tiny", seed=61, n_reads=4000, read_sa_frac=0.25, junction_per_mb=20.0, rev_contig_frac=0.5)
+    return s, helpers.pack(s)
+
+
+def test_oracle_and_device_code_records_follow_the_documented_rules():
+    import emul_lib
+    s, pb = _record_rule_set()
+    for L in (oracle_lib.load(), emul_lib.load()):
+        ctx = abi.Context(L, 0, 1)
+        ctx.set_reference(helpers.reference_arrays(s))
+        ctx.set_contig_records(s.contig_records)
+        n_multi, n_fallback, n_rev = check_record_rules(ctx, s, pb, ctx.get_contig_segments())
+        assert n_multi > 100 and n_fallback > 10 and n_rev > 500, (n_multi, n_fallback, n_rev)
+
+
+@pytest.mark.gpu
+def test_gpu_records_follow_the_documented_rules():
+    s, pb = _record_rule_set()
+    ctx = helpers.gpu_context(s)
+    n_multi, n_fallback, n_rev = check_record_rules(ctx, s, pb, ctx.get_contig_segments())
+    assert n_multi > 100 and n_fallback > 10 and n_rev > 500
