@@ -454,7 +454,7 @@ void ptl_shard_units(uint32_t n_units, const uint64_t* weight, uint32_t n_ranks,
  * header as a ChromList (lib/rust-vc-utils/src/chrom_list.rs:26-44) and the EOF-marker check (bam_reader_utils.rs:29).
  * Written from the SAM specification (4.1 BGZF, 4.2 BAM, 5.2 BAI).  A ptl_bam_file is immutable once opened: any number of
  * threads may fetch from it concurrently, which replaces the per-thread reader set of src/worker_thread_data.rs:8-30.
- * BAM + .bai only (CRAM and .csi are not supported). */
+ * BAM with a .bai or .csi index (CRAM is not supported). */
 typedef struct ptl_bam_file ptl_bam_file;
 typedef struct ptl_decoded_batch ptl_decoded_batch;
 enum {
@@ -486,6 +486,10 @@ const uint8_t* ptl_decoded_raw(const ptl_decoded_batch* d, const uint64_t** rec_
 void ptl_decoded_free(ptl_decoded_batch* d);
 /* samtools-index equivalent (coordinate-sorted BAM -> .bai with the linear index and the metadata pseudo-bins). */
 int ptl_bam_index_build(const char* bam_path, const char* bai_path);
+/* The same as a CSIv1 index (`.csi`: BGZF-compressed; bins of 2^min_shift bases at the finest of depth + 1 levels; what
+ * htslib writes for references longer than 2^29 bases).  depth <= 0: the smallest depth that covers the longest reference.
+ * ptl_bam_open looks for <bam>.bai, <stem>.bai, <bam>.csi, <stem>.csi in that order. */
+int ptl_bam_index_build_csi(const char* bam_path, const char* csi_path, int min_shift, int depth);
 
 /* ---------------------------------------------------------------- Phase A on real input
  *

@@ -320,6 +320,7 @@ extern "C" {
     pub fn ptl_decoded_raw(d: *const ptl_decoded_batch, rec_off: *mut *const u64, n_bytes: *mut u64) -> *const u8;
     pub fn ptl_decoded_free(d: *mut ptl_decoded_batch);
     pub fn ptl_bam_index_build(bam_path: *const c_char, bai_path: *const c_char) -> c_int;
+    pub fn ptl_bam_index_build_csi(bam_path: *const c_char, csi_path: *const c_char, min_shift: c_int, depth: c_int) -> c_int;
     pub fn ptl_fasta_load(path: *const c_char, n_threads: c_int, out: *mut *mut ptl_fasta) -> c_int;
     pub fn ptl_fasta_n(f: *const ptl_fasta) -> u32;
     pub fn ptl_fasta_name(f: *const ptl_fasta, i: u32) -> *const c_char;

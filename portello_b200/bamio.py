@@ -37,6 +37,7 @@ def _dll():
         d.ptl_decoded_raw.restype, d.ptl_decoded_raw.argtypes = u8p, [C.c_void_p, C.POINTER(u64p), u64p]
         d.ptl_decoded_free.argtypes = [C.c_void_p]
         d.ptl_bam_index_build.restype, d.ptl_bam_index_build.argtypes = C.c_int, [C.c_char_p, C.c_char_p]
+        d.ptl_bam_index_build_csi.restype, d.ptl_bam_index_build_csi.argtypes = C.c_int, [C.c_char_p, C.c_char_p, C.c_int, C.c_int]
         d.ptl_fasta_load.restype, d.ptl_fasta_load.argtypes = C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
         d.ptl_fasta_n.restype, d.ptl_fasta_n.argtypes = C.c_uint32, [C.c_void_p]
         d.ptl_fasta_name.restype, d.ptl_fasta_name.argtypes = C.c_char_p, [C.c_void_p, C.c_uint32]
@@ -185,6 +186,10 @@ def bgzf_compress(data, level: int = 6, threads: int = 4, eof: bool = True) -> b
 
 def index_bam(path: str, bai_path: str | None = None):
     _check(_dll().ptl_bam_index_build(path.encode(), bai_path.encode() if bai_path else None))
+
+
+def index_bam_csi(path: str, csi_path: str | None = None, min_shift: int = 14, depth: int = 0):
+    _check(_dll().ptl_bam_index_build_csi(path.encode(), csi_path.encode() if csi_path else None, min_shift, depth))
 
 
 def write_fasta(path: str, names, seqs, width: int = 60):

@@ -133,6 +133,13 @@ int ptl_bam_index_build(const char* bam_path, const char* bai_path) {
         return PTL_OK;
     });
 }
+int ptl_bam_index_build_csi(const char* bam_path, const char* csi_path, int min_shift, int depth) {
+    if (!bam_path) return PTL_ERR_INVALID_ARG;
+    return guarded([&]() {
+        build_csi(bam_path, csi_path ? std::string(csi_path) : std::string(bam_path) + ".csi", min_shift, depth);
+        return PTL_OK;
+    });
+}
 
 int ptl_fasta_load(const char* path, int n_threads, ptl_fasta** out) {
     if (!path || !out) return PTL_ERR_INVALID_ARG;

@@ -1,4 +1,4 @@
-// BAM / BGZF / BAI input and FASTA loading without htslib: see bam_io.hpp.  Written from the SAM specification.
+// BAM / BGZF / BAI / CSI input and FASTA loading without htslib: see bam_io.hpp.  Written from the SAM specification.
 #include "bam_io.hpp"
 
 #include <fcntl.h>
@@ -14,7 +14,7 @@
 namespace ptl {
 namespace {
 
-constexpr uint32_t kMetaBin = 37450;
+constexpr uint32_t kMetaBin = 37450;  // = meta_bin_of(5)
 const uint8_t kEofMarker[28] = {0x1f, 0x8b, 0x08, 0x04, 0, 0, 0, 0, 0, 0xff, 0x06, 0, 0x42, 0x43, 0x02, 0, 0x1b, 0, 0x03, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 
 [[noreturn]] void fail(const std::string& m) { throw BamIoError{m}; }
@@ -34,28 +34,33 @@ size_t pread_full(int fd, void* dst, size_t n, uint64_t off) {
     return got;
 }
 
-// reg2bins (SAM spec 5.3): the bins that may hold records overlapping [beg, end)
-void reg2bins(int64_t beg, int64_t end, std::vector<uint32_t>& out) {
+// reg2bins (SAM spec 5.3; CSIv1 for other min_shift / depth): the bins that may hold records overlapping [beg, end).
+// Level l (0 = the root) has 8^l bins of 2^(min_shift + 3 (depth - l)) bases, numbered from (8^l - 1) / 7.
+void reg2bins(int64_t beg, int64_t end, int min_shift, int depth, std::vector<uint32_t>& out) {
     out.clear();
+    if (beg < 0) beg = 0;
+    const int64_t max_end = int64_t(1) << (min_shift + 3 * depth);
+    if (end > max_end) end = max_end;
     if (end <= beg) end = beg + 1;
     --end;
-    out.push_back(0);
-    for (uint32_t k = 1 + uint32_t(beg >> 26); k <= 1 + uint32_t(end >> 26); ++k) out.push_back(k);
-    for (uint32_t k = 9 + uint32_t(beg >> 23); k <= 9 + uint32_t(end >> 23); ++k) out.push_back(k);
-    for (uint32_t k = 73 + uint32_t(beg >> 20); k <= 73 + uint32_t(end >> 20); ++k) out.push_back(k);
-    for (uint32_t k = 585 + uint32_t(beg >> 17); k <= 585 + uint32_t(end >> 17); ++k) out.push_back(k);
-    for (uint32_t k = 4681 + uint32_t(beg >> 14); k <= 4681 + uint32_t(end >> 14); ++k) out.push_back(k);
+    uint32_t first = 0;
+    for (int l = 0, sh = min_shift + 3 * depth; l <= depth; ++l, sh -= 3) {
+        for (uint32_t k = first + uint32_t(beg >> sh); k <= first + uint32_t(end >> sh); ++k) out.push_back(k);
+        first += 1u << (3 * l);
+    }
 }
-
-uint16_t reg2bin(int64_t beg, int64_t end) {
+// the smallest bin that holds [beg, end) whole
+uint32_t reg2bin_levels(int64_t beg, int64_t end, int min_shift, int depth) {
     --end;
-    if (beg >> 14 == end >> 14) return uint16_t(((1 << 15) - 1) / 7 + (beg >> 14));
-    if (beg >> 17 == end >> 17) return uint16_t(((1 << 12) - 1) / 7 + (beg >> 17));
-    if (beg >> 20 == end >> 20) return uint16_t(((1 << 9) - 1) / 7 + (beg >> 20));
-    if (beg >> 23 == end >> 23) return uint16_t(((1 << 6) - 1) / 7 + (beg >> 23));
-    if (beg >> 26 == end >> 26) return uint16_t(((1 << 3) - 1) / 7 + (beg >> 26));
+    uint32_t first = ((1u << (3 * depth)) - 1u) / 7u;
+    for (int l = depth, sh = min_shift; l > 0; --l, sh += 3) {
+        if ((beg >> sh) == (end >> sh)) return first + uint32_t(beg >> sh);
+        first -= 1u << (3 * (l - 1));
+    }
     return 0;
 }
+inline uint32_t meta_bin_of(int depth) { return ((1u << (3 * depth + 3)) - 1u) / 7u + 1u; }  // 37450 for the BAI's five levels
+
 
 // reference bases consumed by a BAM CIGAR (M, D, N, =, X)
 int64_t cigar_ref_len(const uint8_t* cigar, uint32_t n) {
@@ -190,6 +195,14 @@ bool BgzfReader::read(void* dst, size_t n) {
         done += k;
     }
     return true;
+}
+
+size_t BgzfReader::read_some(void* dst, size_t n) {
+    if (at_eof()) return 0;
+    const size_t k = std::min(n, buf_.size() - size_t(pos_));
+    std::memcpy(dst, buf_.data() + pos_, k);
+    pos_ += uint32_t(k);
+    return k;
 }
 
 bool BgzfReader::at_eof() {
@@ -334,6 +347,60 @@ bool load_bai(const std::string& path, size_t n_ref, BaiIndex& idx) {
     if (at + 8 <= b.size()) { idx.has_no_coor = true; idx.n_no_coor = le64(b.data() + at); }
     return true;
 }
+
+// CSIv1 (the index htslib writes for references longer than 2^29 bases, or on request): a BGZF stream of
+// magic, min_shift, depth, l_aux, aux, n_ref, then per reference its bins { bin, loffset, n_chunk, chunks }.
+bool load_csi(const std::string& path, size_t n_ref, BaiIndex& idx) {
+    const int fd = ::open(path.c_str(), O_RDONLY);
+    if (fd < 0) return false;
+    struct FdGuard { int fd; ~FdGuard() { ::close(fd); } } g{fd};
+    std::vector<uint8_t> b;
+    {
+        BgzfReader r(fd);
+        uint8_t buf[65536];
+        for (size_t n; (n = r.read_some(buf, sizeof buf)) != 0;) b.insert(b.end(), buf, buf + n);
+    }
+    if (b.size() < 16 || std::memcmp(b.data(), "CSI\1", 4) != 0) fail("not a CSI index: " + path);
+    size_t at = 4;
+    auto need = [&](size_t n) { if (at + n > b.size()) fail("truncated CSI index: " + path); };
+    idx.csi = true;
+    idx.min_shift = int(le32(b.data() + 4));
+    idx.depth = int(le32(b.data() + 8));
+    const uint32_t l_aux = le32(b.data() + 12);
+    at = 16;
+    if (idx.min_shift < 1 || idx.min_shift > 30 || idx.depth < 1 || idx.depth > 9 || idx.min_shift + 3 * idx.depth > 62) fail("unsupported CSI geometry: " + path);
+    need(size_t(l_aux) + 4);
+    at += l_aux;
+    const uint32_t nr = le32(b.data() + at); at += 4;
+    if (nr != n_ref) fail("CSI index does not match the BAM header (reference count): " + path);
+    const uint32_t meta = meta_bin_of(idx.depth);
+    idx.refs.assign(nr, BaiRef{});
+    for (uint32_t r = 0; r < nr; ++r) {
+        BaiRef& R = idx.refs[r];
+        need(4);
+        const uint32_t n_bin = le32(b.data() + at); at += 4;
+        for (uint32_t k = 0; k < n_bin; ++k) {
+            need(16);
+            const uint32_t bin = le32(b.data() + at);
+            const uint64_t loff = le64(b.data() + at + 4);
+            const uint32_t n_chunk = le32(b.data() + at + 12);
+            at += 16;
+            need(16ull * n_chunk);
+            if (bin == meta && n_chunk == 2) {
+                R.has_meta = true;
+                R.meta_beg = le64(b.data() + at); R.meta_end = le64(b.data() + at + 8);
+                R.n_mapped = le64(b.data() + at + 16); R.n_unmapped = le64(b.data() + at + 24);
+            } else {
+                R.loffset[bin] = loff;
+                auto& v = R.bins[bin];
+                for (uint32_t c = 0; c < n_chunk; ++c) v.emplace_back(le64(b.data() + at + 16ull * c), le64(b.data() + at + 16ull * c + 8));
+            }
+            at += 16ull * n_chunk;
+        }
+    }
+    if (at + 8 <= b.size()) { idx.has_no_coor = true; idx.n_no_coor = le64(b.data() + at); }
+    return true;
+}
 }  // namespace
 
 BamFile* BamFile::open(const std::string& path) {
@@ -372,8 +439,10 @@ BamFile* BamFile::open(const std::string& path) {
             f->has_eof_ = std::memcmp(tail, kEofMarker, 28) == 0;
         }
         f->has_index_ = load_bai(path + ".bai", n_ref, f->index_);
-        if (!f->has_index_ && path.size() > 4 && path.compare(path.size() - 4, 4, ".bam") == 0)
-            f->has_index_ = load_bai(path.substr(0, path.size() - 4) + ".bai", n_ref, f->index_);
+        const bool dot_bam = path.size() > 4 && path.compare(path.size() - 4, 4, ".bam") == 0;
+        if (!f->has_index_ && dot_bam) f->has_index_ = load_bai(path.substr(0, path.size() - 4) + ".bai", n_ref, f->index_);
+        if (!f->has_index_) f->has_index_ = load_csi(path + ".csi", n_ref, f->index_);
+        if (!f->has_index_ && dot_bam) f->has_index_ = load_csi(path.substr(0, path.size() - 4) + ".csi", n_ref, f->index_);
     } catch (...) {
         delete f;
         throw;
@@ -433,9 +502,20 @@ void BamFile::fetch(int32_t tid, int64_t begin, int64_t end, uint32_t filter, De
     if (tid < 0 || size_t(tid) >= index_.refs.size()) fail("fetch: reference index out of range");
     const BaiRef& R = index_.refs[size_t(tid)];
     std::vector<uint32_t> bins;
-    reg2bins(begin, end, bins);
+    reg2bins(begin, end, index_.min_shift, index_.depth, bins);
     uint64_t min_off = 0;
-    if (!R.ioffset.empty()) {
+    if (index_.csi) {
+        // the lower bound of the finest bin around `begin` that the index has, or of its nearest ancestor (each bin's
+        // loffset is the offset of the first record that overlaps the bin's first window)
+        const int64_t b0 = std::min<int64_t>(std::max<int64_t>(begin, 0), (int64_t(1) << (index_.min_shift + 3 * index_.depth)) - 1);
+        uint32_t bin = ((1u << (3 * index_.depth)) - 1u) / 7u + uint32_t(b0 >> index_.min_shift);
+        for (;;) {
+            auto it = R.loffset.find(bin);
+            if (it != R.loffset.end()) { min_off = it->second; break; }
+            if (bin == 0) break;
+            bin = (bin - 1u) >> 3;
+        }
+    } else if (!R.ioffset.empty()) {
         const size_t w = size_t(std::max<int64_t>(begin, 0) >> 14);
         min_off = R.ioffset[std::min(w, R.ioffset.size() - 1)];
     }
@@ -469,7 +549,16 @@ void BamFile::fetch(int32_t tid, int64_t begin, int64_t end, uint32_t filter, De
 }
 
 // ================================================================================================== BAI builder
-void build_bai(const std::string& bam_path, const std::string& bai_path) {
+namespace {
+void build_index(const std::string& bam_path, const std::string& out_path, bool csi, int min_shift, int depth);
+}
+void build_bai(const std::string& bam_path, const std::string& bai_path) { build_index(bam_path, bai_path, false, 14, 5); }
+void build_csi(const std::string& bam_path, const std::string& csi_path, int min_shift, int depth) {
+    if (min_shift < 1 || min_shift > 30 || depth > 9) fail("build_csi: min_shift must be 1..30 and depth at most 9");
+    build_index(bam_path, csi_path, true, min_shift, depth);
+}
+namespace {
+void build_index(const std::string& bam_path, const std::string& bai_path, bool csi, int min_shift, int depth) {
     BamFile* f = BamFile::open(bam_path);
     struct Guard { BamFile* f; ~Guard() { delete f; } } g{f};
     const size_t n_ref = f->ref_names().size();
@@ -480,6 +569,13 @@ void build_bai(const std::string& bam_path, const std::string& bai_path) {
     };
     std::vector<Ref> refs(n_ref);
     uint64_t n_no_coor = 0;
+    if (csi && depth <= 0) {
+        uint64_t longest = 0;
+        for (uint64_t l : f->ref_len()) longest = std::max(longest, l);
+        for (depth = 1; depth < 9 && (uint64_t(1) << (min_shift + 3 * depth)) < longest; ++depth) {}
+    }
+    if (min_shift + 3 * depth > 62) fail("index geometry too large");
+    const int64_t max_pos = int64_t(1) << (min_shift + 3 * depth);
     // walk the records with their virtual offsets
     const int fd = ::open(bam_path.c_str(), O_RDONLY);
     if (fd < 0) fail("cannot open " + bam_path);
@@ -520,13 +616,14 @@ void build_bai(const std::string& bam_path, const std::string& bai_path) {
         last_tid = v.tid;
         last_pos = v.pos;
         Ref& R = refs[size_t(v.tid)];
-        const uint32_t bin = reg2bin(v.pos, v.end);
+        if (v.end > max_pos) fail(csi ? "a record lies beyond what this CSI geometry can index: raise depth" : "a record lies beyond 2^29: the BAI cannot index it, write a .csi");
+        const uint32_t bin = reg2bin_levels(v.pos, v.end, min_shift, depth);
         auto& chunks = R.bins[bin];
         if (last_bin == bin && last_bin_tid == v.tid && !chunks.empty()) chunks.back().second = v1;
         else chunks.emplace_back(v0, v1);
         last_bin = bin;
         last_bin_tid = v.tid;
-        const size_t w0 = size_t(v.pos >> 14), w1 = size_t((v.end - 1) >> 14);
+        const size_t w0 = size_t(v.pos >> min_shift), w1 = size_t((v.end - 1) >> min_shift);
         if (R.lin.size() <= w1) R.lin.resize(w1 + 1, 0);
         for (size_t k = w0; k <= w1; ++k)
             if (R.lin[k] == 0) R.lin[k] = v0;
@@ -537,27 +634,55 @@ void build_bai(const std::string& bam_path, const std::string& bai_path) {
     std::vector<uint8_t> out;
     auto p32 = [&](uint32_t x) { for (int b = 0; b < 4; ++b) out.push_back(uint8_t(x >> (8 * b))); };
     auto p64 = [&](uint64_t x) { for (int b = 0; b < 8; ++b) out.push_back(uint8_t(x >> (8 * b))); };
-    out.insert(out.end(), {'B', 'A', 'I', 1});
+    if (csi) {
+        out.insert(out.end(), {'C', 'S', 'I', 1});
+        p32(uint32_t(min_shift));
+        p32(uint32_t(depth));
+        p32(0);  // l_aux
+    } else {
+        out.insert(out.end(), {'B', 'A', 'I', 1});
+    }
     p32(uint32_t(n_ref));
+    const uint32_t meta_bin = meta_bin_of(depth);
     for (Ref& R : refs) {
         const bool any = R.beg != ~0ull;
         p32(uint32_t(R.bins.size() + (any ? 1 : 0)));
         std::vector<uint32_t> ids;
         for (const auto& kv : R.bins) ids.push_back(kv.first);
         std::sort(ids.begin(), ids.end());
+        for (size_t k = 1; k < R.lin.size(); ++k)
+            if (R.lin[k] == 0) R.lin[k] = R.lin[k - 1];
         for (uint32_t b : ids) {
             const auto& ch = R.bins[b];
             p32(b);
+            if (csi) {  // loffset: the linear-index entry of the bin's first window
+                int l = 0;
+                uint32_t first = 0;
+                while (l < depth && b >= first + (1u << (3 * l))) { first += 1u << (3 * l); ++l; }
+                const uint64_t win = uint64_t(b - first) << (3 * (depth - l));
+                p64(win < R.lin.size() ? R.lin[size_t(win)] : (R.lin.empty() ? 0 : R.lin.back()));
+            }
             p32(uint32_t(ch.size()));
             for (const auto& c : ch) { p64(c.first); p64(c.second); }
         }
-        if (any) { p32(kMetaBin); p32(2); p64(R.beg); p64(R.end); p64(R.n_mapped); p64(R.n_unmapped); }
-        for (size_t k = 1; k < R.lin.size(); ++k)
-            if (R.lin[k] == 0) R.lin[k] = R.lin[k - 1];
-        p32(uint32_t(R.lin.size()));
-        for (uint64_t o : R.lin) p64(o);
+        if (any) {
+            p32(meta_bin);
+            if (csi) p64(0);
+            p32(2); p64(R.beg); p64(R.end); p64(R.n_mapped); p64(R.n_unmapped);
+        }
+        if (!csi) {
+            p32(uint32_t(R.lin.size()));
+            for (uint64_t o : R.lin) p64(o);
+        }
     }
     p64(n_no_coor);
+    if (csi) {  // a .csi is a BGZF file
+        std::vector<uint8_t> z(ptl_bgzf_bound(out.size()));
+        const int64_t k = ptl_bgzf_compress(out.data(), out.size(), 6, 1, 1, z.data(), z.size());
+        if (k < 0) fail("cannot compress the CSI index");
+        z.resize(size_t(k));
+        out.swap(z);
+    }
     const int ofd = ::open(bai_path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
     if (ofd < 0) fail("cannot write " + bai_path);
     size_t done = 0;
@@ -568,6 +693,7 @@ void build_bai(const std::string& bam_path, const std::string& bai_path) {
     }
     ::close(ofd);
 }
+}  // namespace
 
 // ================================================================================================== FASTA
 std::vector<FastaRecord> read_fasta(const std::string& path, int n_threads) {

@@ -1,4 +1,4 @@
-// BAM / BGZF / BAI input without htslib (input half), host C++ + zlib.
+// BAM / BGZF / BAI / CSI input without htslib (input half), host C++ + zlib.
 //
 // What the reference gets from rust-htslib on its input side:
 //   bam::IndexedReader::from_path + fetch(Region | Unmapped) + read   src/read_alignment_scanner.rs:382-393,537-559
@@ -32,6 +32,7 @@ public:
     // false at a clean end of file (before the first byte); throws on truncation / corruption
     bool read(void* dst, size_t n);
     bool at_eof();
+    size_t read_some(void* dst, size_t n);  // up to n bytes of the current block (0 at the end of the file)
 
 private:
     bool load(uint64_t coffset);  // inflate the block at coffset; false at end of file
@@ -45,11 +46,14 @@ private:
 // ---- BAI (SAM spec 5.2)
 struct BaiRef {
     std::unordered_map<uint32_t, std::vector<std::pair<uint64_t, uint64_t>>> bins;  // bin -> chunks (virtual offsets)
-    std::vector<uint64_t> ioffset;                                                  // 16 kb linear index
+    std::vector<uint64_t> ioffset;                                                  // 16 kb linear index (BAI)
+    std::unordered_map<uint32_t, uint64_t> loffset;                                 // per-bin lower bound (CSI)
     bool has_meta = false;
     uint64_t meta_beg = 0, meta_end = 0, n_mapped = 0, n_unmapped = 0;              // pseudo-bin 37450
 };
 struct BaiIndex {
+    int min_shift = 14, depth = 5;  // BAI: fixed; CSI: from the file (bins of 2^min_shift .. 2^(min_shift + 3 depth) bases)
+    bool csi = false;
     std::vector<BaiRef> refs;
     bool has_no_coor = false;
     uint64_t n_no_coor = 0;
@@ -110,6 +114,9 @@ private:
 
 // samtools-index equivalent: scan `bam_path` and write a .bai next to it (or to bai_path).
 void build_bai(const std::string& bam_path, const std::string& bai_path);
+// the same as a .csi (CSIv1: BGZF-compressed, bins of 2^min_shift bases at the finest of depth + 1 levels, a lower-bound
+// offset per bin instead of the linear index); depth <= 0: the smallest depth that covers the longest reference
+void build_csi(const std::string& bam_path, const std::string& csi_path, int min_shift, int depth);
 
 // FASTA -> (name, upper-cased sequence) per record = get_genome_ref_from_fasta (lib/rust-vc-utils/src/genome_ref.rs:43-79):
 // the id is the header up to the first whitespace, every base upper-cased, nothing else changed.

@@ -215,3 +215,96 @@ def test_errors_are_reported_not_fatal(tmp_path, dataset):
     fc = bamio.BamFile(paths["contigs"])
     with pytest.raises(abi.PtlError):
         fc.scan_contigs(s.contig_names[:-1] + ["someone_else"], s.contig_lengths())
+
+
+def _python_csi(path):
+    """Independent CSIv1 reader (gzip + struct): geometry, and per reference {bin: (loffset, chunks)}."""
+    raw = gzip.open(path, "rb").read()
+    assert raw[:4] == b"CSI\x01"
+    min_shift, depth, l_aux = struct.unpack_from("<iii", raw, 4)
+    at = 16 + l_aux
+    n_ref = struct.unpack_from("<i", raw, at)[0]
+    at += 4
+    refs = []
+    for _ in range(n_ref):
+        n_bin = struct.unpack_from("<i", raw, at)[0]
+        at += 4
+        bins = {}
+        for _ in range(n_bin):
+            b, loff, n_chunk = struct.unpack_from("<IQi", raw, at)
+            at += 16
+            bins[b] = (loff, [struct.unpack_from("<QQ", raw, at + 16 * c) for c in range(n_chunk)])
+            at += 16 * n_chunk
+        refs.append(bins)
+    n_no_coor = struct.unpack_from("<Q", raw, at)[0] if at + 8 <= len(raw) else None
+    return min_shift, depth, refs, n_no_coor
+
+
+@pytest.mark.parametrize("min_shift,depth", [(14, 5), (14, 0), (12, 6), (16, 3)], ids=["bai-geometry", "auto-depth", "fine", "coarse"])
+def test_csi_index_fetches_what_the_bai_fetches(dataset, tmp_path, min_shift, depth):
+    """A .csi (CSIv1: BGZF-compressed, any bin geometry, a lower-bound offset per bin instead of the linear index) built by
+    ptl_bam_index_build_csi must drive the same region / unmapped fetches as the .bai, for the BAI's own geometry and others;
+    the file itself is read back by an independent parser: every bin is the smallest one of its geometry that holds some
+    record, the meta pseudo-bin carries the counts, and each loffset is a valid lower bound."""
+    s, paths = dataset
+    with_bai = bamio.BamFile(paths["reads"])
+    p = tmp_path / "reads.bam"
+    p.write_bytes(open(paths["reads"], "rb").read())
+    assert not bamio.BamFile(str(p)).has_index
+    bamio.index_bam_csi(str(p), None, min_shift, depth)
+    f = bamio.BamFile(str(p))
+    assert f.has_index
+    # ---- the file
+    ms, dp, refs, n_no_coor = _python_csi(str(p) + ".csi")
+    assert ms == min_shift and (dp == depth if depth > 0 else (1 << (ms + 3 * dp)) >= max(f.ref_len) and (dp == 1 or (1 << (ms + 3 * (dp - 1))) < max(f.ref_len)))
+    a = with_bai.fetch(bamio.FETCH_ALL).arrays()
+    n = s.read_records.n_reads
+    cb = a["cigar_begin"]
+    ends = a["pos"][:n] + np.array([max(ref_len_of(a["cigar"][int(cb[i]): int(cb[i + 1])]), 1) for i in range(n)])
+    meta = ((1 << (3 * dp + 3)) - 1) // 7 + 1
+    assert n_no_coor == 25
+
+    def smallest_bin(b, e):
+        e -= 1
+        first, sh = ((1 << (3 * dp)) - 1) // 7, ms
+        for l in range(dp, 0, -1):
+            if b >> sh == e >> sh:
+                return first + (b >> sh)
+            first -= 1 << (3 * (l - 1))
+            sh += 3
+        return 0
+    for t, bins in enumerate(refs):
+        mine = np.flatnonzero(a["tid"][:n] == t)
+        want_bins = {smallest_bin(int(a["pos"][i]), int(ends[i])) for i in mine}
+        assert set(bins) - {meta} == want_bins
+        if len(mine):
+            assert bins[meta][1][1] == (int(np.sum((a["flag"][mine] & 4) == 0)), int(np.sum((a["flag"][mine] & 4) != 0)))
+            lo = bins[meta][1][0][0]
+            assert all(lo <= loff for b, (loff, _) in bins.items() if b != meta)   # (nothing points in front of the reference's first record)
+    # ---- the fetches
+    rng = np.random.default_rng(2)
+    seen = 0
+    for k in range(40):
+        t = int(rng.integers(0, len(f.ref_names)))
+        L = f.ref_len[t]
+        b = int(rng.integers(0, L))
+        e = min(L, b + int(rng.integers(1, 80000))) if k % 4 else L
+        got, want = f.fetch(t, b, e).arrays(), with_bai.fetch(t, b, e).arrays()
+        assert np.array_equal(got["pos"], want["pos"]) and np.array_equal(got["flag"], want["flag"]) and got["names"].tobytes() == want["names"].tobytes()
+        idx = np.flatnonzero((a["tid"][:n] == t) & (a["pos"][:n] < e) & (ends > b))
+        assert np.array_equal(got["pos"], a["pos"][idx])
+        seen += len(idx)
+    assert seen > 500
+    u = f.fetch(bamio.FETCH_UNMAPPED, flt=bamio.ONLY_UNMAPPED | bamio.KEEP_RAW)
+    u0 = with_bai.fetch(bamio.FETCH_UNMAPPED, flt=bamio.ONLY_UNMAPPED | bamio.KEEP_RAW)
+    assert u.n == 25 and u.raw()[0].tobytes() == u0.raw()[0].tobytes()
+
+
+def test_csi_geometry_too_small_is_refused(dataset, tmp_path):
+    s, paths = dataset
+    p = tmp_path / "reads.bam"
+    p.write_bytes(open(paths["reads"], "rb").read())
+    with pytest.raises(abi.PtlError):
+        bamio.index_bam_csi(str(p), None, 10, 1)      # 8 k bases per reference: the records do not fit
+    with pytest.raises(abi.PtlError):
+        bamio.index_bam_csi(str(p), None, 40, 2)
