@@ -526,3 +526,52 @@ def test_gpu_records_follow_the_documented_rules():
     ctx = helpers.gpu_context(s)
     n_multi, n_fallback, n_rev = check_record_rules(ctx, s, pb, ctx.get_contig_segments())
     assert n_multi > 100 and n_fallback > 10 and n_rev > 500
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# a3 (which contig segments a read segment is lifted through) evaluated with numpy from the reference's predicate
+# (src/read_alignment_scanner.rs:80-103 + IntRange::intersect_range, int_range.rs:56-58: `other.end >= self.start &&
+# other.start < self.end`, i.e. a segment that merely TOUCHES the read's low end counts; SURVEY parity trap 1)
+
+def check_pair_enumeration(ctx, s, pb, segs):
+    r = helpers.lift_c(ctx, pb.c, allow_panic=True)
+    b = pb.c
+    g = lambda p, n: np.ctypeslib.as_array(p, (n,))
+    ns = b.n_read_segments
+    ctg, pos, cb, cl = g(b.rseg_contig, ns), g(b.rseg_pos, ns), g(b.rseg_cigar_begin, ns), g(b.rseg_cigar_len, ns)
+    pool = g(b.cigar, int(b.n_cigar))
+    want = set()
+    n_touching = 0
+    for k in range(ns):
+        ops = pool[int(cb[k]): int(cb[k]) + int(cl[k])]
+        start = int(pos[k])
+        end = start + int(sum(int(x) >> 4 for x in ops if (int(x) & 15) in REF_OPS))
+        g0, g1 = int(segs.contig_seg_begin[ctg[k]]), int(segs.contig_seg_begin[ctg[k] + 1])
+        for q in range(g0, g1):
+            s0, s1 = int(segs.seg_seq_order_start[q]), int(segs.seg_seq_order_end[q])
+            if end >= s0 and start < s1:
+                want.add((k, q - g0))
+                n_touching += end == s0
+    assert r.n_pairs == len(want)
+    lifted = {(int(r.rec_read_segment[k]), int(r.rec_contig_segment[k])) for k in range(r.n_records) if r.rec_status[k] == 1}
+    assert lifted <= want and r.n_lifted == len(lifted)
+    return len(want), len(lifted), n_touching
+
+
+def test_oracle_and_device_code_enumerate_the_pairs_of_the_predicate():
+    import emul_lib
+    s, pb = _record_rule_set()
+    for L in (oracle_lib.load(), emul_lib.load()):
+        ctx = abi.Context(L, 0, 1)
+        ctx.set_reference(helpers.reference_arrays(s))
+        ctx.set_contig_records(s.contig_records)
+        n_pairs, n_lifted, _ = check_pair_enumeration(ctx, s, pb, ctx.get_contig_segments())
+        assert n_pairs > pb.c.n_reads and n_lifted > 0.8 * n_pairs
+
+
+@pytest.mark.gpu
+def test_gpu_enumerates_the_pairs_of_the_predicate():
+    s, pb = _record_rule_set()
+    ctx = helpers.gpu_context(s)
+    n_pairs, n_lifted, _ = check_pair_enumeration(ctx, s, pb, ctx.get_contig_segments())
+    assert n_pairs > pb.c.n_reads and n_lifted > 0.8 * n_pairs
