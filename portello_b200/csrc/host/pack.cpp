@@ -7,6 +7,9 @@
 //   ptl_region_segments / ptl_shard_units : a13 work units (lib/rust-vc-utils/src/util.rs:50-67) + LPT sharding
 //   ptl_reg2bin : lib/rust-vc-utils/src/bam_utils/util.rs:10-35
 #include <algorithm>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 #include <cstdlib>
 #include <cstring>
 #include <memory>
@@ -188,6 +191,105 @@ inline CigarScan scan_cigar(const uint32_t* c, uint32_t n, uint32_t* cluster_rea
     return {left, size - right, size, int64_t(ref), n_cl};
 }
 
+#if defined(__x86_64__) && defined(__GNUC__)
+#define PTL_HAVE_AVX2_SCAN 1
+// The same walk, eight ops per step (AVX2, chosen at run time): the three masked sums are plain vector sums; the cluster
+// starts come from two bit masks per 64 ops (I/D ops, non-empty I/D ops) through a carry-lookahead of "an open cluster
+// stays open across I/D ops", and their read offsets from an in-register prefix sum kept in `pre` (room for n + 8 words).
+// 1.5x (22 ops) to 2.3x (70 ops) the scalar walk; identical results (tests/test_host_logic.py: random CIGARs of every op).
+template <bool kClusters>
+__attribute__((target("avx2")))
+static CigarScan scan_cigar_avx2(const uint32_t* c, uint32_t n, uint32_t* cluster_read_begin, uint32_t* pre) {
+    uint64_t left = 0, right = 0, size = 0, ref = 0;
+    uint32_t i = 0, n_cl = 0;
+    while (i < n && is_clip(c[i])) { left += len_of(c[i]); size += len_of(c[i]); ++i; }
+    const __m256i zero = _mm256_setzero_si256(), one = _mm256_set1_epi32(1), two = _mm256_set1_epi32(2), m15 = _mm256_set1_epi32(15);
+    const __m256i kread = _mm256_set1_epi32(int(kReadMask)), kref = _mm256_set1_epi32(int(kRefMask)), kclip = _mm256_set1_epi32(int(kClipMask));
+    const __m256i lo32 = _mm256_set1_epi64x(0xffffffffll);
+    const __m256i lane_idx = _mm256_setr_epi32(0, 1, 2, 3, 4, 5, 6, 7);
+    const __m256i hi_half = _mm256_setr_epi32(0, 0, 0, 0, -1, -1, -1, -1), bc3 = _mm256_set1_epi32(3);
+    __m256i a_size = zero, a_ref = zero, a_right = zero;
+    uint32_t base32 = uint32_t(size);
+    uint64_t Iw = 0, Nw = 0, carry = 0;
+    uint32_t word_base = i, in_word = 0;
+    auto flush_word = [&]() {
+        if (!kClusters) return;
+        uint64_t G = Nw | (Iw & carry), P = Iw;  // carry-in opens position 0 when it is an indel op
+        // F_j = I_j & (N_j | F_{j-1}):  Kogge-Stone over "propagate through I"
+        uint64_t F = G;
+        uint64_t Pm = P;
+        F |= Pm & (F << 1); Pm &= Pm << 1;
+        F |= Pm & (F << 2); Pm &= Pm << 2;
+        F |= Pm & (F << 4); Pm &= Pm << 4;
+        F |= Pm & (F << 8); Pm &= Pm << 8;
+        F |= Pm & (F << 16); Pm &= Pm << 16;
+        F |= Pm & (F << 32);
+        uint64_t starts = Nw & ~((F << 1) | carry);
+        while (starts) {
+            const int j = __builtin_ctzll(starts);
+            cluster_read_begin[n_cl++] = pre[word_base + j];
+            starts &= starts - 1;
+        }
+        carry = F >> 63;
+        Iw = Nw = 0;
+        word_base += 64;
+        in_word = 0;
+    };
+    for (; i < n; i += 8) {
+        const uint32_t rem = n - i;
+        __m256i x;
+        if (rem >= 8) x = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(c + i));
+        else x = _mm256_maskload_epi32(reinterpret_cast<const int*>(c + i), _mm256_cmpgt_epi32(_mm256_set1_epi32(int(rem)), lane_idx));
+        const __m256i op = _mm256_and_si256(x, m15), l = _mm256_srli_epi32(x, 4);
+        const __m256i rd = _mm256_and_si256(l, _mm256_sub_epi32(zero, _mm256_and_si256(_mm256_srlv_epi32(kread, op), one)));
+        const __m256i rf = _mm256_and_si256(l, _mm256_sub_epi32(zero, _mm256_and_si256(_mm256_srlv_epi32(kref, op), one)));
+        const __m256i cl = _mm256_and_si256(l, _mm256_sub_epi32(zero, _mm256_and_si256(_mm256_srlv_epi32(kclip, op), one)));
+        a_size = _mm256_add_epi64(a_size, _mm256_add_epi64(_mm256_and_si256(rd, lo32), _mm256_srli_epi64(rd, 32)));
+        a_ref = _mm256_add_epi64(a_ref, _mm256_add_epi64(_mm256_and_si256(rf, lo32), _mm256_srli_epi64(rf, 32)));
+        a_right = _mm256_add_epi64(a_right, _mm256_add_epi64(_mm256_and_si256(cl, lo32), _mm256_srli_epi64(cl, 32)));
+        if (kClusters) {
+            const __m256i indel = _mm256_or_si256(_mm256_cmpeq_epi32(op, one), _mm256_cmpeq_epi32(op, two));
+            const uint32_t Ib = uint32_t(_mm256_movemask_ps(_mm256_castsi256_ps(indel)));
+            const uint32_t Zb = uint32_t(_mm256_movemask_ps(_mm256_castsi256_ps(_mm256_cmpeq_epi32(l, zero))));
+            Iw |= uint64_t(Ib) << in_word;
+            Nw |= uint64_t(Ib & ~Zb) << in_word;
+            __m256i t = _mm256_add_epi32(rd, _mm256_slli_si256(rd, 4));
+            t = _mm256_add_epi32(t, _mm256_slli_si256(t, 8));
+            const __m256i lowtot = _mm256_permutevar8x32_epi32(t, bc3);
+            t = _mm256_add_epi32(t, _mm256_and_si256(lowtot, hi_half));
+            const __m256i excl = _mm256_add_epi32(_mm256_sub_epi32(t, rd), _mm256_set1_epi32(int(base32)));
+            _mm256_storeu_si256(reinterpret_cast<__m256i*>(pre + i), excl);
+            base32 += uint32_t(_mm256_extract_epi32(t, 7));
+            in_word += 8;
+            if (in_word == 64) flush_word();
+        }
+    }
+    if (kClusters && in_word) flush_word();
+    alignas(32) uint64_t w[12];
+    _mm256_store_si256(reinterpret_cast<__m256i*>(w), a_size);
+    _mm256_store_si256(reinterpret_cast<__m256i*>(w + 4), a_ref);
+    _mm256_store_si256(reinterpret_cast<__m256i*>(w + 8), a_right);
+    size += w[0] + w[1] + w[2] + w[3];
+    ref += w[4] + w[5] + w[6] + w[7];
+    right += w[8] + w[9] + w[10] + w[11];
+    return {left, size - right, size, int64_t(ref), n_cl};
+}
+#endif
+
+// dispatch: the vector walk for CIGARs long enough to fill a few vectors, on CPUs that have it
+template <bool kClusters>
+inline CigarScan scan_cigar_any(const uint32_t* c, uint32_t n, uint32_t* cluster_read_begin, std::vector<uint32_t>& pre) {
+#ifdef PTL_HAVE_AVX2_SCAN
+    static const bool avx2 = __builtin_cpu_supports("avx2") && !std::getenv("PTL_PACK_SCALAR");
+    if (avx2 && n >= 12u) {
+        if (kClusters && pre.size() < size_t(n) + 8u) pre.resize(std::max<size_t>(size_t(n) + 8u, pre.size() * 2));
+        return scan_cigar_avx2<kClusters>(c, n, cluster_read_begin, pre.data());
+    }
+#endif
+    (void)pre;
+    return scan_cigar<kClusters>(c, n, cluster_read_begin);
+}
+
 // The 16 nibbles the shifter may look at for a cluster whose walk starts at read_view[read_end - 1]: nibble q (bits 4q..)
 // is read_view[read_end - 1 - q]; steps outside the read stay 0 (the kernel reports the reference's panic before using them).
 inline uint64_t window_bits(const uint8_t* sq, uint32_t len, uint32_t read_end, bool flip, const uint8_t* pool_end) {
@@ -223,6 +325,7 @@ struct PackScratch {
     std::vector<Seg> segs, tmp;
     std::vector<uint32_t> seg_begin, kept, win_begin, seg_size;
     std::vector<uint32_t> cluster_read_begin;  // per I/D cluster, CIGAR order: read bases consumed before its first op
+    std::vector<uint32_t> prefix;              // scratch of the vector CIGAR walk
     Ops sa_pool;
 };
 
@@ -329,7 +432,7 @@ static int pack_impl(const ptl_read_records* recs, uint32_t first, uint32_t coun
             if (!sa) {
                 // one segment: the primary record itself
                 if (contig_wants_windows) rb_room(ncg);
-                const CigarScan sc = contig_wants_windows ? scan_cigar<true>(cg, ncg, rb.data() + n_rb) : scan_cigar<false>(cg, ncg, nullptr);
+                const CigarScan sc = contig_wants_windows ? scan_cigar_any<true>(cg, ncg, rb.data() + n_rb, S.prefix) : scan_cigar_any<false>(cg, ncg, nullptr, S.prefix);
                 const bool rev = flag & 0x10;
                 Seg p{};
                 if (!rev) { p.so_start = uint32_t(sc.left); p.so_end = uint32_t(sc.right); }
@@ -355,7 +458,7 @@ static int pack_impl(const ptl_read_records* recs, uint32_t first, uint32_t coun
                     if (contig_wants_windows) {
                         const uint32_t* c = g.from_primary ? cg : sa_pool.data() + g.cig_off;
                         rb_room(g.cig_len);
-                        const CigarScan sc = scan_cigar<true>(c, g.cig_len, rb.data() + n_rb);
+                        const CigarScan sc = scan_cigar_any<true>(c, g.cig_len, rb.data() + n_rb, S.prefix);
                         win_begin.push_back(uint32_t(n_rb));
                         if (sc.n_clusters && wants_windows(g.contig, g.pos, g.pos + sc.ref)) n_rb += sc.n_clusters;
                         seg_size.push_back(uint32_t(sc.size));

@@ -403,3 +403,53 @@ def test_packer_on_random_cigars_equals_oracle_packer_and_window_walk(seed):
             assert [int(v) for v in win[b.rseg_win_begin[k]: b.rseg_win_begin[k + 1]]] == exp, (i, rows[i])
             n_win += len(exp)
     assert n_win == b.n_indel_win and n_win > 1000
+
+
+def test_vector_and_scalar_cigar_walks_pack_the_same_batch():
+    """ptl_pack_batch_ex walks long CIGARs eight ops at a time where the CPU has AVX2 (PTL_PACK_SCALAR=1 switches that off):
+    both must produce the same batch, windows included, on reads of 20 to 600 ops and on the random CIGARs of every op kind."""
+    import hashlib
+    import subprocess
+    import sys
+    code = r'''
+import hashlib, sys
+sys.path.insert(0, "tests")
+import numpy as np
+import test_host_logic as T
+from portello_b200 import lib, synth
+h = hashlib.sha1()
+def add(c):
+    for k, v in sorted(T._batch_arrays(c).items()):
+        for a in (v if isinstance(v, list) else [v]):
+            h.update(np.asarray(a).tobytes() if not isinstance(a, bytes) else a)
+    if c.n_indel_win:
+        h.update(np.ctypeslib.as_array(c.indel_win, (int(c.n_indel_win),)).tobytes())
+        h.update(np.ctypeslib.as_array(c.rseg_win_begin, (int(c.n_read_segments) + 1,)).tobytes())
+L = lib.load()
+for name, kw in (("tiny", dict(seed=3, n_reads=1500, read_sa_frac=0.2)), ("stress", dict(n_reads=60))):
+    s = synth.make(name, **kw)
+    for w in (None, True, L.prepare_contig_records(s.contig_records)):
+        add(lib.PackedBatch(L, s.read_records, 0, s.read_records.n_reads, s.contig_names, windows=w).c)
+rng = np.random.default_rng(9)
+rows = []
+while len(rows) < 300:
+    cig = T._random_cigar(rng, 90)
+    row = (int(rng.choice([0, 16])), int(rng.integers(0, 5000)), 0, cig, max(T.helpers.cigar_read_len(cig), 1), None)
+    try:
+        lib.PackedBatch(L, T._records([row]), 0, 1, ["ctg0", "ctg1"], windows=True)
+        rows.append(row)
+    except Exception:
+        pass
+add(lib.PackedBatch(L, T._records(rows), 0, len(rows), ["ctg0", "ctg1"], windows=True).c)
+print(h.hexdigest())
+'''
+    out = []
+    for scalar in ("", "1"):
+        env = dict(os.environ)
+        env.pop("PTL_PACK_SCALAR", None)
+        if scalar:
+            env["PTL_PACK_SCALAR"] = "1"
+        r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        out.append(r.stdout.strip().splitlines()[-1])
+    assert out[0] == out[1] and len(out[0]) == 40
