@@ -156,7 +156,7 @@ def test_emulated_left_shift_vectors(emul, v):
 @pytest.mark.parametrize("name,kw", [
     ("tiny", dict(seed=53, n_reads=3000, rev_contig_frac=0.7, read_cluster_frac=0.2)),
     ("config1", dict(n_reads=3000)),
-    ("stress", dict(n_reads=300)),
+    ("stress", dict(n_reads=120)),
 ], ids=["tiny-reverse-clusters", "config1", "stress"])
 def test_emulated_indel_windows_change_nothing(emul, name, kw):
     """Batches packed WITH indel windows (ptl_pack_batch_ex: the first 16 read bases of every homology walk travel with
