@@ -70,7 +70,7 @@ void error(const std::string& m) { log_line("ERROR", m); }
 struct Settings {
     std::string assembly_to_ref, read_to_assembly, remapped_out, unassembled_out, ref, target_region;
     int threads = 0, gpu = 0;
-    uint32_t batch_reads = 65536;
+    uint32_t batch_reads = 16384;
 };
 
 const char* kHelp =
@@ -87,7 +87,7 @@ const char* kHelp =
     "      --target-region <REGION>          (debugging option of the reference; not supported by this build)\n"
     "      --threads <THREAD_COUNT>          Number of threads to use. Defaults to all logical cpus detected\n"
     "      --gpu <INDEX>                     CUDA device to use [default: 0]\n"
-    "      --batch-reads <N>                 Reads per GPU batch [default: 65536]\n"
+    "      --batch-reads <N>                 Reads per GPU batch [default: 16384]\n"
     "  -h, --help                            Print help\n"
     "  -V, --version                         Print version\n";
 
@@ -303,10 +303,12 @@ int main(int argc, char** argv) {
     }
     // Work units: (contig x window), records assigned by their start (:403-406, :495-535).  The reference's window is 20 Mb;
     // an assembly too small to give every worker a few of those is cut finer (any partition by start position yields the
-    // same records; the output is unsorted either way).
+    // same records; the output is unsorted either way) ...
     uint64_t total_len = 0;
     for (uint64_t l : contig_len) total_len += l;
-    const uint64_t window = std::min<uint64_t>(20000000ull, std::max<uint64_t>(1000000ull, total_len / (4ull * uint64_t(n_workers)) + 1));
+    // ... and capped at 4 Mb: a worker holds the decoded records of its window (~45 KB per 15 kb read, 30x coverage: 0.9 GB
+    // per 20 Mb), and there is one worker per thread.
+    const uint64_t window = std::min<uint64_t>(4000000ull, std::max<uint64_t>(1000000ull, total_len / (4ull * uint64_t(n_workers)) + 1));
     struct Unit { uint32_t contig; uint64_t b, e; };
     std::vector<Unit> units;
     for (uint32_t c = 0; c < contig_len.size(); ++c) {
