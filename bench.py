@@ -666,7 +666,11 @@ def main():
     extra = {}
     if rank == 0 and world == 1 and not args.no_assemble:
         import bench_records
-        extra = bench_records.measure(args, ctx, s, L, chunk_sets[False][0], peak)
+        try:  # (a by-product of the run: the record path must not cost the liftover line if it fails)
+            extra = bench_records.measure(args, ctx, s, L, chunk_sets[False][0], peak)
+        except Exception as e:  # noqa: BLE001
+            extra = {"assemble_records": {"error": f"{type(e).__name__}: {e}"}}
+            print(f"bench_records failed: {e}", file=sys.stderr)
 
     # ---------------------------------------------------------------- CPU baseline (rank 0, N=1 only)
     cpu = None
