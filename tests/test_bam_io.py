@@ -5,6 +5,7 @@ region fetches are compared with a brute-force overlap filter (what IndexedReade
 src/read_alignment_scanner.rs:382-393), and the files themselves are parsed by an independent pure-Python reader
 (gzip module + struct) so that writer and reader cannot agree on a private dialect."""
 import gzip
+import os
 import struct
 
 import numpy as np
@@ -308,3 +309,61 @@ def test_csi_geometry_too_small_is_refused(dataset, tmp_path):
         bamio.index_bam_csi(str(p), None, 10, 1)      # 8 k bases per reference: the records do not fit
     with pytest.raises(abi.PtlError):
         bamio.index_bam_csi(str(p), None, 40, 2)
+
+
+def test_corrupted_bam_and_index_files_error_out_cleanly(dataset, tmp_path):
+    """Random corruption of the BAM (BGZF headers, record lengths, header fields), the .bai and the .csi (bytes flipped,
+    files cut short, 32-bit fields set to extreme values): open / region fetch / unmapped fetch / full scan must either work
+    or report an error -- never crash or hang.  The mutations run in one child process, so a crash fails this test only."""
+    import subprocess
+    import sys
+    s, paths = dataset
+    code = r'''
+import gzip, os, random, sys
+sys.path.insert(0, sys.argv[1])
+from portello_b200 import abi, bamio
+bam, work = sys.argv[2], sys.argv[3]
+bamio.index_bam_csi(bam, work + ".orig.csi", 14, 5)
+orig = [open(bam, "rb").read(), open(bam + ".bai", "rb").read(), open(work + ".orig.csi", "rb").read()]
+rng = random.Random(7)
+n_err = n_ok = 0
+for it in range(60):
+    kind = it % 3
+    for f in (work, work + ".bai", work + ".csi"):
+        if os.path.exists(f):
+            os.remove(f)
+    tgt = bytearray(gzip.decompress(orig[2])) if kind == 2 else bytearray(orig[kind])
+    mode = rng.random()
+    if mode < 0.6:
+        for _ in range(rng.randint(1, 4)):
+            tgt[rng.randrange(len(tgt))] = rng.randrange(256)
+    elif mode < 0.8:
+        del tgt[rng.randrange(len(tgt)):]
+    else:
+        p = rng.randrange(max(1, len(tgt) - 8))
+        tgt[p:p + 4] = (0xffffffff if rng.random() < 0.5 else 0x7fffffff).to_bytes(4, "little")
+    open(work, "wb").write(bytes(tgt) if kind == 0 else orig[0])
+    if kind == 2:
+        open(work + ".csi", "wb").write(bamio.bgzf_compress(bytes(tgt)))
+    else:
+        open(work + ".bai", "wb").write(bytes(tgt) if kind == 1 else orig[1])
+    print("case", it, kind, flush=True)
+    try:
+        f = bamio.BamFile(work)
+        if f.has_index:
+            for t in range(len(f.ref_names)):
+                f.fetch(t, 0, f.ref_len[t]).n
+                f.fetch(t, 1000, 50000, bamio.START_IN_REGION).n
+            f.fetch(bamio.FETCH_UNMAPPED, flt=bamio.ONLY_UNMAPPED).n
+        f.fetch(bamio.FETCH_ALL).n
+        n_ok += 1
+    except abi.PtlError:
+        n_err += 1
+print("done", n_ok, n_err)
+'''
+    r = subprocess.run([sys.executable, "-c", code, os.path.dirname(os.path.dirname(os.path.abspath(__file__))), paths["reads"], str(tmp_path / "w.bam")],
+                       capture_output=True, text=True, timeout=600)
+    tail = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else ""
+    assert r.returncode == 0 and tail.startswith("done"), (r.returncode, tail, r.stderr[-1500:])
+    n_ok, n_err = int(tail.split()[1]), int(tail.split()[2])
+    assert n_ok + n_err == 60 and n_err >= 10      # (corruption is noticed; some mutations land in bytes that do not matter)
