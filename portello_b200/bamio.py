@@ -167,7 +167,7 @@ def load_fasta(path: str, threads: int = 4):
         for i in range(d.ptl_fasta_n(h)):
             n = C.c_uint64()
             p = d.ptl_fasta_seq(h, i, C.byref(n))
-            out.append((d.ptl_fasta_name(h, i).decode(), np.ctypeslib.as_array(p, (int(n.value),)).copy() if n.value else np.zeros(0, np.uint8)))
+            out.append((d.ptl_fasta_name(h, i).decode("utf-8", "surrogateescape"), np.ctypeslib.as_array(p, (int(n.value),)).copy() if n.value else np.zeros(0, np.uint8)))
         return out
     finally:
         d.ptl_fasta_free(h)
