@@ -473,7 +473,7 @@ class Context:
 
     def _check(self, rc: int, allow=()):
         if rc != PTL_OK and rc not in allow:
-            raise PtlError(rc, self.lib._last_error(self.h).decode())
+            raise PtlError(rc, self.lib._last_error(self.h).decode("utf-8", "replace"))
         return rc
 
     def set_reference(self, chroms: Sequence[np.ndarray]):

@@ -56,7 +56,7 @@ def _dll():
 
 def _check(rc):
     if rc != 0:
-        raise PtlError(rc, _dll().ptl_bam_last_error().decode())
+        raise PtlError(rc, _dll().ptl_bam_last_error().decode("utf-8", "replace"))
 
 
 class Decoded:

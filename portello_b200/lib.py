@@ -107,7 +107,7 @@ class ProductLib(LiftLib):
         h = C.c_void_p()
         rc = self.dll.ptl_prepare_contig_records(C.byref(recs_c), C.byref(h))
         if rc != 0:
-            raise PtlError(rc, self.dll.ptl_prepare_last_error().decode())
+            raise PtlError(rc, self.dll.ptl_prepare_last_error().decode("utf-8", "replace"))
         try:
             v = ContigSegmentsC()
             self.dll.ptl_prepared_contigs_view(h, C.byref(v))
@@ -120,7 +120,7 @@ class ProductLib(LiftLib):
         c = segs.to_c()
         rc = self.dll.ptl_prepare_raw_contig_segments(C.byref(c), C.byref(h))
         if rc != 0:
-            raise PtlError(rc, self.dll.ptl_prepare_last_error().decode())
+            raise PtlError(rc, self.dll.ptl_prepare_last_error().decode("utf-8", "replace"))
         try:
             v = ContigSegmentsC()
             self.dll.ptl_prepared_contigs_view(h, C.byref(v))
@@ -177,7 +177,7 @@ class PackedBatch:
             segs_c = windows.to_c()
             rc = lib.dll.ptl_pack_batch_ex(C.byref(recs_c), first, count, len(contig_names), names, int(pinned), 2, C.byref(segs_c), C.byref(self.h))
         if rc != 0:
-            raise PtlError(rc, lib.dll.ptl_pack_last_error().decode())
+            raise PtlError(rc, lib.dll.ptl_pack_last_error().decode("utf-8", "replace"))
         self.c = BatchC()
         lib.dll.ptl_packed_batch_view(self.h, C.byref(self.c))
         self.c._owner = self  # the view must keep the arena alive (`pack(...).c` would otherwise dangle)
@@ -194,7 +194,7 @@ class PackedBatch:
         rc = self.lib.dll.ptl_pack_batch_into(self.h, C.byref(recs_c), first, count, len(self._names), self._names, self._mode,
                                               C.byref(self._segs_c) if self._segs_c is not None else None)
         if rc != 0:
-            raise PtlError(rc, self.lib.dll.ptl_pack_last_error().decode())
+            raise PtlError(rc, self.lib.dll.ptl_pack_last_error().decode("utf-8", "replace"))
         self._recs = recs_c
         self.lib.dll.ptl_packed_batch_view(self.h, C.byref(self.c))
         self.c._owner = self
