@@ -229,6 +229,10 @@ struct DevTotals {
     unsigned int n_long;                 // length of DevWork::long_list
 };
 
+// [off, off + n) inside a pool of `size` elements, without the sum (a caller's offset may be anything, 2^64 - 1 included:
+// off + n would wrap and pass; found by tools/fuzz/fuzz_batch_through_device_code.py under AddressSanitizer)
+PTL_HD inline bool range_in_pool(uint64_t off, uint64_t n, uint64_t size) { return off <= size && n <= size - off; }
+
 // OVF_INVALID: the batch itself is malformed (an index outside its pool); reported by ptl_lift_wait as PTL_ERR_INVALID_ARG
 enum : unsigned { OVF_PAIRS = 1, OVF_SCRATCH = 2, OVF_RESULT = 4, OVF_INVALID = 16 };
 static_assert(sizeof(DevTotals) <= kResultHeaderBytes, "the totals are the header of the result arena");

@@ -106,13 +106,13 @@ __device__ __forceinline__ void table_build_warp_body(const DevStatic& S, uint32
 __device__ __forceinline__ void pair_count_warp_body(const DevStatic& S, const DevBatch& B, const DevWork& W, DevTotals* T, uint32_t r, uint32_t lane) {
 
     const uint32_t s0 = B.read_seg_begin[r], s1 = B.read_seg_begin[r + 1];
-    bool bad = s0 > s1 || s1 > B.n_rsegs || B.read_seq_off[r] + (uint64_t(B.read_seq_len[r]) + 1u) / 2u > B.seq4_bytes;
+    bool bad = s0 > s1 || s1 > B.n_rsegs || !range_in_pool(B.read_seq_off[r], (uint64_t(B.read_seq_len[r]) + 1u) / 2u, B.seq4_bytes);
     for (uint32_t s = s0; s < s1 && s < B.n_rsegs; ++s) {
         if (lane == 0) W.rseg_read[s] = r;
         const uint64_t c0 = B.rseg_cigar_begin[s];
         const uint32_t n = B.rseg_cigar_len[s];
         const int64_t pos = B.rseg_pos[s];
-        if (bad || B.rseg_contig[s] >= S.n_contigs || c0 + n > B.n_cigar || pos < 0 || pos > 0x7fffffffLL) {
+        if (bad || B.rseg_contig[s] >= S.n_contigs || !range_in_pool(c0, n, B.n_cigar) || pos < 0 || pos > 0x7fffffffLL) {
             bad = true;
             if (lane == 0) {
                 W.rseg_ref_len[s] = 0;

@@ -66,6 +66,9 @@ def malformed_batches(s):
     out.append(("position int32", clone("rseg_pos", np.int64, ns, lambda a: a.__setitem__(3, 2**31))))
     out.append(("bases", clone("read_seq_off", np.uint64, n, lambda a: a.__setitem__(n - 1, int(b.seq4_bytes)))))
     out.append(("segment csr", clone("read_seg_begin", np.uint32, n + 1, lambda a: a.__setitem__(5, ns + 9))))
+    # offsets whose sum with the length wraps around 2^64 (found by tools/fuzz/fuzz_batch_through_device_code.py under ASAN)
+    out.append(("cigar range wrap", clone("rseg_cigar_begin", np.uint64, ns, lambda a: a.__setitem__(ns // 2, 2**64 - 1))))
+    out.append(("bases wrap", clone("read_seq_off", np.uint64, n, lambda a: a.__setitem__(n // 2, 2**64 - 1))))
     return out
 
 
