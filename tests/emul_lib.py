@@ -12,6 +12,8 @@ SO = os.path.join(HERE, "_build", "libptl_emul.so")
 
 
 def build() -> str:
+    if os.environ.get("PTL_EMUL_SO"):  # another build of the same sources (e.g. -fsanitize=address, see tools/fuzz/README.md)
+        return os.environ["PTL_EMUL_SO"]
     r = subprocess.run(["make", "-C", HERE], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"emulation build failed:\n{r.stdout[-3000:]}\n{r.stderr[-3000:]}")
