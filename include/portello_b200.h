@@ -184,7 +184,8 @@ typedef struct ptl_contig_records {
     const uint64_t* cigar_begin;       /* [n_records+1] */
     const uint32_t* cigar;
     const char* const* sa_tag;         /* [n_records] SA:Z value or NULL */
-    const uint8_t* const* seq;         /* [n_records] ASCII decode of the stored bases (needed on primary records), else NULL */
+    const uint8_t* const* seq;         /* [n_records] ASCII decode of the stored bases of a primary record: contig_len[contig_id]
+                                        * bytes (the whole contig; ptl_scan_contig_bam checks that), else NULL */
     uint32_t n_contigs;
     const uint64_t* contig_len;        /* [n_contigs] */
     const char* const* contig_names;   /* [n_contigs] (error messages only) */

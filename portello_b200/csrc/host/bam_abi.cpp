@@ -218,6 +218,11 @@ int ptl_scan_contig_bam(const ptl_bam_file* bam, uint32_t n_contigs, const char*
                 std::vector<uint8_t> ascii;
                 if (!(d.flag[r] & 0x800)) {  // add_primary_read decodes record.seq() (mod.rs:113-125)
                     const uint32_t L = d.seq_len[r];
+                    // the contig preparation reads contig_len bases of a primary record (rev_contig_seq): a record that holds
+                    // another number of bases (and is not simply without them) cannot be used
+                    if (L != 0 && uint64_t(L) != contig_len[it->second])
+                        throw InputError("contig '" + qname + "': the primary alignment record holds " + std::to_string(L) + " bases, the read-to-assembly header gives the contig " +
+                                         std::to_string(contig_len[it->second]));
                     ascii.resize(L);
                     const uint8_t* p = d.seq4.data() + d.seq_off[r];
                     for (uint32_t i = 0; i < L; ++i) ascii[i] = uint8_t(kDecode[(i & 1u) ? (p[i >> 1] & 0xf) : (p[i >> 1] >> 4)]);
@@ -230,7 +235,7 @@ int ptl_scan_contig_bam(const ptl_bam_file* bam, uint32_t n_contigs, const char*
         for (size_t i = 0; i < n; ++i) {
             const bool has_sa = !s->sa_s[i].empty();
             s->sa.push_back(has_sa ? s->sa_s[i].c_str() : nullptr);
-            s->seq.push_back((s->flag[i] & 0x800) ? nullptr : s->seq_s[i].data());
+            s->seq.push_back(((s->flag[i] & 0x800) || s->seq_s[i].empty()) ? nullptr : s->seq_s[i].data());
         }
         for (uint32_t i = 0; i < n_contigs; ++i) {
             s->contig_len.push_back(contig_len[i]);
