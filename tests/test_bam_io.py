@@ -367,3 +367,14 @@ print("done", n_ok, n_err)
     assert r.returncode == 0 and tail.startswith("done"), (r.returncode, tail, r.stderr[-1500:])
     n_ok, n_err = int(tail.split()[1]), int(tail.split()[2])
     assert n_ok + n_err == 60 and n_err >= 10      # (corruption is noticed; some mutations land in bytes that do not matter)
+
+
+def test_contig_record_with_another_base_count_than_its_contig_is_refused(dataset):
+    """The contig preparation reads contig_len bases of every primary contig record (rev_contig_seq, mod.rs:113-125): the scan
+    must refuse a record whose sequence has another length instead of letting it read past the record."""
+    s, paths = dataset
+    f = bamio.BamFile(paths["contigs"])
+    lens = np.asarray(s.contig_lengths(), np.uint64)
+    f.scan_contigs(s.contig_names, lens)                      # consistent: fine
+    with pytest.raises(abi.PtlError, match="bases"):
+        f.scan_contigs(s.contig_names, lens + np.uint64(7))   # the read-to-assembly header claims longer contigs
