@@ -293,6 +293,24 @@ std::vector<HostContig> assemble_from_records(const ptl_contig_records& r) {
 }
 
 std::vector<HostContig> contigs_from_flat(const ptl_contig_segments& s) {
+    // a public entry point (ptl_set_contig_segments / ptl_prepare_raw_contig_segments): the two CSR arrays and the per-segment
+    // fields are checked before anything is indexed with them (tools/fuzz/fuzz_segments_through_device_code.py)
+    if (s.n_contigs && (!s.contig_len || !s.contig_seg_begin)) throw InputError("contig segments: missing contig arrays");
+    if (s.n_segments && (!s.seg_seq_order_start || !s.seg_seq_order_end || !s.seg_chrom_index || !s.seg_pos || !s.seg_is_fwd || !s.seg_mapq || !s.seg_cigar_begin || !s.cigar))
+        throw InputError("contig segments: missing segment arrays");
+    if (s.n_contigs) {
+        if (s.contig_seg_begin[0] != 0 || s.contig_seg_begin[s.n_contigs] != s.n_segments) throw InputError("contig segments: contig_seg_begin does not span the segments");
+        for (uint32_t c = 0; c < s.n_contigs; ++c)
+            if (s.contig_seg_begin[c] > s.contig_seg_begin[c + 1]) throw InputError("contig segments: contig_seg_begin is not monotone");
+    } else if (s.n_segments) {
+        throw InputError("contig segments: segments without contigs");
+    }
+    for (uint32_t k = 0; k < s.n_segments; ++k) {
+        if (s.seg_cigar_begin[k] > s.seg_cigar_begin[k + 1]) throw InputError("contig segments: seg_cigar_begin is not monotone");
+        if (s.seg_chrom_index[k] < 0) throw InputError("contig segments: negative chromosome index");
+        if (s.seg_pos[k] < 0 || s.seg_pos[k] > 0x7fffffffLL) throw InputError("contig segments: position outside the BAM range");
+        if (s.seg_seq_order_start[k] > s.seg_seq_order_end[k]) throw InputError("contig segments: sequencing-order interval is reversed");
+    }
     std::vector<HostContig> contigs(s.n_contigs);
     for (uint32_t c = 0; c < s.n_contigs; ++c) {
         HostContig& ct = contigs[c];

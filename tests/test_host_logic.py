@@ -453,3 +453,31 @@ print(h.hexdigest())
         assert r.returncode == 0, r.stderr[-2000:]
         out.append(r.stdout.strip().splitlines()[-1])
     assert out[0] == out[1] and len(out[0]) == 40
+
+
+def test_malformed_contig_segments_are_refused():
+    """ptl_set_contig_segments / ptl_prepare_raw_contig_segments are public entry points: CSR arrays that do not span their pools,
+    negative chromosome indices and positions outside the BAM range must be reported before anything is indexed with them
+    (found by tools/fuzz/fuzz_segments_through_device_code.py under AddressSanitizer)."""
+    import copy
+    s = synth.make("tiny", seed=29, n_reads=10, junction_per_mb=15)
+    L = lib.load()
+    good = L.prepare_contig_records(s.contig_records)
+    L.prepare_raw_contig_segments(good)
+    n_seg = len(good.seg_pos)
+
+    def broken(field, index, value):
+        g = copy.copy(good)
+        g._keep = []
+        a = np.array(getattr(g, field), copy=True)
+        a[index] = value
+        setattr(g, field, a)
+        return g
+    for field, index, value in (("contig_seg_begin", 1, 2878940490), ("contig_seg_begin", len(good.contig_seg_begin) - 1, n_seg + 3), ("contig_seg_begin", 0, 1),
+                                ("seg_cigar_begin", n_seg // 2, 2**40), ("seg_chrom_index", 0, -5), ("seg_pos", 1, -1), ("seg_pos", 1, 2**31),
+                                ("seg_seq_order_start", 0, 2**32 - 1)):
+        with pytest.raises(abi.PtlError):
+            L.prepare_raw_contig_segments(broken(field, index, value))
+        ectx = abi.Context(__import__("emul_lib").load(), 0, 1)
+        with pytest.raises(abi.PtlError):
+            ectx.set_contig_segments(broken(field, index, value))
