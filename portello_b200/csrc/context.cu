@@ -602,6 +602,10 @@ int ptl_set_reference(ptl_ctx* ctx, uint32_t n_chrom, const uint64_t* chrom_len,
     if (!ctx || (n_chrom && (!chrom_len || !chrom_seq))) return PTL_ERR_INVALID_ARG;
     return guarded(ctx, [&]() {
         cudaStream_t st = ctx->setup_stream;
+        // (segments may be installed first: they must fit the reference whichever call comes second)
+        if (ctx->have_segments)
+            for (int32_t c : ctx->flat.chrom)
+                if (c < 0 || uint32_t(c) >= n_chrom) throw InputError("the reference has fewer chromosomes than the installed contig segments use");
         // chromosomes are packed back to back (byte loads need no alignment); chrom_off[c+1]-chrom_off[c] is the exact length
         std::vector<uint64_t> off(size_t(n_chrom) + 1, 0);
         for (uint32_t c = 0; c < n_chrom; ++c) off[c + 1] = off[c] + chrom_len[c];

@@ -323,6 +323,9 @@ const char* ptl_emul_last_error(const ptl_ctx* ctx) { return ctx ? ctx->err.c_st
 
 int ptl_emul_set_reference(ptl_ctx* ctx, uint32_t n_chrom, const uint64_t* chrom_len, const uint8_t* const* chrom_seq) {
     if (!ctx || (n_chrom && (!chrom_len || !chrom_seq))) return PTL_ERR_INVALID_ARG;
+    if (ctx->have_segments)  // (as ptl_set_reference: segments installed first must fit the reference)
+        for (int32_t c : ctx->flat.chrom)
+            if (c < 0 || uint32_t(c) >= n_chrom) return fail(ctx, PTL_ERR_INPUT, "the reference has fewer chromosomes than the installed contig segments use");
     ctx->chrom_off.assign(size_t(n_chrom) + 1, 0);
     for (uint32_t c = 0; c < n_chrom; ++c) ctx->chrom_off[c + 1] = ctx->chrom_off[c] + chrom_len[c];
     ctx->ref.assign(ctx->chrom_off[n_chrom] + 32, 0);

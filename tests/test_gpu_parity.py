@@ -310,3 +310,16 @@ def test_two_host_threads_drive_two_slots():
     for (slot, rep, i), r in got.items():
         assert r.diff(want[i]) is None, (slot, rep, i)
     assert gctx.launch_count() - l0 == serial > 0  # the launch counter is atomic: no lost increments
+
+
+def test_reference_set_after_the_segments_must_cover_their_chromosomes():
+    """ptl_set_reference after ptl_set_contig_records: a reference with fewer chromosomes than the segments use is refused."""
+    s = synth.make("tiny", seed=4, n_reads=10)
+    ref = helpers.reference_arrays(s)
+    ctx = lib.GpuContext(0, 1)
+    ctx.set_contig_records(s.contig_records)
+    with pytest.raises(abi.PtlError):
+        ctx.set_reference(ref[:1])
+    ctx.set_reference(ref)
+    pb = helpers.pack(s)
+    assert helpers.lift_c(ctx, pb.c).diff(helpers.lift_c(helpers.oracle_context(s), pb.c)) is None

@@ -481,3 +481,21 @@ def test_malformed_contig_segments_are_refused():
         ectx = abi.Context(__import__("emul_lib").load(), 0, 1)
         with pytest.raises(abi.PtlError):
             ectx.set_contig_segments(broken(field, index, value))
+
+
+def test_reference_set_after_the_segments_must_cover_their_chromosomes():
+    """Segments may be installed before the reference; a reference with fewer chromosomes than they use is refused by whichever
+    call comes second (the simplify stage indexes the chromosome table with the segment's chromosome)."""
+    import emul_lib
+    s = synth.make("tiny", seed=4, n_reads=10)          # two chromosomes
+    ref = helpers.reference_arrays(s)
+    ctx = abi.Context(emul_lib.load(), 0, 1)
+    ctx.set_contig_records(s.contig_records)
+    assert int(ctx.get_contig_segments().seg_chrom_index.max()) == 1
+    with pytest.raises(abi.PtlError):
+        ctx.set_reference(ref[:1])
+    ctx.set_reference(ref)
+    ctx2 = abi.Context(emul_lib.load(), 0, 1)
+    ctx2.set_reference(ref[:1])
+    with pytest.raises(abi.PtlError):
+        ctx2.set_contig_records(s.contig_records)
