@@ -213,6 +213,19 @@ static inline uint8_t comp_base(uint8_t x) {  // seq_util.rs:1-15
 
 // scan_contig_bam minus BAM I/O (mod.rs:186-240 dispatch, :360-439 fill-in); trim/join are separate calls.
 std::vector<HostContig> assemble_from_records(const ptl_contig_records& r) {
+    // a public entry point (ptl_set_contig_records / ptl_prepare_contig_records): the arrays are checked before they index
+    // anything (tools/fuzz/fuzz_contig_records.py).  cigar_begin[n_records] is the size of the caller's CIGAR pool.
+    if (r.n_records && (!r.contig_id || !r.flag || !r.tid || !r.pos || !r.mapq || !r.cigar_begin)) throw InputError("contig records: missing arrays");
+    if (r.n_contigs && !r.contig_len) throw InputError("contig records: missing contig lengths");
+    if (r.n_ref_chrom && !r.ref_chrom_names) throw InputError("contig records: missing reference names");
+    for (uint32_t i = 0; i < r.n_records; ++i) {
+        if (r.cigar_begin[i] > r.cigar_begin[i + 1] || r.cigar_begin[i + 1] > r.cigar_begin[r.n_records]) throw InputError("contig records: cigar_begin is not monotone");
+        if (r.cigar_begin[i + 1] > r.cigar_begin[i] && !r.cigar) throw InputError("contig records: missing CIGAR pool");
+        if (r.flag[i] & (0x4 | 0x100)) continue;  // (skipped below: their other fields are never looked at)
+        if (r.contig_id[i] >= r.n_contigs) throw InputError("contig record with an out-of-range contig id");
+        if (r.tid[i] < 0 || uint32_t(r.tid[i]) >= r.n_ref_chrom) throw InputError("contig record with a reference index outside the header");
+        if (r.pos[i] < 0 || r.pos[i] > 0x7fffffffLL) throw InputError("contig record position outside the BAM range");
+    }
     std::vector<HostContig> contigs(r.n_contigs);
     for (uint32_t i = 0; i < r.n_contigs; ++i) {
         contigs[i].length = r.contig_len[i];

@@ -499,3 +499,29 @@ def test_reference_set_after_the_segments_must_cover_their_chromosomes():
     ctx2.set_reference(ref[:1])
     with pytest.raises(abi.PtlError):
         ctx2.set_contig_records(s.contig_records)
+
+
+def test_malformed_contig_records_are_refused():
+    """ptl_prepare_contig_records / ptl_set_contig_records are public entry points: a CIGAR CSR that is not monotone, a contig id
+    or reference index outside its table and a position outside the BAM range are reported before they index anything
+    (found by tools/fuzz/fuzz_contig_records.py under AddressSanitizer)."""
+    s = synth.make("tiny", seed=37, n_reads=10, junction_per_mb=20)
+    L = lib.load()
+    r0 = s.contig_records
+    n = r0.n_records
+    L.prepare_contig_records(r0)
+    types = dict(abi.ContigRecordsC._fields_)
+    for field, count, index, value in (("cigar_begin", n + 1, n // 2, 2**50), ("cigar_begin", n + 1, 1, 0 if int(r0.cigar_begin[1]) else None),
+                                       ("contig_id", n, 0, r0.n_contigs + 7), ("tid", n, 0, r0.n_ref_chrom + 3), ("tid", n, 0, -2),
+                                       ("pos", n, 0, -1), ("pos", n, 0, 2**31)):
+        if value is None:
+            continue
+        arr = np.ctypeslib.as_array(getattr(r0, field), (count,)).copy()
+        if field == "cigar_begin" and index == 1:
+            arr[2] = 0                                    # (a later entry below an earlier one)
+        else:
+            arr[index] = value
+        r = abi.ContigRecordsC.from_buffer_copy(r0)
+        setattr(r, field, arr.ctypes.data_as(types[field]))
+        with pytest.raises(abi.PtlError):
+            L.prepare_contig_records(r)
