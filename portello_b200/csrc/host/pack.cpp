@@ -409,7 +409,19 @@ static int pack_impl(const ptl_read_records* recs, uint32_t first, uint32_t coun
         size_t n_rb = 0;  // entries of rb in use (a cluster per op at most: room is made ahead of every walk)
         auto rb_room = [&](size_t ops) { if (rb.size() < n_rb + ops) rb.resize(std::max(n_rb + ops, rb.size() * 2)); };
         std::unique_ptr<NameMap> names;  // built on the first SA tag
-        const uint64_t cig0 = recs->cigar_begin[first], cig1 = recs->cigar_begin[first + count];
+        // (the records are caller memory: the CIGAR CSR is checked before it sizes or indexes anything;
+        //  cigar_begin[n_reads] is the size of the caller's pool -- tools/fuzz/fuzz_read_records.py)
+        if (recs->n_reads && (!recs->cigar_begin || !recs->flag || !recs->tid || !recs->pos || !recs->mapq || !recs->bin || !recs->seq_len || !recs->seq_off))
+            throw InputError("read records: missing arrays");
+        {
+            const uint64_t pool = recs->n_reads ? recs->cigar_begin[recs->n_reads] : 0;
+            for (uint32_t r = first; r < first + count; ++r) {
+                const uint64_t b0 = recs->cigar_begin[r], b1 = recs->cigar_begin[r + 1];
+                if (b0 > b1 || b1 > pool || b1 - b0 > 0xffffffffull) throw InputError("read records: cigar_begin is not a CSR of the CIGAR pool");
+            }
+            if (pool && !recs->cigar) throw InputError("read records: missing CIGAR pool");
+        }
+        const uint64_t cig0 = count ? recs->cigar_begin[first] : 0, cig1 = count ? recs->cigar_begin[first + count] : 0;
         const uint32_t prim_ops = uint32_t(cig1 - cig0);
         uint32_t skipped = 0;
         // The pair test of read_alignment_scanner.rs:80-103 against the reverse-strand segments of the read segment's contig:

@@ -525,3 +525,24 @@ def test_malformed_contig_records_are_refused():
         setattr(r, field, arr.ctypes.data_as(types[field]))
         with pytest.raises(abi.PtlError):
             L.prepare_contig_records(r)
+
+
+def test_read_records_with_a_broken_cigar_csr_are_refused():
+    """ptl_pack_batch* takes caller memory: a cigar_begin that is not a CSR of the CIGAR pool (an entry below its predecessor,
+    beyond the pool, 2^64 - 1) is reported before it sizes a copy or a walk (found by tools/fuzz/fuzz_read_records.py under
+    AddressSanitizer: the vector CIGAR walk read 32 bytes through a wild pointer)."""
+    s = synth.make("tiny", seed=41, n_reads=200)
+    L = lib.load()
+    r0 = s.read_records
+    n = r0.n_reads
+    T = dict(lib.ReadRecordsC._fields_)
+    lib.PackedBatch(L, r0, 0, n, s.contig_names, windows=True)
+    for index, value in ((150, 2**64 - 1), (10, 0), (n - 1, int(r0.cigar_begin[n]) + 5)):
+        arr = np.ctypeslib.as_array(r0.cigar_begin, (n + 1,)).copy()
+        arr[index] = value
+        r = lib.ReadRecordsC.from_buffer_copy(r0)
+        r.cigar_begin = arr.ctypes.data_as(T["cigar_begin"])
+        for w in (None, True):
+            with pytest.raises(abi.PtlError, match="CSR"):
+                lib.PackedBatch(L, r, 0, n, s.contig_names, windows=w)
+        lib.PackedBatch(L, r, 0, min(index, 5), s.contig_names, windows=True)    # (a slice in front of the damage still packs)
