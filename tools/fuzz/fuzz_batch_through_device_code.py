@@ -16,6 +16,8 @@ b = pb.c
 ctx = abi.Context(emul_lib.load(), 0, 1)
 ctx.set_reference(helpers.reference_arrays(s))
 ctx.set_contig_records(s.contig_records)
+if os.environ.get("FUZZ_LONG_OPS"):  # e.g. 0: every pair down the warp-cooperative path (lift_warp.cuh)
+    ctx.set_long_pair_ops(int(os.environ["FUZZ_LONG_OPS"]))
 fields = {"read_flag": b.n_reads, "read_seq_len": b.n_reads, "read_seq_off": b.n_reads, "read_seg_begin": b.n_reads + 1, "rseg_contig": b.n_read_segments,
           "rseg_pos": b.n_read_segments, "rseg_is_fwd": b.n_read_segments, "rseg_cigar_begin": b.n_read_segments, "rseg_cigar_len": b.n_read_segments,
           "cigar": int(b.n_cigar), "rseg_win_begin": b.n_read_segments + 1, "indel_win": int(b.n_indel_win)}
